@@ -1,0 +1,5 @@
+/* Part of oracle/gsl_shim: forwards to the single-header GSL-compatible shim (TEST INFRASTRUCTURE ONLY). */
+#ifndef ORACLE_SHIM_GSL_MATRIX_H
+#define ORACLE_SHIM_GSL_MATRIX_H
+#include "gsl_shim.h"
+#endif

@@ -1,0 +1,497 @@
+/*
+ * ref_harness.cc — drives the UNMODIFIED btk2.0 reference C++ (compiled from
+ * /root/reference against oracle/gsl_shim) behind a small C-ABI so that Python
+ * tests and bench.py's CPU-baseline leg can run the reference's own hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load oracle/_ref/libbtkref.so.  The
+ * product (distant_speech_recognition_b200/) never links or calls it.
+ *
+ * What is the genuine reference here and what is restated:
+ *   - OverSampledDFTAnalysisBank / OverSampledDFTSynthesisBank, SnapShotArray,
+ *     BeamformerWeights, SubbandDS / SubbandGSC / SubbandMVDR / SubbandMVDRGSC,
+ *     pseudoinverse (LINPACK csvdc), ZelinskiPostFilter: the reference's objects,
+ *     wired exactly like unit_test/test_online_beamforming.py:51-228 and
+ *     src/filterBankTest.cc:148-203 wire them.
+ *   - SampleSource below follows feature/feature.cc:605-649 (SampleFeature::next,
+ *     pad_zeros=true); the real class needs libsndfile, which is not installed.
+ *   - GscLmsRestate follows lib/pybeamformer.py:588-762 (SubbandGSCLMSBeamformer;
+ *     Python-2 only in the reference) statement by statement, on top of the
+ *     reference's own analysis banks, SnapShotArray and blocking matrices.
+ *   - smi_covariance_ follows lib/pybeamformer.py:948-1000.
+ */
+#include <vector>
+#include <list>
+#include <complex>
+#include <cstring>
+#include <cmath>
+
+#include "stream/stream.h"
+#include "modulated/modulated.h"
+#include "beamformer/beamformer.h"
+#include "postfilter/postfilter.h"
+
+// declared in beamformer.cc (non-static helpers)
+gsl_matrix_complex* getBlockingMatrix(gsl_vector_complex* arrayManifold, int NC);
+bool pseudoinverse(gsl_matrix_complex* A, gsl_matrix_complex* invA, float dThreshold);
+
+namespace {
+
+// feature/feature.cc:605-649 — SampleFeature::next with block_len == shift_len == D, pad_zeros = true
+class SampleSource : public VectorFloatFeatureStream {
+ public:
+  SampleSource(const float* samples, unsigned n, unsigned D, const String& nm = "SampleSource")
+      : VectorFloatFeatureStream(D, nm), samples_(samples, samples + n), ttl_(n), cur_(0) {}
+  virtual const gsl_vector_float* next(int frame_no = -5) {
+    if (is_end_) throw jiterator_error("end of samples!");
+    if (frame_no == frame_no_) return vector_;
+    if (frame_no >= 0 && frame_no - 1 != frame_no_)
+      throw jindex_error("Problem in Feature %s: %d != %d\n", name().c_str(), frame_no - 1, frame_no_);
+    if (cur_ >= ttl_) { is_end_ = true; throw jiterator_error("end of samples!"); }
+    if (cur_ + size() >= ttl_) {
+      gsl_vector_float_set_zero(vector_);
+      unsigned remainingN = ttl_ - cur_;
+      for (unsigned i = 0; i < remainingN; i++) gsl_vector_float_set(vector_, i, samples_[cur_ + i]);
+    } else {
+      for (unsigned i = 0; i < size(); i++) gsl_vector_float_set(vector_, i, samples_[cur_ + i]);
+    }
+    cur_ += size();
+    increment_();
+    return vector_;
+  }
+  virtual void reset() { cur_ = 0; VectorFloatFeatureStream::reset(); }
+
+ private:
+  std::vector<float> samples_;
+  unsigned ttl_, cur_;
+};
+typedef Inherit<SampleSource, VectorFloatFeatureStreamPtr> SampleSourcePtr;
+
+// feeds pre-computed subband frames (like stream/pyStream.h's PyVectorComplexFeatureStream does from Python)
+class ArrayComplexSource : public VectorComplexFeatureStream {
+ public:
+  ArrayComplexSource(const double* frames, unsigned T, unsigned M) : VectorComplexFeatureStream(M, "ArrayComplexSource"), f_(frames), T_(T), M_(M) {}
+  virtual const gsl_vector_complex* next(int frame_no = -5) {
+    if (frame_no == frame_no_) return vector_;
+    if ((unsigned)(frame_no_ + 1) >= T_) { is_end_ = true; throw jiterator_error("end of samples!"); }
+    increment_();
+    for (unsigned k = 0; k < M_; k++)
+      gsl_vector_complex_set(vector_, k, gsl_complex_rect(f_[2 * ((size_t)frame_no_ * M_ + k)], f_[2 * ((size_t)frame_no_ * M_ + k) + 1]));
+    return vector_;
+  }
+ private:
+  const double* f_; unsigned T_, M_;
+};
+
+typedef std::complex<double> cplx;
+
+struct LmsParams {
+  double beta, gamma, init_diagonal_load, regularization_param, energy_floor, sil_thresh, max_wa_l2norm;
+  int min_frames, slowdown_after;
+};
+
+// lib/pybeamformer.py:588-762 — SubbandGSCLMSBeamformer (leaky power-normalised LMS in GSC form)
+class GscLmsRestate : public VectorComplexFeatureStream {
+ public:
+  GscLmsRestate(unsigned M, std::vector<VectorComplexFeatureStreamPtr>& chans, const LmsParams& p)
+      : VectorComplexFeatureStream(M, "GscLmsRestate"), M_(M), M2_(M / 2), C_(chans.size()), chans_(chans), p_(p),
+        snap_(new SnapShotArray(M, chans.size())) {
+    wqH_.assign((M2_ + 1) * C_, cplx(1, 0));
+    BmH_.assign((size_t)(M2_ + 1) * (C_ - 1) * C_, cplx(0, 0));
+    reset_stats();
+  }
+  ~GscLmsRestate() { delete snap_; }
+
+  // pybeamformer.py:736-743 calc_beamformer_weights: vs = calc_array_manifold_f (284-307); BmH = transpose(calc_blocking_matrix(vs)); wqH = conj(vs)
+  void calc_beamformer_weights(double samplerate, const double* delays) {
+    const double Delta_f = samplerate / (double)M_;
+    gsl_vector_complex* vs = gsl_vector_complex_alloc(C_);
+    for (unsigned m = 0; m <= M2_; m++) {
+      for (unsigned c = 0; c < C_; c++) {
+        cplx v = std::exp(cplx(0, -1) * (2.0 * M_PI * m * Delta_f * delays[c])) / (double)C_;
+        gsl_vector_complex_set(vs, c, gsl_complex_rect(v.real(), v.imag()));
+        wqH_[m * C_ + c] = std::conj(v);
+      }
+      // calc_blocking_matrix (pybeamformer.py:309-341) is the same arithmetic as calc_blocking_matrix_ (beamformer.cc:373-454)
+      gsl_matrix_complex* B = getBlockingMatrix(vs, 1);
+      for (unsigned i = 0; i < C_ - 1; i++)
+        for (unsigned c = 0; c < C_; c++) {
+          gsl_complex b = gsl_matrix_complex_get(B, c, i);
+          BmH_[((size_t)m * (C_ - 1) + i) * C_ + c] = cplx(GSL_REAL(b), GSL_IMAG(b));  // transpose, NO conjugate (:742)
+        }
+      gsl_matrix_complex_free(B);
+    }
+    gsl_vector_complex_free(vs);
+  }
+
+  void reset_stats() {  // :745-757
+    isamp_ = 0; ttl_updates_ = 0; gamma_ = p_.gamma; energy_ = p_.init_diagonal_load;
+    subband_energy_.assign(M2_ + 1, p_.init_diagonal_load);
+    waH_.assign((size_t)(M2_ + 1) * (C_ - 1), cplx(0, 0));
+  }
+
+  virtual const gsl_vector_complex* next(int frame_no = -5) {  // __iter__, :659-734
+    if (frame_no == frame_no_) return vector_;
+    // MultiChannelSource.update_snapshot_array(chan_no=0), :263-277
+    double sigmaK = 0.0;
+    for (unsigned c = 0; c < C_; c++) {
+      const gsl_vector_complex* sb = chans_[c]->next(frame_no);
+      snap_->set_samples(sb, c);
+      if (c == 0) {
+        cplx acc(0, 0);
+        for (unsigned k = 0; k < M_; k++) { gsl_complex z = gsl_vector_complex_get(sb, k); acc += std::conj(cplx(GSL_REAL(z), GSL_IMAG(z))) * cplx(GSL_REAL(z), GSL_IMAG(z)); }
+        sigmaK = std::abs(acc);
+      }
+    }
+    snap_->update();
+    const double energy = sigmaK / (double)M_;
+    for (unsigned k = 0; k < M_; k++) gsl_vector_complex_set(vector_, k, gsl_complex_rect(0, 0));
+    if (isamp_ > 0 && (isamp_ % p_.slowdown_after) == 0) gamma_ /= 2.0;
+    const bool adapt = energy > (energy_ / p_.sil_thresh);
+    if (adapt) ttl_updates_++;
+    std::vector<cplx> XK(C_), ZK(C_ - 1), watHK(C_ - 1);
+    for (unsigned m = 0; m <= M2_; m++) {
+      const gsl_vector_complex* x = snap_->snapshot(m);
+      for (unsigned c = 0; c < C_; c++) { gsl_complex z = gsl_vector_complex_get(x, c); XK[c] = cplx(GSL_REAL(z), GSL_IMAG(z)); }
+      cplx* wa = &waH_[(size_t)m * (C_ - 1)];
+      for (unsigned i = 0; i < C_ - 1; i++) {  // ZK = BmH[m] . XK
+        cplx s(0, 0); for (unsigned c = 0; c < C_; c++) s += BmH_[((size_t)m * (C_ - 1) + i) * C_ + c] * XK[c]; ZK[i] = s;
+      }
+      cplx YcK(0, 0); for (unsigned c = 0; c < C_; c++) YcK += wqH_[m * C_ + c] * XK[c];
+      double xx = 0; { cplx s(0, 0); for (unsigned c = 0; c < C_; c++) s += std::conj(XK[c]) * XK[c]; xx = std::abs(s); }
+      double subband_energy = (isamp_ > 0) ? subband_energy_[m] * p_.beta + (1.0 - p_.beta) * xx : xx;
+      if (subband_energy < p_.energy_floor) subband_energy = p_.energy_floor;
+      if (adapt) {
+        cplx waZ(0, 0); for (unsigned i = 0; i < C_ - 1; i++) waZ += wa[i] * ZK[i];
+        cplx epa = YcK - waZ;
+        double alphaK = gamma_ / subband_energy;
+        for (unsigned i = 0; i < C_ - 1; i++) watHK[i] = wa[i] + epa * std::conj(ZK[i]) * alphaK;
+        if (p_.regularization_param > 0)
+          for (unsigned i = 0; i < C_ - 1; i++) watHK[i] = watHK[i] - alphaK * p_.regularization_param * wa[i];
+        double norm_watK; { cplx s(0, 0); for (unsigned i = 0; i < C_ - 1; i++) s += watHK[i] * std::conj(watHK[i]); norm_watK = std::abs(s); }
+        if (norm_watK > p_.max_wa_l2norm) {
+          double cK = std::sqrt(p_.max_wa_l2norm / norm_watK);
+          for (unsigned i = 0; i < C_ - 1; i++) wa[i] = cK * watHK[i];
+        } else {
+          for (unsigned i = 0; i < C_ - 1; i++) wa[i] = watHK[i];
+        }
+        subband_energy_[m] = subband_energy;
+      }
+      cplx out;
+      if (isamp_ >= p_.min_frames) { cplx waZ(0, 0); for (unsigned i = 0; i < C_ - 1; i++) waZ += wa[i] * ZK[i]; out = YcK - waZ; }
+      else out = YcK;
+      gsl_vector_complex_set(vector_, m, gsl_complex_rect(out.real(), out.imag()));
+      if (m > 0 && m < M2_) gsl_vector_complex_set(vector_, M_ - m, gsl_complex_rect(out.real(), -out.imag()));
+    }
+    energy_ = energy_ * p_.beta + (1.0 - p_.beta) * energy;
+    isamp_++;
+    increment_();
+    return vector_;
+  }
+  virtual void reset() {
+    for (unsigned c = 0; c < C_; c++) chans_[c]->reset();
+    reset_stats(); VectorComplexFeatureStream::reset();
+  }
+  SnapShotArray* snapshot_array() { return snap_; }
+  const std::vector<cplx>& waH() const { return waH_; }
+  int ttl_updates() const { return ttl_updates_; }
+
+ private:
+  unsigned M_, M2_, C_;
+  std::vector<VectorComplexFeatureStreamPtr> chans_;
+  LmsParams p_;
+  SnapShotArray* snap_;
+  std::vector<cplx> wqH_, BmH_, waH_;
+  std::vector<double> subband_energy_;
+  int isamp_, ttl_updates_;
+  double gamma_, energy_;
+};
+typedef Inherit<GscLmsRestate, VectorComplexFeatureStreamPtr> GscLmsRestatePtr;
+
+gsl_vector* make_vec(const double* p, unsigned n) { gsl_vector* v = gsl_vector_alloc(n); for (unsigned i = 0; i < n; i++) gsl_vector_set(v, i, p[i]); return v; }
+
+}  // namespace
+
+extern "C" {
+
+struct ref_config {
+  int C, M, m, r, delay_compensation_type;
+  double samplerate;
+  int bf_kind;            /* 0 DS, 1 GSC (static wa), 2 MVDR super-directive (diffuse), 3 SMI-MVDR (VAD label), 4 GSC-NLMS (restated) */
+  int pf_kind;            /* 0 none, 1 Zelinski */
+  double pf_alpha; int pf_type; int pf_min_frames;
+  double mvdr_mu, sspeed; /* diagonal loading; speed of sound (mm/s) */
+  double smi_target_start, smi_target_end, smi_energy_threshold; /* one VAD segment [start,end] sec (end<0: to the end) */
+  double lms_beta, lms_gamma, lms_init_diagonal_load, lms_regularization_param, lms_energy_floor, lms_sil_thresh, lms_max_wa_l2norm;
+  int lms_min_frames, lms_slowdown_after;
+  int do_synthesis;
+};
+
+/* analysis only: samples[n] -> out[T][M] complex128 interleaved; returns T (or -1 if T > T_cap) */
+int ref_analysis(const float* samples, int n, const double* h, int M, int m, int r, int dct, double* out, int T_cap) {
+  int D = M >> r;
+  gsl_vector* hv = make_vec(h, M * m);
+  int T = 0;
+  {
+    SampleSourcePtr src = new SampleSource(samples, n, D);
+    OverSampledDFTAnalysisBankPtr afb = new OverSampledDFTAnalysisBank((VectorFloatFeatureStreamPtr&)src, hv, M, m, r, dct);
+    for (;;) {
+      const gsl_vector_complex* X;
+      try { X = afb->next(); } catch (jiterator_error& e) { break; }
+      if (T >= T_cap) { T = -1; break; }
+      memcpy(out + (size_t)2 * T * M, X->data, sizeof(double) * 2 * M);
+      T++;
+    }
+  }
+  gsl_vector_free(hv);
+  return T;
+}
+
+/* synthesis only: Y[T][M] complex128 -> out blocks of D floats; returns number of blocks */
+int ref_synthesis(const double* Y, int T, const double* g, int M, int m, int r, int dct, float* out, int blocks_cap) {
+  int D = M >> r;
+  gsl_vector* gv = make_vec(g, M * m);
+  int nb = 0;
+  {
+    VectorComplexFeatureStreamPtr src = new ArrayComplexSource(Y, T, M);
+    OverSampledDFTSynthesisBankPtr sfb = new OverSampledDFTSynthesisBank(src, gv, M, m, r, dct);
+    for (;;) {
+      const gsl_vector_float* b;
+      try { b = sfb->next(); } catch (jiterator_error& e) { break; }
+      if (nb >= blocks_cap) { nb = -1; break; }
+      memcpy(out + (size_t)nb * D, b->data, sizeof(float) * D);
+      nb++;
+    }
+  }
+  gsl_vector_free(gv);
+  return nb;
+}
+
+/* quiescent weights + blocking matrices: BeamformerWeights::calcMainlobe(isGSC=true) (beamformer.cc:502-565)
+   wq_out[M][C] complex128, B_out[M][C][C-1] complex128 (either may be NULL) */
+void ref_gsc_weights(int M, int C, double samplerate, const double* delays, double* wq_out, double* B_out) {
+  BeamformerWeights w(M, C, false, 1);
+  gsl_vector* d = make_vec(delays, C);
+  w.calcMainlobe((float)samplerate, d, B_out != NULL && C > 1);
+  for (int f = 0; f < M; f++) {
+    if (wq_out) memcpy(wq_out + (size_t)2 * f * C, w.wq_f(f)->data, sizeof(double) * 2 * C);
+    if (B_out && C > 1) memcpy(B_out + (size_t)2 * f * C * (C - 1), (w.B())[f]->data, sizeof(double) * 2 * C * (C - 1));
+  }
+  gsl_vector_free(d);
+}
+
+/* LCMV quiescent weights with NC constraints: calcMainlobeN / calcMainlobe2 (beamformer.cc:573-721). delaysJ[NC-1][C] */
+void ref_lcmv_weights(int M, int C, int NC, double samplerate, const double* delaysT, const double* delaysJ, double* wq_out, double* B_out) {
+  BeamformerWeights w(M, C, false, NC);
+  gsl_vector* d = make_vec(delaysT, C);
+  gsl_matrix* dj = gsl_matrix_alloc(NC - 1, C);
+  for (int n = 0; n < NC - 1; n++) for (int c = 0; c < C; c++) gsl_matrix_set(dj, n, c, delaysJ[n * C + c]);
+  w.calcMainlobeN((float)samplerate, d, dj, NC, B_out != NULL);
+  for (int f = 0; f <= M / 2; f++) {
+    if (wq_out) memcpy(wq_out + (size_t)2 * f * C, w.wq_f(f)->data, sizeof(double) * 2 * C);
+    if (B_out) memcpy(B_out + (size_t)2 * f * C * (C - NC), (w.B())[f]->data, sizeof(double) * 2 * C * (C - NC));
+  }
+  gsl_vector_free(d); gsl_matrix_free(dj);
+}
+
+/* pseudoinverse (beamformer.cc:232-289; float LINPACK csvdc). A[n][n] -> invA[n][n]; returns the bool as int */
+int ref_pseudoinverse(const double* A, int n, double thr, double* invA) {
+  gsl_matrix_complex* a = gsl_matrix_complex_alloc(n, n); gsl_matrix_complex* ia = gsl_matrix_complex_alloc(n, n);
+  memcpy(a->data, A, sizeof(double) * 2 * n * n);
+  bool ok = pseudoinverse(a, ia, (float)thr);
+  memcpy(invA, ia->data, sizeof(double) * 2 * n * n);
+  gsl_matrix_complex_free(a); gsl_matrix_complex_free(ia);
+  return ok ? 1 : 0;
+}
+
+/* MVDR weights from given per-bin covariance R[K][C][C] (or diffuse model when R==NULL, using mpos[C][3]):
+   SubbandMVDR::{calc_array_manifold_vectors,set_noise_spatial_spectral_matrix|set_diffuse_noise_model,set_all_diagonal_loading,calc_mvdr_weights}
+   (beamformer.cc:2350-2523).  w_out[K][C] complex128 */
+void ref_mvdr_weights(int M, int C, double samplerate, const double* delays, const double* R, const double* mpos, double sspeed, double mu, double* w_out) {
+  SubbandMVDRPtr bf = new SubbandMVDR(M, false);
+  // chanN() is the channel-list size: register C dummy channels
+  std::vector<VectorComplexFeatureStreamPtr> dummies;
+  std::vector<double> zero((size_t)2 * M, 0.0);
+  for (int c = 0; c < C; c++) { VectorComplexFeatureStreamPtr s = new ArrayComplexSource(zero.data(), 1, M); dummies.push_back(s); bf->set_channel(dummies.back()); }
+  gsl_vector* d = make_vec(delays, C);
+  bf->calc_array_manifold_vectors((float)samplerate, d);
+  int K = M / 2 + 1;
+  if (R) {
+    gsl_matrix_complex* Rm = gsl_matrix_complex_alloc(C, C);
+    for (int f = 0; f < K; f++) { memcpy(Rm->data, R + (size_t)2 * f * C * C, sizeof(double) * 2 * C * C); bf->set_noise_spatial_spectral_matrix(f, Rm); }
+    gsl_matrix_complex_free(Rm);
+  } else {
+    gsl_matrix* mp = gsl_matrix_alloc(C, 3);
+    for (int c = 0; c < C; c++) for (int j = 0; j < 3; j++) gsl_matrix_set(mp, c, j, mpos[c * 3 + j]);
+    bf->set_diffuse_noise_model(mp, (float)samplerate, (float)sspeed);
+    gsl_matrix_free(mp);
+  }
+  bf->set_all_diagonal_loading((float)mu);
+  bf->calc_mvdr_weights((float)samplerate, 1.0E-8, true);
+  for (int f = 0; f < K; f++) memcpy(w_out + (size_t)2 * f * C, bf->mvdr_weights(f)->data, sizeof(double) * 2 * C);
+  gsl_vector_free(d);
+}
+
+/*
+ * Full pipe for one utterance: samples[C][n] float32 -> Y[T][M] complex128 (beamformed, post-filtered subband
+ * spectra) and, if cfg->do_synthesis, out_time[nblocks*D] float32.  Optional outputs (may be NULL):
+ *   wa_in    [K][2(C-1)] packed active weights for bf_kind 1 (set_active_weights_f)
+ *   mpos     [C][3] microphone positions (bf_kind 2)
+ *   cov_out  [K][C][C] complex128 noise covariance after finalize_stats (bf_kind 3)
+ *   w_out    [K][C] complex128: wq (kinds 0,1), wmvdr (2,3); for kind 4: final waH [K][C-1]
+ *   stats    [3]: sum y^2 over time output, frames, n_updates (kind 4)
+ * Returns T (frames of subband output), *nblocks_out = synthesis blocks.
+ */
+int ref_beamform(const ref_config* cfg, const float* samples, int n, const double* h, const double* g, const double* delays,
+                 const double* wa_in, const double* mpos, double* Y_out, int T_cap, float* out_time, int blocks_cap,
+                 int* nblocks_out, double* cov_out, double* w_out, double* stats) {
+  const int C = cfg->C, M = cfg->M, m = cfg->m, r = cfg->r, dct = cfg->delay_compensation_type;
+  const int D = M >> r, K = M / 2 + 1;
+  gsl_vector* hv = make_vec(h, M * m);
+  gsl_vector* gv = g ? make_vec(g, M * m) : NULL;
+  gsl_vector* dv = make_vec(delays, C);
+  int T = 0, nb = 0;
+  double sumsq = 0.0; int n_updates = 0;
+
+  std::vector<double> Rsmi;  // [K][C][C] complex
+  if (cfg->bf_kind == 3) {
+    // PASS 1: pybeamformer.py:948-1000 accu_stats_from_label + finalize_stats
+    std::vector<SampleSourcePtr> srcs; std::vector<OverSampledDFTAnalysisBankPtr> afbs;
+    for (int c = 0; c < C; c++) {
+      srcs.push_back(new SampleSource(samples + (size_t)c * n, n, D));
+      afbs.push_back(new OverSampledDFTAnalysisBank((VectorFloatFeatureStreamPtr&)srcs.back(), hv, M, m, r, dct));
+    }
+    SnapShotArray snap(M, C);
+    Rsmi.assign((size_t)2 * K * C * C, 0.0);
+    double elapsed_time = 0.0, time_delta = D / cfg->samplerate; int noise_frame_num = 0; int labx = 0;
+    for (;;) {
+      bool is_target_source = false;
+      if (labx < 1) {
+        if (elapsed_time >= cfg->smi_target_start && (elapsed_time <= cfg->smi_target_end || cfg->smi_target_end < 0)) is_target_source = true;
+        else if (elapsed_time > cfg->smi_target_end) labx += 1;
+      }
+      double sigmaK = 0; bool end = false;
+      for (int c = 0; c < C; c++) {
+        const gsl_vector_complex* sb;
+        try { sb = afbs[c]->next(); } catch (jiterator_error& e) { end = true; break; }
+        snap.set_samples(sb, c);
+        if (c == 0) { double a = 0; for (int k = 0; k < M; k++) a += gsl_complex_abs2(gsl_vector_complex_get(sb, k)); sigmaK = fabs(a); }
+      }
+      if (end) break;
+      snap.update();
+      double energy = sigmaK / M;
+      if (!is_target_source && energy > cfg->smi_energy_threshold) {
+        noise_frame_num++;
+        for (int f = 0; f < K; f++) {
+          const gsl_vector_complex* x = snap.snapshot(f);
+          for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) {
+            gsl_complex v = gsl_complex_mul(gsl_vector_complex_get(x, i), gsl_complex_conjugate(gsl_vector_complex_get(x, j)));
+            Rsmi[2 * (((size_t)f * C + i) * C + j)] += GSL_REAL(v); Rsmi[2 * (((size_t)f * C + i) * C + j) + 1] += GSL_IMAG(v);
+          }
+        }
+      }
+      elapsed_time += time_delta;
+    }
+    if (noise_frame_num > 0) for (size_t i = 0; i < Rsmi.size(); i++) Rsmi[i] /= noise_frame_num;
+    if (cov_out) memcpy(cov_out, Rsmi.data(), sizeof(double) * Rsmi.size());
+    if (stats) stats[2] = noise_frame_num;
+  }
+
+  {
+    std::vector<SampleSourcePtr> srcs; std::vector<OverSampledDFTAnalysisBankPtr> afbs;
+    std::vector<VectorComplexFeatureStreamPtr> chans;
+    for (int c = 0; c < C; c++) {
+      srcs.push_back(new SampleSource(samples + (size_t)c * n, n, D));
+      afbs.push_back(new OverSampledDFTAnalysisBank((VectorFloatFeatureStreamPtr&)srcs.back(), hv, M, m, r, dct));
+      chans.push_back((VectorComplexFeatureStreamPtr&)afbs.back());
+    }
+    VectorComplexFeatureStreamPtr bfstream;
+    SubbandDSPtr ds; SubbandGSCPtr gsc; SubbandMVDRGSCPtr mvdr; GscLmsRestatePtr lms;
+    SubbandDSPtr bf_for_pf;
+    switch (cfg->bf_kind) {
+      case 0:
+        ds = new SubbandDS(M, false);
+        for (int c = 0; c < C; c++) ds->set_channel(chans[c]);
+        ds->calc_array_manifold_vectors((float)cfg->samplerate, dv);
+        bfstream = (VectorComplexFeatureStreamPtr&)ds; bf_for_pf = ds;
+        if (w_out) for (int f = 0; f < K; f++) memcpy(w_out + (size_t)2 * f * C, ds->get_weights(f)->data, sizeof(double) * 2 * C);
+        break;
+      case 1:
+        gsc = new SubbandGSC(M, false);
+        for (int c = 0; c < C; c++) gsc->set_channel(chans[c]);
+        gsc->calc_gsc_weights((float)cfg->samplerate, dv);
+        if (wa_in) {  // SubbandBeamformer.set_active_weights, pybeamformer.py:464-475
+          gsl_vector* pw = gsl_vector_alloc(2 * (C - 1));
+          for (int f = 0; f < K; f++) { for (int i = 0; i < 2 * (C - 1); i++) gsl_vector_set(pw, i, wa_in[(size_t)f * 2 * (C - 1) + i]); gsc->set_active_weights_f(f, pw); }
+          gsl_vector_free(pw);
+        }
+        bfstream = (VectorComplexFeatureStreamPtr&)gsc; bf_for_pf = (SubbandDSPtr&)gsc;
+        if (w_out) for (int f = 0; f < K; f++) memcpy(w_out + (size_t)2 * f * C, gsc->get_weights(f)->data, sizeof(double) * 2 * C);
+        break;
+      case 2: case 3:
+        mvdr = new SubbandMVDRGSC(M, false);
+        for (int c = 0; c < C; c++) mvdr->set_channel(chans[c]);
+        mvdr->calc_array_manifold_vectors((float)cfg->samplerate, dv);
+        if (cfg->bf_kind == 2) {  // calc_sd_beamformer_weights, pybeamformer.py:557-585
+          gsl_matrix* mp = gsl_matrix_alloc(C, 3);
+          for (int c = 0; c < C; c++) for (int j = 0; j < 3; j++) gsl_matrix_set(mp, c, j, mpos[c * 3 + j]);
+          mvdr->set_diffuse_noise_model(mp, (float)cfg->samplerate, (float)cfg->sspeed);
+          gsl_matrix_free(mp);
+        } else {  // calc_beamformer_weights, pybeamformer.py:1002-1023
+          gsl_matrix_complex* Rm = gsl_matrix_complex_alloc(C, C);
+          for (int f = 0; f < K; f++) { memcpy(Rm->data, Rsmi.data() + (size_t)2 * f * C * C, sizeof(double) * 2 * C * C); mvdr->set_noise_spatial_spectral_matrix(f, Rm); }
+          gsl_matrix_complex_free(Rm);
+        }
+        mvdr->set_all_diagonal_loading((float)cfg->mvdr_mu);
+        mvdr->calc_mvdr_weights((float)cfg->samplerate, 1.0E-8, true);
+        bfstream = (VectorComplexFeatureStreamPtr&)mvdr; bf_for_pf = (SubbandDSPtr&)mvdr;
+        if (w_out) for (int f = 0; f < K; f++) memcpy(w_out + (size_t)2 * f * C, mvdr->mvdr_weights(f)->data, sizeof(double) * 2 * C);
+        break;
+      default: {
+        LmsParams p = {cfg->lms_beta, cfg->lms_gamma, cfg->lms_init_diagonal_load, cfg->lms_regularization_param, cfg->lms_energy_floor,
+                       cfg->lms_sil_thresh, cfg->lms_max_wa_l2norm, cfg->lms_min_frames, cfg->lms_slowdown_after};
+        lms = new GscLmsRestate(M, chans, p);
+        lms->calc_beamformer_weights(cfg->samplerate, delays);
+        bfstream = (VectorComplexFeatureStreamPtr&)lms;
+      }
+    }
+    VectorComplexFeatureStreamPtr tail = bfstream;
+    ZelinskiPostFilterPtr pf;
+    if (cfg->pf_kind == 1) {  // test_online_beamforming.py:132-136,204
+      if (cfg->bf_kind == 4) throw j_error("Zelinski after the restated NLMS is not wired in the harness\n");
+      pf = new ZelinskiPostFilter(bfstream, M, cfg->pf_alpha, cfg->pf_type, cfg->pf_min_frames);
+      pf->set_beamformer(bf_for_pf);
+      tail = (VectorComplexFeatureStreamPtr&)pf;
+    }
+    if (cfg->do_synthesis) {
+      OverSampledDFTSynthesisBankPtr sfb = new OverSampledDFTSynthesisBank(tail, gv, M, m, r, dct);
+      // tap the subband stream as it passes: the synthesis bank pulls `tail`; re-reading current() is idempotent
+      for (;;) {
+        const gsl_vector_float* b;
+        try { b = sfb->next(); } catch (jiterator_error& e) { break; }
+        if (nb < blocks_cap) memcpy(out_time + (size_t)nb * D, b->data, sizeof(float) * D);
+        for (int i = 0; i < D; i++) sumsq += (double)b->data[i] * b->data[i];
+        nb++;
+      }
+      // second pass for the subband tap (streams are deterministic): rebuild is simpler than tapping inside the pull
+    }
+    // subband output pass (fresh pull when synthesis consumed the stream: reset everything)
+    if (cfg->do_synthesis) tail->reset();
+    for (;;) {
+      const gsl_vector_complex* Y;
+      try { Y = tail->next(); } catch (jiterator_error& e) { break; }
+      if (T < T_cap && Y_out) memcpy(Y_out + (size_t)2 * T * M, Y->data, sizeof(double) * 2 * M);
+      T++;
+    }
+    if (cfg->bf_kind == 4) {
+      n_updates = lms->ttl_updates();
+      if (w_out) memcpy(w_out, lms->waH().data(), sizeof(double) * 2 * K * (C - 1));
+    }
+  }
+  gsl_vector_free(hv); if (gv) gsl_vector_free(gv); gsl_vector_free(dv);
+  if (nblocks_out) *nblocks_out = nb;
+  if (stats) { stats[0] = sumsq; stats[1] = T; if (cfg->bf_kind == 4) stats[2] = n_updates; }
+  return T;
+}
+
+}  // extern "C"
