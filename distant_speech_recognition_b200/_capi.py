@@ -1,0 +1,245 @@
+"""ctypes binding of include/btkb.h (libbtkb.so: hand-written sm_100a CUDA behind a C-ABI).
+
+There is NO CPU fallback: importing this module fails if the shared library has not been built
+(`python -c "import __graft_entry__ as g; g.build()"` or `make -C distant_speech_recognition_b200/csrc`), and
+`Pipeline(...)` raises if no CUDA device is usable.
+"""
+import ctypes as ct
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbtkb.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "btkb.h")
+
+BF_DS, BF_GSC, BF_MVDR, BF_GSC_LMS = 0, 1, 2, 3
+PF_NONE, PF_ZELINSKI = 0, 1
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
+
+
+class BtkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("btkb error %d: %s" % (code, msg))
+        self.code = code
+
+
+class LmsParams(ct.Structure):
+    _fields_ = [("beta", ct.c_float), ("gamma", ct.c_float), ("init_diagonal_load", ct.c_float),
+                ("regularization_param", ct.c_float), ("energy_floor", ct.c_float), ("sil_thresh", ct.c_float),
+                ("max_wa_l2norm", ct.c_float), ("min_frames", ct.c_int), ("slowdown_after", ct.c_int)]
+
+
+class Config(ct.Structure):
+    _fields_ = [("device", ct.c_int), ("channels", ct.c_int), ("fft_len", ct.c_int), ("m", ct.c_int), ("r", ct.c_int),
+                ("delay_compensation_type", ct.c_int), ("samplerate", ct.c_float), ("beamformer", ct.c_int),
+                ("postfilter", ct.c_int), ("pf_alpha", ct.c_float), ("pf_type", ct.c_int), ("pf_min_frames", ct.c_int),
+                ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libbtkb.so is not built (%s). Build it with __graft_entry__.build(); there is no CPU path." % LIB_PATH)
+    lib = ct.CDLL(LIB_PATH)
+    lib.btkb_last_error.restype = ct.c_char_p
+    lib.btkb_destroy.restype = None
+    lib.btkb_default_config.restype = None
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc):
+    if rc != 0:
+        raise BtkbError(rc, lib.btkb_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    return int(lib.btkb_device_count())
+
+
+def _fp(a):
+    return a.ctypes.data_as(ct.POINTER(ct.c_float))
+
+
+def _dp(a):
+    return a.ctypes.data_as(ct.POINTER(ct.c_double))
+
+
+class Pipeline:
+    """One batch pipeline: analysis -> per-bin beamformer (+post-filter) -> synthesis on one GPU."""
+
+    def __init__(self, channels, fft_len=512, m=4, r=1, delay_compensation_type=2, samplerate=16000.0, beamformer=BF_DS,
+                 postfilter=PF_NONE, pf_alpha=0.6, pf_type=2, pf_min_frames=0, lms=None, max_utterances=1,
+                 max_samples=160000, device=0):
+        cfg = Config()
+        lib.btkb_default_config(ct.byref(cfg))
+        cfg.device = device; cfg.channels = channels; cfg.fft_len = fft_len; cfg.m = m; cfg.r = r
+        cfg.delay_compensation_type = delay_compensation_type; cfg.samplerate = samplerate
+        cfg.beamformer = beamformer; cfg.postfilter = postfilter
+        cfg.pf_alpha = pf_alpha; cfg.pf_type = pf_type; cfg.pf_min_frames = pf_min_frames
+        if lms:
+            for k, v in lms.items():
+                setattr(cfg.lms, k, v)
+        cfg.max_utterances = max_utterances; cfg.max_samples = max_samples
+        self.cfg = cfg
+        self.C, self.M, self.K, self.D = channels, fft_len, fft_len // 2 + 1, fft_len >> r
+        self._h = ct.c_void_p()
+        _check(lib.btkb_create(ct.byref(cfg), ct.byref(self._h)))
+        self.U = 0
+
+    def close(self):
+        if self._h:
+            lib.btkb_destroy(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup
+    def set_prototypes(self, h, g=None):
+        h = np.ascontiguousarray(h, np.float64)
+        gp = None
+        if g is not None:
+            g = np.ascontiguousarray(g, np.float64)
+            gp = _dp(g)
+        _check(lib.btkb_set_prototypes(self._h, _dp(h), gp, ct.c_int(len(h))))
+
+    def set_delays(self, delays):
+        d = np.ascontiguousarray(np.atleast_2d(delays), np.float64)
+        self.U = d.shape[0]
+        _check(lib.btkb_set_delays(self._h, ct.c_int(d.shape[0]), _dp(d)))
+
+    def set_weights(self, w):
+        w = np.ascontiguousarray(w, np.complex64)
+        self.U = w.shape[0]
+        _check(lib.btkb_set_weights(self._h, ct.c_int(w.shape[0]), _fp(w)))
+
+    def set_active_weights(self, wa):
+        wa = np.ascontiguousarray(wa, np.complex64)
+        _check(lib.btkb_set_active_weights(self._h, ct.c_int(wa.shape[0]), _fp(wa)))
+
+    def set_noise_covariance(self, R):
+        R = np.ascontiguousarray(R, np.complex64)
+        self.U = R.shape[0]
+        _check(lib.btkb_set_noise_covariance(self._h, ct.c_int(R.shape[0]), _fp(R)))
+
+    def set_diffuse_noise_model(self, U, mpos, sspeed=343740.0):
+        mp = np.ascontiguousarray(mpos, np.float64)
+        _check(lib.btkb_set_diffuse_noise_model(self._h, ct.c_int(U), _dp(mp), ct.c_float(sspeed)))
+
+    def calc_mvdr_weights(self, mu):
+        _check(lib.btkb_calc_mvdr_weights(self._h, ct.c_float(mu)))
+
+    # ---- data path
+    def submit(self, samples, lengths=None):
+        """samples float32 [U][C][n] (host).  Keeps a reference until the next submit (the H2D copy is asynchronous)."""
+        s = np.ascontiguousarray(samples, np.float32)
+        assert s.ndim == 3 and s.shape[1] == self.C
+        self._keep = s
+        self.U, self.n = s.shape[0], s.shape[2]
+        lp = None
+        if lengths is not None:
+            self._len = np.ascontiguousarray(lengths, np.int32)
+            lp = self._len.ctypes.data_as(ct.POINTER(ct.c_int))
+        _check(lib.btkb_submit(self._h, _fp(s), ct.c_int(self.U), ct.c_int(self.n), lp))
+
+    def submit_pointer(self, host_ptr, U, n, lengths=None):
+        """Raw host pointer variant (e.g. pinned torch tensor .data_ptr())."""
+        self.U, self.n = U, n
+        lp = None
+        if lengths is not None:
+            self._len = np.ascontiguousarray(lengths, np.int32)
+            lp = self._len.ctypes.data_as(ct.POINTER(ct.c_int))
+        _check(lib.btkb_submit(self._h, ct.cast(ct.c_void_p(host_ptr), ct.POINTER(ct.c_float)), ct.c_int(U), ct.c_int(n), lp))
+
+    def submit_device(self, dev_ptr, U, n, lengths=None):
+        self.U, self.n = U, n
+        lp = None
+        if lengths is not None:
+            self._len = np.ascontiguousarray(lengths, np.int32)
+            lp = self._len.ctypes.data_as(ct.POINTER(ct.c_int))
+        _check(lib.btkb_submit_device(self._h, ct.cast(ct.c_void_p(dev_ptr), ct.POINTER(ct.c_float)), ct.c_int(U), ct.c_int(n), lp))
+
+    def run(self, synthesis=True):
+        _check(lib.btkb_run(self._h, ct.c_int(1 if synthesis else 0)))
+
+    def run_analysis(self):
+        _check(lib.btkb_run_analysis(self._h))
+
+    def run_beamformer(self, synthesis=True):
+        _check(lib.btkb_run_beamformer(self._h, ct.c_int(1 if synthesis else 0)))
+
+    def accumulate_covariance(self, labels=None, energy_threshold=10.0):
+        lp = None
+        if labels is not None:
+            self._labels = np.ascontiguousarray(labels, np.float64)
+            lp = _dp(self._labels)
+        _check(lib.btkb_accumulate_covariance(self._h, lp, ct.c_float(energy_threshold)))
+
+    def synchronize(self):
+        _check(lib.btkb_synchronize(self._h))
+
+    # ---- results
+    @property
+    def num_frames(self):
+        return int(lib.btkb_num_frames(self._h))
+
+    def num_frames_of(self, u):
+        return int(lib.btkb_num_frames_of(self._h, ct.c_int(u)))
+
+    @property
+    def num_blocks(self):
+        return int(lib.btkb_num_blocks(self._h))
+
+    def fetch_subband(self):
+        out = np.empty((self.U, self.num_frames, self.K), np.complex64)
+        _check(lib.btkb_fetch_subband(self._h, _fp(out)))
+        return out
+
+    def fetch_time(self):
+        out = np.empty((self.U, self.num_blocks * self.D), np.float32)
+        _check(lib.btkb_fetch_time(self._h, _fp(out)))
+        return out
+
+    def fetch_time_into(self, host_ptr):
+        _check(lib.btkb_fetch_time(self._h, ct.cast(ct.c_void_p(host_ptr), ct.POINTER(ct.c_float))))
+
+    def fetch_snapshots(self):
+        out = np.empty((self.U, self.num_frames, self.C, self.K), np.complex64)
+        _check(lib.btkb_fetch_snapshots(self._h, _fp(out)))
+        return out
+
+    def fetch_stats(self):
+        out = np.zeros((self.U, 3), np.float64)
+        _check(lib.btkb_fetch_stats(self._h, _dp(out)))
+        return out
+
+    def get_weights(self):
+        out = np.empty((self.U, self.K, self.C), np.complex64)
+        _check(lib.btkb_get_weights(self._h, _fp(out)))
+        return out
+
+    def get_active_weights(self):
+        out = np.empty((self.U, self.K, self.C - 1), np.complex64)
+        _check(lib.btkb_get_active_weights(self._h, _fp(out)))
+        return out
+
+    def get_covariance(self):
+        out = np.empty((self.U, self.K, self.C, self.C), np.complex64)
+        _check(lib.btkb_get_covariance(self._h, _fp(out)))
+        return out
+
+    def get_postfilter_weights(self):
+        out = np.empty((self.U, self.num_frames, self.K), np.float32)
+        _check(lib.btkb_get_postfilter_weights(self._h, _fp(out)))
+        return out
+
+    def last_timing(self):
+        """dict(total_ms, analysis_ms, perbin_ms, synthesis_ms, launches) of the last run (CUDA events on the pipeline stream)."""
+        out = (ct.c_float * 5)()
+        _check(lib.btkb_last_timing(self._h, out))
+        return dict(total_ms=out[0], analysis_ms=out[1], perbin_ms=out[2], synthesis_ms=out[3], launches=int(out[4]))

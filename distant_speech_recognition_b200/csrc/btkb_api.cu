@@ -1,0 +1,591 @@
+// btkb_api.cu — the C-ABI (include/btkb.h) over the sm_100a kernels: pipeline object, device buffers, stream ordering.
+// No CPU compute path exists here: every data-path entry point launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include <algorithm>
+
+#include "../../include/btkb.h"
+#include "btkb_internal.h"
+
+using namespace btkb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return fail(BTKB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+
+struct btkb_pipeline {
+  btkb_config cfg;
+  int C, M, K, D, R, m, laN, pdA, pdS;
+  int Ucap, ncap, n_stride, Tcap, Gpcap;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // device buffers
+  float* d_x = nullptr; const float* x_cur = nullptr;
+  int* d_len = nullptr;
+  float *d_h = nullptr, *d_g = nullptr;
+  float2 *d_X = nullptr, *d_Y = nullptr, *d_W = nullptr, *d_TA = nullptr, *d_WL = nullptr, *d_WA = nullptr, *d_UA = nullptr, *d_R = nullptr;
+  float *d_E = nullptr, *d_time = nullptr, *d_upd = nullptr, *d_PFW = nullptr;
+  double *d_delays = nullptr, *d_mpos = nullptr, *d_labels = nullptr, *d_stats = nullptr;
+  unsigned char* d_mask = nullptr; int* d_count = nullptr;
+  void* d_scratch = nullptr; size_t scratch_bytes = 0;
+  // batch state
+  int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0;
+  std::vector<int> lengths;
+  bool have_h = false, have_g = false, have_ta = false, have_w = false, have_wl = false, have_R = false, R_is_sum = false;
+  bool have_X = false, have_Y = false, have_time = false, have_ua = false;
+  float timing[5] = {0, 0, 0, 0, 0};
+  int launches = 0;
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+extern "C" {
+
+const char* btkb_last_error(void) { return g_err.c_str(); }
+
+int btkb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void btkb_default_config(btkb_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->device = 0; c->channels = 8; c->fft_len = 512; c->m = 4; c->r = 1; c->delay_compensation_type = 2;
+  c->samplerate = 16000.f; c->beamformer = BTKB_BF_DS; c->postfilter = BTKB_PF_NONE;
+  c->pf_alpha = 0.6f; c->pf_type = 2; c->pf_min_frames = 0;
+  c->lms.beta = 0.97f; c->lms.gamma = 0.01f; c->lms.init_diagonal_load = 1.0e6f; c->lms.regularization_param = 1.0e-4f;
+  c->lms.energy_floor = 90.f; c->lms.sil_thresh = 1.0e8f; c->lms.max_wa_l2norm = 100.f; c->lms.min_frames = 128; c->lms.slowdown_after = 4096;
+  c->max_utterances = 1; c->max_samples = 160000; c->keep_snapshots = 1;
+}
+
+static void fb_delays(int m, int r, int dct, bool synthesis, int* pd, int* la) {  // modulated.cc:246-264
+  const int R = 1 << r;
+  *la = 0;
+  if (dct == 1) { *pd = m * R - 1; }
+  else if (dct == 2) { if (synthesis) *pd = m * R / 2; else { *pd = m * R - 1; *la = m * R / 2 - 1; } }
+  else { *pd = 2 * m - 1; }
+}
+
+void btkb_destroy(btkb_pipeline* p) {
+  if (!p) return;
+  cudaSetDevice(p->cfg.device);
+  void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
+                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
+  if (!cfg || !out) return fail(BTKB_ERR_INVALID, "btkb_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(BTKB_ERR_NO_DEVICE, "btkb_create: no CUDA device is visible; this library has no CPU path");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(BTKB_ERR_INVALID, "btkb_create: bad device ordinal");
+  const int M = cfg->fft_len, C = cfg->channels;
+  if (M < 256 || M > 2048 || (M & (M - 1))) return fail(BTKB_ERR_INVALID, "btkb_create: fft_len must be a power of two in [256, 2048]");
+  if (cfg->m < 1 || cfg->m > 8 || cfg->r < 0 || (M >> cfg->r) < 32) return fail(BTKB_ERR_INVALID, "btkb_create: bad m / r");
+  if (C < 1) return fail(BTKB_ERR_INVALID, "btkb_create: channels must be >= 1");
+  if (C != 2 && C != 4 && C != 8) return fail(BTKB_ERR_INVALID, "btkb_create: this build instantiates the per-bin kernel for 2, 4 and 8 channels");
+  if (cfg->max_utterances < 1 || cfg->max_samples < 1) return fail(BTKB_ERR_INVALID, "btkb_create: capacities must be positive");
+  if (cfg->beamformer < BTKB_BF_DS || cfg->beamformer > BTKB_BF_GSC_LMS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown beamformer kind");
+  if (cfg->beamformer == BTKB_BF_GSC_LMS && cfg->postfilter != BTKB_PF_NONE)
+    return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCLMSBeamformer");
+  CK(cudaSetDevice(cfg->device));
+  btkb_pipeline* p = new btkb_pipeline();
+  p->cfg = *cfg;
+  p->C = C; p->M = M; p->K = M / 2 + 1; p->m = cfg->m; p->R = 1 << cfg->r; p->D = M >> cfg->r;
+  fb_delays(cfg->m, cfg->r, cfg->delay_compensation_type, false, &p->pdA, &p->laN);
+  int la_dummy; fb_delays(cfg->m, cfg->r, cfg->delay_compensation_type, true, &p->pdS, &la_dummy);
+  p->Ucap = cfg->max_utterances; p->ncap = cfg->max_samples; p->n_stride = round_up(cfg->max_samples, 4);
+  p->Tcap = frames_of(p->ncap, p->D, p->laN, p->pdA);
+  p->Gpcap = round_up(p->Ucap * p->K, 128);
+  const size_t G = (size_t)p->Gpcap, T = (size_t)p->Tcap, U = (size_t)p->Ucap;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
+  e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  for (auto& ev : p->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+  A((void**)&p->d_x, U * C * p->n_stride * sizeof(float));
+  A((void**)&p->d_len, U * sizeof(int));
+  A((void**)&p->d_h, (size_t)p->m * M * sizeof(float));
+  A((void**)&p->d_g, (size_t)p->m * M * sizeof(float));
+  A((void**)&p->d_X, T * C * G * sizeof(float2));
+  A((void**)&p->d_Y, T * G * sizeof(float2));
+  A((void**)&p->d_W, (size_t)C * G * sizeof(float2));
+  A((void**)&p->d_TA, (size_t)C * G * sizeof(float2));
+  A((void**)&p->d_WL, (size_t)C * G * sizeof(float2));
+  A((void**)&p->d_WA, (size_t)C * G * sizeof(float2));
+  A((void**)&p->d_UA, (size_t)C * G * sizeof(float2));
+  if (cfg->beamformer == BTKB_BF_MVDR) A((void**)&p->d_R, (size_t)C * C * G * sizeof(float2));
+  A((void**)&p->d_E, T * U * sizeof(float));
+  A((void**)&p->d_time, U * (T * p->D) * sizeof(float));
+  A((void**)&p->d_upd, U * sizeof(float));
+  if (cfg->postfilter == BTKB_PF_ZELINSKI) A((void**)&p->d_PFW, T * G * sizeof(float));
+  A((void**)&p->d_delays, U * C * sizeof(double));
+  A((void**)&p->d_mpos, (size_t)C * 3 * sizeof(double));
+  A((void**)&p->d_labels, U * 2 * sizeof(double));
+  A((void**)&p->d_stats, U * 3 * sizeof(double));
+  A((void**)&p->d_mask, T * U);
+  A((void**)&p->d_count, U * sizeof(int));
+  if (e != cudaSuccess) {
+    std::string msg = std::string("btkb_create: allocation failed: ") + cudaGetErrorString(e);
+    btkb_destroy(p);
+    cudaGetLastError();
+    return fail(BTKB_ERR_ALLOC, msg);
+  }
+  *out = p;
+  return BTKB_OK;
+}
+
+int btkb_set_prototypes(btkb_pipeline* p, const double* h, const double* g, int len) {
+  if (!p || !h) return fail(BTKB_ERR_INVALID, "btkb_set_prototypes: null argument");
+  if (len != p->m * p->M)  // modulated.cc:239-241 jconsistency_error
+    return fail(BTKB_ERR_INVALID, "Prototype sizes do not match (" + std::to_string(len) + " vs. " + std::to_string(p->m * p->M) + ").");
+  CK(cudaSetDevice(p->cfg.device));
+  std::vector<float> hf(len), gf(len);
+  for (int i = 0; i < len; i++) hf[i] = (float)h[i];
+  CK(cudaMemcpyAsync(p->d_h, hf.data(), len * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  p->have_h = true;
+  if (g) {
+    for (int i = 0; i < len; i++) gf[i] = (float)g[i];
+    CK(cudaMemcpyAsync(p->d_g, gf.data(), len * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    p->have_g = true;
+  }
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+// host [U][K][X] complex64  <->  device [X][Gp]
+static void to_device_layout(const float* src, std::vector<float2>& dst, int U, int K, int X, int Gp) {
+  dst.assign((size_t)X * Gp, make_float2(0.f, 0.f));
+  for (int u = 0; u < U; u++)
+    for (int k = 0; k < K; k++)
+      for (int c = 0; c < X; c++) {
+        const float* s = src + 2 * (((size_t)u * K + k) * X + c);
+        dst[(size_t)c * Gp + (size_t)u * K + k] = make_float2(s[0], s[1]);
+      }
+}
+static void from_device_layout(const std::vector<float2>& src, float* dst, int U, int K, int X, int Gp) {
+  for (int u = 0; u < U; u++)
+    for (int k = 0; k < K; k++)
+      for (int c = 0; c < X; c++) {
+        float2 v = src[(size_t)c * Gp + (size_t)u * K + k];
+        float* d = dst + 2 * (((size_t)u * K + k) * X + c);
+        d[0] = v.x; d[1] = v.y;
+      }
+}
+
+static int check_weight_batch(btkb_pipeline* p, int U, const char* who) {
+  if (U < 1 || U > p->Ucap) return fail(BTKB_ERR_INVALID, std::string(who) + ": U out of range");
+  if (p->wU != 0 && p->wU != U && p->U != 0 && p->U != U) return fail(BTKB_ERR_INVALID, std::string(who) + ": U differs from the submitted batch");
+  p->wU = U;
+  p->Gp = round_up(U * p->K, 128);
+  return BTKB_OK;
+}
+
+int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
+  if (!p || !delays) return fail(BTKB_ERR_INVALID, "btkb_set_delays: null argument");
+  int rc = check_weight_batch(p, U, "btkb_set_delays"); if (rc) return rc;
+  if ((p->cfg.beamformer == BTKB_BF_GSC || p->cfg.beamformer == BTKB_BF_GSC_LMS) && p->C <= 1)  // beamformer.cc:507-510
+    return fail(BTKB_ERR_INVALID, "The number of channels must be > 1 but it is " + std::to_string(p->C));
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(p->d_delays, delays, (size_t)U * p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  WeightsArgs a{p->d_delays, p->d_TA, U, p->C, p->M, p->K, p->Gp, p->cfg.samplerate};
+  CK(launch_mainlobe_weights(a, p->stream));
+  p->have_ta = true;
+  if (p->cfg.beamformer != BTKB_BF_MVDR) {
+    CK(cudaMemcpyAsync(p->d_W, p->d_TA, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
+    p->have_w = true;
+  }
+  CK(cudaStreamSynchronize(p->stream));  // `delays` is caller memory
+  return BTKB_OK;
+}
+
+int btkb_set_weights(btkb_pipeline* p, int U, const float* w) {
+  if (!p || !w) return fail(BTKB_ERR_INVALID, "btkb_set_weights: null argument");
+  int rc = check_weight_batch(p, U, "btkb_set_weights"); if (rc) return rc;
+  CK(cudaSetDevice(p->cfg.device));
+  std::vector<float2> tmp;
+  to_device_layout(w, tmp, U, p->K, p->C, p->Gp);
+  CK(cudaMemcpyAsync(p->d_W, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_w = true;
+  if (!p->have_ta) {  // setQuiescentVector without delays: the manifold is the weight itself
+    CK(cudaMemcpy(p->d_TA, p->d_W, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice));
+    p->have_ta = true;
+  }
+  return BTKB_OK;
+}
+
+int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa) {
+  if (!p || !wa) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: null argument");
+  if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_gsc_weights_x() once");  // beamformer.cc:1369-1371
+  if (p->C < 2) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: needs at least two channels");
+  int rc = check_weight_batch(p, U, "btkb_set_active_weights"); if (rc) return rc;
+  CK(cudaSetDevice(p->cfg.device));
+  std::vector<float2> tmp;
+  to_device_layout(wa, tmp, U, p->K, p->C - 1, p->Gp);
+  CK(cudaMemcpyAsync(p->d_WA, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+  CK(launch_blocking_wl(p->d_TA, p->d_WA, p->d_WL, U, p->C, p->K, p->Gp, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_wl = true;
+  return BTKB_OK;
+}
+
+int btkb_set_noise_covariance(btkb_pipeline* p, int U, const float* R) {
+  if (!p || !R) return fail(BTKB_ERR_INVALID, "btkb_set_noise_covariance: null argument");
+  if (!p->d_R) return fail(BTKB_ERR_STATE, "btkb_set_noise_covariance: pipeline was not created with BTKB_BF_MVDR");
+  int rc = check_weight_batch(p, U, "btkb_set_noise_covariance"); if (rc) return rc;
+  CK(cudaSetDevice(p->cfg.device));
+  std::vector<float2> tmp;
+  to_device_layout(R, tmp, U, p->K, p->C * p->C, p->Gp);
+  CK(cudaMemcpyAsync(p->d_R, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_R = true; p->R_is_sum = false;
+  return BTKB_OK;
+}
+
+int btkb_set_diffuse_noise_model(btkb_pipeline* p, int U, const double* mpos, float sspeed) {
+  if (!p || !mpos) return fail(BTKB_ERR_INVALID, "btkb_set_diffuse_noise_model: null argument");
+  if (!p->d_R) return fail(BTKB_ERR_STATE, "btkb_set_diffuse_noise_model: pipeline was not created with BTKB_BF_MVDR");
+  int rc = check_weight_batch(p, U, "btkb_set_diffuse_noise_model"); if (rc) return rc;
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(p->d_mpos, mpos, (size_t)p->C * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  CK(launch_diffuse_model(p->d_mpos, p->d_R, U, p->C, p->M, p->K, p->Gp, p->cfg.samplerate, sspeed, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_R = true; p->R_is_sum = false;
+  return BTKB_OK;
+}
+
+int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu) {
+  if (!p) return fail(BTKB_ERR_INVALID, "btkb_calc_mvdr_weights: null argument");
+  if (!p->have_R) return fail(BTKB_ERR_STATE, "Set a spatial spectral matrix before calling calc_mvdr_weights()");  // beamformer.cc:2352-2354
+  if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                      // beamformer.cc:2355-2357
+  CK(cudaSetDevice(p->cfg.device));
+  CK(launch_mvdr_solve(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->stream));
+  p->have_w = true;
+  return BTKB_OK;
+}
+
+static int submit_common(btkb_pipeline* p, int U, int n, const int* lengths) {
+  if (U < 1 || U > p->Ucap) return fail(BTKB_ERR_INVALID, "btkb_submit: U exceeds max_utterances");
+  if (n < 1 || n > p->ncap) return fail(BTKB_ERR_INVALID, "btkb_submit: n exceeds max_samples");
+  if (p->wU != 0 && p->wU != U) return fail(BTKB_ERR_INVALID, "btkb_submit: U differs from the batch the weights were set for");
+  p->U = U; p->n = n;
+  p->lengths.assign(U, n);
+  int Tmax = 0;
+  for (int u = 0; u < U; u++) {
+    if (lengths) { if (lengths[u] < 0 || lengths[u] > n) return fail(BTKB_ERR_INVALID, "btkb_submit: lengths[u] out of range"); p->lengths[u] = lengths[u]; }
+    Tmax = std::max(Tmax, frames_of(p->lengths[u], p->D, p->laN, p->pdA));
+  }
+  p->T = Tmax; p->nb = std::max(Tmax - p->pdS, 0);
+  p->Gp = round_up(U * p->K, 128);
+  p->have_X = p->have_Y = p->have_time = p->have_ua = false;
+  CK(cudaMemcpyAsync(p->d_len, p->lengths.data(), U * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+  return BTKB_OK;
+}
+
+int btkb_submit(btkb_pipeline* p, const float* samples, int U, int n, const int* lengths) {
+  if (!p || !samples) return fail(BTKB_ERR_INVALID, "btkb_submit: null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  int rc = submit_common(p, U, n, lengths); if (rc) return rc;
+  // [U][C][n] host -> [U][C][n_stride] device
+  CK(cudaMemcpy2DAsync(p->d_x, (size_t)p->n_stride * sizeof(float), samples, (size_t)n * sizeof(float), (size_t)n * sizeof(float), (size_t)U * p->C,
+                       cudaMemcpyHostToDevice, p->stream));
+  p->x_cur = p->d_x;
+  return BTKB_OK;
+}
+
+int btkb_submit_device(btkb_pipeline* p, const float* d_samples, int U, int n, const int* lengths) {
+  if (!p || !d_samples) return fail(BTKB_ERR_INVALID, "btkb_submit_device: null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  int rc = submit_common(p, U, n, lengths); if (rc) return rc;
+  if (n % 4 == 0 && n == p->n_stride) { p->x_cur = d_samples; return BTKB_OK; }
+  CK(cudaMemcpy2DAsync(p->d_x, (size_t)p->n_stride * sizeof(float), d_samples, (size_t)n * sizeof(float), (size_t)n * sizeof(float), (size_t)U * p->C,
+                       cudaMemcpyDeviceToDevice, p->stream));
+  p->x_cur = p->d_x;
+  return BTKB_OK;
+}
+
+static int do_analysis(btkb_pipeline* p) {
+  if (!p->have_h) return fail(BTKB_ERR_STATE, "btkb_run: set the analysis prototype first");
+  if (p->U == 0) return fail(BTKB_ERR_STATE, "btkb_run: no batch submitted");
+  AnalysisArgs a{p->x_cur, p->d_len, p->d_h, p->d_X, p->d_E, p->U, p->C, p->n, (p->x_cur == p->d_x) ? p->n_stride : p->n, p->T, p->M, p->m, p->D, p->laN,
+                 p->Gp, 1};
+  CK(launch_analysis(a, p->stream));
+  p->launches++;
+  p->have_X = true;
+  return BTKB_OK;
+}
+
+static PerBinArgs perbin_args(btkb_pipeline* p) {
+  PerBinArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = p->d_X; a.E = p->d_E; a.lengths = p->d_len; a.W = p->d_W; a.TA = p->d_TA;
+  a.WL = p->have_wl ? p->d_WL : nullptr;
+  a.Y = p->d_Y; a.PFW = p->d_PFW; a.UA = p->d_UA; a.stats_updates = p->d_upd;
+  a.R = p->d_R; a.noise_mask = p->d_mask; a.noise_count = p->d_count;
+  a.U = p->U; a.C = p->C; a.T = p->T; a.M = p->M; a.K = p->K; a.G = p->U * p->K; a.Gp = p->Gp; a.D = p->D; a.laN = p->laN; a.pdA = p->pdA;
+  a.kind = p->cfg.beamformer; a.pf_kind = p->cfg.postfilter; a.pf_alpha = p->cfg.pf_alpha; a.pf_type = p->cfg.pf_type; a.pf_min_frames = p->cfg.pf_min_frames;
+  const btkb_lms_params& l = p->cfg.lms;
+  a.lms = LmsArgs{l.beta, l.gamma, l.init_diagonal_load, l.regularization_param, l.energy_floor, l.sil_thresh, l.max_wa_l2norm, l.min_frames, l.slowdown_after};
+  return a;
+}
+
+static int do_beamformer(btkb_pipeline* p) {
+  if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_run_beamformer: run the analysis first");
+  if (!p->have_w) {
+    if (p->cfg.beamformer == BTKB_BF_MVDR) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");            // beamformer.cc:2544-2546
+    return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                                          // beamformer.cc:1098-1100
+  }
+  if (p->wU != p->U) return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: weights were set for a different number of utterances");
+  PerBinArgs a = perbin_args(p);
+  CK(launch_perbin(a, p->stream));
+  p->launches++;
+  p->have_Y = true;
+  p->have_ua = (p->cfg.beamformer == BTKB_BF_GSC_LMS);
+  return BTKB_OK;
+}
+
+static int do_synthesis(btkb_pipeline* p) {
+  if (!p->have_g) return fail(BTKB_ERR_STATE, "btkb_run: set the synthesis prototype first");
+  if (!p->have_Y) return fail(BTKB_ERR_STATE, "btkb_run: no beamformer output to synthesise");
+  CK(cudaMemsetAsync(p->d_stats, 0, (size_t)p->U * 3 * sizeof(double), p->stream));
+  SynthesisArgs a{p->d_Y, p->d_len, p->d_g, p->d_time, p->d_stats, p->U, p->n, p->T, p->M, p->m, p->cfg.r, p->D, p->K, p->Gp, p->pdS, p->laN, p->pdA,
+                  p->nb, p->nb * p->D, 1};
+  CK(launch_synthesis(a, p->stream));
+  p->launches++;
+  p->have_time = true;
+  return BTKB_OK;
+}
+
+int btkb_run_analysis(btkb_pipeline* p) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  p->launches = 0;
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  int rc = do_analysis(p); if (rc) return rc;
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  CK(cudaEventRecord(p->ev[2], p->stream));
+  CK(cudaEventRecord(p->ev[3], p->stream));
+  return BTKB_OK;
+}
+
+int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float energy_threshold) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_accumulate_covariance: run the analysis first");
+  if (!p->d_R) return fail(BTKB_ERR_STATE, "btkb_accumulate_covariance: pipeline was not created with BTKB_BF_MVDR");
+  CK(cudaSetDevice(p->cfg.device));
+  if (labels) {
+    CK(cudaMemcpyAsync(p->d_labels, labels, (size_t)p->U * 2 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  }
+  CK(launch_noise_mask(p->d_E, p->d_len, labels ? p->d_labels : nullptr, p->d_mask, p->d_count, p->U, p->T, p->D, p->laN, p->pdA, p->cfg.samplerate,
+                       energy_threshold, p->stream));
+  PerBinArgs a = perbin_args(p);
+  CK(launch_covariance(a, p->stream));
+  if (labels) CK(cudaStreamSynchronize(p->stream));
+  p->have_R = true; p->R_is_sum = true;
+  p->wU = p->U;
+  return BTKB_OK;
+}
+
+int btkb_run_beamformer(btkb_pipeline* p, int do_syn) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  p->launches = 0;
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  int rc = do_beamformer(p); if (rc) return rc;
+  CK(cudaEventRecord(p->ev[2], p->stream));
+  if (do_syn) { rc = do_synthesis(p); if (rc) return rc; }
+  CK(cudaEventRecord(p->ev[3], p->stream));
+  return BTKB_OK;
+}
+
+int btkb_run(btkb_pipeline* p, int do_syn) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  p->launches = 0;
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  int rc = do_analysis(p); if (rc) return rc;
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  rc = do_beamformer(p); if (rc) return rc;
+  CK(cudaEventRecord(p->ev[2], p->stream));
+  if (do_syn) { rc = do_synthesis(p); if (rc) return rc; }
+  CK(cudaEventRecord(p->ev[3], p->stream));
+  return BTKB_OK;
+}
+
+int btkb_synchronize(btkb_pipeline* p) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+int btkb_last_timing(btkb_pipeline* p, float* out5) {
+  if (!p || !out5) return fail(BTKB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaEventSynchronize(p->ev[3]));
+  CK(cudaEventElapsedTime(&out5[0], p->ev[0], p->ev[3]));
+  CK(cudaEventElapsedTime(&out5[1], p->ev[0], p->ev[1]));
+  CK(cudaEventElapsedTime(&out5[2], p->ev[1], p->ev[2]));
+  CK(cudaEventElapsedTime(&out5[3], p->ev[2], p->ev[3]));
+  out5[4] = (float)p->launches;
+  return BTKB_OK;
+}
+
+int btkb_num_frames(const btkb_pipeline* p) { return p ? p->T : 0; }
+int btkb_num_frames_of(const btkb_pipeline* p, int u) { return (p && u >= 0 && u < p->U) ? frames_of(p->lengths[u], p->D, p->laN, p->pdA) : 0; }
+int btkb_num_blocks(const btkb_pipeline* p) { return p ? p->nb : 0; }
+
+static int ensure_scratch(btkb_pipeline* p, size_t bytes) {
+  if (p->scratch_bytes >= bytes) return BTKB_OK;
+  if (p->d_scratch) { cudaFree(p->d_scratch); p->d_scratch = nullptr; p->scratch_bytes = 0; }
+  CK(cudaMalloc(&p->d_scratch, bytes));
+  p->scratch_bytes = bytes;
+  return BTKB_OK;
+}
+
+// device [T][rows][Gp] complex -> packed [U][T][rows][K]
+__global__ void k_gather(const float2* src, float2* dst, int U, int T, int rows, int K, int Gp) {
+  const size_t total = (size_t)U * T * rows * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % K); size_t r = i / K;
+    int c = (int)(r % rows); r /= rows;
+    int t = (int)(r % T); int u = (int)(r / T);
+    dst[i] = src[((size_t)t * rows + c) * Gp + (size_t)u * K + k];
+  }
+}
+__global__ void k_gather_f(const float* src, float* dst, int U, int T, int K, int Gp) {
+  const size_t total = (size_t)U * T * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % K); size_t r = i / K;
+    int t = (int)(r % T); int u = (int)(r / T);
+    dst[i] = src[(size_t)t * Gp + (size_t)u * K + k];
+  }
+}
+
+int btkb_fetch_subband(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_Y) return fail(BTKB_ERR_STATE, "btkb_fetch_subband: nothing has been beamformed");
+  CK(cudaSetDevice(p->cfg.device));
+  const size_t bytes = (size_t)p->U * p->T * p->K * sizeof(float2);
+  int rc = ensure_scratch(p, bytes); if (rc) return rc;
+  k_gather<<<2048, 256, 0, p->stream>>>(p->d_Y, (float2*)p->d_scratch, p->U, p->T, 1, p->K, p->Gp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+int btkb_fetch_snapshots(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_fetch_snapshots: run the analysis first");
+  CK(cudaSetDevice(p->cfg.device));
+  const size_t bytes = (size_t)p->U * p->T * p->C * p->K * sizeof(float2);
+  int rc = ensure_scratch(p, bytes); if (rc) return rc;
+  k_gather<<<2048, 256, 0, p->stream>>>(p->d_X, (float2*)p->d_scratch, p->U, p->T, p->C, p->K, p->Gp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+int btkb_get_postfilter_weights(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->d_PFW || !p->have_Y) return fail(BTKB_ERR_STATE, "btkb_get_postfilter_weights: no post-filter output");
+  CK(cudaSetDevice(p->cfg.device));
+  const size_t bytes = (size_t)p->U * p->T * p->K * sizeof(float);
+  int rc = ensure_scratch(p, bytes); if (rc) return rc;
+  k_gather_f<<<2048, 256, 0, p->stream>>>(p->d_PFW, (float*)p->d_scratch, p->U, p->T, p->K, p->Gp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+int btkb_fetch_time(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_time) return fail(BTKB_ERR_STATE, "btkb_fetch_time: synthesis has not run");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(out, p->d_time, (size_t)p->U * p->nb * p->D * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+int btkb_fetch_stats(btkb_pipeline* p, double* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  std::vector<float> upd(p->U, 0.f);
+  if (p->have_time) CK(cudaMemcpyAsync(out, p->d_stats, (size_t)p->U * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  else memset(out, 0, (size_t)p->U * 3 * sizeof(double));
+  if (p->have_ua) CK(cudaMemcpyAsync(upd.data(), p->d_upd, (size_t)p->U * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  for (int u = 0; u < p->U; u++) { out[3 * u + 1] = frames_of(p->lengths[u], p->D, p->laN, p->pdA); out[3 * u + 2] = upd[u]; }
+  return BTKB_OK;
+}
+
+static int get_rows(btkb_pipeline* p, const float2* d_src, int rows, float* out) {
+  std::vector<float2> tmp((size_t)rows * p->Gp);
+  CK(cudaMemcpyAsync(tmp.data(), d_src, tmp.size() * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  from_device_layout(tmp, out, p->wU ? p->wU : p->U, p->K, rows, p->Gp);
+  return BTKB_OK;
+}
+
+int btkb_get_weights(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_w) return fail(BTKB_ERR_STATE, "btkb_get_weights: no weights");
+  CK(cudaSetDevice(p->cfg.device));
+  return get_rows(p, p->d_W, p->C, out);
+}
+
+int btkb_get_active_weights(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  if (p->cfg.beamformer == BTKB_BF_GSC_LMS) {
+    if (!p->have_ua) return fail(BTKB_ERR_STATE, "btkb_get_active_weights: the NLMS has not run");
+    CK(launch_ua_to_wa(p->d_UA, p->d_TA, p->d_WA, p->U, p->C, p->K, p->Gp, p->stream));
+  } else if (!p->have_wl) {
+    return fail(BTKB_ERR_STATE, "btkb_get_active_weights: no active weights set");
+  }
+  return get_rows(p, p->d_WA, p->C - 1, out);
+}
+
+int btkb_get_covariance(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_R) return fail(BTKB_ERR_STATE, "btkb_get_covariance: no covariance");
+  CK(cudaSetDevice(p->cfg.device));
+  int rc = get_rows(p, p->d_R, p->C * p->C, out); if (rc) return rc;
+  if (p->R_is_sum) {  // finalize_stats (pybeamformer.py:994-1000): divide by the number of noise frames
+    std::vector<int> cnt(p->U);
+    CK(cudaMemcpy(cnt.data(), p->d_count, (size_t)p->U * sizeof(int), cudaMemcpyDeviceToHost));
+    const size_t per = (size_t)p->K * p->C * p->C * 2;
+    for (int u = 0; u < p->U; u++)
+      if (cnt[u] > 0) for (size_t i = 0; i < per; i++) out[(size_t)u * per + i] /= (float)cnt[u];
+  }
+  return BTKB_OK;
+}
+
+int btkb_device_pointers(btkb_pipeline* p, void** X, void** Y, void** time_out) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  if (X) *X = p->d_X; if (Y) *Y = p->d_Y; if (time_out) *time_out = p->d_time;
+  return BTKB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// btkb_fft.cuh — register-resident Stockham FFT used by the OverSampledDFT analysis / synthesis kernels (sm_100a).
+//
+// An M-point complex DFT is done by NT = M/8 threads holding 8 complex values each.  M = R0 * 8^P with R0 in {2,4,8}:
+// one leading radix-R0 pass (no twiddles) followed by P radix-8 passes.  Between passes the data goes through a
+// ping-pong shared-memory buffer (one barrier per pass).  The per-thread twiddles depend only on the thread index, so
+// they are computed once per CTA (sincospif, exact argument reduction) and stay in registers for every transform the
+// CTA performs.
+//
+// Direction: SIGN = +1 is the reference's gsl_fft_complex_radix2_backward (unnormalised e^{+2 pi i nk/M}, used by
+// OverSampledDFTAnalysisBank::next, modulated.cc:396); SIGN = -1 is gsl_fft_complex_radix2_forward (synthesis,
+// modulated.cc:559).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace btkb {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+// multiply by SIGN * i
+template <int SIGN>
+__device__ __forceinline__ float2 mul_si(float2 a) {
+  return SIGN > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <int M>
+struct FftPlan {
+  static_assert(M >= 64 && M <= 4096 && (M & (M - 1)) == 0, "M must be a power of two in [64,4096]");
+  static constexpr int log2m() { int q = 0; for (int v = M; v > 1; v >>= 1) q++; return q; }
+  static constexpr int P = (log2m() - 1) / 3;                           // number of radix-8 passes
+  static constexpr int pow8(int p) { return p == 0 ? 1 : 8 * pow8(p - 1); }
+  static constexpr int R0 = M / pow8(P);                                // leading radix: 2, 4 or 8
+  static constexpr int NT = M / 8;                                      // threads per transform
+  static constexpr int NPASS = P + 1;
+  static constexpr int BUF = M + M / 16;                                // padded buffer length (float2)
+};
+
+// padded shared-memory index: breaks the stride-8 / stride-64 patterns of the pass outputs
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+
+template <int SIGN>
+__device__ __forceinline__ void dft2(float2& a, float2& b) {
+  float2 t = a; a = cadd(t, b); b = csub(t, b);
+}
+template <int SIGN>
+__device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = mul_si<SIGN>(csub(v1, v3));
+  v0 = cadd(a0, a2); v2 = csub(a0, a2); v1 = cadd(a1, a3); v3 = csub(a1, a3);
+}
+// X[q] = sum_r v[r] exp(SIGN 2 pi i q r / 8), natural order in and out
+template <int SIGN>
+__device__ __forceinline__ void dft8(float2* v) {
+  float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4<SIGN>(e0, e1, e2, e3);
+  dft4<SIGN>(o0, o1, o2, o3);
+  const float s = 0.70710678118654752440f;
+  // o1 *= (1 + SIGN i)/sqrt2 ; o2 *= SIGN i ; o3 *= (-1 + SIGN i)/sqrt2
+  float2 t1 = mul_si<SIGN>(o1);
+  o1 = make_float2((o1.x + t1.x) * s, (o1.y + t1.y) * s);
+  o2 = mul_si<SIGN>(o2);
+  float2 t3 = mul_si<SIGN>(o3);
+  o3 = make_float2((t3.x - o3.x) * s, (t3.y - o3.y) * s);
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// Per-thread twiddles for the P radix-8 passes: tw[p][r-1] = exp(SIGN 2 pi i k r / (Ns 8)), k = tid % Ns, Ns = R0 8^p.
+template <int M, int SIGN>
+struct FftTwiddles {
+  using Plan = FftPlan<M>;
+  float2 tw[Plan::P][7];
+  __device__ __forceinline__ void init(int tid) {
+    int Ns = Plan::R0;
+#pragma unroll
+    for (int p = 0; p < Plan::P; p++) {
+      int k = tid % Ns;
+#pragma unroll
+      for (int r = 1; r < 8; r++) {
+        float s, c;
+        // angle / pi = SIGN * 2 k r / (8 Ns)  (exact in float: k r < 2^15, power-of-two denominator)
+        sincospif((float)(SIGN * 2 * k * r) / (float)(8 * Ns), &s, &c);
+        tw[p][r - 1] = make_float2(c, s);
+      }
+      Ns *= 8;
+    }
+  }
+};
+
+// Store the leading-pass or radix-8-pass results (Stockham scatter): element r of butterfly j goes to
+// (j / Ns) Ns R + (j % Ns) + r Ns.
+template <int R>
+__device__ __forceinline__ void stockham_store(float2* buf, const float2* v, int j, int Ns) {
+  int k = j % Ns;
+  int j0 = (j - k) * R + k;
+#pragma unroll
+  for (int r = 0; r < R; r++) buf[pidx(j0 + r * Ns)] = v[r];
+}
+
+// The leading radix-R0 pass on registers that were loaded as v[b*R0 + r] = in[(tid + b NT) + r M/R0].
+template <int M, int SIGN>
+__device__ __forceinline__ void fft_first_pass(float2* v, float2* buf, int tid) {
+  using Plan = FftPlan<M>;
+  constexpr int R0 = Plan::R0, NT = Plan::NT, NB = 8 / R0;
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    float2* w = v + b * R0;
+    if (R0 == 8) dft8<SIGN>(w);
+    else if (R0 == 4) dft4<SIGN>(w[0], w[1], w[2], w[3]);
+    else dft2<SIGN>(w[0], w[1]);
+    stockham_store<R0>(buf, w, tid + b * NT, 1);
+  }
+}
+
+// Radix-8 pass p (0-based among the radix-8 passes): reads `in`, writes `out` (both padded smem buffers).
+template <int M, int SIGN>
+__device__ __forceinline__ void fft_radix8_pass(const float2* in, float2* out, int tid, int p, int Ns,
+                                                const FftTwiddles<M, SIGN>& T) {
+  float2 v[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) v[r] = in[pidx(tid + r * (M / 8))];
+#pragma unroll
+  for (int r = 1; r < 8; r++) v[r] = cmul(v[r], T.tw[p][r - 1]);
+  dft8<SIGN>(v);
+  stockham_store<8>(out, v, tid, Ns);
+}
+
+// Full transform after the caller filled v (leading-pass operand order).  bufA/bufB: two padded smem buffers of
+// FftPlan<M>::BUF float2 each, private to the NT threads of this transform.  `sync()` must be a barrier covering at
+// least those NT threads.  On return the natural-order spectrum is in the returned buffer (already synchronised).
+template <int M, int SIGN, typename Sync>
+__device__ __forceinline__ float2* fft_run(float2* v, float2* bufA, float2* bufB, int tid,
+                                           const FftTwiddles<M, SIGN>& T, Sync sync) {
+  using Plan = FftPlan<M>;
+  fft_first_pass<M, SIGN>(v, bufA, tid);
+  sync();
+  float2* in = bufA;
+  float2* out = bufB;
+  int Ns = Plan::R0;
+#pragma unroll
+  for (int p = 0; p < Plan::P; p++) {
+    fft_radix8_pass<M, SIGN>(in, out, tid, p, Ns, T);
+    sync();
+    float2* t = in; in = out; out = t;
+    Ns *= 8;
+  }
+  return in;
+}
+
+}  // namespace btkb

@@ -1,0 +1,75 @@
+// btkb_internal.h — argument blocks and launch prototypes shared by the kernels and the C-ABI (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace btkb {
+
+// ------------------------------------------------------------------ HBM layout
+// samples  x  [U][C][n_stride]        float32   (time-major per channel; n_stride multiple of 4)
+// snapshots X [T][C][Gp]              complex64, g = u*K + k  (bin fastest, utterances interleaved, frame-major slabs)
+// output   Y  [T][Gp]                 complex64
+// energy   E  [T][U]                  float32   channel-0 frame energy |x0^H x0| / M
+// weights  W  [C][Gp]                 complex64 (wq / wmvdr), WL same shape (wl = B wa)
+// time     out[U][nb_stride]          float32
+
+struct AnalysisArgs {
+  const float* x; const int* lengths; const float* h;
+  float2* X; float* E;
+  int U, C, n, n_stride, T, M, m, D, laN, Gp, gain;
+};
+
+struct SynthesisArgs {
+  const float2* Y; const int* lengths; const float* g;
+  float* out; double* stats;  // stats [U][3]: sum of squares accumulated into [u][0]
+  int U, n, T, M, m, r, D, K, Gp, pdS, laN, pdA, nb, nb_stride, gain;
+};
+
+struct LmsArgs {
+  float beta, gamma, init_diagonal_load, regularization_param, energy_floor, sil_thresh, max_wa_l2norm;
+  int min_frames, slowdown_after;
+};
+
+struct PerBinArgs {
+  const float2* X; const float* E; const int* lengths;
+  const float2* W;    // [C][Gp] quiescent / mvdr weights (not conjugated)
+  const float2* WL;   // [C][Gp] wl = B wa (may be null)
+  const float2* TA;   // [C][Gp] time-alignment manifold for the post-filter (D&S weights)
+  float2* Y;          // [T][Gp]
+  float* PFW;         // [T][Gp] post-filter gains (may be null)
+  float2* UA;         // [C][Gp] NLMS state u = waH B^T (in/out, final value written)
+  float* stats_updates;  // [U] NLMS update counts (written by the thread owning bin 0)
+  // covariance accumulation
+  float2* R;          // [C*C][Gp] (row-major i*C+j) accumulated x_i conj(x_j)
+  const unsigned char* noise_mask;  // [T][U] 1 = accumulate this frame
+  int* noise_count;   // [U]
+  int U, C, T, M, K, G, Gp, D, laN, pdA;
+  int kind;           // BTKB_BF_*
+  int pf_kind; float pf_alpha; int pf_type, pf_min_frames;
+  LmsArgs lms;
+  float energy_threshold;
+};
+
+struct WeightsArgs {
+  const double* delays;  // [U][C]
+  float2* W;             // [C][Gp]
+  int U, C, M, K, Gp; float samplerate;
+};
+
+cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
+cudaError_t launch_synthesis(const SynthesisArgs& a, cudaStream_t st);
+cudaError_t launch_perbin(const PerBinArgs& a, cudaStream_t st);
+cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st);
+cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st);
+
+// setup kernels (btkb_weights.cu)
+cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, cudaStream_t st);
+cudaError_t launch_diffuse_model(const double* mpos, float2* R, int U, int C, int M, int K, int Gp, float samplerate, float sspeed, cudaStream_t st);
+cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count, cudaStream_t st);
+cudaError_t launch_ua_to_wa(const float2* UA, const float2* W, float2* WA, int U, int C, int K, int Gp, cudaStream_t st);
+cudaError_t launch_noise_mask(const float* E, const int* lengths, const double* labels, unsigned char* mask, int* count, int U, int T, int D, int laN, int pdA,
+                              float samplerate, float thr, cudaStream_t st);
+
+__host__ __device__ inline int frames_of(int len, int D, int laN, int pdA) { return (len + D - 1) / D - laN + pdA; }
+
+}  // namespace btkb

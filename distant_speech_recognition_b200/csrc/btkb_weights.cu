@@ -1,0 +1,246 @@
+// btkb_weights.cu — setup-time kernels (once per look direction / per utterance, never per frame), sm_100a.
+// One thread per (utterance, bin) chain g = u K + k; double precision throughout (the reference computes these in
+// double; they are O(U K C^3) and invisible next to the data path).
+//
+//   k_mainlobe      BeamformerWeights::calcMainlobe            btk20_src/beamformer/beamformer.cc:502-565
+//                   == calc_array_manifold_f                   btk20_src/lib/pybeamformer.py:284-306
+//   blocking matrix calc_blocking_matrix_ / calc_blocking_matrix   beamformer.cc:373-454 / pybeamformer.py:309-341
+//   k_blocking_wl   calcSidelobeCancellerP_f / U_f: wl = B wa   beamformer.cc:729-767
+//   k_ua_to_wa      export of the NLMS state: waH = u conj(B)   (inverse of u = waH B^T)
+//   k_diffuse       SubbandMVDR::set_diffuse_noise_model        beamformer.cc:2442-2509
+//   k_mvdr_solve    set_all_diagonal_loading + calc_mvdr_weights beamformer.cc:2350-2402, 2511-2523
+//                   (the reference inverts R with a single-precision LINPACK SVD, beamformer.cc:232-289; here a
+//                   double-precision LU solve of R^H t = d — same mathematics, tighter rounding)
+//   k_noise_mask    label / energy gating of accu_stats_from_label  pybeamformer.py:963-975
+#include "btkb_internal.h"
+
+namespace btkb {
+
+struct cd { double x, y; };
+__device__ __forceinline__ cd cdmake(double x, double y) { cd r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ cd cdadd(cd a, cd b) { return cdmake(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cd cdsub(cd a, cd b) { return cdmake(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cd cdmul(cd a, cd b) { return cdmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cd cdconj(cd a) { return cdmake(a.x, -a.y); }
+__device__ __forceinline__ cd cdscale(cd a, double s) { return cdmake(a.x * s, a.y * s); }
+__device__ __forceinline__ double cdabs2(cd a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ cd cddiv(cd a, cd b) { double d = cdabs2(b); return cdmake((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d); }
+
+constexpr int MAXC = 8;
+
+__global__ void k_mainlobe(WeightsArgs a) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.U * a.K) return;
+  const int u = g / a.K, k = g - u * a.K;
+  const double fs = (double)a.samplerate;  // the C++ signature takes float
+  for (int c = 0; c < a.C; c++) {
+    const double tau = a.delays[(size_t)u * a.C + c];
+    double val;
+    if (k == 0) val = 0.0;
+    else if (k == a.M / 2) val = -M_PI * fs * tau;
+    else val = -2.0 * M_PI * (double)k * tau * fs / (double)a.M;
+    double s, co;
+    sincos(val, &s, &co);
+    a.W[(size_t)c * a.Gp + g] = make_float2((float)(co / a.C), (float)(s / a.C));
+  }
+}
+
+// B[C][C-1]: P = I - conj(v) v^T / ||v||^2 ; Gram-Schmidt over its first C-1 columns (NC = 1)
+template <int C>
+__device__ void blocking_matrix(const cd* v, cd (*B)[C - 1]) {
+  double nv = 0.0;
+  for (int c = 0; c < C; c++) nv += cdabs2(v[c]);
+  cd vec[C];
+  for (int idim = 0; idim < C - 1; idim++) {
+    for (int r = 0; r < C; r++) {
+      cd p = cdscale(cdmul(cdconj(v[r]), v[idim]), -1.0 / nv);  // P[r][idim]
+      if (r == idim) p.x += 1.0;
+      vec[r] = p;
+    }
+    for (int jdim = 0; jdim < idim; jdim++) {
+      cd ip = cdmake(0, 0);
+      for (int r = 0; r < C; r++) ip = cdadd(ip, cdmul(cdconj(B[r][jdim]), vec[r]));  // zdotc(rvec, vec)
+      for (int r = 0; r < C; r++) vec[r] = cdsub(vec[r], cdmul(ip, B[r][jdim]));
+    }
+    double nrm = 0.0;
+    for (int r = 0; r < C; r++) nrm += cdabs2(vec[r]);
+    nrm = 1.0 / sqrt(nrm);
+    for (int r = 0; r < C; r++) B[r][idim] = cdscale(vec[r], nrm);
+  }
+}
+
+template <int C, int DIR>  // DIR 0: WL = B WA ; DIR 1: WA = UA conj(B)
+__global__ void k_blocking(const float2* W, const float2* IN, float2* OUT, int U, int K, int Gp) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= U * K) return;
+  cd v[C];
+  cd B[C][C - 1];
+  for (int c = 0; c < C; c++) { float2 t = W[(size_t)c * Gp + g]; v[c] = cdmake(t.x, t.y); }
+  blocking_matrix<C>(v, B);
+  if (DIR == 0) {
+    cd wa[C - 1];
+    for (int i = 0; i < C - 1; i++) { float2 t = IN[(size_t)i * Gp + g]; wa[i] = cdmake(t.x, t.y); }
+    for (int c = 0; c < C; c++) {
+      cd s = cdmake(0, 0);
+      for (int i = 0; i < C - 1; i++) s = cdadd(s, cdmul(B[c][i], wa[i]));
+      OUT[(size_t)c * Gp + g] = make_float2((float)s.x, (float)s.y);
+    }
+  } else {
+    cd ua[C];
+    for (int c = 0; c < C; c++) { float2 t = IN[(size_t)c * Gp + g]; ua[c] = cdmake(t.x, t.y); }
+    for (int i = 0; i < C - 1; i++) {
+      cd s = cdmake(0, 0);
+      for (int c = 0; c < C; c++) s = cdadd(s, cdmul(ua[c], cdconj(B[c][i])));
+      OUT[(size_t)i * Gp + g] = make_float2((float)s.x, (float)s.y);
+    }
+  }
+}
+
+template <int DIR>
+static cudaError_t launch_blocking(const float2* W, const float2* IN, float2* OUT, int U, int C, int K, int Gp, cudaStream_t st) {
+  const int n = U * K, bs = 128, gs = (n + bs - 1) / bs;
+  switch (C) {
+    case 2: k_blocking<2, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
+    case 3: k_blocking<3, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
+    case 4: k_blocking<4, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
+    case 6: k_blocking<6, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
+    case 8: k_blocking<8, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, cudaStream_t st) {
+  return launch_blocking<0>(W, WA, WL, U, C, K, Gp, st);
+}
+cudaError_t launch_ua_to_wa(const float2* UA, const float2* W, float2* WA, int U, int C, int K, int Gp, cudaStream_t st) {
+  return launch_blocking<1>(W, UA, WA, U, C, K, Gp, st);
+}
+
+cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st) {
+  const int n = a.U * a.K, bs = 128;
+  k_mainlobe<<<(n + bs - 1) / bs, bs, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// Gamma_ij = sinc(2 fs k d_ij / (M c)) (GSL sinc(x) = sin(pi x)/(pi x)), diagonal 1.  mpos [C][3] doubles (mm).
+__global__ void k_diffuse(const double* mpos, float2* R, int U, int C, int M, int K, int Gp, float samplerate, float sspeed) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= U * K) return;
+  const int k = g % K;
+  const double omega_d_c = 2.0 * (double)samplerate * (double)k / ((double)M * (double)sspeed);
+  for (int i = 0; i < C; i++)
+    for (int j = 0; j < C; j++) {
+      double val = 1.0;
+      if (i != j) {
+        double dx = mpos[i * 3] - mpos[j * 3], dy = mpos[i * 3 + 1] - mpos[j * 3 + 1], dz = mpos[i * 3 + 2] - mpos[j * 3 + 2];
+        double x = omega_d_c * sqrt(dx * dx + dy * dy + dz * dz);
+        double y = M_PI * x;
+        val = (fabs(y) < 1e-12) ? 1.0 : sin(y) / y;
+      }
+      R[(size_t)(i * C + j) * Gp + g] = make_float2((float)val, 0.f);
+    }
+}
+cudaError_t launch_diffuse_model(const double* mpos, float2* R, int U, int C, int M, int K, int Gp, float samplerate, float sspeed, cudaStream_t st) {
+  const int n = U * K, bs = 128;
+  k_diffuse<<<(n + bs - 1) / bs, bs, 0, st>>>(mpos, R, U, C, M, K, Gp, samplerate, sspeed);
+  return cudaGetLastError();
+}
+
+// w = (R^H)^-1 d / (C d^H R^-1 d), bin 0: all ones (beamformer.cc:2369-2371).  R row-major [i*C+j][g].
+template <int C>
+__global__ void k_mvdr_solve(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int K, int Gp, float mu, int normalize) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= U * K) return;
+  const int u = g / K, k = g - u * K;
+  if (k == 0) {
+    for (int c = 0; c < C; c++) W[(size_t)c * Gp + g] = make_float2(1.f, 0.f);
+    return;
+  }
+  double scale = 1.0;
+  if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
+  // A = R^H (conjugate transpose), with finalize_stats scaling and diagonal loading applied to R first
+  cd A[C][C];
+  cd b[C], d[C];
+  for (int i = 0; i < C; i++)
+    for (int j = 0; j < C; j++) {
+      float2 t = R[(size_t)(i * C + j) * Gp + g];
+      cd rij = cdmake((double)t.x * scale, (double)t.y * scale);
+      if (i == j) rij.x += (double)mu;  // set_all_diagonal_loading: float diagonalWeight
+      A[j][i] = cdconj(rij);
+    }
+  for (int c = 0; c < C; c++) { float2 t = Dm[(size_t)c * Gp + g]; d[c] = cdmake(t.x, t.y); b[c] = d[c]; }
+  // LU with partial pivoting, in place; solve A t = d
+  bool singular = false;
+  for (int col = 0; col < C; col++) {
+    int piv = col; double best = cdabs2(A[col][col]);
+    for (int r = col + 1; r < C; r++) { double v = cdabs2(A[r][col]); if (v > best) { best = v; piv = r; } }
+    if (!(best > 1e-60)) { singular = true; break; }
+    if (piv != col) {
+      for (int j = 0; j < C; j++) { cd t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
+      cd t = b[col]; b[col] = b[piv]; b[piv] = t;
+    }
+    for (int r = col + 1; r < C; r++) {
+      cd f = cddiv(A[r][col], A[col][col]);
+      for (int j = col + 1; j < C; j++) A[r][j] = cdsub(A[r][j], cdmul(f, A[col][j]));
+      b[r] = cdsub(b[r], cdmul(f, b[col]));
+    }
+  }
+  cd tvec[C];
+  if (!singular) {
+    for (int r = C - 1; r >= 0; r--) {
+      cd s = b[r];
+      for (int j = r + 1; j < C; j++) s = cdsub(s, cdmul(A[r][j], tvec[j]));
+      tvec[r] = cddiv(s, A[r][r]);
+    }
+  } else {
+    for (int c = 0; c < C; c++) tvec[c] = d[c];  // identity fallback (beamformer.cc:2381-2383)
+  }
+  cd lam = cdmake(0, 0);  // Lambda = tmpH^H d
+  for (int c = 0; c < C; c++) lam = cdadd(lam, cdmul(cdconj(tvec[c]), d[c]));
+  cd norm = cdscale(lam, (double)C);
+  for (int c = 0; c < C; c++) { cd wv = cddiv(tvec[c], norm); W[(size_t)c * Gp + g] = make_float2((float)wv.x, (float)wv.y); }
+}
+cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu,
+                              int normalize_by_count, cudaStream_t st) {
+  const int n = U * K, bs = 64, gs = (n + bs - 1) / bs;
+  switch (C) {
+    case 2: k_mvdr_solve<2><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    case 3: k_mvdr_solve<3><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    case 4: k_mvdr_solve<4><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    case 6: k_mvdr_solve<6><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    case 8: k_mvdr_solve<8><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// mask[t][u] = frame t of utterance u is a noise frame with energy > thr (pybeamformer.py:963-975); count[u] = their number
+__global__ void k_noise_mask(const float* E, const int* lengths, const double* labels, unsigned char* mask, int* count, int U, int T, int D, int laN,
+                             int pdA, float samplerate, float thr) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  const int Tu = frames_of(lengths[u], D, laN, pdA);
+  double elapsed = 0.0;
+  const double dt = (double)D / (double)samplerate;
+  int labx = 0, n = 0;
+  const double s = labels ? labels[2 * u] : 0.0, e = labels ? labels[2 * u + 1] : 0.0;
+  for (int t = 0; t < T; t++) {
+    bool is_target = false;
+    if (labels != nullptr && labx < 1) {
+      if (elapsed >= s && (elapsed <= e || e < 0)) is_target = true;
+      else if (elapsed > e) labx += 1;
+    }
+    const bool mk = (t < Tu) && !is_target && (E[(size_t)t * U + u] > thr);
+    mask[(size_t)t * U + u] = mk ? 1 : 0;
+    n += mk ? 1 : 0;
+    elapsed += dt;
+  }
+  count[u] = n;
+}
+cudaError_t launch_noise_mask(const float* E, const int* lengths, const double* labels, unsigned char* mask, int* count, int U, int T, int D, int laN,
+                              int pdA, float samplerate, float thr, cudaStream_t st) {
+  k_noise_mask<<<(U + 63) / 64, 64, 0, st>>>(E, lengths, labels, mask, count, U, T, D, laN, pdA, samplerate, thr);
+  return cudaGetLastError();
+}
+
+}  // namespace btkb

@@ -1,0 +1,148 @@
+/*
+ * btkb.h — C-ABI of the B200-native subband beamforming pipe ("btk batch").
+ *
+ * This is the drop-in boundary for btk2.0's hot path: everything the reference computes per frame inside
+ *   OverSampledDFTAnalysisBank::next        (btk20_src/modulated/modulated.cc:375-409)
+ *   SnapShotArray::update                   (btk20_src/beamformer/beamformer.cc:56-70)
+ *   SubbandDS/GSC/MVDR/MVDRGSC::next        (beamformer.cc:1095-1157, 1251-1316, 2537-2587, 2719-2773)
+ *   SubbandGSCLMSBeamformer.__iter__        (btk20_src/lib/pybeamformer.py:659-734)
+ *   SubbandSMIMVDRBeamformer.accu_stats...  (pybeamformer.py:948-1023)  +  SubbandMVDR::calc_mvdr_weights (beamformer.cc:2350-2402)
+ *   ZelinskiPostFilter::next                (btk20_src/postfilter/postfilter.cc:424-491)
+ *   OverSampledDFTSynthesisBank::next       (modulated.cc:569-612)
+ * is executed here for a whole batch of utterances by hand-written sm_100a CUDA kernels.
+ *
+ * Conventions: plain C types only (no torch / C++ types); every function returns BTKB_OK (0) or a negative
+ * error code and never throws; btkb_last_error() returns a thread-local description of the last failure.  One host
+ * thread per pipeline handle.  All work is stream-ordered on the pipeline's CUDA stream; functions that hand data to
+ * the host synchronise that stream before returning.  There is NO CPU fallback: creation fails with
+ * BTKB_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Shapes: U utterances, C channels, M subbands (fft_len), m prototype-length factor, r decimation exponent,
+ * D = M >> r samples per frame, K = M/2 + 1 unique bins, T frames:
+ *   T(n) = ceil(n / D) - laN + pd_A   (modulated.cc:246-264, 418-469; = ceil(n/D) + m 2^r / 2 for delay-comp. type 2).
+ * Complex arrays are interleaved (re, im).
+ */
+#ifndef BTKB_H
+#define BTKB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTKB_OK 0
+#define BTKB_ERR_INVALID (-1)    /* bad argument / configuration (the reference throws jdimension_error / jconsistency_error) */
+#define BTKB_ERR_NO_DEVICE (-2)  /* no usable CUDA device: the product never falls back to the CPU */
+#define BTKB_ERR_CUDA (-3)       /* a CUDA runtime call failed; see btkb_last_error() */
+#define BTKB_ERR_STATE (-4)      /* call order violated (the reference throws j_error "call calc_..._weights() once") */
+#define BTKB_ERR_ALLOC (-5)      /* jallocation_error */
+
+/* beamformer kinds */
+#define BTKB_BF_DS 0       /* SubbandDS: y = wq^H x                                          (beamformer.cc:1095-1157) */
+#define BTKB_BF_GSC 1      /* SubbandGSC: DC bin wq^H x, bins >= 1 (wq - wl)^H x, static wl  (beamformer.cc:1208-1316) */
+#define BTKB_BF_MVDR 2     /* SubbandMVDR / SubbandMVDRGSC: y = (wmvdr - wl)^H x             (beamformer.cc:2537-2587, 2719-2773) */
+#define BTKB_BF_GSC_LMS 3  /* SubbandGSCLMSBeamformer: leaky power-normalised NLMS           (pybeamformer.py:588-762) */
+
+/* post-filter kinds */
+#define BTKB_PF_NONE 0
+#define BTKB_PF_ZELINSKI 1 /* ZelinskiPostFilter (postfilter.cc:57-219, 424-491); type bits: 1 = Re, 2 = |.| */
+
+typedef struct btkb_pipeline btkb_pipeline;
+
+typedef struct btkb_lms_params { /* defaults = unit_test/confs/gsclms.json / pybeamformer.py:597-607 */
+  float beta, gamma, init_diagonal_load, regularization_param, energy_floor, sil_thresh, max_wa_l2norm;
+  int min_frames, slowdown_after;
+} btkb_lms_params;
+
+typedef struct btkb_config {
+  int device;                  /* CUDA device ordinal */
+  int channels;                /* C >= 1 (GSC kinds need C >= 2) */
+  int fft_len;                 /* M, power of two in [64, 4096] */
+  int m;                       /* prototype length factor (prototype length = m*M) */
+  int r;                       /* decimation exponent, D = M >> r */
+  int delay_compensation_type; /* 0, 1 or 2 (modulated.cc:246-264) */
+  float samplerate;
+  int beamformer;              /* BTKB_BF_* */
+  int postfilter;              /* BTKB_PF_* */
+  float pf_alpha;              /* Zelinski forgetting factor (default 0.6) */
+  int pf_type;                 /* 1 or 2 (postfilter.h:41-47) */
+  int pf_min_frames;
+  btkb_lms_params lms;
+  int max_utterances;          /* capacity of one batch */
+  int max_samples;             /* capacity: samples per channel per utterance */
+  int keep_snapshots;          /* 1: keep the analysis output X resident so btkb_fetch_snapshots works (always true today) */
+} btkb_config;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------------- */
+void btkb_default_config(btkb_config* cfg);
+int btkb_create(const btkb_config* cfg, btkb_pipeline** out);
+void btkb_destroy(btkb_pipeline* p);
+const char* btkb_last_error(void);
+int btkb_device_count(void);
+
+/* ---- setup (replaces OverSampledDFTFilterBank ctor, modulated.cc:232-268, and BeamformerWeights, beamformer.cc:485-965) */
+/* analysis prototype h and synthesis prototype g, len = m*M doubles each (g may be NULL when synthesis is not used) */
+int btkb_set_prototypes(btkb_pipeline* p, const double* h, const double* g, int len);
+/* per-utterance time delays [U][C] (seconds) -> quiescent weights wq = calcMainlobe (beamformer.cc:502-565), ta = wq */
+int btkb_set_delays(btkb_pipeline* p, int U, const double* delays);
+/* explicit quiescent / MVDR weights [U][K][C] complex64 (replaces setQuiescentVector / wmvdr_) */
+int btkb_set_weights(btkb_pipeline* p, int U, const float* w);
+/* active weights wa [U][K][C-1] complex64 -> wl = B wa with B = calc_blocking_matrix_(wq) (beamformer.cc:373-454, 729-767) */
+int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa);
+/* noise covariance R [U][K][C][C] complex64, row-major (set_noise_spatial_spectral_matrix, beamformer.cc:2410-2433) */
+int btkb_set_noise_covariance(btkb_pipeline* p, int U, const float* R);
+/* diffuse-noise coherence from microphone positions [C][3] (mm) (set_diffuse_noise_model, beamformer.cc:2442-2509) */
+int btkb_set_diffuse_noise_model(btkb_pipeline* p, int U, const double* mpos, float sspeed);
+/* R += mu I (set_all_diagonal_loading, beamformer.cc:2511-2523) then w = R^-H d / (C d^H R^-1 d), w[0] = 1
+ * (calc_mvdr_weights, beamformer.cc:2350-2402).  Uses the covariance from btkb_set_noise_covariance,
+ * btkb_set_diffuse_noise_model or btkb_accumulate_covariance. */
+int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu);
+
+/* ---- data path ------------------------------------------------------------------------------------------------ */
+/* host samples float32 [U][C][n] (int16 scale, like SampleFeature, feature/feature.cc:605-649), lengths[U] <= n (NULL: all n).
+ * Asynchronous H2D on the pipeline stream (pinned host memory recommended). */
+int btkb_submit(btkb_pipeline* p, const float* samples, int U, int n, const int* lengths);
+/* same, but `samples` is a DEVICE pointer in the same layout (no copy) */
+int btkb_submit_device(btkb_pipeline* p, const float* d_samples, int U, int n, const int* lengths);
+/* analysis only: time -> snapshots X (OverSampledDFTAnalysisBank + SnapShotArray) */
+int btkb_run_analysis(btkb_pipeline* p);
+/* SMI pass 1 (pybeamformer.py:948-1000): R[u][k] = mean over noise frames (outside [start,end] s, energy > threshold) of x x^H.
+ * labels [U][2] seconds (NULL: every frame is noise).  Requires btkb_run_analysis. */
+int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float energy_threshold);
+/* the per-bin beamformer (+ post-filter) over the resident snapshots, then synthesis when do_synthesis != 0 */
+int btkb_run_beamformer(btkb_pipeline* p, int do_synthesis);
+/* whole pipe: analysis -> beamformer (+post-filter) -> synthesis */
+int btkb_run(btkb_pipeline* p, int do_synthesis);
+int btkb_synchronize(btkb_pipeline* p);
+
+/* ---- results (all synchronise the stream) ------------------------------------------------------------------- */
+int btkb_num_frames(const btkb_pipeline* p);        /* T of the longest utterance in the batch */
+int btkb_num_frames_of(const btkb_pipeline* p, int u);
+int btkb_num_blocks(const btkb_pipeline* p);        /* synthesis output blocks (T - pd_S), D samples each */
+/* beamformed subband spectra [U][T][K] complex64 (bins above M/2 are conjugate mirrors, beamformer.cc:1142-1149) */
+int btkb_fetch_subband(btkb_pipeline* p, float* out);
+/* resynthesised signal float32 [U][blocks*D] */
+int btkb_fetch_time(btkb_pipeline* p, float* out);
+/* snapshots X [U][T][C][K] complex64 (the SnapShotArray contents per frame) */
+int btkb_fetch_snapshots(btkb_pipeline* p, float* out);
+/* per-utterance statistics [U][3] float64: sum of squared output samples, frames, NLMS update count
+ * (test_online_beamforming.py:208,336-337; pybeamformer.py:751) */
+int btkb_fetch_stats(btkb_pipeline* p, double* out);
+int btkb_get_weights(btkb_pipeline* p, float* out);            /* [U][K][C] complex64: wq or wmvdr */
+int btkb_get_active_weights(btkb_pipeline* p, float* out);     /* [U][K][C-1] complex64 (NLMS: waH of pybeamformer.py) */
+int btkb_get_covariance(btkb_pipeline* p, float* out);         /* [U][K][C][C] complex64 */
+int btkb_get_postfilter_weights(btkb_pipeline* p, float* out); /* [U][T][K] float32 Zelinski gains (wp1_) */
+
+/* ---- measurement -------------------------------------------------------------------------------------------- */
+/* device time (ms, CUDA events on the pipeline stream) of the last run: total and per kernel
+ * out[0] total, out[1] analysis, out[2] per-bin beamformer, out[3] synthesis, out[4] launches */
+int btkb_last_timing(btkb_pipeline* p, float* out5);
+/* device pointers for zero-copy consumers (torch tensors via from_dlpack / data_ptr): X, Y, time */
+int btkb_device_pointers(btkb_pipeline* p, void** X, void** Y, void** time_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTKB_H */
