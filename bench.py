@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — multichannel subband frames/s through the GSC pipe (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3                      # our arm, 1 GPU
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...    # our arm, N GPUs (utterance shards, weak scaling)
+  python bench.py --impl reference --gpus 1 --steps K --warmup W      # the reference's own CPU path on the host cores
+
+One "step" = one pass of the hot path (OverSampledDFT analysis -> GSC with NLMS sidelobe canceller -> OverSampledDFT
+synthesis) over one batch of synthetic utterances.  Workload at every N: BASELINE.json configs[1] per GPU — 8 mics,
+M = 512 subbands (m = 4, r = 1, delay-compensation type 2), 256 synthetic 5 s utterances (SURVEY.md §8d generator),
+81 152 frames per GPU per step.  One frame = one beamformed output frame of one utterance.
+
+`value`    device-timed (CUDA events on the pipeline stream), inputs already resident in HBM.
+`e2e`      same metric through the public C-ABI with HOST buffers: pinned H2D of the step's samples + delays, the three
+           kernels, D2H of the resynthesised signal and statistics inside the timed region.
+`roofline` dominant kernel (largest share of the step): algorithmic bytes per frame (SURVEY.md §8d / DESIGN.md §5) x
+           frames / its CUDA-event time, against the measured HBM copy peak in MEASURED_PEAKS.json.
+`cpu_baseline` the reference's own C++ (oracle/_ref, compiled unmodified; NLMS restated in C++) on a bounded sample of
+           the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 16000.0
+CFG = dict(C=8, M=512, m=4, r=1, U=256, n=80000)
+LMS = dict()  # unit_test/confs/gsclms.json defaults (min_frames 128, slowdown_after 4096, ...)
+METRIC = "multichannel subband frames/sec through GSC pipe"
+
+
+def frames_per_utt(n, M, m, r):
+    D = M >> r
+    R = 1 << r
+    return -(-n // D) + m * R // 2
+
+
+def load_proto(M):
+    p = np.load(os.path.join(ROOT, "tests", "golden", "prototype_M%d_m4_r1.npz" % M))
+    return p["h"], p["g"]
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.stop_flag = False; self.rows = []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    first, count, C, n, M, m, r = args
+    from oracle import ref
+    from distant_speech_recognition_b200 import synthetic
+    h, g = load_proto(M)
+    xs = [synthetic.make_utterance(first + i, C, n)[:2] for i in range(count)]
+    t0 = time.perf_counter()
+    frames = 0
+    for x, d in xs:
+        res = ref.beamform(x, h, g, d, M, m, r, bf_kind=ref.BF_GSC_LMS, do_synthesis=True, want_subband=False)
+        frames += int(res["stats"][1])
+    return frames, time.perf_counter() - t0
+
+
+def cpu_reference(utts_per_core, cores, seed0=0):
+    """The reference's own CPU implementation of the path on `cores` host cores (one utterance range per process,
+    the reference is single-threaded).  Returns (frames/s, frames, seconds, cores)."""
+    import multiprocessing as mp
+    c = CFG
+    jobs = [(seed0 + i * utts_per_core, utts_per_core, c["C"], c["n"], c["M"], c["m"], c["r"]) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+        wall = res[0][1]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+        wall = max(r[1] for r in res)  # processing time only (input synthesis excluded), slowest worker
+    frames = sum(r[0] for r in res)
+    return frames / wall, frames, wall, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    upc = 2  # utterances per core per step: bounded sample
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference(1, cores)
+    vals, fr, secs = [], 0, 0.0
+    for k in range(args.steps):
+        v, f, s, _ = cpu_reference(upc, cores, seed0=k * upc * cores)
+        vals.append(v); fr += f; secs += s
+    value = fr / secs
+    c = CFG
+    T = frames_per_utt(c["n"], c["M"], c["m"], c["r"])
+    sample = "%d utterances (%d per core x %d cores) of configs[1] per step, %d steps" % (upc * cores, upc, cores, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "xrt": value * (c["n"] / FS) / T,
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    c = CFG
+    return {"workload": "configs[1]: 8-mic SubbandGSC (NLMS sidelobe canceller), 512 subbands, batch of 256 synthetic 5 s utterances per GPU",
+            "channels": c["C"], "subbands": c["M"], "m": c["m"], "r": c["r"], "utterances_per_gpu": c["U"], "samples_per_utterance": c["n"],
+            "frames_per_utterance": frames_per_utt(c["n"], c["M"], c["m"], c["r"]), "global_utterances": c["U"] * n_gpus,
+            "parallelism": "utterance shards x%d (no data-path collective)" % n_gpus,
+            "l2_policy": "inputs (655 MB samples, 1.33 GB snapshots per step) exceed the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------- our arm
+def make_inputs(rank):
+    from distant_speech_recognition_b200 import synthetic
+    import multiprocessing as mp
+    c = CFG
+    first = rank * c["U"]
+    procs = min(os.cpu_count() or 1, 8)
+    chunks = [(first + i * (c["U"] // procs), c["U"] // procs) for i in range(procs)] if c["U"] % procs == 0 else [(first, c["U"])]
+    with mp.get_context("fork").Pool(len(chunks)) as pool:
+        parts = pool.starmap(_gen_chunk, [(a, b, c["C"], c["n"]) for a, b in chunks])
+    x = np.concatenate([p[0] for p in parts]); d = np.concatenate([p[1] for p in parts])
+    return x, d
+
+
+def _gen_chunk(first, count, C, n):
+    from distant_speech_recognition_b200 import synthetic
+    return synthetic.make_batch(count, C, n, first=first)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from distant_speech_recognition_b200 import _capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or _capi.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c = CFG
+    U, C, n, M, m, r = c["U"], c["C"], c["n"], c["M"], c["m"], c["r"]
+    T = frames_per_utt(n, M, m, r)
+    frames_step = U * T
+    h, g = load_proto(M)
+
+    x_np, delays = make_inputs(rank)
+    x_pin = torch.from_numpy(x_np).pin_memory()
+    del x_np
+    pipe = _capi.Pipeline(C, M, m, r, beamformer=_capi.BF_GSC_LMS, lms=LMS, max_utterances=U, max_samples=n, device=local)
+    pipe.set_prototypes(h, g)
+    pipe.set_delays(delays)
+    nb = (T - m * (1 << r) // 2) * (M >> r)
+    out_pin = torch.empty((U, nb), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: inputs in HBM before the timed region
+    pipe.submit_pointer(x_pin.data_ptr(), U, n)
+    pipe.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        pipe.run(True)
+    pipe.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    ks = {"analysis_ms": 0.0, "perbin_ms": 0.0, "synthesis_ms": 0.0}
+    launches = 0
+    barrier()
+    tot_ms = 0.0
+    for _ in range(args.steps):
+        pipe.run(True)
+        t = pipe.last_timing()  # CUDA events recorded on the pipeline stream around the step and around each kernel
+        tot_ms += t["total_ms"]; launches += t["launches"]
+        for k in ks:
+            ks[k] += t[k]
+    barrier()
+    # ---- end-to-end arm through the public C-ABI with host buffers
+    for _ in range(2):
+        pipe.submit_pointer(x_pin.data_ptr(), U, n); pipe.set_delays(delays); pipe.run(True); pipe.fetch_time_into(out_pin.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe.submit_pointer(x_pin.data_ptr(), U, n)
+        pipe.set_delays(delays)
+        pipe.run(True)
+        pipe.fetch_time_into(out_pin.data_ptr())
+        stats = pipe.fetch_stats()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    dev_s = tot_ms / 1000.0
+    if world > 1:
+        tt = torch.tensor([dev_s, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(tt[0]), float(tt[1])
+        # the single end-of-run exchange of the path: per-utterance statistics gathered to every rank
+        st = torch.from_numpy(stats).cuda()
+        gathered = [torch.empty_like(st) for _ in range(world)]
+        dist.all_gather(gathered, st)
+        stats_all = torch.cat(gathered).cpu().numpy()
+    else:
+        stats_all = stats
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * frames_step * args.steps / dev_s
+    e2e = world * frames_step * args.steps / e2e_s
+    peak, peak_src = hbm_peak()
+    K = M // 2 + 1; D = M >> r
+    alg = {"analysis_ms": C * D * 4 + C * K * 8, "perbin_ms": (C + 1) * K * 8, "synthesis_ms": K * 8 + D * 4}
+    dom = max(ks, key=lambda k: ks[k])
+    kname = {"analysis_ms": "k_analysis", "perbin_ms": "k_perbin<8,LMS>", "synthesis_ms": "k_synthesis"}[dom]
+    achieved = alg[dom] * frames_step * args.steps / (ks[dom] / 1000.0) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(kname)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "xrt": value * (n / FS) / T, "config": workload_config(world),
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(U * C * n * 4 + delays.nbytes), "d2h_bytes_per_step": int(out_pin.numel() * 4 + stats.nbytes),
+                "ms_per_step": 1000.0 * e2e_s / args.steps},
+        "gpu_launches": int(launches),
+        "kernel_ms_per_step": {k: v / args.steps for k, v in ks.items()},
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_frame": alg[dom],
+                     "all_kernels_frac": {k: alg[k] * frames_step * args.steps / (ks[k] / 1000.0) / 1e9 / peak for k in ks if ks[k] > 0}},
+        "clocks": sampler.summary(),
+        "stats_check": {"utterances": int(stats_all.shape[0]), "frames": float(stats_all[:, 1].sum()), "nlms_updates": float(stats_all[:, 2].sum())},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, f, s, cores = cpu_reference(2, os.cpu_count() or 1)
+        v1, f1, s1, _ = cpu_reference(4, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
+                                "sample": "%d utterances of configs[1] (2 per core, %d processes; reference C++ via oracle/_ref, NLMS restated in C++), %.1f s" % (2 * cores, cores, s),
+                                "single_core_value": v1, "xrt": v * (n / FS) / T}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--utterances", type=int, default=None, help="override utterances per GPU (default 256 = configs[1])")
+    args = ap.parse_args()
+    if args.utterances:
+        CFG["U"] = args.utterances
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

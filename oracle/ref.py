@@ -119,7 +119,7 @@ def mvdr_weights(M, C, samplerate, delays, R=None, mpos=None, sspeed=343740.0, m
 
 def beamform(samples, h, g, delays, M, m=4, r=1, dct=2, samplerate=16000.0, bf_kind=BF_DS, wa=None, mpos=None,
              pf=None, mvdr_mu=1.0e-4, sspeed=343740.0, smi_label=(1.0, -1.0), smi_energy_threshold=10.0, lms=None,
-             do_synthesis=True):
+             do_synthesis=True, want_subband=True):
     """Run the reference pipe on one utterance.  samples float32 [C][n].
     Returns dict(Y=[T][M] complex128, time=float32[nb*D], cov, w, stats)."""
     from . import restate
@@ -142,7 +142,7 @@ def beamform(samples, h, g, delays, M, m=4, r=1, dct=2, samplerate=16000.0, bf_k
                     lms_min_frames=lp["min_frames"], lms_slowdown_after=lp["slowdown_after"],
                     do_synthesis=1 if do_synthesis else 0)
     Tcap = _num_frames(n, M, m, r, dct) + 8
-    Y = np.zeros((Tcap, M), np.complex128)
+    Y = np.zeros((Tcap, M), np.complex128) if want_subband else None
     out_time = np.zeros((Tcap * D,), np.float32)
     nblocks = ct.c_int(0)
     cov = np.zeros((K, C, C), np.complex128) if bf_kind == BF_SMI_MVDR else None
@@ -156,7 +156,7 @@ def beamform(samples, h, g, delays, M, m=4, r=1, dct=2, samplerate=16000.0, bf_k
     T = lib().ref_beamform(ct.byref(cfg), _p(samples, ct.c_float), n, _p(h, ct.c_double), _p(g, ct.c_double), _p(delays, ct.c_double),
                            _p(wa_p, ct.c_double), _p(mp, ct.c_double), _p(Y, ct.c_double), Tcap, _p(out_time, ct.c_float), Tcap,
                            ct.byref(nblocks), _p(cov, ct.c_double), _p(w, ct.c_double), _p(stats, ct.c_double))
-    res = dict(Y=Y[:T].copy(), time=out_time[:nblocks.value * D].copy(), cov=cov, stats=stats)
+    res = dict(Y=None if Y is None else Y[:T].copy(), time=out_time[:nblocks.value * D].copy(), cov=cov, stats=stats)
     if bf_kind == BF_GSC_LMS:
         res["w"] = w.reshape(-1)[:K * (C - 1)].reshape(K, C - 1).copy()
     else:

@@ -476,12 +476,18 @@ int ref_beamform(const ref_config* cfg, const float* samples, int n, const doubl
       // second pass for the subband tap (streams are deterministic): rebuild is simpler than tapping inside the pull
     }
     // subband output pass (fresh pull when synthesis consumed the stream: reset everything)
-    if (cfg->do_synthesis) tail->reset();
-    for (;;) {
-      const gsl_vector_complex* Y;
-      try { Y = tail->next(); } catch (jiterator_error& e) { break; }
-      if (T < T_cap && Y_out) memcpy(Y_out + (size_t)2 * T * M, Y->data, sizeof(double) * 2 * M);
-      T++;
+    if (cfg->do_synthesis && Y_out == NULL) {
+      // timing mode (bench.py): one pass only; frames = blocks + synthesis processing delay (modulated.cc:246-264)
+      const int R = 1 << r;
+      T = nb + ((dct == 1) ? m * R - 1 : (dct == 2) ? m * R / 2 : 2 * m - 1);
+    } else {
+      if (cfg->do_synthesis) tail->reset();
+      for (;;) {
+        const gsl_vector_complex* Y;
+        try { Y = tail->next(); } catch (jiterator_error& e) { break; }
+        if (T < T_cap && Y_out) memcpy(Y_out + (size_t)2 * T * M, Y->data, sizeof(double) * 2 * M);
+        T++;
+      }
     }
     if (cfg->bf_kind == 4) {
       n_updates = lms->ttl_updates();
