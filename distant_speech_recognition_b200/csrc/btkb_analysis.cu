@@ -20,11 +20,12 @@
 // HBM layout written: X[t][c][g], g = u K + k (complex64), row pitch Gp; E[t][u] = |x0^H x0| / M.
 #include "btkb_internal.h"
 #include "btkb_fft.cuh"
+#include <cstdlib>
 
 namespace btkb {
 
 template <int M, int MT, int FR, int G>
-__global__ void __launch_bounds__(G*(M / 8)) k_analysis(AnalysisArgs a) {
+__global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) {
   using Plan = FftPlan<M>;
   constexpr int NT = Plan::NT;
   constexpr int R0 = Plan::R0;
@@ -150,14 +151,169 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis(AnalysisArgs a) {
   }
 }
 
-template <int M, int MT>
-static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path (r = 1, i.e. D = M/2, compile-time tap count MT): each group of NT threads produces TWO consecutive frames
+// per iteration.  Consecutive frames are D = 4 NT samples apart and a thread's polyphase indices are {tg + NT q}, so 28
+// of the 32 samples frame t+1 needs are the ones the same thread already loaded for frame t: 36 shared-memory loads feed
+// 64 (x2 channels) MACs.  The two transforms then advance pass by pass together (independent instruction streams, one
+// in-place buffer each, every barrier covers two transforms).
+template <int M, int MT, int FR, int G>
+__global__ void __launch_bounds__(G*(M / 8)) k_analysis_r1(AnalysisArgs a) {
   using Plan = FftPlan<M>;
-  constexpr int FR = 16;
+  constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0, P = Plan::P;
+  constexpr int D = M / 2, SH = 4;
+  static_assert(FR % (2 * G) == 0, "tile must hold whole frame pairs per group");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tile = blockIdx.x, pair = blockIdx.y, u = blockIdx.z;
+  const int tid = threadIdx.x, grp = tid / NT, tg = tid % NT;
+  constexpr int W = (FR - 1) * D + MT * M;
+  // the two channels are staged as separate planes (16-byte cp.async chunks land without a register round trip)
+  float* xsa = reinterpret_cast<float*>(smem_raw);                    // [W] channel a
+  float* xsb = xsa + W;                                               // [W] channel b
+  float2* fbuf = reinterpret_cast<float2*>(xsb + W);                  // [G][2][BUF]
+  float* red = reinterpret_cast<float*>(fbuf + G * 2 * Plan::BUF);    // [G][2][NW]
+  float2* buf0 = fbuf + (grp * 2 + 0) * Plan::BUF;
+  float2* buf1 = fbuf + (grp * 2 + 1) * Plan::BUF;
+
+  const int t0 = tile * FR;
+  const int ca = 2 * pair, cb = 2 * pair + 1;
+  const bool has_b = cb < a.C;
+  const int len = a.lengths[u];
+  const long long w0 = (long long)(a.laN + t0 + 1) * D - (long long)MT * M;
+  const float* xa = a.x + ((size_t)u * a.C + ca) * a.n_stride;
+  const float* xb = a.x + ((size_t)u * a.C + (has_b ? cb : ca)) * a.n_stride;
+  // Asynchronous 16-byte copies with zero fill (cp.async ... src-size): every thread puts ~W/(2 NT G) chunks per channel
+  // in flight at once, samples outside [0, len) arrive as zeros (w0 and W are multiples of 4, rows are 16 B aligned).
+  static_assert(W % 4 == 0, "tile length must be a multiple of 4 samples");
+  for (int w = 4 * tid; w < W; w += 4 * G * NT) {
+    const long long s = w0 + w;
+    long long rem = (long long)len - s;                         // valid samples from s on
+    int nb = (s < 0 || rem <= 0) ? 0 : (rem >= 4 ? 16 : (int)rem * 4);
+    const float* pa = (nb > 0) ? xa + s : xa;
+    const float* pb = (nb > 0) ? xb + s : xb;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xsa + w)), "l"(pa), "r"(nb) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xsb + w)), "l"(pb), "r"(has_b ? nb : 0) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // slot(q): register slot of polyphase index i_q = tg + NT q  (q = b + r NB, slot = b R0 + r)
+#define BTKB_SLOT(q) (((q) % NB) * R0 + (q) / NB)
+  float hreg[8 * MT];
+#pragma unroll
+  for (int q = 0; q < 8; q++)
+#pragma unroll
+    for (int k = 0; k < MT; k++) hreg[BTKB_SLOT(q) * MT + k] = __ldg(a.h + (tg + NT * q) + k * M);
+  FftTwiddles<M, +1> tw;
+  tw.init(tg);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  constexpr int K = M / 2 + 1;
+  constexpr int NW = (NT + 31) / 32;
+  for (int f0 = 0; f0 < FR; f0 += 2 * G) {
+    const int f = f0 + 2 * grp;
+    const int ta = t0 + f, tb = ta + 1;
+    const bool act0 = ta < a.T, act1 = tb < a.T;
+    float2 v0[8], v1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { v0[i] = make_float2(0.f, 0.f); v1[i] = make_float2(0.f, 0.f); }
+    if (act0) {
+      const int base = f * D + MT * M - 1;
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+#pragma unroll
+        for (int k = 0; k < MT; k++) {
+          const float2 s = make_float2(xsa[base - (tg + NT * q) - k * M], xsb[base - (tg + NT * q) - k * M]);
+          const float h0 = hreg[BTKB_SLOT(q) * MT + k];
+          v0[BTKB_SLOT(q)].x = fmaf(h0, s.x, v0[BTKB_SLOT(q)].x);
+          v0[BTKB_SLOT(q)].y = fmaf(h0, s.y, v0[BTKB_SLOT(q)].y);
+          constexpr int dummy = 0; (void)dummy;
+          const int q1 = (q + SH >= 8) ? q + SH - 8 : q + SH;
+          const int k1 = (q + SH >= 8) ? k + 1 : k;
+          if (k1 < MT) {
+            const float h1 = hreg[BTKB_SLOT(q1) * MT + k1];
+            v1[BTKB_SLOT(q1)].x = fmaf(h1, s.x, v1[BTKB_SLOT(q1)].x);
+            v1[BTKB_SLOT(q1)].y = fmaf(h1, s.y, v1[BTKB_SLOT(q1)].y);
+          }
+        }
+#pragma unroll
+      for (int q = 0; q < SH; q++) {  // the D new samples of frame t+1 (tap block k = 0)
+        const float2 s = make_float2(xsa[base + D - (tg + NT * q)], xsb[base + D - (tg + NT * q)]);
+        const float h1 = hreg[BTKB_SLOT(q) * MT + 0];
+        v1[BTKB_SLOT(q)].x = fmaf(h1, s.x, v1[BTKB_SLOT(q)].x);
+        v1[BTKB_SLOT(q)].y = fmaf(h1, s.y, v1[BTKB_SLOT(q)].y);
+      }
+    }
+    // ---- two transforms, pass by pass, in place (one buffer each)
+    fft_first_pass<M, +1>(v0, buf0, tg);
+    fft_first_pass<M, +1>(v1, buf1, tg);
+    __syncthreads();
+    {
+      int Ns = R0;
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) { v0[r] = buf0[pidx(tg + r * (M / 8))]; v1[r] = buf1[pidx(tg + r * (M / 8))]; }
+        __syncthreads();
+#pragma unroll
+        for (int r = 1; r < 8; r++) { v0[r] = cmul(v0[r], tw.tw[p][r - 1]); v1[r] = cmul(v1[r], tw.tw[p][r - 1]); }
+        dft8<+1>(v0);
+        dft8<+1>(v1);
+        stockham_store<8>(buf0, v0, tg, Ns);
+        stockham_store<8>(buf1, v1, tg, Ns);
+        __syncthreads();
+        Ns *= 8;
+      }
+    }
+    // ---- untangle the channel pair, write snapshots, channel-0 energy
+    float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+    for (int q = 0; q <= 4; q++) {
+      const int k = tg + q * NT;
+      if (q == 4 && tg != 0) break;
+      const float wgt = (k == 0 || k == M / 2) ? 1.f : 2.f;
+      const int km = (M - k) & (M - 1);
+      if (act0) {
+        const float2 zk = buf0[pidx(k)], zm = buf0[pidx(km)];
+        const float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        a.X[((size_t)ta * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
+        if (has_b) a.X[((size_t)ta * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
+        e0 = fmaf(wgt, fmaf(A.x, A.x, A.y * A.y), e0);
+      }
+      if (act1) {
+        const float2 zk = buf1[pidx(k)], zm = buf1[pidx(km)];
+        const float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        a.X[((size_t)tb * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
+        if (has_b) a.X[((size_t)tb * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
+        e1 = fmaf(wgt, fmaf(A.x, A.x, A.y * A.y), e1);
+      }
+    }
+    if (pair == 0 && a.E != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { e0 += __shfl_xor_sync(0xffffffffu, e0, o); e1 += __shfl_xor_sync(0xffffffffu, e1, o); }
+      if ((tg & 31) == 0) { red[(grp * 2 + 0) * NW + tg / 32] = e0; red[(grp * 2 + 1) * NW + tg / 32] = e1; }
+      __syncthreads();
+      if (tg == 0) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { s0 += red[(grp * 2 + 0) * NW + w]; s1 += red[(grp * 2 + 1) * NW + w]; }
+        if (act0) a.E[(size_t)ta * a.U + u] = s0 / (float)M;
+        if (act1) a.E[(size_t)tb * a.U + u] = s1 / (float)M;
+      }
+    }
+    __syncthreads();  // untangle reads done before the next iteration's first pass overwrites the buffers
+  }
+#undef BTKB_SLOT
+}
+
+template <int M, int MT, int FR>
+static cudaError_t launch_analysis_r1(const AnalysisArgs& a, cudaStream_t st) {
+  using Plan = FftPlan<M>;
   constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
-  const int m = (MT > 0) ? MT : a.m;
-  size_t smem = sizeof(float2) * ((size_t)(FR - 1) * a.D + (size_t)m * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 4;
-  auto kern = k_analysis<M, MT, FR, G>;
+  size_t smem = sizeof(float2) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * 4;
+  auto kern = k_analysis_r1<M, MT, FR, G>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((a.T + FR - 1) / FR, (a.C + 1) / 2, a.U);
@@ -165,9 +321,31 @@ static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <int M, int MT>
+static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
+  using Plan = FftPlan<M>;
+  constexpr int FR = 16;
+  constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
+  const int m = (MT > 0) ? MT : a.m;
+  size_t smem = sizeof(float2) * ((size_t)(FR - 1) * a.D + (size_t)m * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 4;
+  auto kern = k_analysis_generic<M, MT, FR, G>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((a.T + FR - 1) / FR, (a.C + 1) / 2, a.U);
+  kern<<<grid, G * Plan::NT, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+static int analysis_tile_frames() {  // tuning knob (frames per CTA tile): BTKB_ANALYSIS_FR=8|16 (default 16)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BTKB_ANALYSIS_FR"); v = (e && atoi(e) == 8) ? 8 : 16; }
+  return v;
+}
+
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st) {
 #define BTKB_CASE(MM)                                                                  \
   case MM:                                                                             \
+    if (a.m == 4 && a.D == MM / 2) return (analysis_tile_frames() == 8) ? launch_analysis_r1<MM, 4, 8>(a, st) : launch_analysis_r1<MM, 4, 16>(a, st); \
     return (a.m == 4) ? launch_analysis_m<MM, 4>(a, st) : launch_analysis_m<MM, 0>(a, st);
   switch (a.M) {
     BTKB_CASE(256) BTKB_CASE(512) BTKB_CASE(1024) BTKB_CASE(2048)

@@ -20,14 +20,17 @@
 // blocking matrix of v (B^T v = 0, B^H B = I), carry u = waH B^T (C-vector) instead of waH:
 //   waH.Z = u.x ;  conj(Z) B^T = conj(x - C Yc v) ;  ||u~|| = ||wa~||.
 // The (C-1) x C product per bin-frame disappears; waH = u conj(B) is recovered at export time (btkb_weights.cu).
+#include <cuda.h>           // CUtensorMap (the encode entry point is fetched at run time; libcuda is not linked)
 #include "btkb_internal.h"
 #include "btkb_fft.cuh"   // complex helpers
 #include "../../include/btkb.h"
 
 namespace btkb {
 
-constexpr int TILE = 128;   // chains (threads) per CTA
-constexpr int STAGES = 4;   // frames in flight per CTA
+constexpr int TILE = 64;    // chains (threads) per CTA: 1028 CTAs at configs[1] = 6.95 per SM (balanced single wave)
+constexpr int FCH = 2;      // frames per ring slot: one 2-D TMA box is [FCH*C rows][TILE chains]
+constexpr int STAGES = 4;   // ring slots per CTA (3 slots = 6 frames in flight)
+constexpr int NWARP = TILE / 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -50,47 +53,102 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 2-D tiled TMA load: box {2*TILE floats, FCH*C rows} of the [T*C][2*Gp] float view of X at (col0, row0) -> smem
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int col0, int row0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(col0), "r"(row0), "r"(smem_u32(bar)) : "memory");
+}
+
+// Ring of STAGES slots; a slot holds FCH consecutive frames of the CTA's mic x bin tile, [FCH][C][TILE] complex64, and is
+// filled by ONE tensor-map TMA instruction (rows (t, c) of X are consecutive, so FCH frames x C channels is a dense 2-D
+// box; rows past the end of the batch are zero-filled by the TMA unit).  full[s]: armed with the slot's byte count,
+// completed by the TMA.  empty[s]: one arrival per warp once all its lanes hold the slot's last frame in registers.
+// The producer (lane 0 of warp 0) refills the previous slot while the CTA works on the current one, so warps never meet
+// at a CTA-wide barrier.
 template <int C>
 struct TileRing {
-  float2* stage;     // [STAGES][C][TILE]
+  float2* stage;     // [STAGES][FCH][C][TILE]
   uint64_t* full;    // [STAGES]
-  const float2* X; int Gp, g0, T;
-  __device__ __forceinline__ void init(unsigned char* smem, const float2* X_, int Gp_, int g0_, int T_) {
+  uint64_t* empty;   // [STAGES]
+  const CUtensorMap* tm; int g0, NS;   // NS = number of slots' worth of frames = ceil(T / FCH)
+  static constexpr uint32_t SLOT_BYTES = FCH * C * TILE * sizeof(float2);
+  __device__ __forceinline__ void init(unsigned char* smem, const CUtensorMap* tm_, int g0_, int T_) {
     stage = reinterpret_cast<float2*>(smem);
-    full = reinterpret_cast<uint64_t*>(smem + sizeof(float2) * STAGES * C * TILE);
-    X = X_; Gp = Gp_; g0 = g0_; T = T_;
+    full = reinterpret_cast<uint64_t*>(smem + (size_t)SLOT_BYTES * STAGES);
+    empty = full + STAGES;
+    tm = tm_; g0 = g0_; NS = (T_ + FCH - 1) / FCH;
     if (threadIdx.x == 0) {
-      for (int s = 0; s < STAGES; s++) mbar_init(full + s, 1);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+      for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, NWARP); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0)
-      for (int t = 0; t < STAGES && t < T; t++) issue(t);
+      for (int j = 0; j < STAGES - 1 && j < NS; j++) issue(j);
   }
-  // called by ONE thread: fetch frame t into slot t % STAGES
-  __device__ __forceinline__ void issue(int t) {
-    const int s = t % STAGES;
-    mbar_expect_tx(full + s, (uint32_t)(C * TILE * sizeof(float2)));
-#pragma unroll
-    for (int c = 0; c < C; c++)
-      bulk_g2s(stage + ((size_t)s * C + c) * TILE, X + ((size_t)t * C + c) * Gp + g0, (uint32_t)(TILE * sizeof(float2)), full + s);
+  // called by ONE thread: fetch frame group j (frames j*FCH ..) into slot j % STAGES
+  __device__ __forceinline__ void issue(int j) {
+    const int s = j % STAGES;
+    mbar_expect_tx(full + s, SLOT_BYTES);
+    tma_load_2d(reinterpret_cast<unsigned char*>(stage) + (size_t)s * SLOT_BYTES, tm, 2 * g0, j * FCH * C, full + s);
   }
-  // all threads: wait for frame t, copy this thread's column to registers, release the slot, refill it
-  __device__ __forceinline__ void fetch(int t, float2* x) {
-    const int s = t % STAGES;
-    mbar_wait(full + s, (uint32_t)((t / STAGES) & 1));
+  // all threads, at the first frame of group j: the producer refills the previous slot, everybody waits for this one
+  __device__ __forceinline__ void acquire(int j) {
+    if (threadIdx.x == 0 && j + STAGES - 1 < NS) {
+      if (j >= 1) mbar_wait(empty + ((j - 1) % STAGES), (uint32_t)(((j - 1) / STAGES) & 1));
+      issue(j + STAGES - 1);
+    }
+    mbar_wait(full + (j % STAGES), (uint32_t)((j / STAGES) & 1));
+  }
+  __device__ __forceinline__ void load(int j, int f, float2* x) const {
+    const float2* base = stage + ((size_t)(j % STAGES) * FCH + f) * C * TILE + threadIdx.x;
 #pragma unroll
-    for (int c = 0; c < C; c++) x[c] = stage[((size_t)s * C + c) * TILE + threadIdx.x];
-    __syncthreads();  // every thread has its copy: the slot may be overwritten by the async proxy
-    if (threadIdx.x == 0 && t + STAGES < T) issue(t + STAGES);
+    for (int c = 0; c < C; c++) x[c] = base[(size_t)c * TILE];
+  }
+  // all threads, after loading the last frame of group j into registers
+  __device__ __forceinline__ void release(int j) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty + (j % STAGES));
+  }
+  // frame t -> registers (wraps acquire / load / release)
+  __device__ __forceinline__ void fetch(int t, int T, float2* x) {
+    const int j = t / FCH, f = t % FCH;
+    if (f == 0) acquire(j);
+    load(j, f, x);
+    if (f == FCH - 1 || t == T - 1) release(j);
   }
 };
 
 constexpr int MODE_STATIC = 0, MODE_LMS = 1;
 
+// FMA-only complex multiply-accumulate (4 FFMA each, no separate adds)
+__device__ __forceinline__ void cmac(float2& acc, float2 a, float2 b) {        // acc += a b
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cmac_conj(float2& acc, float2 a, float2 b) {   // acc += a conj(b)
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.y, b.x, acc.y); acc.y = fmaf(-a.x, b.y, acc.y);
+}
+// sum_c a[c] b[c] (or a[c] conj(b[c])) with two independent accumulators (halves the dependent FMA chain)
+template <int C, bool CONJ>
+__device__ __forceinline__ float2 cdot(const float2* a, const float2* b) {
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < C; c += 2) {
+    if (CONJ) { cmac_conj(s0, a[c], b[c]); if (c + 1 < C) cmac_conj(s1, a[c + 1], b[c + 1]); }
+    else { cmac(s0, a[c], b[c]); if (c + 1 < C) cmac(s1, a[c + 1], b[c + 1]); }
+  }
+  return make_float2(s0.x + s1.x, s0.y + s1.y);
+}
+
 template <int C, int MODE, int PF>
-__global__ void __launch_bounds__(TILE) k_perbin(PerBinArgs a) {
+__global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int g0 = blockIdx.x * TILE;
   const int g = g0 + threadIdx.x;
@@ -101,7 +159,7 @@ __global__ void __launch_bounds__(TILE) k_perbin(PerBinArgs a) {
   const int Tu = valid ? frames_of(len, a.D, a.laN, a.pdA) : 0;
 
   TileRing<C> ring;
-  ring.init(smem_raw, a.X, a.Gp, g0, a.T);
+  ring.init(smem_raw, &tmX, g0, a.T);
 
   // ---- per-chain constants
   float2 w[C];     // static: effective weights (wq - wl, DC: wq); LMS: v = array manifold (wq)
@@ -137,46 +195,49 @@ __global__ void __launch_bounds__(TILE) k_perbin(PerBinArgs a) {
 
   float e_next = 0.f;
   if (MODE == MODE_LMS && a.T > 0) e_next = __ldg(a.E + u);
+  int slow_cnt = a.lms.slowdown_after + 1;  // first halving at t == slowdown_after
+  const float one_m_beta = 1.0f - a.lms.beta;
+  const float inv_sil = 1.0f / a.lms.sil_thresh;
 
   for (int t = 0; t < a.T; t++) {
     float2 x[C];
-    ring.fetch(t, x);
+    ring.fetch(t, a.T, x);
     float energy = e_next;
     if (MODE == MODE_LMS && t + 1 < a.T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
 
     // upper branch: Yc = w^H x
-    float2 y = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < C; c++) { float2 p = cmulc(x[c], w[c]); y.x += p.x; y.y += p.y; }
+    float2 y = cdot<C, true>(x, w);
     const bool live = t < Tu;
 
     if (MODE == MODE_LMS) {
       // pybeamformer.py:665-734 with isamp == t
-      if (t > 0 && (t % a.lms.slowdown_after) == 0) gamma *= 0.5f;
-      const bool adapt = energy > (Eavg / a.lms.sil_thresh);
-      float nx = 0.f;
+      if (--slow_cnt == 0) { gamma *= 0.5f; slow_cnt = a.lms.slowdown_after; }  // isamp > 0 and isamp % slowdown_after == 0
+      const bool adapt = energy > (Eavg * inv_sil);
+      float nx0 = 0.f, nx1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; c++) nx = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, nx));
-      float sub = (t > 0) ? fmaf(se, a.lms.beta, (1.0f - a.lms.beta) * nx) : nx;
+      for (int c = 0; c < C; c++) { nx0 = fmaf(x[c].x, x[c].x, nx0); nx1 = fmaf(x[c].y, x[c].y, nx1); }
+      const float nx = nx0 + nx1;
+      float sub = (t > 0) ? fmaf(se, a.lms.beta, one_m_beta * nx) : nx;
       sub = fmaxf(sub, a.lms.energy_floor);
       if (adapt && live) {
-        float2 ux = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < C; c++) { float2 p = cmul(uw[c], x[c]); ux.x += p.x; ux.y += p.y; }
+        const float2 ux = cdot<C, false>(uw, x);
         const float2 epa = csub(y, ux);
         const float alphaK = gamma / sub;
         const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
         const float2 ea = make_float2(epa.x * alphaK, epa.y * alphaK);
-        const float leak = (a.lms.regularization_param > 0.f) ? alphaK * a.lms.regularization_param : 0.f;
-        float n2 = 0.f;
+        const float keep = (a.lms.regularization_param > 0.f) ? 1.0f - alphaK * a.lms.regularization_param : 1.0f;
+        float n20 = 0.f, n21 = 0.f;
 #pragma unroll
         for (int c = 0; c < C; c++) {
-          float2 q = csub(x[c], cmul(cy, w[c]));      // (Q x)_c = x_c - C Yc v_c
-          float2 d = cmulc(ea, q);                    // e a conj(q)
-          float2 un = make_float2(uw[c].x + d.x - leak * uw[c].x, uw[c].y + d.y - leak * uw[c].y);
-          uw[c] = un;
-          n2 = fmaf(un.x, un.x, fmaf(un.y, un.y, n2));
+          // (Q x)_c = x_c - C Yc v_c ;  u~_c = (1 - a reg) u_c + a e conj(q_c)
+          const float qx = fmaf(-cy.x, w[c].x, fmaf(cy.y, w[c].y, x[c].x));
+          const float qy = fmaf(-cy.x, w[c].y, fmaf(-cy.y, w[c].x, x[c].y));
+          const float unx = fmaf(ea.y, qy, fmaf(ea.x, qx, keep * uw[c].x));
+          const float uny = fmaf(-ea.x, qy, fmaf(ea.y, qx, keep * uw[c].y));
+          uw[c] = make_float2(unx, uny);
+          n20 = fmaf(unx, unx, n20); n21 = fmaf(uny, uny, n21);
         }
+        const float n2 = n20 + n21;
         if (n2 > a.lms.max_wa_l2norm) {
           const float cK = sqrtf(a.lms.max_wa_l2norm / n2);
 #pragma unroll
@@ -186,12 +247,10 @@ __global__ void __launch_bounds__(TILE) k_perbin(PerBinArgs a) {
         n_updates++;
       }
       if (t >= a.lms.min_frames) {
-        float2 ux = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < C; c++) { float2 p = cmul(uw[c], x[c]); ux.x += p.x; ux.y += p.y; }
+        const float2 ux = cdot<C, false>(uw, x);
         y = csub(y, ux);
       }
-      Eavg = fmaf(Eavg, a.lms.beta, (1.0f - a.lms.beta) * energy);
+      Eavg = fmaf(Eavg, a.lms.beta, one_m_beta * energy);
     }
 
     if (PF) {
@@ -243,14 +302,14 @@ __global__ void __launch_bounds__(TILE) k_perbin(PerBinArgs a) {
 
 // K2: R[u][k] += x x^H over the frames flagged in noise_mask (pybeamformer.py:976-982)
 template <int C>
-__global__ void __launch_bounds__(TILE) k_covariance(PerBinArgs a) {
+__global__ void __launch_bounds__(TILE) k_covariance(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int g0 = blockIdx.x * TILE;
   const int g = g0 + threadIdx.x;
   const bool valid = g < a.G;
   const int u = valid ? g / a.K : a.U - 1;
   TileRing<C> ring;
-  ring.init(smem_raw, a.X, a.Gp, g0, a.T);
+  ring.init(smem_raw, &tmX, g0, a.T);
   constexpr int NP = C * (C - 1) / 2;
   float2 off[NP > 0 ? NP : 1];
   float dg[C];
@@ -261,7 +320,7 @@ __global__ void __launch_bounds__(TILE) k_covariance(PerBinArgs a) {
   unsigned char m_next = (a.T > 0) ? a.noise_mask[u] : 0;
   for (int t = 0; t < a.T; t++) {
     float2 x[C];
-    ring.fetch(t, x);
+    ring.fetch(t, a.T, x);
     const unsigned char mk = m_next;
     if (t + 1 < a.T) m_next = a.noise_mask[(size_t)(t + 1) * a.U + u];
     if (mk) {
@@ -290,12 +349,36 @@ __global__ void __launch_bounds__(TILE) k_covariance(PerBinArgs a) {
 }
 
 template <int C>
-static size_t ring_smem() { return sizeof(float2) * STAGES * C * TILE + sizeof(uint64_t) * STAGES + 64; }
+static size_t ring_smem() { return sizeof(float2) * STAGES * FCH * C * TILE + sizeof(uint64_t) * 2 * STAGES + 64; }
+
+// Tensor map of X viewed as a 2-D float tensor [T*C rows][2*Gp floats]; box = [FCH*C rows][2*TILE floats].
+static cudaError_t make_tensor_map(CUtensorMap* tm, const PerBinArgs& a, int C) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C};
+  cuuint64_t gstride[1] = {(cuuint64_t)a.Gp * sizeof(float2)};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * TILE), (cuuint32_t)(FCH * C)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(a.X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+}
 
 template <int C>
 static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
   const size_t smem = ring_smem<C>();
   const int grid = (a.G + TILE - 1) / TILE;
+  CUtensorMap tm;
+  { cudaError_t e = make_tensor_map(&tm, a, C); if (e != cudaSuccess) return e; }
   const bool lms = a.kind == BTKB_BF_GSC_LMS;
   const bool pf = a.pf_kind == BTKB_PF_ZELINSKI;
 #define BTKB_LAUNCH(MODE_, PF_)                                                                  \
@@ -303,7 +386,7 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
     auto kern = k_perbin<C, MODE_, PF_>;                                                         \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                              \
-    kern<<<grid, TILE, smem, st>>>(a);                                                           \
+    kern<<<grid, TILE, smem, st>>>(tm, a);                                                       \
     return cudaGetLastError();                                                                   \
   } while (0)
   if (lms) { if (pf) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_LMS, 0); }
@@ -328,7 +411,10 @@ static cudaError_t launch_cov_c(const PerBinArgs& a, cudaStream_t st) {
   auto kern = k_covariance<C>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<(a.G + TILE - 1) / TILE, TILE, smem, st>>>(a);
+  CUtensorMap tm;
+  e = make_tensor_map(&tm, a, C);
+  if (e != cudaSuccess) return e;
+  kern<<<(a.G + TILE - 1) / TILE, TILE, smem, st>>>(tm, a);
   return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@
 namespace btkb {
 
 template <int M, int FB, int G>
-__global__ void __launch_bounds__(G*(M / 8)) k_synthesis(SynthesisArgs a) {
+__global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a) {
   using Plan = FftPlan<M>;
   constexpr int NT = Plan::NT;
   constexpr int R0 = Plan::R0;
@@ -120,6 +120,187 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis(SynthesisArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path (compile-time m = MT taps and R = RR = 2^r): the tile's Y rows are first staged in shared memory with
+// asynchronous 8-byte copies (zero fill for frames outside the utterance), each group transforms TWO frame pairs per
+// iteration (independent instruction streams) and writes the real sequences v back IN PLACE over the Y rows it consumed;
+// the polyphase taps a thread needs (R m per output position) live in registers for all FB blocks of the tile.
+template <int M, int FB, int G, int MT, int RR>
+__global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
+  using Plan = FftPlan<M>;
+  constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0, P = Plan::P;
+  constexpr int D = M / RR, K = M / 2 + 1;
+  constexpr int NV = FB + RR * (MT - 1) + (RR - 1);
+  constexpr int NVP = (NV + 3) & ~3;                       // multiple of 4 frames (two pairs per group iteration)
+  constexpr int ROW = ((K * 2 + 3) & ~3);                  // floats per staged row (>= 2K and >= M), 16 B multiple
+  static_assert(ROW >= M, "row must hold M reals");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tile = blockIdx.x, u = blockIdx.y;
+  const int tid = threadIdx.x, grp = tid / NT, tg = tid % NT;
+  constexpr int NTHREADS = G * NT;
+  float* rows = reinterpret_cast<float*>(smem_raw);        // [NVP][ROW]: Y (complex) on the way in, v (real) on the way out
+  float2* fbuf = reinterpret_cast<float2*>(rows + (size_t)NVP * ROW);
+  float* red = reinterpret_cast<float*>(fbuf + G * 2 * Plan::BUF);
+  float2* buf0 = fbuf + (grp * 2 + 0) * Plan::BUF;
+  float2* buf1 = fbuf + (grp * 2 + 1) * Plan::BUF;
+
+  const int len = a.lengths[u];
+  const int Tu = frames_of(len, D, a.laN, a.pdA);
+  const int nbu = max(Tu - a.pdS, 0);
+  const int t0 = tile * FB;
+  const int tau0 = t0 + a.pdS - RR * (MT - 1) - (RR - 1);
+
+  // ---- stage Y rows
+  for (int e = tid; e < NVP * K; e += NTHREADS) {
+    const int fr = e / K, k = e - fr * K;
+    const int tau = tau0 + fr;
+    const bool ok = (fr < NV) && tau >= 0 && tau < Tu;
+    const float2* src = ok ? a.Y + (size_t)tau * a.Gp + (size_t)u * K + k : a.Y;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(rows + (size_t)fr * ROW + 2 * k)), "l"(src), "r"(ok ? 8 : 0) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // polyphase taps for this thread's output positions d = tid + j NTHREADS
+  constexpr int ND = (D + NTHREADS - 1) / NTHREADS;
+  float gt[ND][RR][MT];
+#pragma unroll
+  for (int j = 0; j < ND; j++)
+#pragma unroll
+    for (int s2 = 0; s2 < RR; s2++)
+#pragma unroll
+      for (int k = 0; k < MT; k++) {
+        const int d = tid + j * NTHREADS;
+        gt[j][s2][k] = (d < D) ? __ldg(a.g + (M - 1 - (d + s2 * D)) + k * M) : 0.f;
+      }
+  FftTwiddles<M, -1> tw;
+  tw.init(tg);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- transforms: group handles frame quads (2 pairs); v overwrites the Y rows of the same frames
+  for (int q0 = 0; q0 < NVP / 4; q0 += G) {
+    const int qd = q0 + grp;
+    const bool act = qd < NVP / 4;
+    float2 v0[8], v1[8];
+    const float* ra = rows + (size_t)(4 * qd + 0) * ROW;
+    const float* rb = rows + (size_t)(4 * qd + 1) * ROW;
+    const float* rc = rows + (size_t)(4 * qd + 2) * ROW;
+    const float* rd = rows + (size_t)(4 * qd + 3) * ROW;
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+#pragma unroll
+      for (int r = 0; r < R0; r++) {
+        const int i = (tg + b * NT) + r * (M / R0);
+        const int k = (i <= M / 2) ? i : M - i;
+        const bool cj = i > M / 2;
+        const bool edge = (k == 0) || (k == M / 2);
+        float2 ya = make_float2(0.f, 0.f), yb = ya, yc = ya, yd = ya;
+        if (act) {
+          ya = *reinterpret_cast<const float2*>(ra + 2 * k); yb = *reinterpret_cast<const float2*>(rb + 2 * k);
+          yc = *reinterpret_cast<const float2*>(rc + 2 * k); yd = *reinterpret_cast<const float2*>(rd + 2 * k);
+        }
+        if (edge) { ya.y = 0.f; yb.y = 0.f; yc.y = 0.f; yd.y = 0.f; }
+        if (cj) { ya.y = -ya.y; yb.y = -yb.y; yc.y = -yc.y; yd.y = -yd.y; }
+        v0[b * R0 + r] = make_float2(ya.x - yb.y, ya.y + yb.x);
+        v1[b * R0 + r] = make_float2(yc.x - yd.y, yc.y + yd.x);
+      }
+    fft_first_pass<M, -1>(v0, buf0, tg);
+    fft_first_pass<M, -1>(v1, buf1, tg);
+    __syncthreads();   // also: every thread of every group has consumed its Y rows
+    {
+      int Ns = R0;
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) { v0[r] = buf0[pidx(tg + r * (M / 8))]; v1[r] = buf1[pidx(tg + r * (M / 8))]; }
+        __syncthreads();
+#pragma unroll
+        for (int r = 1; r < 8; r++) { v0[r] = cmul(v0[r], tw.tw[p][r - 1]); v1[r] = cmul(v1[r], tw.tw[p][r - 1]); }
+        dft8<-1>(v0);
+        dft8<-1>(v1);
+        if (p == P - 1) {
+          // last pass: natural-order element tg + r M/8 -> real parts to row a/c, imaginary parts to row b/d
+          if (act) {
+            float* wa = rows + (size_t)(4 * qd + 0) * ROW; float* wb = rows + (size_t)(4 * qd + 1) * ROW;
+            float* wc = rows + (size_t)(4 * qd + 2) * ROW; float* wd = rows + (size_t)(4 * qd + 3) * ROW;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+              const int i = tg + r * (M / 8);
+              wa[i] = v0[r].x; wb[i] = v0[r].y; wc[i] = v1[r].x; wd[i] = v1[r].y;
+            }
+          }
+        } else {
+          stockham_store<8>(buf0, v0, tg, Ns);
+          stockham_store<8>(buf1, v1, tg, Ns);
+        }
+        __syncthreads();
+        Ns *= 8;
+      }
+    }
+  }
+
+  // ---- polyphase + overlap-add (taps in registers)
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < ND; j++) {
+    const int d = tid + j * NTHREADS;
+    if (d < D) {
+      for (int tl = 0; tl < FB; tl++) {
+        const int t = t0 + tl;
+        if (t >= a.nb) break;
+        float acc = 0.f;
+        if (t < nbu) {
+#pragma unroll
+          for (int s2 = 0; s2 < RR; s2++) {
+            const int twf = t - (RR - 1 - s2);
+            float w = 0.f;
+            if (twf >= 0) {
+#pragma unroll
+              for (int k = 0; k < MT; k++) {
+                const int slot = tl + s2 - RR * k + RR * (MT - 1);
+                w = fmaf(gt[j][s2][k], rows[(size_t)slot * ROW + d + s2 * D], w);
+              }
+            }
+            acc += w;
+          }
+          if (a.gain > 0) acc *= (float)a.gain;
+        }
+        a.out[(size_t)u * a.nb_stride + (size_t)t * D + (D - 1 - d)] = acc;
+        sq = fmaf(acc, acc, sq);
+      }
+    }
+  }
+  if (a.stats != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((tid & 31) == 0) red[tid / 32] = sq;
+    __syncthreads();
+    if (tid == 0) {
+      double sum = 0.0;
+      for (int w = 0; w < (NTHREADS + 31) / 32; w++) sum += (double)red[w];
+      atomicAdd(a.stats + (size_t)u * 3, sum);
+    }
+  }
+}
+
+template <int M>
+static cudaError_t launch_synthesis_fast(const SynthesisArgs& a, cudaStream_t st) {
+  using Plan = FftPlan<M>;
+  constexpr int FB = 16, MT = 4, RR = 2;
+  constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
+  constexpr int NV = FB + RR * (MT - 1) + (RR - 1);
+  constexpr int NVP = (NV + 3) & ~3;
+  constexpr int ROW = (((M / 2 + 1) * 2 + 3) & ~3);
+  size_t smem = sizeof(float) * (size_t)NVP * ROW + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * 32;
+  auto kern = k_synthesis_fast<M, FB, G, MT, RR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (a.nb <= 0) return cudaSuccess;
+  dim3 grid((a.nb + FB - 1) / FB, a.U);
+  kern<<<grid, G * Plan::NT, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <int M>
 static cudaError_t launch_synthesis_m(const SynthesisArgs& a, cudaStream_t st) {
   using Plan = FftPlan<M>;
@@ -129,7 +310,7 @@ static cudaError_t launch_synthesis_m(const SynthesisArgs& a, cudaStream_t st) {
   const int NV = FB + R * (a.m - 1) + (R - 1);
   const int NVP = (NV + 1) & ~1;
   size_t smem = sizeof(float) * (size_t)NVP * M + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * 32;
-  auto kern = k_synthesis<M, FB, G>;
+  auto kern = k_synthesis_generic<M, FB, G>;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -141,9 +322,9 @@ static cudaError_t launch_synthesis_m(const SynthesisArgs& a, cudaStream_t st) {
 
 cudaError_t launch_synthesis(const SynthesisArgs& a, cudaStream_t st) {
   switch (a.M) {
-    case 256: return launch_synthesis_m<256>(a, st);
-    case 512: return launch_synthesis_m<512>(a, st);
-    case 1024: return launch_synthesis_m<1024>(a, st);
+    case 256: return (a.m == 4 && a.r == 1) ? launch_synthesis_fast<256>(a, st) : launch_synthesis_m<256>(a, st);
+    case 512: return (a.m == 4 && a.r == 1) ? launch_synthesis_fast<512>(a, st) : launch_synthesis_m<512>(a, st);
+    case 1024: return (a.m == 4 && a.r == 1) ? launch_synthesis_fast<1024>(a, st) : launch_synthesis_m<1024>(a, st);
     case 2048: return launch_synthesis_m<2048>(a, st);
     default: return cudaErrorInvalidValue;
   }

@@ -44,11 +44,11 @@ def test_no_cpu_fallback(lib):
 
 
 def test_kernels_are_sm100a_with_tma(lib):
-    """The shipped cubin is sm_100a and the per-bin kernel stages tiles with bulk async copies (SASS UBLKCP)."""
+    """The shipped cubin is sm_100a and the per-bin kernel stages tiles with tensor-map TMA loads (SASS UTMALDG)."""
     import shutil, subprocess
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump not available")
     out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4btkb8k_perbinILi8ELi1ELi0EEEvNS_10PerBinArgsE", LIB], capture_output=True, text=True).stdout
-    assert "UBLKCP" in sass and "SYNCS" in sass
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4btkb8k_perbinILi8ELi1ELi0EEEv14CUtensorMap_stNS_10PerBinArgsE", LIB], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass and "SYNCS" in sass
