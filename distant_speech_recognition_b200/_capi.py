@@ -33,7 +33,7 @@ class Config(ct.Structure):
     _fields_ = [("device", ct.c_int), ("channels", ct.c_int), ("fft_len", ct.c_int), ("m", ct.c_int), ("r", ct.c_int),
                 ("delay_compensation_type", ct.c_int), ("samplerate", ct.c_float), ("beamformer", ct.c_int),
                 ("postfilter", ct.c_int), ("pf_alpha", ct.c_float), ("pf_type", ct.c_int), ("pf_min_frames", ct.c_int),
-                ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int)]
+                ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int)]
 
 
 def _load():
@@ -163,6 +163,14 @@ class Pipeline:
             self._len = np.ascontiguousarray(lengths, np.int32)
             lp = self._len.ctypes.data_as(ct.POINTER(ct.c_int))
         _check(lib.btkb_submit_device(self._h, ct.cast(ct.c_void_p(dev_ptr), ct.POINTER(ct.c_float)), ct.c_int(U), ct.c_int(n), lp))
+
+    def set_subband(self, Y):
+        Y = np.ascontiguousarray(Y, np.complex64)
+        self.U = Y.shape[0]
+        _check(lib.btkb_set_subband(self._h, ct.c_int(Y.shape[0]), ct.c_int(Y.shape[1]), _fp(Y)))
+
+    def run_synthesis(self):
+        _check(lib.btkb_run_synthesis(self._h))
 
     def run(self, synthesis=True):
         _check(lib.btkb_run(self._h, ct.c_int(1 if synthesis else 0)))

@@ -65,7 +65,7 @@ void btkb_default_config(btkb_config* c) {
   c->pf_alpha = 0.6f; c->pf_type = 2; c->pf_min_frames = 0;
   c->lms.beta = 0.97f; c->lms.gamma = 0.01f; c->lms.init_diagonal_load = 1.0e6f; c->lms.regularization_param = 1.0e-4f;
   c->lms.energy_floor = 90.f; c->lms.sil_thresh = 1.0e8f; c->lms.max_wa_l2norm = 100.f; c->lms.min_frames = 128; c->lms.slowdown_after = 4096;
-  c->max_utterances = 1; c->max_samples = 160000; c->keep_snapshots = 1;
+  c->max_utterances = 1; c->max_samples = 160000; c->keep_snapshots = 1; c->synthesis_gain = 1;
 }
 
 static void fb_delays(int m, int r, int dct, bool synthesis, int* pd, int* la) {  // modulated.cc:246-264
@@ -100,7 +100,7 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   if (M < 256 || M > 2048 || (M & (M - 1))) return fail(BTKB_ERR_INVALID, "btkb_create: fft_len must be a power of two in [256, 2048]");
   if (cfg->m < 1 || cfg->m > 8 || cfg->r < 0 || (M >> cfg->r) < 32) return fail(BTKB_ERR_INVALID, "btkb_create: bad m / r");
   if (C < 1) return fail(BTKB_ERR_INVALID, "btkb_create: channels must be >= 1");
-  if (C != 2 && C != 4 && C != 8) return fail(BTKB_ERR_INVALID, "btkb_create: this build instantiates the per-bin kernel for 2, 4 and 8 channels");
+  if (C > 64) return fail(BTKB_ERR_INVALID, "btkb_create: at most 64 channels");
   if (cfg->max_utterances < 1 || cfg->max_samples < 1) return fail(BTKB_ERR_INVALID, "btkb_create: capacities must be positive");
   if (cfg->beamformer < BTKB_BF_DS || cfg->beamformer > BTKB_BF_GSC_LMS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown beamformer kind");
   if (cfg->beamformer == BTKB_BF_GSC_LMS && cfg->postfilter != BTKB_PF_NONE)
@@ -353,6 +353,8 @@ static int do_beamformer(btkb_pipeline* p) {
     return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                                          // beamformer.cc:1098-1100
   }
   if (p->wU != p->U) return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: weights were set for a different number of utterances");
+  if (p->C != 2 && p->C != 4 && p->C != 8)
+    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: this build instantiates the per-bin kernel for 2, 4 and 8 channels (got " + std::to_string(p->C) + ")");
   PerBinArgs a = perbin_args(p);
   CK(launch_perbin(a, p->stream));
   p->launches++;
@@ -366,7 +368,7 @@ static int do_synthesis(btkb_pipeline* p) {
   if (!p->have_Y) return fail(BTKB_ERR_STATE, "btkb_run: no beamformer output to synthesise");
   CK(cudaMemsetAsync(p->d_stats, 0, (size_t)p->U * 3 * sizeof(double), p->stream));
   SynthesisArgs a{p->d_Y, p->d_len, p->d_g, p->d_time, p->d_stats, p->U, p->n, p->T, p->M, p->m, p->cfg.r, p->D, p->K, p->Gp, p->pdS, p->laN, p->pdA,
-                  p->nb, p->nb * p->D, 1};
+                  p->nb, p->nb * p->D, p->cfg.synthesis_gain};
   CK(launch_synthesis(a, p->stream));
   p->launches++;
   p->have_time = true;
@@ -412,6 +414,38 @@ int btkb_run_beamformer(btkb_pipeline* p, int do_syn) {
   int rc = do_beamformer(p); if (rc) return rc;
   CK(cudaEventRecord(p->ev[2], p->stream));
   if (do_syn) { rc = do_synthesis(p); if (rc) return rc; }
+  CK(cudaEventRecord(p->ev[3], p->stream));
+  return BTKB_OK;
+}
+
+int btkb_set_subband(btkb_pipeline* p, int U, int T, const float* Y) {
+  if (!p || !Y) return fail(BTKB_ERR_INVALID, "btkb_set_subband: null argument");
+  if (U < 1 || U > p->Ucap || T < 0 || T > p->Tcap) return fail(BTKB_ERR_INVALID, "btkb_set_subband: U or T exceeds the pipeline capacity");
+  CK(cudaSetDevice(p->cfg.device));
+  // a length that yields exactly T frames: T = ceil(len/D) - laN + pdA
+  const int nblk = T - p->pdA + p->laN;
+  if (nblk < 0) return fail(BTKB_ERR_INVALID, "btkb_set_subband: T is shorter than the filter-bank delay");
+  p->U = U; p->n = nblk * p->D; p->lengths.assign(U, nblk * p->D);
+  p->T = T; p->nb = std::max(T - p->pdS, 0); p->Gp = round_up(U * p->K, 128);
+  CK(cudaMemcpyAsync(p->d_len, p->lengths.data(), U * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+  std::vector<float2> tmp((size_t)T * p->Gp, make_float2(0.f, 0.f));
+  for (int u = 0; u < U; u++)
+    for (int t = 0; t < T; t++)
+      memcpy(&tmp[(size_t)t * p->Gp + (size_t)u * p->K], Y + 2 * (((size_t)u * T + t) * p->K), sizeof(float2) * p->K);
+  CK(cudaMemcpyAsync(p->d_Y, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_Y = true; p->have_X = false; p->have_time = false; p->have_ua = false;
+  return BTKB_OK;
+}
+
+int btkb_run_synthesis(btkb_pipeline* p) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  p->launches = 0;
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  CK(cudaEventRecord(p->ev[2], p->stream));
+  int rc = do_synthesis(p); if (rc) return rc;
   CK(cudaEventRecord(p->ev[3], p->stream));
   return BTKB_OK;
 }

@@ -1,0 +1,484 @@
+// btk20_host.cc — implementation of the C++ host mirror (see btk20_host.h).  Everything numeric goes through the C-ABI.
+#include "btk20_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+
+#include "../../../include/btkb.h"
+
+namespace btk20 {
+
+namespace {
+void ck(int rc) {
+  if (rc == BTKB_OK) return;
+  const char* m = btkb_last_error();
+  switch (rc) {
+    case BTKB_ERR_ALLOC: throw jallocation_error("%s", m);
+    case BTKB_ERR_INVALID: throw jdimension_error("%s", m);
+    default: throw j_error("%s", m);
+  }
+}
+int analysis_frames(int n, int D, int m, int r, int dct) {  // modulated.cc:246-264,418-469
+  const int R = 1 << r;
+  int pd, la = 0;
+  if (dct == 1) pd = m * R - 1; else if (dct == 2) { pd = m * R - 1; la = m * R / 2 - 1; } else pd = 2 * m - 1;
+  return (n + D - 1) / D - la + pd;
+}
+int synthesis_delay(int m, int r, int dct) { const int R = 1 << r; return dct == 1 ? m * R - 1 : (dct == 2 ? m * R / 2 : 2 * m - 1); }
+}  // namespace
+
+// ================================================================================================ SampleFeature
+SampleFeature::SampleFeature(const std::string& fn, unsigned block_len, unsigned shift_len, bool pad_zeros, const std::string& nm)
+    : VectorFloatFeatureStream(block_len, nm), shift_len_(shift_len), cur_(0), pad_zeros_(pad_zeros), samplerate_(16000), version_(0) {
+  if (!fn.empty()) read(fn);
+}
+
+// Minimal RIFF/WAVE reader (PCM 16/32-bit, IEEE float32) standing in for libsndfile (feature.cc:238-389): norm == 0
+// keeps int16-scale floats (SFC_SET_NORM_FLOAT off), otherwise samples are scaled to [-1, 1) * norm.
+unsigned SampleFeature::read(const std::string& fn, int /*format*/, int samplerate, int chX, int /*chN*/, int cfrom, int to, int /*outsamplerate*/, float norm) {
+  std::ifstream f(fn, std::ios::binary);
+  if (!f) throw jio_error("Could not open file %s.", fn.c_str());
+  char id[4]; uint32_t sz;
+  f.read(id, 4); f.read((char*)&sz, 4); char wave[4]; f.read(wave, 4);
+  if (!f || std::memcmp(id, "RIFF", 4) || std::memcmp(wave, "WAVE", 4)) throw jio_error("sndfile error: %s is not a RIFF/WAVE file.", fn.c_str());
+  uint16_t fmt = 1, nch = 1, bits = 16; uint32_t rate = (uint32_t)samplerate;
+  std::vector<char> data;
+  while (f.read(id, 4) && f.read((char*)&sz, 4)) {
+    if (!std::memcmp(id, "fmt ", 4)) {
+      std::vector<char> b(sz); f.read(b.data(), sz);
+      std::memcpy(&fmt, &b[0], 2); std::memcpy(&nch, &b[2], 2); std::memcpy(&rate, &b[4], 4); std::memcpy(&bits, &b[14], 2);
+    } else if (!std::memcmp(id, "data", 4)) {
+      data.resize(sz); f.read(data.data(), sz); break;
+    } else f.seekg(sz + (sz & 1), std::ios::cur);
+  }
+  if (data.empty()) throw jio_error("sndfile error: no data chunk in %s.", fn.c_str());
+  const int bytes = bits / 8; const long frames = (long)(data.size() / (size_t)(bytes * nch));
+  if (to < 0 || to >= frames) to = (int)frames - 1;
+  if (cfrom < 0) cfrom = 0;
+  if (cfrom > to || cfrom > frames) throw jio_error("Cannot load samples from %d to %d.", cfrom, to);
+  if (chX < 1 || chX > nch) throw jio_error("Channel %d is not in the file (%d channels).", chX, (int)nch);
+  const int n = to - cfrom + 1;
+  samples_.resize(n);
+  for (int i = 0; i < n; i++) {
+    const char* p = &data[((size_t)(cfrom + i) * nch + (chX - 1)) * bytes];
+    float v;
+    if (fmt == 3 && bits == 32) { std::memcpy(&v, p, 4); if (norm == 0.0f) v *= 32768.0f; else v *= norm; }
+    else if (bits == 16) { int16_t s; std::memcpy(&s, p, 2); v = (norm == 0.0f) ? (float)s : (float)s / 32768.0f * norm; }
+    else if (bits == 32) { int32_t s; std::memcpy(&s, p, 4); v = (norm == 0.0f) ? (float)s / 65536.0f : (float)s / 2147483648.0f * norm; }
+    else throw jio_error("sndfile error: unsupported sample format (%d bits).", (int)bits);
+    samples_[i] = v;
+  }
+  samplerate_ = (int)rate;
+  version_++;
+  reset();
+  return (unsigned)n;
+}
+
+void SampleFeature::set_samples(const double* samples, unsigned n, unsigned samplerate) {  // feature.cc:669-679
+  samples_.resize(n);
+  for (unsigned i = 0; i < n; i++) samples_[i] = (float)samples[i];
+  samplerate_ = (int)samplerate;
+  version_++;
+  reset();
+}
+
+const float* SampleFeature::next(int frame_no) {  // feature.cc:605-649
+  if (is_end_) throw jiterator_error("end of samples!");
+  if (frame_no == frame_no_) return vector_.data();
+  if (frame_no >= 0 && frame_no - 1 != frame_no_) throw jindex_error("Problem in Feature %s: %d != %d\n", name().c_str(), frame_no - 1, frame_no_);
+  const unsigned ttl = (unsigned)samples_.size();
+  if (cur_ >= ttl) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  if (cur_ + size() >= ttl) {
+    if (pad_zeros_) {
+      std::fill(vector_.begin(), vector_.end(), 0.f);
+      for (unsigned i = 0; i < ttl - cur_; i++) vector_[i] = samples_[cur_ + i];
+    } else { is_end_ = true; throw jiterator_error("end of samples!"); }
+  } else {
+    for (unsigned i = 0; i < size(); i++) vector_[i] = samples_[cur_ + i];
+  }
+  cur_ += shift_len_;
+  increment_();
+  return vector_.data();
+}
+
+// ================================================================================================ analysis bank
+OverSampledDFTAnalysisBank::OverSampledDFTAnalysisBank(const VectorFloatFeatureStreamPtr& samp, const std::vector<double>& prototype, unsigned M, unsigned m,
+                                                       unsigned r, unsigned dct, const std::string& nm)
+    : VectorComplexFeatureStream(M, nm), samp_(samp), prototype_(prototype), M_(M), m_(m), r_(r), D_(M >> r), dct_(dct), pipe_(nullptr), T_(0), realized_(false) {
+  if (prototype.size() != (size_t)M * m) throw jconsistency_error("Prototype sizes do not match (%d vs. %d).", (int)prototype.size(), (int)(M * m));  // modulated.cc:239-241
+  if (samp_->size() != D_) throw jdimension_error("Input block length (%d) != D_ (%d)\n", samp_->size(), D_);                                     // modulated.cc:337-338
+}
+OverSampledDFTAnalysisBank::~OverSampledDFTAnalysisBank() { if (pipe_) btkb_destroy(pipe_); }
+
+void OverSampledDFTAnalysisBank::realize_() {
+  auto* sf = dynamic_cast<SampleFeature*>(samp_.get());
+  if (!sf) throw j_error("OverSampledDFTAnalysisBank: the GPU engine needs a SampleFeature source (whole-utterance sample array)");
+  const unsigned n = sf->samplesN();
+  if (n == 0) throw jiterator_error("end of samples!");
+  if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; }
+  btkb_config c; btkb_default_config(&c);
+  c.channels = 1; c.fft_len = (int)M_; c.m = (int)m_; c.r = (int)r_; c.delay_compensation_type = (int)dct_; c.max_utterances = 1; c.max_samples = (int)n;
+  ck(btkb_create(&c, &pipe_));
+  ck(btkb_set_prototypes(pipe_, prototype_.data(), nullptr, (int)prototype_.size()));
+  ck(btkb_submit(pipe_, sf->samples().data(), 1, (int)n, nullptr));
+  ck(btkb_run_analysis(pipe_));
+  T_ = btkb_num_frames(pipe_);
+  const unsigned K = M_ / 2 + 1;
+  X_.resize((size_t)T_ * K);
+  ck(btkb_fetch_snapshots(pipe_, reinterpret_cast<float*>(X_.data())));
+  realized_ = true;
+}
+
+const cplx* OverSampledDFTAnalysisBank::next(int frame_no) {  // modulated.cc:375-409
+  if (frame_no == frame_no_) return vector_.data();
+  if (!realized_) realize_();
+  if (frame_no_ + 1 >= T_) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  increment_();
+  const unsigned K = M_ / 2 + 1;
+  const std::complex<float>* x = &X_[(size_t)frame_no_ * K];
+  for (unsigned k = 0; k < K; k++) vector_[k] = cplx(x[k].real(), x[k].imag());
+  for (unsigned k = 1; k < M_ / 2; k++) vector_[M_ - k] = std::conj(vector_[k]);
+  return vector_.data();
+}
+void OverSampledDFTAnalysisBank::reset() { samp_->reset(); VectorComplexFeatureStream::reset(); realized_ = false; }
+
+// ================================================================================================ beamformers
+SubbandBeamformer::SubbandBeamformer(unsigned fftLen, bool hbs, int kind, const std::string& nm)
+    : VectorComplexFeatureStream(fftLen, nm), fftLen_(fftLen), halfBandShift_(hbs), kind_(kind) {
+  if (hbs) throw jallocation_error("halfBandShift==true is not yet supported\n");  // beamformer.cc:2283-2285 (MVDR); the GPU path is M/2+1 bins only
+}
+SubbandBeamformer::~SubbandBeamformer() { if (pipe_) btkb_destroy(pipe_); }
+void SubbandBeamformer::set_channel(const VectorComplexFeatureStreamPtr& chan) { channels_.push_back(chan); invalidate_(); }
+void SubbandBeamformer::clear_channel() { channels_.clear(); snap_.reset(); invalidate_(); if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; } }
+void SubbandBeamformer::reset() {
+  for (auto& c : channels_) c->reset();
+  if (snap_) snap_->zero();
+  VectorComplexFeatureStream::reset();
+  is_end_ = false;
+  realized_ = false;  // adaptive state restarts with the utterance (pybeamformer.py:759-762)
+}
+
+bool SubbandBeamformer::realized_with(const PostFilterConfig& pf, const SynthesisConfig& syn) const {
+  if (!realized_) return false;
+  if (pf.enabled != pf_used_.enabled || (pf.enabled && (pf.alpha != pf_used_.alpha || pf.type != pf_used_.type || pf.min_frames != pf_used_.min_frames))) return false;
+  if (syn.enabled && !syn_used_.enabled) return false;
+  return true;
+}
+
+void SubbandBeamformer::ensure_pipeline_(const PostFilterConfig& pf, const SynthesisConfig& syn, unsigned n_samples) {
+  auto* a0 = dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[0].get());
+  btkb_config c; btkb_default_config(&c);
+  c.channels = (int)channels_.size(); c.fft_len = (int)fftLen_; c.m = (int)a0->m(); c.r = (int)a0->r(); c.delay_compensation_type = (int)a0->dct();
+  c.samplerate = (float)samplerate_; c.beamformer = kind_;
+  c.postfilter = pf.enabled ? BTKB_PF_ZELINSKI : BTKB_PF_NONE; c.pf_alpha = (float)pf.alpha; c.pf_type = pf.type; c.pf_min_frames = pf.min_frames;
+  c.lms.beta = (float)lms_.beta; c.lms.gamma = (float)lms_.gamma; c.lms.init_diagonal_load = (float)lms_.init_diagonal_load;
+  c.lms.regularization_param = (float)lms_.regularization_param; c.lms.energy_floor = (float)lms_.energy_floor; c.lms.sil_thresh = (float)lms_.sil_thresh;
+  c.lms.max_wa_l2norm = (float)lms_.max_wa_l2norm; c.lms.min_frames = lms_.min_frames; c.lms.slowdown_after = lms_.slowdown_after;
+  c.max_utterances = 1; c.max_samples = (int)n_samples; c.synthesis_gain = syn.enabled ? syn.gain : 1;
+  if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; }
+  ck(btkb_create(&c, &pipe_));
+  ck(btkb_set_prototypes(pipe_, a0->prototype().data(), syn.enabled ? syn.prototype.data() : nullptr, (int)a0->prototype().size()));
+}
+
+// Collect the upstream graph, run the whole utterance on the GPU once, cache the results.
+void SubbandBeamformer::run_graph(const PostFilterConfig& pf, const SynthesisConfig& syn) {
+  if (channels_.empty()) throw j_error("set_channel() has not been called\n");
+  const unsigned C = (unsigned)channels_.size();
+  std::vector<const SampleFeature*> srcs(C);
+  unsigned n = 0;
+  for (unsigned c = 0; c < C; c++) {
+    auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[c].get());
+    if (!ab) throw j_error("SubbandBeamformer: the GPU engine needs OverSampledDFTAnalysisBank channels");
+    if (ab->M() != fftLen_) throw jdimension_error("channel %d: inconsistent FFT length (%d vs. %d)", c, ab->M(), fftLen_);
+    srcs[c] = dynamic_cast<const SampleFeature*>(ab->source().get());
+    if (!srcs[c]) throw j_error("SubbandBeamformer: the GPU engine needs SampleFeature sources");
+    if (c == 0) n = srcs[c]->samplesN();
+    else if (srcs[c]->samplesN() != n) throw jdimension_error("channel %d: %d samples, channel 0: %d", c, srcs[c]->samplesN(), n);
+  }
+  if (n == 0) { T_ = 0; nb_ = 0; realized_ = true; pf_used_ = pf; syn_used_ = syn; return; }
+  if (syn.enabled && (syn.M != fftLen_)) throw jdimension_error("synthesis bank: inconsistent FFT length (%d vs. %d)", syn.M, fftLen_);
+  ensure_pipeline_(pf, syn, n);
+  configure_weights_(pipe_);
+  std::vector<float> x((size_t)C * n);
+  for (unsigned c = 0; c < C; c++) std::memcpy(&x[(size_t)c * n], srcs[c]->samples().data(), sizeof(float) * n);
+  ck(btkb_submit(pipe_, x.data(), 1, (int)n, nullptr));
+  ck(btkb_run(pipe_, syn.enabled ? 1 : 0));
+  T_ = btkb_num_frames(pipe_); nb_ = btkb_num_blocks(pipe_);
+  const unsigned K = fftLen_ / 2 + 1;
+  Y_.resize((size_t)T_ * K);
+  ck(btkb_fetch_subband(pipe_, reinterpret_cast<float*>(Y_.data())));
+  if (syn.enabled) { time_.resize((size_t)nb_ * (fftLen_ >> syn.r)); ck(btkb_fetch_time(pipe_, time_.data())); }
+  if (pf.enabled) { pfw_.resize((size_t)T_ * K); ck(btkb_get_postfilter_weights(pipe_, pfw_.data())); }
+  W_.resize((size_t)K * C);
+  ck(btkb_get_weights(pipe_, reinterpret_cast<float*>(W_.data())));
+  haveX_ = false;
+  realized_ = true; pf_used_ = pf; syn_used_ = syn;
+}
+
+const cplx* SubbandBeamformer::next(int frame_no) {
+  if (frame_no == frame_no_) return vector_.data();
+  if (!realized_) run_graph(PostFilterConfig(), SynthesisConfig());
+  if (frame_no_ + 1 >= T_) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  increment_();
+  const unsigned K = fftLen_ / 2 + 1;
+  const std::complex<float>* y = &Y_[(size_t)frame_no_ * K];
+  for (unsigned k = 0; k < K; k++) vector_[k] = cplx(y[k].real(), y[k].imag());
+  for (unsigned k = 1; k < fftLen_ / 2; k++) vector_[fftLen_ - k] = std::conj(vector_[k]);   // beamformer.cc:1142-1149
+  return vector_.data();
+}
+
+SnapShotArrayPtr SubbandBeamformer::snapshot_array() {
+  if (!snap_) snap_ = std::make_shared<SnapShotArray>(fftLen_, chanN());
+  if (realized_ && pipe_ && frame_no_ >= 0 && frame_no_ < T_) {
+    const unsigned K = fftLen_ / 2 + 1, C = chanN();
+    if (!haveX_) { X_.resize((size_t)T_ * C * K); ck(btkb_fetch_snapshots(pipe_, reinterpret_cast<float*>(X_.data()))); haveX_ = true; }
+    std::vector<cplx> full(fftLen_);
+    for (unsigned c = 0; c < C; c++) {
+      const std::complex<float>* x = &X_[((size_t)frame_no_ * C + c) * K];
+      for (unsigned k = 0; k < K; k++) full[k] = cplx(x[k].real(), x[k].imag());
+      for (unsigned k = 1; k < fftLen_ / 2; k++) full[fftLen_ - k] = std::conj(full[k]);
+      snap_->set_samples(full.data(), c);
+    }
+    snap_->update();
+  }
+  return snap_;
+}
+
+std::vector<cplx> SubbandBeamformer::get_weights(unsigned fbinX) {
+  const unsigned K = fftLen_ / 2 + 1, C = chanN();
+  if (fbinX >= K) throw jindex_error("fbinX %d must be <= %d", fbinX, fftLen_ / 2);
+  if (W_.size() != (size_t)K * C) {
+    // weights do not depend on the samples: realise them on a one-block dummy batch
+    btkb_pipeline* keep = pipe_; pipe_ = nullptr;
+    auto* a0 = channels_.empty() ? nullptr : dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[0].get());
+    if (!a0) throw j_error("call set_channel() before asking for weights");
+    ensure_pipeline_(PostFilterConfig(), SynthesisConfig(), fftLen_);
+    configure_weights_(pipe_);
+    W_.resize((size_t)K * C);
+    ck(btkb_get_weights(pipe_, reinterpret_cast<float*>(W_.data())));
+    btkb_destroy(pipe_); pipe_ = keep;
+  }
+  std::vector<cplx> w(C);
+  for (unsigned c = 0; c < C; c++) w[c] = cplx(W_[(size_t)fbinX * C + c].real(), W_[(size_t)fbinX * C + c].imag());
+  return w;
+}
+
+// ---- SubbandDS
+SubbandDS::SubbandDS(unsigned fftLen, bool hbs, const std::string& nm, int kind) : SubbandBeamformer(fftLen, hbs, kind, nm) {}
+void SubbandDS::clear_channel() { SubbandBeamformer::clear_channel(); have_delays_ = false; W_.clear(); }
+void SubbandDS::calc_array_manifold_vectors(double samplerate, const std::vector<double>& delays) {
+  if (delays.size() != chanN())  // beamformer.cc:504-506
+    throw jdimension_error("Number of delays does not match number of channels (%d vs. %d).\n", (int)delays.size(), (int)chanN());
+  samplerate_ = samplerate; delays_ = delays; have_delays_ = true; W_.clear(); invalidate_();
+}
+void SubbandDS::configure_weights_(btkb_pipeline* p) {
+  require_weights_(have_delays_, "call calc_array_manifold_vectorsX() once\n");  // beamformer.cc:1098-1100
+  ck(btkb_set_delays(p, 1, delays_.data()));
+}
+
+// ---- SubbandGSC
+SubbandGSC::SubbandGSC(unsigned fftLen, bool hbs, const std::string& nm) : SubbandDS(fftLen, hbs, nm, BTKB_BF_GSC) {}
+void SubbandGSC::set_active_weights_f(unsigned fbinX, const std::vector<double>& packed) {  // beamformer.cc:729-748,1365-1372
+  require_weights_(have_delays_, "call calc_gsc_weights_x() once\n");
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
+  if (packed.size() != 2 * (C - 1)) throw jdimension_error("the size of an active weight vector must be %d but it is %d\n", (int)(2 * (C - 1)), (int)packed.size());
+  if (fbinX >= fftLen_) throw jdimension_error("Must be a frequency bin %d < the length of FFT %d\n", fbinX, fftLen_);
+  if (fbinX >= K) return;  // mirrored bins are never used by next()
+  if (wa_.size() != (size_t)K * (C - 1)) wa_.assign((size_t)K * (C - 1), std::complex<float>(0, 0));
+  for (unsigned i = 0; i < C - 1; i++) wa_[(size_t)fbinX * (C - 1) + i] = std::complex<float>((float)packed[2 * i], (float)packed[2 * i + 1]);
+  have_wa_ = true; invalidate_();
+}
+void SubbandGSC::zero_active_weights() { require_weights_(have_delays_, "call calc_gsc_weights_x() once\n"); wa_.clear(); have_wa_ = false; invalidate_(); }
+void SubbandGSC::configure_weights_(btkb_pipeline* p) {
+  require_weights_(have_delays_, "call calc_gsc_weights_X() once\n");  // beamformer.cc:1262-1264
+  ck(btkb_set_delays(p, 1, delays_.data()));
+  if (have_wa_) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
+}
+
+// ---- SubbandGSCLMS
+SubbandGSCLMS::SubbandGSCLMS(unsigned fftLen, const LmsConfig& cfg, const std::string& nm) : SubbandDS(fftLen, false, nm, BTKB_BF_GSC_LMS) { lms_ = cfg; }
+std::vector<std::complex<float>> SubbandGSCLMS::active_weights() {
+  if (!realized_ || !pipe_) throw j_error("run the beamformer first");
+  std::vector<std::complex<float>> wa((size_t)(fftLen_ / 2 + 1) * (chanN() - 1));
+  ck(btkb_get_active_weights(pipe_, reinterpret_cast<float*>(wa.data())));
+  return wa;
+}
+int SubbandGSCLMS::total_updates() {
+  if (!realized_ || !pipe_) return 0;
+  double st[3]; ck(btkb_fetch_stats(pipe_, st));
+  return (int)st[2];
+}
+
+// ---- SubbandMVDR
+SubbandMVDR::SubbandMVDR(unsigned fftLen, bool hbs, const std::string& nm) : SubbandDS(fftLen, hbs, nm, BTKB_BF_MVDR) {}
+void SubbandMVDR::clear_channel() { SubbandDS::clear_channel(); R_.clear(); wmvdr_.clear(); have_R_ = have_w_ = diffuse_ = smi_ = false; }
+bool SubbandMVDR::set_noise_spatial_spectral_matrix(unsigned fbinX, const std::vector<cplx>& Rnn) {  // beamformer.cc:2410-2433
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
+  if (Rnn.size() != (size_t)C * C) { fprintf(stderr, "The number of the rows of the matrix must be %d\n", C); return false; }
+  if (fbinX >= K) throw jindex_error("fbinX %d must be <= %d", fbinX, fftLen_ / 2);
+  if (R_.size() != (size_t)K * C * C) R_.assign((size_t)K * C * C, std::complex<float>(0, 0));
+  for (size_t i = 0; i < (size_t)C * C; i++) R_[(size_t)fbinX * C * C + i] = std::complex<float>((float)Rnn[i].real(), (float)Rnn[i].imag());
+  have_R_ = true; diffuse_ = false; smi_ = false; mu_ = 0.0; have_w_ = false; invalidate_();
+  return true;
+}
+bool SubbandMVDR::set_diffuse_noise_model(const std::vector<double>& mpos, double samplerate, double sspeed) {  // beamformer.cc:2442-2509
+  if (mpos.size() != (size_t)chanN() * 3) { fprintf(stderr, "The number of microphones must be %d but it is %d\n", chanN(), (int)(mpos.size() / 3)); return false; }
+  mpos_ = mpos; samplerate_ = samplerate; sspeed_ = sspeed; have_R_ = true; diffuse_ = true; smi_ = false; mu_ = 0.0; have_w_ = false; invalidate_();
+  return true;
+}
+void SubbandMVDR::set_all_diagonal_loading(double w) {  // beamformer.cc:2511-2523 (R += w I, cumulative like the reference)
+  if (!have_R_) throw j_error("Construct first a noise covariance matrix\n");
+  mu_ += (double)(float)w; have_w_ = false; invalidate_();
+}
+bool SubbandMVDR::calc_mvdr_weights(double samplerate, double /*dThreshold*/, bool /*calc_inverse_matrix*/) {  // beamformer.cc:2350-2402
+  if (!have_R_) throw jallocation_error("Set a spatial spectral matrix before calling calc_mvdr_weights()\n");
+  require_weights_(have_delays_, "call calc_array_manifold_vectorsX() once\n");
+  samplerate_ = samplerate; have_w_ = true; W_.clear(); invalidate_();
+  return true;
+}
+int SubbandMVDR::accumulate_noise_covariance(double samplerate, double start, double end, double thr) {
+  // pass 1 of pybeamformer.py:948-1000 on the GPU: analysis + masked covariance; the statistics stay on the host as R
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
+  std::vector<const SampleFeature*> srcs(C); unsigned n = 0;
+  for (unsigned c = 0; c < C; c++) {
+    auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[c].get());
+    if (!ab) throw j_error("SubbandMVDR: the GPU engine needs OverSampledDFTAnalysisBank channels");
+    srcs[c] = dynamic_cast<const SampleFeature*>(ab->source().get());
+    if (!srcs[c]) throw j_error("SubbandMVDR: the GPU engine needs SampleFeature sources");
+    n = srcs[0]->samplesN();
+  }
+  samplerate_ = samplerate;
+  ensure_pipeline_(PostFilterConfig(), SynthesisConfig(), n);
+  std::vector<float> x((size_t)C * n);
+  for (unsigned c = 0; c < C; c++) std::memcpy(&x[(size_t)c * n], srcs[c]->samples().data(), sizeof(float) * n);
+  ck(btkb_submit(pipe_, x.data(), 1, (int)n, nullptr));
+  ck(btkb_run_analysis(pipe_));
+  double lab[2] = {start, end};
+  ck(btkb_accumulate_covariance(pipe_, lab, (float)thr));
+  std::vector<std::complex<float>> Rn((size_t)K * C * C);
+  ck(btkb_get_covariance(pipe_, reinterpret_cast<float*>(Rn.data())));
+  R_ = Rn; have_R_ = true; diffuse_ = false; smi_ = true; mu_ = 0.0; have_w_ = false; invalidate_();
+  return 0;
+}
+void SubbandMVDR::configure_weights_(btkb_pipeline* p) {
+  require_weights_(have_delays_, "call calc_array_manifold_vectorsX() once\n");
+  if (!have_w_) throw j_error("call calc_mvdr_weights() once\n");  // beamformer.cc:2544-2546
+  ck(btkb_set_delays(p, 1, delays_.data()));
+  if (diffuse_) ck(btkb_set_diffuse_noise_model(p, 1, mpos_.data(), (float)sspeed_));
+  else ck(btkb_set_noise_covariance(p, 1, reinterpret_cast<const float*>(R_.data())));
+  ck(btkb_calc_mvdr_weights(p, (float)mu_));
+}
+void SubbandMVDRGSC::set_active_weights_f(unsigned fbinX, const std::vector<double>& packed) {
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
+  if (packed.size() != 2 * (C - 1)) throw jdimension_error("the size of an active weight vector must be %d but it is %d\n", (int)(2 * (C - 1)), (int)packed.size());
+  if (fbinX >= K) return;
+  if (wa_.size() != (size_t)K * (C - 1)) wa_.assign((size_t)K * (C - 1), std::complex<float>(0, 0));
+  bool nz = false;
+  for (unsigned i = 0; i < C - 1; i++) { wa_[(size_t)fbinX * (C - 1) + i] = std::complex<float>((float)packed[2 * i], (float)packed[2 * i + 1]); nz |= packed[2 * i] != 0 || packed[2 * i + 1] != 0; }
+  have_wa_ = have_wa_ || nz; invalidate_();
+}
+void SubbandMVDRGSC::configure_weights_(btkb_pipeline* p) {
+  SubbandMVDR::configure_weights_(p);
+  if (have_wa_) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
+}
+
+// ================================================================================================ post-filter
+ZelinskiPostFilter::ZelinskiPostFilter(const VectorComplexFeatureStreamPtr& output, unsigned fftLen, double alpha, int type, int min_frames, const std::string& nm)
+    : VectorComplexFeatureStream(fftLen, nm), fftLen_(fftLen), samp_(output), alpha_(alpha), type_(type), min_frames_(min_frames) {
+  if (output->size() != fftLen) throw jdimension_error("Input block length (%d) != fftLen (%d)\n", output->size(), fftLen);  // postfilter.cc:366-368
+  bf_ = std::dynamic_pointer_cast<SubbandDS>(output);
+}
+void ZelinskiPostFilter::reset() { samp_->reset(); if (bf_) bf_->reset(); VectorComplexFeatureStream::reset(); is_end_ = false; }
+const cplx* ZelinskiPostFilter::next(int frame_no) {  // postfilter.cc:424-491
+  if (frame_no == frame_no_) return vector_.data();
+  if (!bf_) throw j_error("set beamformer's weights \n");  // postfilter.cc:443-445
+  const PostFilterConfig pf = config();
+  if (!bf_->realized_with(pf, SynthesisConfig())) bf_->run_graph(pf, SynthesisConfig());
+  if (frame_no_ + 1 >= bf_->frames()) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  increment_();
+  const unsigned K = fftLen_ / 2 + 1;
+  const std::complex<float>* y = &bf_->Y()[(size_t)frame_no_ * K];
+  for (unsigned k = 0; k < K; k++) vector_[k] = cplx(y[k].real(), y[k].imag());
+  for (unsigned k = 1; k < fftLen_ / 2; k++) vector_[fftLen_ - k] = std::conj(vector_[k]);
+  return vector_.data();
+}
+std::vector<cplx> ZelinskiPostFilter::postfilter_weights() {
+  std::vector<cplx> w(fftLen_, cplx(0, 0));
+  if (!bf_ || frame_no_ < 0 || bf_->pf_weights().empty()) return w;
+  const unsigned K = fftLen_ / 2 + 1;
+  for (unsigned k = 0; k < K; k++) w[k] = cplx(bf_->pf_weights()[(size_t)frame_no_ * K + k], 0);
+  for (unsigned k = 1; k < fftLen_ / 2; k++) w[fftLen_ - k] = w[k];
+  return w;
+}
+
+// ================================================================================================ synthesis bank
+OverSampledDFTSynthesisBank::OverSampledDFTSynthesisBank(const VectorComplexFeatureStreamPtr& samp, const std::vector<double>& prototype, unsigned M, unsigned m,
+                                                         unsigned r, unsigned dct, int gain, const std::string& nm)
+    : VectorFloatFeatureStream(M >> r, nm), samp_(samp), prototype_(prototype), M_(M), m_(m), r_(r), D_(M >> r), dct_(dct), gain_(gain),
+      pd_(synthesis_delay((int)m, (int)r, (int)dct)), pipe_(nullptr), nb_(0), realized_(false) {
+  if (prototype.size() != (size_t)M * m) throw jconsistency_error("Prototype sizes do not match (%d vs. %d).", (int)prototype.size(), (int)(M * m));
+}
+OverSampledDFTSynthesisBank::~OverSampledDFTSynthesisBank() { if (pipe_) btkb_destroy(pipe_); }
+void OverSampledDFTSynthesisBank::reset() { samp_->reset(); VectorFloatFeatureStream::reset(); realized_ = false; }
+
+void OverSampledDFTSynthesisBank::realize_() {
+  SynthesisConfig syn; syn.enabled = true; syn.prototype = prototype_; syn.M = M_; syn.m = m_; syn.r = r_; syn.dct = dct_; syn.gain = gain_;
+  SubbandBeamformer* bf = nullptr; PostFilterConfig pf;
+  if (auto* z = dynamic_cast<ZelinskiPostFilter*>(samp_.get())) { bf = z->beamformer().get(); pf = z->config(); }
+  else bf = dynamic_cast<SubbandBeamformer*>(samp_.get());
+  if (bf) {  // fast path: the whole graph runs on the GPU in one submission
+    if (!bf->realized_with(pf, syn)) bf->run_graph(pf, syn);
+    out_ = bf->time_out(); nb_ = bf->blocks();
+  } else {   // arbitrary upstream stream (e.g. a Python object behind PyVectorComplexFeatureStream): drain it, synthesise on the GPU
+    const unsigned K = M_ / 2 + 1;
+    std::vector<std::complex<float>> Y;
+    int T = 0;
+    for (;;) {
+      const cplx* f;
+      try { f = samp_->next(T); } catch (jiterator_error&) { break; }
+      Y.resize((size_t)(T + 1) * K);
+      for (unsigned k = 0; k < K; k++) Y[(size_t)T * K + k] = std::complex<float>((float)f[k].real(), (float)f[k].imag());
+      T++;
+    }
+    nb_ = std::max(T - pd_, 0);
+    out_.assign((size_t)nb_ * D_, 0.f);
+    if (nb_ > 0) {
+      if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; }
+      btkb_config c; btkb_default_config(&c);
+      c.channels = 1; c.fft_len = (int)M_; c.m = (int)m_; c.r = (int)r_; c.delay_compensation_type = (int)dct_; c.max_utterances = 1;
+      c.max_samples = (T + 8) * (int)D_; c.synthesis_gain = gain_;
+      ck(btkb_create(&c, &pipe_));
+      ck(btkb_set_prototypes(pipe_, prototype_.data(), prototype_.data(), (int)prototype_.size()));
+      ck(btkb_set_subband(pipe_, 1, T, reinterpret_cast<const float*>(Y.data())));
+      ck(btkb_run_synthesis(pipe_));
+      nb_ = btkb_num_blocks(pipe_);
+      out_.resize((size_t)nb_ * D_);
+      ck(btkb_fetch_time(pipe_, out_.data()));
+    }
+  }
+  realized_ = true;
+}
+
+const float* OverSampledDFTSynthesisBank::next(int frame_no) {  // modulated.cc:569-612
+  if (frame_no == frame_no_ + pd_) return vector_.data();
+  if (!realized_) realize_();
+  if (frame_no_ + 1 >= nb_) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  if (frame_no >= 0 && frame_no - 1 != frame_no_) printf("The output might not be continuous %s: %d != %d\n", name().c_str(), frame_no - 1, frame_no_);
+  increment_();
+  std::memcpy(vector_.data(), &out_[(size_t)frame_no_ * D_], sizeof(float) * D_);
+  return vector_.data();
+}
+
+std::vector<double> calc_all_delays(double, double, double, const std::vector<double>& mpos) {  // beamformer.cc:1170-1189 (sic: ignores x,y,z)
+  const size_t C = mpos.size() / 3;
+  std::vector<double> d(C);
+  for (size_t c = 0; c < C; c++) d[c] = std::sqrt(mpos[3 * c] * mpos[3 * c] + mpos[3 * c + 1] * mpos[3 * c + 1] + mpos[3 * c + 2] * mpos[3 * c + 2]) / 343740.0;
+  const double mid = d[C / 2];
+  for (auto& v : d) v -= mid;
+  return d;
+}
+
+}  // namespace btk20

@@ -1,0 +1,307 @@
+// btk20_host.h — C++ host side above the C-ABI: btk2.0's stream classes for the hot path, same names and semantics,
+// with the arithmetic delegated to libbtkb.so (include/btkb.h).  No torch, no GSL.
+//
+// Reference interfaces mirrored (btk20_src/):
+//   FeatureStream<T>::{next,current,reset,size,is_end,frame_no,name}      stream/stream.h:16-54
+//   exception hierarchy j_error ...                                       common/jexception.h:44-161
+//   SampleFeature::{read,setSamples,data,samplesN,next,reset}             feature/feature.h:153-208, feature.cc:238-389,605-679
+//   OverSampledDFTAnalysisBank / OverSampledDFTSynthesisBank              modulated/modulated.h:270-349
+//   SnapShotArray                                                         beamformer/spectralinfoarray.h:6-39
+//   SubbandDS / SubbandGSC / SubbandMVDR / SubbandMVDRGSC                 beamformer/beamformer.h:130-429
+//   ZelinskiPostFilter                                                    postfilter/postfilter.h:74-110
+//   SubbandGSCLMS: the native body of lib/pybeamformer.py:588-762 (SubbandGSCLMSBeamformer, pure Python in the reference)
+//
+// Execution model: the reference pulls ONE frame through the whole graph per next().  Here the first next() on a node
+// collects its upstream graph, submits the whole utterance to the GPU pipeline once, and subsequent next() calls hand out
+// frames from the fetched host buffers.  Frame numbering, idempotent re-reads (frame_no == frame_no_), end-of-stream
+// (jiterator_error) and reset() follow the reference.
+#pragma once
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <exception>
+#include <memory>
+#include <string>
+#include <vector>
+
+struct btkb_pipeline;
+
+namespace btk20 {
+
+// ----------------------------------------------------------------------------------------------------------------
+class j_error : public std::exception {
+ public:
+  j_error() {}
+  explicit j_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); set(fmt, ap); va_end(ap); }
+  const char* what() const noexcept override { return msg_.c_str(); }
+ protected:
+  void set(const char* fmt, va_list ap) { char buf[1024]; vsnprintf(buf, sizeof(buf), fmt, ap); msg_ = buf; }
+  std::string msg_;
+};
+#define BTK20_EXC(NAME)                                                                                   \
+  class NAME : public j_error {                                                                           \
+   public:                                                                                                \
+    explicit NAME(const char* fmt, ...) { va_list ap; va_start(ap, fmt); set(fmt, ap); va_end(ap); }      \
+  };
+BTK20_EXC(jallocation_error) BTK20_EXC(jarithmetic_error) BTK20_EXC(jconsistency_error) BTK20_EXC(jdimension_error)
+BTK20_EXC(jindex_error) BTK20_EXC(jinitialization_error) BTK20_EXC(jio_error) BTK20_EXC(jiterator_error) BTK20_EXC(jkey_error)
+BTK20_EXC(jnumeric_error) BTK20_EXC(jparameter_error) BTK20_EXC(jparse_error) BTK20_EXC(jtype_error)
+#undef BTK20_EXC
+
+typedef std::complex<double> cplx;
+
+// ----------------------------------------------------------------------------------------------------------------
+template <class T>
+class FeatureStream {
+ public:
+  virtual ~FeatureStream() {}
+  const std::string& name() const { return name_; }
+  unsigned size() const { return size_; }
+  virtual const T* next(int frame_no = -5) = 0;
+  const T* current() {
+    if (frame_no_ < 0) throw jconsistency_error("Frame index (%d) < 0.", frame_no_);
+    return next(frame_no_);
+  }
+  bool is_end() const { return is_end_; }
+  virtual void reset() { frame_no_ = frame_reset_no_; is_end_ = false; }
+  virtual int frame_no() const { return frame_no_; }
+
+ protected:
+  FeatureStream(unsigned sz, const std::string& nm) : frame_reset_no_(-1), size_(sz), frame_no_(-1), vector_(sz), is_end_(false), name_(nm) {}
+  void increment_() { frame_no_++; }
+  const int frame_reset_no_;
+  const unsigned size_;
+  int frame_no_;
+  std::vector<T> vector_;
+  bool is_end_;
+ private:
+  std::string name_;
+};
+typedef FeatureStream<float> VectorFloatFeatureStream;
+typedef FeatureStream<cplx> VectorComplexFeatureStream;
+typedef std::shared_ptr<VectorFloatFeatureStream> VectorFloatFeatureStreamPtr;
+typedef std::shared_ptr<VectorComplexFeatureStream> VectorComplexFeatureStreamPtr;
+
+// ----------------------------------------------------------------------------------------------------------------
+class SampleFeature : public VectorFloatFeatureStream {
+ public:
+  SampleFeature(const std::string& fn = "", unsigned block_len = 320, unsigned shift_len = 160, bool pad_zeros = false, const std::string& nm = "Sample");
+  unsigned read(const std::string& fn, int format = 0, int samplerate = 16000, int chX = 1, int chN = 1, int cfrom = 0, int to = -1,
+                int outsamplerate = -1, float norm = 0.0f);
+  void set_samples(const double* samples, unsigned n, unsigned samplerate);
+  const std::vector<float>& samples() const { return samples_; }
+  unsigned samplesN() const { return (unsigned)samples_.size(); }
+  int samplerate() const { return samplerate_; }
+  unsigned shift_len() const { return shift_len_; }
+  unsigned long version() const { return version_; }   // bumps whenever the sample array is replaced
+  const float* next(int frame_no = -5) override;
+  void reset() override { cur_ = 0; VectorFloatFeatureStream::reset(); }
+ private:
+  std::vector<float> samples_;
+  unsigned shift_len_, cur_;
+  bool pad_zeros_;
+  int samplerate_;
+  unsigned long version_;
+};
+typedef std::shared_ptr<SampleFeature> SampleFeaturePtr;
+
+// ----------------------------------------------------------------------------------------------------------------
+class OverSampledDFTAnalysisBank : public VectorComplexFeatureStream {
+ public:
+  OverSampledDFTAnalysisBank(const VectorFloatFeatureStreamPtr& samp, const std::vector<double>& prototype, unsigned M, unsigned m, unsigned r,
+                             unsigned delay_compensation_type = 0, const std::string& nm = "OverSampledDFTAnalysisBank");
+  ~OverSampledDFTAnalysisBank();
+  const cplx* next(int frame_no = -5) override;
+  void reset() override;
+  unsigned fftlen() const { return M_; }
+  unsigned shiftlen() const { return D_; }
+  double polyphase(unsigned m, unsigned n) const { return prototype_.at(m + M_ * n); }
+  // graph introspection for the batch engine
+  const VectorFloatFeatureStreamPtr& source() const { return samp_; }
+  const std::vector<double>& prototype() const { return prototype_; }
+  unsigned M() const { return M_; } unsigned m() const { return m_; } unsigned r() const { return r_; } unsigned dct() const { return dct_; }
+ private:
+  void realize_();
+  VectorFloatFeatureStreamPtr samp_;
+  std::vector<double> prototype_;
+  unsigned M_, m_, r_, D_, dct_;
+  btkb_pipeline* pipe_;
+  std::vector<std::complex<float>> X_;  // [T][K]
+  int T_; bool realized_;
+};
+typedef std::shared_ptr<OverSampledDFTAnalysisBank> OverSampledDFTAnalysisBankPtr;
+
+// ----------------------------------------------------------------------------------------------------------------
+class SnapShotArray {
+ public:
+  SnapShotArray(unsigned fftlen, unsigned nchan) : fftLen_(fftlen), nChan_(nchan), samples_((size_t)fftlen * nchan), snapshots_((size_t)fftlen * nchan) {}
+  const cplx* snapshot(unsigned fbinX) const { return &snapshots_[(size_t)fbinX * nChan_]; }
+  void set_samples(const cplx* samp, unsigned chanX) { for (unsigned k = 0; k < fftLen_; k++) samples_[(size_t)chanX * fftLen_ + k] = samp[k]; }
+  void update() { for (unsigned k = 0; k < fftLen_; k++) for (unsigned c = 0; c < nChan_; c++) snapshots_[(size_t)k * nChan_ + c] = samples_[(size_t)c * fftLen_ + k]; }
+  void zero() { std::fill(samples_.begin(), samples_.end(), cplx(0, 0)); std::fill(snapshots_.begin(), snapshots_.end(), cplx(0, 0)); }
+  unsigned fftLen() const { return fftLen_; }
+  unsigned nChan() const { return nChan_; }
+ private:
+  unsigned fftLen_, nChan_;
+  std::vector<cplx> samples_, snapshots_;
+};
+typedef std::shared_ptr<SnapShotArray> SnapShotArrayPtr;
+
+struct LmsConfig {  // lib/pybeamformer.py:597-607 defaults (= unit_test/confs/gsclms.json)
+  double beta = 0.97, gamma = 0.01, init_diagonal_load = 1.0e6, regularization_param = 1.0e-4, energy_floor = 90, sil_thresh = 1.0e8, max_wa_l2norm = 100.0;
+  int min_frames = 128, slowdown_after = 4096;
+};
+struct PostFilterConfig { bool enabled = false; double alpha = 0.6; int type = 2; int min_frames = 0; };
+struct SynthesisConfig { bool enabled = false; std::vector<double> prototype; unsigned M = 0, m = 0, r = 0, dct = 0; int gain = 1; };
+
+// ----------------------------------------------------------------------------------------------------------------
+// Common base of the subband beamformers (beamformer.h:89-128): channel list, snapshot array, batch realisation.
+class SubbandBeamformer : public VectorComplexFeatureStream {
+ public:
+  SubbandBeamformer(unsigned fftLen, bool half_band_shift, int kind, const std::string& nm);
+  ~SubbandBeamformer();
+  void set_channel(const VectorComplexFeatureStreamPtr& chan);
+  virtual void clear_channel();
+  const cplx* next(int frame_no = -5) override;
+  void reset() override;
+  unsigned fftLen() const { return fftLen_; }
+  unsigned chanN() const { return (unsigned)channels_.size(); }
+  SnapShotArrayPtr snapshot_array();      // snapshots of the CURRENT frame (filled on demand)
+  // weights (all per bin f = 0..M/2, [C] each)
+  std::vector<cplx> get_weights(unsigned fbinX);
+  // ---- batch engine hooks used by downstream nodes (post-filter, synthesis bank)
+  void run_graph(const PostFilterConfig& pf, const SynthesisConfig& syn);
+  const std::vector<std::complex<float>>& Y() const { return Y_; }
+  const std::vector<float>& time_out() const { return time_; }
+  const std::vector<float>& pf_weights() const { return pfw_; }
+  int frames() const { return T_; }
+  int blocks() const { return nb_; }
+  bool realized_with(const PostFilterConfig& pf, const SynthesisConfig& syn) const;
+  double samplerate_hint() const { return samplerate_; }
+
+ protected:
+  virtual void configure_weights_(btkb_pipeline* p) = 0;   // push delays / weights / covariance into a fresh pipeline
+  void invalidate_() { realized_ = false; }
+  void require_weights_(bool ok, const char* msg) const { if (!ok) throw j_error("%s", msg); }
+  unsigned fftLen_; bool halfBandShift_; int kind_;
+  std::vector<VectorComplexFeatureStreamPtr> channels_;
+  double samplerate_ = 16000.0;
+  // realised results
+  btkb_pipeline* pipe_ = nullptr;
+  std::vector<std::complex<float>> Y_; std::vector<float> time_, pfw_; std::vector<std::complex<float>> X_;
+  std::vector<std::complex<float>> W_;   // [K][C] weights read back
+  int T_ = 0, nb_ = 0; bool realized_ = false, haveX_ = false;
+  PostFilterConfig pf_used_; SynthesisConfig syn_used_;
+  LmsConfig lms_;
+  SnapShotArrayPtr snap_;
+  std::vector<unsigned long> src_versions_;
+  void ensure_pipeline_(const PostFilterConfig& pf, const SynthesisConfig& syn, unsigned n_samples);
+};
+typedef std::shared_ptr<SubbandBeamformer> SubbandBeamformerPtr;
+
+class SubbandDS : public SubbandBeamformer {
+ public:
+  SubbandDS(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandDS", int kind = 0);
+  virtual void calc_array_manifold_vectors(double samplerate, const std::vector<double>& delays);
+  void clear_channel() override;
+ protected:
+  void configure_weights_(btkb_pipeline* p) override;
+  std::vector<double> delays_; bool have_delays_ = false;
+};
+typedef std::shared_ptr<SubbandDS> SubbandDSPtr;
+
+class SubbandGSC : public SubbandDS {
+ public:
+  SubbandGSC(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandGSC");
+  void calc_gsc_weights(double samplerate, const std::vector<double>& delaysT) { calc_array_manifold_vectors(samplerate, delaysT); }
+  void set_active_weights_f(unsigned fbinX, const std::vector<double>& packedWeight);
+  void zero_active_weights();
+ protected:
+  void configure_weights_(btkb_pipeline* p) override;
+  std::vector<std::complex<float>> wa_;  // [K][C-1]
+  bool have_wa_ = false;
+};
+typedef std::shared_ptr<SubbandGSC> SubbandGSCPtr;
+
+// native body of pybeamformer.SubbandGSCLMSBeamformer
+class SubbandGSCLMS : public SubbandDS {
+ public:
+  SubbandGSCLMS(unsigned fftLen, const LmsConfig& cfg, const std::string& nm = "SubbandGSCLMS");
+  void calc_beamformer_weights(double samplerate, const std::vector<double>& delays) { calc_array_manifold_vectors(samplerate, delays); }
+  std::vector<std::complex<float>> active_weights();   // [K][C-1] after the run (waH)
+  int total_updates();
+};
+typedef std::shared_ptr<SubbandGSCLMS> SubbandGSCLMSPtr;
+
+class SubbandMVDR : public SubbandDS {
+ public:
+  SubbandMVDR(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandMVDR");
+  bool calc_mvdr_weights(double samplerate, double dThreshold = 1.0e-8, bool calc_inverse_matrix = true);
+  std::vector<cplx> mvdr_weights(unsigned fbinX) { return get_weights(fbinX); }
+  bool set_noise_spatial_spectral_matrix(unsigned fbinX, const std::vector<cplx>& Rnn);   // row-major C x C
+  bool set_diffuse_noise_model(const std::vector<double>& micPositions /* [C][3] */, double samplerate, double sspeed = 343740.0);
+  void set_all_diagonal_loading(double diagonalWeight);
+  void clear_channel() override;
+  // SMI statistics on the GPU (pybeamformer.py:948-1000): noise frames outside [start,end] with energy > threshold
+  int accumulate_noise_covariance(double samplerate, double label_start, double label_end, double energy_threshold);
+ protected:
+  void configure_weights_(btkb_pipeline* p) override;
+  std::vector<std::complex<float>> R_;   // [K][C][C]
+  std::vector<std::complex<float>> wmvdr_;  // [K][C]
+  bool have_R_ = false, have_w_ = false, diffuse_ = false, smi_ = false;
+  std::vector<double> mpos_; double sspeed_ = 343740.0; double mu_ = 0.0;
+};
+typedef std::shared_ptr<SubbandMVDR> SubbandMVDRPtr;
+
+class SubbandMVDRGSC : public SubbandMVDR {
+ public:
+  SubbandMVDRGSC(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandMVDR") : SubbandMVDR(fftLen, half_band_shift, nm) {}
+  void set_active_weights_f(unsigned fbinX, const std::vector<double>& packedWeight);
+  void zero_active_weights() { wa_.clear(); have_wa_ = false; invalidate_(); }
+  bool calc_blocking_matrix1(double samplerate, const std::vector<double>& delaysT) { calc_array_manifold_vectors(samplerate, delaysT); return true; }
+ protected:
+  void configure_weights_(btkb_pipeline* p) override;
+  std::vector<std::complex<float>> wa_; bool have_wa_ = false;
+};
+typedef std::shared_ptr<SubbandMVDRGSC> SubbandMVDRGSCPtr;
+
+// ----------------------------------------------------------------------------------------------------------------
+class ZelinskiPostFilter : public VectorComplexFeatureStream {
+ public:
+  ZelinskiPostFilter(const VectorComplexFeatureStreamPtr& output, unsigned fftLen, double alpha = 0.6, int type = 2, int min_frames = 0,
+                     const std::string& nm = "ZelinskPostFilter");
+  const cplx* next(int frame_no = -5) override;
+  void reset() override;
+  void set_beamformer(const SubbandDSPtr& bf) { bf_ = bf; }
+  std::vector<cplx> postfilter_weights();
+  const SubbandDSPtr& beamformer() const { return bf_; }
+  PostFilterConfig config() const { PostFilterConfig c; c.enabled = true; c.alpha = alpha_; c.type = type_; c.min_frames = min_frames_; return c; }
+  const VectorComplexFeatureStreamPtr& source() const { return samp_; }
+ private:
+  unsigned fftLen_; VectorComplexFeatureStreamPtr samp_; double alpha_; int type_, min_frames_;
+  SubbandDSPtr bf_;
+};
+typedef std::shared_ptr<ZelinskiPostFilter> ZelinskiPostFilterPtr;
+
+class OverSampledDFTSynthesisBank : public VectorFloatFeatureStream {
+ public:
+  OverSampledDFTSynthesisBank(const VectorComplexFeatureStreamPtr& samp, const std::vector<double>& prototype, unsigned M, unsigned m, unsigned r = 0,
+                              unsigned delay_compensation_type = 0, int gain_factor = 1, const std::string& nm = "OverSampledDFTSynthesisBank");
+  ~OverSampledDFTSynthesisBank();
+  const float* next(int frame_no = -5) override;
+  void reset() override;
+  double polyphase(unsigned m, unsigned n) const { return prototype_.at(m + M_ * n); }
+ private:
+  void realize_();
+  VectorComplexFeatureStreamPtr samp_;
+  std::vector<double> prototype_;
+  unsigned M_, m_, r_, D_, dct_; int gain_; int pd_;
+  btkb_pipeline* pipe_;            // only for the generic (arbitrary upstream) path
+  std::vector<float> out_; int nb_; bool realized_;
+};
+typedef std::shared_ptr<OverSampledDFTSynthesisBank> OverSampledDFTSynthesisBankPtr;
+
+// delays (beamformer.cc:1170-1189 calc_all_delays)
+std::vector<double> calc_all_delays(double x, double y, double z, const std::vector<double>& mpos /* [C][3] */);
+
+}  // namespace btk20

@@ -1,0 +1,216 @@
+// btk20_pybind.cc — Python surface of the C++ host mirror (pybind11 stands in for SWIG, which is not installed).
+// Mirrors the SWIG interface files of the reference: stream/stream.i, feature/feature.i:205-250, modulated/modulated.i:91-192,
+// beamformer/beamformer.i:46-540, postfilter/postfilter.i:46-90, include/jexception.i:20-86 (exception map).
+#include <pybind11/complex.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "btk20_host.h"
+
+namespace py = pybind11;
+using namespace btk20;
+
+namespace {
+
+// stream/pyStream.h:25-133 — a Python iterable exposing __iter__/next/size/reset as a C++ stream
+class PyVectorComplexFeatureStream : public VectorComplexFeatureStream {
+ public:
+  PyVectorComplexFeatureStream(py::object obj, const std::string& nm)
+      : VectorComplexFeatureStream(py::cast<unsigned>(obj.attr("size")()), nm), obj_(obj), iter_(py::none()) {}
+  const cplx* next(int frame_no = -5) override {
+    if (frame_no == frame_no_) return vector_.data();
+    py::gil_scoped_acquire gil;
+    if (iter_.is_none()) iter_ = obj_.attr("__iter__")();
+    py::object item;
+    try {
+      item = py::hasattr(iter_, "__next__") ? iter_.attr("__next__")() : iter_.attr("next")();
+    } catch (py::error_already_set& e) {
+      if (e.matches(PyExc_StopIteration)) { is_end_ = true; throw jiterator_error("end of samples!"); }
+      throw;
+    }
+    auto arr = py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast>::ensure(item);
+    if (!arr || (unsigned)arr.size() != size()) throw jdimension_error("PyFeatureStream: expected a complex vector of length %d", size());
+    std::memcpy(vector_.data(), arr.data(), sizeof(cplx) * size());
+    increment_();
+    return vector_.data();
+  }
+  void reset() override {
+    py::gil_scoped_acquire gil;
+    if (py::hasattr(obj_, "reset")) obj_.attr("reset")();
+    iter_ = py::none();
+    VectorComplexFeatureStream::reset();
+  }
+ private:
+  py::object obj_, iter_;
+};
+
+template <class T, class S>
+py::array_t<T> view(S& self, const T* p, size_t n) {  // aliases internal storage, like PyArray_FromDimsAndData (include/vector.i:302)
+  return py::array_t<T>({n}, {sizeof(T)}, p, py::cast(&self, py::return_value_policy::reference));
+}
+
+template <class Cls, class PyCls>
+void add_complex_stream_api(PyCls& c) {
+  c.def("next", [](Cls& s, int frame_no) { const cplx* p = s.next(frame_no); return view<cplx>(s, p, s.size()); }, py::arg("frame_no") = -5)
+      .def("__next__", [](Cls& s) { const cplx* p = s.next(-5); return view<cplx>(s, p, s.size()); })
+      .def("__iter__", [](py::object self) { self.attr("reset")(); return self; })
+      .def("reset", &Cls::reset)
+      .def("size", &Cls::size)
+      .def("is_end", &Cls::is_end)
+      .def("frame_no", &Cls::frame_no)
+      .def("name", &Cls::name);
+}
+template <class Cls, class PyCls>
+void add_float_stream_api(PyCls& c) {
+  c.def("next", [](Cls& s, int frame_no) { const float* p = s.next(frame_no); return view<float>(s, p, s.size()); }, py::arg("frame_no") = -5)
+      .def("__next__", [](Cls& s) { const float* p = s.next(-5); return view<float>(s, p, s.size()); })
+      .def("__iter__", [](py::object self) { self.attr("reset")(); return self; })
+      .def("reset", &Cls::reset)
+      .def("size", &Cls::size)
+      .def("is_end", &Cls::is_end)
+      .def("frame_no", &Cls::frame_no)
+      .def("name", &Cls::name);
+}
+std::vector<double> vec_d(py::array_t<double, py::array::c_style | py::array::forcecast> a) { return std::vector<double>(a.data(), a.data() + a.size()); }
+
+}  // namespace
+
+PYBIND11_MODULE(_btk20host, m) {
+  m.doc() = "C++ host mirror of btk2.0's hot-path stream classes over libbtkb.so (sm_100a CUDA)";
+
+  // include/jexception.i:20-86
+  static py::exception<j_error> ex_base(m, "j_error", PyExc_Exception);
+  py::register_exception_translator([](std::exception_ptr p) {
+    try { if (p) std::rethrow_exception(p); }
+    catch (const jiterator_error& e) { PyErr_SetString(PyExc_StopIteration, "stop iteration"); }
+    catch (const jallocation_error& e) { PyErr_SetString(PyExc_MemoryError, e.what()); }
+    catch (const jarithmetic_error& e) { PyErr_SetString(PyExc_ArithmeticError, e.what()); }
+    catch (const jnumeric_error& e) { PyErr_SetString(PyExc_FloatingPointError, e.what()); }
+    catch (const jindex_error& e) { PyErr_SetString(PyExc_IndexError, e.what()); }
+    catch (const jio_error& e) { PyErr_SetString(PyExc_IOError, e.what()); }
+    catch (const jkey_error& e) { PyErr_SetString(PyExc_KeyError, e.what()); }
+    catch (const jparameter_error& e) { PyErr_SetString(PyExc_ValueError, e.what()); }
+    catch (const jparse_error& e) { PyErr_SetString(PyExc_SyntaxError, e.what()); }
+    catch (const jtype_error& e) { PyErr_SetString(PyExc_TypeError, e.what()); }
+    catch (const j_error& e) { PyErr_SetString(PyExc_Exception, e.what()); }
+  });
+
+  py::class_<VectorFloatFeatureStream, VectorFloatFeatureStreamPtr> vf(m, "VectorFloatFeatureStreamPtr");
+  add_float_stream_api<VectorFloatFeatureStream>(vf);
+  py::class_<VectorComplexFeatureStream, VectorComplexFeatureStreamPtr> vc(m, "VectorComplexFeatureStreamPtr");
+  add_complex_stream_api<VectorComplexFeatureStream>(vc);
+
+  py::class_<PyVectorComplexFeatureStream, VectorComplexFeatureStream, std::shared_ptr<PyVectorComplexFeatureStream>>(m, "PyVectorComplexFeatureStreamPtr")
+      .def(py::init<py::object, const std::string&>(), py::arg("obj"), py::arg("nm") = "PyVectorComplexFeatureStream");
+
+  py::class_<SampleFeature, VectorFloatFeatureStream, SampleFeaturePtr>(m, "SampleFeaturePtr")
+      .def(py::init<const std::string&, unsigned, unsigned, bool, const std::string&>(), py::arg("fn") = "", py::arg("block_len") = 320,
+           py::arg("shift_len") = 160, py::arg("pad_zeros") = false, py::arg("nm") = "Sample")
+      .def("read", &SampleFeature::read, py::arg("fn"), py::arg("format") = 0, py::arg("samplerate") = 16000, py::arg("chX") = 1, py::arg("chN") = 1,
+           py::arg("cfrom") = 0, py::arg("to") = -1, py::arg("outsamplerate") = -1, py::arg("norm") = 0.0f)
+      .def("setSamples", [](SampleFeature& s, py::array_t<double, py::array::c_style | py::array::forcecast> a, unsigned rate) { s.set_samples(a.data(), (unsigned)a.size(), rate); },
+           py::arg("samples"), py::arg("samplerate"))
+      .def("set_samples", [](SampleFeature& s, py::array_t<double, py::array::c_style | py::array::forcecast> a, unsigned rate) { s.set_samples(a.data(), (unsigned)a.size(), rate); },
+           py::arg("samples"), py::arg("samplerate"))
+      .def("data", [](SampleFeature& s) { return view<float>(s, s.samples().data(), s.samples().size()); })
+      .def("samplesN", &SampleFeature::samplesN)
+      .def("getSampleRate", &SampleFeature::samplerate);
+
+  py::class_<OverSampledDFTAnalysisBank, VectorComplexFeatureStream, OverSampledDFTAnalysisBankPtr>(m, "OverSampledDFTAnalysisBankPtr")
+      .def(py::init([](VectorFloatFeatureStreamPtr samp, py::array_t<double, py::array::c_style | py::array::forcecast> prototype, unsigned M, unsigned mm, unsigned r,
+                       unsigned dct, const std::string& nm) { return std::make_shared<OverSampledDFTAnalysisBank>(samp, vec_d(prototype), M, mm, r, dct, nm); }),
+           py::arg("samp"), py::arg("prototype"), py::arg("M") = 256, py::arg("m") = 3, py::arg("r") = 0, py::arg("delay_compensation_type") = 0,
+           py::arg("nm") = "OverSampledDFTAnalysisBankFloat")
+      .def("fftlen", &OverSampledDFTAnalysisBank::fftlen)
+      .def("shiftlen", &OverSampledDFTAnalysisBank::shiftlen)
+      .def("fftLen", &OverSampledDFTAnalysisBank::fftlen)
+      .def("polyphase", &OverSampledDFTAnalysisBank::polyphase, py::arg("m"), py::arg("n"));
+
+  py::class_<OverSampledDFTSynthesisBank, VectorFloatFeatureStream, OverSampledDFTSynthesisBankPtr>(m, "OverSampledDFTSynthesisBankPtr")
+      .def(py::init([](VectorComplexFeatureStreamPtr samp, py::array_t<double, py::array::c_style | py::array::forcecast> prototype, unsigned M, unsigned mm, unsigned r,
+                       unsigned dct, int gain, const std::string& nm) { return std::make_shared<OverSampledDFTSynthesisBank>(samp, vec_d(prototype), M, mm, r, dct, gain, nm); }),
+           py::arg("samp"), py::arg("prototype"), py::arg("M"), py::arg("m"), py::arg("r") = 0, py::arg("delay_compensation_type") = 0, py::arg("gain_factor") = 1,
+           py::arg("nm") = "OverSampledDFTSynthesisBank")
+      .def("polyphase", &OverSampledDFTSynthesisBank::polyphase, py::arg("m"), py::arg("n"));
+
+  py::class_<SnapShotArray, SnapShotArrayPtr>(m, "SnapShotArrayPtr")
+      .def(py::init<unsigned, unsigned>(), py::arg("fftlen"), py::arg("chan_num"))
+      .def("snapshot", [](SnapShotArray& s, unsigned f) { return view<cplx>(s, s.snapshot(f), s.nChan()); }, py::arg("fbinX"))
+      .def("set_samples", [](SnapShotArray& s, py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> a, unsigned ch) {
+        if ((unsigned)a.size() != s.fftLen()) throw jdimension_error("set_samples: expected %d bins", s.fftLen());
+        s.set_samples(a.data(), ch); }, py::arg("samp"), py::arg("chanX"))
+      .def("update", &SnapShotArray::update).def("zero", &SnapShotArray::zero).def("fftLen", &SnapShotArray::fftLen).def("nChan", &SnapShotArray::nChan);
+
+  py::class_<SubbandBeamformer, VectorComplexFeatureStream, SubbandBeamformerPtr>(m, "SubbandBeamformerPtr")
+      .def("set_channel", &SubbandBeamformer::set_channel, py::arg("chan"))
+      .def("clear_channel", &SubbandBeamformer::clear_channel)
+      .def("fftLen", &SubbandBeamformer::fftLen).def("chanN", &SubbandBeamformer::chanN)
+      .def("snapshot_array", &SubbandBeamformer::snapshot_array)
+      .def("get_weights", &SubbandBeamformer::get_weights, py::arg("fbinX"));
+
+  py::class_<SubbandDS, SubbandBeamformer, SubbandDSPtr>(m, "SubbandDSPtr")
+      .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandDS>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,
+           py::arg("half_band_shift") = false, py::arg("nm") = "SubbandDS")
+      .def("calc_array_manifold_vectors", [](SubbandDS& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { s.calc_array_manifold_vectors(fs, vec_d(d)); },
+           py::arg("samplerate"), py::arg("delays"));
+
+  py::class_<SubbandGSC, SubbandDS, SubbandGSCPtr>(m, "SubbandGSCPtr")
+      .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandGSC>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,
+           py::arg("half_band_shift") = false, py::arg("nm") = "SubbandGSC")
+      .def("calc_gsc_weights", [](SubbandGSC& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { s.calc_gsc_weights(fs, vec_d(d)); },
+           py::arg("samplerate"), py::arg("delaysT"))
+      .def("set_active_weights_f", [](SubbandGSC& s, unsigned f, py::array_t<double, py::array::c_style | py::array::forcecast> w) { s.set_active_weights_f(f, vec_d(w)); },
+           py::arg("fbinX"), py::arg("packedWeight"))
+      .def("zero_active_weights", &SubbandGSC::zero_active_weights);
+
+  py::class_<LmsConfig>(m, "LmsConfig")
+      .def(py::init<>())
+      .def_readwrite("beta", &LmsConfig::beta).def_readwrite("gamma", &LmsConfig::gamma).def_readwrite("init_diagonal_load", &LmsConfig::init_diagonal_load)
+      .def_readwrite("regularization_param", &LmsConfig::regularization_param).def_readwrite("energy_floor", &LmsConfig::energy_floor)
+      .def_readwrite("sil_thresh", &LmsConfig::sil_thresh).def_readwrite("max_wa_l2norm", &LmsConfig::max_wa_l2norm)
+      .def_readwrite("min_frames", &LmsConfig::min_frames).def_readwrite("slowdown_after", &LmsConfig::slowdown_after);
+
+  py::class_<SubbandGSCLMS, SubbandDS, SubbandGSCLMSPtr>(m, "SubbandGSCLMSPtr")
+      .def(py::init([](unsigned fftlen, const LmsConfig& c, const std::string& nm) { return std::make_shared<SubbandGSCLMS>(fftlen, c, nm); }), py::arg("fftlen"),
+           py::arg("config"), py::arg("nm") = "SubbandGSCLMS")
+      .def("calc_beamformer_weights", [](SubbandGSCLMS& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { s.calc_beamformer_weights(fs, vec_d(d)); },
+           py::arg("samplerate"), py::arg("delays"))
+      .def("active_weights", [](SubbandGSCLMS& s) {
+        auto w = s.active_weights();
+        py::array_t<std::complex<float>> a({(size_t)(s.fftLen() / 2 + 1), (size_t)(s.chanN() - 1)});
+        std::memcpy(a.mutable_data(), w.data(), sizeof(std::complex<float>) * w.size());
+        return a; })
+      .def("total_updates", &SubbandGSCLMS::total_updates);
+
+  py::class_<SubbandMVDR, SubbandDS, SubbandMVDRPtr>(m, "SubbandMVDRPtr")
+      .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandMVDR>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,
+           py::arg("half_band_shift") = false, py::arg("nm") = "SubbandMVDR")
+      .def("calc_mvdr_weights", &SubbandMVDR::calc_mvdr_weights, py::arg("samplerate"), py::arg("dthreshold") = 1.0e-8, py::arg("calc_inverse_matrix") = true)
+      .def("mvdr_weights", &SubbandMVDR::mvdr_weights, py::arg("fbinX"))
+      .def("set_noise_spatial_spectral_matrix", [](SubbandMVDR& s, unsigned f, py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> R) {
+        return s.set_noise_spatial_spectral_matrix(f, std::vector<cplx>(R.data(), R.data() + R.size())); }, py::arg("fbinX"), py::arg("Rnn"))
+      .def("set_diffuse_noise_model", [](SubbandMVDR& s, py::array_t<double, py::array::c_style | py::array::forcecast> mpos, double fs, double c) {
+        return s.set_diffuse_noise_model(vec_d(mpos), fs, c); }, py::arg("micPositions"), py::arg("samplerate"), py::arg("sspeed") = 343740.0)
+      .def("set_all_diagonal_loading", &SubbandMVDR::set_all_diagonal_loading, py::arg("diagonalWeight"))
+      .def("accumulate_noise_covariance", &SubbandMVDR::accumulate_noise_covariance, py::arg("samplerate"), py::arg("label_start"), py::arg("label_end"),
+           py::arg("energy_threshold"));
+
+  py::class_<SubbandMVDRGSC, SubbandMVDR, SubbandMVDRGSCPtr>(m, "SubbandMVDRGSCPtr")
+      .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandMVDRGSC>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,
+           py::arg("half_band_shift") = false, py::arg("nm") = "SubbandMVDR")
+      .def("set_active_weights_f", [](SubbandMVDRGSC& s, unsigned f, py::array_t<double, py::array::c_style | py::array::forcecast> w) { s.set_active_weights_f(f, vec_d(w)); },
+           py::arg("fbinX"), py::arg("packedWeight"))
+      .def("zero_active_weights", &SubbandMVDRGSC::zero_active_weights)
+      .def("calc_blocking_matrix1", [](SubbandMVDRGSC& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { return s.calc_blocking_matrix1(fs, vec_d(d)); },
+           py::arg("samplerate"), py::arg("delaysT"));
+
+  py::class_<ZelinskiPostFilter, VectorComplexFeatureStream, ZelinskiPostFilterPtr>(m, "ZelinskiPostFilterPtr")
+      .def(py::init<const VectorComplexFeatureStreamPtr&, unsigned, double, int, int, const std::string&>(), py::arg("output"), py::arg("M"), py::arg("alpha") = 0.6,
+           py::arg("type") = 2, py::arg("min_frames") = 0, py::arg("nm") = "ZelinskPostFilter")
+      .def("set_beamformer", &ZelinskiPostFilter::set_beamformer, py::arg("beamformer"))
+      .def("postfilter_weights", &ZelinskiPostFilter::postfilter_weights);
+
+  m.def("calc_all_delays", [](double x, double y, double z, py::array_t<double, py::array::c_style | py::array::forcecast> mpos) { return calc_all_delays(x, y, z, vec_d(mpos)); },
+        py::arg("x"), py::arg("y"), py::arg("z"), py::arg("mpos"));
+}

@@ -73,6 +73,7 @@ typedef struct btkb_config {
   int max_utterances;          /* capacity of one batch */
   int max_samples;             /* capacity: samples per channel per utterance */
   int keep_snapshots;          /* 1: keep the analysis output X resident so btkb_fetch_snapshots works (always true today) */
+  int synthesis_gain;          /* OverSampledDFTSynthesisBank gain_factor (modulated.cc:608-609); default 1 */
 } btkb_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */
@@ -113,6 +114,11 @@ int btkb_run_analysis(btkb_pipeline* p);
 int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float energy_threshold);
 /* the per-bin beamformer (+ post-filter) over the resident snapshots, then synthesis when do_synthesis != 0 */
 int btkb_run_beamformer(btkb_pipeline* p, int do_synthesis);
+/* inject beamformed subband frames from the host, Y [U][T][K] complex64 (the stream an arbitrary upstream
+ * VectorComplexFeatureStream would deliver to OverSampledDFTSynthesisBank::next, modulated.cc:533-549), then
+ * btkb_run_synthesis resynthesises them.  lengths are taken from T: every utterance is treated as T frames long. */
+int btkb_set_subband(btkb_pipeline* p, int U, int T, const float* Y);
+int btkb_run_synthesis(btkb_pipeline* p);
 /* whole pipe: analysis -> beamformer (+post-filter) -> synthesis */
 int btkb_run(btkb_pipeline* p, int do_synthesis);
 int btkb_synchronize(btkb_pipeline* p);

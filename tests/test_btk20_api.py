@@ -1,0 +1,184 @@
+"""The reference's Python surface (btk20.*) over the C++ host mirror.  CPU part: stream protocol, SampleFeature block
+logic (feature/feature.cc:605-649), wav reading, exception mapping (include/jexception.i:20-86).  GPU part (-m gpu): the
+front-end script flow of unit_test/test_online_beamforming.py:51-228 / test_sos_batch_beamforming.py:95-233 reproduced
+with the same calls and compared with the reference goldens."""
+import os
+import struct
+import wave
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+
+btk20 = pytest.importorskip("distant_speech_recognition_b200.btk20")
+from distant_speech_recognition_b200.btk20.feature import SampleFeaturePtr  # noqa: E402
+from distant_speech_recognition_b200.btk20.modulated import OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, get_window  # noqa: E402
+from distant_speech_recognition_b200.btk20.beamformer import SubbandDSPtr, SubbandGSCPtr, SnapShotArrayPtr, calc_all_delays  # noqa: E402
+from distant_speech_recognition_b200.btk20.postfilter import ZelinskiPostFilterPtr  # noqa: E402
+from distant_speech_recognition_b200.btk20.stream import PyVectorComplexFeatureStreamPtr  # noqa: E402
+from distant_speech_recognition_b200.btk20 import pybeamformer  # noqa: E402
+
+FS = 16000
+
+
+def test_sample_feature_blocks_and_padding():
+    s = SampleFeaturePtr(block_len=128, shift_len=128, pad_zeros=True)
+    x = np.arange(300, dtype=np.float64)
+    s.setSamples(x, FS)
+    assert s.samplesN() == 300 and s.size() == 128
+    blocks = [np.array(b) for b in s]            # __iter__ = reset(); return self  (feature.i)
+    assert len(blocks) == 3
+    assert np.array_equal(blocks[0], x[:128]) and np.array_equal(blocks[2][:44], x[256:]) and np.all(blocks[2][44:] == 0)
+    assert s.is_end() is False or True
+    with pytest.raises(StopIteration):            # jiterator_error -> StopIteration
+        s.next()
+    s.reset()
+    b0 = np.array(s.next(0)); again = np.array(s.next(0))   # frame_no == frame_no_ -> cached frame
+    assert np.array_equal(b0, again) and s.frame_no() == 0
+    with pytest.raises(IndexError):               # jindex_error: non-consecutive frame number (feature.cc:614-616)
+        s.next(5)
+    # without zero padding the last partial block ends the stream
+    s2 = SampleFeaturePtr(block_len=128, shift_len=128, pad_zeros=False); s2.setSamples(x, FS)
+    assert len([1 for _ in s2]) == 2
+
+
+def test_sample_feature_reads_wav(tmp_path):
+    path = os.path.join(tmp_path, "t.wav")
+    data = (np.arange(-500, 500) * 7).astype(np.int16)
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(FS); w.writeframes(data.tobytes())
+    s = SampleFeaturePtr(block_len=256, shift_len=256, pad_zeros=True)
+    n = s.read(path, FS)                          # test_online_beamforming.py:83 call shape
+    assert n == 1000 and np.array_equal(np.array(s.data()), data.astype(np.float32))   # norm=0: raw int16-scale floats
+    with pytest.raises(IOError):
+        s.read(os.path.join(tmp_path, "missing.wav"), FS)
+
+
+def test_constructor_checks_and_misc(protos):
+    h, g = protos[256]
+    s = SampleFeaturePtr(block_len=100, shift_len=100, pad_zeros=True)
+    with pytest.raises(Exception):                # jdimension_error: Input block length != D (modulated.cc:337-338)
+        OverSampledDFTAnalysisBankPtr(s, prototype=h, M=256, m=4, r=1, delay_compensation_type=2)
+    s = SampleFeaturePtr(block_len=128, shift_len=128, pad_zeros=True)
+    with pytest.raises(Exception):                # jconsistency_error: prototype size (modulated.cc:239-241)
+        OverSampledDFTAnalysisBankPtr(s, prototype=h[:100], M=256, m=4, r=1, delay_compensation_type=2)
+    afb = OverSampledDFTAnalysisBankPtr(s, prototype=h, M=256, m=4, r=1, delay_compensation_type=2)
+    assert afb.fftlen() == 256 and afb.shiftlen() == 128 and afb.size() == 256
+    assert afb.polyphase(3, 2) == h[3 + 256 * 2]
+    ds = SubbandDSPtr(fftlen=256, half_band_shift=False)
+    ds.set_channel(afb)
+    with pytest.raises(Exception):                # delays/channels mismatch (beamformer.cc:504-506)
+        ds.calc_array_manifold_vectors(FS, np.zeros(3))
+    snap = SnapShotArrayPtr(8, 2)
+    snap.set_samples(np.arange(8) + 1j, 0); snap.set_samples(np.arange(8) * 2.0, 1); snap.update()
+    assert np.allclose(np.array(snap.snapshot(3)), [3 + 1j, 6])
+    assert np.allclose(get_window(2, 5), 0.5 * (1 - np.cos(2 * np.pi * np.arange(5) / 4)))
+    d = calc_all_delays(0, 0, 0, np.array([[0.0, 0, 0], [30.0, 40.0, 0], [0, 0, 100.0]]))
+    assert np.allclose(d, (np.array([0.0, 50.0, 100.0]) - 50.0) / 343740.0)
+    mpos = [[-113.0, 0, 2], [36.0, 0, 2], [76.0, 0, 2], [113.0, 0, 2]]
+    from oracle import restate
+    assert np.allclose(pybeamformer.calc_delays("linear", mpos, [-1.306379, None, None]), restate.calc_la_delays(mpos, -1.306379))
+    assert np.allclose(pybeamformer.calc_nf_delays(mpos, 10.0, 500.0, 3.0), restate.calc_nf_delays(mpos, 10.0, 500.0, 3.0))
+
+
+def _afbs(x, h, M, D):
+    afbs = []
+    for c in range(x.shape[0]):
+        sf = SampleFeaturePtr(block_len=D, shift_len=D, pad_zeros=True)
+        sf.setSamples(x[c].astype(np.float64), FS)
+        afbs.append(OverSampledDFTAnalysisBankPtr(sf, prototype=h, M=M, m=4, r=1, delay_compensation_type=2))
+    return afbs
+
+
+@pytest.mark.gpu
+def test_frontend_flow_gsclms(protos):
+    """unit_test/test_online_beamforming.py with "type":"gsclms": afbs -> SubbandGSCLMSBeamformer -> PyVectorComplexFeatureStreamPtr
+    -> OverSampledDFTSynthesisBankPtr; for buf in sfb."""
+    g = load_golden("gsclms_c8_m512"); h, gg = protos[512]; M, D = 512, 256
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandGSCLMSBeamformer(afbs, min_frames=int(g["min_frames"]))
+    bf.calc_beamformer_weights(FS, g["delays"])
+    spatial_filter = PyVectorComplexFeatureStreamPtr(bf)
+    sfb = OverSampledDFTSynthesisBankPtr(spatial_filter, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    out, total_energy = [], 0.0
+    for frame_no, buf in enumerate(sfb):
+        total_energy += np.inner(buf, buf); out.append(np.array(buf))
+    y = np.concatenate(out)
+    assert y.shape == g["time"].shape and rel_l2(y, g["time"]) < 1e-4
+    assert abs(total_energy - g["stats"][0]) < 1e-4 * g["stats"][0]
+    assert bf.total_updates() == g["stats"][2]
+    assert rel_l2(bf.active_weights(), g["waH"]) < 1e-3
+    # the subband stream itself, with Hermitian fill, and idempotent re-read
+    bf.reset()
+    Y = np.array([np.array(v) for v in bf])
+    assert Y.shape == (g["Y"].shape[0], M) and rel_l2(Y[:, :257], g["Y"]) < 1e-4
+    assert np.allclose(Y[:, 300], np.conj(Y[:, M - 300]))
+    # second utterance through the same graph: reset() rewinds everything and restarts adaptation
+    sfb.reset()
+    y2 = np.concatenate([np.array(b) for b in sfb])
+    assert np.array_equal(y, y2)
+
+
+@pytest.mark.gpu
+def test_frontend_flow_gsc_zelinski(protos):
+    """D&S/GSC + Zelinski (confs/ds_and_zelinski.json flow): ZelinskiPostFilterPtr(pybf, M, alpha, subtype); set_beamformer."""
+    g = load_golden("gsc_zelinski_c8_m512"); h, gg = protos[512]; M, D = 512, 256
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandGSCBeamformer(afbs, Nc=1)
+    bf._waH[:257] = g["wa"]
+    bf.calc_beamformer_weights(FS, g["delays"])
+    pybf = PyVectorComplexFeatureStreamPtr(bf)
+    pf = ZelinskiPostFilterPtr(pybf, M, 0.7, 2)
+    pf.set_beamformer(bf.beamformer())
+    sfb = OverSampledDFTSynthesisBankPtr(pf, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert rel_l2(y, g["time"]) < 1e-4
+    pf.reset()
+    Y = np.array([np.array(v) for v in pf])
+    assert rel_l2(Y[:, :257], g["Y"]) < 1e-4
+    w = np.real(np.array(pf.postfilter_weights()))
+    assert w[:257].min() >= 1e-4 - 1e-9 and w.max() <= 1.0
+    assert rel_l2(np.array(bf.beamformer().get_weights(17)), g["wq"][17]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_frontend_flow_smimvdr(protos):
+    """unit_test/test_sos_batch_beamforming.py:186-223 with "type":"smimvdr"."""
+    g = load_golden("smimvdr_zelinski_c8_m512"); h, gg = protos[512]; M, D = 512, 256
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandSMIMVDRBeamformer(afbs, Nc=1)
+    bf.accu_stats_from_label(FS, target_labs=[(0.25, 0.75)], energy_threshold=10)
+    bf.finalize_stats()
+    bf.calc_beamformer_weights(FS, g["delays"], mu=float(g["mu"]))
+    pf = ZelinskiPostFilterPtr(PyVectorComplexFeatureStreamPtr(bf), M, 0.7, 2)
+    pf.set_beamformer(bf.beamformer())
+    sfb = OverSampledDFTSynthesisBankPtr(pf, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert rel_l2(y, g["time"]) < 3e-4      # bounded by the reference's float-SVD noise (tests/test_parity_gpu.py)
+
+
+@pytest.mark.gpu
+def test_generic_python_stream_into_synthesis_and_analysis_iteration(protos):
+    """A pure-Python spatial filter between the banks (the reference's PyFeatureStream use): analysis frames are pulled
+    one by one in Python, modified, and fed to the synthesis bank through PyVectorComplexFeatureStreamPtr."""
+    from oracle import restate
+    h, gg = protos[256]; M, D = 256, 128
+    rng = np.random.default_rng(0)
+    x = (1000 * rng.standard_normal(5000)).astype(np.float32)
+    sf = SampleFeaturePtr(block_len=D, shift_len=D, pad_zeros=True); sf.setSamples(x.astype(np.float64), FS)
+    afb = OverSampledDFTAnalysisBankPtr(sf, prototype=h, M=M, m=4, r=1, delay_compensation_type=2)
+    X = np.array([np.array(v) for v in afb])
+    Xo = restate.analysis(x, h, M, 4, 1)
+    assert X.shape == Xo.shape and rel_l2(X, Xo) < 1e-5
+
+    class Halve:
+        def __init__(self, src): self.src = src
+        def __iter__(self):
+            for v in self.src: yield 0.5 * np.array(v)
+        def size(self): return self.src.size()
+        def reset(self): self.src.reset()
+    sfb = OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(Halve(afb)), prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    yo = restate.synthesis(0.5 * Xo, gg, M, 4, 1)
+    assert y.shape == yo.shape and rel_l2(y, yo) < 1e-5
