@@ -156,6 +156,20 @@ class Pipeline:
             lp = self._len.ctypes.data_as(ct.POINTER(ct.c_int))
         _check(lib.btkb_submit(self._h, ct.cast(ct.c_void_p(host_ptr), ct.POINTER(ct.c_float)), ct.c_int(U), ct.c_int(n), lp))
 
+    def submit_i16_pointer(self, host_ptr, U, n, lengths=None):
+        """16-bit PCM host buffer [U][C][n] (e.g. a pinned torch int16 tensor's data_ptr())."""
+        self.U, self.n = U, n
+        lp = None
+        if lengths is not None:
+            self._len = np.ascontiguousarray(lengths, np.int32)
+            lp = self._len.ctypes.data_as(ct.POINTER(ct.c_int))
+        _check(lib.btkb_submit_i16(self._h, ct.cast(ct.c_void_p(host_ptr), ct.POINTER(ct.c_int16)), ct.c_int(U), ct.c_int(n), lp))
+
+    def submit_i16(self, samples, lengths=None):
+        s = np.ascontiguousarray(samples, np.int16)
+        self._keep = s
+        self.submit_i16_pointer(s.ctypes.data, s.shape[0], s.shape[2], lengths)
+
     def submit_device(self, dev_ptr, U, n, lengths=None):
         self.U, self.n = U, n
         lp = None

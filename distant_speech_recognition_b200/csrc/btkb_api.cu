@@ -37,6 +37,7 @@ struct btkb_pipeline {
   double *d_delays = nullptr, *d_mpos = nullptr, *d_labels = nullptr, *d_stats = nullptr;
   unsigned char* d_mask = nullptr; int* d_count = nullptr;
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
+  int16_t* d_x16 = nullptr; double* h_delays = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0;
   std::vector<int> lengths;
@@ -80,7 +81,8 @@ void btkb_destroy(btkb_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
   void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
-                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch};
+                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16};
+  if (p->h_delays) cudaFreeHost(p->h_delays);
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -203,7 +205,13 @@ int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
   if ((p->cfg.beamformer == BTKB_BF_GSC || p->cfg.beamformer == BTKB_BF_GSC_LMS) && p->C <= 1)  // beamformer.cc:507-510
     return fail(BTKB_ERR_INVALID, "The number of channels must be > 1 but it is " + std::to_string(p->C));
   CK(cudaSetDevice(p->cfg.device));
-  CK(cudaMemcpyAsync(p->d_delays, delays, (size_t)U * p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  // stage through pinned host memory owned by the pipeline: the call stays asynchronous (no stream sync) and `delays`
+  // may be reused by the caller immediately
+  if (!p->h_delays) CK(cudaMallocHost((void**)&p->h_delays, (size_t)p->Ucap * p->C * sizeof(double)));
+  CK(cudaEventSynchronize(p->ev[4]));  // the previous delays upload (if any) has left the staging buffer
+  memcpy(p->h_delays, delays, (size_t)U * p->C * sizeof(double));
+  CK(cudaMemcpyAsync(p->d_delays, p->h_delays, (size_t)U * p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaEventRecord(p->ev[4], p->stream));
   WeightsArgs a{p->d_delays, p->d_TA, U, p->C, p->M, p->K, p->Gp, p->cfg.samplerate};
   CK(launch_mainlobe_weights(a, p->stream));
   p->have_ta = true;
@@ -211,7 +219,6 @@ int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
     CK(cudaMemcpyAsync(p->d_W, p->d_TA, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
     p->have_w = true;
   }
-  CK(cudaStreamSynchronize(p->stream));  // `delays` is caller memory
   return BTKB_OK;
 }
 
@@ -306,6 +313,27 @@ int btkb_submit(btkb_pipeline* p, const float* samples, int U, int n, const int*
   // [U][C][n] host -> [U][C][n_stride] device
   CK(cudaMemcpy2DAsync(p->d_x, (size_t)p->n_stride * sizeof(float), samples, (size_t)n * sizeof(float), (size_t)n * sizeof(float), (size_t)U * p->C,
                        cudaMemcpyHostToDevice, p->stream));
+  p->x_cur = p->d_x;
+  return BTKB_OK;
+}
+
+__global__ void k_i16_to_f32(const int16_t* __restrict__ src, float* __restrict__ dst, size_t rows, int n, int n_stride) {
+  const size_t total = rows * (size_t)n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / n; const int c = (int)(i - r * n);
+    dst[r * n_stride + c] = (float)src[i];
+  }
+}
+
+int btkb_submit_i16(btkb_pipeline* p, const int16_t* samples, int U, int n, const int* lengths) {
+  if (!p || !samples) return fail(BTKB_ERR_INVALID, "btkb_submit_i16: null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  int rc = submit_common(p, U, n, lengths); if (rc) return rc;
+  if (!p->d_x16) CK(cudaMalloc((void**)&p->d_x16, (size_t)p->Ucap * p->C * p->n_stride * sizeof(int16_t)));
+  const size_t rows = (size_t)U * p->C;
+  CK(cudaMemcpyAsync(p->d_x16, samples, rows * n * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
+  k_i16_to_f32<<<148 * 8, 256, 0, p->stream>>>(p->d_x16, p->d_x, rows, n, p->n_stride);
+  CK(cudaGetLastError());
   p->x_cur = p->d_x;
   return BTKB_OK;
 }

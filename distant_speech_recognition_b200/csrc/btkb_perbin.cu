@@ -29,7 +29,7 @@ namespace btkb {
 
 constexpr int TILE = 64;    // chains (threads) per CTA: 1028 CTAs at configs[1] = 6.95 per SM (balanced single wave)
 constexpr int FCH = 2;      // frames per ring slot: one 2-D TMA box is [FCH*C rows][TILE chains]
-constexpr int STAGES = 4;   // ring slots per CTA (3 slots = 6 frames in flight)
+constexpr int STAGES = 3;   // ring slots per CTA (2 slots = 4 frames in flight); 24 KiB per CTA so 7 CTAs fit one SM (single balanced wave)
 constexpr int NWARP = TILE / 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

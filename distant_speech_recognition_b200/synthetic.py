@@ -66,8 +66,10 @@ def _lowpass_noise(rng, n, fs, cutoff, sigma):
     return s * (sigma / max(np.std(s), 1e-12))
 
 
-def make_utterance(u, C, n, fs=16000.0, target_az=np.pi / 3, interferer_az=2 * np.pi / 3, target_start_s=1.0):
-    """Returns (samples float32 [C][n], delays_target float64 [C], mpos [C][3], array_type)."""
+def make_utterance(u, C, n, fs=16000.0, target_az=np.pi / 3, interferer_az=2 * np.pi / 3, target_start_s=1.0, pcm16=False):
+    """Returns (samples float32 [C][n], delays_target float64 [C], mpos [C][3], array_type).
+    pcm16=True rounds and clips to the int16 grid (what a 16-bit wav holds): the float32 values are then exactly
+    representable as int16, so the float and the 16-bit PCM entry points of the C-ABI see identical inputs."""
     rng = np.random.default_rng(BASE_SEED + int(u))
     array_type, mpos = array_for_channels(C)
     d_t = far_field_delays(array_type, mpos, target_az)
@@ -76,13 +78,15 @@ def make_utterance(u, C, n, fs=16000.0, target_az=np.pi / 3, interferer_az=2 * n
     s[: min(n, int(target_start_s * fs))] = 0.0
     j = _lowpass_noise(rng, n, fs, 4000.0, 1500.0)
     x = _delayed_copies(s, d_t, fs) + _delayed_copies(j, d_j, fs) + 100.0 * rng.standard_normal((C, n))
+    if pcm16:
+        x = np.clip(np.rint(x), -32768, 32767)
     return x.astype(np.float32), d_t, mpos, array_type
 
 
-def make_batch(U, C, n, fs=16000.0, first=0):
+def make_batch(U, C, n, fs=16000.0, first=0, pcm16=False):
     """samples float32 [U][C][n], delays float64 [U][C]."""
     X = np.empty((U, C, n), np.float32)
     dl = np.empty((U, C), np.float64)
     for u in range(U):
-        X[u], dl[u], _, _ = make_utterance(first + u, C, n, fs)
+        X[u], dl[u], _, _ = make_utterance(first + u, C, n, fs, pcm16=pcm16)
     return X, dl

@@ -105,6 +105,9 @@ int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu);
 /* host samples float32 [U][C][n] (int16 scale, like SampleFeature, feature/feature.cc:605-649), lengths[U] <= n (NULL: all n).
  * Asynchronous H2D on the pipeline stream (pinned host memory recommended). */
 int btkb_submit(btkb_pipeline* p, const float* samples, int U, int n, const int* lengths);
+/* 16-bit PCM variant (what SampleFeature::read gets from a wav file before its float conversion, feature/feature.cc:265-305,
+ * norm == 0): host samples int16 [U][C][n]; halves the H2D bytes, the int16 -> float32 conversion runs on the device. */
+int btkb_submit_i16(btkb_pipeline* p, const int16_t* samples, int U, int n, const int* lengths);
 /* same, but `samples` is a DEVICE pointer in the same layout (no copy) */
 int btkb_submit_device(btkb_pipeline* p, const float* d_samples, int U, int n, const int* lengths);
 /* analysis only: time -> snapshots X (OverSampledDFTAnalysisBank + SnapShotArray) */
