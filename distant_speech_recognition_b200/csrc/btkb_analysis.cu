@@ -186,16 +186,24 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_r1(AnalysisArgs a) {
   // Asynchronous 16-byte copies with zero fill (cp.async ... src-size): every thread puts ~W/(2 NT G) chunks per channel
   // in flight at once, samples outside [0, len) arrive as zeros (w0 and W are multiples of 4, rows are 16 B aligned).
   static_assert(W % 4 == 0, "tile length must be a multiple of 4 samples");
-  for (int w = 4 * tid; w < W; w += 4 * G * NT) {
-    const long long s = w0 + w;
-    long long rem = (long long)len - s;                         // valid samples from s on
-    int nb = (s < 0 || rem <= 0) ? 0 : (rem >= 4 ? 16 : (int)rem * 4);
-    const float* pa = (nb > 0) ? xa + s : xa;
-    const float* pb = (nb > 0) ? xb + s : xb;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xsa + w)), "l"(pa), "r"(nb) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xsb + w)), "l"(pb), "r"(has_b ? nb : 0) : "memory");
+  // The copies are committed in NIT groups, group i holding the samples iteration i needs beyond those of iteration i-1,
+  // so the first frames start as soon as their window has landed while the rest of the tile is still in flight.
+  constexpr int NIT = FR / (2 * G);
+#pragma unroll
+  for (int gi = 0; gi < NIT; gi++) {
+    const int lo = (gi == 0) ? 0 : (2 * G * gi - 1) * D + MT * M;
+    const int hi = (2 * G * (gi + 1) - 1) * D + MT * M;
+    for (int w = lo + 4 * tid; w < hi; w += 4 * G * NT) {
+      const long long s = w0 + w;
+      long long rem = (long long)len - s;                         // valid samples from s on
+      int nb = (s < 0 || rem <= 0) ? 0 : (rem >= 4 ? 16 : (int)rem * 4);
+      const float* pa = (nb > 0) ? xa + s : xa;
+      const float* pb = (nb > 0) ? xb + s : xb;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xsa + w)), "l"(pa), "r"(nb) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xsb + w)), "l"(pb), "r"(has_b ? nb : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   // slot(q): register slot of polyphase index i_q = tg + NT q  (q = b + r NB, slot = b R0 + r)
 #define BTKB_SLOT(q) (((q) % NB) * R0 + (q) / NB)
   float hreg[8 * MT];
@@ -205,12 +213,24 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_r1(AnalysisArgs a) {
     for (int k = 0; k < MT; k++) hreg[BTKB_SLOT(q) * MT + k] = __ldg(a.h + (tg + NT * q) + k * M);
   FftTwiddles<M, +1> tw;
   tw.init(tg);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
 
   constexpr int K = M / 2 + 1;
   constexpr int NW = (NT + 31) / 32;
-  for (int f0 = 0; f0 < FR; f0 += 2 * G) {
+#pragma unroll 1
+  for (int it = 0; it < NIT; it++) {
+    const int f0 = it * 2 * G;
+    // groups 0..it must have landed: at most NIT-1-it of the most recent groups may still be pending
+    switch (NIT - 1 - it) {
+      case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+      case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+      case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+      case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+      case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+      case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+      default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+    __syncthreads();
     const int f = f0 + 2 * grp;
     const int ta = t0 + f, tb = ta + 1;
     const bool act0 = ta < a.T, act1 = tb < a.T;
