@@ -185,6 +185,7 @@ def run_ours(args):
         raise RuntimeError("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = CFG
     U, C, n, M, m, r = c["U"], c["C"], c["n"], c["M"], c["m"], c["r"]

@@ -33,7 +33,7 @@ class Config(ct.Structure):
     _fields_ = [("device", ct.c_int), ("channels", ct.c_int), ("fft_len", ct.c_int), ("m", ct.c_int), ("r", ct.c_int),
                 ("delay_compensation_type", ct.c_int), ("samplerate", ct.c_float), ("beamformer", ct.c_int),
                 ("postfilter", ct.c_int), ("pf_alpha", ct.c_float), ("pf_type", ct.c_int), ("pf_min_frames", ct.c_int),
-                ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int)]
+                ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int), ("normalize_weight", ct.c_int)]
 
 
 def _load():
@@ -71,7 +71,7 @@ class Pipeline:
 
     def __init__(self, channels, fft_len=512, m=4, r=1, delay_compensation_type=2, samplerate=16000.0, beamformer=BF_DS,
                  postfilter=PF_NONE, pf_alpha=0.6, pf_type=2, pf_min_frames=0, lms=None, max_utterances=1,
-                 max_samples=160000, device=0):
+                 max_samples=160000, device=0, normalize_weight=False):
         cfg = Config()
         lib.btkb_default_config(ct.byref(cfg))
         cfg.device = device; cfg.channels = channels; cfg.fft_len = fft_len; cfg.m = m; cfg.r = r
@@ -81,12 +81,13 @@ class Pipeline:
         if lms:
             for k, v in lms.items():
                 setattr(cfg.lms, k, v)
-        cfg.max_utterances = max_utterances; cfg.max_samples = max_samples
+        cfg.max_utterances = max_utterances; cfg.max_samples = max_samples; cfg.normalize_weight = 1 if normalize_weight else 0
         self.cfg = cfg
         self.C, self.M, self.K, self.D = channels, fft_len, fft_len // 2 + 1, fft_len >> r
         self._h = ct.c_void_p()
         _check(lib.btkb_create(ct.byref(cfg), ct.byref(self._h)))
         self.U = 0
+        self.NC = 1
 
     def close(self):
         if self._h:
@@ -112,6 +113,15 @@ class Pipeline:
         d = np.ascontiguousarray(np.atleast_2d(delays), np.float64)
         self.U = d.shape[0]
         _check(lib.btkb_set_delays(self._h, ct.c_int(d.shape[0]), _dp(d)))
+
+    def set_delays_lcmv(self, delaysT, delaysJ):
+        dT = np.ascontiguousarray(np.atleast_2d(delaysT), np.float64)
+        dJ = np.ascontiguousarray(delaysJ, np.float64).reshape(dT.shape[0], -1, self.C)
+        self.U = dT.shape[0]; self.NC = dJ.shape[1] + 1
+        _check(lib.btkb_set_delays_lcmv(self._h, ct.c_int(self.U), ct.c_int(self.NC), _dp(dT), _dp(dJ)))
+
+    def spectral_matrix_update(self, mu, legacy_noconj=True):
+        _check(lib.btkb_spectral_matrix_update(self._h, ct.c_float(mu), ct.c_int(1 if legacy_noconj else 0)))
 
     def set_weights(self, w):
         w = np.ascontiguousarray(w, np.complex64)
@@ -246,7 +256,7 @@ class Pipeline:
         return out
 
     def get_active_weights(self):
-        out = np.empty((self.U, self.K, self.C - 1), np.complex64)
+        out = np.empty((self.U, self.K, self.C - self.NC), np.complex64)
         _check(lib.btkb_get_active_weights(self._h, _fp(out)))
         return out
 

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) 
 // 64 (x2 channels) MACs.  The two transforms then advance pass by pass together (independent instruction streams, one
 // in-place buffer each, every barrier covers two transforms).
 template <int M, int MT, int FR, int G>
-__global__ void __launch_bounds__(G*(M / 8)) k_analysis_r1(AnalysisArgs a) {
+__global__ void __launch_bounds__(G*(M / 8), (FR == 8 ? 4 : 3)) k_analysis_r1(AnalysisArgs a) {
   using Plan = FftPlan<M>;
   constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0, P = Plan::P;
   constexpr int D = M / 2, SH = 4;

@@ -39,7 +39,8 @@ struct btkb_pipeline {
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   int16_t* d_x16 = nullptr; double* h_delays = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
   // batch state
-  int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0;
+  int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
+  double* d_delaysJ = nullptr;
   std::vector<int> lengths;
   bool have_h = false, have_g = false, have_ta = false, have_w = false, have_wl = false, have_R = false, R_is_sum = false;
   bool have_X = false, have_Y = false, have_time = false, have_ua = false;
@@ -81,7 +82,7 @@ void btkb_destroy(btkb_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
   void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
-                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16};
+                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ};
   if (p->h_delays) cudaFreeHost(p->h_delays);
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -214,11 +215,26 @@ int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
   CK(cudaEventRecord(p->ev[4], p->stream));
   WeightsArgs a{p->d_delays, p->d_TA, U, p->C, p->M, p->K, p->Gp, p->cfg.samplerate};
   CK(launch_mainlobe_weights(a, p->stream));
-  p->have_ta = true;
+  p->have_ta = true; p->NC = 1;
   if (p->cfg.beamformer != BTKB_BF_MVDR) {
     CK(cudaMemcpyAsync(p->d_W, p->d_TA, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
     p->have_w = true;
   }
+  return BTKB_OK;
+}
+
+int btkb_set_delays_lcmv(btkb_pipeline* p, int U, int NC, const double* delaysT, const double* delaysJ) {
+  if (!p || !delaysT || !delaysJ) return fail(BTKB_ERR_INVALID, "btkb_set_delays_lcmv: null argument");
+  if (NC < 2 || NC > 4 || NC > p->C)  // beamformer.cc:592-594
+    return fail(BTKB_ERR_INVALID, "1 < the number of constraints " + std::to_string(NC) + " <= the number of sensors " + std::to_string(p->C) + " (and <= 4 in this build).");
+  if (p->cfg.beamformer == BTKB_BF_GSC_LMS) return fail(BTKB_ERR_INVALID, "btkb_set_delays_lcmv: the NLMS kernel implements one constraint");
+  int rc = btkb_set_delays(p, U, delaysT);  // calcMainlobe first (also the time-alignment manifold), beamformer.cc:617
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(p->stream));
+  if (!p->d_delaysJ) CK(cudaMalloc((void**)&p->d_delaysJ, (size_t)p->Ucap * 3 * p->C * sizeof(double)));
+  CK(cudaMemcpy(p->d_delaysJ, delaysJ, (size_t)U * (NC - 1) * p->C * sizeof(double), cudaMemcpyHostToDevice));
+  CK(launch_lcmv_weights(p->d_delays, p->d_delaysJ, p->d_W, U, p->C, NC, p->M, p->K, p->Gp, p->cfg.samplerate, p->stream));
+  p->NC = NC; p->have_w = true; p->have_wl = false;
   return BTKB_OK;
 }
 
@@ -245,9 +261,11 @@ int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa) {
   int rc = check_weight_batch(p, U, "btkb_set_active_weights"); if (rc) return rc;
   CK(cudaSetDevice(p->cfg.device));
   std::vector<float2> tmp;
-  to_device_layout(wa, tmp, U, p->K, p->C - 1, p->Gp);
+  to_device_layout(wa, tmp, U, p->K, p->C - p->NC, p->Gp);
   CK(cudaMemcpyAsync(p->d_WA, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
-  CK(launch_blocking_wl(p->d_TA, p->d_WA, p->d_WL, U, p->C, p->K, p->Gp, p->stream));
+  // calc_blocking_matrix_(wq_[f], NC, B_[f]) (beamformer.cc:554-562, 693-700): B is built from the quiescent vector
+  const float2* bsrc = (p->cfg.beamformer == BTKB_BF_MVDR) ? p->d_TA : p->d_W;
+  CK(launch_blocking_wl(bsrc, p->d_WA, p->d_WL, U, p->C, p->K, p->Gp, p->NC, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   p->have_wl = true;
   return BTKB_OK;
@@ -368,7 +386,7 @@ static PerBinArgs perbin_args(btkb_pipeline* p) {
   a.Y = p->d_Y; a.PFW = p->d_PFW; a.UA = p->d_UA; a.stats_updates = p->d_upd;
   a.R = p->d_R; a.noise_mask = p->d_mask; a.noise_count = p->d_count;
   a.U = p->U; a.C = p->C; a.T = p->T; a.M = p->M; a.K = p->K; a.G = p->U * p->K; a.Gp = p->Gp; a.D = p->D; a.laN = p->laN; a.pdA = p->pdA;
-  a.kind = p->cfg.beamformer; a.pf_kind = p->cfg.postfilter; a.pf_alpha = p->cfg.pf_alpha; a.pf_type = p->cfg.pf_type; a.pf_min_frames = p->cfg.pf_min_frames;
+  a.kind = p->cfg.beamformer; a.normalize_weight = p->cfg.normalize_weight; a.pf_kind = p->cfg.postfilter; a.pf_alpha = p->cfg.pf_alpha; a.pf_type = p->cfg.pf_type; a.pf_min_frames = p->cfg.pf_min_frames;
   const btkb_lms_params& l = p->cfg.lms;
   a.lms = LmsArgs{l.beta, l.gamma, l.init_diagonal_load, l.regularization_param, l.energy_floor, l.sil_thresh, l.max_wa_l2norm, l.min_frames, l.slowdown_after};
   return a;
@@ -430,6 +448,17 @@ int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float ene
   if (labels) CK(cudaStreamSynchronize(p->stream));
   p->have_R = true; p->R_is_sum = true;
   p->wU = p->U;
+  return BTKB_OK;
+}
+
+int btkb_spectral_matrix_update(btkb_pipeline* p, float mu, int legacy_noconj) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_spectral_matrix_update: run the analysis first");
+  CK(cudaSetDevice(p->cfg.device));
+  if (!p->d_R) CK(cudaMalloc((void**)&p->d_R, (size_t)p->C * p->C * p->Gpcap * sizeof(float2)));
+  PerBinArgs a = perbin_args(p);
+  CK(launch_spectral_recursion(a, mu, legacy_noconj, p->stream));
+  p->have_R = true; p->R_is_sum = false; p->wU = p->U;
   return BTKB_OK;
 }
 
@@ -626,7 +655,7 @@ int btkb_get_active_weights(btkb_pipeline* p, float* out) {
   } else if (!p->have_wl) {
     return fail(BTKB_ERR_STATE, "btkb_get_active_weights: no active weights set");
   }
-  return get_rows(p, p->d_WA, p->C - 1, out);
+  return get_rows(p, p->d_WA, p->C - p->NC, out);
 }
 
 int btkb_get_covariance(btkb_pipeline* p, float* out) {

@@ -45,6 +45,7 @@ struct PerBinArgs {
   int* noise_count;   // [U]
   int U, C, T, M, K, G, Gp, D, laN, pdA;
   int kind;           // BTKB_BF_*
+  int normalize_weight;  // calc_gsc_output's w <- w / (||w|| C) (beamformer.cc:1230-1236)
   int pf_kind; float pf_alpha; int pf_type, pf_min_frames;
   LmsArgs lms;
   float energy_threshold;
@@ -63,7 +64,9 @@ cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st);
 cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st);
 
 // setup kernels (btkb_weights.cu)
-cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, cudaStream_t st);
+cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, int NC, cudaStream_t st);
+cudaError_t launch_lcmv_weights(const double* delaysT, const double* delaysJ, float2* W, int U, int C, int NC, int M, int K, int Gp, float samplerate, cudaStream_t st);
+cudaError_t launch_spectral_recursion(const PerBinArgs& a, float mu, int noconj, cudaStream_t st);
 cudaError_t launch_diffuse_model(const double* mpos, float2* R, int U, int C, int M, int K, int Gp, float samplerate, float sspeed, cudaStream_t st);
 cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count, cudaStream_t st);
 cudaError_t launch_ua_to_wa(const float2* UA, const float2* W, float2* WA, int U, int C, int K, int Gp, cudaStream_t st);

@@ -173,6 +173,15 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
 #pragma unroll
     for (int c = 0; c < C; c++) { float2 l = __ldg(a.WL + (size_t)c * a.Gp + g); w[c] = csub(w[c], l); }
   }
+  if (MODE == MODE_STATIC && a.normalize_weight && k != 0 && a.kind != BTKB_BF_DS) {
+    // calc_gsc_output(normalizeWeight = true): w <- w / (||w|| C) (beamformer.cc:1230-1236); the DC bin bypasses it
+    float nrm = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) nrm = fmaf(w[c].x, w[c].x, fmaf(w[c].y, w[c].y, nrm));
+    const float sc = 1.0f / (sqrtf(nrm) * (float)C);
+#pragma unroll
+    for (int c = 0; c < C; c++) { w[c].x *= sc; w[c].y *= sc; }
+  }
 
   // ---- NLMS state (pybeamformer.py:745-757 reset_stats)
   float2 uw[(MODE == MODE_LMS) ? C : 1];
@@ -348,6 +357,51 @@ __global__ void __launch_bounds__(TILE) k_covariance(const __grid_constant__ CUt
   }
 }
 
+// SpectralMatrixArray::update (beamformer.cc:122-143) over all resident frames: R <- mu R + (1 - mu) x x^T (NOCONJ, the
+// reference's arithmetic: complex-symmetric) or x x^H (Hermitian).  Upper triangle incl. diagonal in registers.
+template <int C, int NOCONJ>
+__global__ void __launch_bounds__(TILE) k_spectral_recursion(const __grid_constant__ CUtensorMap tmX, PerBinArgs a, float mu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int g0 = blockIdx.x * TILE;
+  const int g = g0 + threadIdx.x;
+  const bool valid = g < a.G;
+  const int u = valid ? g / a.K : a.U - 1;
+  const int Tu = valid ? frames_of(a.lengths[u], a.D, a.laN, a.pdA) : 0;
+  TileRing<C> ring;
+  ring.init(smem_raw, &tmX, g0, a.T);
+  constexpr int NU = C * (C + 1) / 2;
+  float2 r[NU];
+#pragma unroll
+  for (int i = 0; i < NU; i++) r[i] = make_float2(0.f, 0.f);
+  const float om = 1.0f - mu;
+  for (int t = 0; t < a.T; t++) {
+    float2 x[C];
+    ring.fetch(t, a.T, x);
+    if (t < Tu) {
+      int idx = 0;
+#pragma unroll
+      for (int i = 0; i < C; i++)
+#pragma unroll
+        for (int j = i; j < C; j++) {
+          const float2 p = NOCONJ ? cmul(x[i], x[j]) : cmulc(x[i], x[j]);
+          r[idx].x = fmaf(mu, r[idx].x, om * p.x); r[idx].y = fmaf(mu, r[idx].y, om * p.y);
+          idx++;
+        }
+    }
+  }
+  if (valid) {
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < C; i++)
+#pragma unroll
+      for (int j = i; j < C; j++) {
+        a.R[(size_t)(i * C + j) * a.Gp + g] = r[idx];
+        if (j != i) a.R[(size_t)(j * C + i) * a.Gp + g] = NOCONJ ? r[idx] : make_float2(r[idx].x, -r[idx].y);
+        idx++;
+      }
+  }
+}
+
 template <int C>
 static size_t ring_smem() { return sizeof(float2) * STAGES * FCH * C * TILE + sizeof(uint64_t) * 2 * STAGES + 64; }
 
@@ -428,4 +482,36 @@ cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st) {
   }
 }
 
+}  // namespace btkb
+
+namespace btkb {
+template <int C>
+static cudaError_t launch_rec_c(const PerBinArgs& a, float mu, int noconj, cudaStream_t st) {
+  const size_t smem = ring_smem<C>();
+  CUtensorMap tm;
+  cudaError_t e = make_tensor_map(&tm, a, C);
+  if (e != cudaSuccess) return e;
+  const int grid = (a.G + TILE - 1) / TILE;
+  if (noconj) {
+    auto kern = k_spectral_recursion<C, 1>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TILE, smem, st>>>(tm, a, mu);
+  } else {
+    auto kern = k_spectral_recursion<C, 0>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TILE, smem, st>>>(tm, a, mu);
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_spectral_recursion(const PerBinArgs& a, float mu, int noconj, cudaStream_t st) {
+  if (a.T <= 0 || a.G <= 0) return cudaSuccess;
+  switch (a.C) {
+    case 2: return launch_rec_c<2>(a, mu, noconj, st);
+    case 4: return launch_rec_c<4>(a, mu, noconj, st);
+    case 8: return launch_rec_c<8>(a, mu, noconj, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
 }  // namespace btkb

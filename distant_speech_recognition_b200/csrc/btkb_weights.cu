@@ -47,11 +47,11 @@ __global__ void k_mainlobe(WeightsArgs a) {
 
 // B[C][C-1]: P = I - conj(v) v^T / ||v||^2 ; Gram-Schmidt over its first C-1 columns (NC = 1)
 template <int C>
-__device__ void blocking_matrix(const cd* v, cd (*B)[C - 1]) {
+__device__ void blocking_matrix(const cd* v, cd (*B)[C - 1], int NC = 1) {
   double nv = 0.0;
   for (int c = 0; c < C; c++) nv += cdabs2(v[c]);
   cd vec[C];
-  for (int idim = 0; idim < C - 1; idim++) {
+  for (int idim = 0; idim < C - NC; idim++) {
     for (int r = 0; r < C; r++) {
       cd p = cdscale(cdmul(cdconj(v[r]), v[idim]), -1.0 / nv);  // P[r][idim]
       if (r == idim) p.x += 1.0;
@@ -70,25 +70,26 @@ __device__ void blocking_matrix(const cd* v, cd (*B)[C - 1]) {
 }
 
 template <int C, int DIR>  // DIR 0: WL = B WA ; DIR 1: WA = UA conj(B)
-__global__ void k_blocking(const float2* W, const float2* IN, float2* OUT, int U, int K, int Gp) {
+__global__ void k_blocking(const float2* W, const float2* IN, float2* OUT, int U, int K, int Gp, int NC) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= U * K) return;
   cd v[C];
   cd B[C][C - 1];
   for (int c = 0; c < C; c++) { float2 t = W[(size_t)c * Gp + g]; v[c] = cdmake(t.x, t.y); }
-  blocking_matrix<C>(v, B);
+  blocking_matrix<C>(v, B, NC);
+  const int NA = C - NC;
   if (DIR == 0) {
     cd wa[C - 1];
-    for (int i = 0; i < C - 1; i++) { float2 t = IN[(size_t)i * Gp + g]; wa[i] = cdmake(t.x, t.y); }
+    for (int i = 0; i < NA; i++) { float2 t = IN[(size_t)i * Gp + g]; wa[i] = cdmake(t.x, t.y); }
     for (int c = 0; c < C; c++) {
       cd s = cdmake(0, 0);
-      for (int i = 0; i < C - 1; i++) s = cdadd(s, cdmul(B[c][i], wa[i]));
+      for (int i = 0; i < NA; i++) s = cdadd(s, cdmul(B[c][i], wa[i]));
       OUT[(size_t)c * Gp + g] = make_float2((float)s.x, (float)s.y);
     }
   } else {
     cd ua[C];
     for (int c = 0; c < C; c++) { float2 t = IN[(size_t)c * Gp + g]; ua[c] = cdmake(t.x, t.y); }
-    for (int i = 0; i < C - 1; i++) {
+    for (int i = 0; i < NA; i++) {
       cd s = cdmake(0, 0);
       for (int c = 0; c < C; c++) s = cdadd(s, cdmul(ua[c], cdconj(B[c][i])));
       OUT[(size_t)i * Gp + g] = make_float2((float)s.x, (float)s.y);
@@ -97,23 +98,23 @@ __global__ void k_blocking(const float2* W, const float2* IN, float2* OUT, int U
 }
 
 template <int DIR>
-static cudaError_t launch_blocking(const float2* W, const float2* IN, float2* OUT, int U, int C, int K, int Gp, cudaStream_t st) {
+static cudaError_t launch_blocking(const float2* W, const float2* IN, float2* OUT, int U, int C, int K, int Gp, int NC, cudaStream_t st) {
   const int n = U * K, bs = 128, gs = (n + bs - 1) / bs;
   switch (C) {
-    case 2: k_blocking<2, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
-    case 3: k_blocking<3, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
-    case 4: k_blocking<4, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
-    case 6: k_blocking<6, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
-    case 8: k_blocking<8, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp); break;
+    case 2: k_blocking<2, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
+    case 3: k_blocking<3, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
+    case 4: k_blocking<4, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
+    case 6: k_blocking<6, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
+    case 8: k_blocking<8, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
-cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, cudaStream_t st) {
-  return launch_blocking<0>(W, WA, WL, U, C, K, Gp, st);
+cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, int NC, cudaStream_t st) {
+  return launch_blocking<0>(W, WA, WL, U, C, K, Gp, NC, st);
 }
 cudaError_t launch_ua_to_wa(const float2* UA, const float2* W, float2* WA, int U, int C, int K, int Gp, cudaStream_t st) {
-  return launch_blocking<1>(W, UA, WA, U, C, K, Gp, st);
+  return launch_blocking<1>(W, UA, WA, U, C, K, Gp, 1, st);
 }
 
 cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st) {
@@ -240,6 +241,108 @@ __global__ void k_noise_mask(const float* E, const int* lengths, const double* l
 cudaError_t launch_noise_mask(const float* E, const int* lengths, const double* labels, unsigned char* mask, int* count, int U, int T, int D, int laN,
                               int pdA, float samplerate, float thr, cudaStream_t st) {
   k_noise_mask<<<(U + 63) / 64, 64, 0, st>>>(E, lengths, labels, mask, count, U, T, D, laN, pdA, samplerate, thr);
+  return cudaGetLastError();
+}
+
+}  // namespace btkb
+
+// ---------------------------------------------------------------------------------------------------------------
+// LCMV quiescent weights: BeamformerWeights::calcMainlobeN / calcMainlobe2 (beamformer.cc:573-721) with
+// calc_null_beamformer_ (beamformer.cc:299-363): wq = Cm (Cm^H Cm)^-1 g, Cm = [target | jammers] (unit modulus), g = e0.
+// NC == 2 inverts with calc_inverse_22mat_ (beamformer.cc:181-221: diagonal +0.01 when |det| < 1e-7); NC > 2 uses the
+// reference's pseudoinverse (float SVD there, a double LU inverse here).  The f = M/2 branch of the reference calls
+// calc_null_beamformer_ INSIDE its channel loop with the jammer manifolds left over from bin M/2-1
+// (beamformer.cc:677-689); that cascade is reproduced literally so the weights match the reference bin for bin.
+namespace btkb {
+
+constexpr int MAXNC = 4;
+
+template <int C>
+__device__ void null_beamformer(cd* wt, const cd (*Wj)[C], int NC) {
+  cd A[MAXNC][MAXNC], inv[MAXNC][MAXNC];
+  auto col = [&](int j, int c) -> cd { return j == 0 ? wt[c] : Wj[j - 1][c]; };
+  for (int i = 0; i < NC; i++)
+    for (int j = 0; j < NC; j++) {
+      cd s = cdmake(0, 0);
+      for (int c = 0; c < C; c++) s = cdadd(s, cdmul(cdconj(col(i, c)), col(j, c)));
+      A[i][j] = s;
+    }
+  if (NC == 2) {
+    cd det = cdsub(cdmul(A[0][0], A[1][1]), cdmul(A[0][1], A[1][0]));
+    if (sqrt(cdabs2(det)) < 1.0e-7) {
+      A[0][0].x += 0.01; A[1][1].x += 0.01;
+      det = cdsub(cdmul(A[0][0], A[1][1]), cdmul(A[0][1], A[1][0]));
+    }
+    inv[0][0] = cddiv(A[1][1], det); inv[1][1] = cddiv(A[0][0], det);
+    inv[0][1] = cdscale(cddiv(A[0][1], det), -1.0); inv[1][0] = cdscale(cddiv(A[1][0], det), -1.0);
+  } else {
+    // Gauss-Jordan inverse with partial pivoting
+    cd aug[MAXNC][2 * MAXNC];
+    for (int i = 0; i < NC; i++) for (int j = 0; j < NC; j++) { aug[i][j] = A[i][j]; aug[i][NC + j] = cdmake(i == j ? 1.0 : 0.0, 0.0); }
+    for (int cI = 0; cI < NC; cI++) {
+      int piv = cI; double best = cdabs2(aug[cI][cI]);
+      for (int r = cI + 1; r < NC; r++) if (cdabs2(aug[r][cI]) > best) { best = cdabs2(aug[r][cI]); piv = r; }
+      if (piv != cI) for (int j = 0; j < 2 * NC; j++) { cd t = aug[cI][j]; aug[cI][j] = aug[piv][j]; aug[piv][j] = t; }
+      cd d = aug[cI][cI];
+      for (int j = 0; j < 2 * NC; j++) aug[cI][j] = cddiv(aug[cI][j], d);
+      for (int r = 0; r < NC; r++) if (r != cI) { cd f = aug[r][cI]; for (int j = 0; j < 2 * NC; j++) aug[r][j] = cdsub(aug[r][j], cdmul(f, aug[cI][j])); }
+    }
+    for (int i = 0; i < NC; i++) for (int j = 0; j < NC; j++) inv[i][j] = aug[i][NC + j];
+  }
+  cd out[C];
+  for (int c = 0; c < C; c++) {
+    cd s = cdmake(0, 0);
+    for (int j = 0; j < NC; j++) s = cdadd(s, cdmul(col(j, c), inv[j][0]));  // Cm (inv g), g = e0
+    out[c] = s;
+  }
+  for (int c = 0; c < C; c++) wt[c] = out[c];
+}
+
+template <int C>
+__global__ void k_lcmv(const double* delaysT, const double* delaysJ, float2* W, int U, int NC, int M, int K, int Gp, float samplerate) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= U * K) return;
+  const int u = g / K, k = g - u * K;
+  const double fs = (double)samplerate;
+  const double* dT = delaysT + (size_t)u * C;
+  const double* dJ = delaysJ + (size_t)u * (NC - 1) * C;
+  cd wt[C]; cd Wj[MAXNC - 1][C];
+  auto polar = [](double a) { double s, c; sincos(a, &s, &c); return cdmake(c, s); };
+  if (k == 0) {
+    for (int c = 0; c < C; c++) wt[c] = cdmake(1.0 / C, 0.0);
+  } else if (k < M / 2) {
+    for (int c = 0; c < C; c++) {
+      wt[c] = polar(-2.0 * M_PI * (double)k * dT[c] * fs / (double)M);
+      for (int n = 0; n < NC - 1; n++) Wj[n][c] = polar(-2.0 * M_PI * (double)k * fs * dJ[n * C + c] / (double)M);
+    }
+    null_beamformer<C>(wt, Wj, NC);
+  } else {
+    // f = M/2: start from calcMainlobe's value; pWj still holds the jammer manifolds of bin M/2 - 1
+    for (int c = 0; c < C; c++) {
+      wt[c] = cdscale(polar(-M_PI * fs * dT[c]), 1.0 / C);
+      for (int n = 0; n < NC - 1; n++) Wj[n][c] = polar(-2.0 * M_PI * (double)(M / 2 - 1) * fs * dJ[n * C + c] / (double)M);
+    }
+    for (int c = 0; c < C; c++) {
+      wt[c] = cdscale(wt[c], (double)C);
+      for (int n = 0; n < NC - 1; n++) wt[c] = cdscale(polar(-M_PI * fs * dJ[n * C + c]), 1.0 / C);
+      null_beamformer<C>(wt, Wj, NC);
+    }
+  }
+  for (int c = 0; c < C; c++) W[(size_t)c * Gp + g] = make_float2((float)wt[c].x, (float)wt[c].y);
+}
+
+cudaError_t launch_lcmv_weights(const double* delaysT, const double* delaysJ, float2* W, int U, int C, int NC, int M, int K, int Gp, float samplerate,
+                                cudaStream_t st) {
+  if (NC < 2 || NC > MAXNC || NC > C) return cudaErrorInvalidValue;
+  const int n = U * K, bs = 64, gs = (n + bs - 1) / bs;
+  switch (C) {
+    case 2: k_lcmv<2><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
+    case 3: k_lcmv<3><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
+    case 4: k_lcmv<4><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
+    case 6: k_lcmv<6><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
+    case 8: k_lcmv<8><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

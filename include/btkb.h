@@ -74,6 +74,7 @@ typedef struct btkb_config {
   int max_samples;             /* capacity: samples per channel per utterance */
   int keep_snapshots;          /* 1: keep the analysis output X resident so btkb_fetch_snapshots works (always true today) */
   int synthesis_gain;          /* OverSampledDFTSynthesisBank gain_factor (modulated.cc:608-609); default 1 */
+  int normalize_weight;        /* SubbandGSC::normalize_weight(flag): w <- w / (||w|| C) for bins >= 1 (beamformer.cc:1230-1236) */
 } btkb_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */
@@ -88,6 +89,11 @@ int btkb_device_count(void);
 int btkb_set_prototypes(btkb_pipeline* p, const double* h, const double* g, int len);
 /* per-utterance time delays [U][C] (seconds) -> quiescent weights wq = calcMainlobe (beamformer.cc:502-565), ta = wq */
 int btkb_set_delays(btkb_pipeline* p, int U, const double* delays);
+/* LCMV quiescent weights with NC >= 2 linear constraints: target delays [U][C] + NC-1 jammer delay vectors [U][NC-1][C]
+ * (calc_gsc_weights_n / calc_array_manifold_vectors_n -> BeamformerWeights::calcMainlobeN, beamformer.cc:573-721, with
+ * calc_null_beamformer_, beamformer.cc:299-363).  The time-alignment manifold stays the delay-and-sum one; active
+ * weights then have C-NC entries per bin. */
+int btkb_set_delays_lcmv(btkb_pipeline* p, int U, int NC, const double* delaysT, const double* delaysJ);
 /* explicit quiescent / MVDR weights [U][K][C] complex64 (replaces setQuiescentVector / wmvdr_) */
 int btkb_set_weights(btkb_pipeline* p, int U, const float* w);
 /* active weights wa [U][K][C-1] complex64 -> wl = B wa with B = calc_blocking_matrix_(wq) (beamformer.cc:373-454, 729-767) */
@@ -115,6 +121,10 @@ int btkb_run_analysis(btkb_pipeline* p);
 /* SMI pass 1 (pybeamformer.py:948-1000): R[u][k] = mean over noise frames (outside [start,end] s, energy > threshold) of x x^H.
  * labels [U][2] seconds (NULL: every frame is noise).  Requires btkb_run_analysis. */
 int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float energy_threshold);
+/* SpectralMatrixArray::update over every resident frame (beamformer.cc:122-143): R <- mu R + (1-mu) x x^T with NO
+ * conjugate when legacy_noconj != 0 (the reference's arithmetic), x x^H otherwise.
+ * Result readable with btkb_get_covariance.  Requires btkb_run_analysis. */
+int btkb_spectral_matrix_update(btkb_pipeline* p, float mu, int legacy_noconj);
 /* the per-bin beamformer (+ post-filter) over the resident snapshots, then synthesis when do_synthesis != 0 */
 int btkb_run_beamformer(btkb_pipeline* p, int do_synthesis);
 /* inject beamformed subband frames from the host, Y [U][T][K] complex64 (the stream an arbitrary upstream

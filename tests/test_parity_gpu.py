@@ -213,3 +213,77 @@ def test_error_paths(capi, protos):
         p.submit(np.zeros((3, 8, 4000), np.float32))
     with pytest.raises(capi.BtkbError):
         capi.Pipeline(8, 500, 4, 1)       # fft_len not a power of two
+
+
+def test_lcmv_quiescent_weights_golden(capi, protos):
+    """calc_gsc_weights_n -> calcMainlobeN + calc_null_beamformer_ (beamformer.cc:299-363,573-721) against the reference's
+    own weights (tests/golden/make_golden_lcmv.py), including the reference's peculiar f = M/2 cascade."""
+    g = load_golden("lcmv")
+    M, C, K = 512, 8, 257
+    p = _pipe(capi, C, M, protos, n=4096, beamformer=capi.BF_GSC)
+    p.set_delays_lcmv(g["dT"][None], g["dJ1"][None, None])
+    w = p.get_weights()[0]
+    assert rel_l2(w, g["w2"]) < 1e-6                      # all 257 bins, NC = 2 (2x2 closed-form inverse)
+    p.set_delays_lcmv(g["dT"][None], np.stack([g["dJ1"], g["dJ2"]])[None])
+    w3 = p.get_weights()[0]
+    # NC = 3: the reference inverts C^H C with a single-precision SVD; at the lowest bins the constraint matrix is
+    # near-singular and the reference's own result is rounding noise, so compare where it is well conditioned
+    assert rel_l2(w3[8:256], g["w3"][8:256]) < 1e-5
+    # constraints hold: w^H v_target = 1, w^H v_jammer = 0
+    k = np.arange(8, 256)
+    vt = np.exp(-2j * np.pi * k[:, None] * g["dT"][None, :] * FS / M)
+    vj = np.exp(-2j * np.pi * k[:, None] * g["dJ2"][None, :] * FS / M)
+    assert np.abs(np.einsum("kc,kc->k", np.conj(w3[8:256]), vt) - 1).max() < 1e-4
+    assert np.abs(np.einsum("kc,kc->k", np.conj(w3[8:256]), vj)).max() < 1e-4
+    # active weights now have C - NC entries; wl = B wa with B from calc_blocking_matrix_(wq, NC)
+    rng = np.random.default_rng(2)
+    wa = (0.1 * (rng.standard_normal((1, K, C - 3)) + 1j * rng.standard_normal((1, K, C - 3)))).astype(np.complex64)
+    p.set_active_weights(wa)
+    from oracle import restate
+    x = (1000 * rng.standard_normal((1, C, 4096))).astype(np.float32)
+    p.submit(x); p.run(False)
+    X = np.stack([restate.analysis(x[0, c], protos[M][0], M, 4, 1) for c in range(C)], axis=1)
+    wq = np.zeros((M, C), complex); wq[:K] = w3
+    wl = np.zeros((M, C), complex)
+    wl[:K] = np.stack([restate.calc_blocking_matrix(w3[f].astype(complex), 3) @ wa[0, f] for f in range(K)])
+    assert rel_l2(p.fetch_subband()[0], restate.subband_gsc(X, wq, wl)[:, :K]) < TOL
+
+
+def test_normalize_weight_and_spectral_recursion(capi, protos):
+    """SubbandGSC::normalize_weight (calc_gsc_output, beamformer.cc:1230-1236) and SpectralMatrixArray::update
+    (beamformer.cc:122-143, x x^T without conjugate) against the fp64 restatement."""
+    from oracle import restate
+    g = load_golden("gsc_zelinski_c8_m512")
+    x = g["x"]; M, C, K = 512, 8, 257
+    h, gg = protos[M]
+    X = np.stack([restate.analysis(x[c], h, M, 4, 1) for c in range(C)], axis=1)
+    wq = restate.calc_mainlobe(M, C, FS, g["delays"])
+    wl = np.zeros((M, C), complex); wl[:K] = restate.active_to_wl(g["B"], g["wa"])
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC, max_utterances=1, max_samples=x.shape[1], normalize_weight=True)
+    p.set_prototypes(h, gg)
+    p.set_delays(g["delays"][None]); p.set_active_weights(g["wa"][None])
+    p.submit(x[None]); p.run(False)
+    assert rel_l2(p.fetch_subband()[0], restate.subband_gsc(X, wq, wl, normalize_weight=True)[:, :K]) < TOL
+    for noconj in (True, False):
+        p.spectral_matrix_update(0.95, legacy_noconj=noconj)
+        R = np.zeros((K, C, C), complex)
+        for t in range(X.shape[0]):
+            R = restate.spectral_matrix_update(R, X[t, :, :K].T, 0.95, legacy_noconj=noconj)
+        assert rel_l2(p.get_covariance()[0], R) < 1e-5
+
+
+def test_m1024_pipe_cfg5_filterbank_shape(capi, protos):
+    """configs[4] filter-bank shape (M = 1024, D = 512): D&S pipe against the fp64 oracle."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, C, n = 1024, 8, 20000
+    h, g = protos[M]
+    x, d = synthetic.make_batch(2, C, n, first=300)
+    p = _pipe(capi, C, M, protos, U=2, n=n, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=4))
+    p.set_delays(d); p.submit(x); p.run(True)
+    Y = p.fetch_subband(); y = p.fetch_time()
+    for u in range(2):
+        X = np.stack([restate.analysis(x[u, c], h, M, 4, 1) for c in range(C)], axis=1)
+        Yo, _, _ = restate.gsc_lms(X, FS, d[u], min_frames=4)
+        assert X.shape[0] == 44 and rel_l2(Y[u], Yo[:, :513]) < TOL
+        assert rel_l2(y[u], restate.synthesis(Yo, g, M, 4, 1)) < TOL
