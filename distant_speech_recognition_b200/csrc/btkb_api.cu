@@ -258,6 +258,7 @@ int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa) {
   if (!p || !wa) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: null argument");
   if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_gsc_weights_x() once");  // beamformer.cc:1369-1371
   if (p->C < 2) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: needs at least two channels");
+  if (p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: the blocking-matrix kernels are built for <= 8 channels");
   int rc = check_weight_batch(p, U, "btkb_set_active_weights"); if (rc) return rc;
   CK(cudaSetDevice(p->cfg.device));
   std::vector<float2> tmp;
@@ -301,7 +302,8 @@ int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu) {
   if (!p->have_R) return fail(BTKB_ERR_STATE, "Set a spatial spectral matrix before calling calc_mvdr_weights()");  // beamformer.cc:2352-2354
   if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                      // beamformer.cc:2355-2357
   CK(cudaSetDevice(p->cfg.device));
-  CK(launch_mvdr_solve(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->stream));
+  if (p->C <= 8) CK(launch_mvdr_solve(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->stream));
+  else CK(launch_mvdr_solve_wide(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->stream));
   p->have_w = true;
   return BTKB_OK;
 }
@@ -399,10 +401,13 @@ static int do_beamformer(btkb_pipeline* p) {
     return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                                          // beamformer.cc:1098-1100
   }
   if (p->wU != p->U) return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: weights were set for a different number of utterances");
-  if (p->C != 2 && p->C != 4 && p->C != 8)
-    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: this build instantiates the per-bin kernel for 2, 4 and 8 channels (got " + std::to_string(p->C) + ")");
+  const bool narrow = (p->C == 2 || p->C == 4 || p->C == 8), wide = (p->C == 16 || p->C == 32 || p->C == 64);
+  if (!narrow && !wide)
+    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the per-bin kernel is instantiated for 2, 4, 8 (register path) and 16, 32, 64 (lane-split path) channels (got " + std::to_string(p->C) + ")");
+  if (wide && p->cfg.postfilter != BTKB_PF_NONE)
+    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the Zelinski post-filter is built for <= 8 channels (its C(C-1)/2 cross-spectral densities must fit the register file)");
   PerBinArgs a = perbin_args(p);
-  CK(launch_perbin(a, p->stream));
+  if (narrow) CK(launch_perbin(a, p->stream)); else CK(launch_perbin_wide(a, p->stream));
   p->launches++;
   p->have_Y = true;
   p->have_ua = (p->cfg.beamformer == BTKB_BF_GSC_LMS);
@@ -444,7 +449,7 @@ int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float ene
   CK(launch_noise_mask(p->d_E, p->d_len, labels ? p->d_labels : nullptr, p->d_mask, p->d_count, p->U, p->T, p->D, p->laN, p->pdA, p->cfg.samplerate,
                        energy_threshold, p->stream));
   PerBinArgs a = perbin_args(p);
-  CK(launch_covariance(a, p->stream));
+  if (p->C <= 8) CK(launch_covariance(a, p->stream)); else CK(launch_covariance_wide(a, p->stream));
   if (labels) CK(cudaStreamSynchronize(p->stream));
   p->have_R = true; p->R_is_sum = true;
   p->wU = p->U;
@@ -651,6 +656,7 @@ int btkb_get_active_weights(btkb_pipeline* p, float* out) {
   CK(cudaSetDevice(p->cfg.device));
   if (p->cfg.beamformer == BTKB_BF_GSC_LMS) {
     if (!p->have_ua) return fail(BTKB_ERR_STATE, "btkb_get_active_weights: the NLMS has not run");
+    if (p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_get_active_weights: the blocking-matrix export is built for <= 8 channels");
     CK(launch_ua_to_wa(p->d_UA, p->d_TA, p->d_WA, p->U, p->C, p->K, p->Gp, p->stream));
   } else if (!p->have_wl) {
     return fail(BTKB_ERR_STATE, "btkb_get_active_weights: no active weights set");

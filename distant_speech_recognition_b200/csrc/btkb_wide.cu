@@ -1,0 +1,365 @@
+// btkb_wide.cu — per-bin kernels for wide arrays (C = 16, 32, 64 channels; configs[3] uses 64), sm_100a.
+//
+// Same mathematics and reference citations as btkb_perbin.cu (SubbandDS/GSC/MVDR apply, beamformer.cc:1095-1316,2537-2773;
+// NLMS, lib/pybeamformer.py:659-734; SMI covariance, pybeamformer.py:948-1000; MVDR solve, beamformer.cc:2350-2402), but a
+// (utterance, bin) chain is spread over L = C/8 adjacent lanes, 8 channels per lane, so all per-chain state still lives
+// in registers; the per-bin complex reductions (Yc = v^H x, u.x, ||x||^2, ||u||^2) are finished with warp shuffles
+// across the L lanes.  A CTA owns 16 consecutive chains: its mic x bin tile per frame is a [C rows][16 chains] box
+// (128 B rows) fetched by one tensor-map TMA instruction with the 128-byte swizzle, which spreads the L lanes of a chain
+// (reading the same column of 8 different rows) over different shared-memory banks.
+//
+// The covariance / MVDR-solve kernels here are the plain CUDA-core versions (one CTA per chain); the tcgen05 batched
+// contraction for the 64-mic covariance is a later-round item.
+#include <cuda.h>
+#include "btkb_internal.h"
+#include "btkb_fft.cuh"
+#include "../../include/btkb.h"
+
+namespace btkb {
+namespace wide {
+
+constexpr int TC = 16;      // chains per CTA (16 x 8 B = one 128 B swizzle row)
+constexpr int WSTAGES = 4;  // ring slots, one frame each
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n) : "memory"); }
+__device__ __forceinline__ void mb_expect(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mb_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* tm, int c0, int r0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(s32(dst)), "l"(tm), "r"(c0), "r"(r0), "r"(s32(bar)) : "memory");
+}
+
+// Butterfly sum over the L lanes of one chain.  `gm` names exactly those lanes: chains sharing a warp may diverge (padding
+// chains, ragged utterance lengths, per-utterance silence gate), so a full-warp mask inside the adaptation branch would
+// deadlock; the L lanes of one chain always take the same path.
+template <int L>
+__device__ __forceinline__ float red(float v, unsigned gm) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o);
+  return v;
+}
+template <int L>
+__device__ __forceinline__ float2 red2(float2 v, unsigned gm) { return make_float2(red<L>(v.x, gm), red<L>(v.y, gm)); }
+
+__device__ __forceinline__ void mac(float2& acc, float2 a, float2 b) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x); acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void macc(float2& acc, float2 a, float2 b) {  // a conj(b)
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x); acc.y = fmaf(a.y, b.x, acc.y); acc.y = fmaf(-a.x, b.y, acc.y);
+}
+
+// MODE 0: static weights; MODE 1: NLMS
+template <int L, int MODE>
+__global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
+  constexpr int C = 8 * L;
+  constexpr int NTH = TC * L;
+  constexpr int NWARPS = (NTH + 31) / 32;
+  constexpr uint32_t SLOT = C * TC * sizeof(float2);   // C rows of 128 B
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* stage = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SLOT * WSTAGES);
+  uint64_t* empty = full + WSTAGES;
+
+  const int tid = threadIdx.x, j = tid / L, l = tid % L;
+  const unsigned gm = ((L >= 32) ? 0xffffffffu : ((1u << L) - 1u)) << (((tid & 31) / L) * L);
+  const int g0 = blockIdx.x * TC, g = g0 + j;
+  const bool valid = g < a.G;
+  const int u = valid ? g / a.K : a.U - 1;
+  const int k = valid ? g - u * a.K : 0;
+  const int Tu = valid ? frames_of(a.lengths[u], a.D, a.laN, a.pdA) : 0;
+  const int T = a.T;
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    for (int s = 0; s < WSTAGES; s++) { mb_init(full + s, 1); mb_init(empty + s, NWARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t) {
+    const int s = t % WSTAGES;
+    mb_expect(full + s, SLOT);
+    tma2d(stage + (size_t)s * SLOT, &tmX, 2 * g0, t * C, full + s);
+  };
+  if (tid == 0) for (int t = 0; t < WSTAGES - 1 && t < T; t++) issue(t);
+
+  // this lane's channels: c = l + L i
+  float2 w[8], uw[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    w[i] = __ldg(a.W + (size_t)(l + L * i) * a.Gp + g);
+    if (MODE == 0 && a.WL != nullptr && k != 0) { float2 wl = __ldg(a.WL + (size_t)(l + L * i) * a.Gp + g); w[i] = csub(w[i], wl); }
+    uw[i] = make_float2(0.f, 0.f);
+  }
+  if (MODE == 0 && a.normalize_weight && k != 0 && a.kind != BTKB_BF_DS) {
+    float nrm = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nrm = fmaf(w[i].x, w[i].x, fmaf(w[i].y, w[i].y, nrm));
+    nrm = red<L>(nrm, gm);
+    const float sc = 1.0f / (sqrtf(nrm) * (float)C);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w[i].x *= sc; w[i].y *= sc; }
+  }
+  float se = a.lms.init_diagonal_load, Eavg = a.lms.init_diagonal_load, gamma = a.lms.gamma;
+  int n_updates = 0, slow_cnt = a.lms.slowdown_after + 1;
+  const float one_m_beta = 1.0f - a.lms.beta, inv_sil = 1.0f / a.lms.sil_thresh;
+  float e_next = (MODE == 1 && T > 0) ? __ldg(a.E + u) : 0.f;
+
+  for (int t = 0; t < T; t++) {
+    const int s = t % WSTAGES;
+    if (tid == 0 && t + WSTAGES - 1 < T) {
+      if (t >= 1) mb_wait(empty + ((t - 1) % WSTAGES), (uint32_t)(((t - 1) / WSTAGES) & 1));
+      issue(t + WSTAGES - 1);
+    }
+    mb_wait(full + s, (uint32_t)((t / WSTAGES) & 1));
+    float2 x[8];
+    {
+      const unsigned char* base = stage + (size_t)s * SLOT;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int r = l + L * i;
+        x[i] = *reinterpret_cast<const float2*>(base + r * 128 + ((((j >> 1) ^ (r & 7)) << 4) | ((j & 1) << 3)));
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mb_arrive(empty + s);
+
+    const float energy = e_next;
+    if (MODE == 1 && t + 1 < T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
+    float2 y = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; i++) macc(y, x[i], w[i]);
+    y = red2<L>(y, gm);
+    const bool live = t < Tu;
+    if (MODE == 1) {
+      if (--slow_cnt == 0) { gamma *= 0.5f; slow_cnt = a.lms.slowdown_after; }
+      const bool adapt = energy > (Eavg * inv_sil);
+      float nx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) nx = fmaf(x[i].x, x[i].x, fmaf(x[i].y, x[i].y, nx));
+      nx = red<L>(nx, gm);
+      float sub = (t > 0) ? fmaf(se, a.lms.beta, one_m_beta * nx) : nx;
+      sub = fmaxf(sub, a.lms.energy_floor);
+      if (adapt && live) {   // uniform over the L lanes of a chain
+        float2 ux = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) mac(ux, uw[i], x[i]);
+        ux = red2<L>(ux, gm);
+        const float2 epa = csub(y, ux);
+        const float alphaK = gamma / sub;
+        const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
+        const float2 ea = make_float2(epa.x * alphaK, epa.y * alphaK);
+        const float keep = (a.lms.regularization_param > 0.f) ? 1.0f - alphaK * a.lms.regularization_param : 1.0f;
+        float n2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float qx = fmaf(-cy.x, w[i].x, fmaf(cy.y, w[i].y, x[i].x));
+          const float qy = fmaf(-cy.x, w[i].y, fmaf(-cy.y, w[i].x, x[i].y));
+          const float unx = fmaf(ea.y, qy, fmaf(ea.x, qx, keep * uw[i].x));
+          const float uny = fmaf(-ea.x, qy, fmaf(ea.y, qx, keep * uw[i].y));
+          uw[i] = make_float2(unx, uny);
+          n2 = fmaf(unx, unx, fmaf(uny, uny, n2));
+        }
+        n2 = red<L>(n2, gm);
+        if (n2 > a.lms.max_wa_l2norm) {
+          const float cK = sqrtf(a.lms.max_wa_l2norm / n2);
+#pragma unroll
+          for (int i = 0; i < 8; i++) { uw[i].x *= cK; uw[i].y *= cK; }
+        }
+        se = sub;
+        n_updates++;
+      }
+      if (t >= a.lms.min_frames) {
+        float2 ux = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) mac(ux, uw[i], x[i]);
+        ux = red2<L>(ux, gm);
+        y = csub(y, ux);
+      }
+      Eavg = fmaf(Eavg, a.lms.beta, one_m_beta * energy);
+    }
+    if (valid && l == 0) a.Y[(size_t)t * a.Gp + g] = live ? y : make_float2(0.f, 0.f);
+  }
+  if (MODE == 1 && valid) {
+    if (a.UA != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) a.UA[(size_t)(l + L * i) * a.Gp + g] = uw[i];
+    }
+    if (k == 0 && l == 0 && a.stats_updates != nullptr) a.stats_updates[u] = (float)n_updates;
+  }
+}
+
+// One CTA (256 threads) per chain: R += x x^H over the frames flagged in noise_mask (pybeamformer.py:976-982), any C <= 64.
+__global__ void __launch_bounds__(256) k_covariance_wide(PerBinArgs a) {
+  __shared__ float2 xs[64];
+  const int g = blockIdx.x;
+  const int u = g / a.K, C = a.C;
+  const int NE = C * C;                         // matrix entries; thread handles e = tid, tid+256, ...
+  float2 acc[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) acc[q] = make_float2(0.f, 0.f);
+  for (int t = 0; t < a.T; t++) {
+    if (!a.noise_mask[(size_t)t * a.U + u]) continue;   // uniform over the CTA
+    __syncthreads();
+    if (threadIdx.x < C) xs[threadIdx.x] = a.X[((size_t)t * C + threadIdx.x) * a.Gp + g];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int e = threadIdx.x + q * 256;
+      if (e < NE) macc(acc[q], xs[e / C], xs[e % C]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const int e = threadIdx.x + q * 256;
+    if (e < NE) a.R[(size_t)e * a.Gp + g] = acc[q];
+  }
+}
+
+// One CTA (C threads, one per row) per chain: w = (R^H)^-1 d / (C d^H R^-1 d) by Gaussian elimination with partial
+// pivoting in double precision, matrix in shared memory (beamformer.cc:2350-2402; bin 0: all ones).
+struct cdw { double x, y; };
+__device__ __forceinline__ cdw cw(double x, double y) { cdw r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ cdw cwmul(cdw a, cdw b) { return cw(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cdw cwsub(cdw a, cdw b) { return cw(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cdw cwdiv(cdw a, cdw b) { double d = b.x * b.x + b.y * b.y; return cw((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d); }
+
+__global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  cdw* A = reinterpret_cast<cdw*>(sm);          // [C][C+1] augmented, row-major
+  __shared__ int piv_row; __shared__ int singular;
+  __shared__ double lam_re, lam_im;
+  const int g = blockIdx.x, r = threadIdx.x;
+  const int u = g / K, k = g - u * K;
+  if (k == 0) { W[(size_t)r * Gp + g] = make_float2(1.f, 0.f); return; }
+  double scale = 1.0;
+  if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
+  const int LD = C + 1;
+  // A = R^H with loading; row r of A = conj of column r of R
+  for (int c = 0; c < C; c++) {
+    float2 t = R[(size_t)(c * C + r) * Gp + g];
+    cdw v = cw((double)t.x * scale, -(double)t.y * scale);
+    if (c == r) v.x += (double)mu;
+    A[r * LD + c] = v;
+  }
+  { float2 t = Dm[(size_t)r * Gp + g]; A[r * LD + C] = cw(t.x, t.y); }
+  if (r == 0) singular = 0;
+  __syncthreads();
+  for (int col = 0; col < C; col++) {
+    if (r == 0) {
+      int p = col; double best = A[col * LD + col].x * A[col * LD + col].x + A[col * LD + col].y * A[col * LD + col].y;
+      for (int q = col + 1; q < C; q++) { cdw v = A[q * LD + col]; double m2 = v.x * v.x + v.y * v.y; if (m2 > best) { best = m2; p = q; } }
+      piv_row = p; if (!(best > 1e-60)) singular = 1;
+    }
+    __syncthreads();
+    if (singular) break;
+    if (piv_row != col) {   // swap rows col <-> piv_row: thread r handles column r (and the rhs by the last thread)
+      cdw t = A[col * LD + r]; A[col * LD + r] = A[piv_row * LD + r]; A[piv_row * LD + r] = t;
+      if (r == 0) { cdw t2 = A[col * LD + C]; A[col * LD + C] = A[piv_row * LD + C]; A[piv_row * LD + C] = t2; }
+    }
+    __syncthreads();
+    if (r > col) {
+      const cdw f = cwdiv(A[r * LD + col], A[col * LD + col]);
+      for (int c = col + 1; c <= C; c++) A[r * LD + c] = cwsub(A[r * LD + c], cwmul(f, A[col * LD + c]));
+    }
+    __syncthreads();
+  }
+  // back substitution (serial in rows, parallel over nothing: C <= 64, done by thread 0) into column C
+  if (r == 0) {
+    if (!singular) {
+      for (int i = C - 1; i >= 0; i--) {
+        cdw sacc = A[i * LD + C];
+        for (int c = i + 1; c < C; c++) sacc = cwsub(sacc, cwmul(A[i * LD + c], A[c * LD + C]));
+        A[i * LD + C] = cwdiv(sacc, A[i * LD + i]);
+      }
+    } else {
+      for (int i = 0; i < C; i++) { float2 t = Dm[(size_t)i * Gp + g]; A[i * LD + C] = cw(t.x, t.y); }   // identity fallback
+    }
+    double lr = 0, li = 0;
+    for (int i = 0; i < C; i++) { float2 d = Dm[(size_t)i * Gp + g]; cdw tv = A[i * LD + C]; lr += tv.x * d.x + tv.y * d.y; li += tv.x * d.y - tv.y * d.x; }  // conj(t) d
+    lam_re = lr * C; lam_im = li * C;
+  }
+  __syncthreads();
+  const cdw wv = cwdiv(A[r * LD + C], cw(lam_re, lam_im));
+  W[(size_t)r * Gp + g] = make_float2((float)wv.x, (float)wv.y);
+}
+
+static cudaError_t make_map_wide(CUtensorMap* tm, const PerBinArgs& a, int C) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C};
+  cuuint64_t gstride[1] = {(cuuint64_t)a.Gp * sizeof(float2)};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * TC), (cuuint32_t)C};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(a.X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int L>
+static cudaError_t launch_wide_l(const PerBinArgs& a, cudaStream_t st) {
+  constexpr int C = 8 * L;
+  const size_t smem = (size_t)C * TC * sizeof(float2) * WSTAGES + sizeof(uint64_t) * 2 * WSTAGES + 1024;
+  CUtensorMap tm;
+  cudaError_t e = make_map_wide(&tm, a, C);
+  if (e != cudaSuccess) return e;
+  const int grid = (a.G + TC - 1) / TC;
+  if (a.kind == BTKB_BF_GSC_LMS) {
+    auto kern = k_perbin_wide<L, 1>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TC * L, smem, st>>>(tm, a);
+  } else {
+    auto kern = k_perbin_wide<L, 0>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TC * L, smem, st>>>(tm, a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace wide
+
+cudaError_t launch_perbin_wide(const PerBinArgs& a, cudaStream_t st) {
+  if (a.T <= 0 || a.G <= 0) return cudaSuccess;
+  if (a.pf_kind != BTKB_PF_NONE) return cudaErrorInvalidValue;   // the CSD state of C > 8 channels does not fit registers
+  switch (a.C) {
+    case 16: return wide::launch_wide_l<2>(a, st);
+    case 32: return wide::launch_wide_l<4>(a, st);
+    case 64: return wide::launch_wide_l<8>(a, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st) {
+  if (a.T <= 0 || a.G <= 0) return cudaSuccess;
+  if (a.C > 64) return cudaErrorInvalidValue;
+  wide::k_covariance_wide<<<a.G, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu,
+                                   int normalize_by_count, cudaStream_t st) {
+  const size_t smem = sizeof(wide::cdw) * (size_t)C * (C + 1);
+  cudaError_t e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  wide::k_mvdr_solve_wide<<<U * K, C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count);
+  return cudaGetLastError();
+}
+
+}  // namespace btkb

@@ -288,3 +288,39 @@ def test_m1024_pipe_cfg5_filterbank_shape(capi, protos):
         Yo, _, _ = restate.gsc_lms(X, FS, d[u], min_frames=4)
         assert X.shape[0] == 44 and rel_l2(Y[u], Yo[:, :513]) < TOL
         assert rel_l2(y[u], restate.synthesis(Yo, g, M, 4, 1)) < TOL
+
+
+def test_64_mic_gsc_lms_and_mvdr_cfg4_shape(capi, protos):
+    """configs[3] shape (64-mic 8x8 planar array, M = 512): NLMS GSC (lane-split per-bin kernel, projector form against the
+    reference's B-form with 64 x 63 blocking matrices) and SMI covariance + MVDR solve, against the fp64 oracle."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, C, U, n = 512, 64, 2, 5000
+    h, g = protos[M]
+    x, d = synthetic.make_batch(U, C, n, first=400)
+    lms = dict(min_frames=4)
+    p = _pipe(capi, C, M, protos, U=U, n=n, beamformer=capi.BF_GSC_LMS, lms=lms)
+    p.set_delays(d); p.submit(x); p.run(True)
+    Y = p.fetch_subband(); y = p.fetch_time()
+    Xs = []
+    for u in range(U):
+        X = np.stack([restate.analysis(x[u, c], h, M, 4, 1) for c in range(C)], axis=1)
+        Xs.append(X)
+        Yo, _, nu = restate.gsc_lms(X, FS, d[u], **lms)
+        assert rel_l2(Y[u], Yo[:, :257]) < TOL
+        assert rel_l2(y[u], restate.synthesis(Yo, g, M, 4, 1)) < TOL
+        assert p.fetch_stats()[u][2] == nu
+    # SMI-MVDR with 64 channels: covariance (one CTA per chain) + shared-memory LU solve
+    q = _pipe(capi, C, M, protos, U=U, n=n, beamformer=capi.BF_MVDR)
+    q.set_delays(d); q.submit(x); q.run_analysis()
+    q.accumulate_covariance(labels=np.array([[0.1, 0.2], [0.1, 0.2]]), energy_threshold=10.0)
+    q.calc_mvdr_weights(1.0e6)    # few noise frames (< C) make the sample covariance rank deficient: load it at signal scale
+    q.run_beamformer(True)
+    cov = q.get_covariance(); w = q.get_weights(); Yq = q.fetch_subband()
+    for u in range(U):
+        R, nf = restate.smi_covariance(Xs[u], FS, 256, ((0.1, 0.2),), 10.0)
+        assert rel_l2(cov[u], R) < 1e-5
+        wq = restate.calc_mainlobe(M, C, FS, d[u])
+        wo = restate.calc_mvdr_weights(R + float(np.float32(1.0e6)) * np.eye(C), wq, single=False)
+        assert rel_l2(w[u], wo[:257]) < 1e-3
+        assert rel_l2(Yq[u], restate.subband_mvdr(Xs[u], wo)[:, :257]) < TOL
