@@ -159,13 +159,13 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) 
 // 64 (x2 channels) MACs.  The two transforms then advance pass by pass together (independent instruction streams, one
 // in-place buffer each, every barrier covers two transforms).
 template <int M, int MT, int FR, int G>
-__global__ void __launch_bounds__(G*(M / 8), (FR == 8 ? 4 : 3)) k_analysis_r1(AnalysisArgs a) {
+__global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(AnalysisArgs a) {
   using Plan = FftPlan<M>;
   constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0, P = Plan::P;
   constexpr int D = M / 2, SH = 4;
   static_assert(FR % (2 * G) == 0, "tile must hold whole frame pairs per group");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tile = blockIdx.x, pair = blockIdx.y, u = blockIdx.z;
+  const int pair = blockIdx.y, u = blockIdx.z;
   const int tid = threadIdx.x, grp = tid / NT, tg = tid % NT;
   constexpr int W = (FR - 1) * D + MT * M;
   // the two channels are staged as separate planes (16-byte cp.async chunks land without a register round trip)
@@ -176,16 +176,34 @@ __global__ void __launch_bounds__(G*(M / 8), (FR == 8 ? 4 : 3)) k_analysis_r1(An
   float2* buf0 = fbuf + (grp * 2 + 0) * Plan::BUF;
   float2* buf1 = fbuf + (grp * 2 + 1) * Plan::BUF;
 
-  const int t0 = tile * FR;
   const int ca = 2 * pair, cb = 2 * pair + 1;
   const bool has_b = cb < a.C;
   const int len = a.lengths[u];
-  const long long w0 = (long long)(a.laN + t0 + 1) * D - (long long)MT * M;
   const float* xa = a.x + ((size_t)u * a.C + ca) * a.n_stride;
   const float* xb = a.x + ((size_t)u * a.C + (has_b ? cb : ca)) * a.n_stride;
+  // slot(q): register slot of polyphase index i_q = tg + NT q  (q = b + r NB, slot = b R0 + r)
+#define BTKB_SLOT(q) (((q) % NB) * R0 + (q) / NB)
+  float hreg[8 * MT];
+#pragma unroll
+  for (int q = 0; q < 8; q++)
+#pragma unroll
+    for (int k = 0; k < MT; k++) hreg[BTKB_SLOT(q) * MT + k] = __ldg(a.h + (tg + NT * q) + k * M);
+  FftTwiddles<M, +1> tw;
+  tw.init_from_table(tg, a.twtab);
+  constexpr int K = M / 2 + 1;
+  constexpr int NW = (NT + 31) / 32;
+  static_assert(W % 4 == 0, "tile length must be a multiple of 4 samples");
+
+  // A CTA walks a.tiles_per_cta consecutive frame tiles of its (utterance, channel pair): prototype taps and twiddles are
+  // set up once, the previous tile's last barrier protects the staged samples before they are overwritten.
+  const int ntiles = (a.T + FR - 1) / FR;
+  const int tile_end = min((int)(blockIdx.x + 1) * a.tiles_per_cta, ntiles);
+#pragma unroll 1
+  for (int tile = blockIdx.x * a.tiles_per_cta; tile < tile_end; tile++) {
+  const int t0 = tile * FR;
+  const long long w0 = (long long)(a.laN + t0 + 1) * D - (long long)MT * M;
   // Asynchronous 16-byte copies with zero fill (cp.async ... src-size): every thread puts ~W/(2 NT G) chunks per channel
   // in flight at once, samples outside [0, len) arrive as zeros (w0 and W are multiples of 4, rows are 16 B aligned).
-  static_assert(W % 4 == 0, "tile length must be a multiple of 4 samples");
   // The copies are committed in NIT groups, group i holding the samples iteration i needs beyond those of iteration i-1,
   // so the first frames start as soon as their window has landed while the rest of the tile is still in flight.
   constexpr int NIT = FR / (2 * G);
@@ -204,18 +222,6 @@ __global__ void __launch_bounds__(G*(M / 8), (FR == 8 ? 4 : 3)) k_analysis_r1(An
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  // slot(q): register slot of polyphase index i_q = tg + NT q  (q = b + r NB, slot = b R0 + r)
-#define BTKB_SLOT(q) (((q) % NB) * R0 + (q) / NB)
-  float hreg[8 * MT];
-#pragma unroll
-  for (int q = 0; q < 8; q++)
-#pragma unroll
-    for (int k = 0; k < MT; k++) hreg[BTKB_SLOT(q) * MT + k] = __ldg(a.h + (tg + NT * q) + k * M);
-  FftTwiddles<M, +1> tw;
-  tw.init(tg);
-
-  constexpr int K = M / 2 + 1;
-  constexpr int NW = (NT + 31) / 32;
 #pragma unroll 1
   for (int it = 0; it < NIT; it++) {
     const int f0 = it * 2 * G;
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR == 8 ? 4 : 3)) k_analysis_r1(An
     float2 v0[8], v1[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { v0[i] = make_float2(0.f, 0.f); v1[i] = make_float2(0.f, 0.f); }
-    if (act0) {
+    if (act0 && !(a.debug & 2)) {
       const int base = f * D + MT * M - 1;
 #pragma unroll
       for (int q = 0; q < 8; q++)
@@ -268,45 +274,40 @@ __global__ void __launch_bounds__(G*(M / 8), (FR == 8 ? 4 : 3)) k_analysis_r1(An
     fft_first_pass<M, +1>(v0, buf0, tg);
     fft_first_pass<M, +1>(v1, buf1, tg);
     __syncthreads();
-    {
-      int Ns = R0;
-#pragma unroll
-      for (int p = 0; p < P; p++) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) { v0[r] = buf0[pidx(tg + r * (M / 8))]; v1[r] = buf1[pidx(tg + r * (M / 8))]; }
-        __syncthreads();
-#pragma unroll
-        for (int r = 1; r < 8; r++) { v0[r] = cmul(v0[r], tw.tw[p][r - 1]); v1[r] = cmul(v1[r], tw.tw[p][r - 1]); }
-        dft8<+1>(v0);
-        dft8<+1>(v1);
-        stockham_store<8>(buf0, v0, tg, Ns);
-        stockham_store<8>(buf1, v1, tg, Ns);
-        __syncthreads();
-        Ns *= 8;
-      }
+    if (!(a.debug & 4)) {
+      auto sync = [] { __syncthreads(); };
+      FftPassChain<M, +1, 0, decltype(sync)>::run(v0, v1, buf0, buf1, tg, tw, sync);
     }
-    // ---- untangle the channel pair, write snapshots, channel-0 energy
+    // ---- untangle the channel pair, write snapshots, channel-0 energy.  After the last pass this thread holds
+    // Z[tg + r NT] in v[r]; bins k = tg + q NT (q < 4) and k = M/2 (tg == 0, r = 4) are its own, only the partner
+    // Z[M - k] (upper half, natural order in the buffer) comes from shared memory.
     float e0 = 0.f, e1 = 0.f;
 #pragma unroll
     for (int q = 0; q <= 4; q++) {
       const int k = tg + q * NT;
       if (q == 4 && tg != 0) break;
       const float wgt = (k == 0 || k == M / 2) ? 1.f : 2.f;
-      const int km = (M - k) & (M - 1);
+      const bool self = (k == 0) || (q == 4);       // Z[M - k] is this thread's own value (k = 0 and k = M/2)
       if (act0) {
-        const float2 zk = buf0[pidx(k)], zm = buf0[pidx(km)];
+        const float2 zk = v0[q];
+        const float2 zm = self ? zk : buf0[M - k];
         const float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        if (!(a.debug & 1)) {
         a.X[((size_t)ta * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
         if (has_b) a.X[((size_t)ta * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
+        }
         e0 = fmaf(wgt, fmaf(A.x, A.x, A.y * A.y), e0);
       }
       if (act1) {
-        const float2 zk = buf1[pidx(k)], zm = buf1[pidx(km)];
+        const float2 zk = v1[q];
+        const float2 zm = self ? zk : buf1[M - k];
         const float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        if (!(a.debug & 1)) {
         a.X[((size_t)tb * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
         if (has_b) a.X[((size_t)tb * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
+        }
         e1 = fmaf(wgt, fmaf(A.x, A.x, A.y * A.y), e1);
       }
     }
@@ -325,18 +326,28 @@ __global__ void __launch_bounds__(G*(M / 8), (FR == 8 ? 4 : 3)) k_analysis_r1(An
     }
     __syncthreads();  // untangle reads done before the next iteration's first pass overwrites the buffers
   }
+  }  // tile loop
 #undef BTKB_SLOT
 }
 
 template <int M, int MT, int FR>
-static cudaError_t launch_analysis_r1(const AnalysisArgs& a, cudaStream_t st) {
+static cudaError_t launch_analysis_r1(const AnalysisArgs& a_in, cudaStream_t st) {
+  AnalysisArgs a = a_in;
   using Plan = FftPlan<M>;
   constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
   size_t smem = sizeof(float2) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * 4;
   auto kern = k_analysis_r1<M, MT, FR, G>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((a.T + FR - 1) / FR, (a.C + 1) / 2, a.U);
+  // tiles per CTA: amortise the per-CTA set-up while keeping >= ~8 waves of CTAs for balance
+  const int ntiles = (a.T + FR - 1) / FR;
+  const long long ctas1 = (long long)ntiles * ((a.C + 1) / 2) * a.U;
+  int tpc = 1;
+  while (tpc < 8 && tpc * 2 <= ntiles && ctas1 / (tpc * 2) >= 148LL * 3 * 8) tpc *= 2;
+  if (const char* e = getenv("BTKB_ANALYSIS_TPC")) { int v = atoi(e); if (v >= 1 && v <= 64) tpc = v; }
+  a.tiles_per_cta = tpc;
+  if (const char* e = getenv("BTKB_ANALYSIS_DEBUG")) a.debug = atoi(e);
+  dim3 grid((ntiles + tpc - 1) / tpc, (a.C + 1) / 2, a.U);
   kern<<<grid, G * Plan::NT, smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -358,14 +369,14 @@ static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
 
 static int analysis_tile_frames() {  // tuning knob (frames per CTA tile): BTKB_ANALYSIS_FR=8|16 (default 16)
   static int v = -1;
-  if (v < 0) { const char* e = getenv("BTKB_ANALYSIS_FR"); v = (e && atoi(e) == 8) ? 8 : 16; }
+  if (v < 0) { const char* e = getenv("BTKB_ANALYSIS_FR"); v = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 12) ? 12 : 16; }
   return v;
 }
 
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st) {
 #define BTKB_CASE(MM)                                                                  \
   case MM:                                                                             \
-    if (a.m == 4 && a.D == MM / 2) return (analysis_tile_frames() == 8) ? launch_analysis_r1<MM, 4, 8>(a, st) : launch_analysis_r1<MM, 4, 16>(a, st); \
+    if (a.m == 4 && a.D == MM / 2) return (analysis_tile_frames() == 8) ? launch_analysis_r1<MM, 4, 8>(a, st) : (analysis_tile_frames() == 12 && MM == 512) ? launch_analysis_r1<MM, 4, (MM == 512 ? 12 : 16)>(a, st) : launch_analysis_r1<MM, 4, 16>(a, st); \
     return (a.m == 4) ? launch_analysis_m<MM, 4>(a, st) : launch_analysis_m<MM, 0>(a, st);
   switch (a.M) {
     BTKB_CASE(256) BTKB_CASE(512) BTKB_CASE(1024) BTKB_CASE(2048)

@@ -37,7 +37,7 @@ struct btkb_pipeline {
   double *d_delays = nullptr, *d_mpos = nullptr, *d_labels = nullptr, *d_stats = nullptr;
   unsigned char* d_mask = nullptr; int* d_count = nullptr;
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
-  int16_t* d_x16 = nullptr; double* h_delays = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
+  int16_t* d_x16 = nullptr; double* h_delays = nullptr; float2* d_tw = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
   double* d_delaysJ = nullptr;
@@ -82,7 +82,7 @@ void btkb_destroy(btkb_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
   void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
-                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ};
+                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw};
   if (p->h_delays) cudaFreeHost(p->h_delays);
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -144,11 +144,20 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   A((void**)&p->d_stats, U * 3 * sizeof(double));
   A((void**)&p->d_mask, T * U);
   A((void**)&p->d_count, U * sizeof(int));
+  A((void**)&p->d_tw, (size_t)M * sizeof(float2));
   if (e != cudaSuccess) {
     std::string msg = std::string("btkb_create: allocation failed: ") + cudaGetErrorString(e);
     btkb_destroy(p);
     cudaGetLastError();
     return fail(BTKB_ERR_ALLOC, msg);
+  }
+  {  // twiddle table exp(+2 pi i n / M) in double precision, rounded once
+    std::vector<float2> tw(M);
+    for (int i = 0; i < M; i++) { const double a = 2.0 * M_PI * (double)i / (double)M; tw[i] = make_float2((float)cos(a), (float)sin(a)); }
+    if (cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+      btkb_destroy(p); cudaGetLastError();
+      return fail(BTKB_ERR_CUDA, "btkb_create: twiddle upload failed");
+    }
   }
   *out = p;
   return BTKB_OK;
@@ -373,7 +382,7 @@ static int do_analysis(btkb_pipeline* p) {
   if (!p->have_h) return fail(BTKB_ERR_STATE, "btkb_run: set the analysis prototype first");
   if (p->U == 0) return fail(BTKB_ERR_STATE, "btkb_run: no batch submitted");
   AnalysisArgs a{p->x_cur, p->d_len, p->d_h, p->d_X, p->d_E, p->U, p->C, p->n, (p->x_cur == p->d_x) ? p->n_stride : p->n, p->T, p->M, p->m, p->D, p->laN,
-                 p->Gp, 1};
+                 p->Gp, 1, p->d_tw, 1, 0};
   CK(launch_analysis(a, p->stream));
   p->launches++;
   p->have_X = true;
@@ -419,7 +428,7 @@ static int do_synthesis(btkb_pipeline* p) {
   if (!p->have_Y) return fail(BTKB_ERR_STATE, "btkb_run: no beamformer output to synthesise");
   CK(cudaMemsetAsync(p->d_stats, 0, (size_t)p->U * 3 * sizeof(double), p->stream));
   SynthesisArgs a{p->d_Y, p->d_len, p->d_g, p->d_time, p->d_stats, p->U, p->n, p->T, p->M, p->m, p->cfg.r, p->D, p->K, p->Gp, p->pdS, p->laN, p->pdA,
-                  p->nb, p->nb * p->D, p->cfg.synthesis_gain};
+                  p->nb, p->nb * p->D, p->cfg.synthesis_gain, p->d_tw};
   CK(launch_synthesis(a, p->stream));
   p->launches++;
   p->have_time = true;

@@ -34,15 +34,24 @@ struct FftPlan {
   static_assert(M >= 64 && M <= 4096 && (M & (M - 1)) == 0, "M must be a power of two in [64,4096]");
   static constexpr int log2m() { int q = 0; for (int v = M; v > 1; v >>= 1) q++; return q; }
   static constexpr int P = (log2m() - 1) / 3;                           // number of radix-8 passes
-  static constexpr int pow8(int p) { return p == 0 ? 1 : 8 * pow8(p - 1); }
+  __host__ __device__ static constexpr int pow8(int p) { return p == 0 ? 1 : 8 * pow8(p - 1); }
   static constexpr int R0 = M / pow8(P);                                // leading radix: 2, 4 or 8
   static constexpr int NT = M / 8;                                      // threads per transform
   static constexpr int NPASS = P + 1;
-  static constexpr int BUF = M + M / 16;                                // padded buffer length (float2)
+  static constexpr int BUF = M + M / 16;                                // padded buffer length (float2), covers every layout of lidx<>
 };
 
 // padded shared-memory index: breaks the stride-8 / stride-64 patterns of the pass outputs
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+
+// Per-exchange shared-memory layouts (a store and the load that consumes it must agree; different exchanges may differ):
+//   0 identity            for stores with stride >= 16 (lanes consecutive) and the natural-order spectrum
+//   1 i + (i >> 4)        for the leading pass (lane stride R0 <= 8 elements)
+//   2 i ^ (bit6(i) << 3)  for the radix-8 pass with Ns = 8 (lanes (a, b) -> 64 a + b): the two a-groups of a half warp
+//                         land 8 slots apart, which the i >> 4 padding does not achieve (2-way conflicts, ncu r01b)
+template <int LAY>
+__device__ __forceinline__ int lidx(int i) { return LAY == 0 ? i : (LAY == 1 ? i + (i >> 4) : (i ^ (((i >> 6) & 1) << 3))); }
+__host__ __device__ constexpr int lay_of(int Ns) { return Ns >= 16 ? 0 : (Ns == 8 ? 2 : 1); }
 
 template <int SIGN>
 __device__ __forceinline__ void dft2(float2& a, float2& b) {
@@ -89,6 +98,22 @@ struct FftTwiddles {
         // angle / pi = SIGN * 2 k r / (8 Ns)  (exact in float: k r < 2^15, power-of-two denominator)
         sincospif((float)(SIGN * 2 * k * r) / (float)(8 * Ns), &s, &c);
         tw[p][r - 1] = make_float2(c, s);
+      }
+      Ns *= 8;
+    }
+  }
+  // Same values from a table tab[n] = exp(+2 pi i n / M), n < M, built once on the host in double precision: 7 P loads
+  // instead of 7 P sincospif evaluations (~40 instructions each) in every CTA prologue.
+  __device__ __forceinline__ void init_from_table(int tid, const float2* __restrict__ tab) {
+    int Ns = Plan::R0;
+#pragma unroll
+    for (int p = 0; p < Plan::P; p++) {
+      const int k = tid % Ns;
+      const int step = M / (8 * Ns);
+#pragma unroll
+      for (int r = 1; r < 8; r++) {
+        float2 w = __ldg(tab + k * r * step);     // k r < 8 Ns  =>  index < M
+        tw[p][r - 1] = (SIGN > 0) ? w : make_float2(w.x, -w.y);
       }
       Ns *= 8;
     }
@@ -154,5 +179,46 @@ __device__ __forceinline__ float2* fft_run(float2* v, float2* bufA, float2* bufB
   }
   return in;
 }
+
+
+// One radix-8 pass (index PASS among the P radix-8 passes) of TWO independent transforms held in v0 / v1, exchanged through
+// their own in-place buffers b0 / b1.  The buffers were filled by the previous exchange with layout lay_of(previous stride).
+// On the last pass only the upper half of the spectrum (indices >= M/2, i.e. r = 4..7) is written back, in natural order:
+// callers that untangle real sequences keep Z[k] for k < M/2 in registers (v[r], r < 4) and fetch only Z[M - k].
+template <int M, int SIGN, int PASS, typename Sync>
+__device__ __forceinline__ void fft_pass_pair(float2* v0, float2* v1, float2* b0, float2* b1, int tg, const FftTwiddles<M, SIGN>& T, Sync sync) {
+  using Plan = FftPlan<M>;
+  constexpr int NsPrev = (PASS == 0) ? 1 : Plan::R0 * Plan::pow8(PASS - 1);
+  constexpr int Ns = Plan::R0 * Plan::pow8(PASS);
+  constexpr int LIN = (PASS == 0) ? 1 : lay_of(NsPrev);
+  constexpr int LOUT = lay_of(Ns);
+#pragma unroll
+  for (int r = 0; r < 8; r++) { v0[r] = b0[lidx<LIN>(tg + r * (M / 8))]; v1[r] = b1[lidx<LIN>(tg + r * (M / 8))]; }
+  sync();
+#pragma unroll
+  for (int r = 1; r < 8; r++) { v0[r] = cmul(v0[r], T.tw[PASS][r - 1]); v1[r] = cmul(v1[r], T.tw[PASS][r - 1]); }
+  dft8<SIGN>(v0);
+  dft8<SIGN>(v1);
+  if (PASS == Plan::P - 1) {
+    static_assert(Ns * 8 == M || PASS != Plan::P - 1, "last pass stride");
+#pragma unroll
+    for (int r = 4; r < 8; r++) { b0[tg + r * (M / 8)] = v0[r]; b1[tg + r * (M / 8)] = v1[r]; }
+  } else {
+    const int k = tg % Ns;
+    const int j0 = (tg - k) * 8 + k;
+#pragma unroll
+    for (int r = 0; r < 8; r++) { b0[lidx<LOUT>(j0 + r * Ns)] = v0[r]; b1[lidx<LOUT>(j0 + r * Ns)] = v1[r]; }
+  }
+  sync();
+}
+template <int M, int SIGN, int PASS, typename Sync>
+struct FftPassChain {
+  static __device__ __forceinline__ void run(float2* v0, float2* v1, float2* b0, float2* b1, int tg, const FftTwiddles<M, SIGN>& T, Sync sync) {
+    if constexpr (PASS < FftPlan<M>::P) {
+      fft_pass_pair<M, SIGN, PASS>(v0, v1, b0, b1, tg, T, sync);
+      FftPassChain<M, SIGN, PASS + 1, Sync>::run(v0, v1, b0, b1, tg, T, sync);
+    }
+  }
+};
 
 }  // namespace btkb

@@ -17,12 +17,16 @@ struct AnalysisArgs {
   const float* x; const int* lengths; const float* h;
   float2* X; float* E;
   int U, C, n, n_stride, T, M, m, D, laN, Gp, gain;
+  const float2* twtab;   // exp(+2 pi i n / M), n < M (device)
+  int tiles_per_cta;     // set by the launcher
+  int debug;             // BTKB_ANALYSIS_DEBUG bit mask (profiling experiments only): 1 skip X stores, 2 skip fold, 4 skip FFT passes
 };
 
 struct SynthesisArgs {
   const float2* Y; const int* lengths; const float* g;
   float* out; double* stats;  // stats [U][3]: sum of squares accumulated into [u][0]
   int U, n, T, M, m, r, D, K, Gp, pdS, laN, pdA, nb, nb_stride, gain;
+  const float2* twtab;   // exp(+2 pi i n / M), n < M (device)
 };
 
 struct LmsArgs {

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
         gt[j][s2][k] = (d < D) ? __ldg(a.g + (M - 1 - (d + s2 * D)) + k * M) : 0.f;
       }
   FftTwiddles<M, -1> tw;
-  tw.init(tg);
+  tw.init_from_table(tg, a.twtab);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 

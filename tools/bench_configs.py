@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Device-side timing of the BASELINE.json configs other than the bench.py headline (configs[1]) — parity-test shapes run at
+full size for the record (profiles/), not bench lines.  python tools/bench_configs.py > gpurun_out/configs.json"""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from distant_speech_recognition_b200 import _capi, synthetic
+
+FS = 16000.0
+
+
+def proto(M):
+    p = np.load(os.path.join(ROOT, "tests", "golden", "prototype_M%d_m4_r1.npz" % M)); return p["h"], p["g"]
+
+
+def tiled_batch(U, C, n, distinct):
+    x, d = synthetic.make_batch(distinct, C, n, pcm16=True)
+    reps = -(-U // distinct)
+    return np.tile(x, (reps, 1, 1))[:U], np.tile(d, (reps, 1))[:U]
+
+
+def timed(fn, steps=5, warm=2):
+    for _ in range(warm): fn()
+    t0 = time.perf_counter()
+    for _ in range(steps): fn()
+    return (time.perf_counter() - t0) / steps
+
+
+def main():
+    out = {}
+    # configs[0]: 2-mic D&S, M=256, one 10 s utterance
+    C, M, U, n = 2, 256, 1, 160000
+    h, g = proto(M); x, d = tiled_batch(U, C, n, 1)
+    p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_DS, max_utterances=U, max_samples=n); p.set_prototypes(h, g); p.set_delays(d); p.submit(x)
+    def f0(): p.run(True); p.synchronize()
+    s = timed(f0); T = p.num_frames
+    out["configs[0] 2-mic SubbandDS M=256 1x10s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels=p.last_timing())
+    p.close()
+    # configs[2]: 8-mic SMI-MVDR + Zelinski, M=512, 1000 utterances
+    C, M, U, n = 8, 512, 1000, 80000
+    h, g = proto(M); x, d = tiled_batch(U, C, n, 16)
+    p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_MVDR, postfilter=_capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.synchronize()
+    labels = np.tile(np.array([[1.0, 5.0]]), (U, 1))
+    def f2():
+        p.run_analysis(); p.accumulate_covariance(labels, 10.0); p.calc_mvdr_weights(1e-4); p.run_beamformer(True); p.synchronize()
+    s = timed(f2, steps=3, warm=1); T = p.num_frames
+    out["configs[2] 8-mic SMI-MVDR+Zelinski M=512 1000x5s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels_last_call=p.last_timing())
+    p.close(); del x
+    # configs[3]: 64-mic GSC-NLMS, M=512, 256 utterances
+    C, M, U, n = 64, 512, 256, 80000
+    h, g = proto(M); x, d = tiled_batch(U, C, n, 4)
+    p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_GSC_LMS, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.synchronize()
+    def f3(): p.run(True); p.synchronize()
+    s = timed(f3, steps=3, warm=1); T = p.num_frames; t = p.last_timing()
+    bytes_perbin = (C + 1) * (M // 2 + 1) * 8 * U * T
+    out["configs[3] 64-mic GSC-NLMS M=512 256x5s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels=t,
+                                                          perbin_hbm_frac=bytes_perbin / (t["perbin_ms"] * 1e-3) / 1e9 / 6566.7)
+    p.close()
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
