@@ -1,11 +1,12 @@
 // btkb_perbin.cu — K4 (+K2, K6): the fused per-bin spatial kernel (sm_100a).
 //
-// One thread owns one (utterance, bin) chain and walks the frames in order; a CTA owns TILE = 128 consecutive chains
-// of the flattened g = u K + k axis.  Per frame the CTA's mic x bin tile ([C][128] complex64, C KiB) is brought from
-// HBM into a 4-deep shared-memory ring by bulk asynchronous copies (cp.async.bulk + mbarrier complete_tx, i.e. the TMA
-// engine; SASS: UBLKCP), issued by one elected thread, so the recurrences never wait on a global load and the loads
-// are full 1 KiB row segments.  All per-chain state (weights, NLMS vector, sub-band energy, cross-spectral densities,
-// covariance accumulators) lives in registers for the whole utterance.
+// One thread owns one (utterance, bin) chain and walks the frames in order; a CTA owns TILE = 64 consecutive chains
+// of the flattened g = u K + k axis.  The CTA's mic x bin tile of FCH = 2 frames ([2][C][64] complex64, 8 KiB at C = 8) is
+// brought from HBM into a 3-slot shared-memory ring by ONE tensor-map TMA instruction per slot
+// (cp.async.bulk.tensor.2d + mbarrier complete_tx; SASS: UTMALDG.2D), issued by one elected thread; slots are released
+// through per-slot `empty` mbarriers (one arrival per warp), so the frame loop has no CTA-wide barrier and the
+// recurrences never wait on a global load.  All per-chain state (weights, NLMS vector, sub-band energy, cross-spectral
+// densities, covariance accumulators) lives in registers for the whole utterance.
 //
 // What it replaces (reference: btk20_src/):
 //   static weights   SubbandDS::next            beamformer/beamformer.cc:1095-1157   y = wq^H x
