@@ -27,6 +27,7 @@ class RefConfig(ct.Structure):
         ("lms_max_wa_l2norm", ct.c_double),
         ("lms_min_frames", ct.c_int), ("lms_slowdown_after", ct.c_int),
         ("do_synthesis", ct.c_int),
+        ("pf_threshold", ct.c_double), ("pf_min_sv", ct.c_double), ("pf_diag_load", ct.c_double), ("pf_fbin1", ct.c_int),
     ]
 
 
@@ -131,7 +132,9 @@ def beamform(samples, h, g, delays, M, m=4, r=1, dct=2, samplerate=16000.0, bf_k
     if lms:
         lp.update(lms)
     cfg = RefConfig(C=C, M=M, m=m, r=r, delay_compensation_type=dct, samplerate=samplerate, bf_kind=bf_kind,
-                    pf_kind=0 if pf is None else 1,
+                    pf_kind=0 if pf is None else {"zelinski": 1, "mccowan": 2, "lefkimmiatis": 3}[pf.get("kind", "zelinski")],
+                    pf_threshold=0.99 if pf is None else pf.get("threshold", 0.99), pf_min_sv=1e-8 if pf is None else pf.get("min_sv", 1e-8),
+                    pf_diag_load=0.0 if pf is None else pf.get("diag_load", 0.01), pf_fbin1=0 if pf is None else pf.get("fbin1", 0),
                     pf_alpha=0.0 if pf is None else pf.get("alpha", 0.6), pf_type=2 if pf is None else pf.get("type", 2),
                     pf_min_frames=0 if pf is None else pf.get("min_frames", 0),
                     mvdr_mu=mvdr_mu, sspeed=sspeed, smi_target_start=smi_label[0], smi_target_end=smi_label[1],

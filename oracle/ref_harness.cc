@@ -83,6 +83,28 @@ class ArrayComplexSource : public VectorComplexFeatureStream {
   const double* f_; unsigned T_, M_;
 };
 
+// Pass-through stream that records every frame the synthesis bank pulls (one pass only: a second pass after reset()
+// would see the post-filters' vector_ still holding the previous pass's upper bins, postfilter.cc:826-919).
+class SubbandTap : public VectorComplexFeatureStream {
+ public:
+  SubbandTap(VectorComplexFeatureStreamPtr& src, unsigned M, double* out, int cap)
+      : VectorComplexFeatureStream(M, "SubbandTap"), src_(src), M_(M), out_(out), cap_(cap), T_(0) {}
+  virtual const gsl_vector_complex* next(int frame_no = -5) {
+    if (frame_no == frame_no_) return vector_;
+    const gsl_vector_complex* v = src_->next(frame_no);
+    increment_();
+    memcpy(vector_->data, v->data, sizeof(double) * 2 * M_);
+    if (out_ && frame_no_ < cap_) memcpy(out_ + (size_t)2 * frame_no_ * M_, v->data, sizeof(double) * 2 * M_);
+    T_ = frame_no_ + 1;
+    return vector_;
+  }
+  virtual void reset() { src_->reset(); VectorComplexFeatureStream::reset(); }
+  int frames() const { return T_; }
+ private:
+  VectorComplexFeatureStreamPtr src_; unsigned M_; double* out_; int cap_; int T_;
+};
+typedef Inherit<SubbandTap, VectorComplexFeatureStreamPtr> SubbandTapPtr;
+
 typedef std::complex<double> cplx;
 
 struct LmsParams {
@@ -225,6 +247,9 @@ struct ref_config {
   double lms_beta, lms_gamma, lms_init_diagonal_load, lms_regularization_param, lms_energy_floor, lms_sil_thresh, lms_max_wa_l2norm;
   int lms_min_frames, lms_slowdown_after;
   int do_synthesis;
+  /* post-filters beyond Zelinski (pf_kind 2 = McCowan, 3 = Lefkimmiatis; postfilter.cc:496-1200), wired like
+     unit_test/test_online_beamforming.py:137-151: diffuse coherence from mpos + diagonal loading */
+  double pf_threshold, pf_min_sv, pf_diag_load; int pf_fbin1;
 };
 
 /* analysis only: samples[n] -> out[T][M] complex128 interleaved; returns T (or -1 if T > T_cap) */
@@ -457,13 +482,36 @@ int ref_beamform(const ref_config* cfg, const float* samples, int n, const doubl
     }
     VectorComplexFeatureStreamPtr tail = bfstream;
     ZelinskiPostFilterPtr pf;
+    McCowanPostFilterPtr pfm; LefkimmiatisPostFilterPtr pfl;
+    if (cfg->pf_kind == 2 || cfg->pf_kind == 3) {  // test_online_beamforming.py:137-151,204
+      if (cfg->bf_kind == 4) throw j_error("post-filters after the restated NLMS are not wired in the harness\n");
+      gsl_matrix* mp = gsl_matrix_alloc(C, 3);
+      for (int c = 0; c < C; c++) for (int j = 0; j < 3; j++) gsl_matrix_set(mp, c, j, mpos[c * 3 + j]);
+      if (cfg->pf_kind == 2) {
+        pfm = new McCowanPostFilter(bfstream, M, cfg->pf_alpha, cfg->pf_type, cfg->pf_min_frames, (float)cfg->pf_threshold);
+        pfm->set_diffuse_noise_model(mp, cfg->samplerate, cfg->sspeed);
+        pfm->set_all_diagonal_loading((float)cfg->pf_diag_load);
+        pfm->set_beamformer(bf_for_pf);
+        tail = (VectorComplexFeatureStreamPtr&)pfm;
+      } else {
+        pfl = new LefkimmiatisPostFilter(bfstream, M, cfg->pf_min_sv, cfg->pf_fbin1, cfg->pf_alpha, cfg->pf_type, cfg->pf_min_frames, (float)cfg->pf_threshold);
+        pfl->set_diffuse_noise_model(mp, cfg->samplerate, cfg->sspeed);
+        pfl->set_all_diagonal_loading((float)cfg->pf_diag_load);
+        pfl->calc_inverse_noise_spatial_spectral_matrix();
+        pfl->set_beamformer(bf_for_pf);
+        tail = (VectorComplexFeatureStreamPtr&)pfl;
+      }
+      gsl_matrix_free(mp);
+    }
     if (cfg->pf_kind == 1) {  // test_online_beamforming.py:132-136,204
       if (cfg->bf_kind == 4) throw j_error("Zelinski after the restated NLMS is not wired in the harness\n");
       pf = new ZelinskiPostFilter(bfstream, M, cfg->pf_alpha, cfg->pf_type, cfg->pf_min_frames);
       pf->set_beamformer(bf_for_pf);
       tail = (VectorComplexFeatureStreamPtr&)pf;
     }
+    SubbandTapPtr tap;
     if (cfg->do_synthesis) {
+      if (Y_out) { tap = new SubbandTap(tail, M, Y_out, T_cap); tail = (VectorComplexFeatureStreamPtr&)tap; }
       OverSampledDFTSynthesisBankPtr sfb = new OverSampledDFTSynthesisBank(tail, gv, M, m, r, dct);
       // tap the subband stream as it passes: the synthesis bank pulls `tail`; re-reading current() is idempotent
       for (;;) {
@@ -480,8 +528,9 @@ int ref_beamform(const ref_config* cfg, const float* samples, int n, const doubl
       // timing mode (bench.py): one pass only; frames = blocks + synthesis processing delay (modulated.cc:246-264)
       const int R = 1 << r;
       T = nb + ((dct == 1) ? m * R - 1 : (dct == 2) ? m * R / 2 : 2 * m - 1);
+    } else if (cfg->do_synthesis) {
+      T = tap->frames();
     } else {
-      if (cfg->do_synthesis) tail->reset();
       for (;;) {
         const gsl_vector_complex* Y;
         try { Y = tail->next(); } catch (jiterator_error& e) { break; }
