@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libbtkb.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "btkb.h")
 
 BF_DS, BF_GSC, BF_MVDR, BF_GSC_LMS = 0, 1, 2, 3
-PF_NONE, PF_ZELINSKI = 0, 1
+PF_NONE, PF_ZELINSKI, PF_MCCOWAN, PF_LEFKIMMIATIS = 0, 1, 2, 3
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
 
 
@@ -33,7 +33,8 @@ class Config(ct.Structure):
     _fields_ = [("device", ct.c_int), ("channels", ct.c_int), ("fft_len", ct.c_int), ("m", ct.c_int), ("r", ct.c_int),
                 ("delay_compensation_type", ct.c_int), ("samplerate", ct.c_float), ("beamformer", ct.c_int),
                 ("postfilter", ct.c_int), ("pf_alpha", ct.c_float), ("pf_type", ct.c_int), ("pf_min_frames", ct.c_int),
-                ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int), ("normalize_weight", ct.c_int)]
+                ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int), ("normalize_weight", ct.c_int),
+                ("pf_threshold", ct.c_float), ("pf_min_sv", ct.c_double), ("pf_fbin1", ct.c_int)]
 
 
 def _load():
@@ -71,13 +72,14 @@ class Pipeline:
 
     def __init__(self, channels, fft_len=512, m=4, r=1, delay_compensation_type=2, samplerate=16000.0, beamformer=BF_DS,
                  postfilter=PF_NONE, pf_alpha=0.6, pf_type=2, pf_min_frames=0, lms=None, max_utterances=1,
-                 max_samples=160000, device=0, normalize_weight=False):
+                 max_samples=160000, device=0, normalize_weight=False, pf_threshold=0.99, pf_min_sv=1.0e-8, pf_fbin1=0):
         cfg = Config()
         lib.btkb_default_config(ct.byref(cfg))
         cfg.device = device; cfg.channels = channels; cfg.fft_len = fft_len; cfg.m = m; cfg.r = r
         cfg.delay_compensation_type = delay_compensation_type; cfg.samplerate = samplerate
         cfg.beamformer = beamformer; cfg.postfilter = postfilter
         cfg.pf_alpha = pf_alpha; cfg.pf_type = pf_type; cfg.pf_min_frames = pf_min_frames
+        cfg.pf_threshold = pf_threshold; cfg.pf_min_sv = pf_min_sv; cfg.pf_fbin1 = pf_fbin1
         if lms:
             for k, v in lms.items():
                 setattr(cfg.lms, k, v)
@@ -140,6 +142,27 @@ class Pipeline:
     def set_diffuse_noise_model(self, U, mpos, sspeed=343740.0):
         mp = np.ascontiguousarray(mpos, np.float64)
         _check(lib.btkb_set_diffuse_noise_model(self._h, ct.c_int(U), _dp(mp), ct.c_float(sspeed)))
+
+    # ---- noise coherence of the McCowan / Lefkimmiatis post-filters (postfilter.cc:541-680)
+    def pf_set_diffuse_noise_model(self, mpos, samplerate=16000.0, sspeed=343740.0):
+        mp = np.ascontiguousarray(mpos, np.float64)
+        _check(lib.btkb_pf_set_diffuse_noise_model(self._h, _dp(mp), ct.c_double(samplerate), ct.c_double(sspeed)))
+
+    def pf_set_noise_coherence(self, R):
+        R = np.ascontiguousarray(R, np.complex128)
+        assert R.shape == (self.K, self.C, self.C)
+        _check(lib.btkb_pf_set_noise_coherence(self._h, R.ctypes.data_as(ct.POINTER(ct.c_double))))
+
+    def pf_get_noise_coherence(self):
+        R = np.empty((self.K, self.C, self.C), np.complex128)
+        _check(lib.btkb_pf_get_noise_coherence(self._h, R.ctypes.data_as(ct.POINTER(ct.c_double))))
+        return R
+
+    def pf_set_diagonal_loading(self, mu):
+        _check(lib.btkb_pf_set_diagonal_loading(self._h, ct.c_float(mu)))
+
+    def pf_divide_nondiagonal(self, mu):
+        _check(lib.btkb_pf_divide_nondiagonal(self._h, ct.c_float(mu)))
 
     def calc_mvdr_weights(self, mu):
         _check(lib.btkb_calc_mvdr_weights(self._h, ct.c_float(mu)))

@@ -38,6 +38,8 @@ struct btkb_pipeline {
   unsigned char* d_mask = nullptr; int* d_count = nullptr;
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   int16_t* d_x16 = nullptr; double* h_delays = nullptr; float2* d_tw = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
+  double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
+  bool have_pfR = false, pf_applied = false;  // pf_applied: d_Y came out of this pipeline's post-filter (not btkb_set_subband)
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
   double* d_delaysJ = nullptr;
@@ -65,6 +67,7 @@ void btkb_default_config(btkb_config* c) {
   c->device = 0; c->channels = 8; c->fft_len = 512; c->m = 4; c->r = 1; c->delay_compensation_type = 2;
   c->samplerate = 16000.f; c->beamformer = BTKB_BF_DS; c->postfilter = BTKB_PF_NONE;
   c->pf_alpha = 0.6f; c->pf_type = 2; c->pf_min_frames = 0;
+  c->pf_threshold = 0.99f; c->pf_min_sv = 1.0e-8; c->pf_fbin1 = 0;
   c->lms.beta = 0.97f; c->lms.gamma = 0.01f; c->lms.init_diagonal_load = 1.0e6f; c->lms.regularization_param = 1.0e-4f;
   c->lms.energy_floor = 90.f; c->lms.sil_thresh = 1.0e8f; c->lms.max_wa_l2norm = 100.f; c->lms.min_frames = 128; c->lms.slowdown_after = 4096;
   c->max_utterances = 1; c->max_samples = 160000; c->keep_snapshots = 1; c->synthesis_gain = 1;
@@ -82,7 +85,8 @@ void btkb_destroy(btkb_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
   void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
-                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw};
+                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
+                  p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM};
   if (p->h_delays) cudaFreeHost(p->h_delays);
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -106,6 +110,9 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   if (C > 64) return fail(BTKB_ERR_INVALID, "btkb_create: at most 64 channels");
   if (cfg->max_utterances < 1 || cfg->max_samples < 1) return fail(BTKB_ERR_INVALID, "btkb_create: capacities must be positive");
   if (cfg->beamformer < BTKB_BF_DS || cfg->beamformer > BTKB_BF_GSC_LMS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown beamformer kind");
+  if (cfg->postfilter < BTKB_PF_NONE || cfg->postfilter > BTKB_PF_LEFKIMMIATIS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown post-filter kind");
+  if (cfg->postfilter >= BTKB_PF_MCCOWAN && (C < 2 || C > 8))
+    return fail(BTKB_ERR_INVALID, "btkb_create: the McCowan / Lefkimmiatis post-filters are built for 2..8 channels");
   if (cfg->beamformer == BTKB_BF_GSC_LMS && cfg->postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCLMSBeamformer");
   CK(cudaSetDevice(cfg->device));
@@ -137,7 +144,13 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   A((void**)&p->d_E, T * U * sizeof(float));
   A((void**)&p->d_time, U * (T * p->D) * sizeof(float));
   A((void**)&p->d_upd, U * sizeof(float));
-  if (cfg->postfilter == BTKB_PF_ZELINSKI) A((void**)&p->d_PFW, T * G * sizeof(float));
+  if (cfg->postfilter != BTKB_PF_NONE) A((void**)&p->d_PFW, T * G * sizeof(float));
+  if (cfg->postfilter >= BTKB_PF_MCCOWAN) {
+    A((void**)&p->d_pfR, (size_t)p->K * C * C * sizeof(double2));
+    A((void**)&p->d_pfInvR, (size_t)p->K * C * C * sizeof(double2));
+    A((void**)&p->d_pfQ, (size_t)pf_num_consts(C) * p->K * sizeof(float2));
+    A((void**)&p->d_LAM, G * sizeof(float));
+  }
   A((void**)&p->d_delays, U * C * sizeof(double));
   A((void**)&p->d_mpos, (size_t)C * 3 * sizeof(double));
   A((void**)&p->d_labels, U * 2 * sizeof(double));
@@ -306,6 +319,59 @@ int btkb_set_diffuse_noise_model(btkb_pipeline* p, int U, const double* mpos, fl
   return BTKB_OK;
 }
 
+static int pf_check(btkb_pipeline* p, const char* who) {
+  if (!p) return fail(BTKB_ERR_INVALID, std::string(who) + ": null pipeline");
+  if (!p->d_pfR) return fail(BTKB_ERR_STATE, std::string(who) + ": pipeline was not created with BTKB_PF_MCCOWAN or BTKB_PF_LEFKIMMIATIS");
+  return BTKB_OK;
+}
+
+int btkb_pf_set_diffuse_noise_model(btkb_pipeline* p, const double* mpos, double samplerate, double sspeed) {
+  int rc = pf_check(p, "btkb_pf_set_diffuse_noise_model"); if (rc) return rc;
+  if (!mpos) return fail(BTKB_ERR_INVALID, "btkb_pf_set_diffuse_noise_model: null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(p->d_mpos, mpos, (size_t)p->C * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  CK(launch_pf_diffuse(p->d_mpos, p->d_pfR, p->C, p->M, p->K, samplerate, sspeed, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_pfR = true;
+  return BTKB_OK;
+}
+
+int btkb_pf_set_noise_coherence(btkb_pipeline* p, const double* R) {
+  int rc = pf_check(p, "btkb_pf_set_noise_coherence"); if (rc) return rc;
+  if (!R) return fail(BTKB_ERR_INVALID, "btkb_pf_set_noise_coherence: null argument");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(p->d_pfR, R, (size_t)p->K * p->C * p->C * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_pfR = true;
+  return BTKB_OK;
+}
+
+int btkb_pf_get_noise_coherence(btkb_pipeline* p, double* R) {
+  int rc = pf_check(p, "btkb_pf_get_noise_coherence"); if (rc) return rc;
+  if (!R) return fail(BTKB_ERR_INVALID, "btkb_pf_get_noise_coherence: null argument");
+  if (!p->have_pfR) return fail(BTKB_ERR_STATE, "Construct/set first a noise coherence matrix");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(R, p->d_pfR, (size_t)p->K * p->C * p->C * sizeof(double2), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+int btkb_pf_set_diagonal_loading(btkb_pipeline* p, float mu) {
+  int rc = pf_check(p, "btkb_pf_set_diagonal_loading"); if (rc) return rc;
+  if (!p->have_pfR) return fail(BTKB_ERR_STATE, "Construct/set first a noise coherence matrix");  // postfilter.cc:631-633
+  CK(cudaSetDevice(p->cfg.device));
+  CK(launch_pf_diag_load(p->d_pfR, p->C, p->K, mu, p->stream));
+  return BTKB_OK;
+}
+
+int btkb_pf_divide_nondiagonal(btkb_pipeline* p, float mu) {
+  int rc = pf_check(p, "btkb_pf_divide_nondiagonal"); if (rc) return rc;
+  if (!p->have_pfR) return fail(BTKB_ERR_STATE, "Construct/set first a noise coherence matrix");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(launch_pf_divide_nondiag(p->d_pfR, p->C, p->K, mu, p->stream));
+  return BTKB_OK;
+}
+
 int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu) {
   if (!p) return fail(BTKB_ERR_INVALID, "btkb_calc_mvdr_weights: null argument");
   if (!p->have_R) return fail(BTKB_ERR_STATE, "Set a spatial spectral matrix before calling calc_mvdr_weights()");  // beamformer.cc:2352-2354
@@ -392,7 +458,7 @@ static int do_analysis(btkb_pipeline* p) {
 static PerBinArgs perbin_args(btkb_pipeline* p) {
   PerBinArgs a;
   memset(&a, 0, sizeof(a));
-  a.X = p->d_X; a.E = p->d_E; a.lengths = p->d_len; a.W = p->d_W; a.TA = p->d_TA;
+  a.X = p->d_X; a.E = p->d_E; a.lengths = p->d_len; a.W = p->d_W; a.TA = p->have_ta ? p->d_TA : nullptr;
   a.WL = p->have_wl ? p->d_WL : nullptr;
   a.Y = p->d_Y; a.PFW = p->d_PFW; a.UA = p->d_UA; a.stats_updates = p->d_upd;
   a.R = p->d_R; a.noise_mask = p->d_mask; a.noise_count = p->d_count;
@@ -414,11 +480,22 @@ static int do_beamformer(btkb_pipeline* p) {
   if (!narrow && !wide)
     return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the per-bin kernel is instantiated for 2, 4, 8 (register path) and 16, 32, 64 (lane-split path) channels (got " + std::to_string(p->C) + ")");
   if (wide && p->cfg.postfilter != BTKB_PF_NONE)
-    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the Zelinski post-filter is built for <= 8 channels (its C(C-1)/2 cross-spectral densities must fit the register file)");
+    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the post-filters are built for <= 8 channels (their C(C-1)/2 cross-spectral densities must fit the register file)");
   PerBinArgs a = perbin_args(p);
+  if (p->cfg.postfilter >= BTKB_PF_MCCOWAN) {
+    if (!p->have_pfR) return fail(BTKB_ERR_STATE, "McCowanPostFilter:  construct/set a noise coherence matrix");  // postfilter.cc:828-830
+    const bool lef = p->cfg.postfilter == BTKB_PF_LEFKIMMIATIS;
+    CK(launch_pf_prepare(p->d_pfR, p->d_pfInvR, p->d_pfQ, p->C, p->K, p->cfg.pf_threshold, p->cfg.pf_min_sv, lef ? 1 : 0, p->stream));
+    p->launches++;
+    if (lef) {  // Lambda uses arrayManifold() = the delay-and-sum manifold (postfilter.cc:984-987)
+      CK(launch_pf_lambda(p->d_pfInvR, p->have_ta ? p->d_TA : p->d_W, p->d_LAM, p->U, p->C, p->K, p->Gp, p->cfg.pf_type, p->stream));
+      p->launches++;
+    }
+    a.PFQ = p->d_pfQ; a.LAM = p->d_LAM; a.pf_fbin1 = p->cfg.pf_fbin1;
+  }
   if (narrow) CK(launch_perbin(a, p->stream)); else CK(launch_perbin_wide(a, p->stream));
   p->launches++;
-  p->have_Y = true;
+  p->have_Y = true; p->pf_applied = true;
   p->have_ua = (p->cfg.beamformer == BTKB_BF_GSC_LMS);
   return BTKB_OK;
 }
@@ -428,7 +505,8 @@ static int do_synthesis(btkb_pipeline* p) {
   if (!p->have_Y) return fail(BTKB_ERR_STATE, "btkb_run: no beamformer output to synthesise");
   CK(cudaMemsetAsync(p->d_stats, 0, (size_t)p->U * 3 * sizeof(double), p->stream));
   SynthesisArgs a{p->d_Y, p->d_len, p->d_g, p->d_time, p->d_stats, p->U, p->n, p->T, p->M, p->m, p->cfg.r, p->D, p->K, p->Gp, p->pdS, p->laN, p->pdA,
-                  p->nb, p->nb * p->D, p->cfg.synthesis_gain, p->d_tw};
+                  p->nb, p->nb * p->D, p->cfg.synthesis_gain, p->d_tw,
+                  (p->cfg.postfilter >= BTKB_PF_MCCOWAN && p->pf_applied) ? p->cfg.pf_min_frames + 1 : 0};
   CK(launch_synthesis(a, p->stream));
   p->launches++;
   p->have_time = true;
@@ -505,7 +583,7 @@ int btkb_set_subband(btkb_pipeline* p, int U, int T, const float* Y) {
       memcpy(&tmp[(size_t)t * p->Gp + (size_t)u * p->K], Y + 2 * (((size_t)u * T + t) * p->K), sizeof(float2) * p->K);
   CK(cudaMemcpyAsync(p->d_Y, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
   CK(cudaStreamSynchronize(p->stream));
-  p->have_Y = true; p->have_X = false; p->have_time = false; p->have_ua = false;
+  p->have_Y = true; p->have_X = false; p->have_time = false; p->have_ua = false; p->pf_applied = false;
   return BTKB_OK;
 }
 

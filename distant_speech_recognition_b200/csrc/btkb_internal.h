@@ -27,6 +27,8 @@ struct SynthesisArgs {
   float* out; double* stats;  // stats [U][3]: sum of squares accumulated into [u][0]
   int U, n, T, M, m, r, D, K, Gp, pdS, laN, pdA, nb, nb_stride, gain;
   const float2* twtab;   // exp(+2 pi i n / M), n < M (device)
+  int onesided;          // frames tau < onesided carry bins 0..M/2 only (upper half zero): the McCowan / Lefkimmiatis post-filters
+                         // leave vector_[M/2+1..M-1] untouched until frame_no_ >= min_frames (postfilter.cc:896-901)
 };
 
 struct LmsArgs {
@@ -51,6 +53,8 @@ struct PerBinArgs {
   int kind;           // BTKB_BF_*
   int normalize_weight;  // calc_gsc_output's w <- w / (||w|| C) (beamformer.cc:1230-1236)
   int pf_kind; float pf_alpha; int pf_type, pf_min_frames;
+  // McCowan / Lefkimmiatis constants (btkb_postfilter.cu): PFQ [NQ][K] per-bin pair factors, LAM [Gp] Lambda = d^H R^-1 d
+  const float2* PFQ; const float* LAM; int pf_fbin1;
   LmsArgs lms;
   float energy_threshold;
 };
@@ -80,6 +84,14 @@ cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const
 cudaError_t launch_ua_to_wa(const float2* UA, const float2* W, float2* WA, int U, int C, int K, int Gp, cudaStream_t st);
 cudaError_t launch_noise_mask(const float* E, const int* lengths, const double* labels, unsigned char* mask, int* count, int U, int T, int D, int laN, int pdA,
                               float samplerate, float thr, cudaStream_t st);
+
+// McCowan / Lefkimmiatis post-filter setup (btkb_postfilter.cu); Rpf / invR are [K][C][C] complex128, C <= 8
+cudaError_t launch_pf_diffuse(const double* mpos, double2* Rpf, int C, int M, int K, double samplerate, double sspeed, cudaStream_t st);
+cudaError_t launch_pf_diag_load(double2* Rpf, int C, int K, float mu, cudaStream_t st);
+cudaError_t launch_pf_divide_nondiag(double2* Rpf, int C, int K, float mu, cudaStream_t st);
+cudaError_t launch_pf_prepare(const double2* Rpf, double2* invR, float2* PFQ, int C, int K, float threshold, double min_sv, int want_inverse, cudaStream_t st);
+cudaError_t launch_pf_lambda(const double2* invR, const float2* TA, float* LAM, int U, int C, int K, int Gp, int pf_type, cudaStream_t st);
+inline int pf_num_consts(int C) { return C * (C - 1) + 2 * C; }  // q'[NP], rho'[C], q''[NP], rho''[C]
 
 __host__ __device__ inline int frames_of(int len, int D, int laN, int pdA) { return (len + D - 1) / D - laN + pdA; }
 

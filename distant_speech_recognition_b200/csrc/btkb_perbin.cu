@@ -125,6 +125,10 @@ struct TileRing {
   }
 };
 
+// bytes of dynamic shared memory the ring owns (slots + mbarriers, padded to 128 so what follows stays aligned)
+template <int C>
+__host__ __device__ constexpr size_t ring_bytes() { return ((sizeof(float2) * STAGES * FCH * C * TILE + sizeof(uint64_t) * 2 * STAGES + 64) + 127) / 128 * 128; }
+
 constexpr int MODE_STATIC = 0, MODE_LMS = 1;
 
 // FMA-only complex multiply-accumulate (4 FFMA each, no separate adds)
@@ -194,13 +198,27 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
   }
   // ---- Zelinski state: CSDs_ (beamformer.cc:874-887): upper triangle complex + real diagonal
   constexpr int NP = C * (C - 1) / 2;
-  float2 csd[PF ? (NP > 0 ? NP : 1) : 1];
+  float2 csd[(PF == 1) ? (NP > 0 ? NP : 1) : 1];
   float psd[PF ? C : 1];
   if (PF) {
+    if (PF == 1) {
 #pragma unroll
-    for (int i = 0; i < NP; i++) csd[i] = make_float2(0.f, 0.f);
+      for (int i = 0; i < NP; i++) csd[i] = make_float2(0.f, 0.f);
+    }
 #pragma unroll
     for (int c = 0; c < C; c++) psd[c] = 0.f;
+  }
+  // ---- McCowan / Lefkimmiatis state.  The per-pair CSD recursion phi_ij <- al phi_ij + (1-al) z_i conj(z_j) is linear, so
+  // the two pair sums the filters need, S' = sum q'_ij phi_ij and S'' = sum q''_ij phi_ij, obey the same recursion and are
+  // carried as two complex scalars; the bin's constants q', rho', q'', rho'' (btkb_postfilter.cu) sit in this thread's
+  // column of shared memory, [entry][TILE], read conflict-free every frame.
+  constexpr int NQ = (PF == 3) ? 2 * (NP + C) : (NP + C);
+  float2* pfc = reinterpret_cast<float2*>(smem_raw + ring_bytes<C>()) + threadIdx.x;
+  float2 S1 = make_float2(0.f, 0.f), S2 = make_float2(0.f, 0.f);
+  float lam_inv = 1.0f;
+  if (PF >= 2) {
+    for (int q = 0; q < NQ; q++) pfc[q * TILE] = __ldg(a.PFQ + (size_t)q * a.K + k);
+    if (PF == 3) lam_inv = (k < a.pf_fbin1) ? 1.0f : 1.0f / __ldg(a.LAM + g);
   }
 
   float e_next = 0.f;
@@ -263,7 +281,57 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
       Eavg = fmaf(Eavg, a.lms.beta, one_m_beta * energy);
     }
 
-    if (PF) {
+    if constexpr (PF >= 2) {
+      // McCowanPostFilter::post_filtering_ (postfilter.cc:826-885) / LefkimmiatisPostFilter::post_filtering_ (:1090-1160);
+      // alpha = 0 while frame_no_ <= 0, i.e. for the first two frames, as in Zelinski's filter
+      const float al = (t >= 2) ? a.pf_alpha : 0.f;
+      const float be = 1.0f - al;
+      float2 z[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) z[c] = cmulc(x[c], ta[c]);
+      float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+      int idx = 0;
+#pragma unroll
+      for (int i = 0; i < C - 1; i++)
+#pragma unroll
+        for (int j = i + 1; j < C; j++) {
+          const float2 zz = cmulc(z[i], z[j]);
+          cmac(a1, zz, pfc[idx * TILE]);
+          if (PF == 3) cmac(a2, zz, pfc[(NP + C + idx) * TILE]);
+          idx++;
+        }
+      const float2 s1 = (al > 0.f) ? make_float2(fmaf(al, S1.x, be * a1.x), fmaf(al, S1.y, be * a1.y)) : a1;
+      const float2 s2 = (al > 0.f) ? make_float2(fmaf(al, S2.x, be * a2.x), fmaf(al, S2.y, be * a2.y)) : a2;
+      float2 r1 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);
+      float den = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const float pz = fmaf(z[c].x, z[c].x, z[c].y * z[c].y);
+        const float ps = (al > 0.f) ? fmaf(al, psd[c], be * pz) : pz;
+        if (live) psd[c] = ps;
+        den += ps;
+        const float2 h1 = pfc[(NP + c) * TILE];
+        r1.x = fmaf(ps, h1.x, r1.x); r1.y = fmaf(ps, h1.y, r1.y);
+        if (PF == 3) { const float2 h2 = pfc[(2 * NP + C + c) * TILE]; r2.x = fmaf(ps, h2.x, r2.x); r2.y = fmaf(ps, h2.y, r2.y); }
+      }
+      if (live) { S1 = s1; S2 = s2; }
+      const float pn = 2.0f / ((float)C * ((float)C - 1.0f));
+      const float2 cs = make_float2(s1.x - r1.x, s1.y - r1.y);  // sum over pairs of (phi_ij - R' (phi_ii + phi_jj)/2) / (1 - R')
+      const float phi_ss = pn * ((a.pf_type & 1) ? cs.x : sqrtf(fmaf(cs.x, cs.x, cs.y * cs.y)));
+      float Wf;
+      if (PF == 2) {
+        Wf = phi_ss / (den / (float)C);
+      } else {
+        const float2 cv = make_float2(r2.x - s2.x, r2.y - s2.y);  // sum over pairs of ((phi_ii + phi_jj)/2 - phi_ij) / (1 - R'')
+        const float phi_vv = pn * ((a.pf_type & 1) ? cv.x : sqrtf(fmaf(cv.x, cv.x, cv.y * cv.y)));
+        Wf = phi_ss / fmaf(phi_vv, lam_inv, phi_ss);
+      }
+      Wf = (Wf > 1.0f) ? 1.0f : Wf;
+      Wf = (Wf < 1.0e-4f) ? 1.0e-4f : Wf;
+      if (!(Wf == Wf)) Wf = 1.0e-4f;  // all-zero snapshot: 0/0 in the reference; keep the output finite
+      if (t - 1 >= a.pf_min_frames) { y.x *= Wf; y.y *= Wf; }
+      if (a.PFW != nullptr && valid) a.PFW[(size_t)t * a.Gp + g] = Wf;
+    } else if constexpr (PF == 1) {
       // ZelinskiFilter_f (postfilter.cc:57-140); alpha = 0 for the first two frames (postfilter.cc:460-463)
       const float al = (t >= 2) ? a.pf_alpha : 0.f;
       float2 z[C];
@@ -404,7 +472,7 @@ __global__ void __launch_bounds__(TILE) k_spectral_recursion(const __grid_consta
 }
 
 template <int C>
-static size_t ring_smem() { return sizeof(float2) * STAGES * FCH * C * TILE + sizeof(uint64_t) * 2 * STAGES + 64; }
+static size_t ring_smem() { return ring_bytes<C>(); }
 
 // Tensor map of X viewed as a 2-D float tensor [T*C rows][2*Gp floats]; box = [FCH*C rows][2*TILE floats].
 static cudaError_t make_tensor_map(CUtensorMap* tm, const PerBinArgs& a, int C) {
@@ -435,17 +503,21 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
   CUtensorMap tm;
   { cudaError_t e = make_tensor_map(&tm, a, C); if (e != cudaSuccess) return e; }
   const bool lms = a.kind == BTKB_BF_GSC_LMS;
-  const bool pf = a.pf_kind == BTKB_PF_ZELINSKI;
+  const int pf = a.pf_kind;
+  constexpr int NPAIR = C * (C - 1) / 2;
 #define BTKB_LAUNCH(MODE_, PF_)                                                                  \
   do {                                                                                           \
     auto kern = k_perbin<C, MODE_, PF_>;                                                         \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    const size_t sm = smem + ((PF_) == 3 ? 2 * (NPAIR + C) : (PF_) == 2 ? (NPAIR + C) : 0) * TILE * sizeof(float2); \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
     if (e != cudaSuccess) return e;                                                              \
-    kern<<<grid, TILE, smem, st>>>(tm, a);                                                       \
+    kern<<<grid, TILE, sm, st>>>(tm, a);                                                         \
     return cudaGetLastError();                                                                   \
   } while (0)
-  if (lms) { if (pf) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_LMS, 0); }
-  if (pf) BTKB_LAUNCH(MODE_STATIC, 1);
+  if (lms) { if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_LMS, 0); }
+  if (pf == BTKB_PF_ZELINSKI) BTKB_LAUNCH(MODE_STATIC, 1);
+  if (pf == BTKB_PF_MCCOWAN) { if (!a.PFQ) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 2); }
+  if (pf == BTKB_PF_LEFKIMMIATIS) { if (!a.PFQ || !a.LAM) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 3); }
   BTKB_LAUNCH(MODE_STATIC, 0);
 #undef BTKB_LAUNCH
 }

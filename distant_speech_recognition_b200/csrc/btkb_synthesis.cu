@@ -64,6 +64,10 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a
         if (vb) yb = __ldg(a.Y + (size_t)tb * a.Gp + (size_t)u * K + k);
         if (edge) { ya.y = 0.f; yb.y = 0.f; }
         if (cj) { ya.y = -ya.y; yb.y = -yb.y; }
+        if (a.onesided > 0 && !edge) {  // Re IFFT of a spectrum whose upper half is zero = half the Hermitian one (DC, Nyquist whole)
+          if (ta < a.onesided) { ya.x *= 0.5f; ya.y *= 0.5f; }
+          if (tb < a.onesided) { yb.x *= 0.5f; yb.y *= 0.5f; }
+        }
         v[b * R0 + r] = make_float2(ya.x - yb.y, ya.y + yb.x);  // ya + i yb
       }
     float2* Z = fft_run<M, -1>(v, bufA, bufB, tg, tw, [] { __syncthreads(); });
@@ -201,6 +205,13 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
         }
         if (edge) { ya.y = 0.f; yb.y = 0.f; yc.y = 0.f; yd.y = 0.f; }
         if (cj) { ya.y = -ya.y; yb.y = -yb.y; yc.y = -yc.y; yd.y = -yd.y; }
+        if (a.onesided > 0 && !edge) {  // see k_synthesis_generic
+          const int tq = tau0 + 4 * qd;
+          if (tq + 0 < a.onesided) { ya.x *= 0.5f; ya.y *= 0.5f; }
+          if (tq + 1 < a.onesided) { yb.x *= 0.5f; yb.y *= 0.5f; }
+          if (tq + 2 < a.onesided) { yc.x *= 0.5f; yc.y *= 0.5f; }
+          if (tq + 3 < a.onesided) { yd.x *= 0.5f; yd.y *= 0.5f; }
+        }
         v0[b * R0 + r] = make_float2(ya.x - yb.y, ya.y + yb.x);
         v1[b * R0 + r] = make_float2(yc.x - yd.y, yc.y + yd.x);
       }

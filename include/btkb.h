@@ -48,6 +48,8 @@ extern "C" {
 /* post-filter kinds */
 #define BTKB_PF_NONE 0
 #define BTKB_PF_ZELINSKI 1 /* ZelinskiPostFilter (postfilter.cc:57-219, 424-491); type bits: 1 = Re, 2 = |.| */
+#define BTKB_PF_MCCOWAN 2  /* McCowanPostFilter: noise-coherence-compensated Wiener gain (postfilter.cc:496-934) */
+#define BTKB_PF_LEFKIMMIATIS 3 /* LefkimmiatisPostFilter: McCowan's clean PSD + noise PSD / (d^H R^-1 d) (postfilter.cc:935-1200) */
 
 typedef struct btkb_pipeline btkb_pipeline;
 
@@ -75,6 +77,9 @@ typedef struct btkb_config {
   int keep_snapshots;          /* 1: keep the analysis output X resident so btkb_fetch_snapshots works (always true today) */
   int synthesis_gain;          /* OverSampledDFTSynthesisBank gain_factor (modulated.cc:608-609); default 1 */
   int normalize_weight;        /* SubbandGSC::normalize_weight(flag): w <- w / (||w|| C) for bins >= 1 (beamformer.cc:1230-1236) */
+  float pf_threshold;          /* McCowan / Lefkimmiatis: clip of the noise coherence R_ij (default 0.99, postfilter.h) */
+  double pf_min_sv;            /* Lefkimmiatis: singular-value floor of the coherence pseudo-inverse (default 1e-8) */
+  int pf_fbin1;                /* Lefkimmiatis: first bin that divides the noise PSD by Lambda = d^H R^-1 d (default 0) */
 } btkb_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */
@@ -102,6 +107,16 @@ int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa);
 int btkb_set_noise_covariance(btkb_pipeline* p, int U, const float* R);
 /* diffuse-noise coherence from microphone positions [C][3] (mm) (set_diffuse_noise_model, beamformer.cc:2442-2509) */
 int btkb_set_diffuse_noise_model(btkb_pipeline* p, int U, const double* mpos, float sspeed);
+/* ---- noise coherence of the McCowan / Lefkimmiatis post-filters: one [K][C][C] matrix set per pipeline (postfilter.h R_) */
+/* McCowanPostFilter::set_diffuse_noise_model(micPositions [C][3], sampleRate, sspeed) (postfilter.cc:562-627) */
+int btkb_pf_set_diffuse_noise_model(btkb_pipeline* p, const double* mpos, double samplerate, double sspeed);
+/* McCowanPostFilter::set_noise_spatial_spectral_matrix for every bin: R [K][C][C] complex128 row-major (postfilter.cc:541-560) */
+int btkb_pf_set_noise_coherence(btkb_pipeline* p, const double* R);
+int btkb_pf_get_noise_coherence(btkb_pipeline* p, double* R);  /* noise_spatial_spectral_matrix(fbinX), all bins */
+/* set_all_diagonal_loading(diagonalWeight): ADDS (float)mu to every diagonal, cumulatively like the reference (postfilter.cc:629-642) */
+int btkb_pf_set_diagonal_loading(btkb_pipeline* p, float mu);
+/* divide_all_nondiagonal_elements(mu): off-diagonals /= (1 + mu) (postfilter.cc:662-680) */
+int btkb_pf_divide_nondiagonal(btkb_pipeline* p, float mu);
 /* R += mu I (set_all_diagonal_loading, beamformer.cc:2511-2523) then w = R^-H d / (C d^H R^-1 d), w[0] = 1
  * (calc_mvdr_weights, beamformer.cc:2350-2402).  Uses the covariance from btkb_set_noise_covariance,
  * btkb_set_diffuse_noise_model or btkb_accumulate_covariance. */
@@ -152,7 +167,7 @@ int btkb_fetch_stats(btkb_pipeline* p, double* out);
 int btkb_get_weights(btkb_pipeline* p, float* out);            /* [U][K][C] complex64: wq or wmvdr */
 int btkb_get_active_weights(btkb_pipeline* p, float* out);     /* [U][K][C-1] complex64 (NLMS: waH of pybeamformer.py) */
 int btkb_get_covariance(btkb_pipeline* p, float* out);         /* [U][K][C][C] complex64 */
-int btkb_get_postfilter_weights(btkb_pipeline* p, float* out); /* [U][T][K] float32 Zelinski gains (wp1_) */
+int btkb_get_postfilter_weights(btkb_pipeline* p, float* out); /* [U][T][K] float32 post-filter gains (wp1_) */
 
 /* ---- measurement -------------------------------------------------------------------------------------------- */
 /* device time (ms, CUDA events on the pipeline stream) of the last run: total and per kernel

@@ -136,6 +136,43 @@ def test_mvdr_superdirective_golden(protos):
     assert rel_l2(Y[:, :K], g["Y"]) < 1e-12
 
 
+def _coherence(M, mpos, load):
+    R = restate.diffuse_noise_model(M, mpos, FS)
+    return R + float(np.float32(load)) * np.eye(R.shape[1])
+
+
+def test_mccowan_postfilter_golden(protos):
+    """McCowanPostFilter behind the super-directive MVDR (postfilter.cc:496-934): restatement vs the reference's output."""
+    g = load_golden("mccowan_c4_m256"); h, gg = protos[256]
+    M = 256; K = 129
+    X = _X(g["x"], h, M)
+    wq = restate.calc_mainlobe(M, 4, FS, g["delays"])
+    Ybf = restate.subband_mvdr(X, g["w"])
+    Ya, Wa = restate.mccowan_postfilter(Ybf, X, wq, _coherence(M, g["mpos"], 0.01), 0.7, 2, 0, 0.99)
+    assert rel_l2(Ya[:, :K], g["Ya"]) < 1e-12
+    assert np.array_equal(Ya[:2, K:] == 0, g["upper_a"] == 0)  # frame 0 leaves the upper half of vector_ at zero
+    assert rel_l2(restate.synthesis(Ya, gg, M, 4, 1)[: len(g["timea"])], g["timea"]) < 1e-6
+    Yb, _ = restate.mccowan_postfilter(Ybf, X, wq, _coherence(M, g["mpos"], 0.0), 0.6, 1, 3, 0.9)
+    assert rel_l2(Yb[:, :K], g["Yb"]) < 1e-12
+    assert np.array_equal(Yb[:5, K:] == 0, g["upper_b"] == 0)
+    assert Wa.min() >= 1e-4 and Wa.max() <= 1.0
+
+
+def test_lefkimmiatis_postfilter_golden(protos):
+    """LefkimmiatisPostFilter behind delay-and-sum (postfilter.cc:935-1200); the coherence inverse is the reference's
+    float LINPACK SVD, so agreement is at single precision."""
+    g = load_golden("lefkimmiatis_c8_m512"); h, gg = protos[512]
+    M = 512; K = 257
+    X = _X(g["x"], h, M)
+    wq = restate.calc_mainlobe(M, 8, FS, g["delays"])
+    Ybf = restate.subband_ds(X, wq)
+    Ya, _ = restate.lefkimmiatis_postfilter(Ybf, X, wq, _coherence(M, g["mpos"], 0.1), 0.8, 2, 0, 0.99, 1e-4, 100, single=False)
+    assert rel_l2(Ya[:, :K], g["Ya"]) < 2e-6
+    Yb, _ = restate.lefkimmiatis_postfilter(Ybf, X, wq, _coherence(M, g["mpos"], 0.01), 0.6, 1, 2, 0.99, 1e-8, 0, single=False)
+    assert rel_l2(Yb[:, :K], g["Yb"]) < 2e-5
+    assert rel_l2(restate.synthesis(Yb, gg, M, 4, 1)[: len(g["timeb"])], g["timeb"]) < 2e-5
+
+
 def test_pseudoinverse_golden():
     g = load_golden("pseudoinverse")
     for A, inv in zip(g["A"], g["inv"]):
@@ -167,6 +204,10 @@ def test_compiled_reference_matches_its_goldens(protos):
     g = load_golden("gsclms_c8_m512"); h, gg = protos[512]
     res = ref.beamform(g["x"], h, gg, g["delays"], 512, 4, 1, bf_kind=ref.BF_GSC_LMS, lms=dict(min_frames=int(g["min_frames"])))
     assert np.array_equal(res["Y"][:, :257], g["Y"]) and np.array_equal(res["time"], g["time"])
+    g = load_golden("mccowan_c4_m256"); h, gg = protos[256]
+    res = ref.beamform(g["x"], h, gg, g["delays"], 256, 4, 1, bf_kind=ref.BF_MVDR_SD, mpos=g["mpos"], mvdr_mu=0.01,
+                       pf=dict(kind="mccowan", alpha=0.7, type=2, diag_load=0.01))
+    assert np.array_equal(res["Y"][:, :129], g["Ya"]) and np.array_equal(res["time"], g["timea"])
     g = load_golden("ds_c2_m256"); h, gg = protos[256]
     res = ref.beamform(g["x"], h, gg, g["delays"], 256, 4, 1, bf_kind=ref.BF_DS)
     assert np.array_equal(res["Y"][:, :129], g["Y"]) and np.array_equal(res["time"], g["time"])

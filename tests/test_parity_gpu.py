@@ -153,6 +153,83 @@ def test_mvdr_superdirective_zelinski1_golden(capi, protos):
     assert rel_l2(p.fetch_time()[0], g["time"]) < TOL
 
 
+def test_mccowan_postfilter_golden(capi, protos):
+    """SubbandMVDR (super-directive) + McCowanPostFilter as test_online_beamforming.py:137-143 wires them, vs the reference's output."""
+    g = load_golden("mccowan_c4_m256")
+    x = g["x"]
+    for tag, kw, load in (("a", dict(pf_alpha=0.7, pf_type=2), 0.01), ("b", dict(pf_alpha=0.6, pf_type=1, pf_min_frames=3, pf_threshold=0.9), 0.0)):
+        p = _pipe(capi, 4, 256, protos, n=x.shape[1], beamformer=capi.BF_MVDR, postfilter=capi.PF_MCCOWAN, **kw)
+        p.set_delays(g["delays"][None])
+        p.set_diffuse_noise_model(1, g["mpos"])
+        p.calc_mvdr_weights(float(g["mu"]))
+        p.submit(x[None])
+        with pytest.raises(capi.BtkbError) as ei:  # postfilter.cc:828-830
+            p.run(True)
+        assert ei.value.code == capi.ERR_STATE and "noise coherence" in str(ei.value)
+        p.pf_set_diffuse_noise_model(g["mpos"], FS)
+        p.pf_set_diagonal_loading(load)
+        R = p.pf_get_noise_coherence()
+        assert abs(R[0, 0, 0].real - (1.0 + float(np.float32(load)))) < 1e-12 and abs(R[0, 0, 1] - 1.0) < 1e-12
+        p.run(True)
+        assert rel_l2(p.fetch_subband()[0], g["Y" + tag]) < TOL, tag
+        assert rel_l2(p.fetch_time()[0], g["time" + tag]) < TOL, tag
+        W = p.get_postfilter_weights()[0]
+        assert W.min() >= 1e-4 - 1e-9 and W.max() <= 1.0
+        p.close()
+
+
+def test_lefkimmiatis_postfilter_golden(capi, protos):
+    """SubbandDS + LefkimmiatisPostFilter (test_online_beamforming.py:144-151; confs/sd_and_lefkimmiatis.json parameters)."""
+    g = load_golden("lefkimmiatis_c8_m512")
+    x = g["x"]
+    for tag, kw, load in (("a", dict(pf_alpha=0.8, pf_type=2, pf_min_sv=1e-4, pf_fbin1=100), 0.1),
+                          ("b", dict(pf_alpha=0.6, pf_type=1, pf_min_frames=2, pf_min_sv=1e-8, pf_fbin1=0), 0.01)):
+        p = _pipe(capi, 8, 512, protos, n=x.shape[1], beamformer=capi.BF_DS, postfilter=capi.PF_LEFKIMMIATIS, **kw)
+        p.set_delays(g["delays"][None])
+        p.pf_set_diffuse_noise_model(g["mpos"], FS)
+        p.pf_set_diagonal_loading(load)
+        p.submit(x[None])
+        p.run(True)
+        assert rel_l2(p.fetch_subband()[0], g["Y" + tag]) < TOL, tag
+        assert rel_l2(p.fetch_time()[0], g["time" + tag]) < TOL, tag
+        p.close()
+
+
+def test_postfilters_batched_match_oracle(capi, protos):
+    """Batch of ragged utterances through GSC + McCowan / Lefkimmiatis vs the fp64 restatement, utterance by utterance."""
+    from oracle import restate
+    from distant_speech_recognition_b200 import synthetic
+    M, C, U, n = 256, 4, 3, 6000
+    K = M // 2 + 1
+    h, gq = protos[M]
+    X, dl = synthetic.make_batch(U, C, n, first=20)
+    lengths = np.array([n, n - 700, n - 2500], np.int32)
+    _, _, mpos, _ = synthetic.make_utterance(0, C, 16)
+    Rc = restate.diffuse_noise_model(M, mpos, FS) + float(np.float32(0.05)) * np.eye(C)
+    for kind, name in ((capi.PF_MCCOWAN, "mccowan"), (capi.PF_LEFKIMMIATIS, "lefkimmiatis")):
+        p = _pipe(capi, C, M, protos, U=U, n=n, beamformer=capi.BF_DS, postfilter=kind, pf_alpha=0.65, pf_type=2, pf_min_frames=1, pf_fbin1=10)
+        p.set_delays(dl)
+        p.pf_set_diffuse_noise_model(mpos, FS)
+        p.pf_set_diagonal_loading(0.05)
+        p.submit(X, lengths)
+        p.run(True)
+        Y = p.fetch_subband(); tm = p.fetch_time()
+        for u in range(U):
+            xu = X[u][:, : lengths[u]]
+            Xs = np.stack([restate.analysis(xu[c], h, M, 4, 1) for c in range(C)], axis=1)
+            wq = restate.calc_mainlobe(M, C, FS, dl[u])
+            Ybf = restate.subband_ds(Xs, wq)
+            if name == "mccowan":
+                Yo, _ = restate.mccowan_postfilter(Ybf, Xs, wq, Rc, 0.65, 2, 1, 0.99)
+            else:
+                Yo, _ = restate.lefkimmiatis_postfilter(Ybf, Xs, wq, Rc, 0.65, 2, 1, 0.99, 1e-8, 10, single=False)
+            T = Yo.shape[0]
+            assert rel_l2(Y[u][:T], Yo[:, :K]) < TOL, (name, u)
+            to = restate.synthesis(Yo, gq, M, 4, 1)
+            assert rel_l2(tm[u][: len(to)], to) < TOL, (name, u)
+        p.close()
+
+
 def test_batch_ragged_lengths_match_single_runs(capi, protos):
     """Utterances are independent units: a ragged batch must reproduce each utterance run alone (and the oracle)."""
     from distant_speech_recognition_b200 import synthetic
