@@ -1,2 +1,2 @@
-"""btk20.postfilter (postfilter/postfilter.i:46-90)."""
-from .._btk20host import ZelinskiPostFilterPtr  # noqa: F401
+"""btk20.postfilter (postfilter/postfilter.i:46-188)."""
+from .._btk20host import ZelinskiPostFilterPtr, McCowanPostFilterPtr, LefkimmiatisPostFilterPtr  # noqa: F401

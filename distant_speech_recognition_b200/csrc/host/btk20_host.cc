@@ -164,6 +164,8 @@ void SubbandBeamformer::reset() {
 bool SubbandBeamformer::realized_with(const PostFilterConfig& pf, const SynthesisConfig& syn) const {
   if (!realized_) return false;
   if (pf.enabled != pf_used_.enabled || (pf.enabled && (pf.alpha != pf_used_.alpha || pf.type != pf_used_.type || pf.min_frames != pf_used_.min_frames))) return false;
+  if (pf.enabled && (pf.kind != pf_used_.kind || pf.threshold != pf_used_.threshold || pf.min_sv != pf_used_.min_sv || pf.fbin1 != pf_used_.fbin1 ||
+                     pf.coherence != pf_used_.coherence || pf.coherence_version != pf_used_.coherence_version)) return false;
   if (syn.enabled && !syn_used_.enabled) return false;
   return true;
 }
@@ -173,7 +175,8 @@ void SubbandBeamformer::ensure_pipeline_(const PostFilterConfig& pf, const Synth
   btkb_config c; btkb_default_config(&c);
   c.channels = (int)channels_.size(); c.fft_len = (int)fftLen_; c.m = (int)a0->m(); c.r = (int)a0->r(); c.delay_compensation_type = (int)a0->dct();
   c.samplerate = (float)samplerate_; c.beamformer = kind_;
-  c.postfilter = pf.enabled ? BTKB_PF_ZELINSKI : BTKB_PF_NONE; c.pf_alpha = (float)pf.alpha; c.pf_type = pf.type; c.pf_min_frames = pf.min_frames;
+  c.postfilter = pf.enabled ? pf.kind : BTKB_PF_NONE; c.pf_alpha = (float)pf.alpha; c.pf_type = pf.type; c.pf_min_frames = pf.min_frames;
+  c.pf_threshold = pf.threshold; c.pf_min_sv = pf.min_sv; c.pf_fbin1 = (int)pf.fbin1;
   c.lms.beta = (float)lms_.beta; c.lms.gamma = (float)lms_.gamma; c.lms.init_diagonal_load = (float)lms_.init_diagonal_load;
   c.lms.regularization_param = (float)lms_.regularization_param; c.lms.energy_floor = (float)lms_.energy_floor; c.lms.sil_thresh = (float)lms_.sil_thresh;
   c.lms.max_wa_l2norm = (float)lms_.max_wa_l2norm; c.lms.min_frames = lms_.min_frames; c.lms.slowdown_after = lms_.slowdown_after;
@@ -202,6 +205,11 @@ void SubbandBeamformer::run_graph(const PostFilterConfig& pf, const SynthesisCon
   if (syn.enabled && (syn.M != fftLen_)) throw jdimension_error("synthesis bank: inconsistent FFT length (%d vs. %d)", syn.M, fftLen_);
   ensure_pipeline_(pf, syn, n);
   configure_weights_(pipe_);
+  if (pf.enabled && pf.kind != BTKB_PF_ZELINSKI) {
+    if (!pf.coherence) throw j_error("McCowanPostFilter:  construct/set a noise coherence matrix\n");  // postfilter.cc:828-830
+    if (pf.coherence->chanN() != C) throw jdimension_error("noise coherence matrix is %d x %d but the beamformer has %d channels\n", pf.coherence->chanN(), pf.coherence->chanN(), C);
+    pf.coherence->push_coherence(pipe_);
+  }
   std::vector<float> x((size_t)C * n);
   for (unsigned c = 0; c < C; c++) std::memcpy(&x[(size_t)c * n], srcs[c]->samples().data(), sizeof(float) * n);
   ck(btkb_submit(pipe_, x.data(), 1, (int)n, nullptr));
@@ -402,9 +410,92 @@ const cplx* ZelinskiPostFilter::next(int frame_no) {  // postfilter.cc:424-491
   const unsigned K = fftLen_ / 2 + 1;
   const std::complex<float>* y = &bf_->Y()[(size_t)frame_no_ * K];
   for (unsigned k = 0; k < K; k++) vector_[k] = cplx(y[k].real(), y[k].imag());
-  for (unsigned k = 1; k < fftLen_ / 2; k++) vector_[fftLen_ - k] = std::conj(vector_[k]);
+  if (frame_no_ < onesided_frames_()) { for (unsigned k = K; k < fftLen_; k++) vector_[k] = cplx(0, 0); }
+  else for (unsigned k = 1; k < fftLen_ / 2; k++) vector_[fftLen_ - k] = std::conj(vector_[k]);
   return vector_.data();
 }
+
+// ---- McCowan / Lefkimmiatis
+McCowanPostFilter::McCowanPostFilter(const VectorComplexFeatureStreamPtr& output, unsigned fftLen, double alpha, int type, int min_frames, float threshold,
+                                     const std::string& nm)
+    : ZelinskiPostFilter(output, fftLen, alpha, type, min_frames, nm), kind_(BTKB_PF_MCCOWAN), threshold_(threshold) {}
+McCowanPostFilter::~McCowanPostFilter() { if (store_) btkb_destroy(store_); }
+void McCowanPostFilter::ensure_store_(unsigned C) {
+  if (store_ && chanN_ == C) return;
+  if (store_) { btkb_destroy(store_); store_ = nullptr; }
+  btkb_config c; btkb_default_config(&c);
+  c.channels = (int)C; c.fft_len = (int)fftLen_; c.postfilter = BTKB_PF_MCCOWAN; c.max_utterances = 1; c.max_samples = (int)fftLen_;
+  ck(btkb_create(&c, &store_));
+  chanN_ = C; haveR_ = false;
+}
+void McCowanPostFilter::require_R_() const { if (!store_ || !haveR_) throw j_error("Construct/set first a noise coherence matrix\n"); }  // postfilter.cc:631-633
+std::vector<cplx> McCowanPostFilter::get_all_() const {
+  std::vector<cplx> R((size_t)(fftLen_ / 2 + 1) * chanN_ * chanN_);
+  ck(btkb_pf_get_noise_coherence(store_, reinterpret_cast<double*>(R.data())));
+  return R;
+}
+void McCowanPostFilter::set_all_(const std::vector<cplx>& R) {
+  ck(btkb_pf_set_noise_coherence(store_, reinterpret_cast<const double*>(R.data())));
+  haveR_ = true; version_++;
+}
+std::vector<cplx> McCowanPostFilter::noise_spatial_spectral_matrix(unsigned fbinX) {
+  require_R_();
+  if (fbinX > fftLen_ / 2) throw jindex_error("frequency bin %d out of range", fbinX);
+  const std::vector<cplx> R = get_all_();
+  const size_t n = (size_t)chanN_ * chanN_;
+  return std::vector<cplx>(R.begin() + fbinX * n, R.begin() + (fbinX + 1) * n);
+}
+bool McCowanPostFilter::set_noise_spatial_spectral_matrix(unsigned fbinX, const std::vector<cplx>& Rnn, unsigned rows, unsigned cols) {
+  if (rows != cols) { fprintf(stderr, "The noise coherence matrix should be the square matrix\n"); return false; }  // postfilter.cc:543-546
+  if (fbinX > fftLen_ / 2) throw jindex_error("frequency bin %d out of range", fbinX);
+  const bool fresh = !(store_ && chanN_ == rows && haveR_);
+  ensure_store_(rows);
+  const size_t n = (size_t)rows * rows;
+  std::vector<cplx> R = fresh ? std::vector<cplx>((size_t)(fftLen_ / 2 + 1) * n, cplx(0, 0)) : get_all_();
+  std::copy(Rnn.begin(), Rnn.begin() + n, R.begin() + fbinX * n);
+  set_all_(R);
+  return true;
+}
+bool McCowanPostFilter::set_diffuse_noise_model(const std::vector<double>& mpos, unsigned rows, unsigned cols, double sampleRate, double sspeed) {
+  if (cols < 3) { fprintf(stderr, "The microphone positions should be described in the three dimensions\n"); return false; }  // postfilter.cc:567-570
+  ensure_store_(rows);
+  std::vector<double> mp((size_t)rows * 3);
+  for (unsigned c = 0; c < rows; c++) for (unsigned j = 0; j < 3; j++) mp[c * 3 + j] = mpos[(size_t)c * cols + j];
+  ck(btkb_pf_set_diffuse_noise_model(store_, mp.data(), sampleRate, sspeed));
+  haveR_ = true; version_++;
+  return true;
+}
+void McCowanPostFilter::set_all_diagonal_loading(float w) { require_R_(); ck(btkb_pf_set_diagonal_loading(store_, w)); version_++; }
+void McCowanPostFilter::divide_all_nondiagonal_elements(float mu) { require_R_(); ck(btkb_pf_divide_nondiagonal(store_, mu)); version_++; }
+void McCowanPostFilter::set_diagonal_looading(unsigned fbinX, float w) {  // postfilter.cc:644-655
+  require_R_();
+  std::vector<cplx> R = get_all_();
+  const size_t n = (size_t)chanN_ * chanN_;
+  for (unsigned c = 0; c < chanN_; c++) R[fbinX * n + (size_t)c * chanN_ + c] += (double)w;
+  set_all_(R);
+}
+void McCowanPostFilter::divide_nondiagonal_elements(unsigned fbinX, float mu) {  // postfilter.cc:669-680
+  require_R_();
+  std::vector<cplx> R = get_all_();
+  const size_t n = (size_t)chanN_ * chanN_;
+  for (unsigned i = 0; i < chanN_; i++) for (unsigned j = 0; j < chanN_; j++) if (i != j) R[fbinX * n + (size_t)i * chanN_ + j] /= (1.0 + mu);
+  set_all_(R);
+}
+PostFilterConfig McCowanPostFilter::config() const {
+  PostFilterConfig c = ZelinskiPostFilter::config();
+  c.kind = kind_; c.threshold = threshold_; c.min_sv = min_sv_; c.fbin1 = fbin1_;
+  c.coherence = haveR_ ? this : nullptr; c.coherence_version = version_;
+  return c;
+}
+void McCowanPostFilter::push_coherence(btkb_pipeline* dst) const {
+  const std::vector<cplx> R = get_all_();
+  ck(btkb_pf_set_noise_coherence(dst, reinterpret_cast<const double*>(R.data())));
+}
+LefkimmiatisPostFilter::LefkimmiatisPostFilter(const VectorComplexFeatureStreamPtr& output, unsigned fftLen, double minSV, unsigned fbinX1, double alpha, int type,
+                                               int min_frames, float threshold, const std::string& nm)
+    : McCowanPostFilter(output, fftLen, alpha, type, min_frames, threshold, nm) { kind_ = BTKB_PF_LEFKIMMIATIS; min_sv_ = minSV; fbin1_ = fbinX1; }
+void LefkimmiatisPostFilter::calc_inverse_noise_spatial_spectral_matrix() { require_R_(); }
+
 std::vector<cplx> ZelinskiPostFilter::postfilter_weights() {
   std::vector<cplx> w(fftLen_, cplx(0, 0));
   if (!bf_ || frame_no_ < 0 || bf_->pf_weights().empty()) return w;

@@ -151,7 +151,13 @@ struct LmsConfig {  // lib/pybeamformer.py:597-607 defaults (= unit_test/confs/g
   double beta = 0.97, gamma = 0.01, init_diagonal_load = 1.0e6, regularization_param = 1.0e-4, energy_floor = 90, sil_thresh = 1.0e8, max_wa_l2norm = 100.0;
   int min_frames = 128, slowdown_after = 4096;
 };
-struct PostFilterConfig { bool enabled = false; double alpha = 0.6; int type = 2; int min_frames = 0; };
+class McCowanPostFilter;
+struct PostFilterConfig {
+  bool enabled = false; double alpha = 0.6; int type = 2; int min_frames = 0;
+  int kind = 1;                              // BTKB_PF_ZELINSKI / MCCOWAN / LEFKIMMIATIS
+  float threshold = 0.99f; double min_sv = 1.0e-8; unsigned fbin1 = 0;
+  const McCowanPostFilter* coherence = nullptr; unsigned long coherence_version = 0;  // owner of the noise coherence R_
+};
 struct SynthesisConfig { bool enabled = false; std::vector<double> prototype; unsigned M = 0, m = 0, r = 0, dct = 0; int gain = 1; };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -275,13 +281,51 @@ class ZelinskiPostFilter : public VectorComplexFeatureStream {
   void set_beamformer(const SubbandDSPtr& bf) { bf_ = bf; }
   std::vector<cplx> postfilter_weights();
   const SubbandDSPtr& beamformer() const { return bf_; }
-  PostFilterConfig config() const { PostFilterConfig c; c.enabled = true; c.alpha = alpha_; c.type = type_; c.min_frames = min_frames_; return c; }
+  virtual PostFilterConfig config() const { PostFilterConfig c; c.enabled = true; c.alpha = alpha_; c.type = type_; c.min_frames = min_frames_; return c; }
   const VectorComplexFeatureStreamPtr& source() const { return samp_; }
- private:
+ protected:
+  virtual int onesided_frames_() const { return 0; }  // frames whose upper half-spectrum the reference leaves untouched
   unsigned fftLen_; VectorComplexFeatureStreamPtr samp_; double alpha_; int type_, min_frames_;
   SubbandDSPtr bf_;
 };
 typedef std::shared_ptr<ZelinskiPostFilter> ZelinskiPostFilterPtr;
+
+// McCowanPostFilter (postfilter.h / postfilter.cc:496-934).  The noise coherence R_[fbinX] lives on the device in a small
+// pipeline of its own, so every setter below is the corresponding C-ABI call; the beamformer's pipeline receives a copy
+// when the graph runs.
+class McCowanPostFilter : public ZelinskiPostFilter {
+ public:
+  McCowanPostFilter(const VectorComplexFeatureStreamPtr& output, unsigned fftLen, double alpha = 0.6, int type = 2, int min_frames = 0, float threshold = 0.99f,
+                    const std::string& nm = "McCowanPostFilterPtr");
+  ~McCowanPostFilter();
+  std::vector<cplx> noise_spatial_spectral_matrix(unsigned fbinX);                        // [C][C] row-major
+  bool set_noise_spatial_spectral_matrix(unsigned fbinX, const std::vector<cplx>& Rnn, unsigned rows, unsigned cols);
+  bool set_diffuse_noise_model(const std::vector<double>& mpos, unsigned rows, unsigned cols, double sampleRate, double sspeed = 343740.0);
+  void set_all_diagonal_loading(float diagonalWeight);
+  void set_diagonal_looading(unsigned fbinX, float diagonalWeight);
+  void divide_all_nondiagonal_elements(float mu);
+  void divide_nondiagonal_elements(unsigned fbinX, float mu);
+  PostFilterConfig config() const override;
+  void push_coherence(btkb_pipeline* dst) const;   // copy R_ into the beamformer's pipeline
+  unsigned chanN() const { return chanN_; }
+ protected:
+  int onesided_frames_() const override { return min_frames_ + 1; }  // postfilter.cc:896-901
+  void ensure_store_(unsigned C);
+  void require_R_() const;
+  std::vector<cplx> get_all_() const; void set_all_(const std::vector<cplx>& R);
+  int kind_; float threshold_; double min_sv_ = 1.0e-8; unsigned fbin1_ = 0;
+  btkb_pipeline* store_ = nullptr; unsigned chanN_ = 0; bool haveR_ = false; unsigned long version_ = 0;
+};
+typedef std::shared_ptr<McCowanPostFilter> McCowanPostFilterPtr;
+
+// LefkimmiatisPostFilter (postfilter.cc:935-1200)
+class LefkimmiatisPostFilter : public McCowanPostFilter {
+ public:
+  LefkimmiatisPostFilter(const VectorComplexFeatureStreamPtr& output, unsigned fftLen, double minSV = 1.0e-8, unsigned fbinX1 = 0, double alpha = 0.6, int type = 2,
+                         int min_frames = 0, float threshold = 0.99f, const std::string& nm = "LefkimmiatisPostFilterPtr");
+  void calc_inverse_noise_spatial_spectral_matrix();  // the inverse is (re)computed on the device whenever the graph runs
+};
+typedef std::shared_ptr<LefkimmiatisPostFilter> LefkimmiatisPostFilterPtr;
 
 class OverSampledDFTSynthesisBank : public VectorFloatFeatureStream {
  public:

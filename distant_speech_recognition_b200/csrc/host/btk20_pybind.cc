@@ -211,6 +211,34 @@ PYBIND11_MODULE(_btk20host, m) {
       .def("set_beamformer", &ZelinskiPostFilter::set_beamformer, py::arg("beamformer"))
       .def("postfilter_weights", &ZelinskiPostFilter::postfilter_weights);
 
+  py::class_<McCowanPostFilter, ZelinskiPostFilter, McCowanPostFilterPtr>(m, "McCowanPostFilterPtr")
+      .def(py::init<const VectorComplexFeatureStreamPtr&, unsigned, double, int, int, float, const std::string&>(), py::arg("output"), py::arg("fftlen"),
+           py::arg("alpha") = 0.6, py::arg("type") = 2, py::arg("min_frames") = 0, py::arg("threshold") = 0.99f, py::arg("nm") = "McCowanPostFilterPtr")
+      .def("noise_spatial_spectral_matrix", [](McCowanPostFilter& s, unsigned fbinX) {
+             std::vector<cplx> R = s.noise_spatial_spectral_matrix(fbinX);
+             py::array_t<cplx> out({(py::ssize_t)s.chanN(), (py::ssize_t)s.chanN()});
+             std::memcpy(out.mutable_data(), R.data(), R.size() * sizeof(cplx));
+             return out; }, py::arg("fbinX"))
+      .def("set_noise_spatial_spectral_matrix", [](McCowanPostFilter& s, unsigned fbinX, py::array_t<cplx, py::array::c_style | py::array::forcecast> Rnn) {
+             if (Rnn.ndim() != 2) throw jdimension_error("Rnn must be a matrix");
+             std::vector<cplx> v(Rnn.data(), Rnn.data() + Rnn.size());
+             return s.set_noise_spatial_spectral_matrix(fbinX, v, (unsigned)Rnn.shape(0), (unsigned)Rnn.shape(1)); }, py::arg("fbinX"), py::arg("Rnn"))
+      .def("set_diffuse_noise_model", [](McCowanPostFilter& s, py::array_t<double, py::array::c_style | py::array::forcecast> mpos, double samplerate, double sspeed) {
+             if (mpos.ndim() != 2) throw jdimension_error("micPositions must be a matrix");
+             std::vector<double> v(mpos.data(), mpos.data() + mpos.size());
+             return s.set_diffuse_noise_model(v, (unsigned)mpos.shape(0), (unsigned)mpos.shape(1), samplerate, sspeed); },
+           py::arg("micPositions"), py::arg("sampleRate"), py::arg("sspeed") = 343740.0)
+      .def("set_all_diagonal_loading", &McCowanPostFilter::set_all_diagonal_loading, py::arg("diagonalWeight"))
+      .def("set_diagonal_looading", &McCowanPostFilter::set_diagonal_looading, py::arg("fbinX"), py::arg("diagonalWeight"))
+      .def("divide_all_nondiagonal_elements", &McCowanPostFilter::divide_all_nondiagonal_elements, py::arg("mu"))
+      .def("divide_nondiagonal_elements", &McCowanPostFilter::divide_nondiagonal_elements, py::arg("fbinX"), py::arg("mu"));
+
+  py::class_<LefkimmiatisPostFilter, McCowanPostFilter, LefkimmiatisPostFilterPtr>(m, "LefkimmiatisPostFilterPtr")
+      .def(py::init<const VectorComplexFeatureStreamPtr&, unsigned, double, unsigned, double, int, int, float, const std::string&>(), py::arg("output"), py::arg("fftlen"),
+           py::arg("min_sv") = 1.0e-8, py::arg("fbin_no1") = 0, py::arg("alpha") = 0.6, py::arg("type") = 2, py::arg("min_frames") = 0, py::arg("threshold") = 0.99f,
+           py::arg("nm") = "LefkimmiatisPostFilterPtr")
+      .def("calc_inverse_noise_spatial_spectral_matrix", &LefkimmiatisPostFilter::calc_inverse_noise_spatial_spectral_matrix);
+
   m.def("calc_all_delays", [](double x, double y, double z, py::array_t<double, py::array::c_style | py::array::forcecast> mpos) { return calc_all_delays(x, y, z, vec_d(mpos)); },
         py::arg("x"), py::arg("y"), py::arg("z"), py::arg("mpos"));
 }

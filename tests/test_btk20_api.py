@@ -15,7 +15,7 @@ btk20 = pytest.importorskip("distant_speech_recognition_b200.btk20")
 from distant_speech_recognition_b200.btk20.feature import SampleFeaturePtr  # noqa: E402
 from distant_speech_recognition_b200.btk20.modulated import OverSampledDFTAnalysisBankPtr, OverSampledDFTSynthesisBankPtr, get_window  # noqa: E402
 from distant_speech_recognition_b200.btk20.beamformer import SubbandDSPtr, SubbandGSCPtr, SnapShotArrayPtr, calc_all_delays  # noqa: E402
-from distant_speech_recognition_b200.btk20.postfilter import ZelinskiPostFilterPtr  # noqa: E402
+from distant_speech_recognition_b200.btk20.postfilter import ZelinskiPostFilterPtr, McCowanPostFilterPtr, LefkimmiatisPostFilterPtr  # noqa: E402
 from distant_speech_recognition_b200.btk20.stream import PyVectorComplexFeatureStreamPtr  # noqa: E402
 from distant_speech_recognition_b200.btk20 import pybeamformer  # noqa: E402
 
@@ -140,6 +140,48 @@ def test_frontend_flow_gsc_zelinski(protos):
     w = np.real(np.array(pf.postfilter_weights()))
     assert w[:257].min() >= 1e-4 - 1e-9 and w.max() <= 1.0
     assert rel_l2(np.array(bf.beamformer().get_weights(17)), g["wq"][17]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_frontend_flow_sd_mccowan_and_ds_lefkimmiatis(protos):
+    """unit_test/test_online_beamforming.py:132-156,204 with confs/sd_and_mccowan.json and sd_and_lefkimmiatis.json parameters."""
+    g = load_golden("mccowan_c4_m256"); h, gg = protos[256]; M, D = 256, 128
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandMVDRBeamformer(afbs)
+    bf.calc_sd_beamformer_weights(FS, g["delays"], g["mpos"], mu=float(g["mu"]))
+    pf = McCowanPostFilterPtr(PyVectorComplexFeatureStreamPtr(bf), M, 0.7, 2)
+    with pytest.raises(Exception, match="noise coherence"):      # j_error: "Construct/set first a noise coherence matrix" (postfilter.cc:631-633)
+        pf.set_all_diagonal_loading(0.01)
+    assert pf.set_diffuse_noise_model(g["mpos"], FS, 343740.0)
+    pf.set_all_diagonal_loading(0.01)
+    R5 = np.array(pf.noise_spatial_spectral_matrix(5))
+    assert R5.shape == (4, 4) and abs(R5[0, 0] - (1.0 + float(np.float32(0.01)))) < 1e-12 and abs(R5[0, 1] - R5[1, 0]) < 1e-15
+    pf.set_beamformer(bf.beamformer())
+    sfb = OverSampledDFTSynthesisBankPtr(pf, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert rel_l2(y, g["timea"]) < 1e-4
+    pf.reset()
+    Y = np.array([np.array(v) for v in pf])
+    assert rel_l2(Y[:, :129], g["Ya"]) < 1e-4
+    assert np.all(Y[0, 129:] == 0) and np.allclose(Y[2, 129:], np.conj(Y[2, 1:128][::-1]))   # frame 0: upper half left at zero (postfilter.cc:896-901)
+    # per-bin setters round-trip through the device store
+    pf.set_noise_spatial_spectral_matrix(7, np.eye(4) * 2.0)
+    pf.set_diagonal_looading(7, 0.5); pf.divide_nondiagonal_elements(5, 1.0)
+    assert np.allclose(np.array(pf.noise_spatial_spectral_matrix(7)), np.eye(4) * 2.5)
+    assert abs(np.array(pf.noise_spatial_spectral_matrix(5))[0, 1] - R5[0, 1] / 2.0) < 1e-15
+
+    g = load_golden("lefkimmiatis_c8_m512"); h, gg = protos[512]; M, D = 512, 256
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandGSCBeamformer(afbs, Nc=1)   # 'delay_and_sum' type: zero active weights
+    bf.calc_beamformer_weights(FS, g["delays"])
+    pf = LefkimmiatisPostFilterPtr(PyVectorComplexFeatureStreamPtr(bf), M, 1e-4, 100, 0.8, 2)
+    pf.set_diffuse_noise_model(g["mpos"], FS, 343740.0)
+    pf.set_all_diagonal_loading(0.1)
+    pf.calc_inverse_noise_spatial_spectral_matrix()
+    pf.set_beamformer(bf.beamformer())
+    sfb = OverSampledDFTSynthesisBankPtr(pf, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert rel_l2(y, g["timea"]) < 1e-4
 
 
 @pytest.mark.gpu
