@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbtkb.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "btkb.h")
 
-BF_DS, BF_GSC, BF_MVDR, BF_GSC_LMS = 0, 1, 2, 3
+BF_DS, BF_GSC, BF_MVDR, BF_GSC_LMS, BF_GSC_RLS = 0, 1, 2, 3, 4
 PF_NONE, PF_ZELINSKI, PF_MCCOWAN, PF_LEFKIMMIATIS = 0, 1, 2, 3
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
 
@@ -29,12 +29,18 @@ class LmsParams(ct.Structure):
                 ("max_wa_l2norm", ct.c_float), ("min_frames", ct.c_int), ("slowdown_after", ct.c_int)]
 
 
+class RlsParams(ct.Structure):
+    _fields_ = [("beta", ct.c_float), ("gamma", ct.c_float), ("mu", ct.c_float), ("init_diagonal_load", ct.c_float),
+                ("regularization_param", ct.c_float), ("sil_thresh", ct.c_float), ("alpha2", ct.c_float), ("max_wa_l2norm", ct.c_float),
+                ("constraint_option", ct.c_int), ("min_frames", ct.c_int)]
+
+
 class Config(ct.Structure):
     _fields_ = [("device", ct.c_int), ("channels", ct.c_int), ("fft_len", ct.c_int), ("m", ct.c_int), ("r", ct.c_int),
                 ("delay_compensation_type", ct.c_int), ("samplerate", ct.c_float), ("beamformer", ct.c_int),
                 ("postfilter", ct.c_int), ("pf_alpha", ct.c_float), ("pf_type", ct.c_int), ("pf_min_frames", ct.c_int),
                 ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int), ("normalize_weight", ct.c_int),
-                ("pf_threshold", ct.c_float), ("pf_min_sv", ct.c_double), ("pf_fbin1", ct.c_int)]
+                ("pf_threshold", ct.c_float), ("pf_min_sv", ct.c_double), ("pf_fbin1", ct.c_int), ("rls", RlsParams)]
 
 
 def _load():
@@ -72,7 +78,7 @@ class Pipeline:
 
     def __init__(self, channels, fft_len=512, m=4, r=1, delay_compensation_type=2, samplerate=16000.0, beamformer=BF_DS,
                  postfilter=PF_NONE, pf_alpha=0.6, pf_type=2, pf_min_frames=0, lms=None, max_utterances=1,
-                 max_samples=160000, device=0, normalize_weight=False, pf_threshold=0.99, pf_min_sv=1.0e-8, pf_fbin1=0):
+                 max_samples=160000, device=0, normalize_weight=False, pf_threshold=0.99, pf_min_sv=1.0e-8, pf_fbin1=0, rls=None):
         cfg = Config()
         lib.btkb_default_config(ct.byref(cfg))
         cfg.device = device; cfg.channels = channels; cfg.fft_len = fft_len; cfg.m = m; cfg.r = r
@@ -83,6 +89,10 @@ class Pipeline:
         if lms:
             for k, v in lms.items():
                 setattr(cfg.lms, k, v)
+        if rls:
+            for k, v in rls.items():
+                if k != "slowdown_after":   # a constructor argument the reference's RLS loop never reads
+                    setattr(cfg.rls, k, v)
         cfg.max_utterances = max_utterances; cfg.max_samples = max_samples; cfg.normalize_weight = 1 if normalize_weight else 0
         self.cfg = cfg
         self.C, self.M, self.K, self.D = channels, fft_len, fft_len // 2 + 1, fft_len >> r

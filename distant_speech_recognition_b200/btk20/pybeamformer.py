@@ -4,7 +4,7 @@ the per-bin Python loops of the reference (`__iter__` of SubbandGSCLMSBeamformer
 kernels behind native stream objects."""
 import numpy
 
-from .beamformer import SubbandGSCPtr, SubbandMVDRGSCPtr, SubbandGSCLMSPtr, LmsConfig
+from .beamformer import SubbandGSCPtr, SubbandMVDRGSCPtr, SubbandGSCLMSPtr, LmsConfig, SubbandGSCRLSNativePtr, RlsConfig
 
 SSPEED = 343740.0
 
@@ -189,6 +189,40 @@ class SubbandGSCLMSBeamformer(SubbandBeamformer):
 
     def active_weights(self):
         """waH[K][C-Nc] after the run (the reference's self._waH)."""
+        return numpy.array(self._beamformer.active_weights(), numpy.complex128)
+
+    def total_updates(self):
+        return self._beamformer.total_updates()
+
+
+class SubbandGSCRLSBeamformer(SubbandBeamformer):
+    """lib/pybeamformer.py:765-928 — regularised RLS sidelobe canceller in GSC form.  The reference's per-bin Python loop
+    (precision-matrix update, quadratic constraint, norm reset) is the fused CUDA kernel k_perbin_rls (csrc/btkb_perbin.cu)."""
+
+    def __init__(self, spec_sources, beta=0.97, gamma=0.04, mu=0.97, init_diagonal_load=1.0E+6, regularization_param=1.0E-2, sil_thresh=1.0E+8,
+                 constraint_option=3, alpha2=10.0, max_wa_l2norm=100.0, min_frames=128, slowdown_after=4096, Nc=1):
+        SubbandBeamformer.__init__(self, spec_sources)
+        if Nc != 1:
+            raise NotImplementedError("the GPU RLS implements one linear constraint (Nc = 1)")
+        self._Nc = Nc
+        cfg = RlsConfig()
+        cfg.beta = beta; cfg.gamma = gamma; cfg.mu = mu; cfg.init_diagonal_load = init_diagonal_load
+        cfg.regularization_param = regularization_param; cfg.sil_thresh = sil_thresh; cfg.constraint_option = constraint_option
+        cfg.alpha2 = alpha2; cfg.max_wa_l2norm = max_wa_l2norm; cfg.min_frames = min_frames
+        self._slowdown_after = slowdown_after   # accepted and, as in the reference's loop, never read (pybeamformer.py:817-901)
+        self._beamformer = SubbandGSCRLSNativePtr(self._fftlen, cfg)
+        for source in self._spec_sources:
+            self._beamformer.set_channel(source)
+
+    def calc_beamformer_weights(self, samplerate, delays):
+        """lib/pybeamformer.py:903-911."""
+        self._beamformer.calc_beamformer_weights(samplerate, numpy.asarray(delays, numpy.float64))
+
+    def reset_stats(self):
+        """lib/pybeamformer.py:913-925."""
+        self._beamformer.reset()
+
+    def active_weights(self):
         return numpy.array(self._beamformer.active_weights(), numpy.complex128)
 
     def total_updates(self):

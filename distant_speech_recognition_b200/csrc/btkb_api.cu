@@ -71,6 +71,8 @@ void btkb_default_config(btkb_config* c) {
   c->lms.beta = 0.97f; c->lms.gamma = 0.01f; c->lms.init_diagonal_load = 1.0e6f; c->lms.regularization_param = 1.0e-4f;
   c->lms.energy_floor = 90.f; c->lms.sil_thresh = 1.0e8f; c->lms.max_wa_l2norm = 100.f; c->lms.min_frames = 128; c->lms.slowdown_after = 4096;
   c->max_utterances = 1; c->max_samples = 160000; c->keep_snapshots = 1; c->synthesis_gain = 1;
+  c->rls.beta = 0.97f; c->rls.gamma = 0.04f; c->rls.mu = 0.97f; c->rls.init_diagonal_load = 1.0e6f; c->rls.regularization_param = 1.0e-2f;
+  c->rls.sil_thresh = 1.0e8f; c->rls.alpha2 = 10.f; c->rls.max_wa_l2norm = 100.f; c->rls.constraint_option = 3; c->rls.min_frames = 128;
 }
 
 static void fb_delays(int m, int r, int dct, bool synthesis, int* pd, int* la) {  // modulated.cc:246-264
@@ -109,10 +111,14 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   if (C < 1) return fail(BTKB_ERR_INVALID, "btkb_create: channels must be >= 1");
   if (C > 64) return fail(BTKB_ERR_INVALID, "btkb_create: at most 64 channels");
   if (cfg->max_utterances < 1 || cfg->max_samples < 1) return fail(BTKB_ERR_INVALID, "btkb_create: capacities must be positive");
-  if (cfg->beamformer < BTKB_BF_DS || cfg->beamformer > BTKB_BF_GSC_LMS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown beamformer kind");
+  if (cfg->beamformer < BTKB_BF_DS || cfg->beamformer > BTKB_BF_GSC_RLS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown beamformer kind");
   if (cfg->postfilter < BTKB_PF_NONE || cfg->postfilter > BTKB_PF_LEFKIMMIATIS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown post-filter kind");
   if (cfg->postfilter >= BTKB_PF_MCCOWAN && (C < 2 || C > 8))
     return fail(BTKB_ERR_INVALID, "btkb_create: the McCowan / Lefkimmiatis post-filters are built for 2..8 channels");
+  if (cfg->beamformer == BTKB_BF_GSC_RLS && cfg->postfilter != BTKB_PF_NONE)
+    return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCRLSBeamformer");
+  if (cfg->beamformer == BTKB_BF_GSC_RLS && !(C == 2 || C == 4 || C == 8))
+    return fail(BTKB_ERR_INVALID, "btkb_create: the RLS sidelobe canceller keeps its C x C precision matrix in registers and is built for 2, 4 or 8 channels");
   if (cfg->beamformer == BTKB_BF_GSC_LMS && cfg->postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCLMSBeamformer");
   CK(cudaSetDevice(cfg->device));
@@ -225,7 +231,7 @@ static int check_weight_batch(btkb_pipeline* p, int U, const char* who) {
 int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
   if (!p || !delays) return fail(BTKB_ERR_INVALID, "btkb_set_delays: null argument");
   int rc = check_weight_batch(p, U, "btkb_set_delays"); if (rc) return rc;
-  if ((p->cfg.beamformer == BTKB_BF_GSC || p->cfg.beamformer == BTKB_BF_GSC_LMS) && p->C <= 1)  // beamformer.cc:507-510
+  if ((p->cfg.beamformer == BTKB_BF_GSC || p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS) && p->C <= 1)  // beamformer.cc:507-510
     return fail(BTKB_ERR_INVALID, "The number of channels must be > 1 but it is " + std::to_string(p->C));
   CK(cudaSetDevice(p->cfg.device));
   // stage through pinned host memory owned by the pipeline: the call stays asynchronous (no stream sync) and `delays`
@@ -249,7 +255,8 @@ int btkb_set_delays_lcmv(btkb_pipeline* p, int U, int NC, const double* delaysT,
   if (!p || !delaysT || !delaysJ) return fail(BTKB_ERR_INVALID, "btkb_set_delays_lcmv: null argument");
   if (NC < 2 || NC > 4 || NC > p->C)  // beamformer.cc:592-594
     return fail(BTKB_ERR_INVALID, "1 < the number of constraints " + std::to_string(NC) + " <= the number of sensors " + std::to_string(p->C) + " (and <= 4 in this build).");
-  if (p->cfg.beamformer == BTKB_BF_GSC_LMS) return fail(BTKB_ERR_INVALID, "btkb_set_delays_lcmv: the NLMS kernel implements one constraint");
+  if (p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS)
+    return fail(BTKB_ERR_INVALID, "btkb_set_delays_lcmv: the adaptive (NLMS / RLS) kernels implement one constraint");
   int rc = btkb_set_delays(p, U, delaysT);  // calcMainlobe first (also the time-alignment manifold), beamformer.cc:617
   if (rc) return rc;
   CK(cudaStreamSynchronize(p->stream));
@@ -466,6 +473,8 @@ static PerBinArgs perbin_args(btkb_pipeline* p) {
   a.kind = p->cfg.beamformer; a.normalize_weight = p->cfg.normalize_weight; a.pf_kind = p->cfg.postfilter; a.pf_alpha = p->cfg.pf_alpha; a.pf_type = p->cfg.pf_type; a.pf_min_frames = p->cfg.pf_min_frames;
   const btkb_lms_params& l = p->cfg.lms;
   a.lms = LmsArgs{l.beta, l.gamma, l.init_diagonal_load, l.regularization_param, l.energy_floor, l.sil_thresh, l.max_wa_l2norm, l.min_frames, l.slowdown_after};
+  const btkb_rls_params& q = p->cfg.rls;
+  a.rls = RlsArgs{q.beta, q.gamma, q.mu, q.init_diagonal_load, q.regularization_param, q.sil_thresh, q.alpha2, q.max_wa_l2norm, q.constraint_option, q.min_frames};
   return a;
 }
 
@@ -496,7 +505,7 @@ static int do_beamformer(btkb_pipeline* p) {
   if (narrow) CK(launch_perbin(a, p->stream)); else CK(launch_perbin_wide(a, p->stream));
   p->launches++;
   p->have_Y = true; p->pf_applied = true;
-  p->have_ua = (p->cfg.beamformer == BTKB_BF_GSC_LMS);
+  p->have_ua = (p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS);
   return BTKB_OK;
 }
 
@@ -741,8 +750,8 @@ int btkb_get_weights(btkb_pipeline* p, float* out) {
 int btkb_get_active_weights(btkb_pipeline* p, float* out) {
   if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(p->cfg.device));
-  if (p->cfg.beamformer == BTKB_BF_GSC_LMS) {
-    if (!p->have_ua) return fail(BTKB_ERR_STATE, "btkb_get_active_weights: the NLMS has not run");
+  if (p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS) {
+    if (!p->have_ua) return fail(BTKB_ERR_STATE, "btkb_get_active_weights: the adaptive sidelobe canceller has not run");
     if (p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_get_active_weights: the blocking-matrix export is built for <= 8 channels");
     CK(launch_ua_to_wa(p->d_UA, p->d_TA, p->d_WA, p->U, p->C, p->K, p->Gp, p->stream));
   } else if (!p->have_wl) {

@@ -36,6 +36,11 @@ struct LmsArgs {
   int min_frames, slowdown_after;
 };
 
+struct RlsArgs {
+  float beta, gamma, mu, init_diagonal_load, regularization_param, sil_thresh, alpha2, max_wa_l2norm;
+  int constraint_option, min_frames;
+};
+
 struct PerBinArgs {
   const float2* X; const float* E; const int* lengths;
   const float2* W;    // [C][Gp] quiescent / mvdr weights (not conjugated)
@@ -56,6 +61,7 @@ struct PerBinArgs {
   // McCowan / Lefkimmiatis constants (btkb_postfilter.cu): PFQ [NQ][K] per-bin pair factors, LAM [Gp] Lambda = d^H R^-1 d
   const float2* PFQ; const float* LAM; int pf_fbin1;
   LmsArgs lms;
+  RlsArgs rls;
   float energy_threshold;
 };
 

@@ -379,6 +379,179 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
 }
 
 // K2: R[u][k] += x x^H over the frames flagged in noise_mask (pybeamformer.py:976-982)
+// ---------------------------------------------------------------------------------------------------------------------
+// RLS sidelobe canceller: SubbandGSCRLSBeamformer.__iter__ (lib/pybeamformer.py:817-901), one thread per (utterance, bin)
+// chain, in the C-dimensional projector form (oracle/restate.py gsc_rls_projector; equal to the reference's B-form to
+// 1e-15 in fp64).  With Q = conj(B) (Q^H Q = I, Q^H v = 0) the kernel carries u = waH Q^H (C complex) and the Hermitian
+// Pt = Q Pz Q^H (C real diagonals + C(C-1)/2 complex) in registers, so the (C-1) x C blocking product never runs:
+//   x~ = x - C Yc v        p = Pt x~        ip = Re(x~^H p)        Pt <- (Pt - p p^H / (mu + ip)) / mu
+//   u  <- u + gamma ep p^H / (mu + ip) - reg u Pt^H      (ep = Yc - u.x with the OLD u, pybeamformer.py:843-847)
+//   |u|^2 > alpha2: quadratic constraint with va = Pt u^H (:851-861);  |u|^2 > max_wa_l2norm: rescale u and reset
+//   Pt = (I - C v v^H) / init_diagonal_load (:862-865).
+template <int C>
+struct HermP {   // Hermitian C x C: d[i] real diagonal, o[idx(i,j)], i > j, lower triangle
+  float d[C];
+  float2 o[C * (C - 1) / 2 > 0 ? C * (C - 1) / 2 : 1];
+  __device__ __forceinline__ static constexpr int idx(int i, int j) { return i * (i - 1) / 2 + j; }  // i > j
+  __device__ __forceinline__ float2 get(int i, int j) const {
+    if (i == j) return make_float2(d[i], 0.f);
+    if (i > j) return o[idx(i, j)];
+    const float2 t = o[idx(j, i)];
+    return make_float2(t.x, -t.y);
+  }
+};
+
+template <int C>
+__global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int g0 = blockIdx.x * TILE;
+  const int g = g0 + threadIdx.x;
+  const bool valid = g < a.G;
+  const int u = valid ? g / a.K : a.U - 1;
+  const int k = valid ? g - u * a.K : 0;
+  const int len = a.lengths ? a.lengths[u] : 0;
+  const int Tu = valid ? frames_of(len, a.D, a.laN, a.pdA) : 0;
+
+  TileRing<C> ring;
+  ring.init(smem_raw, &tmX, g0, a.T);
+
+  float2 w[C], uw[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) { w[c] = __ldg(a.W + (size_t)c * a.Gp + g); uw[c] = make_float2(0.f, 0.f); }
+  const float inv_load = 1.0f / a.rls.init_diagonal_load;
+  HermP<C> P;
+  auto reset_P = [&]() {
+#pragma unroll
+    for (int i = 0; i < C; i++) {
+      P.d[i] = (1.0f - (float)C * fmaf(w[i].x, w[i].x, w[i].y * w[i].y)) * inv_load;
+#pragma unroll
+      for (int j = 0; j < i; j++) {  // -(C v_i conj(v_j)) / load
+        P.o[HermP<C>::idx(i, j)] = make_float2(-(float)C * fmaf(w[i].x, w[j].x, w[i].y * w[j].y) * inv_load,
+                                               -(float)C * fmaf(w[i].y, w[j].x, -w[i].x * w[j].y) * inv_load);
+      }
+    }
+  };
+  reset_P();
+  float Eavg = a.rls.init_diagonal_load;
+  int n_updates = 0;
+  float e_next = (a.T > 0) ? __ldg(a.E + u) : 0.f;
+  const float one_m_beta = 1.0f - a.rls.beta;
+  const float inv_sil = 1.0f / a.rls.sil_thresh;
+  const float mu = a.rls.mu, inv_mu = 1.0f / a.rls.mu;
+  const int opt = a.rls.constraint_option;
+
+  for (int t = 0; t < a.T; t++) {
+    float2 x[C];
+    ring.fetch(t, a.T, x);
+    const float energy = e_next;
+    if (t + 1 < a.T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
+    float2 y = cdot<C, true>(x, w);   // Yc = v^H x
+    const bool live = t < Tu;
+    const bool adapt = energy > (Eavg * inv_sil);
+    if (adapt && live) {
+      const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
+      float2 xt[C], pv[C];
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        xt[c] = make_float2(fmaf(-cy.x, w[c].x, fmaf(cy.y, w[c].y, x[c].x)), fmaf(-cy.x, w[c].y, fmaf(-cy.y, w[c].x, x[c].y)));
+#pragma unroll
+      for (int i = 0; i < C; i++) {
+        float2 s = make_float2(P.d[i] * xt[i].x, P.d[i] * xt[i].y);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+          if (j == i) continue;
+          if (j < i) cmac(s, P.o[HermP<C>::idx(i, j)], xt[j]);
+          else cmac_conj(s, xt[j], P.o[HermP<C>::idx(j, i)]);   // conj(P_ji) x_j
+        }
+        pv[i] = s;
+      }
+      float ip = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; c++) ip = fmaf(xt[c].x, pv[c].x, fmaf(xt[c].y, pv[c].y, ip));
+      const float inv = 1.0f / (mu + ip);
+      // Pt <- (Pt - p p^H inv) / mu
+#pragma unroll
+      for (int i = 0; i < C; i++) {
+        P.d[i] = (P.d[i] - fmaf(pv[i].x, pv[i].x, pv[i].y * pv[i].y) * inv) * inv_mu;
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+          float2& e = P.o[HermP<C>::idx(i, j)];
+          const float2 pp = cmulc(pv[i], pv[j]);  // p_i conj(p_j)
+          e.x = (e.x - pp.x * inv) * inv_mu; e.y = (e.y - pp.y * inv) * inv_mu;
+        }
+      }
+      const float2 ep = csub(y, cdot<C, false>(uw, x));
+      const float2 ge = make_float2(a.rls.gamma * inv * ep.x, a.rls.gamma * inv * ep.y);
+      float2 un[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) {  // u + gamma ep conj(p) inv
+        un[c] = uw[c];
+        cmac_conj(un[c], ge, pv[c]);
+      }
+      if (a.rls.regularization_param > 0.f) {
+        const float reg = a.rls.regularization_param;
+#pragma unroll
+        for (int c = 0; c < C; c++) {  // (u Pt^H)_c = sum_j u_j conj(Pt_cj)
+          float2 s = make_float2(uw[c].x * P.d[c], uw[c].y * P.d[c]);
+#pragma unroll
+          for (int j = 0; j < C; j++) {
+            if (j == c) continue;
+            if (j < c) cmac_conj(s, uw[j], P.o[HermP<C>::idx(c, j)]);
+            else cmac(s, uw[j], P.o[HermP<C>::idx(j, c)]);         // conj(P_cj) = P_jc
+          }
+          un[c].x = fmaf(-reg, s.x, un[c].x); un[c].y = fmaf(-reg, s.y, un[c].y);
+        }
+      }
+      if (opt > 0) {
+        float n2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) n2 = fmaf(un[c].x, un[c].x, fmaf(un[c].y, un[c].y, n2));
+        if ((opt == 1 || opt == 3) && n2 > a.rls.alpha2) {
+          float2 va[C];
+          float qa = 0.f, qb = 0.f;
+#pragma unroll
+          for (int i = 0; i < C; i++) {  // va = Pt conj(un)
+            float2 s = make_float2(P.d[i] * un[i].x, -P.d[i] * un[i].y);
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+              if (j == i) continue;
+              const float2 pij = P.get(i, j);
+              cmac_conj(s, pij, un[j]);
+            }
+            va[i] = s;
+            qa = fmaf(s.x, s.x, fmaf(s.y, s.y, qa));
+            qb = fmaf(s.x, un[i].x, fmaf(-s.y, un[i].y, qb));   // Re(conj(va_i) conj(un_i))
+          }
+          const float b = -2.0f * qb, cc = n2 - a.rls.alpha2;
+          const float arg = fmaf(b, b, -4.0f * qa * cc);
+          const float betaK = (arg > 0.f) ? -(b + sqrtf(arg)) / (2.0f * qa) : -b / (2.0f * qa);
+#pragma unroll
+          for (int c = 0; c < C; c++) { un[c].x = fmaf(-betaK, va[c].x, un[c].x); un[c].y = fmaf(betaK, va[c].y, un[c].y); }
+        }
+        if (opt >= 2 && n2 > a.rls.max_wa_l2norm) {
+          const float sc = sqrtf(a.rls.max_wa_l2norm / n2);
+#pragma unroll
+          for (int c = 0; c < C; c++) { un[c].x *= sc; un[c].y *= sc; }
+          reset_P();
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) uw[c] = un[c];
+      if (k == 0) n_updates++;
+    }
+    if (t >= a.rls.min_frames) y = csub(y, cdot<C, false>(uw, x));
+    Eavg = fmaf(Eavg, a.rls.beta, one_m_beta * energy);
+    if (valid) a.Y[(size_t)t * a.Gp + g] = live ? y : make_float2(0.f, 0.f);
+  }
+  if (valid) {
+    if (a.UA != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; c++) a.UA[(size_t)c * a.Gp + g] = uw[c];
+    }
+    if (k == 0 && a.stats_updates != nullptr) a.stats_updates[u] = (float)n_updates;
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(TILE) k_covariance(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -514,6 +687,14 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
     kern<<<grid, TILE, sm, st>>>(tm, a);                                                         \
     return cudaGetLastError();                                                                   \
   } while (0)
+  if (a.kind == BTKB_BF_GSC_RLS) {
+    if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue;
+    auto kern = k_perbin_rls<C>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TILE, smem, st>>>(tm, a);
+    return cudaGetLastError();
+  }
   if (lms) { if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_LMS, 0); }
   if (pf == BTKB_PF_ZELINSKI) BTKB_LAUNCH(MODE_STATIC, 1);
   if (pf == BTKB_PF_MCCOWAN) { if (!a.PFQ) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 2); }

@@ -180,6 +180,9 @@ void SubbandBeamformer::ensure_pipeline_(const PostFilterConfig& pf, const Synth
   c.lms.beta = (float)lms_.beta; c.lms.gamma = (float)lms_.gamma; c.lms.init_diagonal_load = (float)lms_.init_diagonal_load;
   c.lms.regularization_param = (float)lms_.regularization_param; c.lms.energy_floor = (float)lms_.energy_floor; c.lms.sil_thresh = (float)lms_.sil_thresh;
   c.lms.max_wa_l2norm = (float)lms_.max_wa_l2norm; c.lms.min_frames = lms_.min_frames; c.lms.slowdown_after = lms_.slowdown_after;
+  c.rls.beta = (float)rls_.beta; c.rls.gamma = (float)rls_.gamma; c.rls.mu = (float)rls_.mu; c.rls.init_diagonal_load = (float)rls_.init_diagonal_load;
+  c.rls.regularization_param = (float)rls_.regularization_param; c.rls.sil_thresh = (float)rls_.sil_thresh; c.rls.alpha2 = (float)rls_.alpha2;
+  c.rls.max_wa_l2norm = (float)rls_.max_wa_l2norm; c.rls.constraint_option = rls_.constraint_option; c.rls.min_frames = rls_.min_frames;
   c.max_utterances = 1; c.max_samples = (int)n_samples; c.synthesis_gain = syn.enabled ? syn.gain : 1;
   if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; }
   ck(btkb_create(&c, &pipe_));
@@ -315,6 +318,20 @@ std::vector<std::complex<float>> SubbandGSCLMS::active_weights() {
   return wa;
 }
 int SubbandGSCLMS::total_updates() {
+  if (!realized_ || !pipe_) return 0;
+  double st[3]; ck(btkb_fetch_stats(pipe_, st));
+  return (int)st[2];
+}
+
+// ---- SubbandGSCRLSNative
+SubbandGSCRLSNative::SubbandGSCRLSNative(unsigned fftLen, const RlsConfig& cfg, const std::string& nm) : SubbandDS(fftLen, false, nm, BTKB_BF_GSC_RLS) { rls_ = cfg; }
+std::vector<std::complex<float>> SubbandGSCRLSNative::active_weights() {
+  if (!realized_ || !pipe_) throw j_error("run the beamformer first");
+  std::vector<std::complex<float>> wa((size_t)(fftLen_ / 2 + 1) * (chanN() - 1));
+  ck(btkb_get_active_weights(pipe_, reinterpret_cast<float*>(wa.data())));
+  return wa;
+}
+int SubbandGSCRLSNative::total_updates() {
   if (!realized_ || !pipe_) return 0;
   double st[3]; ck(btkb_fetch_stats(pipe_, st));
   return (int)st[2];

@@ -152,6 +152,11 @@ struct LmsConfig {  // lib/pybeamformer.py:597-607 defaults (= unit_test/confs/g
   int min_frames = 128, slowdown_after = 4096;
 };
 class McCowanPostFilter;
+struct RlsConfig {  // lib/pybeamformer.py:773-786 defaults (= unit_test/confs/gscrls.json)
+  double beta = 0.97, gamma = 0.04, mu = 0.97, init_diagonal_load = 1.0e6, regularization_param = 1.0e-2, sil_thresh = 1.0e8, alpha2 = 10.0,
+         max_wa_l2norm = 100.0;
+  int constraint_option = 3, min_frames = 128;
+};
 struct PostFilterConfig {
   bool enabled = false; double alpha = 0.6; int type = 2; int min_frames = 0;
   int kind = 1;                              // BTKB_PF_ZELINSKI / MCCOWAN / LEFKIMMIATIS
@@ -198,7 +203,7 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
   std::vector<std::complex<float>> W_;   // [K][C] weights read back
   int T_ = 0, nb_ = 0; bool realized_ = false, haveX_ = false;
   PostFilterConfig pf_used_; SynthesisConfig syn_used_;
-  LmsConfig lms_;
+  LmsConfig lms_; RlsConfig rls_;
   SnapShotArrayPtr snap_;
   std::vector<unsigned long> src_versions_;
   void ensure_pipeline_(const PostFilterConfig& pf, const SynthesisConfig& syn, unsigned n_samples);
@@ -238,6 +243,17 @@ class SubbandGSCLMS : public SubbandDS {
   int total_updates();
 };
 typedef std::shared_ptr<SubbandGSCLMS> SubbandGSCLMSPtr;
+
+// native body of pybeamformer.SubbandGSCRLSBeamformer (lib/pybeamformer.py:765-928; NOT the reference's C++ SubbandGSCRLS,
+// beamformer.cc:1447-1699, which forms Z = B^H x and is a different recursion)
+class SubbandGSCRLSNative : public SubbandDS {
+ public:
+  SubbandGSCRLSNative(unsigned fftLen, const RlsConfig& cfg, const std::string& nm = "SubbandGSCRLSNative");
+  void calc_beamformer_weights(double samplerate, const std::vector<double>& delays) { calc_array_manifold_vectors(samplerate, delays); }
+  std::vector<std::complex<float>> active_weights();
+  int total_updates();
+};
+typedef std::shared_ptr<SubbandGSCRLSNative> SubbandGSCRLSNativePtr;
 
 class SubbandMVDR : public SubbandDS {
  public:

@@ -183,6 +183,25 @@ PYBIND11_MODULE(_btk20host, m) {
         return a; })
       .def("total_updates", &SubbandGSCLMS::total_updates);
 
+  py::class_<RlsConfig>(m, "RlsConfig")
+      .def(py::init<>())
+      .def_readwrite("beta", &RlsConfig::beta).def_readwrite("gamma", &RlsConfig::gamma).def_readwrite("mu", &RlsConfig::mu)
+      .def_readwrite("init_diagonal_load", &RlsConfig::init_diagonal_load).def_readwrite("regularization_param", &RlsConfig::regularization_param)
+      .def_readwrite("sil_thresh", &RlsConfig::sil_thresh).def_readwrite("alpha2", &RlsConfig::alpha2).def_readwrite("max_wa_l2norm", &RlsConfig::max_wa_l2norm)
+      .def_readwrite("constraint_option", &RlsConfig::constraint_option).def_readwrite("min_frames", &RlsConfig::min_frames);
+
+  py::class_<SubbandGSCRLSNative, SubbandDS, SubbandGSCRLSNativePtr>(m, "SubbandGSCRLSNativePtr")
+      .def(py::init([](unsigned fftlen, const RlsConfig& c, const std::string& nm) { return std::make_shared<SubbandGSCRLSNative>(fftlen, c, nm); }), py::arg("fftlen"),
+           py::arg("config"), py::arg("nm") = "SubbandGSCRLSNative")
+      .def("calc_beamformer_weights", [](SubbandGSCRLSNative& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { s.calc_beamformer_weights(fs, vec_d(d)); },
+           py::arg("samplerate"), py::arg("delays"))
+      .def("active_weights", [](SubbandGSCRLSNative& s) {
+        auto w = s.active_weights();
+        py::array_t<std::complex<float>> a({(size_t)(s.fftLen() / 2 + 1), (size_t)(s.chanN() - 1)});
+        std::memcpy(a.mutable_data(), w.data(), sizeof(std::complex<float>) * w.size());
+        return a; })
+      .def("total_updates", &SubbandGSCRLSNative::total_updates);
+
   py::class_<SubbandMVDR, SubbandDS, SubbandMVDRPtr>(m, "SubbandMVDRPtr")
       .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandMVDR>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,
            py::arg("half_band_shift") = false, py::arg("nm") = "SubbandMVDR")

@@ -44,6 +44,7 @@ extern "C" {
 #define BTKB_BF_GSC 1      /* SubbandGSC: DC bin wq^H x, bins >= 1 (wq - wl)^H x, static wl  (beamformer.cc:1208-1316) */
 #define BTKB_BF_MVDR 2     /* SubbandMVDR / SubbandMVDRGSC: y = (wmvdr - wl)^H x             (beamformer.cc:2537-2587, 2719-2773) */
 #define BTKB_BF_GSC_LMS 3  /* SubbandGSCLMSBeamformer: leaky power-normalised NLMS           (pybeamformer.py:588-762) */
+#define BTKB_BF_GSC_RLS 4  /* SubbandGSCRLSBeamformer: regularised RLS sidelobe canceller    (pybeamformer.py:765-928) */
 
 /* post-filter kinds */
 #define BTKB_PF_NONE 0
@@ -57,6 +58,12 @@ typedef struct btkb_lms_params { /* defaults = unit_test/confs/gsclms.json / pyb
   float beta, gamma, init_diagonal_load, regularization_param, energy_floor, sil_thresh, max_wa_l2norm;
   int min_frames, slowdown_after;
 } btkb_lms_params;
+
+typedef struct btkb_rls_params { /* defaults = unit_test/confs/gscrls.json / pybeamformer.py:773-786 */
+  float beta, gamma, mu, init_diagonal_load, regularization_param, sil_thresh, alpha2, max_wa_l2norm;
+  int constraint_option;  /* 0 none, 1 quadratic constraint, 2 norm normalisation, 3 both */
+  int min_frames;
+} btkb_rls_params;
 
 typedef struct btkb_config {
   int device;                  /* CUDA device ordinal */
@@ -80,6 +87,7 @@ typedef struct btkb_config {
   float pf_threshold;          /* McCowan / Lefkimmiatis: clip of the noise coherence R_ij (default 0.99, postfilter.h) */
   double pf_min_sv;            /* Lefkimmiatis: singular-value floor of the coherence pseudo-inverse (default 1e-8) */
   int pf_fbin1;                /* Lefkimmiatis: first bin that divides the noise PSD by Lambda = d^H R^-1 d (default 0) */
+  btkb_rls_params rls;         /* BTKB_BF_GSC_RLS */
 } btkb_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */

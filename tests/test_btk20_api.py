@@ -121,6 +121,22 @@ def test_frontend_flow_gsclms(protos):
 
 
 @pytest.mark.gpu
+def test_frontend_flow_gscrls(protos):
+    """unit_test/test_online_beamforming.py with "type":"gscrls" (confs/gscrls.json): SubbandGSCRLSBeamformer in the same graph."""
+    g = load_golden("gscrls_c8_m512"); h, gg = protos[512]; M, D = 512, 256
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandGSCRLSBeamformer(afbs, beta=0.97, gamma=0.04, mu=0.97, init_diagonal_load=1.0E+6, regularization_param=1.0E-2,
+                                              sil_thresh=1.0E+8, constraint_option=3, alpha2=10.0, max_wa_l2norm=100.0,
+                                              min_frames=int(g["min_frames"]), slowdown_after=4096)
+    bf.calc_beamformer_weights(FS, g["delays"])
+    sfb = OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(bf), prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert y.shape == g["time"].shape and rel_l2(y, g["time"]) < 1e-4
+    assert bf.total_updates() == int(g["n_updates"])
+    assert rel_l2(bf.active_weights(), g["waH"]) < 1e-3
+
+
+@pytest.mark.gpu
 def test_frontend_flow_gsc_zelinski(protos):
     """D&S/GSC + Zelinski (confs/ds_and_zelinski.json flow): ZelinskiPostFilterPtr(pybf, M, alpha, subtype); set_beamformer."""
     g = load_golden("gsc_zelinski_c8_m512"); h, gg = protos[512]; M, D = 512, 256

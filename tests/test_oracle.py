@@ -173,6 +173,44 @@ def test_lefkimmiatis_postfilter_golden(protos):
     assert rel_l2(restate.synthesis(Yb, gg, M, 4, 1)[: len(g["timeb"])], g["timeb"]) < 2e-5
 
 
+def test_gsc_lms_golden_is_the_reference_pythons_output():
+    """golden_gsclms_c8_m512 came from the C++ re-statement in oracle/ref_harness.cc; golden_pyref_gsclms_c8_m512 from the
+    reference's own SubbandGSCLMSBeamformer.__iter__ run through oracle/pyref.py on the same snapshots: they must agree."""
+    a = load_golden("gsclms_c8_m512"); b = load_golden("pyref_gsclms_c8_m512")
+    assert rel_l2(a["Y"], b["Y"]) < 1e-13 and rel_l2(a["waH"], b["waH"]) < 1e-12
+    assert int(a["stats"][2]) == int(b["n_updates"])
+
+
+def test_gsc_rls_golden(protos):
+    """SubbandGSCRLSBeamformer (pybeamformer.py:765-928): B-form and projector-form restatements vs the reference Python's output."""
+    for name, M in (("gscrls_c8_m512", 512), ("gscrls_c4_m256", 256)):
+        g = load_golden(name); h, gg = protos[M]; K = M // 2 + 1
+        X = _X(g["x"], h, M)
+        kw = {k: (int(g[k]) if k in ("min_frames", "constraint_option") else float(g[k])) for k in restate.DEFAULT_RLS if k in g.files}
+        Y, waH, nu = restate.gsc_rls(X, FS, g["delays"], **kw)
+        assert rel_l2(Y[:, :K], g["Y"]) < 1e-11 and rel_l2(waH, g["waH"]) < 1e-10 and nu == int(g["n_updates"])
+        Yp, u, nup = restate.gsc_rls_projector(X, FS, g["delays"], **kw)
+        assert rel_l2(Yp[:, :K], g["Y"]) < 1e-11 and nup == nu
+        B = np.stack([restate.calc_blocking_matrix(restate.calc_array_manifold_f(f, M, FS, g["delays"]), 1) for f in range(K)])
+        assert rel_l2(np.einsum("kc,kci->ki", u, np.conj(B)), g["waH"]) < 1e-10      # waH = u conj(B)
+        assert rel_l2(restate.synthesis(Y, gg, M, 4, 1)[: len(g["time"])], g["time"]) < 1e-6
+
+
+def test_reference_python_runs_live_when_present(protos):
+    """With /root/reference mounted (build container), run the reference's own Python NLMS / RLS loops now."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("reference not mounted (GPU box)")
+    g = load_golden("gscrls_c4_m256"); h, _ = protos[256]
+    X = _X(g["x"], h, 256)
+    Y, waH, nu = pyref.run_adaptive("lms", X, FS, g["delays"], 128, min_frames=4)
+    Yo, wo, no = restate.gsc_lms(X, FS, g["delays"], min_frames=4)
+    assert rel_l2(Yo, Y) < 1e-13 and no == nu
+    Y, waH, nu = pyref.run_adaptive("rls", X, FS, g["delays"], 128, min_frames=4, constraint_option=1, alpha2=0.02)
+    Yo, wo, no = restate.gsc_rls(X, FS, g["delays"], min_frames=4, constraint_option=1, alpha2=0.02)
+    assert rel_l2(Yo, Y) < 1e-12 and no == nu
+
+
 def test_pseudoinverse_golden():
     g = load_golden("pseudoinverse")
     for A, inv in zip(g["A"], g["inv"]):

@@ -230,6 +230,42 @@ def test_postfilters_batched_match_oracle(capi, protos):
         p.close()
 
 
+def test_gsc_rls_golden(capi, protos):
+    """SubbandGSCRLSBeamformer (pybeamformer.py:765-928) vs the output of the reference's own Python loop (goldens made
+    through oracle/pyref.py): defaults of confs/gscrls.json, and a run where the quadratic constraint and the reset fire."""
+    from oracle import restate
+    for name, M, C in (("gscrls_c8_m512", 512, 8), ("gscrls_c4_m256", 256, 4)):
+        g = load_golden(name)
+        K = M // 2 + 1
+        x = g["x"]
+        rls = {k: (int(g[k]) if k in ("min_frames", "constraint_option") else float(g[k])) for k in restate.DEFAULT_RLS if k in g.files}
+        p = _pipe(capi, C, M, protos, n=x.shape[1], beamformer=capi.BF_GSC_RLS, rls=rls)
+        p.set_delays(g["delays"][None])
+        p.submit(x[None])
+        p.run(True)
+        assert rel_l2(p.fetch_subband()[0], g["Y"]) < TOL, name
+        assert rel_l2(p.fetch_time()[0], g["time"]) < TOL, name
+        assert rel_l2(p.get_active_weights()[0], g["waH"]) < 1e-3, name
+        assert int(p.fetch_stats()[0, 2]) == int(g["n_updates"])
+        p.close()
+
+
+def test_gsc_rls_long_utterance_vs_fp64_oracle(capi, protos):
+    """5 s utterance (317 frames, the configs[1] shape): fp32 precision-matrix recursion against the fp64 restatement."""
+    from oracle import restate
+    from distant_speech_recognition_b200 import synthetic
+    M, C, n = 512, 8, 80000
+    h, gq = protos[M]
+    x, d, _, _ = synthetic.make_utterance(11, C, n)
+    rls = dict(min_frames=20)
+    p = _pipe(capi, C, M, protos, n=n, beamformer=capi.BF_GSC_RLS, rls=rls)
+    p.set_delays(d[None]); p.submit(x[None]); p.run(True)
+    X = np.stack([restate.analysis(x[c], h, M, 4, 1) for c in range(C)], axis=1)
+    Yo, u, nu = restate.gsc_rls_projector(X, FS, d, **rls)
+    assert rel_l2(p.fetch_subband()[0], Yo[:, :257]) < TOL
+    assert rel_l2(p.fetch_time()[0], restate.synthesis(Yo, gq, M, 4, 1)) < TOL
+
+
 def test_batch_ragged_lengths_match_single_runs(capi, protos):
     """Utterances are independent units: a ragged batch must reproduce each utterance run alone (and the oracle)."""
     from distant_speech_recognition_b200 import synthetic
