@@ -35,12 +35,17 @@ class RlsParams(ct.Structure):
                 ("constraint_option", ct.c_int), ("min_frames", ct.c_int)]
 
 
+class WpeParams(ct.Structure):
+    _fields_ = [("enabled", ct.c_int), ("lower_num", ct.c_int), ("upper_num", ct.c_int), ("iterations_num", ct.c_int),
+                ("load_db", ct.c_double), ("band_width", ct.c_double), ("diagonal_bias", ct.c_double), ("fp32_normal_equations", ct.c_int)]
+
+
 class Config(ct.Structure):
     _fields_ = [("device", ct.c_int), ("channels", ct.c_int), ("fft_len", ct.c_int), ("m", ct.c_int), ("r", ct.c_int),
                 ("delay_compensation_type", ct.c_int), ("samplerate", ct.c_float), ("beamformer", ct.c_int),
                 ("postfilter", ct.c_int), ("pf_alpha", ct.c_float), ("pf_type", ct.c_int), ("pf_min_frames", ct.c_int),
                 ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int), ("normalize_weight", ct.c_int),
-                ("pf_threshold", ct.c_float), ("pf_min_sv", ct.c_double), ("pf_fbin1", ct.c_int), ("rls", RlsParams)]
+                ("pf_threshold", ct.c_float), ("pf_min_sv", ct.c_double), ("pf_fbin1", ct.c_int), ("rls", RlsParams), ("wpe", WpeParams)]
 
 
 def _load():
@@ -78,7 +83,7 @@ class Pipeline:
 
     def __init__(self, channels, fft_len=512, m=4, r=1, delay_compensation_type=2, samplerate=16000.0, beamformer=BF_DS,
                  postfilter=PF_NONE, pf_alpha=0.6, pf_type=2, pf_min_frames=0, lms=None, max_utterances=1,
-                 max_samples=160000, device=0, normalize_weight=False, pf_threshold=0.99, pf_min_sv=1.0e-8, pf_fbin1=0, rls=None):
+                 max_samples=160000, device=0, normalize_weight=False, pf_threshold=0.99, pf_min_sv=1.0e-8, pf_fbin1=0, rls=None, wpe=None):
         cfg = Config()
         lib.btkb_default_config(ct.byref(cfg))
         cfg.device = device; cfg.channels = channels; cfg.fft_len = fft_len; cfg.m = m; cfg.r = r
@@ -93,6 +98,10 @@ class Pipeline:
             for k, v in rls.items():
                 if k != "slowdown_after":   # a constructor argument the reference's RLS loop never reads
                     setattr(cfg.rls, k, v)
+        if wpe is not None:
+            cfg.wpe.enabled = 1
+            for k, v in wpe.items():
+                setattr(cfg.wpe, k, v)
         cfg.max_utterances = max_utterances; cfg.max_samples = max_samples; cfg.normalize_weight = 1 if normalize_weight else 0
         self.cfg = cfg
         self.C, self.M, self.K, self.D = channels, fft_len, fft_len // 2 + 1, fft_len >> r
@@ -152,6 +161,21 @@ class Pipeline:
     def set_diffuse_noise_model(self, U, mpos, sspeed=343740.0):
         mp = np.ascontiguousarray(mpos, np.float64)
         _check(lib.btkb_set_diffuse_noise_model(self._h, ct.c_int(U), _dp(mp), ct.c_float(sspeed)))
+
+    # ---- multi-channel WPE (dereverberation.cc:312-733)
+    def run_wpe(self, start_frame_no=0, end_frame_no=-1):
+        _check(lib.btkb_run_wpe(self._h, ct.c_int(start_frame_no), ct.c_int(end_frame_no)))
+
+    def get_wpe_filter(self):
+        P = self.cfg.wpe.upper_num - self.cfg.wpe.lower_num + 1
+        out = np.empty((self.U, self.K, self.C, self.C * P), np.complex64)
+        _check(lib.btkb_get_wpe_filter(self._h, _fp(out)))
+        return out
+
+    def last_timing_wpe(self):
+        ms = ct.c_float(0)
+        _check(lib.btkb_last_timing_wpe(self._h, ct.byref(ms)))
+        return float(ms.value)
 
     # ---- noise coherence of the McCowan / Lefkimmiatis post-filters (postfilter.cc:541-680)
     def pf_set_diffuse_noise_model(self, mpos, samplerate=16000.0, sspeed=343740.0):

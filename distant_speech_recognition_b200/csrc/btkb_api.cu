@@ -39,6 +39,10 @@ struct btkb_pipeline {
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   int16_t* d_x16 = nullptr; double* h_delays = nullptr; float2* d_tw = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
   double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
+  // multi-channel WPE (lazily sized at create when cfg.wpe.enabled)
+  float2 *d_wS = nullptr, *d_wG = nullptr; void* d_wR = nullptr; float* d_wTH = nullptr; int* d_werr = nullptr;
+  int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_Ts = 0, wpe_nbins = 0; bool have_wpe = false;
+  cudaEvent_t wev[2] = {nullptr, nullptr};
   bool have_pfR = false, pf_applied = false;  // pf_applied: d_Y came out of this pipeline's post-filter (not btkb_set_subband)
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
@@ -71,6 +75,8 @@ void btkb_default_config(btkb_config* c) {
   c->lms.beta = 0.97f; c->lms.gamma = 0.01f; c->lms.init_diagonal_load = 1.0e6f; c->lms.regularization_param = 1.0e-4f;
   c->lms.energy_floor = 90.f; c->lms.sil_thresh = 1.0e8f; c->lms.max_wa_l2norm = 100.f; c->lms.min_frames = 128; c->lms.slowdown_after = 4096;
   c->max_utterances = 1; c->max_samples = 160000; c->keep_snapshots = 1; c->synthesis_gain = 1;
+  c->wpe.enabled = 0; c->wpe.lower_num = 0; c->wpe.upper_num = 32; c->wpe.iterations_num = 2; c->wpe.load_db = -18.0; c->wpe.band_width = 0.0;
+  c->wpe.diagonal_bias = 1.0e-4;
   c->rls.beta = 0.97f; c->rls.gamma = 0.04f; c->rls.mu = 0.97f; c->rls.init_diagonal_load = 1.0e6f; c->rls.regularization_param = 1.0e-2f;
   c->rls.sil_thresh = 1.0e8f; c->rls.alpha2 = 10.f; c->rls.max_wa_l2norm = 100.f; c->rls.constraint_option = 3; c->rls.min_frames = 128;
 }
@@ -88,10 +94,11 @@ void btkb_destroy(btkb_pipeline* p) {
   cudaSetDevice(p->cfg.device);
   void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
                   p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
-                  p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM};
+                  p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM, p->d_wS, p->d_wG, p->d_wR, p->d_wTH, p->d_werr};
   if (p->h_delays) cudaFreeHost(p->h_delays);
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : p->wev) if (e) cudaEventDestroy(e);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -121,6 +128,13 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
     return fail(BTKB_ERR_INVALID, "btkb_create: the RLS sidelobe canceller keeps its C x C precision matrix in registers and is built for 2, 4 or 8 channels");
   if (cfg->beamformer == BTKB_BF_GSC_LMS && cfg->postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCLMSBeamformer");
+  if (cfg->wpe.enabled) {
+    if (!(C == 1 || C == 2 || C == 4 || C == 8)) return fail(BTKB_ERR_INVALID, "btkb_create: WPE is built for 1, 2, 4 or 8 channels");
+    if (cfg->wpe.lower_num < 0 || cfg->wpe.upper_num < cfg->wpe.lower_num || cfg->wpe.iterations_num < 0)
+      return fail(BTKB_ERR_INVALID, "btkb_create: bad WPE lag range / iteration count");
+    if (cfg->wpe.band_width > cfg->samplerate / 2.0)  // dereverberation.cc:369-370
+      return fail(BTKB_ERR_INVALID, "Bandwidth is greater than the Nyquist rate.");
+  }
   CK(cudaSetDevice(cfg->device));
   btkb_pipeline* p = new btkb_pipeline();
   p->cfg = *cfg;
@@ -164,6 +178,21 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   A((void**)&p->d_mask, T * U);
   A((void**)&p->d_count, U * sizeof(int));
   A((void**)&p->d_tw, (size_t)M * sizeof(float2));
+  if (cfg->wpe.enabled) {
+    p->wpe_P = cfg->wpe.upper_num - cfg->wpe.lower_num + 1; p->wpe_L = C * p->wpe_P; p->wpe_Lr = round_up(p->wpe_L + 1, 2);  // column L exists: the augmented row carries its own diagonal entry
+    p->wpe_Ts = round_up(p->Tcap, 2);
+    const int lo = (cfg->wpe.band_width == 0.0) ? M / 2 : (int)((cfg->wpe.band_width / (cfg->samplerate / 2.0)) * (M / 2));  // set_band_width_ (:365-373)
+    p->wpe_nbins = std::min(lo, p->K - 1) + 1;
+    const char* ce = getenv("BTKB_WPE_CHUNK");
+    p->wpe_chunk = ce ? std::max(1, atoi(ce)) : 36;
+    p->wpe_chunk = std::min(p->wpe_chunk, p->Ucap * p->wpe_nbins);
+    for (auto& ev : p->wev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    A((void**)&p->d_wS, (size_t)p->Ucap * p->K * C * p->wpe_Ts * sizeof(float2));
+    A((void**)&p->d_wTH, (size_t)p->Ucap * p->K * C * p->wpe_Ts * sizeof(float));
+    A((void**)&p->d_wG, (size_t)p->Ucap * p->K * C * p->wpe_L * sizeof(float2));
+    A((void**)&p->d_wR, wpe_workspace_bytes(C, p->wpe_L, p->wpe_Lr, p->wpe_chunk, cfg->wpe.fp32_normal_equations));
+    A((void**)&p->d_werr, sizeof(int));
+  }
   if (e != cudaSuccess) {
     std::string msg = std::string("btkb_create: allocation failed: ") + cudaGetErrorString(e);
     btkb_destroy(p);
@@ -478,6 +507,30 @@ static PerBinArgs perbin_args(btkb_pipeline* p) {
   return a;
 }
 
+static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no) {
+  if (!p->cfg.wpe.enabled) return fail(BTKB_ERR_STATE, "btkb_run_wpe: the pipeline was created without cfg.wpe.enabled");
+  if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_run_wpe: run the analysis first");
+  const btkb_wpe_params& w = p->cfg.wpe;
+  WpeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = p->d_X; a.lengths = p->d_len; a.S = p->d_wS; a.TH = p->d_wTH; a.Gf = p->d_wG; a.Rw = p->d_wR; a.err_flag = p->d_werr;
+  a.U = p->U; a.C = p->C; a.T = p->T; a.Ts = round_up(p->T, 2); a.K = p->K; a.G = p->U * p->K; a.Gp = p->Gp; a.D = p->D; a.laN = p->laN; a.pdA = p->pdA;
+  a.lowerN = w.lower_num; a.P = p->wpe_P; a.L = p->wpe_L; a.Lr = p->wpe_Lr; a.iterations = w.iterations_num; a.nbins = p->wpe_nbins;
+  a.est_frames = (end_frame_no < 0) ? -1 : std::max(0, end_frame_no - std::max(start_frame_no, 0));   // fill_buffer_ (:500-534) never skips input frames
+  a.load_factor = (float)pow(10.0, w.load_db / 10.0); a.diagonal_bias = (float)w.diagonal_bias;
+  CK(cudaMemsetAsync(p->d_werr, 0, sizeof(int), p->stream));
+  CK(cudaEventRecord(p->wev[0], p->stream));
+  CK(launch_wpe(a, p->wpe_chunk, p->cfg.wpe.fp32_normal_equations, p->stream, &p->launches));
+  CK(cudaEventRecord(p->wev[1], p->stream));
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, p->d_werr, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  if (err)  // dereverberation.cc:676-678
+    return fail(BTKB_ERR_INVALID, "MultiChannelWPEDereverberation: GSL Cholesky decomposition failed.\nSome channels may be too similar. Try to increase 'diagonal_bias' or use 'SingleChannelWPEDereverberationFeature' for each channel");
+  p->have_wpe = true;
+  return BTKB_OK;
+}
+
 static int do_beamformer(btkb_pipeline* p) {
   if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_run_beamformer: run the analysis first");
   if (!p->have_w) {
@@ -563,6 +616,31 @@ int btkb_spectral_matrix_update(btkb_pipeline* p, float mu, int legacy_noconj) {
   return BTKB_OK;
 }
 
+int btkb_run_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  p->launches = 0;
+  return do_wpe(p, start_frame_no, end_frame_no);
+}
+
+int btkb_get_wpe_filter(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_wpe) return fail(BTKB_ERR_STATE, "Call estimate_filter() first");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(out, p->d_wG, (size_t)p->U * p->K * p->C * p->wpe_L * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return BTKB_OK;
+}
+
+int btkb_last_timing_wpe(btkb_pipeline* p, float* ms) {
+  if (!p || !ms) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_wpe) return fail(BTKB_ERR_STATE, "btkb_last_timing_wpe: WPE has not run");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaEventSynchronize(p->wev[1]));
+  CK(cudaEventElapsedTime(ms, p->wev[0], p->wev[1]));
+  return BTKB_OK;
+}
+
 int btkb_run_beamformer(btkb_pipeline* p, int do_syn) {
   if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
   CK(cudaSetDevice(p->cfg.device));
@@ -614,6 +692,7 @@ int btkb_run(btkb_pipeline* p, int do_syn) {
   p->launches = 0;
   CK(cudaEventRecord(p->ev[0], p->stream));
   int rc = do_analysis(p); if (rc) return rc;
+  if (p->cfg.wpe.enabled) { rc = do_wpe(p, 0, -1); if (rc) return rc; }   // counted in the "analysis" segment of btkb_last_timing; btkb_last_timing_wpe isolates it
   CK(cudaEventRecord(p->ev[1], p->stream));
   rc = do_beamformer(p); if (rc) return rc;
   CK(cudaEventRecord(p->ev[2], p->stream));

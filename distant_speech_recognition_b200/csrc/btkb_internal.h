@@ -65,6 +65,22 @@ struct PerBinArgs {
   float energy_threshold;
 };
 
+// multi-channel WPE (btkb_wpe.cu)
+struct WpeArgs {
+  float2* X;             // [T][C][Gp] snapshots: reverberant in, dereverberated out
+  const int* lengths;
+  float2* S;             // [G][C][Ts] series-major copy of X
+  float* TH;             // [G][C][Ts] theta
+  float2* Gf;            // [G][C][L] prediction filters (chains outside the estimated band stay zero)
+  void* Rw;              // workspace [chunk][C][L+1][Lr] complex128 (or complex64): lower triangle of R_c, row L = conj(r_c)
+  int* err_flag;         // set to 1 when a Cholesky pivot is not positive
+  int U, C, T, Ts, K, G, Gp, D, laN, pdA;
+  int lowerN, P, L, Lr, iterations, nbins, est_frames;
+  float load_factor, diagonal_bias;
+};
+size_t wpe_workspace_bytes(int C, int L, int Lr, int chunk, int fp32);
+cudaError_t launch_wpe(const WpeArgs& a, int chunk, int fp32, cudaStream_t st, int* launches);
+
 struct WeightsArgs {
   const double* delays;  // [U][C]
   float2* W;             // [C][Gp]

@@ -1,0 +1,406 @@
+// btkb_wpe.cu — multi-channel WPE dereverberation between the analysis bank and the beamformer (sm_100a).
+//
+// Replaces MultiChannelWPEDereverberation::{fill_buffer_, calc_Thetan_, calc_Rr_, load_R_, estimate_Gn_,
+// calc_every_channel_output} (dereverberation/dereverberation.cc:441-700).  Unit of work: a "problem" = one (utterance, bin)
+// series of C channels x T frames; problems are independent, so the batch is a grid of them.
+//
+//   k_wpe_gather   X[T][C][Gp] -> S[g][c][Ts]      series-major copy (every later kernel reads contiguous series)
+//   k_wpe_resid<0> theta[g][c][t] = max(|x_c(t) - G_c^H lags(t)|, 1e-3)^2                       calc_Thetan_  (:619-646)
+//   k_wpe_corr     R_c = sum_s lags lags^H / theta_c(s) (lower triangle) and r_c^H as an extra row  calc_Rr_    (:553-617)
+//   k_wpe_chol     + diagonal_bias, load_R_ (:648-663), Cholesky, solve R_c g = r_c              estimate_Gn_ (:665-690)
+//   k_wpe_resid<1> X'[t][c][g] = x_c(t) - G_c^H lags(t)                                          calc_every_channel_output (:441-497)
+//
+// lags(s)[(c', l)] = x_c'(s - lower - l), channel-major then lag (get_lags_, :536-551).  The lag matrix is block-Toeplitz in
+// the series, so k_wpe_corr keeps only the C series (and the C weight series 1/theta_c) in shared memory; a thread owns 2x2
+// entries of the lower triangle for ALL C output channels, forms each lag product once and scales it by the C weights
+// (4 + 2C FMA per entry-frame instead of 4C).  The right-hand side rides along as row L of the matrix (the Cholesky factor
+// of [[R, r], [r^H, .]] carries L^-1 r in its last row), so the forward substitution costs nothing extra; k_wpe_chol is a
+// right-looking panel Cholesky (panel in shared memory, trailing update on the L2-resident workspace) followed by a
+// panel-wise backward substitution.  First-round version: fp32 CUDA-core arithmetic; the tcgen05 contraction for k_wpe_corr
+// is the next step.
+#include "btkb_internal.h"
+#include <math.h>
+
+namespace btkb {
+namespace {
+
+constexpr int WPE_NB = 16;        // Cholesky panel width
+constexpr int WPE_CORR_THREADS = 256;
+constexpr int WPE_CHOL_THREADS = 256;
+
+template <typename RT> struct cx { RT x, y; };
+template <typename RT> __device__ __forceinline__ cx<RT> mk(RT x, RT y) { cx<RT> r; r.x = x; r.y = y; return r; }
+template <typename RT> __device__ __forceinline__ cx<RT> cmulc(cx<RT> a, cx<RT> b) { return mk<RT>(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y)); }  // a conj(b)
+template <typename RT> __device__ __forceinline__ void cmsubc(cx<RT>& s, cx<RT> a, cx<RT> b) {  // s -= a conj(b)
+  s.x = fma(-a.x, b.x, s.x); s.x = fma(-a.y, b.y, s.x); s.y = fma(-a.y, b.x, s.y); s.y = fma(a.x, b.y, s.y);
+}
+__device__ __forceinline__ void cmacf(float2& s, float2 a, float2 b) { s.x = fmaf(a.x, b.x, s.x); s.x = fmaf(-a.y, b.y, s.x); s.y = fmaf(a.x, b.y, s.y); s.y = fmaf(a.y, b.x, s.y); }
+
+// problem index q -> chain g = u*K + k, k over the estimated band 0..nbins-1 (dereverberation.cc:669: bins inside
+// (lower_bandWidthN_, upper_bandWidthN_) are skipped; of the bins the output stage reads, those are k > lower_bandWidthN_)
+__device__ __forceinline__ int problem_chain(const WpeArgs& a, int q) { const int u = q / a.nbins; return u * a.K + (q - u * a.nbins); }
+__device__ __forceinline__ int est_frames_of(const WpeArgs& a, int u) {
+  const int Tu = frames_of(a.lengths[u], a.D, a.laN, a.pdA);
+  return (a.est_frames >= 0) ? min(Tu, a.est_frames) : Tu;
+}
+
+__global__ void k_wpe_gather(WpeArgs a) {
+  __shared__ float2 tile[32][33];
+  const int c = blockIdx.y;
+  const int g0 = blockIdx.x * 32, t0 = blockIdx.z * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, g = g0 + threadIdx.x;
+    tile[j][threadIdx.x] = (t < a.T && g < a.G) ? a.X[((size_t)t * a.C + c) * a.Gp + g] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int g = g0 + j, t = t0 + threadIdx.x;
+    if (g < a.G && t < a.Ts) a.S[((size_t)g * a.C + c) * a.Ts + t] = (t < a.T) ? tile[threadIdx.x][j] : make_float2(0.f, 0.f);
+  }
+}
+
+// shared-memory series with P leading zeros: xs[c][P + t]
+__device__ __forceinline__ void load_series(const WpeArgs& a, int g, int nfr, float2* xs, int xstride) {
+  for (int i = threadIdx.x; i < a.C * xstride; i += blockDim.x) {
+    const int c = i / xstride, j = i - c * xstride, t = j - a.P;
+    xs[i] = (t >= 0 && t < nfr) ? a.S[((size_t)g * a.C + c) * a.Ts + t] : make_float2(0.f, 0.f);
+  }
+}
+template <typename RT>
+__device__ __forceinline__ void load_series_t(const WpeArgs& a, int g, int nfr, cx<RT>* xs, int xstride) {
+  for (int i = threadIdx.x; i < a.C * xstride; i += blockDim.x) {
+    const int c = i / xstride, j = i - c * xstride, t = j - a.P;
+    const float2 v = (t >= 0 && t < nfr) ? a.S[((size_t)g * a.C + c) * a.Ts + t] : make_float2(0.f, 0.f);
+    xs[i] = mk<RT>((RT)v.x, (RT)v.y);
+  }
+}
+
+// MODE 0: theta over the estimation frames; MODE 1: the output stage over every frame of the utterance (writes X in place)
+template <int MODE>
+__global__ void __launch_bounds__(128) k_wpe_resid(WpeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int g = (MODE == 0) ? problem_chain(a, blockIdx.x) : blockIdx.x;
+  if (g >= a.G) return;
+  const int u = g / a.K, k = g - u * a.K;
+  const int Tu = frames_of(a.lengths[u], a.D, a.laN, a.pdA);
+  const int nfr = (MODE == 0) ? est_frames_of(a, u) : Tu;
+  const bool in_band = k < a.nbins;
+  if (MODE == 1 && !in_band) return;  // X already holds the unprocessed value
+  const int xstride = a.P + a.T;
+  float2* xs = reinterpret_cast<float2*>(smem);
+  float2* Gs = xs + (size_t)a.C * xstride;   // conj(G) [C][L]
+  load_series(a, g, nfr, xs, xstride);
+  for (int i = threadIdx.x; i < a.C * a.L; i += blockDim.x) { const float2 v = a.Gf[(size_t)g * a.C * a.L + i]; Gs[i] = make_float2(v.x, -v.y); }
+  __syncthreads();
+  // the sliding buffer of the output stage holds P frames: lags beyond P-1-lower read as zero (dereverberation.cc:473-490)
+  const int lmax = (MODE == 1) ? min(a.P - 1, a.P - 1 - a.lowerN) : a.P - 1;
+  for (int idx = threadIdx.x; idx < a.C * nfr; idx += blockDim.x) {
+    const int c = idx / nfr, t = idx - c * nfr;
+    const float2 x = xs[c * xstride + a.P + t];
+    float2 acc = make_float2(0.f, 0.f);
+    if (t >= a.lowerN) {
+      const float2* gr = Gs + (size_t)c * a.L;
+      for (int cp = 0; cp < a.C; cp++) {
+        const float2* xr = xs + cp * xstride + a.P + t - a.lowerN;
+        const float2* gc = gr + cp * a.P;
+        for (int l = 0; l <= lmax; l++) cmacf(acc, gc[l], xr[-l]);
+      }
+    }
+    const float2 d = make_float2(x.x - acc.x, x.y - acc.y);
+    if (MODE == 0) {
+      float th = sqrtf(fmaf(d.x, d.x, d.y * d.y));
+      th = fmaxf(th, 1.0e-3f);  // subband_floor_ (dereverberation.cc:617)
+      a.TH[((size_t)g * a.C + c) * a.Ts + t] = th * th;
+    } else {
+      a.X[((size_t)t * a.C + c) * a.Gp + g] = d;
+    }
+  }
+}
+
+// R_c (lower triangle) and the augmented row L = conj(r_c) for the problems [q0, q0 + gridDim.y); blockIdx.x = split.
+// RT = double reproduces the reference's fp64 normal equations (light diagonal loading leaves lambda_min / lambda_max near
+// 1e-5, below what an fp32 running sum of T terms resolves); RT = float is the fast variant for well-loaded problems.
+template <int C, typename RT>
+__global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_corr(WpeArgs a, int q0) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typedef cx<RT> CX;
+  const int q = q0 + blockIdx.y;
+  const int g = problem_chain(a, q);
+  const int u = g / a.K;
+  const int nfr = est_frames_of(a, u);
+  const int xstride = a.P + a.T;
+  CX* xs = reinterpret_cast<CX*>(smem);
+  RT* ws = reinterpret_cast<RT*>(xs + (size_t)C * xstride);  // [T][C] weights 1/theta, 0 outside the estimation frames
+  load_series_t<RT>(a, g, nfr, xs, xstride);
+  for (int i = threadIdx.x; i < C * a.T; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    ws[i] = (t < nfr && t >= a.lowerN) ? (RT)1 / (RT)a.TH[((size_t)g * C + c) * a.Ts + t] : (RT)0;
+  }
+  __syncthreads();
+  const int L = a.L, P = a.P, Lr = a.Lr;
+  CX* Rq = reinterpret_cast<CX*>(a.Rw) + (size_t)blockIdx.y * C * (size_t)(L + 1) * Lr;
+  const int nS = max(nfr - a.lowerN, 0);   // s' = s - lower, s = lower .. nfr-1
+  const int L2 = (L + 1) / 2;
+  const int ntiles = L2 * (L2 + 1) / 2;
+  for (int tq = blockIdx.x * blockDim.x + threadIdx.x; tq < ntiles; tq += gridDim.x * blockDim.x) {
+    int bi = (int)((sqrtf(8.0f * (float)tq + 1.0f) - 1.0f) * 0.5f);
+    while ((bi + 1) * (bi + 2) / 2 <= tq) bi++;
+    while (bi * (bi + 1) / 2 > tq) bi--;
+    const int bj = tq - bi * (bi + 1) / 2;
+    const int i0 = 2 * bi, i1 = min(i0 + 1, L - 1), j0 = 2 * bj, j1 = min(j0 + 1, L - 1);
+    const CX* pi0 = xs + (i0 / P) * xstride + P - (i0 % P);
+    const CX* pi1 = xs + (i1 / P) * xstride + P - (i1 % P);
+    const CX* pj0 = xs + (j0 / P) * xstride + P - (j0 % P);
+    const CX* pj1 = xs + (j1 / P) * xstride + P - (j1 % P);
+    CX acc[4][C];
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int c = 0; c < C; c++) acc[e][c] = mk<RT>(0, 0);
+    for (int s = 0; s < nS; s++) {
+      const CX a0 = pi0[s], a1 = pi1[s], b0 = pj0[s], b1 = pj1[s];
+      const CX p00 = cmulc(a0, b0), p01 = cmulc(a0, b1), p10 = cmulc(a1, b0), p11 = cmulc(a1, b1);
+      const RT* w = ws + (size_t)(s + a.lowerN) * C;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const RT wc = w[c];
+        acc[0][c].x = fma(wc, p00.x, acc[0][c].x); acc[0][c].y = fma(wc, p00.y, acc[0][c].y);
+        acc[1][c].x = fma(wc, p01.x, acc[1][c].x); acc[1][c].y = fma(wc, p01.y, acc[1][c].y);
+        acc[2][c].x = fma(wc, p10.x, acc[2][c].x); acc[2][c].y = fma(wc, p10.y, acc[2][c].y);
+        acc[3][c].x = fma(wc, p11.x, acc[3][c].x); acc[3][c].y = fma(wc, p11.y, acc[3][c].y);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      CX* Rc = Rq + (size_t)c * (L + 1) * Lr;
+      Rc[(size_t)i0 * Lr + j0] = acc[0][c];
+      if (j0 + 1 < L && j0 + 1 <= i0) Rc[(size_t)i0 * Lr + j0 + 1] = acc[1][c];
+      if (i0 + 1 < L) {
+        Rc[(size_t)(i0 + 1) * Lr + j0] = acc[2][c];
+        if (j0 + 1 < L) Rc[(size_t)(i0 + 1) * Lr + j0 + 1] = acc[3][c];
+      }
+    }
+  }
+  // augmented row: A_c[L][j] = conj(r_c[j]) = sum_s x_c(s) conj(lags_j(s)) / theta_c(s)
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x) {
+    const CX* pj = xs + (j / P) * xstride + P - (j % P);
+    CX acc[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) acc[c] = mk<RT>(0, 0);
+    for (int s = 0; s < nS; s++) {
+      const CX b = pj[s];
+      const RT* w = ws + (size_t)(s + a.lowerN) * C;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const CX x = xs[c * xstride + P + s + a.lowerN];
+        const CX pr = cmulc(x, b);
+        acc[c].x = fma(w[c], pr.x, acc[c].x); acc[c].y = fma(w[c], pr.y, acc[c].y);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) Rq[((size_t)c * (L + 1) + L) * Lr + j] = acc[c];
+  }
+}
+
+// one CTA per (problem, channel): diagonal bias + loading, panel Cholesky of the augmented matrix, backward substitution
+template <typename RT>
+__global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0, int C) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typedef cx<RT> CX;
+  const int qq = blockIdx.x / C, c = blockIdx.x - qq * C;
+  const int g = problem_chain(a, q0 + qq);
+  const int L = a.L, Lr = a.Lr, n = L + 1;
+  CX* A = reinterpret_cast<CX*>(a.Rw) + ((size_t)qq * C + c) * (size_t)n * Lr;
+  CX* Pn = reinterpret_cast<CX*>(smem);                   // [n][WPE_NB] current panel (rows relative to j0)
+  CX* yv = Pn + (size_t)n * WPE_NB;                        // [L]
+  RT* red = reinterpret_cast<RT*>(yv + L);                 // [32]
+  const int tid = threadIdx.x;
+  const RT bias = (RT)a.diagonal_bias, loadf = (RT)a.load_factor;
+
+  // ---- diagonal: + diagonal_bias (calc_Rr_, :577-580), then |d| + max|d| load_factor (load_R_, :648-663)
+  RT mx = 0;
+  for (int i = tid; i < L; i += blockDim.x) {
+    CX d = A[(size_t)i * Lr + i];
+    d.x += bias;
+    mx = fmax(mx, sqrt(fma(d.x, d.x, d.y * d.y)));
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, red[w]);
+  for (int i = tid; i < L; i += blockDim.x) {
+    CX d = A[(size_t)i * Lr + i];
+    d.x += bias;
+    A[(size_t)i * Lr + i] = mk<RT>(sqrt(fma(d.x, d.x, d.y * d.y)) + mx * loadf, 0);
+  }
+  __syncthreads();
+
+  bool bad = false;
+  for (int j0 = 0; j0 < L; j0 += WPE_NB) {
+    const int nb = min(WPE_NB, L - j0);
+    const int nrows = n - j0;   // rows j0 .. L (the augmented row included)
+    // ---- load the panel
+    for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
+      const int r = i / WPE_NB, jj = i - r * WPE_NB;
+      Pn[i] = (jj < nb && jj <= r) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
+    }
+    // ---- factor it: column by column, one thread per row
+    for (int jj = 0; jj < nb; jj++) {
+      __syncthreads();   // the panel load / the previous column's row updates (incl. this pivot) are visible
+      const RT dj = Pn[jj * WPE_NB + jj].x;
+      if (!(dj > (RT)0)) bad = true;
+      const RT inv = (RT)1 / sqrt(fmax(dj, (RT)1e-30));
+      __syncthreads();   // everybody has read the pivot before its owner overwrites it
+      for (int r = tid; r < nrows; r += blockDim.x) {
+        if (r == jj) Pn[r * WPE_NB + jj] = mk<RT>(dj * inv, 0);
+        else if (r > jj) { CX v = Pn[r * WPE_NB + jj]; Pn[r * WPE_NB + jj] = mk<RT>(v.x * inv, v.y * inv); }
+      }
+      __syncthreads();
+      for (int r = tid; r < nrows; r += blockDim.x) {
+        if (r <= jj) continue;
+        const CX lij = Pn[r * WPE_NB + jj];
+        const int kend = min(nb - 1, r);
+        for (int kk = jj + 1; kk <= kend; kk++) {
+          CX v = Pn[r * WPE_NB + kk];
+          cmsubc(v, lij, Pn[kk * WPE_NB + jj]);
+          if (kk == r) v.y = 0;
+          Pn[r * WPE_NB + kk] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- write the factored panel back (needed by the backward substitution)
+    for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
+      const int r = i / WPE_NB, jj = i - r * WPE_NB;
+      if (jj < nb && jj <= r) A[(size_t)(j0 + r) * Lr + j0 + jj] = Pn[i];
+    }
+    // ---- trailing update: A[i][k] -= sum_jj Pn[i][jj] conj(Pn[k][jj]) for j1 <= k <= i <= L
+    const int j1 = j0 + nb;
+    const int nt = n - j1;             // trailing rows (incl. the augmented one)
+    if (nt > 0) {
+      const int nt2 = (nt + 1) / 2;
+      const int ntiles = nt2 * (nt2 + 1) / 2;
+      for (int tq = tid; tq < ntiles; tq += blockDim.x) {
+        int bi = (int)((sqrtf(8.0f * (float)tq + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= tq) bi++;
+        while (bi * (bi + 1) / 2 > tq) bi--;
+        const int bj = tq - bi * (bi + 1) / 2;
+        const int ri0 = 2 * bi, ri1 = min(ri0 + 1, nt - 1), rk0 = 2 * bj, rk1 = min(rk0 + 1, nt - 1);
+        const CX* pi0 = Pn + (size_t)(nb + ri0) * WPE_NB;
+        const CX* pi1 = Pn + (size_t)(nb + ri1) * WPE_NB;
+        const CX* pk0 = Pn + (size_t)(nb + rk0) * WPE_NB;
+        const CX* pk1 = Pn + (size_t)(nb + rk1) * WPE_NB;
+        CX s00 = mk<RT>(0, 0), s01 = s00, s10 = s00, s11 = s00;
+        for (int jj = 0; jj < nb; jj++) {
+          const CX a0 = pi0[jj], a1 = pi1[jj], b0 = pk0[jj], b1 = pk1[jj];
+          cmsubc(s00, a0, b0); cmsubc(s01, a0, b1); cmsubc(s10, a1, b0); cmsubc(s11, a1, b1);
+        }
+        const int i0 = j1 + ri0, k0 = j1 + rk0;
+        CX* r0 = A + (size_t)i0 * Lr + k0;
+        { CX v = r0[0]; v.x += s00.x; v.y += s00.y; r0[0] = v; }
+        if (rk0 + 1 < nt && rk0 + 1 <= ri0) { CX v = r0[1]; v.x += s01.x; v.y += s01.y; r0[1] = v; }
+        if (ri0 + 1 < nt) {
+          CX* r1 = r0 + Lr;
+          { CX v = r1[0]; v.x += s10.x; v.y += s10.y; r1[0] = v; }
+          if (rk0 + 1 < nt) { CX v = r1[1]; v.x += s11.x; v.y += s11.y; r1[1] = v; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (bad && tid == 0) atomicExch(a.err_flag, 1);
+
+  // ---- backward substitution L^H gvec = y, y_j = conj(A[L][j])
+  for (int j = tid; j < L; j += blockDim.x) { const CX v = A[(size_t)L * Lr + j]; yv[j] = mk<RT>(v.x, -v.y); }
+  __syncthreads();
+  CX* Db = Pn;  // [WPE_NB][WPE_NB] diagonal block
+  for (int j0 = ((L - 1) / WPE_NB) * WPE_NB; j0 >= 0; j0 -= WPE_NB) {
+    const int nb = min(WPE_NB, L - j0);
+    for (int i = tid; i < nb * WPE_NB; i += blockDim.x) {
+      const int r = i / WPE_NB, jj = i - r * WPE_NB;
+      Db[i] = (jj <= r && jj < nb) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int jj = nb - 1; jj >= 0; jj--) {
+        CX s = yv[j0 + jj];
+        for (int kk = jj + 1; kk < nb; kk++) cmsubc(s, yv[j0 + kk], Db[kk * WPE_NB + jj]);  // s -= g_kk conj(L[kk][jj])
+        const RT inv = (RT)1 / Db[jj * WPE_NB + jj].x;
+        yv[j0 + jj] = mk<RT>(s.x * inv, s.y * inv);
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < j0; k += blockDim.x) {   // y_k -= sum_i conj(L[i][k]) g_i over the panel rows
+      CX s = yv[k];
+      for (int r = 0; r < nb; r++) cmsubc(s, yv[j0 + r], A[(size_t)(j0 + r) * Lr + k]);
+      yv[k] = s;
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < L; j += blockDim.x) a.Gf[((size_t)g * C + c) * L + j] = make_float2((float)yv[j].x, (float)yv[j].y);
+}
+
+}  // namespace
+
+size_t wpe_workspace_bytes(int C, int L, int Lr, int chunk, int fp32) {
+  return (size_t)chunk * C * (size_t)(L + 1) * Lr * (fp32 ? sizeof(float2) : sizeof(double2));
+}
+
+template <typename RT>
+static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, int* launches) {
+  const int C = a.C;
+  cudaError_t e;
+  {
+    dim3 grid((a.G + 31) / 32, C, (a.Ts + 31) / 32), block(32, 8);
+    k_wpe_gather<<<grid, block, 0, st>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    (*launches)++;
+  }
+  e = cudaMemsetAsync(a.Gf, 0, (size_t)a.G * C * a.L * sizeof(float2), st);
+  if (e != cudaSuccess) return e;
+  const int xstride = a.P + a.T;
+  const size_t sm_resid = ((size_t)C * xstride + (size_t)C * a.L) * sizeof(float2);
+  const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (size_t)C * a.T * sizeof(RT);
+  const size_t sm_chol = ((size_t)(a.L + 1) * WPE_NB + a.L) * sizeof(cx<RT>) + 32 * sizeof(RT);
+  if (sm_resid > 200 * 1024 || sm_corr > 200 * 1024 || sm_chol > 200 * 1024) return cudaErrorInvalidValue;
+  if ((e = cudaFuncSetAttribute(k_wpe_resid<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_wpe_resid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_wpe_chol<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol)) != cudaSuccess) return e;
+  void (*corr)(WpeArgs, int) = nullptr;
+  switch (C) {
+    case 1: corr = k_wpe_corr<1, RT>; break;
+    case 2: corr = k_wpe_corr<2, RT>; break;
+    case 4: corr = k_wpe_corr<4, RT>; break;
+    case 8: corr = k_wpe_corr<8, RT>; break;
+    default: return cudaErrorInvalidValue;
+  }
+  if ((e = cudaFuncSetAttribute(corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_corr)) != cudaSuccess) return e;
+  const int nprob = a.U * a.nbins;
+  const int split = 8;
+  for (int it = 0; it < a.iterations; it++) {
+    k_wpe_resid<0><<<nprob, 128, sm_resid, st>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    (*launches)++;
+    for (int q0 = 0; q0 < nprob; q0 += chunk) {
+      const int nq = (nprob - q0 < chunk) ? nprob - q0 : chunk;
+      corr<<<dim3(split, nq), WPE_CORR_THREADS, sm_corr, st>>>(a, q0);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      k_wpe_chol<RT><<<nq * C, WPE_CHOL_THREADS, sm_chol, st>>>(a, q0, C);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      (*launches) += 2;
+    }
+  }
+  k_wpe_resid<1><<<a.G, 128, sm_resid, st>>>(a);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  (*launches)++;
+  return cudaSuccess;
+}
+
+cudaError_t launch_wpe(const WpeArgs& a, int chunk, int fp32, cudaStream_t st, int* launches) {
+  if (a.T <= 0 || a.G <= 0) return cudaSuccess;
+  if (!(a.C == 1 || a.C == 2 || a.C == 4 || a.C == 8)) return cudaErrorInvalidValue;
+  return fp32 ? launch_wpe_t<float>(a, chunk, st, launches) : launch_wpe_t<double>(a, chunk, st, launches);
+}
+
+}  // namespace btkb

@@ -65,6 +65,13 @@ typedef struct btkb_rls_params { /* defaults = unit_test/confs/gscrls.json / pyb
   int min_frames;
 } btkb_rls_params;
 
+typedef struct btkb_wpe_params { /* MultiChannelWPEDereverberation ctor (dereverberation.cc:312-334); defaults = unit_test/confs/wpe.json */
+  int enabled;         /* 1: btkb_run() dereverberates the snapshots between the analysis bank and the beamformer */
+  int lower_num, upper_num, iterations_num;
+  double load_db, band_width, diagonal_bias;
+  int fp32_normal_equations; /* 0 (default): R_c, r_c and the Cholesky solve in fp64 like the reference; 1: fp32 (faster, for well-loaded problems) */
+} btkb_wpe_params;
+
 typedef struct btkb_config {
   int device;                  /* CUDA device ordinal */
   int channels;                /* C >= 1 (GSC kinds need C >= 2) */
@@ -88,6 +95,7 @@ typedef struct btkb_config {
   double pf_min_sv;            /* Lefkimmiatis: singular-value floor of the coherence pseudo-inverse (default 1e-8) */
   int pf_fbin1;                /* Lefkimmiatis: first bin that divides the noise PSD by Lambda = d^H R^-1 d (default 0) */
   btkb_rls_params rls;         /* BTKB_BF_GSC_RLS */
+  btkb_wpe_params wpe;         /* multi-channel WPE dereverberation of the snapshots (C = 1, 2, 4 or 8) */
 } btkb_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */
@@ -149,6 +157,13 @@ int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float ene
  * Result readable with btkb_get_covariance.  Requires btkb_run_analysis. */
 int btkb_spectral_matrix_update(btkb_pipeline* p, float mu, int legacy_noconj);
 /* the per-bin beamformer (+ post-filter) over the resident snapshots, then synthesis when do_synthesis != 0 */
+/* MultiChannelWPEDereverberation::estimate_filter(start_frame_no, end_frame_no) (dereverberation.cc:405-431) followed by
+ * calc_every_channel_output for every frame (:441-497): the resident snapshots X are replaced by the dereverberated ones
+ * (read them with btkb_fetch_snapshots; the beamformer / synthesis stages then run on them).  end_frame_no < 0 = all frames.
+ * A non-positive Cholesky pivot reports BTKB_ERR_INVALID with the reference's jnumeric_error text (:676-678). */
+int btkb_run_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no);
+/* prediction filters Gn_ [U][K][C][L] complex64, L = C * (upper_num - lower_num + 1), channel-major then lag (zero outside the band) */
+int btkb_get_wpe_filter(btkb_pipeline* p, float* out);
 int btkb_run_beamformer(btkb_pipeline* p, int do_synthesis);
 /* inject beamformed subband frames from the host, Y [U][T][K] complex64 (the stream an arbitrary upstream
  * VectorComplexFeatureStream would deliver to OverSampledDFTSynthesisBank::next, modulated.cc:533-549), then
@@ -182,6 +197,8 @@ int btkb_get_postfilter_weights(btkb_pipeline* p, float* out); /* [U][T][K] floa
  * out[0] total, out[1] analysis, out[2] per-bin beamformer, out[3] synthesis, out[4] launches */
 int btkb_last_timing(btkb_pipeline* p, float* out5);
 /* device pointers for zero-copy consumers (torch tensors via from_dlpack / data_ptr): X, Y, time */
+/* device time (ms) of the last WPE pass (estimation + output stage) */
+int btkb_last_timing_wpe(btkb_pipeline* p, float* ms);
 int btkb_device_pointers(btkb_pipeline* p, void** X, void** Y, void** time_out);
 
 #ifdef __cplusplus

@@ -81,6 +81,23 @@ def synthesis(Y, g, M, m, r, dct=2):
     return out[:nb * D].copy()
 
 
+def wpe(X, lower_num=0, upper_num=32, iterations_num=2, load_db=-20.0, band_width=0.0, diagonal_bias=0.001, samplerate=16000.0,
+        start_frame_no=0, end_frame_no=-1):
+    """MultiChannelWPEDereverberation + MultiChannelWPEDereverberationFeature (dereverberation.cc:312-733) on snapshots
+    X[T][C][M] -> dereverberated X'[T][C][M]; returns (X', frames used for the estimation)."""
+    X = np.asarray(X, np.complex128)
+    T, C, M = X.shape
+    Xin = np.ascontiguousarray(np.transpose(X, (1, 0, 2)))
+    Xout = np.zeros_like(Xin)
+    L = lib()
+    L.ref_wpe.restype = ct.c_int
+    used = L.ref_wpe(_p(Xin, ct.c_double), ct.c_int(C), ct.c_int(T), ct.c_int(M), ct.c_int(lower_num), ct.c_int(upper_num), ct.c_int(iterations_num),
+                     ct.c_double(load_db), ct.c_double(band_width), ct.c_double(diagonal_bias), ct.c_double(samplerate),
+                     ct.c_int(start_frame_no), ct.c_int(end_frame_no), _p(Xout, ct.c_double))
+    assert used >= 0, "the reference raised an exception"
+    return np.ascontiguousarray(np.transpose(Xout, (1, 0, 2))), used
+
+
 def gsc_weights(M, C, samplerate, delays, want_B=True):
     delays = np.ascontiguousarray(delays, np.float64)
     wq = np.zeros((M, C), np.complex128)

@@ -30,6 +30,7 @@
 #include "modulated/modulated.h"
 #include "beamformer/beamformer.h"
 #include "postfilter/postfilter.h"
+#include "dereverberation/dereverberation.h"
 
 // declared in beamformer.cc (non-static helpers)
 gsl_matrix_complex* getBlockingMatrix(gsl_vector_complex* arrayManifold, int NC);
@@ -270,6 +271,33 @@ int ref_analysis(const float* samples, int n, const double* h, int M, int m, int
   }
   gsl_vector_free(hv);
   return T;
+}
+
+/* Multi-channel WPE (dereverberation/dereverberation.cc:312-733) wired as unit_test/test_subband_dereverberator.py:114-170:
+ * X_in [C][T][M] complex128 subband snapshots per channel -> X_out [C][T][M] dereverberated.  Returns frames used for the
+ * filter estimation (estimate_filter's return value), or -1 on a reference exception. */
+int ref_wpe(const double* X_in, int C, int T, int M, int lowerN, int upperN, int iterationsN, double loadDb, double bandWidth, double diagonal_bias,
+            double samplerate, int start_frame, int end_frame, double* X_out) {
+  int used = -1;
+  try {
+    MultiChannelWPEDereverberationPtr wpe = new MultiChannelWPEDereverberation(M, C, lowerN, upperN, iterationsN, loadDb, bandWidth, diagonal_bias, samplerate);
+    for (int c = 0; c < C; c++) {
+      VectorComplexFeatureStreamPtr src = new ArrayComplexSource(X_in + (size_t)2 * c * T * M, T, M);
+      wpe->set_input(src);
+    }
+    used = (int)wpe->estimate_filter(start_frame, end_frame);
+    std::vector<MultiChannelWPEDereverberationFeaturePtr> feats;
+    for (int c = 0; c < C; c++) feats.push_back(new MultiChannelWPEDereverberationFeature(wpe, c, 0));
+    for (int t = 0; t < T; t++)
+      for (int c = 0; c < C; c++) {
+        const gsl_vector_complex* v = feats[c]->next();
+        memcpy(X_out + (size_t)2 * ((size_t)c * T + t) * M, v->data, sizeof(double) * 2 * M);
+      }
+  } catch (std::exception& e) {
+    fprintf(stderr, "ref_wpe: %s\n", e.what());
+    return -1;
+  }
+  return used;
 }
 
 /* synthesis only: Y[T][M] complex128 -> out blocks of D floats; returns number of blocks */

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Golden vectors of the multi-channel WPE dereverberator from the REFERENCE's own C++ (dereverberation/dereverberation.cc,
+compiled unmodified into oracle/_ref/libbtkref.so), wired as unit_test/test_subband_dereverberator.py:114-170: analysis-bank
+snapshots in, MultiChannelWPEDereverberation::estimate_filter, MultiChannelWPEDereverberationFeature::next per channel out.
+Stored: the input samples and X'[T][C][0..M/2].
+
+  golden_wpe_c4_m256.npz   4 mics, M = 256: (a) lower 0 / upper 5 / 2 iterations / load -18 dB / bias 1e-4 (confs/wpe.json with a
+                           shorter filter), (b) lower 2 / upper 8 / 3 iterations / -20 dB / band_width 3000 Hz, estimation on
+                           estimate_filter(2, 42), (c) lower 1 / upper 5 / 2 iterations / load -40 dB (light loading: large filters)
+  golden_wpe_c8_m512.npz   8 mics, M = 512, lower 1 / upper 8 (L = 64), 2 iterations, load -35 dB
+
+Usage: python tests/golden/make_golden_wpe.py
+"""
+import os, sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref  # noqa: E402
+from distant_speech_recognition_b200 import synthetic  # noqa: E402
+from make_golden import proto, save  # noqa: E402
+
+
+def reverberant(u, C, n, seed):
+    """make_utterance + a decaying multi-tap tail per channel, so that the linear prediction has something to remove."""
+    x, d, mpos, _ = synthetic.make_utterance(u, C, n, target_start_s=0.05)
+    rng = np.random.default_rng(seed)
+    y = x.astype(np.float64).copy()
+    for c in range(C):
+        for tap in range(1, 7):
+            dl = 300 * tap + int(rng.integers(0, 120))
+            y[c, dl:] += (0.55 ** tap) * rng.choice([-1.0, 1.0]) * x[c, :-dl]
+    return y.astype(np.float32)
+
+
+def main():
+    M = 256; K = M // 2 + 1; h, _ = proto(M)
+    x = reverberant(6, 4, 8000, 1)
+    X = np.stack([ref.analysis(x[c], h, M, 4, 1) for c in range(4)], axis=1)
+    ka = dict(lower_num=0, upper_num=5, iterations_num=2, load_db=-18.0, band_width=0.0, diagonal_bias=1e-4)
+    kb = dict(lower_num=2, upper_num=8, iterations_num=3, load_db=-20.0, band_width=3000.0, diagonal_bias=1e-3, start_frame_no=2, end_frame_no=42)
+    kc = dict(lower_num=1, upper_num=5, iterations_num=2, load_db=-40.0, band_width=0.0, diagonal_bias=1e-4)
+    Xa, ua = ref.wpe(X, **ka)
+    Xb, ub = ref.wpe(X, **kb)
+    Xc, uc = ref.wpe(X, **kc)
+    save("wpe_c4_m256", x=x, Xa=Xa[:, :, :K], Xb=Xb[:, :, :K], Xc=Xc[:, :, :K], used_a=ua, used_b=ub)
+
+    M = 512; K = M // 2 + 1; h, _ = proto(M)
+    x = reverberant(7, 8, 12000, 2)
+    X = np.stack([ref.analysis(x[c], h, M, 4, 1) for c in range(8)], axis=1)
+    Xa, ua = ref.wpe(X, lower_num=1, upper_num=8, iterations_num=2, load_db=-35.0, band_width=0.0, diagonal_bias=1e-4)
+    save("wpe_c8_m512", x=x, Xa=Xa[:, :, :K], used_a=ua)
+
+
+if __name__ == "__main__":
+    main()

@@ -211,6 +211,29 @@ def test_reference_python_runs_live_when_present(protos):
     assert rel_l2(Yo, Y) < 1e-12 and no == nu
 
 
+WPE_A = dict(lower_num=0, upper_num=5, iterations_num=2, load_db=-18.0, band_width=0.0, diagonal_bias=1e-4)
+WPE_B = dict(lower_num=2, upper_num=8, iterations_num=3, load_db=-20.0, band_width=3000.0, diagonal_bias=1e-3, start_frame_no=2, end_frame_no=42)
+WPE_C = dict(lower_num=1, upper_num=5, iterations_num=2, load_db=-40.0, band_width=0.0, diagonal_bias=1e-4)
+WPE_8 = dict(lower_num=1, upper_num=8, iterations_num=2, load_db=-35.0, band_width=0.0, diagonal_bias=1e-4)
+
+
+def test_wpe_golden(protos):
+    """MultiChannelWPEDereverberation (dereverberation.cc:312-733): restatement vs the compiled reference's output, incl. the
+    output stage's truncated lag window (lower_num > 0), band_width and estimate_filter(start, end)."""
+    g = load_golden("wpe_c4_m256"); h, _ = protos[256]
+    X = _X(g["x"], h, 256)
+    for tag, kw in (("a", WPE_A), ("b", WPE_B), ("c", WPE_C)):
+        Xo, G, used = restate.wpe(X, samplerate=FS, **kw)
+        assert rel_l2(Xo[:, :, :129], g["X" + tag]) < 1e-11, tag
+        assert np.allclose(Xo[:, :, 129:], np.conj(Xo[:, :, 1:128][:, :, ::-1]))
+    assert used == 67 and int(g["used_b"]) == 40
+    assert rel_l2(g["Xb"], X[:, :, :129]) > 0.1 and rel_l2(g["Xc"], X[:, :, :129]) > 0.03   # the filters really remove something
+    g = load_golden("wpe_c8_m512"); h, _ = protos[512]
+    X = _X(g["x"], h, 512)
+    Xo, G, used = restate.wpe(X, samplerate=FS, **WPE_8)
+    assert rel_l2(Xo[:, :, :257], g["Xa"]) < 1e-11
+
+
 def test_pseudoinverse_golden():
     g = load_golden("pseudoinverse")
     for A, inv in zip(g["A"], g["inv"]):

@@ -266,6 +266,62 @@ def test_gsc_rls_long_utterance_vs_fp64_oracle(capi, protos):
     assert rel_l2(p.fetch_time()[0], restate.synthesis(Yo, gq, M, 4, 1)) < TOL
 
 
+def test_wpe_golden(capi, protos):
+    """Multi-channel WPE (dereverberation.cc:312-733) between analysis and beamformer: dereverberated snapshots vs the
+    compiled reference's output (tests/golden/make_golden_wpe.py)."""
+    from test_oracle import WPE_A, WPE_B, WPE_C, WPE_8
+    g = load_golden("wpe_c4_m256")
+    x = g["x"]
+    for tag, kw in (("a", WPE_A), ("b", WPE_B), ("c", WPE_C)):
+        kw = dict(kw)
+        start, end = kw.pop("start_frame_no", 0), kw.pop("end_frame_no", -1)
+        p = _pipe(capi, 4, 256, protos, n=x.shape[1], beamformer=capi.BF_DS, wpe=kw)
+        p.submit(x[None])
+        p.run_analysis()
+        p.run_wpe(start, end)
+        Xd = np.transpose(p.fetch_snapshots()[0], (0, 1, 2))   # [T][C][K]
+        assert rel_l2(Xd, g["X" + tag]) < TOL, tag
+        assert p.last_timing_wpe() > 0
+        p.close()
+    g = load_golden("wpe_c8_m512")
+    x = g["x"]
+    p = _pipe(capi, 8, 512, protos, n=x.shape[1], beamformer=capi.BF_DS, wpe=dict(WPE_8))
+    p.submit(x[None]); p.run_analysis(); p.run_wpe()
+    assert rel_l2(p.fetch_snapshots()[0], g["Xa"]) < TOL
+    p.close()
+
+
+def test_wpe_chain_batched_vs_oracle(capi, protos):
+    """configs[4] chain at small size: ragged batch -> analysis -> WPE -> GSC NLMS -> synthesis in one btkb_run, vs the fp64
+    restatement utterance by utterance; also the filters themselves."""
+    from oracle import restate
+    from distant_speech_recognition_b200 import synthetic
+    M, C, U, n = 256, 4, 3, 7000
+    K = M // 2 + 1
+    h, gq = protos[M]
+    X, dl = synthetic.make_batch(U, C, n, first=40)
+    lengths = np.array([n, n - 900, n - 3000], np.int32)
+    wpe = dict(lower_num=1, upper_num=6, iterations_num=2, load_db=-30.0, band_width=0.0, diagonal_bias=1e-4)
+    lms = dict(min_frames=5)
+    p = _pipe(capi, C, M, protos, U=U, n=n, beamformer=capi.BF_GSC_LMS, lms=lms, wpe=wpe)
+    p.set_delays(dl)
+    p.submit(X, lengths)
+    p.run(True)
+    Y = p.fetch_subband(); tm = p.fetch_time(); Gd = p.get_wpe_filter(); Xd = p.fetch_snapshots()
+    for u in range(U):
+        xu = X[u][:, : lengths[u]]
+        Xs = np.stack([restate.analysis(xu[c], h, M, 4, 1) for c in range(C)], axis=1)
+        Xw, G, used = restate.wpe(Xs, samplerate=FS, **wpe)
+        T = Xs.shape[0]
+        assert rel_l2(Xd[u][:T], Xw[:, :, :K]) < TOL, u
+        assert rel_l2(Gd[u], np.transpose(G, (1, 0, 2))) < 1e-3, u
+        Yo, _, _ = restate.gsc_lms(Xw, FS, dl[u], **lms)
+        assert rel_l2(Y[u][:T], Yo[:, :K]) < TOL, u
+        to = restate.synthesis(Yo, gq, M, 4, 1)
+        assert rel_l2(tm[u][: len(to)], to) < TOL, u
+    p.close()
+
+
 def test_batch_ragged_lengths_match_single_runs(capi, protos):
     """Utterances are independent units: a ragged batch must reproduce each utterance run alone (and the oracle)."""
     from distant_speech_recognition_b200 import synthetic
