@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libbtkb.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "btkb.h")
 
 BF_DS, BF_GSC, BF_MVDR, BF_GSC_LMS, BF_GSC_RLS = 0, 1, 2, 3, 4
+SOS_BMVDR, SOS_GEV = 0, 1
 PF_NONE, PF_ZELINSKI, PF_MCCOWAN, PF_LEFKIMMIATIS = 0, 1, 2, 3
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
 
@@ -268,6 +269,36 @@ class Pipeline:
             self._labels = np.ascontiguousarray(labels, np.float64)
             lp = _dp(self._labels)
         _check(lib.btkb_accumulate_covariance(self._h, lp, ct.c_float(energy_threshold)))
+
+    # ---- SOS batch beamformers: blind MVDR / GEV (lib/pybeamformer.py:1026-1357)
+    def sos_reset_stats(self):
+        _check(lib.btkb_sos_reset_stats(self._h))
+
+    def sos_accumulate_from_label(self, labels, energy_threshold=10.0):
+        """labels [U][NL][2] (or [NL][2] for one utterance): target segments in seconds."""
+        lab = np.ascontiguousarray(labels, np.float64)
+        if lab.ndim == 2:
+            lab = lab[None]
+        assert lab.ndim == 3 and lab.shape[2] == 2 and lab.shape[0] == self.U
+        _check(lib.btkb_sos_accumulate_from_label(self._h, _dp(lab), ct.c_int(lab.shape[1]), ct.c_float(energy_threshold)))
+
+    def sos_accumulate_from_tfmask(self, mask_t, mask_j, energy_threshold=10.0):
+        """mask_t, mask_j [U][Tm][K] (or [Tm][K] for one utterance)."""
+        mt = np.ascontiguousarray(mask_t, np.float32); mj = np.ascontiguousarray(mask_j, np.float32)
+        if mt.ndim == 2:
+            mt, mj = mt[None], mj[None]
+        assert mt.shape == mj.shape and mt.shape[0] == self.U and mt.shape[2] == self.K
+        _check(lib.btkb_sos_accumulate_from_tfmask(self._h, _fp(mt), _fp(mj), ct.c_int(mt.shape[1]), ct.c_float(energy_threshold)))
+
+    def sos_calc_weights(self, kind, gamma=1e-6, ref_micx=0, offset=0.0):
+        _check(lib.btkb_sos_calc_weights(self._h, ct.c_int(kind), ct.c_double(gamma), ct.c_int(ref_micx), ct.c_double(offset)))
+
+    def sos_get_stats(self):
+        """(Rt, Rn complex128 [U][K][C][C] raw sums, counts float64 [U][K][2])."""
+        Rt = np.empty((self.U, self.K, self.C, self.C), np.complex128); Rn = np.empty_like(Rt)
+        cnt = np.empty((self.U, self.K, 2), np.float64)
+        _check(lib.btkb_sos_get_stats(self._h, Rt.ctypes.data_as(ct.POINTER(ct.c_double)), Rn.ctypes.data_as(ct.POINTER(ct.c_double)), _dp(cnt)))
+        return Rt, Rn, cnt
 
     def synchronize(self):
         _check(lib.btkb_synchronize(self._h))

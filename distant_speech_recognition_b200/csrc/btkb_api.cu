@@ -43,6 +43,9 @@ struct btkb_pipeline {
   float2 *d_wS = nullptr, *d_wG = nullptr; void* d_wR = nullptr; float* d_wTH = nullptr; int* d_werr = nullptr;
   int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_Ts = 0, wpe_nbins = 0; bool have_wpe = false;
   cudaEvent_t wev[2] = {nullptr, nullptr};
+  // SOS batch beamformers (lazily allocated by the first btkb_sos_accumulate_*)
+  double2 *d_sosR = nullptr, *d_sosWd = nullptr; double* d_sosCnt = nullptr; float *d_sosWtu = nullptr, *d_sosMask = nullptr; double* d_sosLab = nullptr;
+  int* d_sosErr = nullptr; int sos_NLcap = 0; bool have_sos = false;
   bool have_pfR = false, pf_applied = false;  // pf_applied: d_Y came out of this pipeline's post-filter (not btkb_set_subband)
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
@@ -94,7 +97,8 @@ void btkb_destroy(btkb_pipeline* p) {
   cudaSetDevice(p->cfg.device);
   void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
                   p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
-                  p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM, p->d_wS, p->d_wG, p->d_wR, p->d_wTH, p->d_werr};
+                  p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM, p->d_wS, p->d_wG, p->d_wR, p->d_wTH, p->d_werr,
+                  p->d_sosR, p->d_sosWd, p->d_sosCnt, p->d_sosWtu, p->d_sosMask, p->d_sosLab, p->d_sosErr};
   if (p->h_delays) cudaFreeHost(p->h_delays);
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -602,6 +606,140 @@ int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float ene
   if (labels) CK(cudaStreamSynchronize(p->stream));
   p->have_R = true; p->R_is_sum = true;
   p->wU = p->U;
+  return BTKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- SOS batch beamformers
+static int ensure_scratch(btkb_pipeline* p, size_t bytes);
+static int sos_check(btkb_pipeline* p, const char* who, bool need_X) {
+  if (!p) return fail(BTKB_ERR_INVALID, std::string(who) + ": null pipeline");
+  if (p->cfg.beamformer != BTKB_BF_DS) return fail(BTKB_ERR_STATE, std::string(who) + ": the SOS beamformers apply their weights like SubbandDS; create the pipeline with BTKB_BF_DS");
+  if (!(p->C == 2 || p->C == 4 || p->C == 8)) return fail(BTKB_ERR_INVALID, std::string(who) + ": built for 2, 4 or 8 channels");
+  if (need_X && !p->have_X) return fail(BTKB_ERR_STATE, std::string(who) + ": run the analysis first");
+  return BTKB_OK;
+}
+static int sos_alloc(btkb_pipeline* p) {
+  if (p->d_sosR) return BTKB_OK;
+  const size_t G = (size_t)p->Gpcap;
+  CK(cudaMalloc((void**)&p->d_sosR, 2 * (size_t)p->C * p->C * G * sizeof(double2)));
+  CK(cudaMalloc((void**)&p->d_sosWd, (size_t)p->C * G * sizeof(double2)));
+  CK(cudaMalloc((void**)&p->d_sosCnt, 2 * G * sizeof(double)));
+  CK(cudaMalloc((void**)&p->d_sosWtu, 2 * (size_t)p->Tcap * p->Ucap * sizeof(float)));
+  CK(cudaMalloc((void**)&p->d_sosErr, sizeof(int)));
+  return BTKB_OK;
+}
+static SosArgs sos_args(btkb_pipeline* p) {
+  SosArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = p->d_X; a.E = p->d_E; a.lengths = p->d_len; a.wtu = p->d_sosWtu; a.Rs = p->d_sosR; a.cnt = p->d_sosCnt; a.Wd = p->d_sosWd; a.W = p->d_W; a.err = p->d_sosErr;
+  a.accumulate = p->have_sos ? 1 : 0;
+  a.U = p->U; a.C = p->C; a.T = p->T; a.K = p->K; a.G = p->U * p->K; a.Gp = p->Gp; a.D = p->D; a.laN = p->laN; a.pdA = p->pdA;
+  a.samplerate = p->cfg.samplerate;
+  return a;
+}
+
+int btkb_sos_reset_stats(btkb_pipeline* p) {
+  int rc = sos_check(p, "btkb_sos_reset_stats", false); if (rc) return rc;
+  p->have_sos = false;
+  return BTKB_OK;
+}
+
+int btkb_sos_accumulate_from_label(btkb_pipeline* p, const double* labels, int NL, float energy_threshold) {
+  int rc = sos_check(p, "btkb_sos_accumulate_from_label", true); if (rc) return rc;
+  if (!labels || NL < 1) return fail(BTKB_ERR_INVALID, "btkb_sos_accumulate_from_label: need at least one (start, end) segment per utterance");
+  CK(cudaSetDevice(p->cfg.device));
+  rc = sos_alloc(p); if (rc) return rc;
+  if (NL > p->sos_NLcap) {
+    if (p->d_sosLab) { CK(cudaStreamSynchronize(p->stream)); cudaFree(p->d_sosLab); p->d_sosLab = nullptr; }
+    CK(cudaMalloc((void**)&p->d_sosLab, (size_t)p->Ucap * NL * 2 * sizeof(double)));
+    p->sos_NLcap = NL;
+  }
+  CK(cudaMemcpyAsync(p->d_sosLab, labels, (size_t)p->U * NL * 2 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  SosArgs a = sos_args(p);
+  a.labels = p->d_sosLab; a.NL = NL; a.thr = energy_threshold;
+  CK(launch_sos_accumulate(a, p->stream, &p->launches));
+  CK(cudaStreamSynchronize(p->stream));   // `labels` may be pageable host memory
+  p->have_sos = true; p->wU = p->U;
+  return BTKB_OK;
+}
+
+int btkb_sos_accumulate_from_tfmask(btkb_pipeline* p, const float* mask_t, const float* mask_j, int Tm, float energy_threshold) {
+  int rc = sos_check(p, "btkb_sos_accumulate_from_tfmask", true); if (rc) return rc;
+  if (!mask_t || !mask_j) return fail(BTKB_ERR_INVALID, "btkb_sos_accumulate_from_tfmask: null mask");
+  if (Tm < p->T) return fail(BTKB_ERR_INVALID, "btkb_sos_accumulate_from_tfmask: the masks have " + std::to_string(Tm) + " frames, the batch has " + std::to_string(p->T) + " (the reference raises IndexError)");
+  CK(cudaSetDevice(p->cfg.device));
+  rc = sos_alloc(p); if (rc) return rc;
+  if (!p->d_sosMask) CK(cudaMalloc((void**)&p->d_sosMask, 2 * (size_t)p->Tcap * p->Gpcap * sizeof(float)));
+  const size_t raw = (size_t)p->U * Tm * p->K * sizeof(float);
+  rc = ensure_scratch(p, raw); if (rc) return rc;
+  float* mt = p->d_sosMask; float* mj = p->d_sosMask + (size_t)p->Tcap * p->Gpcap;
+  CK(cudaMemcpyAsync(p->d_scratch, mask_t, raw, cudaMemcpyHostToDevice, p->stream));
+  CK(launch_sos_scatter_mask((const float*)p->d_scratch, mt, p->U, Tm, p->T, p->K, p->Gp, p->stream));
+  CK(cudaMemcpyAsync(p->d_scratch, mask_j, raw, cudaMemcpyHostToDevice, p->stream));
+  CK(launch_sos_scatter_mask((const float*)p->d_scratch, mj, p->U, Tm, p->T, p->K, p->Gp, p->stream));
+  p->launches += 2;
+  SosArgs a = sos_args(p);
+  a.mask_t = mt; a.mask_j = mj; a.thr = energy_threshold;
+  CK(launch_sos_accumulate(a, p->stream, &p->launches));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_sos = true; p->wU = p->U;
+  return BTKB_OK;
+}
+
+int btkb_sos_calc_weights(btkb_pipeline* p, int kind, double gamma, int ref_micx, double offset) {
+  int rc = sos_check(p, "btkb_sos_calc_weights", false); if (rc) return rc;
+  if (kind != BTKB_SOS_BMVDR && kind != BTKB_SOS_GEV) return fail(BTKB_ERR_INVALID, "btkb_sos_calc_weights: unknown kind");
+  if (!p->have_sos) return fail(BTKB_ERR_STATE, kind == BTKB_SOS_BMVDR ? "No target signal SOS" : "No target signal SOS");   // pybeamformer.py:1270-1273
+  if (ref_micx < 0 || ref_micx >= p->C) return fail(BTKB_ERR_INVALID, "btkb_sos_calc_weights: ref_micx out of range");
+  if (!(offset >= 0.0 && offset <= 1.0)) return fail(BTKB_ERR_INVALID, "The offset value " + std::to_string(offset) + " is out of [0, 1]");   // :1274
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemsetAsync(p->d_sosErr, 0, sizeof(int), p->stream));
+  SosArgs a = sos_args(p);
+  CK(launch_sos_solve(a, kind, gamma, ref_micx, offset, p->stream, &p->launches));
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, p->d_sosErr, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  if (err & 1) return fail(BTKB_ERR_STATE, "No target signal stats accumulated; Use self.accu_stats_from_label() or accu_stats_from_tfmask()");   // :1264, 1316
+  if (err & 2) return fail(BTKB_ERR_STATE, "No noise stats accumulated; Use self.accu_stats_from_label() or accu_stats_from_tfmask()");
+  if (err & 4) return fail(BTKB_ERR_INVALID, kind == BTKB_SOS_BMVDR ? "Matrix inversion failed\nAdd a small value to the diagonal component of the covariance matrix"
+                                                                   : "GEV failed\nAdd a small value to the diagonal component of the covariance matrix");
+  p->have_w = true;
+  if (!p->have_ta) {  // the time-alignment manifold is only used by post-filters; without delays it is the weight itself (as btkb_set_weights)
+    CK(cudaMemcpyAsync(p->d_TA, p->d_W, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
+    p->have_ta = true;
+  }
+  return BTKB_OK;
+}
+
+int btkb_sos_get_stats(btkb_pipeline* p, double* Rt, double* Rn, double* counts) {
+  int rc = sos_check(p, "btkb_sos_get_stats", false); if (rc) return rc;
+  if (!p->have_sos) return fail(BTKB_ERR_STATE, "btkb_sos_get_stats: no statistics accumulated");
+  CK(cudaSetDevice(p->cfg.device));
+  const int U = p->U, K = p->K, C = p->C, Gp = p->Gp;
+  std::vector<double2> tmp((size_t)C * C * Gp);
+  for (int set = 0; set < 2; set++) {
+    double* dst = set == 0 ? Rt : Rn;
+    if (!dst) continue;
+    CK(cudaMemcpyAsync(tmp.data(), p->d_sosR + (size_t)set * C * C * Gp, tmp.size() * sizeof(double2), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int u = 0; u < U; u++)
+      for (int k = 0; k < K; k++)
+        for (int e = 0; e < C * C; e++) {
+          const double2 v = tmp[(size_t)e * Gp + (size_t)u * K + k];
+          double* d = dst + 2 * (((size_t)u * K + k) * C * C + e);
+          d[0] = v.x; d[1] = v.y;
+        }
+  }
+  if (counts) {
+    std::vector<double> c2((size_t)2 * Gp);
+    CK(cudaMemcpyAsync(c2.data(), p->d_sosCnt, c2.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int u = 0; u < U; u++)
+      for (int k = 0; k < K; k++) {
+        counts[2 * ((size_t)u * K + k)] = c2[(size_t)u * K + k];
+        counts[2 * ((size_t)u * K + k) + 1] = c2[(size_t)Gp + (size_t)u * K + k];
+      }
+  }
   return BTKB_OK;
 }
 

@@ -81,6 +81,25 @@ struct WpeArgs {
 size_t wpe_workspace_bytes(int C, int L, int Lr, int chunk, int fp32);
 cudaError_t launch_wpe(const WpeArgs& a, int chunk, int fp32, cudaStream_t st, int* launches);
 
+// SOS batch beamformers (btkb_sos.cu)
+struct SosArgs {
+  const float2* X; const float* E; const int* lengths;
+  const double* labels; int NL;        // [U][NL][2] VAD segments in seconds (null: TF-mask mode)
+  const float* mask_t; const float* mask_j;   // [T][Gp] masks in device layout (null: label mode)
+  float* wtu;                          // [2][T][U] frame weights: target / noise class x energy gate
+  double2* Rs;                         // [2][C*C][Gp] target / noise covariance sums (row-major i*C+j)
+  double* cnt;                         // [2][Gp] frame counts
+  double2* Wd;                         // [C][Gp] fp64 weights before the GEV phase alignment
+  float2* W;                           // [C][Gp] beamformer weights (y = W^H x)
+  int* err;                            // error bits (see k_sos_solve)
+  int accumulate;                      // add to the statistics already there (accu_stats_* called again, :1113-1127)
+  int U, C, T, K, G, Gp, D, laN, pdA;
+  float samplerate, thr;
+};
+cudaError_t launch_sos_scatter_mask(const float* src, float* dst, int U, int Tm, int T, int K, int Gp, cudaStream_t st);
+cudaError_t launch_sos_accumulate(const SosArgs& a, cudaStream_t st, int* launches);
+cudaError_t launch_sos_solve(const SosArgs& a, int kind, double gamma, int ref_micx, double offset, cudaStream_t st, int* launches);
+
 struct WeightsArgs {
   const double* delays;  // [U][C]
   float2* W;             // [C][Gp]

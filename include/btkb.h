@@ -192,6 +192,31 @@ int btkb_get_active_weights(btkb_pipeline* p, float* out);     /* [U][K][C-1] co
 int btkb_get_covariance(btkb_pipeline* p, float* out);         /* [U][K][C][C] complex64 */
 int btkb_get_postfilter_weights(btkb_pipeline* p, float* out); /* [U][T][K] float32 post-filter gains (wp1_) */
 
+/* ---- second-order-statistics batch beamformers: blind MVDR (MMSE) and GEV ------------------------------------------
+ * SubbandBlindMVDRBeamformer / SubbandGEVBeamformer (lib/pybeamformer.py:1026-1357; driver unit_test/test_sos_batch_beamforming.py:
+ * 186-233).  Use a BTKB_BF_DS pipeline with C = 2, 4 or 8: after btkb_run_analysis the statistics are accumulated per
+ * (utterance, bin) on the device, btkb_sos_calc_weights writes the beamformer weights (y = w^H x for every bin incl. DC, the
+ * reference's wqH = conj(w), pybeamformer.py:1191-1207) and btkb_run_beamformer applies them. */
+#define BTKB_SOS_BMVDR 0   /* w = Rn^-1 Rt u_ref / (offset + tr(Rn^-1 Rt))                       (pybeamformer.py:1257-1295) */
+#define BTKB_SOS_GEV 1     /* principal generalised eigenvector of (Rt, Rn), v^H Rn v = 1, phase-aligned bin to bin (:1311-1357).
+                            * scipy.linalg.eigh leaves the eigenvector's phase to LAPACK; here (first Cholesky column of Rn)^H v is
+                            * real POSITIVE at bin 0, so results equal the reference's up to one global sign per utterance. */
+/* SubbandSOSBatchBeamformer.reset_stats (:1209-1213) */
+int btkb_sos_reset_stats(btkb_pipeline* p);
+/* accu_stats_from_label (:1063-1127): labels [U][NL][2] = NL (start, end) target segments per utterance in seconds, walked
+ * with the reference's running elapsed time and segment cursor (an open end < 0 only works for a segment that starts at 0);
+ * frames with channel-0 energy <= energy_threshold are skipped.  Adds to the statistics already accumulated. */
+int btkb_sos_accumulate_from_label(btkb_pipeline* p, const double* labels, int NL, float energy_threshold);
+/* accu_stats_from_tfmask (:1129-1183): masks float32 [U][Tm][K], Tm >= frames of every utterance (the reference raises
+ * IndexError otherwise); values <= 0 are ignored; counts follow the reference's integer-array truncation. */
+int btkb_sos_accumulate_from_tfmask(btkb_pipeline* p, const float* mask_t, const float* mask_j, int Tm, float energy_threshold);
+/* finalize_stats(gamma) + calc_beamformer_weights(ref_micx, offset) for kind = BTKB_SOS_BMVDR / BTKB_SOS_GEV.  BTKB_ERR_STATE when
+ * a bin has no target / noise statistics (the reference's assertion), BTKB_ERR_INVALID when a factorisation fails
+ * ("Matrix inversion failed" / "GEV failed", :1286-1287, 1336-1337). */
+int btkb_sos_calc_weights(btkb_pipeline* p, int kind, double gamma, int ref_micx, double offset);
+/* raw statistics: Rt, Rn complex128 [U][K][C][C] sums (not normalised), counts float64 [U][K][2] (target, noise); NULLs are skipped */
+int btkb_sos_get_stats(btkb_pipeline* p, double* Rt, double* Rn, double* counts);
+
 /* ---- measurement -------------------------------------------------------------------------------------------- */
 /* device time (ms, CUDA events on the pipeline stream) of the last run: total and per kernel
  * out[0] total, out[1] analysis, out[2] per-bin beamformer, out[3] synthesis, out[4] launches */

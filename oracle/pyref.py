@@ -2,11 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY (build container; /root/reference does not exist on the GPU box).  The reference module is
 Python 2 (print statements, numpy.complex) and star-imports the SWIG modules btk20.*, which cannot be built here.  This
-loader reads the source text where it lies, applies three mechanical Python-2 -> 3 token fixes IN MEMORY (nothing is
+loader reads the source text where it lies, applies three kinds of mechanical Python-2 -> 3 token fixes IN MEMORY (nothing is
 copied into the repo):
 
     print <expr>            ->  print(<expr>)
-    numpy.complex / .float  ->  complex / float
+    numpy.complex / .float / .int  ->  complex / float / int
     raise StopIteration     ->  return            (PEP 479, inside generators)
 
 (the file is executed up to, not including, `class SubbandHOSBatchBeamformer`, whose section uses Python-2-only tuple
@@ -89,6 +89,7 @@ def load():
             line = "%sprint(%s)" % (m.group(1), m.group(2))
         line = re.sub(r"\bnumpy\.complex\b(?!\d)", "complex", line)
         line = re.sub(r"\bnumpy\.float\b(?!\d)", "float", line)
+        line = re.sub(r"\bnumpy\.int\b(?!\d)", "int", line)
         line = re.sub(r"^(\s*)raise StopIteration\s*$", r"\1return", line)
         out.append(line)
     code = "\n".join(out)
@@ -136,3 +137,44 @@ def run_adaptive(kind, X, samplerate, delays, D, **params):
     Y = np.array(Y)
     K = M // 2 + 1
     return Y, np.array(bf._waH)[:K].copy(), bf._ttl_updates
+
+
+def _drain(bf):
+    """Iterate a reference beamformer to the end of its sources (Python 2 semantics of a StopIteration inside a generator)."""
+    Y = []
+    it = iter(bf)
+    while True:
+        try:
+            Y.append(next(it))
+        except StopIteration:
+            break
+        except RuntimeError as e:
+            if isinstance(e.__cause__, StopIteration):
+                break
+            raise
+    return np.array(Y)
+
+
+def run_sos(kind, X, samplerate, D, labels=None, mask_t=None, mask_j=None, energy_threshold=10, gamma=1e-6, ref_micx=0, offset=0.0):
+    """Run the reference's SubbandBlindMVDRBeamformer ('bmvdr', pybeamformer.py:1243-1295) or SubbandGEVBeamformer ('gev',
+    :1298-1357) over snapshots X[T][C][M], statistics from a VAD label (accu_stats_from_label, :1063-1127) or TF masks
+    (accu_stats_from_tfmask, :1129-1183), exactly in the order of unit_test/test_sos_batch_beamforming.py:186-210.
+    Returns dict(Y[T][M], wqH[K][C], Rt, Rn [K][C][C] after finalize_stats, ct, cn [K])."""
+    mod = load()
+    X = np.asarray(X)
+    T, C, M = X.shape
+    srcs = [ArraySpectralSource(X[:, c, :], D) for c in range(C)]
+    bf = (mod.SubbandBlindMVDRBeamformer if kind == "bmvdr" else mod.SubbandGEVBeamformer)(srcs)
+    if mask_t is not None:
+        bf.accu_stats_from_tfmask(samplerate, mask_t, mask_j, energy_threshold=energy_threshold)
+    else:
+        bf.accu_stats_from_label(samplerate, target_labs=labels, energy_threshold=energy_threshold)
+    ct, cn = np.array(bf._target_frame_counts), np.array(bf._noise_frame_counts)
+    bf.finalize_stats(gamma=gamma)
+    if kind == "bmvdr":
+        bf.calc_beamformer_weights(ref_micx=ref_micx, offset=offset)
+    else:
+        bf.calc_beamformer_weights()
+    bf.reset()
+    Y = _drain(bf)
+    return dict(Y=Y, wqH=np.array(bf._wqH), Rt=np.array(bf._target_covariance_matrices), Rn=np.array(bf._noise_covariance_matrices), ct=ct, cn=cn)

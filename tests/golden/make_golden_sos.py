@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Golden vectors for the SOS batch beamformers from the reference's OWN Python (lib/pybeamformer.py:1026-1357, run through
+oracle/pyref.py) on the analysis-bank output of the reference's C++ (oracle/_ref), in the call order of
+unit_test/test_sos_batch_beamforming.py:186-233.
+
+  golden_bmvdr_vad_c8_m512.npz     SubbandBlindMVDRBeamformer, VAD label (confs/bmvdr_vad.json shape: one segment), two segments here
+  golden_bmvdr_tfmask_c4_m256.npz  SubbandBlindMVDRBeamformer, TF masks with FRACTIONAL values (the integer-count truncation quirk)
+  golden_gev_vad_c8_m512.npz       SubbandGEVBeamformer, VAD label (confs/gev_vad.json)
+  golden_gev_tfmask_c4_m256.npz    SubbandGEVBeamformer, binary TF masks (confs/gev_tfmask.json)
+
+Usage: python tests/golden/make_golden_sos.py
+"""
+import os, sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref, pyref, restate  # noqa: E402
+from distant_speech_recognition_b200 import synthetic  # noqa: E402
+from make_golden import proto, save  # noqa: E402
+
+FS = 16000.0
+
+
+def snapshots(x, h, M):
+    return np.stack([ref.analysis(x[c], h, M, 4, 1) for c in range(x.shape[0])], axis=1)
+
+
+def tf_masks(X, K, seed, fractional):
+    """Deterministic TF masks from the snapshot energies: target where channel-0 magnitude is above the bin median."""
+    rng = np.random.default_rng(seed)
+    mag = np.abs(X[:, 0, :K])
+    med = np.median(mag, axis=0, keepdims=True)
+    mt = (mag > med).astype(np.float64)
+    mj = 1.0 - mt
+    if fractional:
+        mt = mt * rng.uniform(0.3, 1.7, mt.shape)
+        mj = mj * rng.uniform(0.3, 1.7, mj.shape)
+        mt[rng.uniform(size=mt.shape) < 0.1] = 0.0
+    # the C-ABI takes float32 masks: round first so the reference sees exactly the stored values
+    return mt.astype(np.float32).astype(np.float64), mj.astype(np.float32).astype(np.float64)
+
+
+def one(name, kind, C, M, n, useed, labels=None, mask=None, **kw):
+    K = M // 2 + 1; h, g = proto(M)
+    x, d, _, _ = synthetic.make_utterance(useed, C, n, target_start_s=0.3)
+    X = snapshots(x, h, M)
+    mt = mj = None
+    if mask is not None:
+        mt, mj = tf_masks(X, K, useed, fractional=(mask == "fractional"))
+    res = pyref.run_sos(kind, X, FS, M // 2, labels=labels, mask_t=mt, mask_j=mj, **kw)
+    w = np.conj(res["wqH"])
+    time = ref.synthesis(res["Y"], g, M, 4, 1)
+    # cross-check the fp64 restatement against the reference's own output before saving
+    Rt, Rn, ct, cn = restate.sos_accumulate(X, FS, M // 2, target_labs=labels, mask_t=mt, mask_j=mj, energy_threshold=kw.get("energy_threshold", 10))
+    assert np.array_equal(ct, res["ct"]) and np.array_equal(cn, res["cn"]), (ct[:5], res["ct"][:5])
+    if kind == "bmvdr":
+        w2 = restate.sos_bmvdr_weights(Rt, Rn, ct, cn, gamma=kw.get("gamma", 1e-6), ref_micx=kw.get("ref_micx", 0), offset=kw.get("offset", 0.0))
+        sgn = 1.0
+    else:
+        w2 = restate.sos_gev_weights(Rt, Rn, cn, gamma=kw.get("gamma", 1e-6))
+        sgn = np.sign(np.real(np.vdot(w2[0], w[0])))
+    err = np.linalg.norm(sgn * w2 - w) / np.linalg.norm(w)
+    Y2 = restate.sos_apply(X, sgn * w2)
+    errY = np.linalg.norm(Y2 - res["Y"]) / np.linalg.norm(res["Y"])
+    print("%s: restatement vs reference python: weights %.2e, Y %.2e (global sign %+d), counts t %d..%d n %d..%d" %
+          (name, err, errY, sgn, ct.min(), ct.max(), cn.min(), cn.max()))
+    assert err < 1e-8 and errY < 1e-8
+    extra = {}
+    if labels is not None:
+        extra["labels"] = np.asarray(labels, np.float64)
+    if mt is not None:
+        extra["mask_t"] = mt.astype(np.float32); extra["mask_j"] = mj.astype(np.float32)
+    save(name, x=x, Y=res["Y"][:, :K].astype(np.complex64), w=w, time=time.astype(np.float32), ct=res["ct"], cn=res["cn"],
+         Rn=res["Rn"].astype(np.complex64), gamma=kw.get("gamma", 1e-6), ref_micx=kw.get("ref_micx", 0), offset=kw.get("offset", 0.0),
+         energy_threshold=kw.get("energy_threshold", 10), **extra)
+
+
+def main():
+    one("bmvdr_vad_c8_m512", "bmvdr", 8, 512, 16000, 11, labels=[(0.3, 0.55), (0.7, -1)], ref_micx=2, offset=0.01)
+    one("bmvdr_tfmask_c4_m256", "bmvdr", 4, 256, 8000, 12, mask="fractional", gamma=1e-4)
+    one("gev_vad_c8_m512", "gev", 8, 512, 16000, 13, labels=[(0.3, 0.8)])
+    one("gev_tfmask_c4_m256", "gev", 4, 256, 8000, 14, mask="binary")
+
+
+if __name__ == "__main__":
+    main()

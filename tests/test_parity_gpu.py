@@ -493,3 +493,106 @@ def test_64_mic_gsc_lms_and_mvdr_cfg4_shape(capi, protos):
         wo = restate.calc_mvdr_weights(R + float(np.float32(1.0e6)) * np.eye(C), wq, single=False)
         assert rel_l2(w[u], wo[:257]) < 1e-3
         assert rel_l2(Yq[u], restate.subband_mvdr(Xs[u], wo)[:, :257]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SOS batch beamformers: blind MVDR / GEV, goldens = the reference's own Python (make_golden_sos.py)
+def _sos_run(capi, protos, g, C, M, kind, accumulate):
+    x = g["x"]
+    p = _pipe(capi, C, M, protos, n=x.shape[1], beamformer=capi.BF_DS)
+    p.submit(x[None])
+    p.run_analysis()
+    accumulate(p)
+    p.sos_calc_weights(kind, gamma=float(g["gamma"]), ref_micx=int(g["ref_micx"]), offset=float(g["offset"]))
+    return p
+
+
+def _sos_check(capi, p, g, allow_sign):
+    w = p.get_weights()[0]
+    sgn = 1.0
+    if allow_sign:   # GEV: scipy/LAPACK leaves ONE global sign per utterance undefined (include/btkb.h BTKB_SOS_GEV)
+        sgn = float(np.sign(np.real(np.vdot(w[0], g["w"][0]))))
+        assert sgn != 0.0
+    assert rel_l2(sgn * w, g["w"]) < TOL
+    _, _, cnt = p.sos_get_stats()
+    assert np.array_equal(cnt[0, :, 0], g["ct"]) and np.array_equal(cnt[0, :, 1], g["cn"])
+    if sgn < 0:
+        p.set_weights((sgn * w)[None])
+    p.run_beamformer(True)
+    assert rel_l2(p.fetch_subband()[0], g["Y"]) < TOL
+    assert rel_l2(p.fetch_time()[0], g["time"]) < TOL
+
+
+def test_blind_mvdr_vad_golden(capi, protos):
+    g = load_golden("bmvdr_vad_c8_m512")
+    p = _sos_run(capi, protos, g, 8, 512, capi.SOS_BMVDR, lambda p: p.sos_accumulate_from_label(g["labels"], float(g["energy_threshold"])))
+    _sos_check(capi, p, g, False)
+
+
+def test_blind_mvdr_fractional_tfmask_golden(capi, protos):
+    g = load_golden("bmvdr_tfmask_c4_m256")
+    p = _sos_run(capi, protos, g, 4, 256, capi.SOS_BMVDR, lambda p: p.sos_accumulate_from_tfmask(g["mask_t"], g["mask_j"], float(g["energy_threshold"])))
+    _sos_check(capi, p, g, False)
+
+
+def test_gev_vad_golden(capi, protos):
+    g = load_golden("gev_vad_c8_m512")
+    p = _sos_run(capi, protos, g, 8, 512, capi.SOS_GEV, lambda p: p.sos_accumulate_from_label(g["labels"], float(g["energy_threshold"])))
+    _sos_check(capi, p, g, True)
+
+
+def test_gev_tfmask_golden(capi, protos):
+    g = load_golden("gev_tfmask_c4_m256")
+    p = _sos_run(capi, protos, g, 4, 256, capi.SOS_GEV, lambda p: p.sos_accumulate_from_tfmask(g["mask_t"], g["mask_j"], float(g["energy_threshold"])))
+    _sos_check(capi, p, g, True)
+
+
+def test_sos_batched_ragged_vs_fp64_oracle_and_accumulation(capi, protos):
+    """Three utterances of different length in one batch, per-utterance labels; statistics accumulated over two calls equal
+    twice the single-call sums (pybeamformer.py:1113-1127); errors for missing statistics."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    C, M, n = 8, 512, 12000
+    h, gp = protos[M]
+    x, _ = synthetic.make_batch(3, C, n, first=40)
+    lengths = np.array([12000, 9000, 10300], np.int32)
+    labels = np.array([[[0.2, 0.45]], [[0.1, 0.3]], [[0.3, 0.5]]])
+    p = _pipe(capi, C, M, protos, U=3, n=n, beamformer=capi.BF_DS)
+    p.submit(x, lengths)
+    p.run_analysis()
+    with pytest.raises(capi.BtkbError):
+        p.sos_calc_weights(capi.SOS_BMVDR)
+    p.sos_accumulate_from_label(labels, 10.0)
+    Rt1, Rn1, c1 = p.sos_get_stats()
+    for kind, fn in ((capi.SOS_BMVDR, None), (capi.SOS_GEV, None)):
+        p.sos_calc_weights(kind, gamma=1e-6, ref_micx=1, offset=0.0)
+        w = p.get_weights()
+        p.run_beamformer(True)
+        Y = p.fetch_subband(); y = p.fetch_time()
+        for u in range(3):
+            xu = x[u][:, : lengths[u]]
+            X = np.stack([restate.analysis(xu[c], h, M, 4, 1) for c in range(C)], axis=1)
+            Rt, Rn, ct, cn = restate.sos_accumulate(X, FS, M // 2, target_labs=[tuple(labels[u, 0])], energy_threshold=10.0)
+            assert np.array_equal(c1[u, :, 0], ct) and np.array_equal(c1[u, :, 1], cn)
+            assert rel_l2(Rt1[u], Rt) < 1e-5 and rel_l2(Rn1[u], Rn) < 1e-5
+            if kind == capi.SOS_BMVDR:
+                wo = restate.sos_bmvdr_weights(Rt, Rn, ct, cn, gamma=1e-6, ref_micx=1, offset=0.0)
+            else:
+                wo = restate.sos_gev_weights(Rt, Rn, cn, gamma=1e-6)
+            assert rel_l2(w[u], wo) < TOL
+            Yo = restate.sos_apply(X, wo)
+            T = X.shape[0]
+            assert rel_l2(Y[u, :T], Yo[:, : M // 2 + 1]) < TOL
+            yo = restate.synthesis(Yo, gp, M, 4, 1)
+            assert rel_l2(y[u, : len(yo)], yo) < TOL
+    p.sos_accumulate_from_label(labels, 10.0)
+    Rt2, Rn2, c2 = p.sos_get_stats()
+    assert np.allclose(Rt2, 2 * Rt1, rtol=1e-12) and np.allclose(Rn2, 2 * Rn1, rtol=1e-12) and np.array_equal(c2, 2 * c1)
+    p.sos_reset_stats()
+    with pytest.raises(capi.BtkbError):
+        p.sos_calc_weights(capi.SOS_GEV)
+    # a label that never fires leaves bins without target statistics: the reference's assertion (pybeamformer.py:1264)
+    p.sos_accumulate_from_label(np.array([[[50.0, 60.0]]] * 3), 10.0)
+    with pytest.raises(capi.BtkbError) as ei:
+        p.sos_calc_weights(capi.SOS_BMVDR)
+    assert "No target signal stats" in str(ei.value)
