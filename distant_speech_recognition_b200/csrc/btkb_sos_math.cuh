@@ -119,7 +119,10 @@ BTKB_HD bool sos_solve_chain(zd (*Rt)[C], zd (*Rn)[C], int kind, double gamma, i
           for (int q = p + 1; q < C; q++) {
             const zd apq = Rt[p][q];
             const double gm = sqrt(zabs2(apq));
-            if (gm == 0.0) continue;
+            if (gm <= 1e-20 * (fabs(Rt[p][p].x) + fabs(Rt[q][q].x)) || gm < 1e-290) {   // a rotation below rounding level
+              Rt[p][q] = zmk(0, 0); Rt[q][p] = zmk(0, 0);
+              continue;
+            }
             const zd ph = zscale(apq, 1.0 / gm);
             const double tau = (Rt[q][q].x - Rt[p][p].x) / (2.0 * gm);
             const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + hypot(1.0, tau));
