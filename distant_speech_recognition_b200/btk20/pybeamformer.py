@@ -4,7 +4,7 @@ the per-bin Python loops of the reference (`__iter__` of SubbandGSCLMSBeamformer
 kernels behind native stream objects."""
 import numpy
 
-from .beamformer import SubbandGSCPtr, SubbandMVDRGSCPtr, SubbandGSCLMSPtr, LmsConfig, SubbandGSCRLSNativePtr, RlsConfig
+from .beamformer import SubbandGSCPtr, SubbandMVDRGSCPtr, SubbandGSCLMSPtr, LmsConfig, SubbandGSCRLSNativePtr, RlsConfig, SubbandSOSNativePtr
 
 SSPEED = 343740.0
 
@@ -255,3 +255,89 @@ class SubbandSMIMVDRBeamformer(SubbandMVDRBeamformer):
         if update_active_weights:
             self.set_active_weights()
         self._wqH = numpy.conjugate(numpy.array([self._beamformer.mvdr_weights(m) for m in range(self._fftlen2 + 1)], numpy.complex128))
+
+
+class SubbandSOSBatchBeamformer(SubbandBeamformer):
+    """lib/pybeamformer.py:1026-1219 — batch beamformer driven by second-order statistics.  The reference accumulates
+    x x^H per bin per frame in a Python loop and applies wqH in another; here both are CUDA kernels (csrc/btkb_sos.cu,
+    k_perbin) behind one native stream object."""
+
+    def __init__(self, spec_sources):
+        SubbandBeamformer.__init__(self, spec_sources)
+        self._beamformer = SubbandSOSNativePtr(self._fftlen)
+        for source in self._spec_sources:
+            self._beamformer.set_channel(source)
+        self._isamp = 0
+        self._have_stats = False
+
+    def accu_stats_from_label(self, samplerate, target_labs=[(0.1, -1)], energy_threshold=10):
+        """lib/pybeamformer.py:1063-1127 (several segments allowed; the segment cursor walks like the reference's `labx`)."""
+        self._beamformer.accu_stats_from_label(samplerate, numpy.asarray(target_labs, numpy.float64).reshape(-1, 2), float(energy_threshold))
+        self._have_stats = True
+
+    def accu_stats_from_tfmask(self, samplerate, mask_t, mask_j, energy_threshold=10):
+        """lib/pybeamformer.py:1129-1183."""
+        self._beamformer.accu_stats_from_tfmask(samplerate, numpy.asarray(mask_t, numpy.float32), numpy.asarray(mask_j, numpy.float32), float(energy_threshold))
+        self._have_stats = True
+
+    def finalize_stats(self):
+        pass
+
+    def reset_stats(self):
+        """lib/pybeamformer.py:1209-1213."""
+        self._beamformer.reset_stats()
+        self._have_stats = False
+
+    def frame_counts(self):
+        """(_target_frame_counts, _noise_frame_counts) of the reference, [K] each."""
+        c = numpy.array(self._beamformer.frame_counts())
+        return c[:, 0], c[:, 1]
+
+    def reset(self):
+        self._beamformer.reset()
+        self._isamp = 0
+
+    def _export_wqH(self):
+        self._wqH = numpy.conjugate(numpy.array([self._beamformer.get_weights(m) for m in range(self._fftlen2 + 1)], numpy.complex128))
+
+
+class SubbandBlindMVDRBeamformer(SubbandSOSBatchBeamformer):
+    """lib/pybeamformer.py:1243-1295 — MVDR without a look direction (MMSE beamformer)."""
+
+    def finalize_stats(self, gamma=1e-6):
+        """lib/pybeamformer.py:1283-1295: the normalisation and the diagonal loading run on the GPU inside calc_beamformer_weights."""
+        assert self._have_stats, "No target signal stats accumulated; Use self.accu_stats_from_label() or accu_stats_from_tfmask()"
+        self._gamma = gamma
+
+    def calc_beamformer_weights(self, ref_micx=0, offset=0.0):
+        """lib/pybeamformer.py:1257-1281."""
+        if not self._have_stats:
+            raise RuntimeError('No target signal SOS')
+        assert offset >= 0 and offset <= 1, "The offset value %f is out of [0, 1]" % (offset)
+        try:
+            self._beamformer.calc_weights(0, getattr(self, "_gamma", 1e-6), ref_micx, offset)
+        except Exception as e:
+            if "Matrix inversion failed" in str(e):
+                raise ArithmeticError(str(e))
+            if "stats accumulated" in str(e):
+                raise AssertionError(str(e))
+            raise
+        self._export_wqH()
+
+
+class SubbandGEVBeamformer(SubbandBlindMVDRBeamformer):
+    """lib/pybeamformer.py:1298-1357 — generalised-eigenvector beamformer (the principal eigenvector's phase is fixed up to one
+    global sign per utterance, see include/btkb.h BTKB_SOS_GEV)."""
+
+    def calc_beamformer_weights(self):
+        if not self._have_stats:
+            raise RuntimeError('No target signal SOS')
+        try:
+            self._beamformer.calc_weights(1, getattr(self, "_gamma", 1e-6), 0, 0.0)
+        except Exception as e:
+            if "GEV failed" in str(e):
+                raise ArithmeticError(str(e))
+            if "stats accumulated" in str(e):
+                raise AssertionError(str(e))
+            raise
+        self._export_wqH()

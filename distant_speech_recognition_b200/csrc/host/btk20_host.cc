@@ -337,6 +337,78 @@ int SubbandGSCRLSNative::total_updates() {
   return (int)st[2];
 }
 
+// ---- SubbandSOSNative
+SubbandSOSNative::SubbandSOSNative(unsigned fftLen, const std::string& nm) : SubbandDS(fftLen, false, nm, BTKB_BF_DS) {}
+SubbandSOSNative::~SubbandSOSNative() { if (stats_) btkb_destroy(stats_); }
+void SubbandSOSNative::clear_channel() { SubbandDS::clear_channel(); if (stats_) { btkb_destroy(stats_); stats_ = nullptr; } stats_cap_ = 0; have_wsos_ = false; }
+void SubbandSOSNative::reset_stats() { if (stats_) ck(btkb_sos_reset_stats(stats_)); }   // pybeamformer.py:1209-1213
+unsigned SubbandSOSNative::stage_(double samplerate) {
+  if (channels_.empty()) throw j_error("set_channel() has not been called\n");
+  const unsigned C = chanN();
+  std::vector<const SampleFeature*> srcs(C); unsigned n = 0;
+  for (unsigned c = 0; c < C; c++) {
+    auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[c].get());
+    if (!ab) throw j_error("SubbandSOS: the GPU engine needs OverSampledDFTAnalysisBank channels");
+    srcs[c] = dynamic_cast<const SampleFeature*>(ab->source().get());
+    if (!srcs[c]) throw j_error("SubbandSOS: the GPU engine needs SampleFeature sources");
+    if (c == 0) n = srcs[c]->samplesN();
+    else if (srcs[c]->samplesN() != n) throw jdimension_error("channel %d: %d samples, channel 0: %d", c, srcs[c]->samplesN(), n);
+  }
+  if (n == 0) throw jiterator_error("end of samples!");
+  samplerate_ = samplerate;
+  if (!stats_ || n > stats_cap_) {
+    if (stats_) throw j_error("SubbandSOS: a later utterance (%d samples) is longer than the first one (%d); call reset_stats() and start with the longest", n, stats_cap_);
+    auto* a0 = dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[0].get());
+    btkb_config c; btkb_default_config(&c);
+    c.channels = (int)C; c.fft_len = (int)fftLen_; c.m = (int)a0->m(); c.r = (int)a0->r(); c.delay_compensation_type = (int)a0->dct();
+    c.samplerate = (float)samplerate; c.beamformer = BTKB_BF_DS; c.max_utterances = 1; c.max_samples = (int)n;
+    ck(btkb_create(&c, &stats_));
+    ck(btkb_set_prototypes(stats_, a0->prototype().data(), nullptr, (int)a0->prototype().size()));
+    stats_cap_ = n;
+  }
+  std::vector<float> x((size_t)C * n);
+  for (unsigned c = 0; c < C; c++) std::memcpy(&x[(size_t)c * n], srcs[c]->samples().data(), sizeof(float) * n);
+  ck(btkb_submit(stats_, x.data(), 1, (int)n, nullptr));
+  ck(btkb_run_analysis(stats_));
+  return n;
+}
+void SubbandSOSNative::accu_stats_from_label(double samplerate, const std::vector<double>& labels, double thr) {
+  if (labels.empty() || labels.size() % 2) throw jdimension_error("target_labs must be a list of (start, end) pairs");
+  stage_(samplerate);
+  ck(btkb_sos_accumulate_from_label(stats_, labels.data(), (int)(labels.size() / 2), (float)thr));
+}
+void SubbandSOSNative::accu_stats_from_tfmask(double samplerate, const std::vector<float>& mt, const std::vector<float>& mj, unsigned rows, unsigned cols, double thr) {
+  const unsigned K = fftLen_ / 2 + 1;
+  if (cols < K || mt.size() != (size_t)rows * cols || mj.size() != mt.size()) throw jdimension_error("TF masks must be [frames][>= %d] and of equal shape", K);
+  stage_(samplerate);
+  const unsigned T = (unsigned)btkb_num_frames(stats_);
+  if (rows < T) throw jindex_error("index %d is out of bounds for axis 0 with size %d", rows, rows);   // mask_t[frame_no] (pybeamformer.py:1151)
+  std::vector<float> a((size_t)rows * K), b((size_t)rows * K);
+  for (unsigned t = 0; t < rows; t++)
+    for (unsigned k = 0; k < K; k++) { a[(size_t)t * K + k] = mt[(size_t)t * cols + k]; b[(size_t)t * K + k] = mj[(size_t)t * cols + k]; }
+  ck(btkb_sos_accumulate_from_tfmask(stats_, a.data(), b.data(), (int)rows, (float)thr));
+}
+void SubbandSOSNative::calc_weights(int kind, double gamma, int ref_micx, double offset) {
+  if (!stats_) throw j_error("No target signal SOS");   // pybeamformer.py:1270-1273
+  ck(btkb_sos_calc_weights(stats_, kind, gamma, ref_micx, offset));
+  const unsigned K = fftLen_ / 2 + 1, C = chanN();
+  wsos_.resize((size_t)K * C);
+  ck(btkb_get_weights(stats_, reinterpret_cast<float*>(wsos_.data())));
+  have_wsos_ = true; W_.clear(); invalidate_();
+}
+std::vector<double> SubbandSOSNative::frame_counts() {
+  if (!stats_) throw j_error("no statistics accumulated");
+  std::vector<double> c((size_t)(fftLen_ / 2 + 1) * 2);
+  ck(btkb_sos_get_stats(stats_, nullptr, nullptr, c.data()));
+  return c;
+}
+void SubbandSOSNative::configure_weights_(btkb_pipeline* p) {
+  // before calc_beamformer_weights the reference's wqH is all ones (pybeamformer.py:1044)
+  const unsigned K = fftLen_ / 2 + 1, C = chanN();
+  if (!have_wsos_) { wsos_.assign((size_t)K * C, std::complex<float>(1.f, 0.f)); }
+  ck(btkb_set_weights(p, 1, reinterpret_cast<const float*>(wsos_.data())));
+}
+
 // ---- SubbandMVDR
 SubbandMVDR::SubbandMVDR(unsigned fftLen, bool hbs, const std::string& nm) : SubbandDS(fftLen, hbs, nm, BTKB_BF_MVDR) {}
 void SubbandMVDR::clear_channel() { SubbandDS::clear_channel(); R_.clear(); wmvdr_.clear(); have_R_ = have_w_ = diffuse_ = smi_ = false; }

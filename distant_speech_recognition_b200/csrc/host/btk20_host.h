@@ -255,6 +255,31 @@ class SubbandGSCRLSNative : public SubbandDS {
 };
 typedef std::shared_ptr<SubbandGSCRLSNative> SubbandGSCRLSNativePtr;
 
+// native body of pybeamformer.SubbandSOSBatchBeamformer / SubbandBlindMVDRBeamformer / SubbandGEVBeamformer
+// (lib/pybeamformer.py:1026-1357): the statistics live on the device in a pipeline of their own and accumulate over calls
+// like the reference's _target/_noise_covariance_matrices; the weights are handed to the beamforming pipeline as explicit
+// quiescent vectors (y = w^H x for every bin, pybeamformer.py:1191-1207).
+class SubbandSOSNative : public SubbandDS {
+ public:
+  SubbandSOSNative(unsigned fftLen, const std::string& nm = "SubbandSOSNative");
+  ~SubbandSOSNative();
+  void reset_stats();
+  // labels: flat [NL][2] (start, end) seconds
+  void accu_stats_from_label(double samplerate, const std::vector<double>& labels, double energy_threshold);
+  // masks: [rows][cols] float, cols >= fftLen/2+1 (only the first fftLen/2+1 columns are read, like the reference's loop)
+  void accu_stats_from_tfmask(double samplerate, const std::vector<float>& mask_t, const std::vector<float>& mask_j, unsigned rows, unsigned cols,
+                              double energy_threshold);
+  void calc_weights(int kind, double gamma, int ref_micx, double offset);   // finalize_stats + calc_beamformer_weights
+  std::vector<double> frame_counts();   // [K][2] target / noise
+  void clear_channel() override;
+ protected:
+  void configure_weights_(btkb_pipeline* p) override;
+  unsigned stage_(double samplerate);   // analysis of the current utterance into the statistics pipeline
+  btkb_pipeline* stats_ = nullptr; unsigned stats_cap_ = 0;
+  std::vector<std::complex<float>> wsos_; bool have_wsos_ = false;
+};
+typedef std::shared_ptr<SubbandSOSNative> SubbandSOSNativePtr;
+
 class SubbandMVDR : public SubbandDS {
  public:
   SubbandMVDR(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandMVDR");

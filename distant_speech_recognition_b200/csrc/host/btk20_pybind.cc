@@ -3,6 +3,7 @@
 // beamformer/beamformer.i:46-540, postfilter/postfilter.i:46-90, include/jexception.i:20-86 (exception map).
 #include <pybind11/complex.h>
 #include <pybind11/numpy.h>
+#include <cstring>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -201,6 +202,24 @@ PYBIND11_MODULE(_btk20host, m) {
         std::memcpy(a.mutable_data(), w.data(), sizeof(std::complex<float>) * w.size());
         return a; })
       .def("total_updates", &SubbandGSCRLSNative::total_updates);
+
+  py::class_<SubbandSOSNative, SubbandDS, SubbandSOSNativePtr>(m, "SubbandSOSNativePtr")
+      .def(py::init([](unsigned fftlen, const std::string& nm) { return std::make_shared<SubbandSOSNative>(fftlen, nm); }), py::arg("fftlen"), py::arg("nm") = "SubbandSOSNative")
+      .def("reset_stats", &SubbandSOSNative::reset_stats)
+      .def("accu_stats_from_label", [](SubbandSOSNative& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> labs, double thr) {
+        s.accu_stats_from_label(fs, vec_d(labs), thr); }, py::arg("samplerate"), py::arg("target_labs"), py::arg("energy_threshold") = 10.0)
+      .def("accu_stats_from_tfmask", [](SubbandSOSNative& s, double fs, py::array_t<float, py::array::c_style | py::array::forcecast> mt,
+                                        py::array_t<float, py::array::c_style | py::array::forcecast> mj, double thr) {
+        if (mt.ndim() != 2 || mj.ndim() != 2) throw jdimension_error("TF masks must be 2-D [frames][subbands]");
+        s.accu_stats_from_tfmask(fs, std::vector<float>(mt.data(), mt.data() + mt.size()), std::vector<float>(mj.data(), mj.data() + mj.size()),
+                                 (unsigned)mt.shape(0), (unsigned)mt.shape(1), thr); },
+           py::arg("samplerate"), py::arg("mask_t"), py::arg("mask_j"), py::arg("energy_threshold") = 10.0)
+      .def("calc_weights", &SubbandSOSNative::calc_weights, py::arg("kind"), py::arg("gamma") = 1.0e-6, py::arg("ref_micx") = 0, py::arg("offset") = 0.0)
+      .def("frame_counts", [](SubbandSOSNative& s) {
+        auto c = s.frame_counts();
+        py::array_t<double> out({(py::ssize_t)(c.size() / 2), (py::ssize_t)2});
+        std::memcpy(out.mutable_data(), c.data(), c.size() * sizeof(double));
+        return out; });
 
   py::class_<SubbandMVDR, SubbandDS, SubbandMVDRPtr>(m, "SubbandMVDRPtr")
       .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandMVDR>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,

@@ -217,6 +217,38 @@ def test_frontend_flow_smimvdr(protos):
 
 
 @pytest.mark.gpu
+def test_frontend_flow_bmvdr_and_gev(protos):
+    """unit_test/test_sos_batch_beamforming.py:186-233 with "type":"bmvdr" (VAD label) and "type":"gev" (TF masks)."""
+    g = load_golden("bmvdr_vad_c8_m512"); h, gg = protos[512]; M, D = 512, 256
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandBlindMVDRBeamformer(afbs)
+    with pytest.raises(RuntimeError):
+        bf.calc_beamformer_weights()
+    bf.accu_stats_from_label(FS, target_labs=[tuple(r) for r in g["labels"]], energy_threshold=10)
+    bf.finalize_stats(gamma=float(g["gamma"]))
+    bf.calc_beamformer_weights(ref_micx=int(g["ref_micx"]), offset=float(g["offset"]))
+    ct, cn = bf.frame_counts()
+    assert np.array_equal(ct, g["ct"]) and np.array_equal(cn, g["cn"])
+    assert rel_l2(np.conj(bf._wqH), g["w"]) < 1e-4
+    sfb = OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(bf), prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert rel_l2(y, g["time"]) < 1e-4
+
+    g = load_golden("gev_tfmask_c4_m256"); h, gg = protos[256]; M, D = 256, 128
+    afbs = _afbs(g["x"], h, M, D)
+    bf = pybeamformer.SubbandGEVBeamformer(afbs)
+    bf.accu_stats_from_tfmask(FS, g["mask_t"], g["mask_j"], energy_threshold=10)
+    bf.finalize_stats(gamma=float(g["gamma"]))
+    bf.calc_beamformer_weights()
+    w = np.conj(bf._wqH)
+    sgn = np.sign(np.real(np.vdot(w[0], g["w"][0])))     # one global sign is LAPACK-defined in the reference
+    assert rel_l2(sgn * w, g["w"]) < 1e-4
+    sfb = OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(bf), prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert rel_l2(sgn * y, g["time"]) < 1e-4
+
+
+@pytest.mark.gpu
 def test_generic_python_stream_into_synthesis_and_analysis_iteration(protos):
     """A pure-Python spatial filter between the banks (the reference's PyFeatureStream use): analysis frames are pulled
     one by one in Python, modified, and fed to the synthesis bank through PyVectorComplexFeatureStreamPtr."""
