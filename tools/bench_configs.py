@@ -59,6 +59,36 @@ def main():
     out["configs[3] 64-mic GSC-NLMS M=512 256x5s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels=t,
                                                           perbin_hbm_frac=bytes_perbin / (t["perbin_ms"] * 1e-3) / 1e9 / 6566.7)
     p.close()
+    # configs[3] with the covariance pass: 64-mic SMI-MVDR (k_covariance_wide + k_mvdr_solve_wide + static apply), same batch
+    p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_MVDR, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.synchronize()
+    labels = np.tile(np.array([[1.0, 5.0]]), (U, 1))
+    p.run_analysis(); p.synchronize()
+    def f3c(): p.accumulate_covariance(labels, 10.0); p.synchronize()
+    s_cov = timed(f3c, steps=2, warm=1)
+    def f3s(): p.calc_mvdr_weights(1e-4); p.synchronize()
+    s_sol = timed(f3s, steps=2, warm=1)
+    def f3a(): p.run_beamformer(True); p.synchronize()
+    s_app = timed(f3a, steps=2, warm=1); T = p.num_frames
+    cov_flops = 8.0 * C * C * (M // 2 + 1) * U * T   # upper bound: every frame accumulated
+    out["configs[3]+covariance 64-mic SMI-MVDR M=512 256x5s"] = dict(frames=U * T, covariance_ms=1e3 * s_cov, solve_ms=1e3 * s_sol, apply_synthesis_ms=1e3 * s_app,
+                                                                       covariance_hbm_frac=C * (M // 2 + 1) * 8 * U * T / s_cov / 1e9 / 6566.7,
+                                                                       covariance_tflops_if_all_frames=cov_flops / s_cov / 1e12)
+    p.close(); del x
+    # configs[4]: 8-mic GSC-NLMS behind multi-channel WPE (confs/wpe.json: 33 lags, 2 iterations), M=1024; a bounded sample of the
+    # 1 024-utterance-per-GPU shard (WPE is compute-bound: fp64 normal equations, L = 264 unknowns per channel and bin)
+    C, M, U, n = 8, 1024, 8, 80000
+    h, g = proto(M); x, d = tiled_batch(U, C, n, 4)
+    for tag, fp32 in (("fp64 normal equations (reference arithmetic)", 0), ("fp32 normal equations", 1)):
+        wpe = dict(lower_num=0, upper_num=32, iterations_num=2, load_db=-18.0, band_width=0.0, diagonal_bias=1e-4, fp32_normal_equations=fp32)
+        p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_GSC_LMS, max_utterances=U, max_samples=n, wpe=wpe)
+        p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.synchronize()
+        def f4(): p.run(True); p.synchronize()
+        s = timed(f4, steps=1, warm=1); T = p.num_frames; t = p.last_timing()
+        out["configs[4] 8-mic WPE+GSC-NLMS M=1024 sample of %d x 5s, %s" % (U, tag)] = dict(
+            frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, wpe_ms=p.last_timing_wpe(), kernels=t,
+            extrapolated_s_per_1024_utterance_shard=s * 1024 / U)
+        p.close()
     print(json.dumps(out, indent=1))
 
 
