@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libbtkref.so")
 
-BF_DS, BF_GSC, BF_MVDR_SD, BF_SMI_MVDR, BF_GSC_LMS = 0, 1, 2, 3, 4
+BF_DS, BF_GSC, BF_MVDR_SD, BF_SMI_MVDR, BF_GSC_LMS, BF_GSC_RLS_CPP = 0, 1, 2, 3, 4, 5
 
 
 class RefConfig(ct.Structure):
@@ -28,6 +28,7 @@ class RefConfig(ct.Structure):
         ("lms_min_frames", ct.c_int), ("lms_slowdown_after", ct.c_int),
         ("do_synthesis", ct.c_int),
         ("pf_threshold", ct.c_double), ("pf_min_sv", ct.c_double), ("pf_diag_load", ct.c_double), ("pf_fbin1", ct.c_int),
+        ("rls_mu", ct.c_double), ("rls_sigma2", ct.c_double), ("rls_init_sigma2", ct.c_double), ("rls_alpha", ct.c_double), ("rls_qctype", ct.c_int),
     ]
 
 
@@ -137,7 +138,7 @@ def mvdr_weights(M, C, samplerate, delays, R=None, mpos=None, sspeed=343740.0, m
 
 def beamform(samples, h, g, delays, M, m=4, r=1, dct=2, samplerate=16000.0, bf_kind=BF_DS, wa=None, mpos=None,
              pf=None, mvdr_mu=1.0e-4, sspeed=343740.0, smi_label=(1.0, -1.0), smi_energy_threshold=10.0, lms=None,
-             do_synthesis=True, want_subband=True):
+             do_synthesis=True, want_subband=True, rls=None):
     """Run the reference pipe on one utterance.  samples float32 [C][n].
     Returns dict(Y=[T][M] complex128, time=float32[nb*D], cov, w, stats)."""
     from . import restate
@@ -161,6 +162,9 @@ def beamform(samples, h, g, delays, M, m=4, r=1, dct=2, samplerate=16000.0, bf_k
                     lms_sil_thresh=lp["sil_thresh"], lms_max_wa_l2norm=lp["max_wa_l2norm"],
                     lms_min_frames=lp["min_frames"], lms_slowdown_after=lp["slowdown_after"],
                     do_synthesis=1 if do_synthesis else 0)
+    if rls:   # SubbandGSCRLS(fftLen, False, myu, sigma2); init_precision_matrix(init_sigma2); set_quadratic_constraint(alpha, qctype)
+        cfg.rls_mu = rls.get("mu", 0.9); cfg.rls_sigma2 = rls.get("sigma2", 0.01); cfg.rls_init_sigma2 = rls.get("init_sigma2", 0.01)
+        cfg.rls_alpha = rls.get("alpha", -1.0); cfg.rls_qctype = rls.get("qctype", 0)
     Tcap = _num_frames(n, M, m, r, dct) + 8
     Y = np.zeros((Tcap, M), np.complex128) if want_subband else None
     out_time = np.zeros((Tcap * D,), np.float32)

@@ -251,6 +251,9 @@ struct ref_config {
   /* post-filters beyond Zelinski (pf_kind 2 = McCowan, 3 = Lefkimmiatis; postfilter.cc:496-1200), wired like
      unit_test/test_online_beamforming.py:137-151: diffuse coherence from mpos + diagonal loading */
   double pf_threshold, pf_min_sv, pf_diag_load; int pf_fbin1;
+  /* bf_kind 5: the reference's C++ SubbandGSCRLS (beamformer.cc:1447-1699): ctor (myu, sigma2), init_precision_matrix(init_sigma2),
+     set_quadratic_constraint(alpha, qctype) when qctype != 0 */
+  double rls_mu, rls_sigma2, rls_init_sigma2, rls_alpha; int rls_qctype;
 };
 
 /* analysis only: samples[n] -> out[T][M] complex128 interleaved; returns T (or -1 if T > T_cap) */
@@ -459,7 +462,7 @@ int ref_beamform(const ref_config* cfg, const float* samples, int n, const doubl
       chans.push_back((VectorComplexFeatureStreamPtr&)afbs.back());
     }
     VectorComplexFeatureStreamPtr bfstream;
-    SubbandDSPtr ds; SubbandGSCPtr gsc; SubbandMVDRGSCPtr mvdr; GscLmsRestatePtr lms;
+    SubbandDSPtr ds; SubbandGSCPtr gsc; SubbandMVDRGSCPtr mvdr; GscLmsRestatePtr lms; SubbandGSCRLSPtr rls;
     SubbandDSPtr bf_for_pf;
     switch (cfg->bf_kind) {
       case 0:
@@ -499,6 +502,14 @@ int ref_beamform(const ref_config* cfg, const float* samples, int n, const doubl
         mvdr->calc_mvdr_weights((float)cfg->samplerate, 1.0E-8, true);
         bfstream = (VectorComplexFeatureStreamPtr&)mvdr; bf_for_pf = (SubbandDSPtr&)mvdr;
         if (w_out) for (int f = 0; f < K; f++) memcpy(w_out + (size_t)2 * f * C, mvdr->mvdr_weights(f)->data, sizeof(double) * 2 * C);
+        break;
+      case 5:
+        rls = new SubbandGSCRLS(M, false, (float)cfg->rls_mu, (float)cfg->rls_sigma2);
+        for (int c = 0; c < C; c++) rls->set_channel(chans[c]);
+        rls->calc_gsc_weights((float)cfg->samplerate, dv);
+        rls->init_precision_matrix((float)cfg->rls_init_sigma2);
+        if (cfg->rls_qctype != 0) rls->set_quadratic_constraint((float)cfg->rls_alpha, cfg->rls_qctype);
+        bfstream = (VectorComplexFeatureStreamPtr&)rls; bf_for_pf = (SubbandDSPtr&)rls;
         break;
       default: {
         LmsParams p = {cfg->lms_beta, cfg->lms_gamma, cfg->lms_init_diagonal_load, cfg->lms_regularization_param, cfg->lms_energy_floor,
