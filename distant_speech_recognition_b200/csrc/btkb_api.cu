@@ -602,7 +602,12 @@ int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float ene
   CK(launch_noise_mask(p->d_E, p->d_len, labels ? p->d_labels : nullptr, p->d_mask, p->d_count, p->U, p->T, p->D, p->laN, p->pdA, p->cfg.samplerate,
                        energy_threshold, p->stream));
   PerBinArgs a = perbin_args(p);
-  if (p->C <= 8) CK(launch_covariance(a, p->stream)); else CK(launch_covariance_wide(a, p->stream));
+  // 64 microphones: the Gram is a batched dense contraction and runs on the tensor cores (btkb_cov_tc.cu: tcgen05 + TMEM,
+  // 3 x TF32 split); BTKB_COV_TC=0 selects the CUDA-core kernel (kept for A/B checks)
+  static const bool use_tc = [] { const char* e = getenv("BTKB_COV_TC"); return !(e && atoi(e) == 0); }();
+  if (p->C <= 8) CK(launch_covariance(a, p->stream));
+  else if (p->C == 64 && use_tc) CK(launch_covariance_tc(a, p->stream));
+  else CK(launch_covariance_wide(a, p->stream));
   if (labels) CK(cudaStreamSynchronize(p->stream));
   p->have_R = true; p->R_is_sum = true;
   p->wU = p->U;

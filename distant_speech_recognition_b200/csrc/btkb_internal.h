@@ -113,6 +113,7 @@ cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st);
 // wide arrays (C = 16, 32, 64): btkb_wide.cu
 cudaError_t launch_perbin_wide(const PerBinArgs& a, cudaStream_t st);
 cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st);
+cudaError_t launch_covariance_tc(const PerBinArgs& a, cudaStream_t st);   // C = 64: tcgen05 / TMEM (btkb_cov_tc.cu)
 cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count, cudaStream_t st);
 cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st);
 

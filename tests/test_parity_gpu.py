@@ -596,3 +596,29 @@ def test_sos_batched_ragged_vs_fp64_oracle_and_accumulation(capi, protos):
     with pytest.raises(capi.BtkbError) as ei:
         p.sos_calc_weights(capi.SOS_BMVDR)
     assert "No target signal stats" in str(ei.value)
+
+
+def test_64_mic_covariance_tensor_core_path(capi, protos):
+    """k_covariance_tc (tcgen05 / TMEM, 3 x TF32 split) on a batch that exercises the shared-memory ring wrap (4 K-blocks of 32
+    frames), both TMEM accumulator buffers (several groups per CTA), an odd chain count (last group half empty), ragged lengths
+    and per-utterance noise labels, against the fp64 restatement of accu_stats_from_label (pybeamformer.py:948-1000)."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, C, U, n = 512, 64, 3, 30000
+    h, g = protos[M]
+    x, d = synthetic.make_batch(U, C, n, first=410)
+    lengths = np.array([30000, 21000, 26500], np.int32)
+    labels = np.array([[0.5, 0.9], [0.2, 0.6], [1.0, 1.4]])
+    q = _pipe(capi, C, M, protos, U=U, n=n, beamformer=capi.BF_MVDR)
+    q.set_delays(d); q.submit(x, lengths); q.run_analysis()
+    q.accumulate_covariance(labels=labels, energy_threshold=10.0)
+    cov = q.get_covariance()
+    worst = 0.0
+    for u in range(U):
+        xu = x[u][:, : lengths[u]]
+        X = np.stack([restate.analysis(xu[c], h, M, 4, 1) for c in range(C)], axis=1)
+        R, nf = restate.smi_covariance(X, FS, 256, (tuple(labels[u]),), 10.0)
+        assert nf > 40
+        worst = max(worst, rel_l2(cov[u], R))
+        assert np.abs(cov[u] - np.conj(np.transpose(cov[u], (0, 2, 1)))).max() <= 1e-6 * np.abs(cov[u]).max()   # Hermitian
+    assert worst < 3e-6, worst   # fp32-class: a plain TF32 Gram would sit near 3e-4
