@@ -46,6 +46,7 @@ struct btkb_pipeline {
   // SOS batch beamformers (lazily allocated by the first btkb_sos_accumulate_*)
   double2 *d_sosR = nullptr, *d_sosWd = nullptr; double* d_sosCnt = nullptr; float *d_sosWtu = nullptr, *d_sosMask = nullptr; double* d_sosLab = nullptr;
   int* d_sosErr = nullptr; int sos_NLcap = 0; bool have_sos = false;
+  float2* d_covS = nullptr;   // series-major workspace of the 64-mic tensor-core covariance (lazily allocated)
   bool have_pfR = false, pf_applied = false;  // pf_applied: d_Y came out of this pipeline's post-filter (not btkb_set_subband)
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
@@ -98,7 +99,7 @@ void btkb_destroy(btkb_pipeline* p) {
   void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
                   p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
                   p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM, p->d_wS, p->d_wG, p->d_wR, p->d_wTH, p->d_werr,
-                  p->d_sosR, p->d_sosWd, p->d_sosCnt, p->d_sosWtu, p->d_sosMask, p->d_sosLab, p->d_sosErr};
+                  p->d_sosR, p->d_sosWd, p->d_sosCnt, p->d_sosWtu, p->d_sosMask, p->d_sosLab, p->d_sosErr, p->d_covS};
   if (p->h_delays) cudaFreeHost(p->h_delays);
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -606,7 +607,12 @@ int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float ene
   // 3 x TF32 split); BTKB_COV_TC=0 selects the CUDA-core kernel (kept for A/B checks)
   static const bool use_tc = [] { const char* e = getenv("BTKB_COV_TC"); return !(e && atoi(e) == 0); }();
   if (p->C <= 8) CK(launch_covariance(a, p->stream));
-  else if (p->C == 64 && use_tc) CK(launch_covariance_tc(a, p->stream));
+  else if (p->C == 64 && use_tc) {
+    const size_t need = covariance_tc_workspace_bytes(p->Ucap * p->K, p->C, p->Tcap);
+    if (!p->d_covS) CK(cudaMalloc((void**)&p->d_covS, need));
+    a.Scov = p->d_covS;
+    CK(launch_covariance_tc(a, p->stream));
+  }
   else CK(launch_covariance_wide(a, p->stream));
   if (labels) CK(cudaStreamSynchronize(p->stream));
   p->have_R = true; p->R_is_sum = true;

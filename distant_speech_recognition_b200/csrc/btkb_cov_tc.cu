@@ -15,16 +15,23 @@
 // Rows are interleaved in blocks of 8 ([Xr 0-7][Xi 0-7][Xr 8-15]...), so the TMEM lanes holding the Xr and the Xi row of a
 // channel sit 8 lanes apart in the same warp and the epilogue combines them with warp shuffles (no shared-memory pass).
 //
-// CTA = 13 warps, persistent over groups of 2 adjacent chains:
-//   warps 5-12  producers: coalesced-by-sector global loads of X[t][c][g..g+1] (lanes along t), noise-frame masking
-//               (pybeamformer.py:963-975 via k_noise_mask), hi/lo split, transposing st.shared into the swizzled operand
-//               tiles (conflict-free: a warp writes one 128-byte row), fence.proxy.async + mbarrier arrive
+// CTA = 14 warps, persistent over groups of 2 adjacent chains:
+//   (pre-pass)  k_cov_gather: series-major copy S[g][c][Ts] of X[t][c][g] through 32 x 32 shared-memory transposes.  A chain pair
+//               is a 16-byte column of X; reading such a column directly costs 26 ms at configs[3] whether per-lane loads
+//               (fully divergent) or a 3-D TMA box with a 16-byte inner extent do it (both measured), the coalesced pre-pass
+//               plus 256-byte TMA rows does not.
+//   warp 13     one thread loads the pair's K-block with two 2-D tensor-map TMAs: box {32 frames x (re, im), 64 channels} of S
+//   warps 5-12  transposers: one LDS.64 per (chain, channel, lane = frame), noise-frame masking
+//               (pybeamformer.py:963-975 via k_noise_mask), hi/lo split, st.shared into the swizzled operand tiles
+//               (conflict-free: a warp writes one 128-byte row), fence.proxy.async + mbarrier arrive
 //   warp 4      one elected thread issues the MMAs and tcgen05.commit's to the `empty` / `accumulator full` mbarriers
 //   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns), shuffle-combine, R[(c C + c')][g] complex64 stores;
 //               TMEM is double-buffered (2 x 2 chains x 128 columns = 512 columns), so it overlaps the next group's MMAs
-// Shared memory: 3 stages x (2 chains x (hi + lo) x 16 KiB) = 192 KiB.
+// Shared memory: 2 operand stages x (2 chains x (hi + lo) x 16 KiB) + 3 raw stages x 32 KiB = 224 KiB.
+#include <cuda.h>
 #include "btkb_internal.h"
 #include <stdint.h>
+#include <cstdlib>
 
 namespace btkb {
 namespace tc {
@@ -34,12 +41,15 @@ constexpr int KB = 32;                     // frames per K-block = tf32 elements
 constexpr int TILE_B = 128 * 128;          // one operand tile: 128 rows x 128 bytes
 constexpr int NCH = 2;                     // chains per group
 constexpr int STAGE_B = NCH * 2 * TILE_B;  // per chain: hi tile, lo tile
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 2;                  // operand stages
+constexpr int RAW_B = NCH * C64 * KB * 8;   // raw K-block of the pair: per chain [c][t] complex64
+constexpr int NRAW = 3;                    // raw stages
 constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS;
-constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS);
+constexpr int TMA_WARP = EPI_WARPS + 1 + PROD_WARPS;
+constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS + 1);
 constexpr uint32_t TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_B + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_B + (size_t)NRAW * RAW_B + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -75,20 +85,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(PerBinArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)NSTAGE * STAGE_B);
-  uint64_t* full = bars;              // [NSTAGE] producers -> MMA
-  uint64_t* empty = bars + NSTAGE;    // [NSTAGE] MMA (tcgen05.commit) -> producers
+__device__ __forceinline__ void mb_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load: box {2 KB floats (KB frames x (re, im)), 64 rows (channels)} of S viewed as float32 [G C][2 Ts] -> smem [c][t] complex64
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x0, int row0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(s_u32(dst)), "l"(tm), "r"(x0), "r"(row0), "r"(s_u32(bar)) : "memory");
+}
+
+// S[g][c][t] = X[t][c][g] (t < T, zero up to Ts): reads coalesced along g, writes coalesced along t
+__global__ void k_cov_gather(PerBinArgs a) {
+  __shared__ float2 tile[32][33];
+  const int c = blockIdx.y;
+  const int g0 = blockIdx.x * 32, t0 = blockIdx.z * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, g = g0 + threadIdx.x;
+    tile[j][threadIdx.x] = (t < a.T && g < a.G) ? a.X[((size_t)t * a.C + c) * a.Gp + g] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int g = g0 + j, t = t0 + threadIdx.x;
+    if (g < a.G && t < a.Ts) a.Scov[((size_t)g * a.C + c) * a.Ts + t] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte alignment by OFFSET from the __shared__ symbol, so the compiler keeps the shared address space (LDS / STS): with a
+  // uintptr_t round trip every access became a generic LD.E / ST.E, which the mbarrier arrive below does not wait for
+  unsigned char* base = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* raw = base + (size_t)NSTAGE * STAGE_B;   // [NRAW][RAW_B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + (size_t)NRAW * RAW_B);
+  uint64_t* full = bars;              // [NSTAGE] transposers -> MMA
+  uint64_t* empty = bars + NSTAGE;    // [NSTAGE] MMA (tcgen05.commit) -> transposers
   uint64_t* accf = bars + 2 * NSTAGE; // [2] MMA -> epilogue
   uint64_t* acce = accf + 2;          // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+  uint64_t* rfull = acce + 2;         // [NRAW] TMA -> transposers
+  uint64_t* rempty = rfull + NRAW;    // [NRAW] transposers -> TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + NRAW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; s++) { mb_init(full + s, PROD_WARPS * 32); mb_init(empty + s, 1); }
     for (int b = 0; b < 2; b++) { mb_init(accf + b, 1); mb_init(acce + b, EPI_WARPS * 32); }
+    for (int s = 0; s < NRAW; s++) { mb_init(rfull + s, 1); mb_init(rempty + s, PROD_WARPS * 32); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -104,8 +146,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(PerBinArgs a) {
   const int ngroups = (G + NCH - 1) / NCH;
   const int NKB = (T + KB - 1) / KB;
 
-  if (warp > MMA_WARP) {
-    // ------------------------------------------------------------------------------------------------ producers
+  if (warp == TMA_WARP) {
+    // ------------------------------------------------------------------------------------------------ raw gather (TMA)
+    if (lane == 0) {
+      int it = 0;
+      for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        for (int kb = 0; kb < NKB; kb++, it++) {
+          const int rs = it % NRAW;
+          mb_wait(rempty + rs, (uint32_t)(((it / NRAW) & 1) ^ 1));
+          mb_expect_tx(rfull + rs, (uint32_t)RAW_B);
+          tma_load_2d(raw + (size_t)rs * RAW_B, &tmX, 2 * kb * KB, (NCH * grp) * C64, rfull + rs);                 // chain g0
+          tma_load_2d(raw + (size_t)rs * RAW_B + RAW_B / 2, &tmX, 2 * kb * KB, (NCH * grp + 1) * C64, rfull + rs); // chain g0 + 1 (rows past G C: zero fill)
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp > MMA_WARP) {
+    // ------------------------------------------------------------------------------------------------ transposers
     const int pw = warp - MMA_WARP - 1;   // 0..7 = (channel & 7) of every row this warp writes
     int it = 0;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -113,20 +170,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(PerBinArgs a) {
       const bool v1 = g0 + 1 < G;
       const int u0 = g0 / K, u1 = v1 ? (g0 + 1) / K : u0;
       for (int kb = 0; kb < NKB; kb++, it++) {
-        const int s = it % NSTAGE;
-        mb_wait(empty + s, (uint32_t)(((it / NSTAGE) & 1) ^ 1));
+        const int s = it % NSTAGE, rs = it % NRAW;
         const int t = kb * KB + lane;
         const bool inb = t < T;
         const bool m0 = inb && a.noise_mask[(size_t)t * U + u0] != 0;
         const bool m1 = inb && v1 && a.noise_mask[(size_t)t * U + u1] != 0;
-        float2 v[8][2];
+        mb_wait(rfull + rs, (uint32_t)((it / NRAW) & 1));
+        float4 v[8];
+        const unsigned char* rb = raw + (size_t)rs * RAW_B;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          const int c = pw + 8 * i;
-          const float2* px = a.X + ((size_t)t * C64 + c) * a.Gp + g0;
-          v[i][0] = m0 ? __ldg(px) : make_float2(0.f, 0.f);
-          v[i][1] = m1 ? __ldg(px + 1) : make_float2(0.f, 0.f);
+          const float2 x0 = *reinterpret_cast<const float2*>(rb + ((size_t)(pw + 8 * i) * KB + lane) * 8);
+          const float2 x1 = *reinterpret_cast<const float2*>(rb + RAW_B / 2 + ((size_t)(pw + 8 * i) * KB + lane) * 8);
+          v[i] = make_float4(m0 ? x0.x : 0.f, m0 ? x0.y : 0.f, m1 ? x1.x : 0.f, m1 ? x1.y : 0.f);   // (xr0, xi0, xr1, xi1)
         }
+        mb_wait(empty + s, (uint32_t)(((it / NSTAGE) & 1) ^ 1));
         unsigned char* sb = base + (size_t)s * STAGE_B;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -137,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(PerBinArgs a) {
           for (int j = 0; j < NCH; j++) {
             unsigned char* th = sb + (size_t)j * 2 * TILE_B;
             unsigned char* tl = th + TILE_B;
-            const float xr = v[i][j].x, xi = v[i][j].y;
+            const float xr = j ? v[i].z : v[i].x, xi = j ? v[i].w : v[i].y;
             const float hr = __uint_as_float(__float_as_uint(xr) & 0xffffe000u), hi = __uint_as_float(__float_as_uint(xi) & 0xffffe000u);
             *reinterpret_cast<float*>(th + off1) = hr; *reinterpret_cast<float*>(tl + off1) = xr - hr;
             *reinterpret_cast<float*>(th + off2) = hi; *reinterpret_cast<float*>(tl + off2) = xi - hi;
@@ -145,6 +203,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(PerBinArgs a) {
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
         mb_arrive(full + s);
+        // the raw slot is released only now: its values have been consumed by the stores above, so the loads have certainly
+        // completed before the TMA unit (async proxy) may overwrite the slot.  Releasing right after ISSUING the loads let the
+        // refill race them (sporadic 10-20 % errors in fully masked K-blocks, where the transposers run ahead).
+        mb_arrive(rempty + rs);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -228,17 +290,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(PerBinArgs a) {
 
 }  // namespace tc
 
-cudaError_t launch_covariance_tc(const PerBinArgs& a, cudaStream_t st) {
-  if (a.T <= 0 || a.G <= 0) return cudaSuccess;
-  if (a.C != tc::C64) return cudaErrorInvalidValue;
+// S viewed as float32 [G C rows][2 Ts]; box {2 KB floats, 64 rows}
+static cudaError_t make_series_map(CUtensorMap* tm, const PerBinArgs& a) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)2 * a.Ts, (cuuint64_t)a.G * a.C};
+  cuuint64_t gstride[1] = {(cuuint64_t)a.Ts * sizeof(float2)};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * tc::KB), (cuuint32_t)tc::C64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.Scov, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+size_t covariance_tc_workspace_bytes(int G, int C, int T) { return (size_t)G * C * (size_t)((T + tc::KB - 1) / tc::KB * tc::KB) * sizeof(float2); }
+
+// a.Scov: workspace of covariance_tc_workspace_bytes(G, C, T) bytes
+cudaError_t launch_covariance_tc(const PerBinArgs& a_in, cudaStream_t st) {
+  if (a_in.T <= 0 || a_in.G <= 0) return cudaSuccess;
+  if (a_in.C != tc::C64 || a_in.Scov == nullptr) return cudaErrorInvalidValue;
+  PerBinArgs a = a_in;
+  a.Ts = (a.T + tc::KB - 1) / tc::KB * tc::KB;
+  {
+    dim3 grid((a.G + 31) / 32, a.C, a.Ts / 32), block(32, 8);
+    tc::k_cov_gather<<<grid, block, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   cudaError_t e = cudaFuncSetAttribute(tc::k_covariance_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  CUtensorMap tm;
+  e = make_series_map(&tm, a);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ngroups = (a.G + tc::NCH - 1) / tc::NCH;
-  const int grid = ngroups < sms ? ngroups : sms;   // persistent: one CTA per SM (192 KiB of shared memory, all 512 TMEM columns)
-  tc::k_covariance_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a);
+  const int grid = ngroups < sms ? ngroups : sms;   // persistent: one CTA per SM (224 KiB of shared memory, all 512 TMEM columns)
+  tc::k_covariance_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tm, a);
   return cudaGetLastError();
 }
 

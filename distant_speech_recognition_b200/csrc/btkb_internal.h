@@ -63,6 +63,7 @@ struct PerBinArgs {
   LmsArgs lms;
   RlsArgs rls;
   float energy_threshold;
+  float2* Scov; int Ts;   // 64-mic tensor-core covariance: series-major workspace S[g][c][Ts] (btkb_cov_tc.cu)
 };
 
 // multi-channel WPE (btkb_wpe.cu)
@@ -113,7 +114,8 @@ cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st);
 // wide arrays (C = 16, 32, 64): btkb_wide.cu
 cudaError_t launch_perbin_wide(const PerBinArgs& a, cudaStream_t st);
 cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st);
-cudaError_t launch_covariance_tc(const PerBinArgs& a, cudaStream_t st);   // C = 64: tcgen05 / TMEM (btkb_cov_tc.cu)
+cudaError_t launch_covariance_tc(const PerBinArgs& a, cudaStream_t st);
+size_t covariance_tc_workspace_bytes(int G, int C, int T);   // C = 64: tcgen05 / TMEM (btkb_cov_tc.cu)
 cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count, cudaStream_t st);
 cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st);
 
