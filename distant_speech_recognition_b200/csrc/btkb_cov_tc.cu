@@ -15,13 +15,13 @@
 // Rows are interleaved in blocks of 8 ([Xr 0-7][Xi 0-7][Xr 8-15]...), so the TMEM lanes holding the Xr and the Xi row of a
 // channel sit 8 lanes apart in the same warp and the epilogue combines them with warp shuffles (no shared-memory pass).
 //
-// CTA = 14 warps, persistent over groups of 2 adjacent chains:
+// CTA = 22 warps, persistent over groups of 2 adjacent chains:
 //   (pre-pass)  k_cov_gather: series-major copy S[g][c][Ts] of X[t][c][g] through 32 x 32 shared-memory transposes.  A chain pair
 //               is a 16-byte column of X; reading such a column directly costs 26 ms at configs[3] whether per-lane loads
 //               (fully divergent) or a 3-D TMA box with a 16-byte inner extent do it (both measured), the coalesced pre-pass
 //               plus 256-byte TMA rows does not.
-//   warp 13     one thread loads the pair's K-block with two 2-D tensor-map TMAs: box {32 frames x (re, im), 64 channels} of S
-//   warps 5-12  transposers: one LDS.64 per (chain, channel, lane = frame), noise-frame masking
+//   warp 21     one thread loads the pair's K-block with two 2-D tensor-map TMAs: box {32 frames x (re, im), 64 channels} of S
+//   warps 5-20  transposers: one LDS.64 per (chain, channel, lane = frame), noise-frame masking
 //               (pybeamformer.py:963-975 via k_noise_mask), hi/lo split, st.shared into the swizzled operand tiles
 //               (conflict-free: a warp writes one 128-byte row), fence.proxy.async + mbarrier arrive
 //   warp 4      one elected thread issues the MMAs and tcgen05.commit's to the `empty` / `accumulator full` mbarriers
@@ -44,7 +44,7 @@ constexpr int STAGE_B = NCH * 2 * TILE_B;  // per chain: hi tile, lo tile
 constexpr int NSTAGE = 2;                  // operand stages
 constexpr int RAW_B = NCH * C64 * KB * 8;   // raw K-block of the pair: per chain [c][t] complex64
 constexpr int NRAW = 3;                    // raw stages
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int TMA_WARP = EPI_WARPS + 1 + PROD_WARPS;
 constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS + 1);
@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
     __syncwarp();
   } else if (warp > MMA_WARP) {
     // ------------------------------------------------------------------------------------------------ transposers
-    const int pw = warp - MMA_WARP - 1;   // 0..7 = (channel & 7) of every row this warp writes
+    const int pw = (warp - MMA_WARP - 1) & 7;    // (channel & 7) of every row this warp writes
+    const int ph = (warp - MMA_WARP - 1) >> 3;   // 0 / 1: which half of the 8-channel blocks (PROD_WARPS = 16)
+    constexpr int NI = 64 / PROD_WARPS;          // channels per warp
     int it = 0;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
       const int g0 = grp * NCH;
@@ -176,20 +178,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
         const bool m0 = inb && a.noise_mask[(size_t)t * U + u0] != 0;
         const bool m1 = inb && v1 && a.noise_mask[(size_t)t * U + u1] != 0;
         mb_wait(rfull + rs, (uint32_t)((it / NRAW) & 1));
-        float4 v[8];
+        float4 v[NI];
         const unsigned char* rb = raw + (size_t)rs * RAW_B;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const float2 x0 = *reinterpret_cast<const float2*>(rb + ((size_t)(pw + 8 * i) * KB + lane) * 8);
-          const float2 x1 = *reinterpret_cast<const float2*>(rb + RAW_B / 2 + ((size_t)(pw + 8 * i) * KB + lane) * 8);
+        for (int i = 0; i < NI; i++) {
+          const int cb = (PROD_WARPS == 16) ? 2 * i + ph : i;   // 8-channel block of this iteration
+          const float2 x0 = *reinterpret_cast<const float2*>(rb + ((size_t)(pw + 8 * cb) * KB + lane) * 8);
+          const float2 x1 = *reinterpret_cast<const float2*>(rb + RAW_B / 2 + ((size_t)(pw + 8 * cb) * KB + lane) * 8);
           v[i] = make_float4(m0 ? x0.x : 0.f, m0 ? x0.y : 0.f, m1 ? x1.x : 0.f, m1 ? x1.y : 0.f);   // (xr0, xi0, xr1, xi1)
         }
         mb_wait(empty + s, (uint32_t)(((it / NSTAGE) & 1) ^ 1));
         unsigned char* sb = base + (size_t)s * STAGE_B;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          // channel c = pw + 8 i: Xr row 16 i + pw, Xi row 16 i + 8 + pw; column = lane (frame within the K-block)
-          const uint32_t off1 = (uint32_t)(16 * i + pw) * 128u + ((uint32_t)((lane >> 2) ^ pw) << 4) + ((uint32_t)(lane & 3) << 2);
+        for (int i = 0; i < NI; i++) {
+          // channel c = pw + 8 cb: Xr row 16 cb + pw, Xi row 16 cb + 8 + pw; column = lane (frame within the K-block)
+          const int cb = (PROD_WARPS == 16) ? 2 * i + ph : i;
+          const uint32_t off1 = (uint32_t)(16 * cb + pw) * 128u + ((uint32_t)((lane >> 2) ^ pw) << 4) + ((uint32_t)(lane & 3) << 2);
           const uint32_t off2 = off1 + 8u * 128u;
 #pragma unroll
           for (int j = 0; j < NCH; j++) {

@@ -19,3 +19,5 @@ for name, labels in (("all frames (label never fires)", np.tile(np.array([[100.0
     xbytes = C * K * 8 * U * T; rbytes = C * C * K * 8 * U
     print(json.dumps({"cov64 " + name: dict(tc=os.environ.get("BTKB_COV_TC", "1"), ms=1e3 * s, hbm_frac_read_X_plus_write_R=(xbytes + rbytes) / s / 1e9 / 6530.3,
                                             tflops_complex_gram=8.0 * C * C * K * U * T / s / 1e12)}))
+s = timed(lambda: (p.calc_mvdr_weights(1e-4), p.synchronize()), steps=3, warm=1)
+print(json.dumps({"mvdr solve 64 x 64, 65 792 matrices": dict(ms=1e3 * s)}))
