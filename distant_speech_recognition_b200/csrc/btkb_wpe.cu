@@ -245,28 +245,42 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
       const int r = i / WPE_NB, jj = i - r * WPE_NB;
       Pn[i] = (jj < nb && jj <= r) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
     }
-    // ---- factor it: column by column, one thread per row
-    for (int jj = 0; jj < nb; jj++) {
-      __syncthreads();   // the panel load / the previous column's row updates (incl. this pivot) are visible
-      const RT dj = Pn[jj * WPE_NB + jj].x;
-      if (!(dj > (RT)0)) bad = true;
-      const RT inv = (RT)1 / sqrt(fmax(dj, (RT)1e-30));
-      __syncthreads();   // everybody has read the pivot before its owner overwrites it
-      for (int r = tid; r < nrows; r += blockDim.x) {
-        if (r == jj) Pn[r * WPE_NB + jj] = mk<RT>(dj * inv, 0);
-        else if (r > jj) { CX v = Pn[r * WPE_NB + jj]; Pn[r * WPE_NB + jj] = mk<RT>(v.x * inv, v.y * inv); }
-      }
-      __syncthreads();
-      for (int r = tid; r < nrows; r += blockDim.x) {
-        if (r <= jj) continue;
-        const CX lij = Pn[r * WPE_NB + jj];
-        const int kend = min(nb - 1, r);
-        for (int kk = jj + 1; kk <= kend; kk++) {
-          CX v = Pn[r * WPE_NB + kk];
-          cmsubc(v, lij, Pn[kk * WPE_NB + jj]);
-          if (kk == r) v.y = 0;
-          Pn[r * WPE_NB + kk] = v;
+    __syncthreads();
+    // ---- factor the nb x nb diagonal block with ONE warp (lane = row, __syncwarp between the dependent steps) ...
+    if (tid < 32) {
+      const int r = tid;
+      for (int jj = 0; jj < nb; jj++) {
+        const RT dj = Pn[jj * WPE_NB + jj].x;
+        if (!(dj > (RT)0)) bad = true;
+        const RT inv = (RT)1 / sqrt(fmax(dj, (RT)1e-30));
+        __syncwarp();   // every lane has read the pivot before its owner overwrites it
+        if (r < nb) {
+          if (r == jj) Pn[r * WPE_NB + jj] = mk<RT>(dj * inv, 0);
+          else if (r > jj) { CX v = Pn[r * WPE_NB + jj]; Pn[r * WPE_NB + jj] = mk<RT>(v.x * inv, v.y * inv); }
         }
+        __syncwarp();
+        if (r < nb && r > jj) {
+          const CX lij = Pn[r * WPE_NB + jj];
+          for (int kk = jj + 1; kk <= r; kk++) {
+            CX v = Pn[r * WPE_NB + kk];
+            cmsubc(v, lij, Pn[kk * WPE_NB + jj]);
+            if (kk == r) v.y = 0;
+            Pn[r * WPE_NB + kk] = v;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- ... then the rows below it are independent: L21 = A21 L11^-H, one thread per row, no barrier (the earlier
+    // column-by-column sweep over the whole panel cost three CTA barriers per column, ~800 per matrix)
+    for (int r = nb + tid; r < nrows; r += blockDim.x) {
+      CX* pr = Pn + (size_t)r * WPE_NB;
+      for (int jj = 0; jj < nb; jj++) {
+        CX v = pr[jj];
+        for (int q = 0; q < jj; q++) cmsubc(v, pr[q], Pn[jj * WPE_NB + q]);
+        const RT inv = (RT)1 / Pn[jj * WPE_NB + jj].x;
+        pr[jj] = mk<RT>(v.x * inv, v.y * inv);
       }
     }
     __syncthreads();
