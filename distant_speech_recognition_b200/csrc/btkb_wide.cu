@@ -231,83 +231,85 @@ __device__ __forceinline__ cdw cwmul(cdw a, cdw b) { return cw(a.x * b.x - a.y *
 __device__ __forceinline__ cdw cwsub(cdw a, cdw b) { return cw(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ cdw cwdiv(cdw a, cdw b) { double d = b.x * b.x + b.y * b.y; return cw((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d); }
 
-// blockDim.x = max(C, 32) threads, thread r owns row r.  Per column: the pivot search is a warp arg-max (shuffles) combined
-// across the (at most two) warps through shared memory, the row swap is spread over the threads, the elimination is one row
-// per thread; the back substitution runs column-oriented with every row updating itself.  Two barriers per column (an
-// earlier version searched the pivot and back-substituted on thread 0 alone: 34 ms at configs[3], 230 us per matrix).
+// blockDim.x = 4 C threads: thread (r = tid % C, q = tid / C) owns the columns c = q (mod 4) of row r, so a warp covers 32
+// rows and the elimination of one column is spread over 4 C threads (8 warps at C = 64: enough to hide the fp64 / shared
+// memory latency that one thread per row could not; 34 ms -> 23 ms -> see profiles/ at configs[3]).  Per column: warp arg-max
+// pivot search on the q = 0 threads combined through shared memory, distributed row swap, elimination; two barriers per
+// column.  The back substitution runs column-oriented with every row updating itself.
+constexpr int SOLVE_Q = 4;
 __global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize) {
   extern __shared__ __align__(16) unsigned char sm[];
   cdw* A = reinterpret_cast<cdw*>(sm);          // [C][C+1] augmented, row-major
   __shared__ double wbest[2]; __shared__ int widx[2];
   __shared__ double lam_part[2][2];
-  const int g = blockIdx.x, r = threadIdx.x;
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int r = tid % C, q = tid / C;           // blockDim.x == SOLVE_Q * C
   const int u = g / K, k = g - u * K;
-  const bool row = r < C;
-  const int nwarp = (int)(blockDim.x >> 5);
-  if (k == 0) { if (row) W[(size_t)r * Gp + g] = make_float2(1.f, 0.f); return; }
+  const int nwarp0 = (C + 31) / 32;             // warps holding the q = 0 threads
+  if (k == 0) { if (tid < C) W[(size_t)tid * Gp + g] = make_float2(1.f, 0.f); return; }
   double scale = 1.0;
   if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
   const int LD = C + 1;
   // A = R^H with loading; row r of A = conj of column r of R
-  if (row) {
-    for (int c = 0; c < C; c++) {
-      float2 t = R[(size_t)(c * C + r) * Gp + g];
-      cdw v = cw((double)t.x * scale, -(double)t.y * scale);
-      if (c == r) v.x += (double)mu;
-      A[r * LD + c] = v;
-    }
-    float2 t = Dm[(size_t)r * Gp + g]; A[r * LD + C] = cw(t.x, t.y);
+  for (int c = q; c < C; c += SOLVE_Q) {
+    float2 t = R[(size_t)(c * C + r) * Gp + g];
+    cdw v = cw((double)t.x * scale, -(double)t.y * scale);
+    if (c == r) v.x += (double)mu;
+    A[r * LD + c] = v;
   }
+  if (q == 0) { float2 t = Dm[(size_t)r * Gp + g]; A[r * LD + C] = cw(t.x, t.y); }
   __syncthreads();
   bool singular = false;
   for (int col = 0; col < C; col++) {
-    // pivot: largest |A[q][col]|, q >= col (ties: the smallest row index, like a serial scan)
-    double m2 = -1.0; int idx = r;
-    if (row && r >= col) { const cdw v = A[r * LD + col]; m2 = v.x * v.x + v.y * v.y; }
+    // pivot: largest |A[row][col]|, row >= col (ties: the smallest row index, like a serial scan)
+    if (tid < 32 * nwarp0) {
+      double m2 = -1.0; int idx = tid;
+      if (tid < C && tid >= col) { const cdw v = A[tid * LD + col]; m2 = v.x * v.x + v.y * v.y; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double om = __shfl_xor_sync(0xffffffffu, m2, o); const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (om > m2 || (om == m2 && oi < idx)) { m2 = om; idx = oi; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double om = __shfl_xor_sync(0xffffffffu, m2, o); const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (om > m2 || (om == m2 && oi < idx)) { m2 = om; idx = oi; }
+      }
+      if ((tid & 31) == 0) { wbest[tid >> 5] = m2; widx[tid >> 5] = idx; }
     }
-    if ((r & 31) == 0) { wbest[r >> 5] = m2; widx[r >> 5] = idx; }
     __syncthreads();
     double best = wbest[0]; int piv = widx[0];
-    if (nwarp > 1 && (wbest[1] > best)) { best = wbest[1]; piv = widx[1]; }
+    if (nwarp0 > 1 && (wbest[1] > best)) { best = wbest[1]; piv = widx[1]; }
     if (!(best > 1e-60)) { singular = true; break; }   // uniform over the CTA
-    if (piv != col && row) {   // swap rows col <-> piv: thread r handles column r (thread 0 also the right-hand side)
-      cdw t = A[col * LD + r]; A[col * LD + r] = A[piv * LD + r]; A[piv * LD + r] = t;
-      if (r == 0) { cdw t2 = A[col * LD + C]; A[col * LD + C] = A[piv * LD + C]; A[piv * LD + C] = t2; }
-    }
+    if (piv != col)
+      for (int c = tid; c <= C; c += blockDim.x) { cdw t = A[col * LD + c]; A[col * LD + c] = A[piv * LD + c]; A[piv * LD + c] = t; }
     __syncthreads();
-    if (row && r > col) {
-      const cdw f = cwdiv(A[r * LD + col], A[col * LD + col]);
-      for (int c = col + 1; c <= C; c++) A[r * LD + c] = cwsub(A[r * LD + c], cwmul(f, A[col * LD + c]));
+    if (r > col) {
+      const cdw f = cwdiv(A[r * LD + col], A[col * LD + col]);   // column `col` of this row is not written in this step
+      for (int c = col + 1 + q; c <= C; c += SOLVE_Q) A[r * LD + c] = cwsub(A[r * LD + c], cwmul(f, A[col * LD + c]));
     }
-    // no barrier here: the next pivot search reads only this thread's own row; the swap waits behind the next barrier
+    __syncthreads();   // rows are shared by four threads now: the next pivot search reads what the other three wrote
   }
   __syncthreads();
   if (!singular) {
     // column-oriented back substitution into column C: x_i = b_i / a_ii, then every row r < i subtracts a_ri x_i from its b_r
     for (int i = C - 1; i >= 0; i--) {
-      if (r == i) A[i * LD + C] = cwdiv(A[i * LD + C], A[i * LD + i]);
+      if (tid == i) A[i * LD + C] = cwdiv(A[i * LD + C], A[i * LD + i]);
       __syncthreads();
-      if (row && r < i) A[r * LD + C] = cwsub(A[r * LD + C], cwmul(A[r * LD + i], A[i * LD + C]));
+      if (tid < i) A[tid * LD + C] = cwsub(A[tid * LD + C], cwmul(A[tid * LD + i], A[i * LD + C]));
     }
-  } else if (row) {
-    float2 t = Dm[(size_t)r * Gp + g]; A[r * LD + C] = cw(t.x, t.y);   // identity fallback (beamformer.cc:2381-2383)
+  } else if (tid < C) {
+    float2 t = Dm[(size_t)tid * Gp + g]; A[tid * LD + C] = cw(t.x, t.y);   // identity fallback (beamformer.cc:2381-2383)
   }
   // Lambda = t^H d (times C)
-  double lr = 0.0, li = 0.0;
-  if (row) { const float2 d = Dm[(size_t)r * Gp + g]; const cdw tv = A[r * LD + C]; lr = tv.x * d.x + tv.y * d.y; li = tv.x * d.y - tv.y * d.x; }
+  if (tid < 32 * nwarp0) {
+    double lr = 0.0, li = 0.0;
+    if (tid < C) { const float2 d = Dm[(size_t)tid * Gp + g]; const cdw tv = A[tid * LD + C]; lr = tv.x * d.x + tv.y * d.y; li = tv.x * d.y - tv.y * d.x; }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { lr += __shfl_xor_sync(0xffffffffu, lr, o); li += __shfl_xor_sync(0xffffffffu, li, o); }
-  if ((r & 31) == 0) { lam_part[r >> 5][0] = lr; lam_part[r >> 5][1] = li; }
+    for (int o = 16; o > 0; o >>= 1) { lr += __shfl_xor_sync(0xffffffffu, lr, o); li += __shfl_xor_sync(0xffffffffu, li, o); }
+    if ((tid & 31) == 0) { lam_part[tid >> 5][0] = lr; lam_part[tid >> 5][1] = li; }
+  }
   __syncthreads();
   double lam_re = lam_part[0][0], lam_im = lam_part[0][1];
-  if (nwarp > 1) { lam_re += lam_part[1][0]; lam_im += lam_part[1][1]; }
-  if (row) {
-    const cdw wv = cwdiv(A[r * LD + C], cw(lam_re * C, lam_im * C));
-    W[(size_t)r * Gp + g] = make_float2((float)wv.x, (float)wv.y);
+  if (nwarp0 > 1) { lam_re += lam_part[1][0]; lam_im += lam_part[1][1]; }
+  if (tid < C) {
+    const cdw wv = cwdiv(A[tid * LD + C], cw(lam_re * C, lam_im * C));
+    W[(size_t)tid * Gp + g] = make_float2((float)wv.x, (float)wv.y);
   }
 }
 
@@ -378,7 +380,7 @@ cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, 
   const size_t smem = sizeof(wide::cdw) * (size_t)C * (C + 1);
   cudaError_t e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  wide::k_mvdr_solve_wide<<<U * K, (C < 32 ? 32 : C), smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count);
+  wide::k_mvdr_solve_wide<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count);
   return cudaGetLastError();
 }
 
