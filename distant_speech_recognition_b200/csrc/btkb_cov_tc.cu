@@ -27,7 +27,7 @@
 //   warp 4      one elected thread issues the MMAs and tcgen05.commit's to the `empty` / `accumulator full` mbarriers
 //   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns), shuffle-combine, R[(c C + c')][g] complex64 stores;
 //               TMEM is double-buffered (2 x 2 chains x 128 columns = 512 columns), so it overlaps the next group's MMAs
-// Shared memory: 2 operand stages x (2 chains x (hi + lo) x 16 KiB) + 3 raw stages x 32 KiB = 224 KiB.
+// Shared memory: 4 operand stages x (hi + lo) x 16 KiB + 6 raw stages x 16 KiB = 224 KiB (the pipeline unit is one chain's K-block).
 #include <cuda.h>
 #include "btkb_internal.h"
 #include <stdint.h>
@@ -40,10 +40,10 @@ constexpr int C64 = 64;
 constexpr int KB = 32;                     // frames per K-block = tf32 elements of one 128-byte operand row
 constexpr int TILE_B = 128 * 128;          // one operand tile: 128 rows x 128 bytes
 constexpr int NCH = 2;                     // chains per group
-constexpr int STAGE_B = NCH * 2 * TILE_B;  // per chain: hi tile, lo tile
-constexpr int NSTAGE = 2;                  // operand stages
-constexpr int RAW_B = NCH * C64 * KB * 8;   // raw K-block of the pair: per chain [c][t] complex64
-constexpr int NRAW = 3;                    // raw stages
+constexpr int STAGE_B = 2 * TILE_B;        // one pipeline unit = one chain's K-block: hi tile, lo tile
+constexpr int NSTAGE = 4;                  // operand stages
+constexpr int RAW_B = C64 * KB * 8;        // raw K-block of one chain: [c][t] complex64
+constexpr int NRAW = 6;                    // raw stages
 constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int TMA_WARP = EPI_WARPS + 1 + PROD_WARPS;
@@ -146,17 +146,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
   const int ngroups = (G + NCH - 1) / NCH;
   const int NKB = (T + KB - 1) / KB;
 
+  // The pipeline unit is ONE chain's K-block (it = ((group, kb), j), j fastest): 4 operand stages and 6 raw stages in the same
+  // 224 KiB give twice the depth of pair-sized stages, which this latency-bound pipeline needs.
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------------ raw gather (TMA)
     if (lane == 0) {
       int it = 0;
       for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        for (int kb = 0; kb < NKB; kb++, it++) {
-          const int rs = it % NRAW;
-          mb_wait(rempty + rs, (uint32_t)(((it / NRAW) & 1) ^ 1));
-          mb_expect_tx(rfull + rs, (uint32_t)RAW_B);
-          tma_load_2d(raw + (size_t)rs * RAW_B, &tmX, 2 * kb * KB, (NCH * grp) * C64, rfull + rs);                 // chain g0
-          tma_load_2d(raw + (size_t)rs * RAW_B + RAW_B / 2, &tmX, 2 * kb * KB, (NCH * grp + 1) * C64, rfull + rs); // chain g0 + 1 (rows past G C: zero fill)
+        for (int kb = 0; kb < NKB; kb++) {
+          for (int j = 0; j < NCH; j++, it++) {
+            const int rs = it % NRAW;
+            mb_wait(rempty + rs, (uint32_t)(((it / NRAW) & 1) ^ 1));
+            mb_expect_tx(rfull + rs, (uint32_t)RAW_B);
+            tma_load_2d(raw + (size_t)rs * RAW_B, &tmX, 2 * kb * KB, (NCH * grp + j) * C64, rfull + rs);   // rows past G C: zero fill
+          }
         }
       }
     }
@@ -169,48 +172,42 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
     int it = 0;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
       const int g0 = grp * NCH;
-      const bool v1 = g0 + 1 < G;
-      const int u0 = g0 / K, u1 = v1 ? (g0 + 1) / K : u0;
-      for (int kb = 0; kb < NKB; kb++, it++) {
-        const int s = it % NSTAGE, rs = it % NRAW;
+      for (int kb = 0; kb < NKB; kb++) {
         const int t = kb * KB + lane;
-        const bool inb = t < T;
-        const bool m0 = inb && a.noise_mask[(size_t)t * U + u0] != 0;
-        const bool m1 = inb && v1 && a.noise_mask[(size_t)t * U + u1] != 0;
-        mb_wait(rfull + rs, (uint32_t)((it / NRAW) & 1));
-        float4 v[NI];
-        const unsigned char* rb = raw + (size_t)rs * RAW_B;
+        for (int j = 0; j < NCH; j++, it++) {
+          const int s = it % NSTAGE, rs = it % NRAW;
+          const bool vj = g0 + j < G;
+          const bool m = vj && t < T && a.noise_mask[(size_t)t * U + (g0 + j) / K] != 0;
+          mb_wait(rfull + rs, (uint32_t)((it / NRAW) & 1));
+          float2 v[NI];
+          const unsigned char* rb = raw + (size_t)rs * RAW_B;
 #pragma unroll
-        for (int i = 0; i < NI; i++) {
-          const int cb = (PROD_WARPS == 16) ? 2 * i + ph : i;   // 8-channel block of this iteration
-          const float2 x0 = *reinterpret_cast<const float2*>(rb + ((size_t)(pw + 8 * cb) * KB + lane) * 8);
-          const float2 x1 = *reinterpret_cast<const float2*>(rb + RAW_B / 2 + ((size_t)(pw + 8 * cb) * KB + lane) * 8);
-          v[i] = make_float4(m0 ? x0.x : 0.f, m0 ? x0.y : 0.f, m1 ? x1.x : 0.f, m1 ? x1.y : 0.f);   // (xr0, xi0, xr1, xi1)
-        }
-        mb_wait(empty + s, (uint32_t)(((it / NSTAGE) & 1) ^ 1));
-        unsigned char* sb = base + (size_t)s * STAGE_B;
+          for (int i = 0; i < NI; i++) {
+            const int cb = (PROD_WARPS == 16) ? 2 * i + ph : i;   // 8-channel block of this iteration
+            const float2 x0 = *reinterpret_cast<const float2*>(rb + ((size_t)(pw + 8 * cb) * KB + lane) * 8);
+            v[i] = make_float2(m ? x0.x : 0.f, m ? x0.y : 0.f);
+          }
+          mb_wait(empty + s, (uint32_t)(((it / NSTAGE) & 1) ^ 1));
+          unsigned char* th = base + (size_t)s * STAGE_B;
+          unsigned char* tl = th + TILE_B;
 #pragma unroll
-        for (int i = 0; i < NI; i++) {
-          // channel c = pw + 8 cb: Xr row 16 cb + pw, Xi row 16 cb + 8 + pw; column = lane (frame within the K-block)
-          const int cb = (PROD_WARPS == 16) ? 2 * i + ph : i;
-          const uint32_t off1 = (uint32_t)(16 * cb + pw) * 128u + ((uint32_t)((lane >> 2) ^ pw) << 4) + ((uint32_t)(lane & 3) << 2);
-          const uint32_t off2 = off1 + 8u * 128u;
-#pragma unroll
-          for (int j = 0; j < NCH; j++) {
-            unsigned char* th = sb + (size_t)j * 2 * TILE_B;
-            unsigned char* tl = th + TILE_B;
-            const float xr = j ? v[i].z : v[i].x, xi = j ? v[i].w : v[i].y;
+          for (int i = 0; i < NI; i++) {
+            // channel c = pw + 8 cb: Xr row 16 cb + pw, Xi row 16 cb + 8 + pw; column = lane (frame within the K-block)
+            const int cb = (PROD_WARPS == 16) ? 2 * i + ph : i;
+            const uint32_t off1 = (uint32_t)(16 * cb + pw) * 128u + ((uint32_t)((lane >> 2) ^ pw) << 4) + ((uint32_t)(lane & 3) << 2);
+            const uint32_t off2 = off1 + 8u * 128u;
+            const float xr = v[i].x, xi = v[i].y;
             const float hr = __uint_as_float(__float_as_uint(xr) & 0xffffe000u), hi = __uint_as_float(__float_as_uint(xi) & 0xffffe000u);
             *reinterpret_cast<float*>(th + off1) = hr; *reinterpret_cast<float*>(tl + off1) = xr - hr;
             *reinterpret_cast<float*>(th + off2) = hi; *reinterpret_cast<float*>(tl + off2) = xi - hi;
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
+          mb_arrive(full + s);
+          // the raw slot is released only now: its values have been consumed by the stores above, so the loads have certainly
+          // completed before the TMA unit (async proxy) may overwrite the slot.  Releasing right after ISSUING the loads let the
+          // refill race them (sporadic 10-20 % errors in fully masked K-blocks, where the transposers run ahead).
+          mb_arrive(rempty + rs);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
-        mb_arrive(full + s);
-        // the raw slot is released only now: its values have been consumed by the stores above, so the loads have certainly
-        // completed before the TMA unit (async proxy) may overwrite the slot.  Releasing right after ISSUING the loads let the
-        // refill race them (sporadic 10-20 % errors in fully masked K-blocks, where the transposers run ahead).
-        mb_arrive(rempty + rs);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -221,14 +218,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
         const int b = gi & 1;
         mb_wait(acce + b, (uint32_t)(((gi >> 1) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kb = 0; kb < NKB; kb++, it++) {
-          const int s = it % NSTAGE;
-          mb_wait(full + s, (uint32_t)((it / NSTAGE) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = s_u32(base + (size_t)s * STAGE_B);
-#pragma unroll
-          for (int j = 0; j < NCH; j++) {
-            const uint32_t ah = sa + (uint32_t)j * 2 * TILE_B, al = ah + TILE_B;
+        for (int kb = 0; kb < NKB; kb++) {
+          for (int j = 0; j < NCH; j++, it++) {
+            const int s = it % NSTAGE;
+            mb_wait(full + s, (uint32_t)((it / NSTAGE) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = s_u32(base + (size_t)s * STAGE_B), al = ah + TILE_B;
             const uint32_t d = tmem_base + (uint32_t)(b * NCH * 128 + j * 128);
 #pragma unroll
             for (int ks = 0; ks < KB / 8; ks++) {
@@ -237,8 +232,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
               umma_tf32(d, dl, dh, 1u);                               // lo hi^T
               umma_tf32(d, dh, dl, 1u);                               // hi lo^T
             }
+            umma_commit(empty + s);   // the slot may be refilled once these MMAs have read it
           }
-          umma_commit(empty + s);   // the slot may be refilled once these MMAs have read it
         }
         umma_commit(accf + b);      // accumulators of this group complete
       }
