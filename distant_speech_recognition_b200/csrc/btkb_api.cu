@@ -189,7 +189,7 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
     const int lo = (cfg->wpe.band_width == 0.0) ? M / 2 : (int)((cfg->wpe.band_width / (cfg->samplerate / 2.0)) * (M / 2));  // set_band_width_ (:365-373)
     p->wpe_nbins = std::min(lo, p->K - 1) + 1;
     const char* ce = getenv("BTKB_WPE_CHUNK");
-    p->wpe_chunk = ce ? std::max(1, atoi(ce)) : 56;   // 56 x C = 448 Cholesky CTAs = one wave at 3 CTAs/SM on 148 SMs
+    p->wpe_chunk = ce ? std::max(1, atoi(ce)) : 55;   // 55 x 8 = 440 Cholesky CTAs fit one wave at 3 CTAs/SM x 148 SMs (56 spills 4 CTAs into a second wave: 663 -> 862 ms measured)
     p->wpe_chunk = std::min(p->wpe_chunk, p->Ucap * p->wpe_nbins);
     for (auto& ev : p->wev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     A((void**)&p->d_wS, (size_t)p->Ucap * p->K * C * p->wpe_Ts * sizeof(float2));
