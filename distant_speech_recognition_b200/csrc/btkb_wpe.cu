@@ -25,6 +25,7 @@ namespace btkb {
 namespace {
 
 constexpr int WPE_NB = 16;        // Cholesky panel width
+constexpr int WPE_LD = WPE_NB + 1; // row stride of the panel in shared memory (elements)
 constexpr int WPE_CORR_THREADS = 256;
 constexpr int WPE_CHOL_THREADS = 256;
 
@@ -211,9 +212,11 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
   const int g = problem_chain(a, q0 + qq);
   const int L = a.L, Lr = a.Lr, n = L + 1;
   CX* A = reinterpret_cast<CX*>(a.Rw) + ((size_t)qq * C + c) * (size_t)n * Lr;
-  CX* Pn = reinterpret_cast<CX*>(smem);                   // [n][WPE_NB] current panel (rows relative to j0)
-  CX* yv = Pn + (size_t)n * WPE_NB;                        // [L]
-  RT* red = reinterpret_cast<RT*>(yv + L);                 // [32]
+  CX* Pn = reinterpret_cast<CX*>(smem);                   // [n][WPE_LD] current panel (rows relative to j0); row stride 17
+                                                           // elements: lanes on consecutive rows hit different banks
+  CX* yv = Pn + (size_t)WPE_NB * WPE_LD;                   // [L] back-substitution vector: lives inside the panel buffer (the
+                                                           // back substitution only needs its first WPE_NB rows as the diagonal block)
+  RT* red = reinterpret_cast<RT*>(Pn + (size_t)n * WPE_LD); // [32]
   const int tid = threadIdx.x;
   const RT bias = (RT)a.diagonal_bias, loadf = (RT)a.load_factor;
 
@@ -243,29 +246,29 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     // ---- load the panel
     for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
       const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      Pn[i] = (jj < nb && jj <= r) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
+      Pn[r * WPE_LD + jj] = (jj < nb && jj <= r) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
     }
     __syncthreads();
     // ---- factor the nb x nb diagonal block with ONE warp (lane = row, __syncwarp between the dependent steps) ...
     if (tid < 32) {
       const int r = tid;
       for (int jj = 0; jj < nb; jj++) {
-        const RT dj = Pn[jj * WPE_NB + jj].x;
+        const RT dj = Pn[jj * WPE_LD + jj].x;
         if (!(dj > (RT)0)) bad = true;
         const RT inv = (RT)1 / sqrt(fmax(dj, (RT)1e-30));
         __syncwarp();   // every lane has read the pivot before its owner overwrites it
         if (r < nb) {
-          if (r == jj) Pn[r * WPE_NB + jj] = mk<RT>(dj * inv, 0);
-          else if (r > jj) { CX v = Pn[r * WPE_NB + jj]; Pn[r * WPE_NB + jj] = mk<RT>(v.x * inv, v.y * inv); }
+          if (r == jj) Pn[r * WPE_LD + jj] = mk<RT>(dj * inv, 0);
+          else if (r > jj) { CX v = Pn[r * WPE_LD + jj]; Pn[r * WPE_LD + jj] = mk<RT>(v.x * inv, v.y * inv); }
         }
         __syncwarp();
         if (r < nb && r > jj) {
-          const CX lij = Pn[r * WPE_NB + jj];
+          const CX lij = Pn[r * WPE_LD + jj];
           for (int kk = jj + 1; kk <= r; kk++) {
-            CX v = Pn[r * WPE_NB + kk];
-            cmsubc(v, lij, Pn[kk * WPE_NB + jj]);
+            CX v = Pn[r * WPE_LD + kk];
+            cmsubc(v, lij, Pn[kk * WPE_LD + jj]);
             if (kk == r) v.y = 0;
-            Pn[r * WPE_NB + kk] = v;
+            Pn[r * WPE_LD + kk] = v;
           }
         }
         __syncwarp();
@@ -275,11 +278,11 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     // ---- ... then the rows below it are independent: L21 = A21 L11^-H, one thread per row, no barrier (the earlier
     // column-by-column sweep over the whole panel cost three CTA barriers per column, ~800 per matrix)
     for (int r = nb + tid; r < nrows; r += blockDim.x) {
-      CX* pr = Pn + (size_t)r * WPE_NB;
+      CX* pr = Pn + (size_t)r * WPE_LD;
       for (int jj = 0; jj < nb; jj++) {
         CX v = pr[jj];
-        for (int q = 0; q < jj; q++) cmsubc(v, pr[q], Pn[jj * WPE_NB + q]);
-        const RT inv = (RT)1 / Pn[jj * WPE_NB + jj].x;
+        for (int q = 0; q < jj; q++) cmsubc(v, pr[q], Pn[jj * WPE_LD + q]);
+        const RT inv = (RT)1 / Pn[jj * WPE_LD + jj].x;
         pr[jj] = mk<RT>(v.x * inv, v.y * inv);
       }
     }
@@ -287,38 +290,51 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     // ---- write the factored panel back (needed by the backward substitution)
     for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
       const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      if (jj < nb && jj <= r) A[(size_t)(j0 + r) * Lr + j0 + jj] = Pn[i];
+      if (jj < nb && jj <= r) A[(size_t)(j0 + r) * Lr + j0 + jj] = Pn[r * WPE_LD + jj];
     }
     // ---- trailing update: A[i][k] -= sum_jj Pn[i][jj] conj(Pn[k][jj]) for j1 <= k <= i <= L
     const int j1 = j0 + nb;
     const int nt = n - j1;             // trailing rows (incl. the augmented one)
     if (nt > 0) {
-      const int nt2 = (nt + 1) / 2;
-      const int ntiles = nt2 * (nt2 + 1) / 2;
-      for (int tq = tid; tq < ntiles; tq += blockDim.x) {
-        int bi = (int)((sqrtf(8.0f * (float)tq + 1.0f) - 1.0f) * 0.5f);
-        while ((bi + 1) * (bi + 2) / 2 <= tq) bi++;
-        while (bi * (bi + 1) / 2 > tq) bi--;
-        const int bj = tq - bi * (bi + 1) / 2;
-        const int ri0 = 2 * bi, ri1 = min(ri0 + 1, nt - 1), rk0 = 2 * bj, rk1 = min(rk0 + 1, nt - 1);
-        const CX* pi0 = Pn + (size_t)(nb + ri0) * WPE_NB;
-        const CX* pi1 = Pn + (size_t)(nb + ri1) * WPE_NB;
-        const CX* pk0 = Pn + (size_t)(nb + rk0) * WPE_NB;
-        const CX* pk1 = Pn + (size_t)(nb + rk1) * WPE_NB;
-        CX s00 = mk<RT>(0, 0), s01 = s00, s10 = s00, s11 = s00;
+      // A thread owns the entries (ri + q nt4, rk + p nt4), q, p = 0..3, of the trailing block (nt4 = ceil(nt / 4)): the
+      // four-way interleave puts the lanes of a warp on CONSECUTIVE panel rows (conflict-free 16-byte loads with the padded
+      // stride, the row operand is a broadcast) and makes the global read-modify-write of A coalesced along a row.  Of the
+      // 16 entries the 6 with q > p always lie in the lower triangle, the 4 with q == p do iff rk <= ri, the rest never.
+      const int nt4 = (nt + 3) / 4;
+      for (int tq = tid; tq < nt4 * nt4; tq += blockDim.x) {
+        const int ri = tq / nt4, rk = tq - ri * nt4;
+        const bool diag = rk <= ri;
+        const CX* pa[4]; const CX* pb[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          pa[q] = Pn + (size_t)(nb + min(ri + q * nt4, nt - 1)) * WPE_LD;
+          pb[q] = Pn + (size_t)(nb + min(rk + q * nt4, nt - 1)) * WPE_LD;
+        }
+        CX sd[4], so[6];
+#pragma unroll
+        for (int e = 0; e < 4; e++) sd[e] = mk<RT>(0, 0);
+#pragma unroll
+        for (int e = 0; e < 6; e++) so[e] = mk<RT>(0, 0);
         for (int jj = 0; jj < nb; jj++) {
-          const CX a0 = pi0[jj], a1 = pi1[jj], b0 = pk0[jj], b1 = pk1[jj];
-          cmsubc(s00, a0, b0); cmsubc(s01, a0, b1); cmsubc(s10, a1, b0); cmsubc(s11, a1, b1);
+          CX av[4], bv[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) { av[q] = pa[q][jj]; bv[q] = pb[q][jj]; }
+          if (diag) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) cmsubc(sd[q], av[q], bv[q]);
+          }
+          cmsubc(so[0], av[1], bv[0]); cmsubc(so[1], av[2], bv[0]); cmsubc(so[2], av[2], bv[1]);
+          cmsubc(so[3], av[3], bv[0]); cmsubc(so[4], av[3], bv[1]); cmsubc(so[5], av[3], bv[2]);
         }
-        const int i0 = j1 + ri0, k0 = j1 + rk0;
-        CX* r0 = A + (size_t)i0 * Lr + k0;
-        { CX v = r0[0]; v.x += s00.x; v.y += s00.y; r0[0] = v; }
-        if (rk0 + 1 < nt && rk0 + 1 <= ri0) { CX v = r0[1]; v.x += s01.x; v.y += s01.y; r0[1] = v; }
-        if (ri0 + 1 < nt) {
-          CX* r1 = r0 + Lr;
-          { CX v = r1[0]; v.x += s10.x; v.y += s10.y; r1[0] = v; }
-          if (rk0 + 1 < nt) { CX v = r1[1]; v.x += s11.x; v.y += s11.y; r1[1] = v; }
+        auto upd = [&](int q, int pcol, const CX& sv) {
+          const int row = ri + q * nt4, col = rk + pcol * nt4;
+          if (row < nt && col < nt) { CX* dst = A + (size_t)(j1 + row) * Lr + j1 + col; CX v = *dst; v.x += sv.x; v.y += sv.y; *dst = v; }
+        };
+        if (diag) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) upd(q, q, sd[q]);
         }
+        upd(1, 0, so[0]); upd(2, 0, so[1]); upd(2, 1, so[2]); upd(3, 0, so[3]); upd(3, 1, so[4]); upd(3, 2, so[5]);
       }
     }
     __syncthreads();
@@ -333,14 +349,14 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     const int nb = min(WPE_NB, L - j0);
     for (int i = tid; i < nb * WPE_NB; i += blockDim.x) {
       const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      Db[i] = (jj <= r && jj < nb) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
+      Db[r * WPE_LD + jj] = (jj <= r && jj < nb) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
     }
     __syncthreads();
     if (tid == 0) {
       for (int jj = nb - 1; jj >= 0; jj--) {
         CX s = yv[j0 + jj];
-        for (int kk = jj + 1; kk < nb; kk++) cmsubc(s, yv[j0 + kk], Db[kk * WPE_NB + jj]);  // s -= g_kk conj(L[kk][jj])
-        const RT inv = (RT)1 / Db[jj * WPE_NB + jj].x;
+        for (int kk = jj + 1; kk < nb; kk++) cmsubc(s, yv[j0 + kk], Db[kk * WPE_LD + jj]);  // s -= g_kk conj(L[kk][jj])
+        const RT inv = (RT)1 / Db[jj * WPE_LD + jj].x;
         yv[j0 + jj] = mk<RT>(s.x * inv, s.y * inv);
       }
     }
@@ -376,7 +392,7 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
   const int xstride = a.P + a.T;
   const size_t sm_resid = ((size_t)C * xstride + (size_t)C * a.L) * sizeof(float2);
   const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (size_t)C * a.T * sizeof(RT);
-  const size_t sm_chol = ((size_t)(a.L + 1) * WPE_NB + a.L) * sizeof(cx<RT>) + 32 * sizeof(RT);
+  const size_t sm_chol = (size_t)(a.L + 1) * WPE_LD * sizeof(cx<RT>) + 32 * sizeof(RT);
   if (sm_resid > 200 * 1024 || sm_corr > 200 * 1024 || sm_chol > 200 * 1024) return cudaErrorInvalidValue;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;

@@ -13,5 +13,5 @@ for tag, fp32 in (("fp64", 0), ("fp32", 1)):
     p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_GSC_LMS, max_utterances=U, max_samples=n, wpe=wpe)
     p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.synchronize()
     s = timed(lambda: (p.run(True), p.synchronize()), steps=1, warm=1)
-    print(json.dumps({"wpe chain %s, %d utterances" % (tag, U): dict(ms=1e3 * s, wpe_ms=p.last_timing_wpe(), chunk=os.environ.get("BTKB_WPE_CHUNK", "36"), s_per_1024_utt=s * 1024 / U)}))
+    print(json.dumps({"wpe chain %s, %d utterances" % (tag, U): dict(ms=1e3 * s, wpe_ms=p.last_timing_wpe(), chunk=os.environ.get("BTKB_WPE_CHUNK", "55 (default)"), s_per_1024_utt=s * 1024 / U)}))
     p.close()
