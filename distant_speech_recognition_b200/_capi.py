@@ -167,6 +167,9 @@ class Pipeline:
     def run_wpe(self, start_frame_no=0, end_frame_no=-1):
         _check(lib.btkb_run_wpe(self._h, ct.c_int(start_frame_no), ct.c_int(end_frame_no)))
 
+    def apply_wpe(self):
+        _check(lib.btkb_apply_wpe(self._h))
+
     def get_wpe_filter(self):
         P = self.cfg.wpe.upper_num - self.cfg.wpe.lower_num + 1
         out = np.empty((self.U, self.K, self.C, self.C * P), np.complex64)

@@ -41,7 +41,7 @@ struct btkb_pipeline {
   double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
   // multi-channel WPE (lazily sized at create when cfg.wpe.enabled)
   float2 *d_wS = nullptr, *d_wG = nullptr; void* d_wR = nullptr; float* d_wTH = nullptr; int* d_werr = nullptr;
-  int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_Ts = 0, wpe_nbins = 0; bool have_wpe = false;
+  int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_Ts = 0, wpe_nbins = 0, wpe_U = 0; bool have_wpe = false;
   cudaEvent_t wev[2] = {nullptr, nullptr};
   // SOS batch beamformers (lazily allocated by the first btkb_sos_accumulate_*)
   double2 *d_sosR = nullptr, *d_sosWd = nullptr; double* d_sosCnt = nullptr; float *d_sosWtu = nullptr, *d_sosMask = nullptr; double* d_sosLab = nullptr;
@@ -512,7 +512,7 @@ static PerBinArgs perbin_args(btkb_pipeline* p) {
   return a;
 }
 
-static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no) {
+static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no, bool apply_only = false) {
   if (!p->cfg.wpe.enabled) return fail(BTKB_ERR_STATE, "btkb_run_wpe: the pipeline was created without cfg.wpe.enabled");
   if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_run_wpe: run the analysis first");
   const btkb_wpe_params& w = p->cfg.wpe;
@@ -523,6 +523,7 @@ static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no) {
   a.lowerN = w.lower_num; a.P = p->wpe_P; a.L = p->wpe_L; a.Lr = p->wpe_Lr; a.iterations = w.iterations_num; a.nbins = p->wpe_nbins;
   a.est_frames = (end_frame_no < 0) ? -1 : std::max(0, end_frame_no - std::max(start_frame_no, 0));   // fill_buffer_ (:500-534) never skips input frames
   a.load_factor = (float)pow(10.0, w.load_db / 10.0); a.diagonal_bias = (float)w.diagonal_bias;
+  a.apply_only = apply_only ? 1 : 0;
   CK(cudaMemsetAsync(p->d_werr, 0, sizeof(int), p->stream));
   CK(cudaEventRecord(p->wev[0], p->stream));
   CK(launch_wpe(a, p->wpe_chunk, p->cfg.wpe.fp32_normal_equations, p->stream, &p->launches));
@@ -533,6 +534,7 @@ static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no) {
   if (err)  // dereverberation.cc:676-678
     return fail(BTKB_ERR_INVALID, "MultiChannelWPEDereverberation: GSL Cholesky decomposition failed.\nSome channels may be too similar. Try to increase 'diagonal_bias' or use 'SingleChannelWPEDereverberationFeature' for each channel");
   p->have_wpe = true;
+  if (!apply_only) p->wpe_U = p->U;
   return BTKB_OK;
 }
 
@@ -770,6 +772,15 @@ int btkb_run_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no) {
   CK(cudaSetDevice(p->cfg.device));
   p->launches = 0;
   return do_wpe(p, start_frame_no, end_frame_no);
+}
+
+int btkb_apply_wpe(btkb_pipeline* p) {
+  if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
+  if (!p->have_wpe) return fail(BTKB_ERR_STATE, "Call MultiChannelWPEDereverberation::estimate_filter()");   // dereverberation.cc:446-447 (jinitialization_error)
+  if (p->U != p->wpe_U) return fail(BTKB_ERR_INVALID, "btkb_apply_wpe: the filters were estimated for a different number of utterances");
+  CK(cudaSetDevice(p->cfg.device));
+  p->launches = 0;
+  return do_wpe(p, 0, -1, true);
 }
 
 int btkb_get_wpe_filter(btkb_pipeline* p, float* out) {

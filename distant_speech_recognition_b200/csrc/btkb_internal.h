@@ -78,6 +78,7 @@ struct WpeArgs {
   int U, C, T, Ts, K, G, Gp, D, laN, pdA;
   int lowerN, P, L, Lr, iterations, nbins, est_frames;
   float load_factor, diagonal_bias;
+  int apply_only;        // keep the filters Gf of an earlier estimation and run the output stage only
 };
 size_t wpe_workspace_bytes(int C, int L, int Lr, int chunk, int fp32);
 cudaError_t launch_wpe(const WpeArgs& a, int chunk, int fp32, cudaStream_t st, int* launches);

@@ -20,6 +20,7 @@
 // is the next step.
 #include "btkb_internal.h"
 #include <math.h>
+#include <algorithm>
 
 namespace btkb {
 namespace {
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
                                                            // elements: lanes on consecutive rows hit different banks
   CX* yv = Pn + (size_t)WPE_NB * WPE_LD;                   // [L] back-substitution vector: lives inside the panel buffer (the
                                                            // back substitution only needs its first WPE_NB rows as the diagonal block)
-  RT* red = reinterpret_cast<RT*>(Pn + (size_t)n * WPE_LD); // [32]
+  RT* red = reinterpret_cast<RT*>(Pn + max((size_t)n * WPE_LD, (size_t)WPE_NB * WPE_LD + L));   // [32] (small L: yv ends past the panel)
   const int tid = threadIdx.x;
   const RT bias = (RT)a.diagonal_bias, loadf = (RT)a.load_factor;
 
@@ -387,12 +388,14 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     (*launches)++;
   }
-  e = cudaMemsetAsync(a.Gf, 0, (size_t)a.G * C * a.L * sizeof(float2), st);
-  if (e != cudaSuccess) return e;
+  if (!a.apply_only) {
+    e = cudaMemsetAsync(a.Gf, 0, (size_t)a.G * C * a.L * sizeof(float2), st);
+    if (e != cudaSuccess) return e;
+  }
   const int xstride = a.P + a.T;
   const size_t sm_resid = ((size_t)C * xstride + (size_t)C * a.L) * sizeof(float2);
   const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (size_t)C * a.T * sizeof(RT);
-  const size_t sm_chol = (size_t)(a.L + 1) * WPE_LD * sizeof(cx<RT>) + 32 * sizeof(RT);
+  const size_t sm_chol = std::max((size_t)(a.L + 1) * WPE_LD, (size_t)WPE_NB * WPE_LD + a.L) * sizeof(cx<RT>) + 32 * sizeof(RT);
   if (sm_resid > 200 * 1024 || sm_corr > 200 * 1024 || sm_chol > 200 * 1024) return cudaErrorInvalidValue;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
@@ -408,7 +411,7 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
   if ((e = cudaFuncSetAttribute(corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_corr)) != cudaSuccess) return e;
   const int nprob = a.U * a.nbins;
   const int split = 8;
-  for (int it = 0; it < a.iterations; it++) {
+  for (int it = 0; it < (a.apply_only ? 0 : a.iterations); it++) {
     k_wpe_resid<0><<<nprob, 128, sm_resid, st>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     (*launches)++;

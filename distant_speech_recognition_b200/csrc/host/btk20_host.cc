@@ -145,6 +145,140 @@ const cplx* OverSampledDFTAnalysisBank::next(int frame_no) {  // modulated.cc:37
 }
 void OverSampledDFTAnalysisBank::reset() { samp_->reset(); VectorComplexFeatureStream::reset(); realized_ = false; }
 
+// ================================================================================================ WPE dereverberation
+MultiChannelWPEDereverberation::MultiChannelWPEDereverberation(unsigned subbandsN, unsigned channelsN, unsigned lowerN, unsigned upperN, unsigned iterationsN,
+                                                               double loadDb, double bandWidth, double diagonalBias, double sampleRate)
+    : subbandsN_(subbandsN), channelsN_(channelsN) {
+  cfg_.lower_num = lowerN; cfg_.upper_num = upperN; cfg_.iterations_num = iterationsN; cfg_.load_db = loadDb; cfg_.band_width = bandWidth;
+  cfg_.diagonal_bias = diagonalBias; cfg_.samplerate = sampleRate;
+  if (bandWidth > sampleRate / 2.0) throw jdimension_error("Bandwidth is greater than the Nyquist rate.\n");   // dereverberation.cc:369-370
+  if (!(channelsN == 1 || channelsN == 2 || channelsN == 4 || channelsN == 8)) throw jdimension_error("the GPU WPE is built for 1, 2, 4 or 8 channels (got %d)", channelsN);
+}
+MultiChannelWPEDereverberation::~MultiChannelWPEDereverberation() { if (pipe_) btkb_destroy(pipe_); }
+void MultiChannelWPEDereverberation::set_input(const VectorComplexFeatureStreamPtr& samples) {
+  if (sources_.size() == channelsN_) throw jallocation_error("Channel capacity exceeded.");   // dereverberation.cc:395-396
+  if (samples->size() != subbandsN_) throw jdimension_error("Input block length (%d) != the number of subbands (%d)\n", samples->size(), subbandsN_);
+  sources_.push_back(samples);
+}
+unsigned MultiChannelWPEDereverberation::gather_(std::vector<float>& x) {
+  if (sources_.size() != channelsN_) throw j_error("MultiChannelWPEDereverberation: %d of %d inputs set", (int)sources_.size(), (int)channelsN_);
+  unsigned n = 0;
+  versions_.assign(channelsN_, 0);
+  std::vector<const SampleFeature*> sf(channelsN_);
+  for (unsigned c = 0; c < channelsN_; c++) {
+    auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(sources_[c].get());
+    if (!ab) throw j_error("MultiChannelWPEDereverberation: the GPU engine needs OverSampledDFTAnalysisBank inputs");
+    if (ab->M() != subbandsN_) throw jdimension_error("channel %d: inconsistent FFT length (%d vs. %d)", c, ab->M(), subbandsN_);
+    sf[c] = dynamic_cast<const SampleFeature*>(ab->source().get());
+    if (!sf[c]) throw j_error("MultiChannelWPEDereverberation: the GPU engine needs SampleFeature sources");
+    if (c == 0) n = sf[c]->samplesN();
+    else if (sf[c]->samplesN() != n) throw jdimension_error("channel %d: %d samples, channel 0: %d", c, sf[c]->samplesN(), n);
+    versions_[c] = sf[c]->version();
+  }
+  if (n == 0) throw jiterator_error("end of samples!");
+  x.resize((size_t)channelsN_ * n);
+  for (unsigned c = 0; c < channelsN_; c++) std::memcpy(&x[(size_t)c * n], sf[c]->samples().data(), sizeof(float) * n);
+  return n;
+}
+unsigned MultiChannelWPEDereverberation::estimate_filter(int start_frame_no, int end_frame_no) {   // dereverberation.cc:405-431
+  std::vector<float> x;
+  const unsigned n = gather_(x);
+  auto* a0 = dynamic_cast<OverSampledDFTAnalysisBank*>(sources_[0].get());
+  if (!pipe_ || n > cap_) {
+    if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; }
+    btkb_config c; btkb_default_config(&c);
+    c.channels = (int)channelsN_; c.fft_len = (int)subbandsN_; c.m = (int)a0->m(); c.r = (int)a0->r(); c.delay_compensation_type = (int)a0->dct();
+    c.samplerate = (float)cfg_.samplerate; c.beamformer = BTKB_BF_DS; c.max_utterances = 1; c.max_samples = (int)n;
+    c.wpe.enabled = 1; c.wpe.lower_num = (int)cfg_.lower_num; c.wpe.upper_num = (int)cfg_.upper_num; c.wpe.iterations_num = (int)cfg_.iterations_num;
+    c.wpe.load_db = cfg_.load_db; c.wpe.band_width = cfg_.band_width; c.wpe.diagonal_bias = cfg_.diagonal_bias;
+    ck(btkb_create(&c, &pipe_));
+    ck(btkb_set_prototypes(pipe_, a0->prototype().data(), nullptr, (int)a0->prototype().size()));
+    cap_ = n;
+  }
+  ck(btkb_submit(pipe_, x.data(), 1, (int)n, nullptr));
+  ck(btkb_run_analysis(pipe_));
+  ck(btkb_run_wpe(pipe_, start_frame_no, end_frame_no));
+  T_ = btkb_num_frames(pipe_);
+  Xd_.resize((size_t)T_ * channelsN_ * (subbandsN_ / 2 + 1));
+  ck(btkb_fetch_snapshots(pipe_, reinterpret_cast<float*>(Xd_.data())));
+  est_start_ = start_frame_no; est_end_ = end_frame_no;
+  estimated_ = true; realized_ = true;
+  for (auto& s : sources_) s->reset();
+  // framesN_: fill_buffer_ (:500-534) takes frames from the head of the stream, (end - start) of them when end >= 0
+  const int want = (end_frame_no < 0) ? T_ : std::max(0, end_frame_no - std::max(start_frame_no, 0));
+  return (unsigned)std::min(T_, want);
+}
+void MultiChannelWPEDereverberation::realize_() {
+  // the sources have been re-read since the estimation: analysis + output stage with the stored filters
+  std::vector<float> x;
+  const unsigned n = gather_(x);
+  if (n > cap_) throw j_error("MultiChannelWPEDereverberation: the utterance (%d samples) is longer than the one the filter was estimated on (%d)", n, cap_);
+  ck(btkb_submit(pipe_, x.data(), 1, (int)n, nullptr));
+  ck(btkb_run_analysis(pipe_));
+  ck(btkb_apply_wpe(pipe_));
+  T_ = btkb_num_frames(pipe_);
+  Xd_.resize((size_t)T_ * channelsN_ * (subbandsN_ / 2 + 1));
+  ck(btkb_fetch_snapshots(pipe_, reinterpret_cast<float*>(Xd_.data())));
+  realized_ = true;
+}
+int MultiChannelWPEDereverberation::frames() {
+  if (!estimated_) throw jinitialization_error("Call SingleChannelWPEDereverberationFeature::estimate_filter()\n");   // dereverberation.cc:446-447 (sic)
+  bool stale = !realized_;
+  for (unsigned c = 0; c < channelsN_ && !stale; c++) {
+    auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(sources_[c].get());
+    auto* sf = ab ? dynamic_cast<const SampleFeature*>(ab->source().get()) : nullptr;
+    if (!sf || sf->version() != versions_[c]) stale = true;
+  }
+  if (stale) realize_();
+  return T_;
+}
+const std::complex<float>* MultiChannelWPEDereverberation::output_frame(unsigned channelX, int t) {
+  if (channelX >= channelsN_) throw jindex_error("Invalid channel index: it exceeds the number of channels: %u >= %u\n", channelX, channelsN_);   // :434-437
+  return &Xd_[((size_t)t * channelsN_ + channelX) * (subbandsN_ / 2 + 1)];
+}
+void MultiChannelWPEDereverberation::reset() { for (auto& s : sources_) s->reset(); }
+void MultiChannelWPEDereverberation::reset_filter() { estimated_ = false; realized_ = false; }
+void MultiChannelWPEDereverberation::next_speaker() { reset(); estimated_ = false; realized_ = false; }   // :692-698 zeroes the filters: the output would equal the input
+
+MultiChannelWPEDereverberationFeature::MultiChannelWPEDereverberationFeature(const MultiChannelWPEDereverberationPtr& source, unsigned channelX,
+                                                                             unsigned primaryChannelX, const std::string& nm)
+    : VectorComplexFeatureStream(source->size(), nm), source_(source), channelX_(channelX), primaryChannelX_(primaryChannelX) {}
+const cplx* MultiChannelWPEDereverberationFeature::next(int frame_no) {   // dereverberation.cc:713-728
+  if (frame_no == frame_no_) return vector_.data();
+  const int T = source_->frames();
+  if (frame_no >= 0 && frame_no - 1 != frame_no_) throw jindex_error("Problem in 'MultiChannelWPEDereverberationFeature': %d - 1 != %d\n", frame_no, frame_no_);
+  if (frame_no_ + 1 >= T) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  increment_();
+  const unsigned M = size(), K = M / 2 + 1;
+  const std::complex<float>* x = source_->output_frame(channelX_, frame_no_);
+  for (unsigned k = 0; k < K; k++) vector_[k] = cplx(x[k].real(), x[k].imag());
+  for (unsigned k = 1; k < M / 2; k++) vector_[M - k] = std::conj(vector_[k]);
+  return vector_.data();
+}
+void MultiChannelWPEDereverberationFeature::reset() { source_->reset(); VectorComplexFeatureStream::reset(); is_end_ = false; }
+
+SingleChannelWPEDereverberationFeature::SingleChannelWPEDereverberationFeature(const VectorComplexFeatureStreamPtr& samples, unsigned lowerN, unsigned upperN,
+                                                                               unsigned iterationsN, double loadDb, double bandWidth, double sampleRate,
+                                                                               const std::string& nm)
+    : VectorComplexFeatureStream(samples->size(), nm),
+      impl_(std::make_shared<MultiChannelWPEDereverberation>(samples->size(), 1, lowerN, upperN, iterationsN, loadDb, bandWidth, 0.0, sampleRate)) {
+  impl_->set_input(samples);
+}
+const cplx* SingleChannelWPEDereverberationFeature::next(int frame_no) {   // dereverberation.cc:227-275
+  if (!impl_->estimated()) throw jinitialization_error("Call SingleChannelWPEDereverberationFeature::estimate_filter()\n");
+  if (frame_no == frame_no_) return vector_.data();
+  if (frame_no >= 0 && frame_no - 1 != frame_no_) throw jindex_error("Problem in Feature %s: %d != %d\n", name().c_str(), frame_no - 1, frame_no_);
+  const int T = impl_->frames();
+  if (frame_no_ + 1 >= T) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  increment_();
+  const unsigned M = size(), K = M / 2 + 1;
+  const std::complex<float>* x = impl_->output_frame(0, frame_no_);
+  for (unsigned k = 0; k < K; k++) vector_[k] = cplx(x[k].real(), x[k].imag());
+  for (unsigned k = 1; k < M / 2; k++) vector_[M - k] = std::conj(vector_[k]);
+  return vector_.data();
+}
+void SingleChannelWPEDereverberationFeature::reset() { impl_->reset(); VectorComplexFeatureStream::reset(); is_end_ = false; }
+
 // ================================================================================================ beamformers
 SubbandBeamformer::SubbandBeamformer(unsigned fftLen, bool hbs, int kind, const std::string& nm)
     : VectorComplexFeatureStream(fftLen, nm), fftLen_(fftLen), halfBandShift_(hbs), kind_(kind) {
@@ -170,8 +304,24 @@ bool SubbandBeamformer::realized_with(const PostFilterConfig& pf, const Synthesi
   return true;
 }
 
+// The analysis bank behind channel c: the channel itself, or — for the configs[4] chain analysis -> WPE -> beamformer — the
+// input of the MultiChannelWPEDereverberation a MultiChannelWPEDereverberationFeature channel belongs to.
+static OverSampledDFTAnalysisBank* bank_behind(const VectorComplexFeatureStreamPtr& ch, MultiChannelWPEDereverberationPtr* wpe) {
+  if (auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(ch.get())) return ab;
+  if (auto* wf = dynamic_cast<MultiChannelWPEDereverberationFeature*>(ch.get())) {
+    const MultiChannelWPEDereverberationPtr& pre = wf->source();
+    if (wf->channel() >= pre->sources().size()) throw j_error("MultiChannelWPEDereverberationFeature: channel %d has no input", (int)wf->channel());
+    if (wpe) {
+      if (*wpe && wpe->get() != pre.get()) throw j_error("SubbandBeamformer: all channels must come from one MultiChannelWPEDereverberation");
+      *wpe = pre;
+    }
+    return dynamic_cast<OverSampledDFTAnalysisBank*>(pre->sources()[wf->channel()].get());
+  }
+  return nullptr;
+}
+
 void SubbandBeamformer::ensure_pipeline_(const PostFilterConfig& pf, const SynthesisConfig& syn, unsigned n_samples) {
-  auto* a0 = dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[0].get());
+  auto* a0 = bank_behind(channels_[0], nullptr);
   btkb_config c; btkb_default_config(&c);
   c.channels = (int)channels_.size(); c.fft_len = (int)fftLen_; c.m = (int)a0->m(); c.r = (int)a0->r(); c.delay_compensation_type = (int)a0->dct();
   c.samplerate = (float)samplerate_; c.beamformer = kind_;
@@ -184,6 +334,11 @@ void SubbandBeamformer::ensure_pipeline_(const PostFilterConfig& pf, const Synth
   c.rls.regularization_param = (float)rls_.regularization_param; c.rls.sil_thresh = (float)rls_.sil_thresh; c.rls.alpha2 = (float)rls_.alpha2;
   c.rls.max_wa_l2norm = (float)rls_.max_wa_l2norm; c.rls.constraint_option = rls_.constraint_option; c.rls.min_frames = rls_.min_frames;
   c.max_utterances = 1; c.max_samples = (int)n_samples; c.synthesis_gain = syn.enabled ? syn.gain : 1;
+  if (wpe_) {
+    const WpeConfig& w = wpe_->config();
+    c.wpe.enabled = 1; c.wpe.lower_num = (int)w.lower_num; c.wpe.upper_num = (int)w.upper_num; c.wpe.iterations_num = (int)w.iterations_num;
+    c.wpe.load_db = w.load_db; c.wpe.band_width = w.band_width; c.wpe.diagonal_bias = w.diagonal_bias;
+  }
   if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; }
   ck(btkb_create(&c, &pipe_));
   ck(btkb_set_prototypes(pipe_, a0->prototype().data(), syn.enabled ? syn.prototype.data() : nullptr, (int)a0->prototype().size()));
@@ -195,9 +350,10 @@ void SubbandBeamformer::run_graph(const PostFilterConfig& pf, const SynthesisCon
   const unsigned C = (unsigned)channels_.size();
   std::vector<const SampleFeature*> srcs(C);
   unsigned n = 0;
+  wpe_.reset();
   for (unsigned c = 0; c < C; c++) {
-    auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(channels_[c].get());
-    if (!ab) throw j_error("SubbandBeamformer: the GPU engine needs OverSampledDFTAnalysisBank channels");
+    auto* ab = bank_behind(channels_[c], &wpe_);
+    if (!ab) throw j_error("SubbandBeamformer: the GPU engine needs OverSampledDFTAnalysisBank channels (directly or behind MultiChannelWPEDereverberationFeature)");
     if (ab->M() != fftLen_) throw jdimension_error("channel %d: inconsistent FFT length (%d vs. %d)", c, ab->M(), fftLen_);
     srcs[c] = dynamic_cast<const SampleFeature*>(ab->source().get());
     if (!srcs[c]) throw j_error("SubbandBeamformer: the GPU engine needs SampleFeature sources");
@@ -216,7 +372,17 @@ void SubbandBeamformer::run_graph(const PostFilterConfig& pf, const SynthesisCon
   std::vector<float> x((size_t)C * n);
   for (unsigned c = 0; c < C; c++) std::memcpy(&x[(size_t)c * n], srcs[c]->samples().data(), sizeof(float) * n);
   ck(btkb_submit(pipe_, x.data(), 1, (int)n, nullptr));
-  ck(btkb_run(pipe_, syn.enabled ? 1 : 0));
+  if (wpe_) {
+    // the dereverberation filters are estimated on the utterance being processed, over the frame range given to
+    // MultiChannelWPEDereverberation::estimate_filter (the reference could also carry filters over from other audio)
+    if (!wpe_->estimated()) throw jinitialization_error("Call SingleChannelWPEDereverberationFeature::estimate_filter()\n");
+    if (wpe_->channelsN() != C) throw jdimension_error("the dereverberator has %d channels, the beamformer %d", (int)wpe_->channelsN(), (int)C);
+    ck(btkb_run_analysis(pipe_));
+    ck(btkb_run_wpe(pipe_, wpe_->est_start(), wpe_->est_end()));
+    ck(btkb_run_beamformer(pipe_, syn.enabled ? 1 : 0));
+  } else {
+    ck(btkb_run(pipe_, syn.enabled ? 1 : 0));
+  }
   T_ = btkb_num_frames(pipe_); nb_ = btkb_num_blocks(pipe_);
   const unsigned K = fftLen_ / 2 + 1;
   Y_.resize((size_t)T_ * K);

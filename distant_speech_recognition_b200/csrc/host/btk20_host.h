@@ -147,6 +147,81 @@ class SnapShotArray {
 };
 typedef std::shared_ptr<SnapShotArray> SnapShotArrayPtr;
 
+// ----------------------------------------------------------------------------------------------------------------
+// WPE dereverberation (dereverberation/dereverberation.h).  The reference estimates the filters from a buffered pass over the
+// input streams (estimate_filter), resets them, and applies the filters frame by frame in next().  Here estimate_filter runs
+// analysis + estimation + output stage for the current sample arrays on the GPU; when the sources have been re-read since
+// (test_subband_dereverberator.py:147-150) the first next() re-runs analysis + output stage with the stored filters.
+struct WpeConfig {
+  unsigned lower_num = 0, upper_num = 32, iterations_num = 2;
+  double load_db = -20.0, band_width = 0.0, diagonal_bias = 0.001, samplerate = 16000.0;
+};
+class MultiChannelWPEDereverberation {
+ public:
+  MultiChannelWPEDereverberation(unsigned subbandsN, unsigned channelsN, unsigned lowerN = 0, unsigned upperN = 32, unsigned iterationsN = 2, double loadDb = -20.0,
+                                 double bandWidth = 0.0, double diagonalBias = 0.001, double sampleRate = 16000.0);
+  ~MultiChannelWPEDereverberation();
+  unsigned size() const { return subbandsN_; }
+  unsigned channelsN() const { return channelsN_; }
+  void set_input(const VectorComplexFeatureStreamPtr& samples);
+  unsigned estimate_filter(int start_frame_no = 0, int end_frame_no = -1);
+  void reset_filter();
+  void next_speaker();
+  void print_objective_func(int /*subband_no*/) {}
+  void reset();
+  bool estimated() const { return estimated_; }
+  // engine hooks
+  int frames();                                               // frames of the (re)realised output
+  const std::complex<float>* output_frame(unsigned channelX, int t);  // [K] dereverberated bins of frame t
+  const std::vector<VectorComplexFeatureStreamPtr>& sources() const { return sources_; }
+  const WpeConfig& config() const { return cfg_; }
+  int est_start() const { return est_start_; }
+  int est_end() const { return est_end_; }
+ private:
+  unsigned gather_(std::vector<float>& x);   // [C][n] samples of the current sources; returns n
+  void realize_();
+  unsigned subbandsN_, channelsN_;
+  WpeConfig cfg_;
+  std::vector<VectorComplexFeatureStreamPtr> sources_;
+  btkb_pipeline* pipe_ = nullptr; unsigned cap_ = 0;
+  std::vector<std::complex<float>> Xd_;      // [T][C][K]
+  std::vector<unsigned long> versions_;
+  int T_ = 0, est_start_ = 0, est_end_ = -1;
+  bool estimated_ = false, realized_ = false;
+};
+typedef std::shared_ptr<MultiChannelWPEDereverberation> MultiChannelWPEDereverberationPtr;
+
+class MultiChannelWPEDereverberationFeature : public VectorComplexFeatureStream {
+ public:
+  MultiChannelWPEDereverberationFeature(const MultiChannelWPEDereverberationPtr& source, unsigned channelX, unsigned primaryChannelX = 0,
+                                        const std::string& nm = "MultiChannelWPEDereverberationFeature");
+  const cplx* next(int frame_no = -5) override;
+  void reset() override;
+  const MultiChannelWPEDereverberationPtr& source() const { return source_; }
+  unsigned channel() const { return channelX_; }
+ private:
+  MultiChannelWPEDereverberationPtr source_; unsigned channelX_, primaryChannelX_;
+};
+typedef std::shared_ptr<MultiChannelWPEDereverberationFeature> MultiChannelWPEDereverberationFeaturePtr;
+
+// SingleChannelWPEDereverberationFeature (dereverberation.cc:24-310) = the multi-channel estimator with one channel and no
+// diagonal bias (bit-identical in the reference itself, tests/test_oracle.py::test_wpe_single_channel_golden)
+class SingleChannelWPEDereverberationFeature : public VectorComplexFeatureStream {
+ public:
+  SingleChannelWPEDereverberationFeature(const VectorComplexFeatureStreamPtr& samples, unsigned lowerN = 0, unsigned upperN = 64, unsigned iterationsN = 2,
+                                         double loadDb = -20.0, double bandWidth = 0.0, double sampleRate = 16000.0,
+                                         const std::string& nm = "SingleChannelWPEDereverberationFeature");
+  unsigned estimate_filter(int start_frame_no = 0, int end_frame_no = -1) { return impl_->estimate_filter(start_frame_no, end_frame_no); }
+  void print_objective_func(int) {}
+  void reset_filter() { impl_->reset_filter(); }
+  void next_speaker() { impl_->next_speaker(); VectorComplexFeatureStream::reset(); }
+  const cplx* next(int frame_no = -5) override;
+  void reset() override;
+ private:
+  MultiChannelWPEDereverberationPtr impl_;
+};
+typedef std::shared_ptr<SingleChannelWPEDereverberationFeature> SingleChannelWPEDereverberationFeaturePtr;
+
 struct LmsConfig {  // lib/pybeamformer.py:597-607 defaults (= unit_test/confs/gsclms.json)
   double beta = 0.97, gamma = 0.01, init_diagonal_load = 1.0e6, regularization_param = 1.0e-4, energy_floor = 90, sil_thresh = 1.0e8, max_wa_l2norm = 100.0;
   int min_frames = 128, slowdown_after = 4096;
@@ -204,6 +279,7 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
   int T_ = 0, nb_ = 0; bool realized_ = false, haveX_ = false;
   PostFilterConfig pf_used_; SynthesisConfig syn_used_;
   LmsConfig lms_; RlsConfig rls_;
+  MultiChannelWPEDereverberationPtr wpe_;   // set by run_graph when the channels are MultiChannelWPEDereverberationFeature streams
   SnapShotArrayPtr snap_;
   std::vector<unsigned long> src_versions_;
   void ensure_pipeline_(const PostFilterConfig& pf, const SynthesisConfig& syn, unsigned n_samples);

@@ -135,6 +135,42 @@ PYBIND11_MODULE(_btk20host, m) {
            py::arg("nm") = "OverSampledDFTSynthesisBank")
       .def("polyphase", &OverSampledDFTSynthesisBank::polyphase, py::arg("m"), py::arg("n"));
 
+  // dereverberation/dereverberation.i:46-185
+  py::class_<SingleChannelWPEDereverberationFeature, VectorComplexFeatureStream, SingleChannelWPEDereverberationFeaturePtr>(m, "SingleChannelWPEDereverberationFeaturePtr")
+      .def(py::init([](VectorComplexFeatureStreamPtr samples, unsigned lower_num, unsigned upper_num, unsigned iterations_num, double load_db, double band_width,
+                       double samplerate, const std::string& nm) {
+             return std::make_shared<SingleChannelWPEDereverberationFeature>(samples, lower_num, upper_num, iterations_num, load_db, band_width, samplerate, nm); }),
+           py::arg("samples"), py::arg("lower_num") = 0, py::arg("upper_num") = 64, py::arg("iterations_num") = 2, py::arg("load_db") = -20.0,
+           py::arg("band_width") = 0.0, py::arg("samplerate") = 16000.0, py::arg("nm") = "SingleChannelWPEDereverberationFeature")
+      .def("estimate_filter", &SingleChannelWPEDereverberationFeature::estimate_filter, py::arg("start_frame_no") = 0, py::arg("frame_num") = -1)
+      .def("print_objective_func", &SingleChannelWPEDereverberationFeature::print_objective_func, py::arg("subband_no"))
+      .def("reset_filter", &SingleChannelWPEDereverberationFeature::reset_filter)
+      .def("next_speaker", &SingleChannelWPEDereverberationFeature::next_speaker);
+  py::class_<MultiChannelWPEDereverberation, MultiChannelWPEDereverberationPtr>(m, "MultiChannelWPEDereverberationPtr")
+      .def(py::init([](unsigned subbands_num, unsigned channels_num, unsigned lower_num, unsigned upper_num, unsigned iterations_num, double load_db,
+                       double band_width, double diagonal_bias, double samplerate) {
+             return std::make_shared<MultiChannelWPEDereverberation>(subbands_num, channels_num, lower_num, upper_num, iterations_num, load_db, band_width,
+                                                                     diagonal_bias, samplerate); }),
+           py::arg("subbands_num"), py::arg("channels_num"), py::arg("lower_num") = 0, py::arg("upper_num") = 32, py::arg("iterations_num") = 2,
+           py::arg("load_db") = -20.0, py::arg("band_width") = 0.0, py::arg("diagonal_bias") = 0.001, py::arg("samplerate") = 16000.0)
+      .def("size", &MultiChannelWPEDereverberation::size)
+      .def("set_input", &MultiChannelWPEDereverberation::set_input, py::arg("samples"))
+      .def("estimate_filter", &MultiChannelWPEDereverberation::estimate_filter, py::arg("start_frame_no") = 0, py::arg("frame_num") = -1)
+      .def("reset_filter", &MultiChannelWPEDereverberation::reset_filter)
+      .def("next_speaker", &MultiChannelWPEDereverberation::next_speaker)
+      .def("print_objective_func", &MultiChannelWPEDereverberation::print_objective_func, py::arg("subband_no"))
+      .def("reset", &MultiChannelWPEDereverberation::reset);
+  py::class_<MultiChannelWPEDereverberationFeature, VectorComplexFeatureStream, MultiChannelWPEDereverberationFeaturePtr>(m, "MultiChannelWPEDereverberationFeaturePtr")
+      .def(py::init([](MultiChannelWPEDereverberationPtr source, unsigned channel_no, unsigned primary_channel_no, const std::string& nm) {
+             return std::make_shared<MultiChannelWPEDereverberationFeature>(source, channel_no, primary_channel_no, nm); }),
+           py::arg("source"), py::arg("channel_no"), py::arg("primary_channel_no") = 0, py::arg("nm") = "MultiChannelWPEDereverberationFeature")
+      // extension: the frame shift of the analysis bank behind the channel, so that the feature streams can feed the btk20.pybeamformer
+      // classes (MultiChannelSource reads spec_sources[0].shiftlen(), lib/pybeamformer.py:251), not only the C++ beamformers
+      .def("shiftlen", [](MultiChannelWPEDereverberationFeature& f) {
+        auto* ab = dynamic_cast<OverSampledDFTAnalysisBank*>(f.source()->sources().at(f.channel()).get());
+        if (!ab) throw j_error("MultiChannelWPEDereverberationFeature: no analysis bank behind channel %d", (int)f.channel());
+        return ab->shiftlen(); });
+
   py::class_<SnapShotArray, SnapShotArrayPtr>(m, "SnapShotArrayPtr")
       .def(py::init<unsigned, unsigned>(), py::arg("fftlen"), py::arg("chan_num"))
       .def("snapshot", [](SnapShotArray& s, unsigned f) { return view<cplx>(s, s.snapshot(f), s.nChan()); }, py::arg("fbinX"))

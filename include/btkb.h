@@ -162,6 +162,10 @@ int btkb_spectral_matrix_update(btkb_pipeline* p, float mu, int legacy_noconj);
  * (read them with btkb_fetch_snapshots; the beamformer / synthesis stages then run on them).  end_frame_no < 0 = all frames.
  * A non-positive Cholesky pivot reports BTKB_ERR_INVALID with the reference's jnumeric_error text (:676-678). */
 int btkb_run_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no);
+/* MultiChannelWPEDereverberationFeature::next over a NEW batch with the filters of the last btkb_run_wpe (the reference estimates once,
+ * then re-reads the audio and pulls the output stage, unit_test/test_subband_dereverberator.py:147-170): run the analysis on the
+ * new samples, then this call replaces the resident snapshots by x - G^H lags.  Same number of utterances as the estimation batch. */
+int btkb_apply_wpe(btkb_pipeline* p);
 /* prediction filters Gn_ [U][K][C][L] complex64, L = C * (upper_num - lower_num + 1), channel-major then lag (zero outside the band) */
 int btkb_get_wpe_filter(btkb_pipeline* p, float* out);
 int btkb_run_beamformer(btkb_pipeline* p, int do_synthesis);

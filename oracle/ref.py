@@ -99,6 +99,21 @@ def wpe(X, lower_num=0, upper_num=32, iterations_num=2, load_db=-20.0, band_widt
     return np.ascontiguousarray(np.transpose(Xout, (1, 0, 2))), used
 
 
+def wpe_single(X, lower_num=0, upper_num=64, iterations_num=2, load_db=-20.0, band_width=0.0, samplerate=16000.0, start_frame_no=0, end_frame_no=-1):
+    """SingleChannelWPEDereverberationFeature (dereverberation.cc:24-310) on one channel's snapshots X[T][M] -> X'[T][M];
+    returns (X', frames used for the estimation)."""
+    X = np.ascontiguousarray(X, np.complex128)
+    T, M = X.shape
+    Xout = np.zeros_like(X)
+    L = lib()
+    L.ref_wpe_single.restype = ct.c_int
+    used = L.ref_wpe_single(_p(X, ct.c_double), ct.c_int(T), ct.c_int(M), ct.c_int(lower_num), ct.c_int(upper_num), ct.c_int(iterations_num),
+                            ct.c_double(load_db), ct.c_double(band_width), ct.c_double(samplerate), ct.c_int(start_frame_no), ct.c_int(end_frame_no),
+                            _p(Xout, ct.c_double))
+    assert used >= 0, "the reference raised an exception"
+    return Xout, used
+
+
 def gsc_weights(M, C, samplerate, delays, want_B=True):
     delays = np.ascontiguousarray(delays, np.float64)
     wq = np.zeros((M, C), np.complex128)

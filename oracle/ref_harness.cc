@@ -303,6 +303,26 @@ int ref_wpe(const double* X_in, int C, int T, int M, int lowerN, int upperN, int
   return used;
 }
 
+/* Single-channel WPE (dereverberation/dereverberation.cc:24-310) wired as unit_test/test_subband_dereverberator.py:53-92:
+ * X_in [T][M] complex128 -> X_out [T][M]; returns estimate_filter's frame count or -1 on a reference exception. */
+int ref_wpe_single(const double* X_in, int T, int M, int lowerN, int upperN, int iterationsN, double loadDb, double bandWidth, double samplerate,
+                   int start_frame, int end_frame, double* X_out) {
+  int used = -1;
+  try {
+    VectorComplexFeatureStreamPtr src = new ArrayComplexSource(X_in, T, M);
+    SingleChannelWPEDereverberationFeaturePtr wpe = new SingleChannelWPEDereverberationFeature(src, lowerN, upperN, iterationsN, loadDb, bandWidth, samplerate);
+    used = (int)wpe->estimate_filter(start_frame, end_frame);
+    for (int t = 0; t < T; t++) {
+      const gsl_vector_complex* v = wpe->next();
+      memcpy(X_out + (size_t)2 * t * M, v->data, sizeof(double) * 2 * M);
+    }
+  } catch (std::exception& e) {
+    fprintf(stderr, "ref_wpe_single: %s\n", e.what());
+    return -1;
+  }
+  return used;
+}
+
 /* synthesis only: Y[T][M] complex128 -> out blocks of D floats; returns number of blocks */
 int ref_synthesis(const double* Y, int T, const double* g, int M, int m, int r, int dct, float* out, int blocks_cap) {
   int D = M >> r;

@@ -8,6 +8,8 @@ Stored: the input samples and X'[T][C][0..M/2].
                            shorter filter), (b) lower 2 / upper 8 / 3 iterations / -20 dB / band_width 3000 Hz, estimation on
                            estimate_filter(2, 42), (c) lower 1 / upper 5 / 2 iterations / load -40 dB (light loading: large filters)
   golden_wpe_c8_m512.npz   8 mics, M = 512, lower 1 / upper 8 (L = 64), 2 iterations, load -35 dB
+  golden_wpe_single_m256.npz  SingleChannelWPEDereverberationFeature, M = 256: (a) lags 0..16, -20 dB; (b) lags 2..12, 3 iterations,
+                           -25 dB, band_width 3000 Hz, estimate_filter(2, 42); plus the resynthesised signal of (a)
 
 Usage: python tests/golden/make_golden_wpe.py
 """
@@ -50,6 +52,15 @@ def main():
     X = np.stack([ref.analysis(x[c], h, M, 4, 1) for c in range(8)], axis=1)
     Xa, ua = ref.wpe(X, lower_num=1, upper_num=8, iterations_num=2, load_db=-35.0, band_width=0.0, diagonal_bias=1e-4)
     save("wpe_c8_m512", x=x, Xa=Xa[:, :, :K], used_a=ua)
+
+    # SingleChannelWPEDereverberationFeature (dereverberation.cc:24-310), wired as test_subband_dereverberator.py:53-92
+    M = 256; K = M // 2 + 1; h, g = proto(M)
+    x = reverberant(9, 1, 8000, 3)
+    X = ref.analysis(x[0], h, M, 4, 1)
+    Xa, ua = ref.wpe_single(X, lower_num=0, upper_num=16, iterations_num=2, load_db=-20.0, band_width=0.0)
+    Xb, ub = ref.wpe_single(X, lower_num=2, upper_num=12, iterations_num=3, load_db=-25.0, band_width=3000.0, start_frame_no=2, end_frame_no=42)
+    ta = ref.synthesis(Xa, g, M, 4, 1)
+    save("wpe_single_m256", x=x, Xa=Xa[:, :K], Xb=Xb[:, :K], used_a=ua, used_b=ub, time_a=ta)
 
 
 if __name__ == "__main__":

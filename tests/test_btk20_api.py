@@ -249,6 +249,90 @@ def test_frontend_flow_bmvdr_and_gev(protos):
 
 
 @pytest.mark.gpu
+def test_frontend_flow_wpe_single_and_multi_channel(protos):
+    """unit_test/test_subband_dereverberator.py:53-170: single-channel WPE feature into the synthesis bank; multi-channel
+    estimator + one feature stream per channel; the audio is re-read between estimate_filter() and the output pass."""
+    from distant_speech_recognition_b200.btk20.dereverberation import (SingleChannelWPEDereverberationFeaturePtr, MultiChannelWPEDereverberationPtr,
+                                                                        MultiChannelWPEDereverberationFeaturePtr)
+    g = load_golden("wpe_single_m256"); h, gg = protos[256]; M, D = 256, 128
+    sf = SampleFeaturePtr(block_len=D, shift_len=D, pad_zeros=True); sf.setSamples(g["x"][0].astype(np.float64), FS)
+    afb = OverSampledDFTAnalysisBankPtr(sf, prototype=h, M=M, m=4, r=1, delay_compensation_type=2)
+    dereverb = SingleChannelWPEDereverberationFeaturePtr(afb, lower_num=0, upper_num=16, iterations_num=2, load_db=-20.0, band_width=0.0, samplerate=FS)
+    sfb = OverSampledDFTSynthesisBankPtr(dereverb, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    with pytest.raises(Exception):
+        dereverb.next()                                   # jinitialization_error before estimate_filter()
+    dereverb.print_objective_func(50)
+    assert dereverb.estimate_filter() == int(g["used_a"])
+    sf.setSamples(g["x"][0].astype(np.float64), FS)       # "sample_feat.read(...)" again
+    y = np.concatenate([np.array(b) for b in sfb])
+    assert rel_l2(y, g["time_a"]) < 1e-4
+    X = np.array([np.array(v) for v in dereverb])          # the stream itself, after reset
+    assert rel_l2(X[:, :129], g["Xa"]) < 1e-4 and np.allclose(X[:, 129:], np.conj(X[:, 1:128][:, ::-1]))
+
+    g = load_golden("wpe_c4_m256"); x = g["x"]
+    pre = MultiChannelWPEDereverberationPtr(subbands_num=M, channels_num=4, lower_num=2, upper_num=8, iterations_num=3, load_db=-20.0, band_width=3000.0,
+                                            diagonal_bias=1e-3, samplerate=FS)
+    sfs, afbs = [], []
+    for c in range(4):
+        s_ = SampleFeaturePtr(block_len=D, shift_len=D, pad_zeros=True); s_.setSamples(x[c].astype(np.float64), FS)
+        a_ = OverSampledDFTAnalysisBankPtr(s_, prototype=h, M=M, m=4, r=1, delay_compensation_type=2)
+        pre.set_input(a_); sfs.append(s_); afbs.append(a_)
+    with pytest.raises(MemoryError):
+        pre.set_input(afbs[0])                             # jallocation_error "Channel capacity exceeded."
+    assert pre.estimate_filter(2, 42) == int(g["used_b"])
+    feats = []
+    for c in range(4):
+        sfs[c].setSamples(x[c].astype(np.float64), FS)
+        feats.append(MultiChannelWPEDereverberationFeaturePtr(pre, channel_no=c))
+    out = [[] for _ in range(4)]
+    while True:
+        try:
+            for c in range(4):
+                out[c].append(np.array(feats[c].next()))
+        except StopIteration:
+            break
+    Xd = np.stack([np.array(o) for o in out], axis=1)      # [T][C][M]
+    assert rel_l2(Xd[:, :, :129], g["Xb"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_frontend_flow_wpe_into_gsclms(protos):
+    """configs[4] chain at script level: analysis banks -> MultiChannelWPEDereverberation -> one feature per channel ->
+    SubbandGSCLMSBeamformer -> synthesis bank, against the fp64 restatement of the same chain."""
+    from oracle import restate
+    from distant_speech_recognition_b200 import synthetic
+    from distant_speech_recognition_b200.btk20.dereverberation import MultiChannelWPEDereverberationPtr, MultiChannelWPEDereverberationFeaturePtr
+    M, D, C, n = 256, 128, 4, 7000
+    h, gg = protos[M]
+    x, d, _, _ = synthetic.make_utterance(55, C, n)
+    wpe = dict(lower_num=1, upper_num=6, iterations_num=2, load_db=-30.0, band_width=0.0, diagonal_bias=1e-4)
+    pre = MultiChannelWPEDereverberationPtr(subbands_num=M, channels_num=C, samplerate=FS, **wpe)
+    afbs = _afbs(x, h, M, D)
+    for a_ in afbs:
+        pre.set_input(a_)
+    pre.estimate_filter()
+    feats = [MultiChannelWPEDereverberationFeaturePtr(pre, channel_no=c) for c in range(C)]
+    bf = pybeamformer.SubbandGSCLMSBeamformer(feats, min_frames=5)
+    bf.calc_beamformer_weights(FS, d)
+    sfb = OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(bf), prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    X = np.stack([restate.analysis(x[c], h, M, 4, 1) for c in range(C)], axis=1)
+    Xw, _, _ = restate.wpe(X, samplerate=FS, **wpe)
+    Yo, _, _ = restate.gsc_lms(Xw, FS, d, min_frames=5)
+    assert rel_l2(y, restate.synthesis(Yo, gg, M, 4, 1)) < 1e-4
+    # the same chain into the C++ SubbandGSC (configs[4]: "SubbandGSC + WPE dereverberation chain"), static weights
+    gsc = SubbandGSCPtr(fftlen=M, half_band_shift=False)
+    for f_ in feats:
+        gsc.set_channel(f_)
+    gsc.calc_gsc_weights(FS, d)
+    sfb = OverSampledDFTSynthesisBankPtr(gsc, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    wq = restate.calc_mainlobe(M, C, FS, d)
+    Yg = restate.subband_gsc(Xw, wq, np.zeros_like(wq))
+    assert rel_l2(y, restate.synthesis(Yg, gg, M, 4, 1)) < 1e-4
+
+
+@pytest.mark.gpu
 def test_generic_python_stream_into_synthesis_and_analysis_iteration(protos):
     """A pure-Python spatial filter between the banks (the reference's PyFeatureStream use): analysis frames are pulled
     one by one in Python, modified, and fed to the synthesis bank through PyVectorComplexFeatureStreamPtr."""

@@ -325,3 +325,16 @@ def test_sos_reference_python_runs_live_when_present(protos):
     X = _X(g["x"], h, 256)
     res = pyref.run_sos("gev", X, FS, 128, mask_t=g["mask_t"], mask_j=g["mask_j"], energy_threshold=10, gamma=float(g["gamma"]))
     assert rel_l2(np.conj(res["wqH"]), g["w"]) < 1e-12
+
+
+def test_wpe_single_channel_golden(protos):
+    """SingleChannelWPEDereverberationFeature (dereverberation.cc:24-310) = the multi-channel estimator with one channel and no
+    diagonal bias: the restatement with C = 1, diagonal_bias = 0 reproduces the compiled reference's single-channel output."""
+    g = load_golden("wpe_single_m256"); h, gg = protos[256]
+    X = restate.analysis(g["x"][0], h, 256, 4, 1)[:, None, :]
+    Xa, _, ua = restate.wpe(X, lower_num=0, upper_num=16, iterations_num=2, load_db=-20.0, band_width=0.0, diagonal_bias=0.0, samplerate=FS)
+    Xb, _, ub = restate.wpe(X, lower_num=2, upper_num=12, iterations_num=3, load_db=-25.0, band_width=3000.0, diagonal_bias=0.0, samplerate=FS,
+                            start_frame_no=2, end_frame_no=42)
+    assert rel_l2(Xa[:, 0, :129], g["Xa"]) < 1e-11 and rel_l2(Xb[:, 0, :129], g["Xb"]) < 1e-11
+    assert ua == int(g["used_a"]) and ub == int(g["used_b"]) == 40
+    assert rel_l2(restate.synthesis(Xa[:, 0, :], gg, 256, 4, 1), g["time_a"]) < 1e-6

@@ -627,3 +627,30 @@ def test_64_mic_covariance_tensor_core_path(capi, protos):
     for _ in range(4):
         q.accumulate_covariance(labels=labels, energy_threshold=10.0)
         assert np.array_equal(q.get_covariance(), cov)
+
+
+def test_wpe_single_channel_golden(capi, protos):
+    """SingleChannelWPEDereverberationFeature (dereverberation.cc:24-310) through the C-ABI: one channel, diagonal_bias = 0; also
+    btkb_apply_wpe (filters of an earlier estimation applied to re-submitted audio, test_subband_dereverberator.py:73-84)."""
+    g = load_golden("wpe_single_m256")
+    x = g["x"]
+    ka = dict(lower_num=0, upper_num=16, iterations_num=2, load_db=-20.0, band_width=0.0, diagonal_bias=0.0)
+    kb = dict(lower_num=2, upper_num=12, iterations_num=3, load_db=-25.0, band_width=3000.0, diagonal_bias=0.0)
+    p = _pipe(capi, 1, 256, protos, n=x.shape[1], beamformer=capi.BF_DS, wpe=ka)
+    p.submit(x[None]); p.run_analysis(); p.run_wpe()
+    assert rel_l2(p.fetch_snapshots()[0][:, 0, :], g["Xa"]) < TOL
+    q = _pipe(capi, 1, 256, protos, n=x.shape[1], beamformer=capi.BF_DS)   # the dereverberated stream feeds the synthesis bank directly
+    q.set_subband(p.fetch_snapshots()[:, :, 0, :]); q.run_synthesis()
+    assert rel_l2(q.fetch_time()[0], g["time_a"]) < TOL
+    q.close()
+    p.submit(x[None]); p.run_analysis(); p.apply_wpe()   # same filters on the re-read audio
+    assert rel_l2(p.fetch_snapshots()[0][:, 0, :], g["Xa"]) < TOL
+    p.submit(0.5 * x[None]); p.run_analysis(); p.apply_wpe()   # the output stage is linear in the audio for fixed filters
+    assert rel_l2(p.fetch_snapshots()[0][:, 0, :], 0.5 * g["Xa"]) < TOL
+    p.close()
+    p = _pipe(capi, 1, 256, protos, n=x.shape[1], beamformer=capi.BF_DS, wpe=kb)
+    with pytest.raises(capi.BtkbError):
+        p.submit(x[None]); p.run_analysis(); p.apply_wpe()     # "Call ... estimate_filter()"
+    p.run_wpe(2, 42)
+    assert rel_l2(p.fetch_snapshots()[0][:, 0, :], g["Xb"]) < TOL
+    p.close()
