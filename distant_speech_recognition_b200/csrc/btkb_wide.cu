@@ -229,6 +229,9 @@ struct cdw { double x, y; };
 __device__ __forceinline__ cdw cw(double x, double y) { cdw r; r.x = x; r.y = y; return r; }
 __device__ __forceinline__ cdw cwmul(cdw a, cdw b) { return cw(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ cdw cwsub(cdw a, cdw b) { return cw(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cdw cwmsub(cdw a, cdw f, cdw b) {   // a - f b as four FMAs
+  return cw(fma(-f.x, b.x, fma(f.y, b.y, a.x)), fma(-f.x, b.y, fma(-f.y, b.x, a.y)));
+}
 __device__ __forceinline__ cdw cwdiv(cdw a, cdw b) { double d = b.x * b.x + b.y * b.y; return cw((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d); }
 
 // blockDim.x = 4 C threads: thread (r = tid % C, q = tid / C) owns the columns c = q (mod 4) of row r, so a warp covers 32
@@ -281,7 +284,8 @@ __global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, 
     __syncthreads();
     if (r > col) {
       const cdw f = cwdiv(A[r * LD + col], A[col * LD + col]);   // column `col` of this row is not written in this step
-      for (int c = col + 1 + q; c <= C; c += SOLVE_Q) A[r * LD + c] = cwsub(A[r * LD + c], cwmul(f, A[col * LD + c]));
+#pragma unroll 4
+      for (int c = col + 1 + q; c <= C; c += SOLVE_Q) A[r * LD + c] = cwmsub(A[r * LD + c], f, A[col * LD + c]);
     }
     __syncthreads();   // rows are shared by four threads now: the next pivot search reads what the other three wrote
   }
@@ -291,7 +295,7 @@ __global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, 
     for (int i = C - 1; i >= 0; i--) {
       if (tid == i) A[i * LD + C] = cwdiv(A[i * LD + C], A[i * LD + i]);
       __syncthreads();
-      if (tid < i) A[tid * LD + C] = cwsub(A[tid * LD + C], cwmul(A[tid * LD + i], A[i * LD + C]));
+      if (tid < i) A[tid * LD + C] = cwmsub(A[tid * LD + C], A[tid * LD + i], A[i * LD + C]);
     }
   } else if (tid < C) {
     float2 t = Dm[(size_t)tid * Gp + g]; A[tid * LD + C] = cw(t.x, t.y);   // identity fallback (beamformer.cc:2381-2383)
