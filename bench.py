@@ -226,10 +226,10 @@ def run_ours(args):
             ks[k] += t[k]
     barrier()
     # ---- end-to-end arm through the public C-ABI with HOST buffers: 16-bit PCM samples in pinned memory (what the
-    # reference's SampleFeature reads from wav files), NP sub-batches on NP pipeline handles so that the H2D copy of one
+    # reference's SampleFeature reads from wav files), NP = 8 sub-batches on NP pipeline handles so that the H2D copy of one
     # sub-batch overlaps the kernels / D2H of the previous one.  Every step uploads all samples + delays and downloads the
     # resynthesised signal + statistics.
-    NP = 4 if U % 4 == 0 else 1
+    NP = 8 if U % 8 == 0 else (4 if U % 4 == 0 else 1)   # 8 sub-batches: 6.3 ms/step, 4: 7.7 ms (tools/dbg/e2e_probe.py; PCIe alone: 5.9 ms)
     Us = U // NP
     x16_pin = x_pin.to(torch.int16).pin_memory()   # exact: the synthetic samples sit on the int16 grid
     subs = []
