@@ -82,6 +82,29 @@ def test_constructor_checks_and_misc(protos):
     assert np.allclose(pybeamformer.calc_nf_delays(mpos, 10.0, 500.0, 3.0), restate.calc_nf_delays(mpos, 10.0, 500.0, 3.0))
 
 
+def test_dereverberation_constructor_checks(protos):
+    """btk20.dereverberation argument checks that need no GPU (dereverberation.cc:365-373, 393-399)."""
+    from distant_speech_recognition_b200.btk20.dereverberation import (SingleChannelWPEDereverberationFeaturePtr, MultiChannelWPEDereverberationPtr,
+                                                                        MultiChannelWPEDereverberationFeaturePtr)
+    h, g = protos[256]
+    with pytest.raises(Exception, match="Nyquist"):
+        MultiChannelWPEDereverberationPtr(subbands_num=256, channels_num=2, band_width=9000.0, samplerate=FS)
+    pre = MultiChannelWPEDereverberationPtr(subbands_num=256, channels_num=2, lower_num=0, upper_num=4)
+    assert pre.size() == 256
+    sf = SampleFeaturePtr(block_len=128, shift_len=128, pad_zeros=True); sf.setSamples(np.zeros(1000), FS)
+    afb = OverSampledDFTAnalysisBankPtr(sf, prototype=h, M=256, m=4, r=1, delay_compensation_type=2)
+    pre.set_input(afb); pre.set_input(afb)
+    with pytest.raises(MemoryError):                      # jallocation_error "Channel capacity exceeded."
+        pre.set_input(afb)
+    feat = MultiChannelWPEDereverberationFeaturePtr(pre, channel_no=1)
+    assert feat.size() == 256 and feat.shiftlen() == 128 and feat.frame_no() == -1
+    with pytest.raises(Exception, match="estimate_filter"):
+        feat.next()                                       # jinitialization_error before estimate_filter()
+    single = SingleChannelWPEDereverberationFeaturePtr(afb, lower_num=0, upper_num=8)
+    with pytest.raises(Exception, match="estimate_filter"):
+        single.next()
+
+
 def _afbs(x, h, M, D):
     afbs = []
     for c in range(x.shape[0]):
