@@ -28,8 +28,8 @@
 //   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns), shuffle-combine, R[(c C + c')][g] complex64 stores;
 //               TMEM is double-buffered (2 x 2 chains x 128 columns = 512 columns), so it overlaps the next group's MMAs
 // Shared memory: 4 operand stages x (hi + lo) x 16 KiB + 6 raw stages x 16 KiB = 224 KiB (the pipeline unit is one chain's K-block).
-#include <cuda.h>
 #include "btkb_internal.h"
+#include "btkb_tensor_map.h"
 #include <stdint.h>
 #include <cstdlib>
 
@@ -291,24 +291,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
 
 // S viewed as float32 [G C rows][2 Ts]; box {2 KB floats, 64 rows}
 static cudaError_t make_series_map(CUtensorMap* tm, const PerBinArgs& a) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess) return e;
-    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)2 * a.Ts, (cuuint64_t)a.G * a.C};
-  cuuint64_t gstride[1] = {(cuuint64_t)a.Ts * sizeof(float2)};
-  cuuint32_t box[2] = {(cuuint32_t)(2 * tc::KB), (cuuint32_t)tc::C64};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.Scov, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+  return encode_tensor_map_2d_f32(tm, a.Scov, (cuuint64_t)2 * a.Ts, (cuuint64_t)a.G * a.C, (cuuint64_t)a.Ts * sizeof(float2), (cuuint32_t)(2 * tc::KB),
+                                  (cuuint32_t)tc::C64, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 size_t covariance_tc_workspace_bytes(int G, int C, int T) { return (size_t)G * C * (size_t)((T + tc::KB - 1) / tc::KB * tc::KB) * sizeof(float2); }

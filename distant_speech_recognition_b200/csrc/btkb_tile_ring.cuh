@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>           // CUtensorMap (the encode entry point is fetched at run time; libcuda is not linked)
 #include "btkb_internal.h"
+#include "btkb_tensor_map.h"
 
 namespace btkb {
 
@@ -109,24 +110,8 @@ __host__ __device__ constexpr size_t ring_bytes() { return ((sizeof(float2) * ST
 
 // Tensor map of X viewed as a 2-D float tensor [T*C rows][2*Gp floats]; box = [FCH*C rows][2*TILE floats].
 static inline cudaError_t make_tensor_map(CUtensorMap* tm, const PerBinArgs& a, int C) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess) return e;
-    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C};
-  cuuint64_t gstride[1] = {(cuuint64_t)a.Gp * sizeof(float2)};
-  cuuint32_t box[2] = {(cuuint32_t)(2 * TILE), (cuuint32_t)(FCH * C)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(a.X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+  return encode_tensor_map_2d_f32(tm, a.X, (cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C, (cuuint64_t)a.Gp * sizeof(float2), (cuuint32_t)(2 * TILE),
+                                  (cuuint32_t)(FCH * C), CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 }  // namespace btkb

@@ -12,6 +12,7 @@
 // contraction for the 64-mic covariance is a later-round item.
 #include <cuda.h>
 #include "btkb_internal.h"
+#include "btkb_tensor_map.h"
 #include "btkb_fft.cuh"
 #include "../../include/btkb.h"
 
@@ -318,23 +319,8 @@ __global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, 
 }
 
 static cudaError_t make_map_wide(CUtensorMap* tm, const PerBinArgs& a, int C) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-    if (e != cudaSuccess) return e;
-    if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
-    encode = reinterpret_cast<EncodeFn>(fn);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C};
-  cuuint64_t gstride[1] = {(cuuint64_t)a.Gp * sizeof(float2)};
-  cuuint32_t box[2] = {(cuuint32_t)(2 * TC), (cuuint32_t)C};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(a.X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return (r == CUDA_SUCCESS) ? cudaSuccess : cudaErrorInvalidValue;
+  return encode_tensor_map_2d_f32(tm, a.X, (cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C, (cuuint64_t)a.Gp * sizeof(float2), (cuuint32_t)(2 * TC), (cuuint32_t)C,
+                                  CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <int L>
