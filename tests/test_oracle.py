@@ -338,3 +338,21 @@ def test_wpe_single_channel_golden(protos):
     assert rel_l2(Xa[:, 0, :129], g["Xa"]) < 1e-11 and rel_l2(Xb[:, 0, :129], g["Xb"]) < 1e-11
     assert ua == int(g["used_a"]) and ub == int(g["used_b"]) == 40
     assert rel_l2(restate.synthesis(Xa[:, 0, :], gg, 256, 4, 1), g["time_a"]) < 1e-6
+
+
+def test_gsc_rls_cpp_golden(protos):
+    """The reference's C++ SubbandGSCRLS (beamformer.cc:1447-1699), run through the compiled reference: the B-form restatement
+    follows it to 1e-9.  At the class defaults (init_precision_matrix(0.01) on int16-scale spectra) the recursion cancels 14
+    digits in every update (Pz - gz Z^H Pz with Z^H Pz Z ~ 1e14 mu), so even in fp64 an algebraically equal form (the
+    blocking-matrix-free projector form) lands 1e-4 away: the reason this class has no fp32 CUDA kernel."""
+    CASES = (dict(mu=0.9, sigma2=0.01, init_sigma2=0.01), dict(mu=0.97, sigma2=0.0, init_sigma2=1e6, alpha=0.5, qctype=2),
+             dict(mu=0.95, sigma2=1e-3, init_sigma2=1.0, alpha=0.3, qctype=1))   # tests/golden/make_golden_rls_cpp.py
+    g = load_golden("gscrls_cpp_c4_m256"); h, _ = protos[256]
+    X = _X(g["x"], h, 256)
+    for i, kw in enumerate(CASES):
+        Y, _ = restate.gsc_rls_cpp(X, FS, g["delays"], **kw)
+        assert rel_l2(Y[:, :129], g["Y%d" % i]) < 1e-8, i
+    Yp, _ = restate.gsc_rls_cpp(X, FS, g["delays"], projector=True, **CASES[0])
+    assert 1e-6 < rel_l2(Yp[:, :129], g["Y0"]) < 1e-2          # equal algebra, 14 cancelled digits
+    Yp, _ = restate.gsc_rls_cpp(X, FS, g["delays"], projector=True, **CASES[1])
+    assert rel_l2(Yp[:, :129], g["Y1"]) < 1e-8                 # a well-scaled start (1/sigma2 = 1e-6) behaves
