@@ -140,6 +140,15 @@ class SubbandGSCBeamformer(SubbandBeamformer):
         self._wq = numpy.array([self._beamformer.get_weights(m) for m in range(self._fftlen2 + 1)], numpy.complex128)
 
 
+    def calc_beamformer_weights_n(self, samplerate, delays_t, delays_js, update_active_weights=True):
+        """lib/pybeamformer.py:516-535 — LCMV: one distortionless constraint plus Nc-1 nulls."""
+        assert (self._Nc - 1) == len(delays_js), 'Mismatch between no. constraints and no. jammers'
+        self._beamformer.calc_gsc_weights_n(samplerate, numpy.asarray(delays_t, numpy.float64), numpy.asarray(delays_js, numpy.float64), self._Nc)
+        if update_active_weights:
+            self.set_active_weights()
+        self._wqH = numpy.conjugate(numpy.array([self._beamformer.get_weights(m) for m in range(self._fftlen2 + 1)], numpy.complex128))
+
+
 class SubbandMVDRBeamformer(SubbandBeamformer):
     """lib/pybeamformer.py:538-585 — super-directive / MVDR beamformer."""
 

@@ -458,20 +458,28 @@ void SubbandDS::configure_weights_(btkb_pipeline* p) {
 
 // ---- SubbandGSC
 SubbandGSC::SubbandGSC(unsigned fftLen, bool hbs, const std::string& nm) : SubbandDS(fftLen, hbs, nm, BTKB_BF_GSC) {}
+void SubbandGSC::calc_gsc_weights_n(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ, unsigned NC) {
+  const unsigned C = chanN();
+  if (NC < 2 || NC > C) throw jdimension_error("1 < the number of constraints %d <= the number of sensors %d.\n", (int)NC, (int)C);   // beamformer.cc:592-594
+  if (delaysJ.size() != (size_t)(NC - 1) * C) throw jdimension_error("delays of the interference signals must be %d x %d\n", (int)(NC - 1), (int)C);
+  calc_array_manifold_vectors(samplerate, delaysT);
+  delaysJ_ = delaysJ; NC_ = NC; wa_.clear(); have_wa_ = false;
+}
 void SubbandGSC::set_active_weights_f(unsigned fbinX, const std::vector<double>& packed) {  // beamformer.cc:729-748,1365-1372
   require_weights_(have_delays_, "call calc_gsc_weights_x() once\n");
-  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
-  if (packed.size() != 2 * (C - 1)) throw jdimension_error("the size of an active weight vector must be %d but it is %d\n", (int)(2 * (C - 1)), (int)packed.size());
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1, NA = C - NC_;
+  if (packed.size() != 2 * NA) throw jdimension_error("the size of an active weight vector must be %d but it is %d\n", (int)(2 * NA), (int)packed.size());
   if (fbinX >= fftLen_) throw jdimension_error("Must be a frequency bin %d < the length of FFT %d\n", fbinX, fftLen_);
   if (fbinX >= K) return;  // mirrored bins are never used by next()
-  if (wa_.size() != (size_t)K * (C - 1)) wa_.assign((size_t)K * (C - 1), std::complex<float>(0, 0));
-  for (unsigned i = 0; i < C - 1; i++) wa_[(size_t)fbinX * (C - 1) + i] = std::complex<float>((float)packed[2 * i], (float)packed[2 * i + 1]);
+  if (wa_.size() != (size_t)K * NA) wa_.assign((size_t)K * NA, std::complex<float>(0, 0));
+  for (unsigned i = 0; i < NA; i++) wa_[(size_t)fbinX * NA + i] = std::complex<float>((float)packed[2 * i], (float)packed[2 * i + 1]);
   have_wa_ = true; invalidate_();
 }
 void SubbandGSC::zero_active_weights() { require_weights_(have_delays_, "call calc_gsc_weights_x() once\n"); wa_.clear(); have_wa_ = false; invalidate_(); }
 void SubbandGSC::configure_weights_(btkb_pipeline* p) {
   require_weights_(have_delays_, "call calc_gsc_weights_X() once\n");  // beamformer.cc:1262-1264
-  ck(btkb_set_delays(p, 1, delays_.data()));
+  if (NC_ > 1) ck(btkb_set_delays_lcmv(p, 1, (int)NC_, delays_.data(), delaysJ_.data()));
+  else ck(btkb_set_delays(p, 1, delays_.data()));
   if (have_wa_) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
 }
 

@@ -300,13 +300,17 @@ typedef std::shared_ptr<SubbandDS> SubbandDSPtr;
 class SubbandGSC : public SubbandDS {
  public:
   SubbandGSC(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandGSC");
-  void calc_gsc_weights(double samplerate, const std::vector<double>& delaysT) { calc_array_manifold_vectors(samplerate, delaysT); }
+  void calc_gsc_weights(double samplerate, const std::vector<double>& delaysT) { NC_ = 1; delaysJ_.clear(); calc_array_manifold_vectors(samplerate, delaysT); }
+  // LCMV quiescent weights: one target + NC-1 jammers, delaysJ flat [NC-1][C] (beamformer.cc:1332-1362)
+  void calc_gsc_weights_n(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ, unsigned NC = 2);
+  void calc_gsc_weights_2(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ) { calc_gsc_weights_n(samplerate, delaysT, delaysJ, 2); }
   void set_active_weights_f(unsigned fbinX, const std::vector<double>& packedWeight);
   void zero_active_weights();
  protected:
   void configure_weights_(btkb_pipeline* p) override;
-  std::vector<std::complex<float>> wa_;  // [K][C-1]
+  std::vector<std::complex<float>> wa_;  // [K][C-NC]
   bool have_wa_ = false;
+  std::vector<double> delaysJ_; unsigned NC_ = 1;
 };
 typedef std::shared_ptr<SubbandGSC> SubbandGSCPtr;
 

@@ -197,6 +197,12 @@ PYBIND11_MODULE(_btk20host, m) {
            py::arg("half_band_shift") = false, py::arg("nm") = "SubbandGSC")
       .def("calc_gsc_weights", [](SubbandGSC& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { s.calc_gsc_weights(fs, vec_d(d)); },
            py::arg("samplerate"), py::arg("delaysT"))
+      .def("calc_gsc_weights_n", [](SubbandGSC& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> dT,
+                                    py::array_t<double, py::array::c_style | py::array::forcecast> dJ, unsigned NC) { s.calc_gsc_weights_n(fs, vec_d(dT), vec_d(dJ), NC); },
+           py::arg("samplerate"), py::arg("delays_t"), py::arg("delays_j"), py::arg("NC") = 2)
+      .def("calc_gsc_weights_2", [](SubbandGSC& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> dT,
+                                    py::array_t<double, py::array::c_style | py::array::forcecast> dJ) { s.calc_gsc_weights_2(fs, vec_d(dT), vec_d(dJ)); },
+           py::arg("samplerate"), py::arg("delays_t"), py::arg("delays_j"))
       .def("set_active_weights_f", [](SubbandGSC& s, unsigned f, py::array_t<double, py::array::c_style | py::array::forcecast> w) { s.set_active_weights_f(f, vec_d(w)); },
            py::arg("fbinX"), py::arg("packedWeight"))
       .def("zero_active_weights", &SubbandGSC::zero_active_weights);

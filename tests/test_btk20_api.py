@@ -182,6 +182,33 @@ def test_frontend_flow_gsc_zelinski(protos):
 
 
 @pytest.mark.gpu
+def test_frontend_flow_lcmv_zelinski(protos):
+    """confs/lcmv_and_zelinski.json flow (test_online_beamforming.py:92-100,183): SubbandGSCBeamformer(afbs, Nc=2),
+    calc_beamformer_weights_n(samplerate, delays_t, delays_js), Zelinski post-filter, synthesis; weights vs the reference's
+    golden (calcMainlobe2), output vs the fp64 restatement."""
+    from oracle import restate
+    from distant_speech_recognition_b200 import synthetic
+    g = load_golden("lcmv"); h, gg = protos[512]; M, D, C = 512, 256, 8
+    x, _, _, _ = synthetic.make_utterance(31, C, 9000)
+    afbs = _afbs(x, h, M, D)
+    bf = pybeamformer.SubbandGSCBeamformer(afbs, Nc=2)
+    with pytest.raises(AssertionError):
+        bf.calc_beamformer_weights_n(FS, g["dT"], [g["dJ1"], g["dJ2"]])      # Nc - 1 jammers expected
+    bf.calc_beamformer_weights_n(FS, g["dT"], [g["dJ1"]])
+    assert rel_l2(np.conj(bf._wqH), g["w2"]) < 1e-6
+    pf = ZelinskiPostFilterPtr(PyVectorComplexFeatureStreamPtr(bf), M, 0.7, 2)
+    pf.set_beamformer(bf.beamformer())
+    sfb = OverSampledDFTSynthesisBankPtr(pf, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+    y = np.concatenate([np.array(b) for b in sfb])
+    X = np.stack([restate.analysis(x[c], h, M, 4, 1) for c in range(C)], axis=1)
+    w2 = np.concatenate([g["w2"], np.conj(g["w2"][1:256][::-1])])          # full-band quiescent vectors (Hermitian mirror)
+    Yo = restate.subband_gsc(X, w2, np.zeros_like(w2))
+    ta = restate.calc_mainlobe(M, C, FS, g["dT"])                          # the post-filter aligns with the D&S manifold
+    Yz, _ = restate.zelinski_postfilter(Yo, X, ta, 0.7, 2, 0)
+    assert rel_l2(y, restate.synthesis(Yz, gg, M, 4, 1)) < 1e-4
+
+
+@pytest.mark.gpu
 def test_frontend_flow_sd_mccowan_and_ds_lefkimmiatis(protos):
     """unit_test/test_online_beamforming.py:132-156,204 with confs/sd_and_mccowan.json and sd_and_lefkimmiatis.json parameters."""
     g = load_golden("mccowan_c4_m256"); h, gg = protos[256]; M, D = 256, 128
