@@ -45,7 +45,7 @@ struct btkb_pipeline {
   cudaEvent_t wev[2] = {nullptr, nullptr};
   // SOS batch beamformers (lazily allocated by the first btkb_sos_accumulate_*)
   double2 *d_sosR = nullptr, *d_sosWd = nullptr; double* d_sosCnt = nullptr; float *d_sosWtu = nullptr, *d_sosMask = nullptr; double* d_sosLab = nullptr;
-  int* d_sosErr = nullptr; int sos_NLcap = 0; bool have_sos = false;
+  int* d_sosErr = nullptr; int sos_NLcap = 0, sos_U = 0; bool have_sos = false;
   float2* d_covS = nullptr;   // series-major workspace of the 64-mic tensor-core covariance (lazily allocated)
   bool have_pfR = false, pf_applied = false;  // pf_applied: d_Y came out of this pipeline's post-filter (not btkb_set_subband)
   // batch state
@@ -629,6 +629,9 @@ static int sos_check(btkb_pipeline* p, const char* who, bool need_X) {
   if (p->cfg.beamformer != BTKB_BF_DS) return fail(BTKB_ERR_STATE, std::string(who) + ": the SOS beamformers apply their weights like SubbandDS; create the pipeline with BTKB_BF_DS");
   if (!(p->C == 2 || p->C == 4 || p->C == 8)) return fail(BTKB_ERR_INVALID, std::string(who) + ": built for 2, 4 or 8 channels");
   if (need_X && !p->have_X) return fail(BTKB_ERR_STATE, std::string(who) + ": run the analysis first");
+  if (need_X && p->have_sos && p->sos_U != p->U)
+    return fail(BTKB_ERR_INVALID, std::string(who) + ": statistics were accumulated for " + std::to_string(p->sos_U) + " utterances, this batch has " +
+                                      std::to_string(p->U) + " (call btkb_sos_reset_stats first)");
   return BTKB_OK;
 }
 static int sos_alloc(btkb_pipeline* p) {
@@ -672,7 +675,7 @@ int btkb_sos_accumulate_from_label(btkb_pipeline* p, const double* labels, int N
   a.labels = p->d_sosLab; a.NL = NL; a.thr = energy_threshold;
   CK(launch_sos_accumulate(a, p->stream, &p->launches));
   CK(cudaStreamSynchronize(p->stream));   // `labels` may be pageable host memory
-  p->have_sos = true; p->wU = p->U;
+  p->have_sos = true; p->wU = p->U; p->sos_U = p->U;
   return BTKB_OK;
 }
 
@@ -695,7 +698,7 @@ int btkb_sos_accumulate_from_tfmask(btkb_pipeline* p, const float* mask_t, const
   a.mask_t = mt; a.mask_j = mj; a.thr = energy_threshold;
   CK(launch_sos_accumulate(a, p->stream, &p->launches));
   CK(cudaStreamSynchronize(p->stream));
-  p->have_sos = true; p->wU = p->U;
+  p->have_sos = true; p->wU = p->U; p->sos_U = p->U;
   return BTKB_OK;
 }
 
