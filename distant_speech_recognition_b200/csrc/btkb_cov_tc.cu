@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; s++) { mb_init(full + s, PROD_WARPS * 32); mb_init(empty + s, 1); }
+    for (int s = 0; s < NSTAGE; s++) { mb_init(full + s, PROD_WARPS); mb_init(empty + s, 1); }   // one arrival per transposer warp
     for (int b = 0; b < 2; b++) { mb_init(accf + b, 1); mb_init(acce + b, EPI_WARPS * 32); }
-    for (int s = 0; s < NRAW; s++) { mb_init(rfull + s, 1); mb_init(rempty + s, PROD_WARPS * 32); }
+    for (int s = 0; s < NRAW; s++) { mb_init(rfull + s, 1); mb_init(rempty + s, PROD_WARPS); }
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,11 +202,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_covariance_tc(const __grid_const
             *reinterpret_cast<float*>(th + off2) = hi; *reinterpret_cast<float*>(tl + off2) = xi - hi;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
-          mb_arrive(full + s);
+          __syncwarp();                                                   // every lane's stores are fenced before the warp's one arrival
+          if (lane == 0) mb_arrive(full + s);
           // the raw slot is released only now: its values have been consumed by the stores above, so the loads have certainly
           // completed before the TMA unit (async proxy) may overwrite the slot.  Releasing right after ISSUING the loads let the
           // refill race them (sporadic 10-20 % errors in fully masked K-blocks, where the transposers run ahead).
-          mb_arrive(rempty + rs);
+          if (lane == 0) mb_arrive(rempty + rs);
         }
       }
     }
