@@ -383,6 +383,38 @@ def test_frontend_flow_wpe_into_gsclms(protos):
 
 
 @pytest.mark.gpu
+def test_batch_front_end(protos):
+    """btk20.batch.BatchBeamformer (the many-utterances-per-submission form bench.py measures) configured like the reference's JSON
+    files: gscrls, bmvdr from VAD labels, delay-and-sum behind WPE, each utterance of the batch against the reference's goldens."""
+    from oracle import restate
+    from distant_speech_recognition_b200.btk20.batch import BatchBeamformer
+    from test_oracle import WPE_8
+    h, gg = protos[512]; M = 512
+    # --- gscrls (confs/gscrls.json defaults, min_frames as in the golden)
+    g = load_golden("gscrls_c8_m512"); x = g["x"]
+    bb = BatchBeamformer(8, h, gg, M=M, beamformer={"type": "gscrls", "min_frames": int(g["min_frames"])}, max_utterances=2, max_samples=x.shape[1])
+    y, Y, st = bb.process(np.stack([x, x]), np.stack([g["delays"], g["delays"]]))
+    for u in range(2):
+        assert rel_l2(Y[u], g["Y"]) < 1e-4 and rel_l2(y[u][: len(g["time"])], g["time"]) < 1e-4 and st[u][2] == int(g["n_updates"])
+    # --- blind MVDR from VAD labels (confs/bmvdr_vad.json)
+    g = load_golden("bmvdr_vad_c8_m512"); x = g["x"]
+    bb = BatchBeamformer(8, h, gg, M=M, beamformer={"type": "bmvdr", "ref_micx": int(g["ref_micx"]), "offset": float(g["offset"]), "gamma": float(g["gamma"])},
+                         max_utterances=2, max_samples=x.shape[1])
+    y, Y, st = bb.process(np.stack([x, x]), vad_labels=np.stack([g["labels"], g["labels"]]))
+    for u in range(2):
+        assert rel_l2(Y[u], g["Y"]) < 1e-4 and rel_l2(y[u], g["time"]) < 1e-4
+    # --- delay-and-sum behind the multi-channel WPE (confs/wpe.json keys)
+    g = load_golden("wpe_c8_m512"); x = g["x"]
+    _, d, _, _ = __import__("distant_speech_recognition_b200.synthetic", fromlist=["x"]).make_utterance(7, 8, 16)
+    bb = BatchBeamformer(8, h, gg, M=M, beamformer={"type": "delay_and_sum"}, wpe=dict(WPE_8), max_utterances=2, max_samples=x.shape[1])
+    y, Y, st = bb.process(np.stack([x, x]), np.stack([d, d]))
+    Xa = np.concatenate([g["Xa"], np.conj(g["Xa"][:, :, 1:256][:, :, ::-1])], axis=2)       # full-band dereverberated snapshots of the reference
+    Yo = restate.subband_ds(Xa, restate.calc_mainlobe(M, 8, FS, d))
+    for u in range(2):
+        assert rel_l2(Y[u], Yo[:, :257]) < 1e-4
+
+
+@pytest.mark.gpu
 def test_generic_python_stream_into_synthesis_and_analysis_iteration(protos):
     """A pure-Python spatial filter between the banks (the reference's PyFeatureStream use): analysis frames are pulled
     one by one in Python, modified, and fed to the synthesis bank through PyVectorComplexFeatureStreamPtr."""
