@@ -356,3 +356,61 @@ def test_gsc_rls_cpp_golden(protos):
     assert 1e-6 < rel_l2(Yp[:, :129], g["Y0"]) < 1e-2          # equal algebra, 14 cancelled digits
     Yp, _ = restate.gsc_rls_cpp(X, FS, g["delays"], projector=True, **CASES[1])
     assert rel_l2(Yp[:, :129], g["Y1"]) < 1e-8                 # a well-scaled start (1/sigma2 = 1e-6) behaves
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Known-answer / property checks that need no golden (last row)
+def test_blocking_matrix_properties():
+    """calc_blocking_matrix_ (beamformer.cc:373-454): orthonormal columns, B B^H = P = I - conj(v) v^T / ||v||^2, B^T v = 0 — for
+    the delay-and-sum manifold of every bin and for NC = 2, 3 constraint sets."""
+    rng = np.random.default_rng(5)
+    C, M = 8, 512
+    d = rng.uniform(-2e-4, 2e-4, C)
+    wq = restate.calc_mainlobe(M, C, FS, d)
+    for f in (1, 7, 100, 255, 256):
+        v = wq[f]
+        for Nc in (1, 2, 3):
+            B = restate.calc_blocking_matrix(v, Nc)
+            assert B.shape == (C, C - Nc)
+            assert np.allclose(B.conj().T @ B, np.eye(C - Nc), atol=1e-12)
+            assert np.abs(B.T @ v).max() < 1e-12
+            if Nc == 1:
+                P = np.eye(C) - np.outer(np.conj(v), v) / np.real(np.vdot(v, v))
+                assert np.allclose(B @ B.conj().T, P, atol=1e-12)
+
+
+def test_mvdr_is_distortionless_and_ds_returns_a_plane_wave(protos):
+    """w^H v = 1 for the MVDR weights of any Hermitian positive-definite R (calc_mvdr_weights, beamformer.cc:2350-2402, with
+    d = wq = v / C); delay-and-sum of a pure look-direction plane wave returns the source spectrum (SubbandDS::next)."""
+    rng = np.random.default_rng(6)
+    C, M = 8, 256; K = M // 2 + 1
+    d = rng.uniform(-2e-4, 2e-4, C)
+    wq = restate.calc_mainlobe(M, C, FS, d)
+    A = rng.standard_normal((K, C, 3 * C)) + 1j * rng.standard_normal((K, C, 3 * C))
+    R = A @ np.conj(np.transpose(A, (0, 2, 1))) + 0.1 * np.eye(C)
+    w = restate.calc_mvdr_weights(R, wq, single=False)
+    v = wq[:K] * C                                              # array manifold (unit modulus)
+    assert np.abs(np.einsum("kc,kc->k", np.conj(w[1:K]), v[1:K]) - 1.0).max() < 1e-10
+    assert np.allclose(w[0], 1.0)                               # the reference's DC quirk (beamformer.cc:2369-2371)
+    s = rng.standard_normal((5, K)) + 1j * rng.standard_normal((5, K))
+    X = np.zeros((5, C, M), complex)
+    X[:, :, :K] = s[:, None, :] * v.T[None, :, :]
+    Y = restate.subband_ds(X, wq)
+    assert np.abs(Y[:, 1:K - 1] - s[:, 1:K - 1]).max() < 1e-12
+
+
+def test_filterbank_round_trip_and_zelinski_gain_range(protos):
+    """Analysis -> synthesis of one channel reproduces the (delayed) input to the prototype's design accuracy (interior error
+    1.7e-3 with the shipped M = 256 pair); the Zelinski gain stays inside [1e-4, 1] (postfilter.cc:30-41)."""
+    h, g = protos[256]; M, m, r = 256, 4, 1; D = M >> r
+    rng = np.random.default_rng(7)
+    x = (3000 * rng.standard_normal(6000)).astype(np.float32)
+    X = restate.analysis(x, h, M, m, r)
+    y = restate.synthesis(X, g, M, m, r)
+    a, b = m * M, len(x) - m * M          # interior: delay compensation type 2 leaves no delay, the edges carry the filter transients
+    assert np.linalg.norm(y[a:b] - x[a:b]) / np.linalg.norm(x[a:b]) < 3e-3
+    xs = np.stack([x, np.roll(x, 3), x + 50 * rng.standard_normal(len(x)).astype(np.float32), 0.5 * x])
+    Xs = np.stack([restate.analysis(xs[c], h, M, m, r) for c in range(4)], axis=1)
+    wq = restate.calc_mainlobe(M, 4, FS, np.zeros(4))
+    Yz, W = restate.zelinski_postfilter(restate.subband_ds(Xs, wq), Xs, wq, 0.6, 2, 0)
+    assert W.min() >= 1e-4 - 1e-12 and W.max() <= 1.0 + 1e-12
