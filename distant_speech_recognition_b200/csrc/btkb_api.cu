@@ -705,7 +705,7 @@ int btkb_sos_accumulate_from_tfmask(btkb_pipeline* p, const float* mask_t, const
 int btkb_sos_calc_weights(btkb_pipeline* p, int kind, double gamma, int ref_micx, double offset) {
   int rc = sos_check(p, "btkb_sos_calc_weights", false); if (rc) return rc;
   if (kind != BTKB_SOS_BMVDR && kind != BTKB_SOS_GEV) return fail(BTKB_ERR_INVALID, "btkb_sos_calc_weights: unknown kind");
-  if (!p->have_sos) return fail(BTKB_ERR_STATE, kind == BTKB_SOS_BMVDR ? "No target signal SOS" : "No target signal SOS");   // pybeamformer.py:1270-1273
+  if (!p->have_sos) return fail(BTKB_ERR_STATE, "No target signal SOS");   // pybeamformer.py:1270-1273
   if (ref_micx < 0 || ref_micx >= p->C) return fail(BTKB_ERR_INVALID, "btkb_sos_calc_weights: ref_micx out of range");
   if (!(offset >= 0.0 && offset <= 1.0)) return fail(BTKB_ERR_INVALID, "The offset value " + std::to_string(offset) + " is out of [0, 1]");   // :1274
   CK(cudaSetDevice(p->cfg.device));
