@@ -16,8 +16,9 @@
 // (4 + 2C FMA per entry-frame instead of 4C).  The right-hand side rides along as row L of the matrix (the Cholesky factor
 // of [[R, r], [r^H, .]] carries L^-1 r in its last row), so the forward substitution costs nothing extra; k_wpe_chol is a
 // right-looking panel Cholesky (panel in shared memory, trailing update on the L2-resident workspace) followed by a
-// panel-wise backward substitution.  First-round version: fp32 CUDA-core arithmetic; the tcgen05 contraction for k_wpe_corr
-// is the next step.
+// panel-wise backward substitution.  Arithmetic: fp64 like the reference (RT = double; the loaded normal equations need it for
+// the 1e-4 parity budget) or fp32 (cfg.wpe.fp32_normal_equations) on the CUDA cores; DESIGN.md K7 says why the Gram is not on the
+// tensor cores.
 #include "btkb_internal.h"
 #include <math.h>
 #include <algorithm>
