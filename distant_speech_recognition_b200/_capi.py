@@ -361,6 +361,13 @@ class Pipeline:
         _check(lib.btkb_get_postfilter_weights(self._h, _fp(out)))
         return out
 
+    def device_pointers(self):
+        """(X, Y, time) device addresses of the resident snapshots [T][C][Gp] complex64, beamformed output [T][Gp] complex64 and
+        resynthesised signal [U][nb D] float32, for zero-copy consumers (e.g. torch tensors built from raw pointers)."""
+        X, Y, t = ct.c_void_p(), ct.c_void_p(), ct.c_void_p()
+        _check(lib.btkb_device_pointers(self._h, ct.byref(X), ct.byref(Y), ct.byref(t)))
+        return X.value, Y.value, t.value
+
     def last_timing(self):
         """dict(total_ms, analysis_ms, perbin_ms, synthesis_ms, launches) of the last run (CUDA events on the pipeline stream)."""
         out = (ct.c_float * 5)()

@@ -33,6 +33,13 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, n), "libbtkb.so does not export %s declared in include/btkb.h" % n
 
 
+def test_every_entry_point_has_a_python_binding():
+    """The ctypes layer (the host side the tests and bench.py drive) reaches every function include/btkb.h declares."""
+    src = open(os.path.join(ROOT, "distant_speech_recognition_b200", "_capi.py")).read()
+    missing = [n for n in _declared() if ("lib.%s(" % n) not in src and ("lib.%s." % n) not in src]
+    assert not missing, missing
+
+
 def test_no_cpu_fallback(lib):
     from distant_speech_recognition_b200 import _capi
     if _capi.device_count() > 0:
