@@ -76,7 +76,47 @@ def one(name, kind, C, M, n, useed, labels=None, mask=None, **kw):
          energy_threshold=kw.get("energy_threshold", 10), **extra)
 
 
+def kinect():
+    """The reference's OWN fixtures for this path (unit_test/confs/{bmvdr,gev}_tfmask.json): the 4-channel Kinect recording
+    unit_test/data/CMU/R1/M1005/KINECT/RAW/segmented/U1001_1M_16k_b16_c{1..4}.wav, its speech / noise TF-mask pickles (622 x 129)
+    and the shipped M = 256 prototype pickles; first 240 frames.  Stored: the int16 samples, the masks, and the outputs of the
+    reference's SubbandBlindMVDRBeamformer / SubbandGEVBeamformer."""
+    import pickle, wave
+    base = "/root/reference/btk20_src/unit_test/"
+    d = base + "data/CMU/R1/M1005/KINECT/RAW/segmented/"
+    M, K, NF = 256, 129, 240
+    xs = []
+    for c in range(1, 5):
+        w = wave.open(d + "U1001_1M_16k_b16_c%d.wav" % c); xs.append(np.frombuffer(w.readframes(w.getnframes()), np.int16)); w.close()
+    x16 = np.stack(xs)[:, : (NF - 4) * (M // 2)]
+
+    def load_mask(path):
+        rows = []
+        with open(path, "rb") as f:
+            while True:
+                try:
+                    rows.append(pickle.load(f, encoding="latin1"))
+                except EOFError:
+                    break
+        return np.array(rows)
+    mt = load_mask(d + "U1001_1M_16k.speech.tfmask.pickle")[:NF].astype(np.uint8)
+    mj = load_mask(d + "U1001_1M_16k.noise.tfmask.pickle")[:NF].astype(np.uint8)
+    h = np.asarray(pickle.load(open(base + "prototype.ny/h-M256-m4-r1.pickle", "rb"), encoding="latin1"), np.float64)
+    g = np.asarray(pickle.load(open(base + "prototype.ny/g-M256-m4-r1.pickle", "rb"), encoding="latin1"), np.float64)
+    x = x16.astype(np.float32)
+    X = snapshots(x, h, M)
+    assert X.shape[0] == NF
+    out = dict(x16=x16, mask_t=mt, mask_j=mj)
+    for kind in ("bmvdr", "gev"):
+        res = pyref.run_sos(kind, X, FS, M // 2, mask_t=mt.astype(np.float64), mask_j=mj.astype(np.float64), energy_threshold=10, gamma=1e-6)
+        out["w_" + kind] = np.conj(res["wqH"]); out["Y_" + kind] = res["Y"][:, :K].astype(np.complex64)
+        out["time_" + kind] = ref.synthesis(res["Y"], g, M, 4, 1).astype(np.float32)
+        out["ct"] = res["ct"]; out["cn"] = res["cn"]
+    save("sos_kinect_c4_m256", **out)
+
+
 def main():
+    kinect()
     one("bmvdr_vad_c8_m512", "bmvdr", 8, 512, 16000, 11, labels=[(0.3, 0.55), (0.7, -1)], ref_micx=2, offset=0.01)
     one("bmvdr_tfmask_c4_m256", "bmvdr", 4, 256, 8000, 12, mask="fractional", gamma=1e-4)
     one("gev_vad_c8_m512", "gev", 8, 512, 16000, 13, labels=[(0.3, 0.8)])

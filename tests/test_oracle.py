@@ -414,3 +414,25 @@ def test_filterbank_round_trip_and_zelinski_gain_range(protos):
     wq = restate.calc_mainlobe(M, 4, FS, np.zeros(4))
     Yz, W = restate.zelinski_postfilter(restate.subband_ds(Xs, wq), Xs, wq, 0.6, 2, 0)
     assert W.min() >= 1e-4 - 1e-12 and W.max() <= 1.0 + 1e-12
+
+
+def test_sos_on_the_references_own_fixtures():
+    """The reference's own fixtures for this path (confs/{bmvdr,gev}_tfmask.json): the 4-channel Kinect recording, its TF-mask pickles
+    and the shipped M = 256 prototypes (first 240 frames; golden_sos_kinect_c4_m256, tests/golden/make_golden_sos.py).  The
+    restatement reproduces the reference Python's blind-MVDR and GEV outputs on them."""
+    g = load_golden("sos_kinect_c4_m256")
+    p = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz"))
+    M, K = 256, 129
+    X = _X(g["x16"].astype(np.float32), p["h"], M)
+    mt, mj = g["mask_t"].astype(np.float64), g["mask_j"].astype(np.float64)
+    Rt, Rn, ct, cn = restate.sos_accumulate(X, FS, M // 2, mask_t=mt, mask_j=mj, energy_threshold=10.0)
+    assert np.array_equal(ct, g["ct"]) and np.array_equal(cn, g["cn"])
+    w = restate.sos_bmvdr_weights(Rt, Rn, ct, cn, gamma=1e-6, ref_micx=0, offset=0.0)
+    assert rel_l2(w, g["w_bmvdr"]) < 1e-10
+    Y = restate.sos_apply(X, w)
+    assert rel_l2(Y[:, :K], g["Y_bmvdr"]) < 1e-6
+    assert rel_l2(restate.synthesis(Y, p["g"], M, 4, 1), g["time_bmvdr"]) < 1e-6
+    w = restate.sos_gev_weights(Rt, Rn, cn, gamma=1e-6)
+    w = w * np.sign(np.real(np.vdot(w[0], g["w_gev"][0])))
+    assert rel_l2(w, g["w_gev"]) < 1e-9
+    assert rel_l2(restate.sos_apply(X, w)[:, :K], g["Y_gev"]) < 1e-6

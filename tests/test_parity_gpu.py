@@ -654,3 +654,25 @@ def test_wpe_single_channel_golden(capi, protos):
     p.run_wpe(2, 42)
     assert rel_l2(p.fetch_snapshots()[0][:, 0, :], g["Xb"]) < TOL
     p.close()
+
+
+def test_blind_mvdr_on_the_references_own_fixtures(capi):
+    """confs/bmvdr_tfmask.json on the reference's own fixtures (Kinect recording as 16-bit PCM, TF-mask pickles, shipped M = 256
+    prototypes; first 240 frames) against the reference Python's output (golden_sos_kinect_c4_m256)."""
+    import os
+    from conftest import GOLDEN
+    g = load_golden("sos_kinect_c4_m256")
+    pr = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz"))
+    x16 = g["x16"]
+    p = capi.Pipeline(4, 256, 4, 1, beamformer=capi.BF_DS, max_utterances=1, max_samples=x16.shape[1])
+    p.set_prototypes(pr["h"], pr["g"])
+    p.submit_i16(x16[None])
+    p.run_analysis()
+    p.sos_accumulate_from_tfmask(g["mask_t"].astype(np.float32), g["mask_j"].astype(np.float32), 10.0)
+    _, _, cnt = p.sos_get_stats()
+    assert np.array_equal(cnt[0, :, 0], g["ct"]) and np.array_equal(cnt[0, :, 1], g["cn"])
+    p.sos_calc_weights(capi.SOS_BMVDR, gamma=1e-6, ref_micx=0, offset=0.0)
+    assert rel_l2(p.get_weights()[0], g["w_bmvdr"]) < 5e-4
+    p.run_beamformer(True)
+    assert rel_l2(p.fetch_subband()[0], g["Y_bmvdr"]) < TOL
+    assert rel_l2(p.fetch_time()[0], g["time_bmvdr"]) < TOL
