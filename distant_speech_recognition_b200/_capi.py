@@ -351,6 +351,11 @@ class Pipeline:
         _check(lib.btkb_get_active_weights(self._h, _fp(out)))
         return out
 
+    def get_sidelobe_weights(self):
+        out = np.empty((self.U, self.K, self.C), np.complex64)
+        _check(lib.btkb_get_sidelobe_weights(self._h, _fp(out)))
+        return out
+
     def get_covariance(self):
         out = np.empty((self.U, self.K, self.C, self.C), np.complex64)
         _check(lib.btkb_get_covariance(self._h, _fp(out)))

@@ -1,8 +1,15 @@
 """btk20.stream (stream/stream.i:24-237): stream handle classes and the Python->C++ adapter."""
 from .. import _btk20host as _h
 
+VectorCharFeatureStreamPtr = _h.VectorCharFeatureStreamPtr
+VectorShortFeatureStreamPtr = _h.VectorShortFeatureStreamPtr
 VectorFloatFeatureStreamPtr = _h.VectorFloatFeatureStreamPtr
+VectorFeatureStreamPtr = _h.VectorFeatureStreamPtr
 VectorComplexFeatureStreamPtr = _h.VectorComplexFeatureStreamPtr
+# stream/pyStream.h:136-231: the Python -> C++ adapters of the other element types
+PyVectorShortFeatureStreamPtr = _h.PyVectorShortFeatureStreamPtr
+PyVectorFloatFeatureStreamPtr = _h.PyVectorFloatFeatureStreamPtr
+PyVectorFeatureStreamPtr = _h.PyVectorFeatureStreamPtr
 
 
 def PyVectorComplexFeatureStreamPtr(obj, nm="PyVectorComplexFeatureStream"):

@@ -1002,6 +1002,19 @@ int btkb_get_active_weights(btkb_pipeline* p, float* out) {
   return get_rows(p, p->d_WA, p->C - p->NC, out);
 }
 
+int btkb_get_sidelobe_weights(btkb_pipeline* p, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_w) return fail(BTKB_ERR_STATE, "btkb_get_sidelobe_weights: no weights");
+  if (p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS)
+    return fail(BTKB_ERR_INVALID, "btkb_get_sidelobe_weights: the adaptive kernels carry u = wa^H B^T, not wl; read btkb_get_active_weights");
+  CK(cudaSetDevice(p->cfg.device));
+  if (!p->have_wl) {  // zero_active_weights: wl = B 0 (beamformer.cc:1387-1399)
+    memset(out, 0, (size_t)(p->wU ? p->wU : p->U) * p->K * p->C * sizeof(float2));
+    return BTKB_OK;
+  }
+  return get_rows(p, p->d_WL, p->C, out);
+}
+
 int btkb_get_covariance(btkb_pipeline* p, float* out) {
   if (!p || !out) return fail(BTKB_ERR_INVALID, "null argument");
   if (!p->have_R) return fail(BTKB_ERR_STATE, "btkb_get_covariance: no covariance");

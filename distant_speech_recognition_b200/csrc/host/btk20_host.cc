@@ -334,6 +334,7 @@ void SubbandBeamformer::ensure_pipeline_(const PostFilterConfig& pf, const Synth
   c.rls.regularization_param = (float)rls_.regularization_param; c.rls.sil_thresh = (float)rls_.sil_thresh; c.rls.alpha2 = (float)rls_.alpha2;
   c.rls.max_wa_l2norm = (float)rls_.max_wa_l2norm; c.rls.constraint_option = rls_.constraint_option; c.rls.min_frames = rls_.min_frames;
   c.max_utterances = 1; c.max_samples = (int)n_samples; c.synthesis_gain = syn.enabled ? syn.gain : 1;
+  c.normalize_weight = normalize_weight_ ? 1 : 0;
   if (wpe_) {
     const WpeConfig& w = wpe_->config();
     c.wpe.enabled = 1; c.wpe.lower_num = (int)w.lower_num; c.wpe.upper_num = (int)w.upper_num; c.wpe.iterations_num = (int)w.iterations_num;
@@ -443,17 +444,46 @@ std::vector<cplx> SubbandBeamformer::get_weights(unsigned fbinX) {
   return w;
 }
 
+void SubbandBeamformer::fetch_static_weights_(std::vector<std::complex<float>>& W, std::vector<std::complex<float>>& WL) {
+  const unsigned K = fftLen_ / 2 + 1, C = chanN();
+  if (channels_.empty() || !bank_behind(channels_[0], nullptr)) throw j_error("call set_channel() before asking for weights");
+  btkb_pipeline* keep = pipe_; pipe_ = nullptr;
+  try {
+    ensure_pipeline_(PostFilterConfig(), SynthesisConfig(), fftLen_);
+    configure_weights_(pipe_);
+    W.resize((size_t)K * C); WL.resize((size_t)K * C);
+    ck(btkb_get_weights(pipe_, reinterpret_cast<float*>(W.data())));
+    ck(btkb_get_sidelobe_weights(pipe_, reinterpret_cast<float*>(WL.data())));
+  } catch (...) {
+    if (pipe_) btkb_destroy(pipe_);
+    pipe_ = keep;
+    throw;
+  }
+  btkb_destroy(pipe_); pipe_ = keep;
+}
+
 // ---- SubbandDS
 SubbandDS::SubbandDS(unsigned fftLen, bool hbs, const std::string& nm, int kind) : SubbandBeamformer(fftLen, hbs, kind, nm) {}
 void SubbandDS::clear_channel() { SubbandBeamformer::clear_channel(); have_delays_ = false; W_.clear(); }
 void SubbandDS::calc_array_manifold_vectors(double samplerate, const std::vector<double>& delays) {
   if (delays.size() != chanN())  // beamformer.cc:504-506
     throw jdimension_error("Number of delays does not match number of channels (%d vs. %d).\n", (int)delays.size(), (int)chanN());
-  samplerate_ = samplerate; delays_ = delays; have_delays_ = true; W_.clear(); invalidate_();
+  samplerate_ = samplerate; delays_ = delays; have_delays_ = true; NC_ = 1; delaysJ_.clear(); W_.clear(); invalidate_();   // alloc_bfweight_(1, 1)
+}
+void SubbandDS::calc_array_manifold_vectors_n(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ, unsigned NC) {
+  const unsigned C = chanN();
+  if (NC < 2 || NC > C) throw jdimension_error("1 < the number of constraints %d <= the number of sensors %d.\n", (int)NC, (int)C);   // beamformer.cc:592-594
+  if (delaysJ.size() != (size_t)(NC - 1) * C) throw jdimension_error("delays of the interference signals must be %d x %d\n", (int)(NC - 1), (int)C);
+  calc_array_manifold_vectors(samplerate, delaysT);
+  delaysJ_ = delaysJ; NC_ = NC;
+}
+void SubbandDS::set_delays_(btkb_pipeline* p) {
+  if (NC_ > 1) ck(btkb_set_delays_lcmv(p, 1, (int)NC_, delays_.data(), delaysJ_.data()));
+  else ck(btkb_set_delays(p, 1, delays_.data()));
 }
 void SubbandDS::configure_weights_(btkb_pipeline* p) {
   require_weights_(have_delays_, "call calc_array_manifold_vectorsX() once\n");  // beamformer.cc:1098-1100
-  ck(btkb_set_delays(p, 1, delays_.data()));
+  set_delays_(p);
 }
 
 // ---- SubbandGSC
@@ -465,8 +495,50 @@ void SubbandGSC::calc_gsc_weights_n(double samplerate, const std::vector<double>
   calc_array_manifold_vectors(samplerate, delaysT);
   delaysJ_ = delaysJ; NC_ = NC; wa_.clear(); have_wa_ = false;
 }
+void SubbandGSC::set_quiescent_weights_f(unsigned fbinX, const std::vector<cplx>& srcWq) {   // beamformer.cc:1318-1324
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
+  if (C == 0) throw j_error("set_channel() has not been called\n");
+  if (srcWq.size() != C) throw jdimension_error("the quiescent vector must have %d elements but it has %d\n", (int)C, (int)srcWq.size());
+  if (fbinX >= fftLen_) throw jindex_error("fbinX %d must be less than %d\n", fbinX, fftLen_);
+  // alloc_bfweight_(1, 1): a fresh, zeroed BeamformerWeights (beamformer.cc:1082-1092); bins above M/2 are never read by next()
+  wq_explicit_.assign((size_t)K * C, std::complex<float>(0, 0));
+  if (fbinX < K) for (unsigned c = 0; c < C; c++) wq_explicit_[(size_t)fbinX * C + c] = std::complex<float>((float)srcWq[c].real(), (float)srcWq[c].imag());
+  have_wq_explicit_ = true; have_delays_ = false; NC_ = 1; delaysJ_.clear(); wa_.clear(); have_wa_ = false; W_.clear(); invalidate_();
+}
+bool SubbandGSC::write_fir_coeff(const std::string& fn, unsigned winType) {   // beamformer.cc:775-828, 1364-1371
+  if (!have_delays_ && !have_wq_explicit_) { fprintf(stderr, "call calc_array_manifold_vectorsX() once\n"); return false; }
+  const unsigned M = fftLen_, M2 = M / 2, C = chanN();
+  std::vector<std::complex<float>> W, WL;
+  fetch_static_weights_(W, WL);
+  FILE* fp = fopen(fn.c_str(), "w");
+  if (!fp) { printf("could not open %s\n", fn.c_str()); return false; }
+  fprintf(fp, "%d %d\n", (int)C, (int)M);
+  std::vector<double> window(M);   // get_window (modulated.cc:47-73): 0 rectangle, 2 Hanning, otherwise Hamming
+  for (unsigned i = 0; i < M; i++) {
+    const double ph = 2.0 * M_PI * i / (double)(M - 1);
+    window[i] = (winType == 0) ? 1.0 : (winType == 2 ? 0.5 * (1.0 - std::cos(ph)) : 0.54 - 0.46 * std::cos(ph));
+  }
+  std::vector<cplx> spec(M), twid(M);
+  for (unsigned i = 0; i < M; i++) twid[i] = std::polar(1.0, 2.0 * M_PI * i / (double)M);
+  for (unsigned c = 0; c < C; c++) {
+    for (unsigned f = 0; f <= M2; f++) {
+      const cplx wq(W[(size_t)f * C + c].real(), W[(size_t)f * C + c].imag()), wl(WL[(size_t)f * C + c].real(), WL[(size_t)f * C + c].imag());
+      const cplx val = std::polar(1.0, M_PI * (double)(f + 1)) * std::conj(wq - wl);   // shift by fftLen/2
+      spec[f] = val;
+      if (f > 0 && f < M2) spec[M - f] = std::conj(val);
+    }
+    for (unsigned n = 0; n < M; n++) {   // gsl_fft_complex_radix2_inverse: (1/M) sum_f spec[f] e^{+2 pi i f n / M}; the real part is written
+      cplx acc(0, 0);
+      for (unsigned f = 0; f < M; f++) acc += spec[f] * twid[(size_t)f * n % M];
+      fprintf(fp, "%e ", window[n] * acc.real() / (double)M);
+    }
+    fprintf(fp, "\n");
+  }
+  fclose(fp);
+  return true;
+}
 void SubbandGSC::set_active_weights_f(unsigned fbinX, const std::vector<double>& packed) {  // beamformer.cc:729-748,1365-1372
-  require_weights_(have_delays_, "call calc_gsc_weights_x() once\n");
+  require_weights_(have_delays_ || have_wq_explicit_, "call calc_gsc_weights_x() once\n");
   const unsigned C = chanN(), K = fftLen_ / 2 + 1, NA = C - NC_;
   if (packed.size() != 2 * NA) throw jdimension_error("the size of an active weight vector must be %d but it is %d\n", (int)(2 * NA), (int)packed.size());
   if (fbinX >= fftLen_) throw jdimension_error("Must be a frequency bin %d < the length of FFT %d\n", fbinX, fftLen_);
@@ -475,11 +547,11 @@ void SubbandGSC::set_active_weights_f(unsigned fbinX, const std::vector<double>&
   for (unsigned i = 0; i < NA; i++) wa_[(size_t)fbinX * NA + i] = std::complex<float>((float)packed[2 * i], (float)packed[2 * i + 1]);
   have_wa_ = true; invalidate_();
 }
-void SubbandGSC::zero_active_weights() { require_weights_(have_delays_, "call calc_gsc_weights_x() once\n"); wa_.clear(); have_wa_ = false; invalidate_(); }
+void SubbandGSC::zero_active_weights() { require_weights_(have_delays_ || have_wq_explicit_, "call calc_gsc_weights_x() once\n"); wa_.clear(); have_wa_ = false; invalidate_(); }
 void SubbandGSC::configure_weights_(btkb_pipeline* p) {
-  require_weights_(have_delays_, "call calc_gsc_weights_X() once\n");  // beamformer.cc:1262-1264
-  if (NC_ > 1) ck(btkb_set_delays_lcmv(p, 1, (int)NC_, delays_.data(), delaysJ_.data()));
-  else ck(btkb_set_delays(p, 1, delays_.data()));
+  require_weights_(have_delays_ || have_wq_explicit_, "call calc_gsc_weights_X() once\n");  // beamformer.cc:1262-1264
+  if (have_wq_explicit_) ck(btkb_set_weights(p, 1, reinterpret_cast<const float*>(wq_explicit_.data())));
+  else set_delays_(p);
   if (have_wa_) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
 }
 
@@ -585,19 +657,39 @@ void SubbandSOSNative::configure_weights_(btkb_pipeline* p) {
 
 // ---- SubbandMVDR
 SubbandMVDR::SubbandMVDR(unsigned fftLen, bool hbs, const std::string& nm) : SubbandDS(fftLen, hbs, nm, BTKB_BF_MVDR) {}
-void SubbandMVDR::clear_channel() { SubbandDS::clear_channel(); R_.clear(); wmvdr_.clear(); have_R_ = have_w_ = diffuse_ = smi_ = false; }
+void SubbandMVDR::clear_channel() { SubbandDS::clear_channel(); R_.clear(); wmvdr_.clear(); load_f_.clear(); div_f_.clear(); have_R_ = have_w_ = diffuse_ = smi_ = false; }
+void SubbandMVDR::set_diagonal_looading(unsigned fbinX, float w) {   // beamformer.cc:2525-2535
+  if (!have_R_) throw j_error("Construct first a noise covariance matrix\n");
+  const unsigned K = fftLen_ / 2 + 1;
+  if (fbinX >= K) throw jindex_error("fbinX %d must be <= %d", fbinX, fftLen_ / 2);
+  if (load_f_.size() != K) load_f_.assign(K, 0.0);
+  load_f_[fbinX] += (double)w; have_w_ = false; W_.clear(); invalidate_();
+}
+void SubbandMVDR::divide_nondiagonal_elements(unsigned fbinX, float mu) {   // beamformer.cc:2589-2599
+  if (!have_R_) throw j_error("Construct first a noise covariance matrix\n");
+  const unsigned K = fftLen_ / 2 + 1;
+  if (fbinX >= K) throw jindex_error("fbinX %d must be <= %d", fbinX, fftLen_ / 2);
+  if (div_f_.size() != K) div_f_.assign(K, 1.0);
+  div_f_[fbinX] *= 1.0 + (double)mu; have_w_ = false; W_.clear(); invalidate_();
+}
+void SubbandMVDR::divide_all_nondiagonal_elements(float mu) {   // beamformer.h:357-360
+  for (unsigned f = 0; f <= fftLen_ / 2; f++) divide_nondiagonal_elements(f, mu);
+}
 bool SubbandMVDR::set_noise_spatial_spectral_matrix(unsigned fbinX, const std::vector<cplx>& Rnn) {  // beamformer.cc:2410-2433
   const unsigned C = chanN(), K = fftLen_ / 2 + 1;
   if (Rnn.size() != (size_t)C * C) { fprintf(stderr, "The number of the rows of the matrix must be %d\n", C); return false; }
   if (fbinX >= K) throw jindex_error("fbinX %d must be <= %d", fbinX, fftLen_ / 2);
   if (R_.size() != (size_t)K * C * C) R_.assign((size_t)K * C * C, std::complex<float>(0, 0));
   for (size_t i = 0; i < (size_t)C * C; i++) R_[(size_t)fbinX * C * C + i] = std::complex<float>((float)Rnn[i].real(), (float)Rnn[i].imag());
+  if (load_f_.size() == K) load_f_[fbinX] = 0.0;   // the bin's matrix is replaced, earlier edits of it are gone
+  if (div_f_.size() == K) div_f_[fbinX] = 1.0;
   have_R_ = true; diffuse_ = false; smi_ = false; mu_ = 0.0; have_w_ = false; invalidate_();
   return true;
 }
 bool SubbandMVDR::set_diffuse_noise_model(const std::vector<double>& mpos, double samplerate, double sspeed) {  // beamformer.cc:2442-2509
   if (mpos.size() != (size_t)chanN() * 3) { fprintf(stderr, "The number of microphones must be %d but it is %d\n", chanN(), (int)(mpos.size() / 3)); return false; }
   mpos_ = mpos; samplerate_ = samplerate; sspeed_ = sspeed; have_R_ = true; diffuse_ = true; smi_ = false; mu_ = 0.0; have_w_ = false; invalidate_();
+  load_f_.clear(); div_f_.clear();
   return true;
 }
 void SubbandMVDR::set_all_diagonal_loading(double w) {  // beamformer.cc:2511-2523 (R += w I, cumulative like the reference)
@@ -632,14 +724,29 @@ int SubbandMVDR::accumulate_noise_covariance(double samplerate, double start, do
   std::vector<std::complex<float>> Rn((size_t)K * C * C);
   ck(btkb_get_covariance(pipe_, reinterpret_cast<float*>(Rn.data())));
   R_ = Rn; have_R_ = true; diffuse_ = false; smi_ = true; mu_ = 0.0; have_w_ = false; invalidate_();
+  load_f_.clear(); div_f_.clear();
   return 0;
 }
 void SubbandMVDR::configure_weights_(btkb_pipeline* p) {
   require_weights_(have_delays_, "call calc_array_manifold_vectorsX() once\n");
   if (!have_w_) throw j_error("call calc_mvdr_weights() once\n");  // beamformer.cc:2544-2546
+  if (NC_ > 1) throw j_error("SubbandMVDR: the GPU MVDR solve takes the delay-and-sum manifold (calc_array_manifold_vectors), not LCMV weights\n");
   ck(btkb_set_delays(p, 1, delays_.data()));
   if (diffuse_) ck(btkb_set_diffuse_noise_model(p, 1, mpos_.data(), (float)sspeed_));
   else ck(btkb_set_noise_covariance(p, 1, reinterpret_cast<const float*>(R_.data())));
+  if (!load_f_.empty() || !div_f_.empty()) {   // per-bin edits (set_diagonal_looading, divide_nondiagonal_elements): O(K C^2) parameter edits
+    const unsigned K = fftLen_ / 2 + 1, C = chanN();
+    std::vector<std::complex<float>> R((size_t)K * C * C);
+    ck(btkb_get_covariance(p, reinterpret_cast<float*>(R.data())));
+    for (unsigned f = 0; f < K; f++)
+      for (unsigned i = 0; i < C; i++)
+        for (unsigned j = 0; j < C; j++) {
+          std::complex<float>& v = R[((size_t)f * C + i) * C + j];
+          if (i == j) { if (!load_f_.empty()) v += std::complex<float>((float)load_f_[f], 0.f); }
+          else if (!div_f_.empty()) v = std::complex<float>((float)(v.real() / div_f_[f]), (float)(v.imag() / div_f_[f]));
+        }
+    ck(btkb_set_noise_covariance(p, 1, reinterpret_cast<const float*>(R.data())));
+  }
   ck(btkb_calc_mvdr_weights(p, (float)mu_));
 }
 void SubbandMVDRGSC::set_active_weights_f(unsigned fbinX, const std::vector<double>& packed) {

@@ -79,6 +79,9 @@ class FeatureStream {
 };
 typedef FeatureStream<float> VectorFloatFeatureStream;
 typedef FeatureStream<cplx> VectorComplexFeatureStream;
+typedef FeatureStream<double> VectorFeatureStream;        // stream/stream.h:72-95: the remaining element types of the handle classes
+typedef FeatureStream<short> VectorShortFeatureStream;
+typedef FeatureStream<char> VectorCharFeatureStream;
 typedef std::shared_ptr<VectorFloatFeatureStream> VectorFloatFeatureStreamPtr;
 typedef std::shared_ptr<VectorComplexFeatureStream> VectorComplexFeatureStreamPtr;
 
@@ -279,6 +282,9 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
   int T_ = 0, nb_ = 0; bool realized_ = false, haveX_ = false;
   PostFilterConfig pf_used_; SynthesisConfig syn_used_;
   LmsConfig lms_; RlsConfig rls_;
+  bool normalize_weight_ = false;          // SubbandGSC::normalize_weight (beamformer.h:177)
+  // wq (or wmvdr) and wl = B wa of the configured weights, [K][C] each, realised on a one-block dummy batch
+  void fetch_static_weights_(std::vector<std::complex<float>>& W, std::vector<std::complex<float>>& WL);
   MultiChannelWPEDereverberationPtr wpe_;   // set by run_graph when the channels are MultiChannelWPEDereverberationFeature streams
   SnapShotArrayPtr snap_;
   std::vector<unsigned long> src_versions_;
@@ -290,10 +296,17 @@ class SubbandDS : public SubbandBeamformer {
  public:
   SubbandDS(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandDS", int kind = 0);
   virtual void calc_array_manifold_vectors(double samplerate, const std::vector<double>& delays);
+  // LCMV weights without a blocking matrix: one target + NC-1 jammers, delaysJ flat [NC-1][C] (beamformer.cc:1057-1074)
+  void calc_array_manifold_vectors_n(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ, unsigned NC = 2);
+  void calc_array_manifold_vectors_2(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ) {
+    calc_array_manifold_vectors_n(samplerate, delaysT, delaysJ, 2);
+  }
   void clear_channel() override;
  protected:
   void configure_weights_(btkb_pipeline* p) override;
+  void set_delays_(btkb_pipeline* p);   // btkb_set_delays or, with NC_ > 1, btkb_set_delays_lcmv
   std::vector<double> delays_; bool have_delays_ = false;
+  std::vector<double> delaysJ_; unsigned NC_ = 1;
 };
 typedef std::shared_ptr<SubbandDS> SubbandDSPtr;
 
@@ -306,11 +319,18 @@ class SubbandGSC : public SubbandDS {
   void calc_gsc_weights_2(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ) { calc_gsc_weights_n(samplerate, delaysT, delaysJ, 2); }
   void set_active_weights_f(unsigned fbinX, const std::vector<double>& packedWeight);
   void zero_active_weights();
+  void normalize_weight(bool flag) { normalize_weight_ = flag; invalidate_(); }                // beamformer.h:177
+  void calc_array_manifold_vectors(double samplerate, const std::vector<double>& delays) override { have_wq_explicit_ = false; SubbandDS::calc_array_manifold_vectors(samplerate, delays); }
+  // beamformer.cc:1318-1324.  The reference re-allocates the whole BeamformerWeights object on every call (alloc_bfweight_(1, 1)),
+  // so only the bin of the LAST call keeps a non-zero quiescent vector; reproduced.
+  void set_quiescent_weights_f(unsigned fbinX, const std::vector<cplx>& srcWq);
+  // beamformer.cc:775-828: conj(wq - wl) e^{j pi (f+1)} -> inverse DFT -> window -> text file ("C M" header, one row per channel)
+  bool write_fir_coeff(const std::string& fn, unsigned winType = 1);
  protected:
   void configure_weights_(btkb_pipeline* p) override;
   std::vector<std::complex<float>> wa_;  // [K][C-NC]
   bool have_wa_ = false;
-  std::vector<double> delaysJ_; unsigned NC_ = 1;
+  std::vector<std::complex<float>> wq_explicit_; bool have_wq_explicit_ = false;   // set_quiescent_weights_f
 };
 typedef std::shared_ptr<SubbandGSC> SubbandGSCPtr;
 
@@ -368,6 +388,9 @@ class SubbandMVDR : public SubbandDS {
   bool set_noise_spatial_spectral_matrix(unsigned fbinX, const std::vector<cplx>& Rnn);   // row-major C x C
   bool set_diffuse_noise_model(const std::vector<double>& micPositions /* [C][3] */, double samplerate, double sspeed = 343740.0);
   void set_all_diagonal_loading(double diagonalWeight);
+  void set_diagonal_looading(unsigned fbinX, float diagonalWeight);          // (sic) beamformer.cc:2525-2535: R[fbinX] += w I
+  void divide_nondiagonal_elements(unsigned fbinX, float mu);               // beamformer.cc:2589-2599: off-diagonals /= (1 + mu)
+  void divide_all_nondiagonal_elements(float mu);                           // beamformer.h:357-360, bins 0..M/2
   void clear_channel() override;
   // SMI statistics on the GPU (pybeamformer.py:948-1000): noise frames outside [start,end] with energy > threshold
   int accumulate_noise_covariance(double samplerate, double label_start, double label_end, double energy_threshold);
@@ -377,6 +400,9 @@ class SubbandMVDR : public SubbandDS {
   std::vector<std::complex<float>> wmvdr_;  // [K][C]
   bool have_R_ = false, have_w_ = false, diffuse_ = false, smi_ = false;
   std::vector<double> mpos_; double sspeed_ = 343740.0; double mu_ = 0.0;
+  // per-bin edits of R applied when the weights are configured (they commute: loading touches the diagonal only, the division
+  // the off-diagonals only): extra diagonal load and the accumulated off-diagonal divisor, [K] each, empty = none
+  std::vector<double> load_f_, div_f_;
 };
 typedef std::shared_ptr<SubbandMVDR> SubbandMVDRPtr;
 

@@ -14,37 +14,40 @@ using namespace btk20;
 
 namespace {
 
-// stream/pyStream.h:25-133 — a Python iterable exposing __iter__/next/size/reset as a C++ stream
-class PyVectorComplexFeatureStream : public VectorComplexFeatureStream {
+// stream/pyStream.h:25-133 — a Python iterable exposing __iter__/next/size/reset as a C++ stream (one adapter per element type:
+// PyVectorShortFeatureStream, PyVectorFloatFeatureStream, PyVectorFeatureStream, PyVectorComplexFeatureStream)
+template <class T>
+class PyFeatureStream : public FeatureStream<T> {
  public:
-  PyVectorComplexFeatureStream(py::object obj, const std::string& nm)
-      : VectorComplexFeatureStream(py::cast<unsigned>(obj.attr("size")()), nm), obj_(obj), iter_(py::none()) {}
-  const cplx* next(int frame_no = -5) override {
-    if (frame_no == frame_no_) return vector_.data();
+  PyFeatureStream(py::object obj, const std::string& nm)
+      : FeatureStream<T>(py::cast<unsigned>(obj.attr("size")()), nm), obj_(obj), iter_(py::none()) {}
+  const T* next(int frame_no = -5) override {
+    if (frame_no == this->frame_no_) return this->vector_.data();
     py::gil_scoped_acquire gil;
     if (iter_.is_none()) iter_ = obj_.attr("__iter__")();
     py::object item;
     try {
       item = py::hasattr(iter_, "__next__") ? iter_.attr("__next__")() : iter_.attr("next")();
     } catch (py::error_already_set& e) {
-      if (e.matches(PyExc_StopIteration)) { is_end_ = true; throw jiterator_error("end of samples!"); }
+      if (e.matches(PyExc_StopIteration)) { this->is_end_ = true; throw jiterator_error("end of samples!"); }
       throw;
     }
-    auto arr = py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast>::ensure(item);
-    if (!arr || (unsigned)arr.size() != size()) throw jdimension_error("PyFeatureStream: expected a complex vector of length %d", size());
-    std::memcpy(vector_.data(), arr.data(), sizeof(cplx) * size());
-    increment_();
-    return vector_.data();
+    auto arr = py::array_t<T, py::array::c_style | py::array::forcecast>::ensure(item);
+    if (!arr || (unsigned)arr.size() != this->size()) throw jdimension_error("PyFeatureStream: expected a vector of length %d", this->size());
+    std::memcpy(this->vector_.data(), arr.data(), sizeof(T) * this->size());
+    this->increment_();
+    return this->vector_.data();
   }
   void reset() override {
     py::gil_scoped_acquire gil;
     if (py::hasattr(obj_, "reset")) obj_.attr("reset")();
     iter_ = py::none();
-    VectorComplexFeatureStream::reset();
+    FeatureStream<T>::reset();
   }
  private:
   py::object obj_, iter_;
 };
+typedef PyFeatureStream<cplx> PyVectorComplexFeatureStream;
 
 template <class T, class S>
 py::array_t<T> view(S& self, const T* p, size_t n) {  // aliases internal storage, like PyArray_FromDimsAndData (include/vector.i:302)
@@ -55,6 +58,7 @@ template <class Cls, class PyCls>
 void add_complex_stream_api(PyCls& c) {
   c.def("next", [](Cls& s, int frame_no) { const cplx* p = s.next(frame_no); return view<cplx>(s, p, s.size()); }, py::arg("frame_no") = -5)
       .def("__next__", [](Cls& s) { const cplx* p = s.next(-5); return view<cplx>(s, p, s.size()); })
+      .def("current", [](Cls& s) { const cplx* p = s.current(); return view<cplx>(s, p, s.size()); })
       .def("__iter__", [](py::object self) { self.attr("reset")(); return self; })
       .def("reset", &Cls::reset)
       .def("size", &Cls::size)
@@ -66,12 +70,33 @@ template <class Cls, class PyCls>
 void add_float_stream_api(PyCls& c) {
   c.def("next", [](Cls& s, int frame_no) { const float* p = s.next(frame_no); return view<float>(s, p, s.size()); }, py::arg("frame_no") = -5)
       .def("__next__", [](Cls& s) { const float* p = s.next(-5); return view<float>(s, p, s.size()); })
+      .def("current", [](Cls& s) { const float* p = s.current(); return view<float>(s, p, s.size()); })
       .def("__iter__", [](py::object self) { self.attr("reset")(); return self; })
       .def("reset", &Cls::reset)
       .def("size", &Cls::size)
       .def("is_end", &Cls::is_end)
       .def("frame_no", &Cls::frame_no)
       .def("name", &Cls::name);
+}
+template <class T, class PyCls>
+void add_stream_api(PyCls& c) {
+  typedef FeatureStream<T> Cls;
+  c.def("next", [](Cls& s, int frame_no) { const T* p = s.next(frame_no); return view<T>(s, p, s.size()); }, py::arg("frame_no") = -5)
+      .def("__next__", [](Cls& s) { const T* p = s.next(-5); return view<T>(s, p, s.size()); })
+      .def("__iter__", [](py::object self) { self.attr("reset")(); return self; })
+      .def("current", [](Cls& s) { const T* p = s.current(); return view<T>(s, p, s.size()); })
+      .def("reset", &Cls::reset)
+      .def("size", &Cls::size)
+      .def("is_end", &Cls::is_end)
+      .def("frame_no", &Cls::frame_no)
+      .def("name", &Cls::name);
+}
+template <class T>
+void add_stream_classes(py::module_& m, const char* base_name, const char* py_name) {
+  py::class_<FeatureStream<T>, std::shared_ptr<FeatureStream<T>>> base(m, base_name);
+  add_stream_api<T>(base);
+  py::class_<PyFeatureStream<T>, FeatureStream<T>, std::shared_ptr<PyFeatureStream<T>>>(m, py_name)
+      .def(py::init<py::object, const std::string&>(), py::arg("obj"), py::arg("nm") = py_name);
 }
 std::vector<double> vec_d(py::array_t<double, py::array::c_style | py::array::forcecast> a) { return std::vector<double>(a.data(), a.data() + a.size()); }
 
@@ -104,6 +129,12 @@ PYBIND11_MODULE(_btk20host, m) {
 
   py::class_<PyVectorComplexFeatureStream, VectorComplexFeatureStream, std::shared_ptr<PyVectorComplexFeatureStream>>(m, "PyVectorComplexFeatureStreamPtr")
       .def(py::init<py::object, const std::string&>(), py::arg("obj"), py::arg("nm") = "PyVectorComplexFeatureStream");
+  py::class_<PyFeatureStream<float>, VectorFloatFeatureStream, std::shared_ptr<PyFeatureStream<float>>>(m, "PyVectorFloatFeatureStreamPtr")
+      .def(py::init<py::object, const std::string&>(), py::arg("obj"), py::arg("nm") = "PyVectorFloatFeatureStream");
+  // the remaining element types of stream/stream.i:24-237 (no hot-path class produces or consumes them; plumbing only)
+  add_stream_classes<double>(m, "VectorFeatureStreamPtr", "PyVectorFeatureStreamPtr");
+  add_stream_classes<short>(m, "VectorShortFeatureStreamPtr", "PyVectorShortFeatureStreamPtr");
+  add_stream_classes<char>(m, "VectorCharFeatureStreamPtr", "PyVectorCharFeatureStreamPtr");
 
   py::class_<SampleFeature, VectorFloatFeatureStream, SampleFeaturePtr>(m, "SampleFeaturePtr")
       .def(py::init<const std::string&, unsigned, unsigned, bool, const std::string&>(), py::arg("fn") = "", py::arg("block_len") = 320,
@@ -190,7 +221,11 @@ PYBIND11_MODULE(_btk20host, m) {
       .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandDS>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,
            py::arg("half_band_shift") = false, py::arg("nm") = "SubbandDS")
       .def("calc_array_manifold_vectors", [](SubbandDS& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { s.calc_array_manifold_vectors(fs, vec_d(d)); },
-           py::arg("samplerate"), py::arg("delays"));
+           py::arg("samplerate"), py::arg("delays"))
+      .def("calc_array_manifold_vectors_2", [](SubbandDS& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> dT, py::array_t<double, py::array::c_style | py::array::forcecast> dJ) { s.calc_array_manifold_vectors_2(fs, vec_d(dT), vec_d(dJ)); },
+           py::arg("samplerate"), py::arg("delays_t"), py::arg("delays_j"))
+      .def("calc_array_manifold_vectors_n", [](SubbandDS& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> dT, py::array_t<double, py::array::c_style | py::array::forcecast> dJ, unsigned NC) { s.calc_array_manifold_vectors_n(fs, vec_d(dT), vec_d(dJ), NC); },
+           py::arg("samplerate"), py::arg("delays_t"), py::arg("delays_j"), py::arg("NC") = 2);
 
   py::class_<SubbandGSC, SubbandDS, SubbandGSCPtr>(m, "SubbandGSCPtr")
       .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandGSC>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,
@@ -205,7 +240,11 @@ PYBIND11_MODULE(_btk20host, m) {
            py::arg("samplerate"), py::arg("delays_t"), py::arg("delays_j"))
       .def("set_active_weights_f", [](SubbandGSC& s, unsigned f, py::array_t<double, py::array::c_style | py::array::forcecast> w) { s.set_active_weights_f(f, vec_d(w)); },
            py::arg("fbinX"), py::arg("packedWeight"))
-      .def("zero_active_weights", &SubbandGSC::zero_active_weights);
+      .def("zero_active_weights", &SubbandGSC::zero_active_weights)
+      .def("normalize_weight", &SubbandGSC::normalize_weight, py::arg("flag"))
+      .def("set_quiescent_weights_f", [](SubbandGSC& s, unsigned f, py::array_t<cplx, py::array::c_style | py::array::forcecast> w) {
+             s.set_quiescent_weights_f(f, std::vector<cplx>(w.data(), w.data() + w.size())); }, py::arg("fbinX"), py::arg("srcWq"))
+      .def("write_fir_coeff", &SubbandGSC::write_fir_coeff, py::arg("fn"), py::arg("winType") = 1);
 
   py::class_<LmsConfig>(m, "LmsConfig")
       .def(py::init<>())
@@ -273,6 +312,9 @@ PYBIND11_MODULE(_btk20host, m) {
       .def("set_diffuse_noise_model", [](SubbandMVDR& s, py::array_t<double, py::array::c_style | py::array::forcecast> mpos, double fs, double c) {
         return s.set_diffuse_noise_model(vec_d(mpos), fs, c); }, py::arg("micPositions"), py::arg("samplerate"), py::arg("sspeed") = 343740.0)
       .def("set_all_diagonal_loading", &SubbandMVDR::set_all_diagonal_loading, py::arg("diagonalWeight"))
+      .def("set_diagonal_looading", &SubbandMVDR::set_diagonal_looading, py::arg("fbinX"), py::arg("diagonalWeight"))
+      .def("divide_all_nondiagonal_elements", &SubbandMVDR::divide_all_nondiagonal_elements, py::arg("mu"))
+      .def("divide_nondiagonal_elements", &SubbandMVDR::divide_nondiagonal_elements, py::arg("fbinX"), py::arg("mu"))
       .def("accumulate_noise_covariance", &SubbandMVDR::accumulate_noise_covariance, py::arg("samplerate"), py::arg("label_start"), py::arg("label_end"),
            py::arg("energy_threshold"));
 

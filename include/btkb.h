@@ -193,6 +193,9 @@ int btkb_fetch_snapshots(btkb_pipeline* p, float* out);
 int btkb_fetch_stats(btkb_pipeline* p, double* out);
 int btkb_get_weights(btkb_pipeline* p, float* out);            /* [U][K][C] complex64: wq or wmvdr */
 int btkb_get_active_weights(btkb_pipeline* p, float* out);     /* [U][K][C-1] complex64 (NLMS: waH of pybeamformer.py) */
+/* [U][K][C] complex64: wl = B wa of the static sidelobe canceller (BeamformerWeights::wl_f, beamformer.cc:729-767); zeros while no
+ * active weights are set.  The reference's write_fir_coeff (beamformer.cc:775-828) exports conj(wq - wl). */
+int btkb_get_sidelobe_weights(btkb_pipeline* p, float* out);
 int btkb_get_covariance(btkb_pipeline* p, float* out);         /* [U][K][C][C] complex64 */
 int btkb_get_postfilter_weights(btkb_pipeline* p, float* out); /* [U][T][K] float32 post-filter gains (wp1_) */
 
