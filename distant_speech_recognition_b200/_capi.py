@@ -154,6 +154,9 @@ class Pipeline:
         wa = np.ascontiguousarray(wa, np.complex64)
         _check(lib.btkb_set_active_weights(self._h, ct.c_int(wa.shape[0]), _fp(wa)))
 
+    def set_blocking_source(self, from_mvdr_weights):
+        _check(lib.btkb_set_blocking_source(self._h, ct.c_int(1 if from_mvdr_weights else 0)))
+
     def set_noise_covariance(self, R):
         R = np.ascontiguousarray(R, np.complex64)
         self.U = R.shape[0]

@@ -50,6 +50,7 @@ struct btkb_pipeline {
   bool have_pfR = false, pf_applied = false;  // pf_applied: d_Y came out of this pipeline's post-filter (not btkb_set_subband)
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
+  int bm_source = 0;  // BTKB_BF_MVDR: 0 = blocking matrix from the delay-and-sum manifold (calc_blocking_matrix1), 1 = from wmvdr (calc_blocking_matrix2)
   double* d_delaysJ = nullptr;
   std::vector<int> lengths;
   bool have_h = false, have_g = false, have_ta = false, have_w = false, have_wl = false, have_R = false, R_is_sum = false;
@@ -328,10 +329,19 @@ int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa) {
   to_device_layout(wa, tmp, U, p->K, p->C - p->NC, p->Gp);
   CK(cudaMemcpyAsync(p->d_WA, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
   // calc_blocking_matrix_(wq_[f], NC, B_[f]) (beamformer.cc:554-562, 693-700): B is built from the quiescent vector
-  const float2* bsrc = (p->cfg.beamformer == BTKB_BF_MVDR) ? p->d_TA : p->d_W;
+  const float2* bsrc = (p->cfg.beamformer == BTKB_BF_MVDR && p->bm_source == 0) ? p->d_TA : p->d_W;
+  if (bsrc == p->d_W && !p->have_w) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");  // calc_blocking_matrix2 returns false without wmvdr (beamformer.cc:2651-2653)
   CK(launch_blocking_wl(bsrc, p->d_WA, p->d_WL, U, p->C, p->K, p->Gp, p->NC, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   p->have_wl = true;
+  return BTKB_OK;
+}
+
+int btkb_set_blocking_source(btkb_pipeline* p, int from_mvdr_weights) {
+  if (!p) return fail(BTKB_ERR_INVALID, "btkb_set_blocking_source: null pipeline");
+  if (p->cfg.beamformer != BTKB_BF_MVDR) return fail(BTKB_ERR_INVALID, "btkb_set_blocking_source: only a BTKB_BF_MVDR pipeline has two candidate quiescent vectors");
+  p->bm_source = from_mvdr_weights ? 1 : 0;
+  p->have_wl = false;  // alloc_bfweight_(1, 1): the active weights set so far are gone (beamformer.cc:2640, 2655)
   return BTKB_OK;
 }
 

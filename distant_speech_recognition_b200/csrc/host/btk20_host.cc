@@ -760,6 +760,7 @@ void SubbandMVDRGSC::set_active_weights_f(unsigned fbinX, const std::vector<doub
 }
 void SubbandMVDRGSC::configure_weights_(btkb_pipeline* p) {
   SubbandMVDR::configure_weights_(p);
+  if (bm_from_mvdr_) ck(btkb_set_blocking_source(p, 1));
   if (have_wa_) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
 }
 

@@ -411,10 +411,19 @@ class SubbandMVDRGSC : public SubbandMVDR {
   SubbandMVDRGSC(unsigned fftLen = 512, bool half_band_shift = false, const std::string& nm = "SubbandMVDR") : SubbandMVDR(fftLen, half_band_shift, nm) {}
   void set_active_weights_f(unsigned fbinX, const std::vector<double>& packedWeight);
   void zero_active_weights() { wa_.clear(); have_wa_ = false; invalidate_(); }
-  bool calc_blocking_matrix1(double samplerate, const std::vector<double>& delaysT) { calc_array_manifold_vectors(samplerate, delaysT); return true; }
+  // B orthogonal to the delay-and-sum weights (beamformer.cc:2638-2643); like the reference's alloc_bfweight_ both variants drop
+  // the active weights set before
+  bool calc_blocking_matrix1(double samplerate, const std::vector<double>& delaysT) {
+    calc_array_manifold_vectors(samplerate, delaysT); bm_from_mvdr_ = false; wa_.clear(); have_wa_ = false; return true;
+  }
+  // B orthogonal to the MVDR weights (beamformer.cc:2649-2672); false when calc_mvdr_weights() has not been called
+  bool calc_blocking_matrix2() {
+    if (!have_w_) return false;
+    bm_from_mvdr_ = true; wa_.clear(); have_wa_ = false; invalidate_(); return true;
+  }
  protected:
   void configure_weights_(btkb_pipeline* p) override;
-  std::vector<std::complex<float>> wa_; bool have_wa_ = false;
+  std::vector<std::complex<float>> wa_; bool have_wa_ = false, bm_from_mvdr_ = false;
 };
 typedef std::shared_ptr<SubbandMVDRGSC> SubbandMVDRGSCPtr;
 

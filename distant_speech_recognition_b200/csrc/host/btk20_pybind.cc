@@ -325,7 +325,8 @@ PYBIND11_MODULE(_btk20host, m) {
            py::arg("fbinX"), py::arg("packedWeight"))
       .def("zero_active_weights", &SubbandMVDRGSC::zero_active_weights)
       .def("calc_blocking_matrix1", [](SubbandMVDRGSC& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { return s.calc_blocking_matrix1(fs, vec_d(d)); },
-           py::arg("samplerate"), py::arg("delaysT"));
+           py::arg("samplerate"), py::arg("delaysT"))
+      .def("calc_blocking_matrix2", &SubbandMVDRGSC::calc_blocking_matrix2);
 
   py::class_<ZelinskiPostFilter, VectorComplexFeatureStream, ZelinskiPostFilterPtr>(m, "ZelinskiPostFilterPtr")
       .def(py::init<const VectorComplexFeatureStreamPtr&, unsigned, double, int, int, const std::string&>(), py::arg("output"), py::arg("M"), py::arg("alpha") = 0.6,

@@ -75,7 +75,7 @@ typedef struct btkb_wpe_params { /* MultiChannelWPEDereverberation ctor (derever
 typedef struct btkb_config {
   int device;                  /* CUDA device ordinal */
   int channels;                /* C >= 1 (GSC kinds need C >= 2) */
-  int fft_len;                 /* M, power of two in [64, 4096] */
+  int fft_len;                 /* M, power of two in [256, 2048] */
   int m;                       /* prototype length factor (prototype length = m*M) */
   int r;                       /* decimation exponent, D = M >> r */
   int delay_compensation_type; /* 0, 1 or 2 (modulated.cc:246-264) */
@@ -119,6 +119,11 @@ int btkb_set_delays_lcmv(btkb_pipeline* p, int U, int NC, const double* delaysT,
 int btkb_set_weights(btkb_pipeline* p, int U, const float* w);
 /* active weights wa [U][K][C-1] complex64 -> wl = B wa with B = calc_blocking_matrix_(wq) (beamformer.cc:373-454, 729-767) */
 int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa);
+/* BTKB_BF_MVDR only: which vector the blocking matrix of the next btkb_set_active_weights is orthogonal to.
+ * 0 (default): the delay-and-sum manifold — SubbandMVDRGSC::calc_blocking_matrix1 (beamformer.cc:2638-2643);
+ * 1: the MVDR weights of the last btkb_calc_mvdr_weights — calc_blocking_matrix2 (beamformer.cc:2649-2672).
+ * Like the reference's alloc_bfweight_, the call discards active weights set before it. */
+int btkb_set_blocking_source(btkb_pipeline* p, int from_mvdr_weights);
 /* noise covariance R [U][K][C][C] complex64, row-major (set_noise_spatial_spectral_matrix, beamformer.cc:2410-2433) */
 int btkb_set_noise_covariance(btkb_pipeline* p, int U, const float* R);
 /* diffuse-noise coherence from microphone positions [C][3] (mm) (set_diffuse_noise_model, beamformer.cc:2442-2509) */

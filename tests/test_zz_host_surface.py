@@ -14,7 +14,7 @@ btk20 = pytest.importorskip("distant_speech_recognition_b200.btk20")
 from distant_speech_recognition_b200.btk20 import stream  # noqa: E402
 from distant_speech_recognition_b200.btk20.feature import SampleFeaturePtr  # noqa: E402
 from distant_speech_recognition_b200.btk20.modulated import OverSampledDFTAnalysisBankPtr, get_window  # noqa: E402
-from distant_speech_recognition_b200.btk20.beamformer import SubbandDSPtr, SubbandGSCPtr, SubbandMVDRPtr  # noqa: E402
+from distant_speech_recognition_b200.btk20.beamformer import SubbandDSPtr, SubbandGSCPtr, SubbandMVDRPtr, SubbandMVDRGSCPtr  # noqa: E402
 
 FS = 16000
 TOL = 1e-4
@@ -111,6 +111,11 @@ def test_argument_checks_of_the_added_methods(protos, tmp_path):
     mv.set_diagonal_looading(2, 0.1); mv.divide_nondiagonal_elements(2, 0.5); mv.divide_all_nondiagonal_elements(0.01)
     with pytest.raises(IndexError):
         mv.set_diagonal_looading(M // 2 + 1, 0.1)
+    mg = SubbandMVDRGSCPtr(fftlen=M)
+    for a in afbs:
+        mg.set_channel(a)
+    assert mg.calc_blocking_matrix2() is False                           # no MVDR weights yet (beamformer.cc:2651-2653)
+    assert mg.calc_blocking_matrix1(FS, d) is True
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU
@@ -289,3 +294,43 @@ def test_mvdr_per_bin_covariance_edits(protos):
     W = np.array([np.array(mv.mvdr_weights(k)) for k in range(K)])
     assert rel_l2(W[1:], want[1:]) < 1e-4
     assert rel_l2(W[7], want[7]) < 1e-4 and rel_l2(W[11], want[11]) < 1e-4
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_mvdrgsc_blocking_matrix_from_the_mvdr_weights(protos):
+    """SubbandMVDRGSC::calc_blocking_matrix2 (beamformer.cc:2649-2672): B orthogonal to w_mvdr instead of the delay-and-sum weights;
+    y[f >= 1] = (w_mvdr - B wa)^H x, the DC bin uses w_mvdr only (beamformer.cc:2750-2768)."""
+    from oracle import restate
+    g = load_golden("mvdrsd_zelinski1_c4_m256"); h, _ = protos[256]; M, D, C, K = 256, 128, 4, 129
+    afbs = _afbs(g["x"], h, M, D)
+    X = np.stack([restate.analysis(g["x"][c], h, M, 4, 1) for c in range(C)], axis=1)
+    rng = np.random.default_rng(7)
+    wa = 0.05 * (rng.standard_normal((K, C - 1)) + 1j * rng.standard_normal((K, C - 1)))
+    wq = restate.calc_mainlobe(M, C, FS, g["delays"])
+    R = restate.diffuse_noise_model(M, g["mpos"], FS)[:K].astype(complex)
+    R[:, np.eye(C, dtype=bool)] += float(np.float32(g["mu"]))
+    wm = np.zeros((M, C), complex); wm[:K] = restate.calc_mvdr_weights(R, wq[:K], single=False)
+    outs = {}
+    for variant in (1, 2):
+        bf = SubbandMVDRGSCPtr(fftlen=M)
+        for a in afbs:
+            bf.set_channel(a)
+        bf.calc_array_manifold_vectors(FS, g["delays"])
+        bf.set_diffuse_noise_model(g["mpos"], FS, 343740.0)
+        bf.set_all_diagonal_loading(float(g["mu"]))
+        bf.calc_mvdr_weights(FS, 1e-8, True)
+        if variant == 1:
+            assert bf.calc_blocking_matrix1(FS, g["delays"])
+            src = wq
+        else:
+            assert bf.calc_blocking_matrix2()
+            src = wm
+        for k in range(K):
+            bf.set_active_weights_f(k, np.stack([wa[k].real, wa[k].imag], axis=1).ravel())
+        wl = np.zeros((M, C), complex)
+        wl[:K] = restate.active_to_wl(np.stack([restate.calc_blocking_matrix(src[k]) for k in range(K)]), wa)
+        Y = np.array([np.array(v) for v in bf])
+        outs[variant] = Y
+        assert rel_l2(Y[:, :K], restate.subband_mvdr(X, wm, wl)[:, :K]) < TOL, variant
+    assert rel_l2(outs[1][:, 1:K], outs[2][:, 1:K]) > 1e-3          # the two blocking matrices really differ
