@@ -436,3 +436,47 @@ def test_sos_on_the_references_own_fixtures():
     w = w * np.sign(np.real(np.vdot(w[0], g["w_gev"][0])))
     assert rel_l2(w, g["w_gev"]) < 1e-9
     assert rel_l2(restate.sos_apply(X, w)[:, :K], g["Y_gev"]) < 1e-6
+
+
+def test_online_beamforming_on_the_references_own_fixtures():
+    """unit_test/test_online_beamforming.py with its default inputs (4-channel Kinect recording, shipped M = 256 prototypes) and its
+    own parameter files confs/{ds, ds_and_zelinski, sd, sd_and_zelinski, sd_and_mccowan, sd_and_lefkimmiatis, gsclms, gscrls}.json:
+    the restatement against the reference's outputs (golden_online_kinect_c4_m256, tests/golden/make_golden_online_kinect.py)."""
+    g = load_golden("online_kinect_c4_m256")
+    p = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz")); h, gg = p["h"], p["g"]
+    M, K, C = 256, 129, 4
+    d, mpos = g["delays"], g["mpos"]
+    assert np.allclose(d, restate.calc_delays("linear", mpos, [-1.306379, None, None]), rtol=0, atol=1e-18)   # confs/*.json look direction
+    s0, n = int(g["s0_static"]), int(g["n_static"])
+    X = _X(g["x16"][:, s0:s0 + n].astype(np.float32), h, M)
+    wq = restate.calc_mainlobe(M, C, FS, d)
+
+    def check(name, Y, tol_y, tol_t):
+        assert rel_l2(Y[:, :K], g["Y_" + name]) < tol_y, name
+        t = restate.synthesis(Y, gg, M, 4, 1)[: len(g["time_" + name])]
+        assert rel_l2(t, g["time_" + name]) < tol_t, name
+        assert abs(float(np.inner(t, t)) / float(g["energy_" + name]) - 1.0) < 10 * tol_t, name    # the script's report: total_energy
+
+    Yds = restate.subband_gsc(X, wq, np.zeros_like(wq))            # 'delay_and_sum' = SubbandGSCBeamformer with zero active weights
+    check("ds", Yds, 1e-6, 1e-6)                                   # (goldens are stored as complex64 / float32)
+    check("ds_and_zelinski", restate.zelinski_postfilter(Yds, X, wq, 0.7, 2, 0)[0], 1e-6, 1e-6)
+    R = restate.diffuse_noise_model(M, mpos, FS)
+    R[:, np.eye(C, dtype=bool)] += float(np.float32(0.01))
+    wsd = restate.calc_mvdr_weights(R, wq, single=True)            # the reference's float LINPACK SVD
+    assert rel_l2(wsd[1:], g["w_sd"][1:]) < 2e-5
+    for name in ("sd", "sd_and_zelinski", "sd_and_mccowan", "sd_and_lefkimmiatis"):
+        assert np.array_equal(g["w_" + name], g["w_sd"])           # every sd* file uses diagonal_load 0.01
+    Ysd = restate.subband_mvdr(X, g["w_sd"])                       # downstream stages on the reference's own weights
+    check("sd", Ysd, 1e-6, 1e-6)
+    check("sd", restate.subband_mvdr(X, wsd), 3e-5, 3e-5)          # ... and end to end on the restated weights
+    check("sd_and_zelinski", restate.zelinski_postfilter(Ysd, X, wq, 0.7, 2, 0)[0], 1e-6, 1e-6)
+    check("sd_and_mccowan", restate.mccowan_postfilter(Ysd, X, wq, _coherence(M, mpos, 0.01), 0.7, 2, 0, 0.99)[0], 1e-6, 1e-6)
+    check("sd_and_lefkimmiatis", restate.lefkimmiatis_postfilter(Ysd, X, wq, _coherence(M, mpos, 0.1), 0.8, 2, 0, 0.99, 1e-4, 100, single=False)[0], 2e-5, 2e-5)
+
+    Xf = _X(g["x16"].astype(np.float32), h, M)
+    Y, waH, nu = restate.gsc_lms(Xf, FS, d)                        # confs/gsclms.json = the class defaults
+    assert nu == int(g["n_updates_gsclms"]) and rel_l2(waH, g["waH_gsclms"]) < 1e-10
+    check("gsclms", Y, 1e-6, 1e-6)
+    Y, waH, nu = restate.gsc_rls(Xf, FS, d)                        # confs/gscrls.json = the class defaults
+    assert nu == int(g["n_updates_gscrls"]) and rel_l2(waH, g["waH_gscrls"]) < 1e-8
+    check("gscrls", Y, 1e-6, 1e-6)

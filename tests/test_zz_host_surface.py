@@ -334,3 +334,63 @@ def test_mvdrgsc_blocking_matrix_from_the_mvdr_weights(protos):
         outs[variant] = Y
         assert rel_l2(Y[:, :K], restate.subband_mvdr(X, wm, wl)[:, :K]) < TOL, variant
     assert rel_l2(outs[1][:, 1:K], outs[2][:, 1:K]) > 1e-3          # the two blocking matrices really differ
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_online_beamforming_on_the_references_own_fixtures(capi):
+    """unit_test/test_online_beamforming.py on its own inputs (Kinect recording as 16-bit PCM, shipped M = 256 prototypes) with its own
+    parameter files confs/{ds, ds_and_zelinski, sd, sd_and_zelinski, sd_and_mccowan, sd_and_lefkimmiatis, gsclms, gscrls}.json, through
+    the C-ABI, against the reference's outputs (golden_online_kinect_c4_m256; the oracle is pinned on the same file in
+    tests/test_oracle.py::test_online_beamforming_on_the_references_own_fixtures)."""
+    import os
+    from conftest import GOLDEN
+    g = load_golden("online_kinect_c4_m256")
+    pr = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz"))
+    M, C = 256, 4
+    d, mpos = g["delays"], g["mpos"]
+    s0, n = int(g["s0_static"]), int(g["n_static"])
+    xs = np.ascontiguousarray(g["x16"][:, s0:s0 + n])
+
+    def run(name, x16, setup=None, **kw):
+        p = capi.Pipeline(C, M, 4, 1, max_utterances=1, max_samples=x16.shape[1], **kw)
+        p.set_prototypes(pr["h"], pr["g"])
+        p.set_delays(d[None])
+        if setup:
+            setup(p)
+        p.submit_i16(x16[None])
+        p.run(True)
+        assert rel_l2(p.fetch_subband()[0], g["Y_" + name]) < TOL, name
+        t = p.fetch_time()[0]
+        assert rel_l2(t, g["time_" + name]) < TOL, name
+        assert abs(p.fetch_stats()[0, 0] / float(g["energy_" + name]) - 1.0) < 1e-3, name     # the script's report: total_energy
+        return p
+
+    def sd(p):
+        p.set_diffuse_noise_model(1, mpos)
+        p.calc_mvdr_weights(0.01)
+
+    def coherence(load):
+        def f(p):
+            sd(p)
+            p.pf_set_diffuse_noise_model(mpos, float(FS))
+            p.pf_set_diagonal_loading(load)
+        return f
+
+    run("ds", xs, beamformer=capi.BF_GSC).close()
+    run("ds_and_zelinski", xs, beamformer=capi.BF_GSC, postfilter=capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2).close()
+    p = run("sd", xs, sd, beamformer=capi.BF_MVDR)
+    assert rel_l2(p.get_weights()[0][1:], g["w_sd"][1:]) < TOL
+    p.close()
+    run("sd_and_zelinski", xs, sd, beamformer=capi.BF_MVDR, postfilter=capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2).close()
+    run("sd_and_mccowan", xs, coherence(0.01), beamformer=capi.BF_MVDR, postfilter=capi.PF_MCCOWAN, pf_alpha=0.7, pf_type=2).close()
+    run("sd_and_lefkimmiatis", xs, coherence(0.1), beamformer=capi.BF_MVDR, postfilter=capi.PF_LEFKIMMIATIS, pf_alpha=0.8, pf_type=2, pf_min_sv=1e-4,
+        pf_fbin1=100).close()
+    xf = np.ascontiguousarray(g["x16"])
+    p = run("gsclms", xf, beamformer=capi.BF_GSC_LMS)               # confs/gsclms.json = the defaults of btkb_default_config
+    assert int(p.fetch_stats()[0, 2]) == int(g["n_updates_gsclms"])
+    assert rel_l2(p.get_active_weights()[0], g["waH_gsclms"]) < 1e-3
+    p.close()
+    p = run("gscrls", xf, beamformer=capi.BF_GSC_RLS)               # confs/gscrls.json = the defaults
+    assert int(p.fetch_stats()[0, 2]) == int(g["n_updates_gscrls"])
+    p.close()
