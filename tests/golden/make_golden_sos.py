@@ -115,8 +115,50 @@ def kinect():
     save("sos_kinect_c4_m256", **out)
 
 
+def kinect_vad():
+    """unit_test/test_sos_batch_beamforming.py on its default inputs (the whole Kinect recording) with confs/{smimvdr, bmvdr_vad,
+    gev_vad}.json read where they lie: VAD label [[1.5, 4.0]], energy_threshold 10, SMI-MVDR with mu 1e-4 towards the look direction
+    of the file.  The samples are the x16 array of golden_online_kinect_c4_m256 (same wav files) and are not stored again; stored per
+    configuration: weights, frame counts, the resynthesised signal and frames 200..359 (speech) of the subband output."""
+    import json, pickle, wave
+    base = "/root/reference/btk20_src/unit_test/"
+    d = base + "data/CMU/R1/M1005/KINECT/RAW/segmented/"
+    M, K, D = 256, 129, 128
+    xs = []
+    for c in range(1, 5):
+        w = wave.open(d + "U1001_1M_16k_b16_c%d.wav" % c); xs.append(np.frombuffer(w.readframes(w.getnframes()), np.int16)); w.close()
+    x = np.stack(xs).astype(np.float32)
+    h = np.asarray(pickle.load(open(base + "prototype.ny/h-M256-m4-r1.pickle", "rb"), encoding="latin1"), np.float64)
+    g = np.asarray(pickle.load(open(base + "prototype.ny/g-M256-m4-r1.pickle", "rb"), encoding="latin1"), np.float64)
+    X = snapshots(x, h, M)
+    out = dict(frames=np.array([200, 360]))
+    for name in ("bmvdr_vad", "gev_vad"):
+        c = json.load(open(base + "confs/%s.json" % name)); bf = c["beamformer"]
+        labels = [tuple(l) for l in c["target"]["vad_label"]]
+        res = pyref.run_sos(bf["type"], X, FS, D, labels=labels, energy_threshold=bf.get("energy_threshold", 10), gamma=bf.get("gamma", 1e-6),
+                            ref_micx=bf.get("ref_micx", 0), offset=bf.get("offset", 0.0))
+        out["labels"] = np.asarray(labels, np.float64)
+        out["w_" + name] = np.conj(res["wqH"]); out["ct"] = res["ct"]; out["cn"] = res["cn"]
+        out["Y_" + name] = res["Y"][200:360, :K].astype(np.complex64)
+        out["time_" + name] = ref.synthesis(res["Y"], g, M, 4, 1).astype(np.float32)
+        print(name, res["Y"].shape, "counts", res["ct"][:3], res["cn"][:3])
+    c = json.load(open(base + "confs/smimvdr.json")); bf = c["beamformer"]
+    mod = pyref.load()
+    delays = np.asarray(mod.calc_delays(c["array_type"], c["microphone_positions"], c["target"]["positions"][0][1], sspeed=343740.0), np.float64)
+    lab = c["target"]["vad_label"]
+    assert len(lab) == 1
+    res = ref.beamform(x, h, g, delays, M, 4, 1, samplerate=FS, bf_kind=ref.BF_SMI_MVDR, mvdr_mu=bf.get("mu", 1e-4), smi_label=tuple(lab[0]),
+                       smi_energy_threshold=bf.get("energy_threshold", 10))
+    out["delays"] = delays; out["mu_smimvdr"] = bf.get("mu", 1e-4)
+    out["cov_smimvdr"] = res["cov"].astype(np.complex64); out["w_smimvdr"] = res["w"]
+    out["Y_smimvdr"] = res["Y"][200:360, :K].astype(np.complex64); out["time_smimvdr"] = res["time"].astype(np.float32)
+    print("smimvdr", res["Y"].shape, "cond(R) median %.1e max %.1e" % (np.median([np.linalg.cond(r) for r in res["cov"]]), max(np.linalg.cond(r) for r in res["cov"])))
+    save("sos_kinect_vad_c4_m256", **out)
+
+
 def main():
     kinect()
+    kinect_vad()
     one("bmvdr_vad_c8_m512", "bmvdr", 8, 512, 16000, 11, labels=[(0.3, 0.55), (0.7, -1)], ref_micx=2, offset=0.01)
     one("bmvdr_tfmask_c4_m256", "bmvdr", 4, 256, 8000, 12, mask="fractional", gamma=1e-4)
     one("gev_vad_c8_m512", "gev", 8, 512, 16000, 13, labels=[(0.3, 0.8)])

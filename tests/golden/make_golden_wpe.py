@@ -63,5 +63,40 @@ def main():
     save("wpe_single_m256", x=x, Xa=Xa[:, :K], Xb=Xb[:, :K], used_a=ua, used_b=ub, time_a=ta)
 
 
+def kinect():
+    """unit_test/test_subband_dereverberator.py on its default inputs (the whole 4-channel Kinect recording, shipped M = 256 prototypes)
+    with confs/wpe.json read where it lies, multi-channel and single-channel (channel 1) variants, estimate_filter() over the whole
+    utterance.  The samples are the x16 array of golden_online_kinect_c4_m256 and are not stored again; stored: the resynthesised
+    output of every channel and frames 240..299 of the dereverberated subband signals."""
+    import json, pickle, wave
+    base = "/root/reference/btk20_src/unit_test/"
+    d = base + "data/CMU/R1/M1005/KINECT/RAW/segmented/"
+    M, K = 256, 129
+    xs = []
+    for c in range(1, 5):
+        w = wave.open(d + "U1001_1M_16k_b16_c%d.wav" % c); xs.append(np.frombuffer(w.readframes(w.getnframes()), np.int16)); w.close()
+    x = np.stack(xs).astype(np.float32)
+    h = np.asarray(pickle.load(open(base + "prototype.ny/h-M256-m4-r1.pickle", "rb"), encoding="latin1"), np.float64)
+    g = np.asarray(pickle.load(open(base + "prototype.ny/g-M256-m4-r1.pickle", "rb"), encoding="latin1"), np.float64)
+    conf = json.load(open(base + "confs/wpe.json"))
+    X = np.stack([ref.analysis(x[c], h, M, 4, 1) for c in range(4)], axis=1)
+    # multi_channel_wpe (:114-170): defaults of the script where the file is silent
+    km = dict(lower_num=conf.get("lower_num", 0), upper_num=conf.get("upper_num", 32), iterations_num=conf.get("iterations_num", 2),
+              load_db=conf.get("load_db", -20.0), band_width=conf.get("band_width", 0.0), diagonal_bias=conf.get("diagonal_bias", 0.001), samplerate=16000.0)
+    Xm, um = ref.wpe(X, **km)
+    tm = np.stack([ref.synthesis(Xm[:, c, :], g, M, 4, 1) for c in range(4)])
+    # single_channel_wpe (:53-92) on the first file
+    ks = dict(lower_num=conf.get("lower_num", 0), upper_num=conf.get("upper_num", 64), iterations_num=conf.get("iterations_num", 2),
+              load_db=conf.get("load_db", -20.0), band_width=conf.get("band_width", 0.0), samplerate=16000.0)
+    Xs, us = ref.wpe_single(X[:, 0, :], **ks)
+    ts = ref.synthesis(Xs, g, M, 4, 1)
+    red = 1.0 - np.linalg.norm(Xm) ** 2 / np.linalg.norm(X) ** 2
+    print("kinect WPE: %d / %d frames used, energy removed %.1f %%" % (um, us, 100 * red))
+    save("wpe_kinect_c4_m256", frames=np.array([240, 300]), used_multi=um, used_single=us, conf=json.dumps(conf),
+         X_multi=Xm[240:300, :, :K].astype(np.complex64), time_multi=tm.astype(np.float32),
+         X_single=Xs[240:300, :K].astype(np.complex64), time_single=ts.astype(np.float32))
+
+
 if __name__ == "__main__":
     main()
+    kinect()

@@ -480,3 +480,60 @@ def test_online_beamforming_on_the_references_own_fixtures():
     Y, waH, nu = restate.gsc_rls(Xf, FS, d)                        # confs/gscrls.json = the class defaults
     assert nu == int(g["n_updates_gscrls"]) and rel_l2(waH, g["waH_gscrls"]) < 1e-8
     check("gscrls", Y, 1e-6, 1e-6)
+
+
+def test_sos_batch_beamforming_vad_on_the_references_own_fixtures():
+    """unit_test/test_sos_batch_beamforming.py on its default inputs (the whole Kinect recording, shipped prototypes) with
+    confs/{bmvdr_vad, gev_vad, smimvdr}.json (VAD label [[1.5, 4.0]]): restatement vs the reference's outputs
+    (golden_sos_kinect_vad_c4_m256, tests/golden/make_golden_sos.py kinect_vad())."""
+    g = load_golden("sos_kinect_vad_c4_m256"); x16 = load_golden("online_kinect_c4_m256")["x16"]
+    p = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz")); h, gg = p["h"], p["g"]
+    M, K, C = 256, 129, 4
+    f0, f1 = [int(v) for v in g["frames"]]
+    X = _X(x16.astype(np.float32), h, M)
+    labels = [tuple(l) for l in g["labels"]]
+    Rt, Rn, ct, cn = restate.sos_accumulate(X, FS, M // 2, target_labs=labels, energy_threshold=10.0)
+    assert np.array_equal(ct, g["ct"]) and np.array_equal(cn, g["cn"]) and ct[0] == 312 and cn[0] == 298
+    w = restate.sos_bmvdr_weights(Rt, Rn, ct, cn, gamma=1e-6, ref_micx=0, offset=0.0)
+    assert rel_l2(w, g["w_bmvdr_vad"]) < 1e-9
+    Y = restate.sos_apply(X, w)
+    assert rel_l2(Y[f0:f1, :K], g["Y_bmvdr_vad"]) < 1e-6 and rel_l2(restate.synthesis(Y, gg, M, 4, 1), g["time_bmvdr_vad"]) < 1e-6
+    w = restate.sos_gev_weights(Rt, Rn, cn, gamma=1e-6)
+    w = w * np.sign(np.real(np.vdot(w[0], g["w_gev_vad"][0])))          # scipy's eigh leaves one global sign to LAPACK
+    assert rel_l2(w, g["w_gev_vad"]) < 1e-8
+    Y = restate.sos_apply(X, w)
+    assert rel_l2(Y[f0:f1, :K], g["Y_gev_vad"]) < 1e-6 and rel_l2(restate.synthesis(Y, gg, M, 4, 1), g["time_gev_vad"]) < 1e-6
+    # SMI-MVDR (confs/smimvdr.json): noise covariance outside the label, mu = 1e-4, look direction of the file
+    R, nf = restate.smi_covariance(X, FS, M // 2, tuple(labels), 10.0)
+    assert nf == 298 and rel_l2(R, g["cov_smimvdr"]) < 1e-6
+    wq = restate.calc_mainlobe(M, C, FS, g["delays"])
+    ws = restate.calc_mvdr_weights(R + float(np.float32(g["mu_smimvdr"])) * np.eye(C), wq, single=True)
+    assert rel_l2(ws[1:], g["w_smimvdr"][1:]) < 1e-4                    # the reference's float LINPACK SVD
+    Y = restate.subband_mvdr(X, g["w_smimvdr"])
+    assert rel_l2(Y[f0:f1, :K], g["Y_smimvdr"]) < 1e-6 and rel_l2(restate.synthesis(Y, gg, M, 4, 1), g["time_smimvdr"]) < 1e-6
+    Y = restate.subband_mvdr(X, restate.calc_mvdr_weights(R + float(np.float32(g["mu_smimvdr"])) * np.eye(C), wq, single=False))
+    assert rel_l2(restate.synthesis(Y, gg, M, 4, 1), g["time_smimvdr"]) < 1e-4   # fp64 solve vs the reference's float SVD: inside the parity budget
+
+
+def test_wpe_on_the_references_own_fixtures():
+    """unit_test/test_subband_dereverberator.py on its default inputs (the whole Kinect recording, shipped prototypes) with
+    confs/wpe.json (lags 0..32, 2 iterations, -18 dB, bias 1e-4): multi-channel and single-channel restatement vs the compiled
+    reference's outputs (golden_wpe_kinect_c4_m256, tests/golden/make_golden_wpe.py kinect())."""
+    import json
+    g = load_golden("wpe_kinect_c4_m256"); x16 = load_golden("online_kinect_c4_m256")["x16"]
+    p = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz")); h, gg = p["h"], p["g"]
+    M, K = 256, 129
+    conf = json.loads(str(g["conf"]))
+    assert conf == dict(lower_num=0, upper_num=32, iterations_num=2, load_db=-18.0, band_width=0.0, diagonal_bias=0.0001)
+    f0, f1 = [int(v) for v in g["frames"]]
+    X = _X(x16.astype(np.float32), h, M)
+    Xm, _, used = restate.wpe(X, samplerate=FS, **conf)
+    assert used == int(g["used_multi"]) == 614
+    assert rel_l2(Xm[f0:f1, :, :K], g["X_multi"]) < 1e-6                  # golden stored as complex64
+    for c in range(4):
+        assert rel_l2(restate.synthesis(Xm[:, c, :], gg, M, 4, 1), g["time_multi"][c]) < 1e-6, c
+    assert rel_l2(Xm[f0:f1, :, :K], X[f0:f1, :, :K]) > 0.05              # the filters really remove something
+    ks = dict(conf); ks["diagonal_bias"] = 0.0                           # the single-channel class has no diagonal bias
+    Xs, _, used = restate.wpe(X[:, :1, :], samplerate=FS, **ks)
+    assert used == int(g["used_single"]) and rel_l2(Xs[f0:f1, 0, :K], g["X_single"]) < 1e-6
+    assert rel_l2(restate.synthesis(Xs[:, 0, :], gg, M, 4, 1), g["time_single"]) < 1e-6

@@ -394,3 +394,84 @@ def test_online_beamforming_on_the_references_own_fixtures(capi):
     p = run("gscrls", xf, beamformer=capi.BF_GSC_RLS)               # confs/gscrls.json = the defaults
     assert int(p.fetch_stats()[0, 2]) == int(g["n_updates_gscrls"])
     p.close()
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_sos_batch_beamforming_vad_on_the_references_own_fixtures(capi):
+    """unit_test/test_sos_batch_beamforming.py on the whole Kinect recording with confs/{bmvdr_vad, gev_vad, smimvdr}.json (VAD label
+    [[1.5, 4.0]]) through the C-ABI, against the reference's outputs (golden_sos_kinect_vad_c4_m256)."""
+    import os
+    from conftest import GOLDEN
+    g = load_golden("sos_kinect_vad_c4_m256"); x16 = np.ascontiguousarray(load_golden("online_kinect_c4_m256")["x16"])
+    pr = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz"))
+    M, C = 256, 4
+    f0, f1 = [int(v) for v in g["frames"]]
+    for name, kind in (("bmvdr_vad", capi.SOS_BMVDR), ("gev_vad", capi.SOS_GEV)):
+        p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_DS, max_utterances=1, max_samples=x16.shape[1])
+        p.set_prototypes(pr["h"], pr["g"])
+        p.submit_i16(x16[None])
+        p.run_analysis()
+        p.sos_accumulate_from_label(g["labels"], 10.0)
+        _, _, cnt = p.sos_get_stats()
+        assert np.array_equal(cnt[0, :, 0], g["ct"]) and np.array_equal(cnt[0, :, 1], g["cn"])
+        p.sos_calc_weights(kind, gamma=1e-6, ref_micx=0, offset=0.0)
+        w = p.get_weights()[0]
+        sgn = 1.0 if kind == capi.SOS_BMVDR else float(np.sign(np.real(np.vdot(w[0], g["w_" + name][0]))))
+        assert rel_l2(sgn * w, g["w_" + name]) < 5e-4, name
+        if sgn < 0:
+            p.set_weights((sgn * w)[None])
+        p.run_beamformer(True)
+        assert rel_l2(p.fetch_subband()[0][f0:f1], g["Y_" + name]) < TOL, name
+        assert rel_l2(p.fetch_time()[0], g["time_" + name]) < TOL, name
+        p.close()
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=1, max_samples=x16.shape[1])
+    p.set_prototypes(pr["h"], pr["g"])
+    p.set_delays(g["delays"][None])
+    p.submit_i16(x16[None])
+    p.run_analysis()
+    p.accumulate_covariance(labels=g["labels"][:1], energy_threshold=10.0)
+    assert rel_l2(p.get_covariance()[0], g["cov_smimvdr"]) < 1e-5
+    p.calc_mvdr_weights(float(g["mu_smimvdr"]))
+    assert rel_l2(p.get_weights()[0][1:], g["w_smimvdr"][1:]) < 2e-4      # fp64 LU here, float LINPACK SVD there
+    p.run_beamformer(True)
+    assert rel_l2(p.fetch_subband()[0][f0:f1], g["Y_smimvdr"]) < TOL
+    assert rel_l2(p.fetch_time()[0], g["time_smimvdr"]) < TOL
+    p.close()
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_wpe_on_the_references_own_fixtures(capi):
+    """unit_test/test_subband_dereverberator.py on the whole Kinect recording with confs/wpe.json (lags 0..32: 132 x 132 normal
+    equations per bin and channel) through the C-ABI, multi- and single-channel, against the compiled reference's outputs
+    (golden_wpe_kinect_c4_m256)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    g = load_golden("wpe_kinect_c4_m256"); x16 = np.ascontiguousarray(load_golden("online_kinect_c4_m256")["x16"])
+    pr = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz"))
+    M = 256
+    conf = json.loads(str(g["conf"]))
+    f0, f1 = [int(v) for v in g["frames"]]
+    p = capi.Pipeline(4, M, 4, 1, beamformer=capi.BF_DS, max_utterances=1, max_samples=x16.shape[1], wpe=conf)
+    p.set_prototypes(pr["h"], pr["g"])
+    p.submit_i16(x16[None]); p.run_analysis(); p.run_wpe()
+    Xd = p.fetch_snapshots()
+    assert rel_l2(Xd[0][f0:f1], g["X_multi"]) < TOL
+    q = capi.Pipeline(1, M, 4, 1, beamformer=capi.BF_DS, max_utterances=4, max_samples=x16.shape[1])   # every channel's stream into a synthesis bank
+    q.set_prototypes(pr["h"], pr["g"])
+    q.set_subband(np.ascontiguousarray(np.transpose(Xd[0], (1, 0, 2)))); q.run_synthesis()
+    assert rel_l2(q.fetch_time(), g["time_multi"]) < TOL
+    q.close(); p.close()
+    ks = dict(conf); ks["diagonal_bias"] = 0.0
+    p = capi.Pipeline(1, M, 4, 1, beamformer=capi.BF_DS, max_utterances=1, max_samples=x16.shape[1], wpe=ks)
+    p.set_prototypes(pr["h"], pr["g"])
+    p.submit_i16(x16[None, :1]); p.run_analysis(); p.run_wpe()
+    Xs = p.fetch_snapshots()
+    assert rel_l2(Xs[0][f0:f1, 0], g["X_single"]) < TOL
+    q = capi.Pipeline(1, M, 4, 1, beamformer=capi.BF_DS, max_utterances=1, max_samples=x16.shape[1])
+    q.set_prototypes(pr["h"], pr["g"])
+    q.set_subband(Xs[:, :, 0, :]); q.run_synthesis()
+    assert rel_l2(q.fetch_time()[0], g["time_single"]) < TOL
+    q.close(); p.close()
