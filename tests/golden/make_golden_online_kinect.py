@@ -4,7 +4,7 @@ unit_test/test_online_beamforming.py with its default inputs — the 4-channel K
 unit_test/data/CMU/R1/M1005/KINECT/RAW/segmented/U1001_1M_16k_b16_c{1..4}.wav, the shipped prototypes
 unit_test/prototype.ny/{h,g}-M256-m4-r1.pickle (M = 256, m = 4, r = 1, delay-compensation type 2) — and the parameter files
 unit_test/confs/{ds, ds_and_zelinski, sd, sd_and_zelinski, sd_and_mccowan, sd_and_lefkimmiatis, gsclms, gscrls}.json, read where
-they lie (microphone positions, look direction, every hyper-parameter).
+they lie (microphone positions, look direction, every hyper-parameter); of confs/lcmv_and_zelinski.json the LCMV weights.
 
 Who computes what (same split as the other goldens): the filter banks, D&S / super-directive weights and the three post-filters
 are the reference's C++ compiled unmodified (oracle/_ref via oracle/ref.py, wired like test_online_beamforming.py:51-228); the two
@@ -98,6 +98,16 @@ def main():
         out["time_" + name] = t.astype(np.float32)
         out["energy_" + name] = float(np.inner(t.astype(np.float64), t.astype(np.float64)))
         print(name, Y.shape, t.shape, "total_energy/frames = %.3f" % (out["energy_" + name] / (len(t) // D)))
+    # confs/lcmv_and_zelinski.json: SubbandGSCBeamformer(afbs, Nc=2).calc_beamformer_weights_n -> C++ calcMainlobeN (beamformer.cc:573-721).
+    # The harness wires the LCMV weights only (ref_lcmv_weights), so the quiescent vectors and blocking matrices are the reference's and
+    # the tests run the (elsewhere pinned) static-GSC + Zelinski chain on them.
+    c = conf("lcmv_and_zelinski")
+    assert np.array_equal(np.asarray(c["microphone_positions"], np.float64), out["mpos"])
+    dT = np.asarray(mod.calc_delays(c["array_type"], c["microphone_positions"], c["target"]["positions"][0][1], sspeed=SSPEED), np.float64)
+    dJ = np.stack([np.asarray(mod.calc_delays(c["array_type"], c["microphone_positions"], nz["positions"][0][1], sspeed=SSPEED), np.float64) for nz in c["noises"]])
+    wl, Bl = ref.lcmv_weights(M, 4, 1 + len(dJ), float(FS), dT, dJ)
+    out.update(lcmv_dT=dT, lcmv_dJ=dJ, lcmv_w=wl, lcmv_B=Bl)
+    print("lcmv: target %s rad, jammer %s rad" % (c["target"]["positions"][0][1][0], c["noises"][0]["positions"][0][1][0]))
     save("online_kinect_c4_m256", **out)
 
 

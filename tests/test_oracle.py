@@ -480,6 +480,15 @@ def test_online_beamforming_on_the_references_own_fixtures():
     Y, waH, nu = restate.gsc_rls(Xf, FS, d)                        # confs/gscrls.json = the class defaults
     assert nu == int(g["n_updates_gscrls"]) and rel_l2(waH, g["waH_gscrls"]) < 1e-8
     check("gscrls", Y, 1e-6, 1e-6)
+    # confs/lcmv_and_zelinski.json: target at 0 rad, a null on -1.306379 rad (the reference's calcMainlobeN weights; bin M/2 is the
+    # reference's own cascade quirk, restated only on the device side and checked there)
+    assert np.allclose(g["lcmv_dT"], restate.calc_delays("linear", mpos, [0.0, None, None]), rtol=0, atol=1e-18)
+    assert np.allclose(g["lcmv_dJ"][0], d, rtol=0, atol=1e-18)
+    wl = restate.calc_mainlobe_n(M, C, FS, g["lcmv_dT"], g["lcmv_dJ"])
+    assert rel_l2(wl[:M // 2], g["lcmv_w"][:M // 2]) < 1e-12
+    k = np.arange(1, M // 2)
+    vj = np.exp(-2j * np.pi * k[:, None] * FS * g["lcmv_dJ"][0][None, :] / M)
+    assert np.abs(np.einsum("kc,kc->k", np.conj(g["lcmv_w"][1:M // 2]), vj)).max() < 1e-9    # the null really sits on the jammer
 
 
 def test_sos_batch_beamforming_vad_on_the_references_own_fixtures():

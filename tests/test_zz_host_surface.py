@@ -394,6 +394,20 @@ def test_online_beamforming_on_the_references_own_fixtures(capi):
     p = run("gscrls", xf, beamformer=capi.BF_GSC_RLS)               # confs/gscrls.json = the defaults
     assert int(p.fetch_stats()[0, 2]) == int(g["n_updates_gscrls"])
     p.close()
+    # confs/lcmv_and_zelinski.json: LCMV quiescent weights vs the reference's calcMainlobeN (every bin, incl. its f = M/2 cascade), then
+    # static GSC + Zelinski on the excerpt vs the restatement run on the reference's weights
+    from oracle import restate
+    p = capi.Pipeline(C, M, 4, 1, max_utterances=1, max_samples=xs.shape[1], beamformer=capi.BF_GSC, postfilter=capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2)
+    p.set_prototypes(pr["h"], pr["g"])
+    p.set_delays_lcmv(g["lcmv_dT"][None], g["lcmv_dJ"][None])
+    assert rel_l2(p.get_weights()[0], g["lcmv_w"]) < 1e-5
+    p.submit_i16(xs[None]); p.run(True)
+    X = np.stack([restate.analysis(xs[c].astype(np.float32), pr["h"], M, 4, 1) for c in range(C)], axis=1)
+    wfull = np.concatenate([g["lcmv_w"], np.conj(g["lcmv_w"][1:M // 2][::-1])])
+    Yo = restate.zelinski_postfilter(restate.subband_gsc(X, wfull, np.zeros_like(wfull)), X, restate.calc_mainlobe(M, C, float(FS), g["lcmv_dT"]), 0.7, 2, 0)[0]
+    assert rel_l2(p.fetch_subband()[0], Yo[:, :M // 2 + 1]) < TOL
+    assert rel_l2(p.fetch_time()[0], restate.synthesis(Yo, pr["g"], M, 4, 1)) < TOL
+    p.close()
 
 
 @pytest.mark.gpu
