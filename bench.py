@@ -124,8 +124,10 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     upc = max(1, CFG["U"] // cores)  # utterances per core per step: one whole configs[1] batch per step (~15 s of CPU work on 16 cores)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference(1, cores)
+    v0, _, _, _ = cpu_reference(1, cores)  # untimed warm-up pass (page-in of the reference library, fork pool), also sizes the sample:
+    T0 = frames_per_utt(CFG["n"], CFG["M"], CFG["m"], CFG["r"])
+    while upc > 1 and args.steps * (upc * cores * T0 / v0) > 150.0:  # keep the K timed steps within ~2.5 minutes of processing
+        upc //= 2
     vals, fr, secs = [], 0, 0.0
     for k in range(args.steps):
         v, f, s, _ = cpu_reference(upc, cores, seed0=k * upc * cores)
