@@ -5,6 +5,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -rxX 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt
 timeout 600 python -m pytest tests/test_zz_host_surface.py -m gpu -q --runxfail 2>&1 | tail -60 > gpurun_out/zz.txt; tail -15 gpurun_out/zz.txt
+timeout 600 python tools/parity_report_kinect.py > gpurun_out/parity_kinect.json 2> gpurun_out/parity_kinect.err; tail -2 gpurun_out/parity_kinect.err; cat gpurun_out/parity_kinect.json
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 timeout 600 python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
