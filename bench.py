@@ -158,6 +158,26 @@ def workload_config(n_gpus):
 
 
 # ----------------------------------------------------------------------------- our arm
+def bind_to_gpu_numa_node(props):
+    """N > 1 only: run this rank (and the pinned buffers it first-touches) on the CPUs NVML names as local to its GPU, so that the
+    ranks' host<->device copies do not all cross the same socket interconnect (at N = 2 the unbound e2e scaled 1.5x while the device
+    part scaled 1.99x, profiles/r01f_bench_n2.json).  Best effort: any failure leaves the affinity untouched.  Returns a description
+    for the JSON line, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        if not after:
+            raise RuntimeError("empty affinity")
+        return {"gpu": bus, "cpus": "%d-%d (%d of %d)" % (after[0], after[-1], len(after), before)}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def make_inputs(rank):
     from distant_speech_recognition_b200 import synthetic
     import multiprocessing as mp
@@ -186,9 +206,11 @@ def run_ours(args):
     if not torch.cuda.is_available() or _capi.device_count() < 1:
         raise RuntimeError("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local))
     c = CFG
     U, C, n, M, m, r = c["U"], c["C"], c["n"], c["M"], c["m"], c["r"]
     T = frames_per_utt(n, M, m, r)
@@ -315,7 +337,7 @@ def run_ours(args):
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "xrt": value * (n / FS) / T, "config": workload_config(world),
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(U * C * n * 2 + delays.nbytes), "d2h_bytes_per_step": int(out_pin.numel() * 4 + stats.nbytes),
-                "ms_per_step": 1000.0 * e2e_s / args.steps, "input": "int16 PCM, pinned", "sub_batches": NP, "pipelining": "results of sub-batch i are fetched just before its handle is re-submitted (uploads of the other sub-batches stay queued); all results on the host before the clock stops"},
+                "ms_per_step": 1000.0 * e2e_s / args.steps, "input": "int16 PCM, pinned", "sub_batches": NP, "cpu_binding": numa, "pipelining": "results of sub-batch i are fetched just before its handle is re-submitted (uploads of the other sub-batches stay queued); all results on the host before the clock stops"},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {k: v / args.steps for k, v in ks.items()},
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
