@@ -489,3 +489,59 @@ def test_wpe_on_the_references_own_fixtures(capi):
     q.set_subband(Xs[:, :, 0, :]); q.run_synthesis()
     assert rel_l2(q.fetch_time()[0], g["time_single"]) < TOL
     q.close(); p.close()
+
+
+# ------------------------------------------------------------------------------------------- a C++ user of the host mirror
+def _cpp_frontend(tmp_path):
+    """tests/host/cpp_frontend.cc: SampleFeature -> analysis banks -> SubbandGSCLMS -> synthesis bank driven from C++ exactly like the
+    reference's C++ programs (src/filterBankTest.cc:189-196), linked against the host mirror sources and libbtkb.so."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "distant_speech_recognition_b200")
+    exe = str(tmp_path / "cpp_frontend")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "host", "cpp_frontend.cc"), os.path.join(pkg, "csrc", "host", "btk20_host.cc"),
+                           "-o", exe, "-L" + pkg, "-lbtkb", "-Wl,-rpath," + pkg])
+    return exe
+
+
+def _cpp_inputs(tmp_path, h, g, M, x, delays):
+    pf, sf = str(tmp_path / "proto.txt"), str(tmp_path / "samples.txt")
+    with open(pf, "w") as f:
+        f.write("%d 4 1\n" % M); f.write(" ".join("%.17g" % v for v in h) + "\n"); f.write(" ".join("%.17g" % v for v in g) + "\n")
+    with open(sf, "w") as f:
+        f.write("%d %d\n" % x.shape)
+        for c in range(x.shape[0]):
+            f.write(" ".join("%d" % v for v in x[c]) + "\n")
+    return [pf, sf] + ["%.17g" % d for d in delays]
+
+
+def test_cpp_user_of_the_host_mirror_builds_and_fails_loudly_without_a_gpu(tmp_path, protos):
+    import subprocess
+    from distant_speech_recognition_b200 import _capi
+    exe = _cpp_frontend(tmp_path)
+    if _capi.device_count() > 0:
+        pytest.skip("a GPU is present: the run itself is covered by the gpu-marked test")
+    h, g = protos[256]
+    args = _cpp_inputs(tmp_path, h, g, 256, np.zeros((2, 1000), np.int16), [0.0, 1e-4])
+    r = subprocess.run([exe] + args, capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("j_error:") and "no CUDA device" in r.stdout   # no CPU path: the library refuses
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cpp_user_of_the_host_mirror_on_the_references_own_fixtures(tmp_path):
+    """The C++ program on the Kinect recording with confs/gsclms.json defaults: block count, NLMS update count and the script's
+    total_energy report equal the reference's (golden_online_kinect_c4_m256)."""
+    import os
+    import subprocess
+    from conftest import GOLDEN
+    g = load_golden("online_kinect_c4_m256")
+    pr = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz"))
+    exe = _cpp_frontend(tmp_path)
+    r = subprocess.run([exe] + _cpp_inputs(tmp_path, pr["h"], pr["g"], 256, g["x16"], g["delays"]), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tok = r.stdout.split()
+    frames, blocks, energy, updates = int(tok[1]), int(tok[3]), float(tok[5]), int(tok[7])
+    assert frames == g["Y_gsclms"].shape[0] and blocks * 128 == len(g["time_gsclms"]) and updates == int(g["n_updates_gsclms"])
+    assert abs(energy / float(g["energy_gsclms"]) - 1.0) < 1e-3
