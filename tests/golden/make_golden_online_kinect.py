@@ -70,6 +70,7 @@ def main():
             delays = d; out["delays"] = d; out["mpos"] = mpos
         assert np.array_equal(d, delays) and np.array_equal(mpos, out["mpos"])      # every file describes the same array and look direction
         bf, pf = c["beamformer"], c.get("postfilter")
+        out["conf_" + name] = json.dumps(c)      # the parameter file itself, so that tests can configure the front end from it
         if bf["type"] in ("delay_and_sum", "super_directive"):
             pfd = None
             if pf is not None:   # test_online_beamforming.py:132-156
@@ -106,7 +107,7 @@ def main():
     dT = np.asarray(mod.calc_delays(c["array_type"], c["microphone_positions"], c["target"]["positions"][0][1], sspeed=SSPEED), np.float64)
     dJ = np.stack([np.asarray(mod.calc_delays(c["array_type"], c["microphone_positions"], nz["positions"][0][1], sspeed=SSPEED), np.float64) for nz in c["noises"]])
     wl, Bl = ref.lcmv_weights(M, 4, 1 + len(dJ), float(FS), dT, dJ)
-    out.update(lcmv_dT=dT, lcmv_dJ=dJ, lcmv_w=wl, lcmv_B=Bl)
+    out.update(lcmv_dT=dT, lcmv_dJ=dJ, lcmv_w=wl, lcmv_B=Bl, conf_lcmv_and_zelinski=json.dumps(c))
     print("lcmv: target %s rad, jammer %s rad" % (c["target"]["positions"][0][1][0], c["noises"][0]["positions"][0][1][0]))
     save("online_kinect_c4_m256", **out)
 

@@ -545,3 +545,35 @@ def test_cpp_user_of_the_host_mirror_on_the_references_own_fixtures(tmp_path):
     frames, blocks, energy, updates = int(tok[1]), int(tok[3]), float(tok[5]), int(tok[7])
     assert frames == g["Y_gsclms"].shape[0] and blocks * 128 == len(g["time_gsclms"]) and updates == int(g["n_updates_gsclms"])
     assert abs(energy / float(g["energy_gsclms"]) - 1.0) < 1e-3
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_batch_front_end_configured_from_the_references_parameter_files():
+    """btk20.batch.BatchBeamformer built from the reference's own unit_test/confs/*.json (carried verbatim inside
+    golden_online_kinect_c4_m256) and btk20.pybeamformer.calc_delays, two copies of the Kinect excerpt / recording per submission,
+    against the reference's outputs."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from distant_speech_recognition_b200.btk20 import pybeamformer
+    from distant_speech_recognition_b200.btk20.batch import BatchBeamformer
+    g = load_golden("online_kinect_c4_m256")
+    pr = np.load(os.path.join(GOLDEN, "prototype_shipped_M256_m4_r1.npz"))
+    s0, n = int(g["s0_static"]), int(g["n_static"])
+    for name in ("ds", "ds_and_zelinski", "sd", "sd_and_zelinski", "sd_and_mccowan", "sd_and_lefkimmiatis", "gsclms", "gscrls"):
+        c = json.loads(str(g["conf_" + name]))
+        x = g["x16"] if name.startswith("gsc") else g["x16"][:, s0:s0 + n]
+        x = np.ascontiguousarray(np.stack([x, x]).astype(np.float32))
+        d = pybeamformer.calc_delays(c["array_type"], c["microphone_positions"], c["target"]["positions"][0][1])
+        assert np.allclose(d, g["delays"], rtol=0, atol=1e-15)
+        bf = dict(c["beamformer"])
+        if bf["type"] == "delay_and_sum":
+            bf["type"] = "gsc"          # the script builds SubbandGSCBeamformer(afbs, Nc=1) with zero active weights for 'delay_and_sum'
+        bb = BatchBeamformer(4, pr["h"], pr["g"], M=256, m=4, r=1, samplerate=16000, beamformer=bf, postfilter=c.get("postfilter"),
+                             max_utterances=2, max_samples=x.shape[2])
+        t, Y, st = bb.process(x, np.stack([d, d]), mpos=c["microphone_positions"])
+        for u in range(2):
+            assert rel_l2(Y[u], g["Y_" + name]) < TOL, (name, u)
+            assert rel_l2(t[u], g["time_" + name]) < TOL, (name, u)
+        bb.pipe.close()
