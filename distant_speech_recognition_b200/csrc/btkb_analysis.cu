@@ -158,7 +158,11 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) 
 // of the 32 samples frame t+1 needs are the ones the same thread already loaded for frame t: 36 shared-memory loads feed
 // 64 (x2 channels) MACs.  The two transforms then advance pass by pass together (independent instruction streams, one
 // in-place buffer each, every barrier covers two transforms).
-template <int M, int MT, int FR, int G>
+//
+// PK = true: the fold and the transforms use the packed 2 x fp32 instructions (btkb_f2.cuh).  The two real channels of a pair are
+// the halves of one float2, so a tap MAC on both channels is one FFMA2 with the tap broadcast; results are bit-identical to
+// PK = false.  Selected with BTKB_ANALYSIS_PACKED=1 (off by default until it has been timed on a B200).
+template <int M, int MT, int FR, int G, bool PK = false>
 __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(AnalysisArgs a) {
   using Plan = FftPlan<M>;
   constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0, P = Plan::P;
@@ -251,32 +255,40 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
         for (int k = 0; k < MT; k++) {
           const float2 s = make_float2(xsa[base - (tg + NT * q) - k * M], xsb[base - (tg + NT * q) - k * M]);
           const float h0 = hreg[BTKB_SLOT(q) * MT + k];
-          v0[BTKB_SLOT(q)].x = fmaf(h0, s.x, v0[BTKB_SLOT(q)].x);
-          v0[BTKB_SLOT(q)].y = fmaf(h0, s.y, v0[BTKB_SLOT(q)].y);
-          constexpr int dummy = 0; (void)dummy;
+          if constexpr (PK) v0[BTKB_SLOT(q)] = f2_fma_s(s, h0, v0[BTKB_SLOT(q)]);
+          else {
+            v0[BTKB_SLOT(q)].x = fmaf(h0, s.x, v0[BTKB_SLOT(q)].x);
+            v0[BTKB_SLOT(q)].y = fmaf(h0, s.y, v0[BTKB_SLOT(q)].y);
+          }
           const int q1 = (q + SH >= 8) ? q + SH - 8 : q + SH;
           const int k1 = (q + SH >= 8) ? k + 1 : k;
           if (k1 < MT) {
             const float h1 = hreg[BTKB_SLOT(q1) * MT + k1];
-            v1[BTKB_SLOT(q1)].x = fmaf(h1, s.x, v1[BTKB_SLOT(q1)].x);
-            v1[BTKB_SLOT(q1)].y = fmaf(h1, s.y, v1[BTKB_SLOT(q1)].y);
+            if constexpr (PK) v1[BTKB_SLOT(q1)] = f2_fma_s(s, h1, v1[BTKB_SLOT(q1)]);
+            else {
+              v1[BTKB_SLOT(q1)].x = fmaf(h1, s.x, v1[BTKB_SLOT(q1)].x);
+              v1[BTKB_SLOT(q1)].y = fmaf(h1, s.y, v1[BTKB_SLOT(q1)].y);
+            }
           }
         }
 #pragma unroll
       for (int q = 0; q < SH; q++) {  // the D new samples of frame t+1 (tap block k = 0)
         const float2 s = make_float2(xsa[base + D - (tg + NT * q)], xsb[base + D - (tg + NT * q)]);
         const float h1 = hreg[BTKB_SLOT(q) * MT + 0];
-        v1[BTKB_SLOT(q)].x = fmaf(h1, s.x, v1[BTKB_SLOT(q)].x);
-        v1[BTKB_SLOT(q)].y = fmaf(h1, s.y, v1[BTKB_SLOT(q)].y);
+        if constexpr (PK) v1[BTKB_SLOT(q)] = f2_fma_s(s, h1, v1[BTKB_SLOT(q)]);
+        else {
+          v1[BTKB_SLOT(q)].x = fmaf(h1, s.x, v1[BTKB_SLOT(q)].x);
+          v1[BTKB_SLOT(q)].y = fmaf(h1, s.y, v1[BTKB_SLOT(q)].y);
+        }
       }
     }
     // ---- two transforms, pass by pass, in place (one buffer each)
-    fft_first_pass<M, +1>(v0, buf0, tg);
-    fft_first_pass<M, +1>(v1, buf1, tg);
+    fft_first_pass<M, +1, PK>(v0, buf0, tg);
+    fft_first_pass<M, +1, PK>(v1, buf1, tg);
     __syncthreads();
     if (!(a.debug & 4)) {
       auto sync = [] { __syncthreads(); };
-      FftPassChain<M, +1, 0, decltype(sync)>::run(v0, v1, buf0, buf1, tg, tw, sync);
+      FftPassChain<M, +1, 0, decltype(sync), PK>::run(v0, v1, buf0, buf1, tg, tw, sync);
     }
     // ---- untangle the channel pair, write snapshots, channel-0 energy.  After the last pass this thread holds
     // Z[tg + r NT] in v[r]; bins k = tg + q NT (q < 4) and k = M/2 (tg == 0, r = 4) are its own, only the partner
@@ -330,13 +342,19 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
 #undef BTKB_SLOT
 }
 
+static bool analysis_packed() {  // BTKB_ANALYSIS_PACKED=1: packed 2 x fp32 variant (bit-identical results; off by default)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BTKB_ANALYSIS_PACKED"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v == 1;
+}
+
 template <int M, int MT, int FR>
 static cudaError_t launch_analysis_r1(const AnalysisArgs& a_in, cudaStream_t st) {
   AnalysisArgs a = a_in;
   using Plan = FftPlan<M>;
   constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
   size_t smem = sizeof(float2) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * 4;
-  auto kern = k_analysis_r1<M, MT, FR, G>;
+  auto kern = analysis_packed() ? k_analysis_r1<M, MT, FR, G, true> : k_analysis_r1<M, MT, FR, G, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // tiles per CTA: amortise the per-CTA set-up while keeping >= ~8 waves of CTAs for balance

@@ -9,8 +9,13 @@
 // Direction: SIGN = +1 is the reference's gsl_fft_complex_radix2_backward (unnormalised e^{+2 pi i nk/M}, used by
 // OverSampledDFTAnalysisBank::next, modulated.cc:396); SIGN = -1 is gsl_fft_complex_radix2_forward (synthesis,
 // modulated.cc:559).
+//
+// PK = true selects the packed 2 x fp32 forms of btkb_f2.cuh (FADD2 / FMUL2 / FFMA2): same operations and roundings per component,
+// half the issue slots for the complex arithmetic (a radix-8 butterfly is 28 instructions instead of 56, a twiddle product 2
+// instead of 4).  Bit-identical to PK = false (tests/test_fft_packed_host.py runs both on the CPU).
 #pragma once
 #include <cuda_runtime.h>
+#include "btkb_f2.cuh"
 
 namespace btkb {
 
@@ -53,23 +58,71 @@ template <int LAY>
 __device__ __forceinline__ int lidx(int i) { return LAY == 0 ? i : (LAY == 1 ? i + (i >> 4) : (i ^ (((i >> 6) & 1) << 3))); }
 __host__ __device__ constexpr int lay_of(int Ns) { return Ns >= 16 ? 0 : (Ns == 8 ? 2 : 1); }
 
-template <int SIGN>
-__device__ __forceinline__ void dft2(float2& a, float2& b) {
-  float2 t = a; a = cadd(t, b); b = csub(t, b);
+// The same indices in "per-thread base + compile-time offset" form (used by the PK = true code: the eight addresses of an exchange
+// then cost one or two registers and no per-iteration integer arithmetic).
+//   lidx_ld<LAY, S>(tg, r)  == lidx<LAY>(tg + r S)               loads of a radix-8 pass, S = M/8, tg < S
+//   lidx_st<LAY, Ns>(tg, r) == lidx<LAY>(j0 + r Ns), j0 = (tg - tg % Ns) 8 + tg % Ns     Stockham scatter of a radix-8 pass
+template <int LAY, int S>
+__device__ __forceinline__ int lidx_ld(int tg, int r) {
+  if constexpr (LAY == 0) return tg + r * S;
+  else if constexpr (LAY == 1) {
+    static_assert(S % 16 == 0, "stride must be a multiple of the padding period");
+    return (tg + (tg >> 4)) + r * (S + S / 16);            // (tg + r S) >> 4 == (tg >> 4) + r S / 16
+  } else {
+    static_assert(S == 64, "the XOR layout is only used for M = 512");
+    return ((r & 1) ? (tg ^ 8) : tg) + r * S;               // bit 6 of tg + 64 r is r & 1 (tg < 64); the XOR touches bit 3 only
+  }
 }
-template <int SIGN>
+template <int LAY, int Ns>
+__device__ __forceinline__ int lidx_st(int tg, int r) {
+  const int k = tg % Ns;
+  const int j0 = (tg - k) * 8 + k;
+  if constexpr (LAY == 0) return j0 + r * Ns;
+  else if constexpr (LAY == 1) {
+    static_assert(Ns == 2 || Ns == 4, "padded layout: strides below 8");
+    return (j0 + (j0 >> 4)) + r * Ns + ((r * Ns) >> 4);     // j0 - k is a multiple of 16 and k + r Ns crosses 16 exactly when r Ns does
+  } else {
+    static_assert(Ns == 8, "XOR layout: stride 8");
+    const int s8 = ((tg >> 3) & 1) << 3;                   // bit 6 of j0 + 8 r is bit 3 of tg; bit 3 of j0 + 8 r is r & 1
+    return ((r & 1) ? (j0 - s8) : (j0 + s8)) + r * Ns;
+  }
+}
+
+template <int SIGN, bool PK = false>
+__device__ __forceinline__ void dft2(float2& a, float2& b) {
+  float2 t = a;
+  if constexpr (PK) { a = f2_add(t, b); b = f2_sub(t, b); }
+  else { a = cadd(t, b); b = csub(t, b); }
+}
+template <int SIGN, bool PK = false>
 __device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  if constexpr (PK) {
+    // a3 = SIGN i (v1 - v3) is never formed: v1 = a1 + SIGN i d, v3 = a1 - SIGN i d (swap + half negation are operand modifiers)
+    const float2 a0 = f2_add(v0, v2), a1 = f2_sub(v0, v2), a2 = f2_add(v1, v3), d = f2_sub(v1, v3);
+    v0 = f2_add(a0, a2); v2 = f2_sub(a0, a2); v1 = f2_add_ib<SIGN>(a1, d); v3 = f2_sub_ib<SIGN>(a1, d);
+    return;
+  }
   float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = mul_si<SIGN>(csub(v1, v3));
   v0 = cadd(a0, a2); v2 = csub(a0, a2); v1 = cadd(a1, a3); v3 = csub(a1, a3);
 }
 // X[q] = sum_r v[r] exp(SIGN 2 pi i q r / 8), natural order in and out
-template <int SIGN>
+template <int SIGN, bool PK = false>
 __device__ __forceinline__ void dft8(float2* v) {
   float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
   float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
-  dft4<SIGN>(e0, e1, e2, e3);
-  dft4<SIGN>(o0, o1, o2, o3);
+  dft4<SIGN, PK>(e0, e1, e2, e3);
+  dft4<SIGN, PK>(o0, o1, o2, o3);
   const float s = 0.70710678118654752440f;
+  if constexpr (PK) {
+    // o1 (1 + SIGN i)/sqrt2 ; SIGN i o2 folded into the last stage ; o3 (-1 + SIGN i)/sqrt2 — the sums the scalar code forms, then * s
+    o1 = f2_scale(f2_add_ib<SIGN>(o1, o1), s);
+    o3 = f2_scale(f2_add_ib<SIGN>(make_float2(-o3.x, -o3.y), o3), s);
+    v[0] = f2_add(e0, o0); v[4] = f2_sub(e0, o0);
+    v[1] = f2_add(e1, o1); v[5] = f2_sub(e1, o1);
+    v[2] = f2_add_ib<SIGN>(e2, o2); v[6] = f2_sub_ib<SIGN>(e2, o2);
+    v[3] = f2_add(e3, o3); v[7] = f2_sub(e3, o3);
+    return;
+  }
   // o1 *= (1 + SIGN i)/sqrt2 ; o2 *= SIGN i ; o3 *= (-1 + SIGN i)/sqrt2
   float2 t1 = mul_si<SIGN>(o1);
   o1 = make_float2((o1.x + t1.x) * s, (o1.y + t1.y) * s);
@@ -131,16 +184,22 @@ __device__ __forceinline__ void stockham_store(float2* buf, const float2* v, int
 }
 
 // The leading radix-R0 pass on registers that were loaded as v[b*R0 + r] = in[(tid + b NT) + r M/R0].
-template <int M, int SIGN>
+template <int M, int SIGN, bool PK = false>
 __device__ __forceinline__ void fft_first_pass(float2* v, float2* buf, int tid) {
   using Plan = FftPlan<M>;
   constexpr int R0 = Plan::R0, NT = Plan::NT, NB = 8 / R0;
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     float2* w = v + b * R0;
-    if (R0 == 8) dft8<SIGN>(w);
-    else if (R0 == 4) dft4<SIGN>(w[0], w[1], w[2], w[3]);
-    else dft2<SIGN>(w[0], w[1]);
+    if (R0 == 8) dft8<SIGN, PK>(w);
+    else if (R0 == 4) dft4<SIGN, PK>(w[0], w[1], w[2], w[3]);
+    else dft2<SIGN, PK>(w[0], w[1]);
+    if constexpr (PK) {   // pidx(j R0 + r) == j R0 + j / (16 / R0) + r  (R0 (j mod 16/R0) + r <= 15)
+      const int j = tid + b * NT;
+      float2* dst = buf + (j * R0 + j / (16 / R0));
+#pragma unroll
+      for (int r = 0; r < R0; r++) dst[r] = w[r];
+    } else
     stockham_store<R0>(buf, w, tid + b * NT, 1);
   }
 }
@@ -185,7 +244,7 @@ __device__ __forceinline__ float2* fft_run(float2* v, float2* bufA, float2* bufB
 // their own in-place buffers b0 / b1.  The buffers were filled by the previous exchange with layout lay_of(previous stride).
 // On the last pass only the upper half of the spectrum (indices >= M/2, i.e. r = 4..7) is written back, in natural order:
 // callers that untangle real sequences keep Z[k] for k < M/2 in registers (v[r], r < 4) and fetch only Z[M - k].
-template <int M, int SIGN, int PASS, typename Sync>
+template <int M, int SIGN, int PASS, typename Sync, bool PK = false>
 __device__ __forceinline__ void fft_pass_pair(float2* v0, float2* v1, float2* b0, float2* b1, int tg, const FftTwiddles<M, SIGN>& T, Sync sync) {
   using Plan = FftPlan<M>;
   constexpr int NsPrev = (PASS == 0) ? 1 : Plan::R0 * Plan::pow8(PASS - 1);
@@ -193,16 +252,25 @@ __device__ __forceinline__ void fft_pass_pair(float2* v0, float2* v1, float2* b0
   constexpr int LIN = (PASS == 0) ? 1 : lay_of(NsPrev);
   constexpr int LOUT = lay_of(Ns);
 #pragma unroll
-  for (int r = 0; r < 8; r++) { v0[r] = b0[lidx<LIN>(tg + r * (M / 8))]; v1[r] = b1[lidx<LIN>(tg + r * (M / 8))]; }
+  for (int r = 0; r < 8; r++) {
+    if constexpr (PK) { v0[r] = b0[lidx_ld<LIN, M / 8>(tg, r)]; v1[r] = b1[lidx_ld<LIN, M / 8>(tg, r)]; }
+    else { v0[r] = b0[lidx<LIN>(tg + r * (M / 8))]; v1[r] = b1[lidx<LIN>(tg + r * (M / 8))]; }
+  }
   sync();
 #pragma unroll
-  for (int r = 1; r < 8; r++) { v0[r] = cmul(v0[r], T.tw[PASS][r - 1]); v1[r] = cmul(v1[r], T.tw[PASS][r - 1]); }
-  dft8<SIGN>(v0);
-  dft8<SIGN>(v1);
+  for (int r = 1; r < 8; r++) {
+    if constexpr (PK) { v0[r] = f2_cmul(v0[r], T.tw[PASS][r - 1]); v1[r] = f2_cmul(v1[r], T.tw[PASS][r - 1]); }
+    else { v0[r] = cmul(v0[r], T.tw[PASS][r - 1]); v1[r] = cmul(v1[r], T.tw[PASS][r - 1]); }
+  }
+  dft8<SIGN, PK>(v0);
+  dft8<SIGN, PK>(v1);
   if (PASS == Plan::P - 1) {
     static_assert(Ns * 8 == M || PASS != Plan::P - 1, "last pass stride");
 #pragma unroll
     for (int r = 4; r < 8; r++) { b0[tg + r * (M / 8)] = v0[r]; b1[tg + r * (M / 8)] = v1[r]; }
+  } else if constexpr (PK) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) { b0[lidx_st<LOUT, Ns>(tg, r)] = v0[r]; b1[lidx_st<LOUT, Ns>(tg, r)] = v1[r]; }
   } else {
     const int k = tg % Ns;
     const int j0 = (tg - k) * 8 + k;
@@ -211,12 +279,12 @@ __device__ __forceinline__ void fft_pass_pair(float2* v0, float2* v1, float2* b0
   }
   sync();
 }
-template <int M, int SIGN, int PASS, typename Sync>
+template <int M, int SIGN, int PASS, typename Sync, bool PK = false>
 struct FftPassChain {
   static __device__ __forceinline__ void run(float2* v0, float2* v1, float2* b0, float2* b1, int tg, const FftTwiddles<M, SIGN>& T, Sync sync) {
     if constexpr (PASS < FftPlan<M>::P) {
-      fft_pass_pair<M, SIGN, PASS>(v0, v1, b0, b1, tg, T, sync);
-      FftPassChain<M, SIGN, PASS + 1, Sync>::run(v0, v1, b0, b1, tg, T, sync);
+      fft_pass_pair<M, SIGN, PASS, Sync, PK>(v0, v1, b0, b1, tg, T, sync);
+      FftPassChain<M, SIGN, PASS + 1, Sync, PK>::run(v0, v1, b0, b1, tg, T, sync);
     }
   }
 };

@@ -1,0 +1,103 @@
+// CPU execution of the kernels' FFT code (csrc/btkb_fft.cuh, the same source k_analysis_r1 / k_synthesis_fast compile for sm_100a):
+// the NT = M/8 "threads" of one transform pair run as std::threads, the shared-memory buffers are plain arrays and the barrier is a
+// std::barrier.  Both the scalar path (PK = false, the one measured on B200) and the packed 2 x fp32 path (PK = true, btkb_f2.cuh;
+// on the host its primitives are plain scalar code with fmaf) are run on the same input; the driver (tests/test_fft_packed_host.py)
+// requires them to agree BIT FOR BIT and checks both against a double-precision DFT.  Test infrastructure only.
+//   argv: M SIGN seed;  stdout: M lines "re0 im0 re1 im1  re0p im0p re1p im1p" (hex floats) = spectra of the two transforms, scalar
+//   then packed, followed by one line "fold <max abs difference of the packed vs scalar polyphase MAC> primitives <mismatches>"
+#include <barrier>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <thread>
+#include <vector>
+
+// device-only intrinsics the header uses in code paths exercised here
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(M_PI * (double)x); *c = (float)std::cos(M_PI * (double)x); }
+
+#include "../../distant_speech_recognition_b200/csrc/btkb_fft.cuh"
+using namespace btkb;
+
+template <int M, int SIGN, bool PK>
+static void run_pair(const std::vector<float2>& in0, const std::vector<float2>& in1, const std::vector<float2>& tab, std::vector<float2>& out0,
+                     std::vector<float2>& out1) {
+  using Plan = FftPlan<M>;
+  constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0;
+  std::vector<float2> buf0(Plan::BUF), buf1(Plan::BUF);
+  std::barrier bar(NT);
+  out0.assign(M, make_float2(0, 0)); out1.assign(M, make_float2(0, 0));
+  auto body = [&](int tg) {
+    FftTwiddles<M, SIGN> tw;
+    tw.init_from_table(tg, tab.data());
+    float2 v0[8], v1[8];
+    for (int b = 0; b < NB; b++)
+      for (int r = 0; r < R0; r++) { v0[b * R0 + r] = in0[(tg + b * NT) + r * (M / R0)]; v1[b * R0 + r] = in1[(tg + b * NT) + r * (M / R0)]; }
+    auto sync = [&] { bar.arrive_and_wait(); };
+    fft_first_pass<M, SIGN, PK>(v0, buf0.data(), tg);
+    fft_first_pass<M, SIGN, PK>(v1, buf1.data(), tg);
+    sync();
+    FftPassChain<M, SIGN, 0, decltype(sync), PK>::run(v0, v1, buf0.data(), buf1.data(), tg, tw, sync);
+    // lower half of the spectrum stays in registers (v[r] = Z[tg + r NT], r < 4), the upper half is in the buffers in natural order
+    for (int r = 0; r < 4; r++) { out0[tg + r * NT] = v0[r]; out1[tg + r * NT] = v1[r]; }
+    for (int r = 4; r < 8; r++) { out0[tg + r * NT] = buf0[tg + r * NT]; out1[tg + r * NT] = buf1[tg + r * NT]; }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < NT; t++) th.emplace_back(body, t);
+  for (auto& t : th) t.join();
+}
+
+static unsigned bits(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+
+template <int M, int SIGN>
+static int run(unsigned seed) {
+  std::mt19937 rng(seed);
+  std::normal_distribution<float> nd(0.f, 3000.f);
+  std::vector<float2> in0(M), in1(M), tab(M);
+  for (int i = 0; i < M; i++) { in0[i] = make_float2(nd(rng), nd(rng)); in1[i] = make_float2(nd(rng), nd(rng)); }
+  for (int i = 0; i < M; i++) { const double a = 2.0 * M_PI * i / M; tab[i] = make_float2((float)std::cos(a), (float)std::sin(a)); }   // btkb_api.cu:207-214
+  std::vector<float2> s0, s1, p0, p1;
+  run_pair<M, SIGN, false>(in0, in1, tab, s0, s1);
+  run_pair<M, SIGN, true>(in0, in1, tab, p0, p1);
+  for (int i = 0; i < M; i++) printf("%a %a %a %a %a %a %a %a\n", in0[i].x, in0[i].y, in1[i].x, in1[i].y, 0.0, 0.0, 0.0, 0.0);
+  for (int i = 0; i < M; i++) printf("%a %a %a %a %a %a %a %a\n", s0[i].x, s0[i].y, s1[i].x, s1[i].y, p0[i].x, p0[i].y, p1[i].x, p1[i].y);
+  // the polyphase MAC of k_analysis_r1: tap h times the (channel a, channel b) sample pair, accumulated (scalar vs f2_fma_s)
+  float dmax = 0.f;
+  for (int trial = 0; trial < 2000; trial++) {
+    float2 acc_s = make_float2(0.f, 0.f), acc_p = acc_s;
+    for (int k = 0; k < 4; k++) {
+      const float h = nd(rng) * 1e-4f; const float2 s = make_float2(nd(rng), nd(rng));
+      acc_s.x = fmaf(h, s.x, acc_s.x); acc_s.y = fmaf(h, s.y, acc_s.y);
+      acc_p = f2_fma_s(s, h, acc_p);
+    }
+    dmax = std::fmax(dmax, std::fmax(std::fabs(acc_s.x - acc_p.x), std::fabs(acc_s.y - acc_p.y)));
+  }
+  // every primitive against the scalar expression it replaces
+  int bad = 0;
+  for (int trial = 0; trial < 20000; trial++) {
+    const float2 a = make_float2(nd(rng), nd(rng)), b = make_float2(nd(rng), nd(rng));
+    const float sc = nd(rng);
+    auto ne = [&](float2 x, float2 y) { return bits(x.x) != bits(y.x) || bits(x.y) != bits(y.y); };
+    bad += ne(f2_add(a, b), cadd(a, b));
+    bad += ne(f2_sub(a, b), csub(a, b));
+    bad += ne(f2_cmul(a, b), cmul(a, b));
+    bad += ne(f2_add_ib<+1>(a, b), cadd(a, mul_si<+1>(b)));
+    bad += ne(f2_add_ib<-1>(a, b), cadd(a, mul_si<-1>(b)));
+    bad += ne(f2_sub_ib<+1>(a, b), csub(a, mul_si<+1>(b)));
+    bad += ne(f2_sub_ib<-1>(a, b), csub(a, mul_si<-1>(b)));
+    bad += ne(f2_scale(a, sc), make_float2(a.x * sc, a.y * sc));
+  }
+  printf("fold %a primitives %d\n", dmax, bad);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) return 2;
+  const int M = atoi(argv[1]), sign = atoi(argv[2]);
+  const unsigned seed = (unsigned)atoi(argv[3]);
+#define CASE(MM) if (M == MM) return sign > 0 ? run<MM, +1>(seed) : run<MM, -1>(seed);
+  CASE(256) CASE(512) CASE(1024) CASE(2048)
+  return 2;
+}
