@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
       if (act0) {
         const float2 zk = v0[q];
         const float2 zm = self ? zk : buf0[M - k];
-        const float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-        const float2 B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        const float2 A = PK ? f2_scale(f2_add_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 B = PK ? f2_scale_mi(f2_sub_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
         if (!(a.debug & 1)) {
         a.X[((size_t)ta * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
         if (has_b) a.X[((size_t)ta * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
       if (act1) {
         const float2 zk = v1[q];
         const float2 zm = self ? zk : buf1[M - k];
-        const float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-        const float2 B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        const float2 A = PK ? f2_scale(f2_add_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 B = PK ? f2_scale_mi(f2_sub_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
         if (!(a.debug & 1)) {
         a.X[((size_t)tb * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
         if (has_b) a.X[((size_t)tb * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
@@ -342,10 +342,9 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
 #undef BTKB_SLOT
 }
 
-static bool analysis_packed() {  // BTKB_ANALYSIS_PACKED=1: packed 2 x fp32 variant (bit-identical results; off by default)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BTKB_ANALYSIS_PACKED"); v = (e && atoi(e) != 0) ? 1 : 0; }
-  return v == 1;
+static bool analysis_packed() {  // BTKB_ANALYSIS_PACKED=1: packed 2 x fp32 variant (bit-identical results; off by default).  Read at
+  const char* e = getenv("BTKB_ANALYSIS_PACKED");   // every launch so that one process can compare the two variants.
+  return e && atoi(e) != 0;
 }
 
 template <int M, int MT, int FR>

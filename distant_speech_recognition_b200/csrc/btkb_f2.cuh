@@ -81,6 +81,38 @@ BTKB_F2 float2 f2_fma_s(float2 a, float s, float2 c) {
   return make_float2(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y));
 #endif
 }
+// (fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)) — two independent MAC chains side by side
+BTKB_F2 float2 f2_fma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+  return f2_upk(f2_fma_raw(f2_pk(a.x, a.y), f2_pk(b.x, b.y), f2_pk(c.x, c.y)));
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+// a + conj(b) = (a.x + b.x, a.y - b.y)   and   a - conj(b) = (a.x - b.x, a.y + b.y): the two sums that untangle a pair of real
+// sequences from one complex transform
+BTKB_F2 float2 f2_add_conj(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return f2_upk(f2_add_raw(f2_pk(a.x, a.y), f2_pk(b.x, -b.y)));
+#else
+  return make_float2(a.x + b.x, a.y + (-b.y));
+#endif
+}
+BTKB_F2 float2 f2_sub_conj(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return f2_upk(f2_add_raw(f2_pk(a.x, a.y), f2_pk(-b.x, b.y)));
+#else
+  return make_float2(a.x + (-b.x), a.y + b.y);
+#endif
+}
+// -i d s = (d.y s, -d.x s)
+BTKB_F2 float2 f2_scale_mi(float2 d, float s) {
+#if defined(__CUDA_ARCH__)
+  return f2_upk(f2_mul_raw(f2_pk(d.y, -d.x), f2_pk(s, s)));
+#else
+  return make_float2(d.y * s, (-d.x) * s);
+#endif
+}
 // complex product, the roundings of btkb::cmul: (fma(a.x, w.x, -(a.y w.y)), fma(a.x, w.y, a.y w.x))
 BTKB_F2 float2 f2_cmul(float2 a, float2 w) {
 #if defined(__CUDA_ARCH__)

@@ -15,6 +15,7 @@
 // memory, then every output sample is 8 (= R m) MACs.
 #include "btkb_internal.h"
 #include "btkb_fft.cuh"
+#include <cstdlib>
 
 namespace btkb {
 
@@ -130,7 +131,12 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a
 // asynchronous 8-byte copies (zero fill for frames outside the utterance), each group transforms TWO frame pairs per
 // iteration (independent instruction streams) and writes the real sequences v back IN PLACE over the Y rows it consumed;
 // the polyphase taps a thread needs (R m per output position) live in registers for all FB blocks of the tile.
-template <int M, int FB, int G, int MT, int RR>
+//
+// PK = true: packed 2 x fp32 arithmetic (btkb_f2.cuh) for the frame-pair combination Y_a + i Y_b, the transforms (the in-place pass
+// chain of btkb_fft.cuh, whose registers hold the whole natural-order spectrum after the last pass) and the polyphase MACs (the
+// R = 2 partial sums of an output sample are the two halves of one FFMA2 chain).  Same operations and roundings per component as
+// PK = false.  Selected with BTKB_SYNTHESIS_PACKED=1 (off by default until it has been timed on a B200).
+template <int M, int FB, int G, int MT, int RR, bool PK = false>
 __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
   using Plan = FftPlan<M>;
   constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0, P = Plan::P;
@@ -212,13 +218,31 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
           if (tq + 2 < a.onesided) { yc.x *= 0.5f; yc.y *= 0.5f; }
           if (tq + 3 < a.onesided) { yd.x *= 0.5f; yd.y *= 0.5f; }
         }
+        if constexpr (PK) { v0[b * R0 + r] = f2_add_ib<+1>(ya, yb); v1[b * R0 + r] = f2_add_ib<+1>(yc, yd); }
+        else {
         v0[b * R0 + r] = make_float2(ya.x - yb.y, ya.y + yb.x);
         v1[b * R0 + r] = make_float2(yc.x - yd.y, yc.y + yd.x);
+        }
       }
-    fft_first_pass<M, -1>(v0, buf0, tg);
-    fft_first_pass<M, -1>(v1, buf1, tg);
+    fft_first_pass<M, -1, PK>(v0, buf0, tg);
+    fft_first_pass<M, -1, PK>(v1, buf1, tg);
     __syncthreads();   // also: every thread of every group has consumed its Y rows
-    {
+    if constexpr (PK) {
+      auto sync = [] { __syncthreads(); };
+      FftPassChain<M, -1, 0, decltype(sync), PK>::run(v0, v1, buf0, buf1, tg, tw, sync);
+      // v[r] = natural-order element tg + r M/8 of the two transforms (all eight still in registers): real parts to row a/c,
+      // imaginary parts to row b/d
+      if (act) {
+        float* wa = rows + (size_t)(4 * qd + 0) * ROW; float* wb = rows + (size_t)(4 * qd + 1) * ROW;
+        float* wc = rows + (size_t)(4 * qd + 2) * ROW; float* wd = rows + (size_t)(4 * qd + 3) * ROW;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const int i = tg + r * (M / 8);
+          wa[i] = v0[r].x; wb[i] = v0[r].y; wc[i] = v1[r].x; wd[i] = v1[r].y;
+        }
+      }
+      __syncthreads();   // the rows are read by every thread of the CTA in the polyphase stage / the next quad's first pass reuses the buffers
+    } else {
       int Ns = R0;
 #pragma unroll
       for (int p = 0; p < P; p++) {
@@ -260,6 +284,20 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
         const int t = t0 + tl;
         if (t >= a.nb) break;
         float acc = 0.f;
+        if (PK && RR == 2 && t < nbu) {
+          // both partial sums w_{s2}, s2 = 0, 1, in one chain: taps (g[d + kM'], g[d + D + kM']) times (v_{t-1-2k}[d], v_{t-2k}[d + D]);
+          // the s2 = 0 term does not exist for the first block of an utterance (twf = t - 1 < 0)
+          float2 w2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < MT; k++) {
+            const int slot0 = tl - RR * k + RR * (MT - 1);
+            const float2 vv = make_float2(rows[(size_t)slot0 * ROW + d], rows[(size_t)(slot0 + 1) * ROW + d + D]);
+            w2 = f2_fma(make_float2(gt[j][0][k], gt[j][1][k]), vv, w2);
+          }
+          acc = (t >= 1 ? w2.x : 0.f) + acc;   // acc = 0 + w_0, then + w_1: the scalar order
+          acc += w2.y;
+          if (a.gain > 0) acc *= (float)a.gain;
+        } else
         if (t < nbu) {
 #pragma unroll
           for (int s2 = 0; s2 < RR; s2++) {
@@ -303,7 +341,9 @@ static cudaError_t launch_synthesis_fast(const SynthesisArgs& a, cudaStream_t st
   constexpr int NVP = (NV + 3) & ~3;
   constexpr int ROW = (((M / 2 + 1) * 2 + 3) & ~3);
   size_t smem = sizeof(float) * (size_t)NVP * ROW + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * 32;
-  auto kern = k_synthesis_fast<M, FB, G, MT, RR>;
+  const char* ev = getenv("BTKB_SYNTHESIS_PACKED");   // =1: packed 2 x fp32 variant (same results; off by default); read at every launch
+  const bool packed = ev && atoi(ev) != 0;
+  auto kern = packed ? k_synthesis_fast<M, FB, G, MT, RR, true> : k_synthesis_fast<M, FB, G, MT, RR, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (a.nb <= 0) return cudaSuccess;

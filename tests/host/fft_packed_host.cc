@@ -4,7 +4,7 @@
 // on the host its primitives are plain scalar code with fmaf) are run on the same input; the driver (tests/test_fft_packed_host.py)
 // requires them to agree BIT FOR BIT and checks both against a double-precision DFT.  Test infrastructure only.
 //   argv: M SIGN seed;  stdout: M lines "re0 im0 re1 im1  re0p im0p re1p im1p" (hex floats) = spectra of the two transforms, scalar
-//   then packed, followed by one line "fold <max abs difference of the packed vs scalar polyphase MAC> primitives <mismatches>"
+//   then packed, followed by one line "fold <max abs difference of the packed vs scalar polyphase MAC> primitives <mismatches> regs_differ <0|1>"
 #include <barrier>
 #include <cmath>
 #include <cstdio>
@@ -20,6 +20,8 @@ static inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin
 
 #include "../../distant_speech_recognition_b200/csrc/btkb_fft.cuh"
 using namespace btkb;
+
+static int regs_differ = 0;
 
 template <int M, int SIGN, bool PK>
 static void run_pair(const std::vector<float2>& in0, const std::vector<float2>& in1, const std::vector<float2>& tab, std::vector<float2>& out0,
@@ -43,6 +45,9 @@ static void run_pair(const std::vector<float2>& in0, const std::vector<float2>& 
     // lower half of the spectrum stays in registers (v[r] = Z[tg + r NT], r < 4), the upper half is in the buffers in natural order
     for (int r = 0; r < 4; r++) { out0[tg + r * NT] = v0[r]; out1[tg + r * NT] = v1[r]; }
     for (int r = 4; r < 8; r++) { out0[tg + r * NT] = buf0[tg + r * NT]; out1[tg + r * NT] = buf1[tg + r * NT]; }
+    // ... and is also still in the registers (k_synthesis_fast<PK> writes all eight values from v[])
+    for (int r = 4; r < 8; r++)
+      if (std::memcmp(&v0[r], &buf0[tg + r * NT], sizeof(float2)) || std::memcmp(&v1[r], &buf1[tg + r * NT], sizeof(float2))) regs_differ = 1;
   };
   std::vector<std::thread> th;
   for (int t = 0; t < NT; t++) th.emplace_back(body, t);
@@ -88,8 +93,12 @@ static int run(unsigned seed) {
     bad += ne(f2_sub_ib<+1>(a, b), csub(a, mul_si<+1>(b)));
     bad += ne(f2_sub_ib<-1>(a, b), csub(a, mul_si<-1>(b)));
     bad += ne(f2_scale(a, sc), make_float2(a.x * sc, a.y * sc));
+    bad += ne(f2_fma(a, b, make_float2(sc, -sc)), make_float2(fmaf(a.x, b.x, sc), fmaf(a.y, b.y, -sc)));
+    // the untangle of k_analysis_r1: A = (zk + conj zm)/2, B = (zk - conj zm)/(2i), exactly as the scalar kernel writes them
+    bad += ne(f2_scale(f2_add_conj(a, b), 0.5f), make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y)));
+    bad += ne(f2_scale_mi(f2_sub_conj(a, b), 0.5f), make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x)));
   }
-  printf("fold %a primitives %d\n", dmax, bad);
+  printf("fold %a primitives %d regs_differ %d\n", dmax, bad, regs_differ);
   return 0;
 }
 

@@ -43,3 +43,4 @@ def test_device_fft_source_on_the_cpu_scalar_and_packed(harness, M, sign):
     assert np.array_equal(S[:, :4], S[:, 4:])                       # packed == scalar, bit for bit (values printed as hex floats)
     tail = out[-1].split()
     assert tail[0] == "fold" and float.fromhex(tail[1]) == 0.0 and tail[2] == "primitives" and int(tail[3]) == 0
+    assert tail[4] == "regs_differ" and int(tail[5]) == 0      # after the last pass every thread still holds its eight outputs in registers
