@@ -113,6 +113,46 @@ BTKB_F2 float2 f2_scale_mi(float2 d, float s) {
   return make_float2(d.y * s, (-d.x) * s);
 #endif
 }
+// ---- complex multiply-accumulates of the per-bin kernels (btkb_perbin.cu cmac / cmac_conj and the NLMS update), two FFMA2 each.
+// The host forms spell out what each half of the two packed instructions computes.
+// acc + a b:        x: fma(a.y, -b.y, fma(a.x, b.x, acc.x))     y: fma(a.y, b.x, fma(a.x, b.y, acc.y))
+BTKB_F2 float2 f2_cmac(float2 acc, float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  const f2raw t = f2_fma_raw(f2_pk(a.x, a.x), f2_pk(b.x, b.y), f2_pk(acc.x, acc.y));
+  return f2_upk(f2_fma_raw(f2_pk(a.y, a.y), f2_pk(-b.y, b.x), t));
+#else
+  return make_float2(fmaf(a.y, -b.y, fmaf(a.x, b.x, acc.x)), fmaf(a.y, b.x, fmaf(a.x, b.y, acc.y)));
+#endif
+}
+// acc + a conj(b):  x: fma(a.y, b.y, fma(a.x, b.x, acc.x))      y: fma(-a.x, b.y, fma(a.y, b.x, acc.y))
+BTKB_F2 float2 f2_cmac_conj(float2 acc, float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  const f2raw t = f2_fma_raw(f2_pk(a.x, a.y), f2_pk(b.x, b.x), f2_pk(acc.x, acc.y));
+  return f2_upk(f2_fma_raw(f2_pk(a.y, -a.x), f2_pk(b.y, b.y), t));
+#else
+  return make_float2(fmaf(a.y, b.y, fmaf(a.x, b.x, acc.x)), fmaf(-a.x, b.y, fmaf(a.y, b.x, acc.y)));
+#endif
+}
+// x - c v  (the projector step of the NLMS update, c = C Yc):
+//                   x: fma(-c.x, v.x, fma(c.y, v.y, x.x))       y: fma(-c.x, v.y, fma(c.y, -v.x, x.y))
+BTKB_F2 float2 f2_sub_cmul(float2 x, float2 c, float2 v) {
+#if defined(__CUDA_ARCH__)
+  const f2raw t = f2_fma_raw(f2_pk(c.y, c.y), f2_pk(v.y, -v.x), f2_pk(x.x, x.y));
+  return f2_upk(f2_fma_raw(f2_pk(-c.x, -c.x), f2_pk(v.x, v.y), t));
+#else
+  return make_float2(fmaf(-c.x, v.x, fmaf(c.y, v.y, x.x)), fmaf(-c.x, v.y, fmaf(c.y, -v.x, x.y)));
+#endif
+}
+// k + e conj(q)  (k = keep u):
+//                   x: fma(e.y, q.y, fma(e.x, q.x, k.x))        y: fma(-e.x, q.y, fma(e.y, q.x, k.y))
+BTKB_F2 float2 f2_add_cmulc(float2 k, float2 e, float2 q) {
+#if defined(__CUDA_ARCH__)
+  const f2raw t = f2_fma_raw(f2_pk(e.x, e.y), f2_pk(q.x, q.x), f2_pk(k.x, k.y));
+  return f2_upk(f2_fma_raw(f2_pk(e.y, -e.x), f2_pk(q.y, q.y), t));
+#else
+  return make_float2(fmaf(e.y, q.y, fmaf(e.x, q.x, k.x)), fmaf(-e.x, q.y, fmaf(e.y, q.x, k.y)));
+#endif
+}
 // complex product, the roundings of btkb::cmul: (fma(a.x, w.x, -(a.y w.y)), fma(a.x, w.y, a.y w.x))
 BTKB_F2 float2 f2_cmul(float2 a, float2 w) {
 #if defined(__CUDA_ARCH__)

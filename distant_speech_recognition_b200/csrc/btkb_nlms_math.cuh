@@ -1,0 +1,80 @@
+// btkb_nlms_math.cuh — the complex arithmetic of the per-bin NLMS recurrence (k_perbin<C, LMS>, btkb_perbin.cu), in a header of its
+// own so that tests/host/fft_packed_host.cc can run the scalar (PK = false) and the packed 2 x fp32 (PK = true, btkb_f2.cuh) forms on
+// the CPU and require bit-identical results.  Reference: SubbandGSCLMSBeamformer.__iter__, btk20_src/lib/pybeamformer.py:659-734, in
+// the O(C) projector form of SURVEY.md App. A.3.
+#pragma once
+#include <cuda_runtime.h>
+#include "btkb_f2.cuh"
+
+namespace btkb {
+
+// FMA-only complex multiply-accumulate (4 FFMA each, no separate adds)
+__device__ __forceinline__ void cmac(float2& acc, float2 a, float2 b) {        // acc += a b
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cmac_conj(float2& acc, float2 a, float2 b) {   // acc += a conj(b)
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.y, b.x, acc.y); acc.y = fmaf(-a.x, b.y, acc.y);
+}
+// sum_c a[c] b[c] (or a[c] conj(b[c])) with two independent accumulators (halves the dependent FMA chain)
+// PK = true: each complex MAC is two FFMA2 (btkb_f2.cuh) instead of four FFMA; same operations and roundings per component.
+template <int C, bool CONJ, bool PK = false>
+__device__ __forceinline__ float2 cdot(const float2* a, const float2* b) {
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < C; c += 2) {
+    if constexpr (PK) {
+      if (CONJ) { s0 = f2_cmac_conj(s0, a[c], b[c]); if (c + 1 < C) s1 = f2_cmac_conj(s1, a[c + 1], b[c + 1]); }
+      else { s0 = f2_cmac(s0, a[c], b[c]); if (c + 1 < C) s1 = f2_cmac(s1, a[c + 1], b[c + 1]); }
+    } else {
+    if (CONJ) { cmac_conj(s0, a[c], b[c]); if (c + 1 < C) cmac_conj(s1, a[c + 1], b[c + 1]); }
+    else { cmac(s0, a[c], b[c]); if (c + 1 < C) cmac(s1, a[c + 1], b[c + 1]); }
+    }
+  }
+  if constexpr (PK) return f2_add(s0, s1);
+  return make_float2(s0.x + s1.x, s0.y + s1.y);
+}
+
+// One adaptation step (pybeamformer.py:689-716): e = Yc - u.x (a-priori error with the OLD u), a = gamma / sub-band energy,
+// (Q x)_c = x_c - C Yc v_c,  u~_c = (1 - a reg) u_c + a e conj((Q x)_c);  returns the two partial sums of ||u~||^2.
+template <int C, bool PK>
+__device__ __forceinline__ void nlms_adapt_step(const float2* x, const float2* w, float2* uw, float2 y, float gamma, float sub, float reg, float& n20,
+                                                float& n21) {
+  const float2 ux = cdot<C, false, PK>(uw, x);
+  if constexpr (PK) {
+    const float2 epa = f2_sub(y, ux);
+    const float alphaK = gamma / sub;
+    const float2 cy = f2_scale(y, (float)C);
+    const float2 ea = f2_scale(epa, alphaK);
+    const float keep = (reg > 0.f) ? 1.0f - alphaK * reg : 1.0f;
+    float2 nn = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const float2 q = f2_sub_cmul(x[c], cy, w[c]);
+      const float2 un = f2_add_cmulc(f2_scale(uw[c], keep), ea, q);
+      uw[c] = un;
+      nn = f2_fma(un, un, nn);
+    }
+    n20 = nn.x; n21 = nn.y;
+  } else {
+    const float2 epa = make_float2(y.x - ux.x, y.y - ux.y);
+    const float alphaK = gamma / sub;
+    const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
+    const float2 ea = make_float2(epa.x * alphaK, epa.y * alphaK);
+    const float keep = (reg > 0.f) ? 1.0f - alphaK * reg : 1.0f;
+    n20 = 0.f; n21 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      // (Q x)_c = x_c - C Yc v_c ;  u~_c = (1 - a reg) u_c + a e conj(q_c)
+      const float qx = fmaf(-cy.x, w[c].x, fmaf(cy.y, w[c].y, x[c].x));
+      const float qy = fmaf(-cy.x, w[c].y, fmaf(-cy.y, w[c].x, x[c].y));
+      const float unx = fmaf(ea.y, qy, fmaf(ea.x, qx, keep * uw[c].x));
+      const float uny = fmaf(-ea.x, qy, fmaf(ea.y, qx, keep * uw[c].y));
+      uw[c] = make_float2(unx, uny);
+      n20 = fmaf(unx, unx, n20); n21 = fmaf(uny, uny, n21);
+    }
+  }
+}
+
+}  // namespace btkb

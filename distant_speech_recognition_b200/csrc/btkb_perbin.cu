@@ -23,34 +23,18 @@
 // The (C-1) x C product per bin-frame disappears; waH = u conj(B) is recovered at export time (btkb_weights.cu).
 #include "btkb_tile_ring.cuh"
 #include "btkb_fft.cuh"   // complex helpers
+#include "btkb_nlms_math.cuh"
 #include "../../include/btkb.h"
+#include <cstdlib>
 
 namespace btkb {
 
 constexpr int MODE_STATIC = 0, MODE_LMS = 1;
 
-// FMA-only complex multiply-accumulate (4 FFMA each, no separate adds)
-__device__ __forceinline__ void cmac(float2& acc, float2 a, float2 b) {        // acc += a b
-  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
-  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
-}
-__device__ __forceinline__ void cmac_conj(float2& acc, float2 a, float2 b) {   // acc += a conj(b)
-  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
-  acc.y = fmaf(a.y, b.x, acc.y); acc.y = fmaf(-a.x, b.y, acc.y);
-}
-// sum_c a[c] b[c] (or a[c] conj(b[c])) with two independent accumulators (halves the dependent FMA chain)
-template <int C, bool CONJ>
-__device__ __forceinline__ float2 cdot(const float2* a, const float2* b) {
-  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < C; c += 2) {
-    if (CONJ) { cmac_conj(s0, a[c], b[c]); if (c + 1 < C) cmac_conj(s1, a[c + 1], b[c + 1]); }
-    else { cmac(s0, a[c], b[c]); if (c + 1 < C) cmac(s1, a[c + 1], b[c + 1]); }
-  }
-  return make_float2(s0.x + s1.x, s0.y + s1.y);
-}
-
-template <int C, int MODE, int PF>
+// PK = true (NLMS mode only, BTKB_PERBIN_PACKED=1, off by default): the complex arithmetic of the frame loop in packed 2 x fp32
+// instructions — 2 FFMA2 per complex MAC instead of 4 FFMA, about half the fp32 issue slots of the recurrence.  Bit-identical
+// results (tests/test_fft_packed_host.py checks every packed formula against the scalar expression it replaces).
+template <int C, int MODE, int PF, bool PK = false>
 __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int g0 = blockIdx.x * TILE;
@@ -132,7 +116,7 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
     if (MODE == MODE_LMS && t + 1 < a.T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
 
     // upper branch: Yc = w^H x
-    float2 y = cdot<C, true>(x, w);
+    float2 y = cdot<C, true, PK>(x, w);
     const bool live = t < Tu;
 
     if (MODE == MODE_LMS) {
@@ -140,41 +124,33 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
       if (--slow_cnt == 0) { gamma *= 0.5f; slow_cnt = a.lms.slowdown_after; }  // isamp > 0 and isamp % slowdown_after == 0
       const bool adapt = energy > (Eavg * inv_sil);
       float nx0 = 0.f, nx1 = 0.f;
+      if constexpr (PK) {
+        float2 nn = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; c++) nn = f2_fma(x[c], x[c], nn);
+        nx0 = nn.x; nx1 = nn.y;
+      } else {
 #pragma unroll
       for (int c = 0; c < C; c++) { nx0 = fmaf(x[c].x, x[c].x, nx0); nx1 = fmaf(x[c].y, x[c].y, nx1); }
+      }
       const float nx = nx0 + nx1;
       float sub = (t > 0) ? fmaf(se, a.lms.beta, one_m_beta * nx) : nx;
       sub = fmaxf(sub, a.lms.energy_floor);
       if (adapt && live) {
-        const float2 ux = cdot<C, false>(uw, x);
-        const float2 epa = csub(y, ux);
-        const float alphaK = gamma / sub;
-        const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
-        const float2 ea = make_float2(epa.x * alphaK, epa.y * alphaK);
-        const float keep = (a.lms.regularization_param > 0.f) ? 1.0f - alphaK * a.lms.regularization_param : 1.0f;
-        float n20 = 0.f, n21 = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          // (Q x)_c = x_c - C Yc v_c ;  u~_c = (1 - a reg) u_c + a e conj(q_c)
-          const float qx = fmaf(-cy.x, w[c].x, fmaf(cy.y, w[c].y, x[c].x));
-          const float qy = fmaf(-cy.x, w[c].y, fmaf(-cy.y, w[c].x, x[c].y));
-          const float unx = fmaf(ea.y, qy, fmaf(ea.x, qx, keep * uw[c].x));
-          const float uny = fmaf(-ea.x, qy, fmaf(ea.y, qx, keep * uw[c].y));
-          uw[c] = make_float2(unx, uny);
-          n20 = fmaf(unx, unx, n20); n21 = fmaf(uny, uny, n21);
-        }
+        float n20, n21;
+        nlms_adapt_step<C, PK>(x, w, uw, y, gamma, sub, a.lms.regularization_param, n20, n21);
         const float n2 = n20 + n21;
         if (n2 > a.lms.max_wa_l2norm) {
           const float cK = sqrtf(a.lms.max_wa_l2norm / n2);
 #pragma unroll
-          for (int c = 0; c < C; c++) { uw[c].x *= cK; uw[c].y *= cK; }
+          for (int c = 0; c < C; c++) { if constexpr (PK) uw[c] = f2_scale(uw[c], cK); else { uw[c].x *= cK; uw[c].y *= cK; } }
         }
         se = sub;
         n_updates++;
       }
       if (t >= a.lms.min_frames) {
-        const float2 ux = cdot<C, false>(uw, x);
-        y = csub(y, ux);
+        const float2 ux = cdot<C, false, PK>(uw, x);
+        y = PK ? f2_sub(y, ux) : csub(y, ux);
       }
       Eavg = fmaf(Eavg, a.lms.beta, one_m_beta * energy);
     }
@@ -572,7 +548,18 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
     kern<<<grid, TILE, smem, st>>>(tm, a);
     return cudaGetLastError();
   }
-  if (lms) { if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_LMS, 0); }
+  if (lms) {
+    if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue;
+    const char* ev = getenv("BTKB_PERBIN_PACKED");   // =1: packed 2 x fp32 NLMS recurrence (bit-identical; off by default); read at every launch
+    if (ev && atoi(ev) != 0) {
+      auto kern = k_perbin<C, MODE_LMS, 0, true>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kern<<<grid, TILE, smem, st>>>(tm, a);
+      return cudaGetLastError();
+    }
+    BTKB_LAUNCH(MODE_LMS, 0);
+  }
   if (pf == BTKB_PF_ZELINSKI) BTKB_LAUNCH(MODE_STATIC, 1);
   if (pf == BTKB_PF_MCCOWAN) { if (!a.PFQ) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 2); }
   if (pf == BTKB_PF_LEFKIMMIATIS) { if (!a.PFQ || !a.LAM) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 3); }

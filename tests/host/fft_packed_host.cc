@@ -4,7 +4,7 @@
 // on the host its primitives are plain scalar code with fmaf) are run on the same input; the driver (tests/test_fft_packed_host.py)
 // requires them to agree BIT FOR BIT and checks both against a double-precision DFT.  Test infrastructure only.
 //   argv: M SIGN seed;  stdout: M lines "re0 im0 re1 im1  re0p im0p re1p im1p" (hex floats) = spectra of the two transforms, scalar
-//   then packed, followed by one line "fold <max abs difference of the packed vs scalar polyphase MAC> primitives <mismatches> regs_differ <0|1>"
+//   then packed, followed by one line "fold <max abs difference of the packed vs scalar polyphase MAC> primitives <mismatches> regs_differ <0|1> nlms <mismatches>"
 #include <barrier>
 #include <cmath>
 #include <cstdio>
@@ -19,7 +19,35 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(M_PI * (double)x); *c = (float)std::cos(M_PI * (double)x); }
 
 #include "../../distant_speech_recognition_b200/csrc/btkb_fft.cuh"
+#include "../../distant_speech_recognition_b200/csrc/btkb_nlms_math.cuh"
 using namespace btkb;
+
+// The NLMS recurrence of k_perbin<C, LMS> (btkb_nlms_math.cuh): 40 consecutive adaptation steps of one chain with the scalar and
+// with the packed arithmetic, states carried separately; every intermediate (Yc, u.x, u, ||u||^2 partial sums) must agree bit for bit.
+template <int C>
+static int nlms_mismatches(unsigned seed) {
+  std::mt19937 rng(seed);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  auto ne = [](float a, float b) { unsigned x, y; std::memcpy(&x, &a, 4); std::memcpy(&y, &b, 4); return x != y; };
+  int bad = 0;
+  float2 w[C], us[C], up[C];
+  for (int c = 0; c < C; c++) { const float ph = 3.f * nd(rng); w[c] = make_float2(std::cos(ph) / C, std::sin(ph) / C); us[c] = up[c] = make_float2(0.f, 0.f); }
+  for (int t = 0; t < 40; t++) {
+    float2 x[C];
+    for (int c = 0; c < C; c++) x[c] = make_float2(3000.f * nd(rng), 3000.f * nd(rng));
+    const float2 ys = cdot<C, true, false>(x, w), yp = cdot<C, true, true>(x, w);
+    bad += ne(ys.x, yp.x) + ne(ys.y, yp.y);
+    const float2 uxs = cdot<C, false, false>(us, x), uxp = cdot<C, false, true>(up, x);
+    bad += ne(uxs.x, uxp.x) + ne(uxs.y, uxp.y);
+    const float gamma = 0.01f, sub = 1.0e6f + 1.0e7f * std::fabs(nd(rng)), reg = (t & 1) ? 1.0e-4f : 0.f;
+    float a0, a1, b0, b1;
+    nlms_adapt_step<C, false>(x, w, us, ys, gamma, sub, reg, a0, a1);
+    nlms_adapt_step<C, true>(x, w, up, yp, gamma, sub, reg, b0, b1);
+    bad += ne(a0, b0) + ne(a1, b1);
+    for (int c = 0; c < C; c++) bad += ne(us[c].x, up[c].x) + ne(us[c].y, up[c].y);
+  }
+  return bad;
+}
 
 static int regs_differ = 0;
 
@@ -94,11 +122,14 @@ static int run(unsigned seed) {
     bad += ne(f2_sub_ib<-1>(a, b), csub(a, mul_si<-1>(b)));
     bad += ne(f2_scale(a, sc), make_float2(a.x * sc, a.y * sc));
     bad += ne(f2_fma(a, b, make_float2(sc, -sc)), make_float2(fmaf(a.x, b.x, sc), fmaf(a.y, b.y, -sc)));
+    { float2 r1 = make_float2(sc, -sc), r2 = r1; cmac(r1, a, b); bad += ne(f2_cmac(r2, a, b), r1); }              // btkb_nlms_math.cuh cmac
+    { float2 r1 = make_float2(sc, -sc), r2 = r1; cmac_conj(r1, a, b); bad += ne(f2_cmac_conj(r2, a, b), r1); }    // ... cmac_conj
     // the untangle of k_analysis_r1: A = (zk + conj zm)/2, B = (zk - conj zm)/(2i), exactly as the scalar kernel writes them
     bad += ne(f2_scale(f2_add_conj(a, b), 0.5f), make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y)));
     bad += ne(f2_scale_mi(f2_sub_conj(a, b), 0.5f), make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x)));
   }
-  printf("fold %a primitives %d regs_differ %d\n", dmax, bad, regs_differ);
+  const int nl = nlms_mismatches<2>(seed) + nlms_mismatches<4>(seed + 1) + nlms_mismatches<8>(seed + 2);
+  printf("fold %a primitives %d regs_differ %d nlms %d\n", dmax, bad, regs_differ, nl);
   return 0;
 }
 

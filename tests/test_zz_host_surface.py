@@ -584,8 +584,8 @@ def test_batch_front_end_configured_from_the_references_parameter_files():
 @UNVERIFIED
 @pytest.mark.parametrize("M", [256, 512, 1024])
 def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
-    """BTKB_ANALYSIS_PACKED=1 / BTKB_SYNTHESIS_PACKED=1 select the FADD2 / FMUL2 / FFMA2 variants of k_analysis_r1 / k_synthesis_fast
-    (csrc/btkb_f2.cuh).  They perform the same IEEE operations per component, so snapshots, subband output and time signal must equal
+    """BTKB_ANALYSIS_PACKED=1 / BTKB_SYNTHESIS_PACKED=1 / BTKB_PERBIN_PACKED=1 select the FADD2 / FMUL2 / FFMA2 variants of k_analysis_r1,
+    k_synthesis_fast and the NLMS recurrence of k_perbin (csrc/btkb_f2.cuh).  They perform the same IEEE operations per component, so snapshots, subband output and time signal must equal
     the default kernels' BIT FOR BIT (the CPU run of the same source says so: tests/test_fft_packed_host.py) — on a ragged batch, and
     for the analysis bank also with an odd channel count (the unpaired last channel)."""
     import os
@@ -598,7 +598,7 @@ def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
     res = {}
     try:
         for tag, env in (("default", "0"), ("packed", "1")):
-            os.environ["BTKB_ANALYSIS_PACKED"] = env; os.environ["BTKB_SYNTHESIS_PACKED"] = env
+            os.environ["BTKB_ANALYSIS_PACKED"] = env; os.environ["BTKB_SYNTHESIS_PACKED"] = env; os.environ["BTKB_PERBIN_PACKED"] = env
             p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=8), max_utterances=U, max_samples=n)
             p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
             out = [p.fetch_snapshots(), p.fetch_subband(), p.fetch_time()]
@@ -609,7 +609,7 @@ def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
             p.close()
             res[tag] = out
     finally:
-        os.environ.pop("BTKB_ANALYSIS_PACKED", None); os.environ.pop("BTKB_SYNTHESIS_PACKED", None)
+        os.environ.pop("BTKB_ANALYSIS_PACKED", None); os.environ.pop("BTKB_SYNTHESIS_PACKED", None); os.environ.pop("BTKB_PERBIN_PACKED", None)
     for a, b in zip(res["default"], res["packed"]):
         assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
     assert np.abs(res["default"][0]).max() > 0 and np.abs(res["default"][2]).max() > 0

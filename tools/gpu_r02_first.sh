@@ -9,9 +9,9 @@ timeout 600 python tools/parity_report_kinect.py > gpurun_out/parity_kinect.json
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 # A/B of the packed 2 x fp32 filter-bank kernels (bit-identical results; see tests/test_fft_packed_host.py)
-for v in "0 0" "1 0" "0 1" "1 1"; do set -- $v
-  echo "== BTKB_ANALYSIS_PACKED=$1 BTKB_SYNTHESIS_PACKED=$2"
-  BTKB_ANALYSIS_PACKED=$1 BTKB_SYNTHESIS_PACKED=$2 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_packed_$1$2.json | python -c "
+for v in "0 0 0" "1 0 0" "0 1 0" "0 0 1" "1 1 1"; do set -- $v
+  echo "== BTKB_ANALYSIS_PACKED=$1 BTKB_SYNTHESIS_PACKED=$2 BTKB_PERBIN_PACKED=$3"
+  BTKB_ANALYSIS_PACKED=$1 BTKB_SYNTHESIS_PACKED=$2 BTKB_PERBIN_PACKED=$3 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_packed_$1$2$3.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','kernel_ms_per_step')}, d['roofline']['all_kernels_frac'], d['e2e']['ms_per_step'])"
 done
