@@ -153,6 +153,15 @@ BTKB_F2 float2 f2_add_cmulc(float2 k, float2 e, float2 q) {
   return make_float2(fmaf(e.y, q.y, fmaf(e.x, q.x, k.x)), fmaf(-e.x, q.y, fmaf(e.y, q.x, k.y)));
 #endif
 }
+// a conj(b), the roundings of btkb::cmulc:  x: fma(a.x, b.x, a.y b.y)     y: fma(a.y, b.x, (-a.x) b.y)
+BTKB_F2 float2 f2_cmulc(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  const f2raw t = f2_mul_raw(f2_pk(a.y, -a.x), f2_pk(b.y, b.y));
+  return f2_upk(f2_fma_raw(f2_pk(a.x, a.y), f2_pk(b.x, b.x), t));
+#else
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, (-a.x) * b.y));
+#endif
+}
 // complex product, the roundings of btkb::cmul: (fma(a.x, w.x, -(a.y w.y)), fma(a.x, w.y, a.y w.x))
 BTKB_F2 float2 f2_cmul(float2 a, float2 w) {
 #if defined(__CUDA_ARCH__)

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "btkb_f2.cuh"
+#include "btkb_fft.cuh"   // cmulc
 
 namespace btkb {
 
@@ -74,6 +75,44 @@ __device__ __forceinline__ void nlms_adapt_step(const float2* x, const float2* w
       uw[c] = make_float2(unx, uny);
       n20 = fmaf(unx, unx, n20); n21 = fmaf(uny, uny, n21);
     }
+  }
+}
+
+// One frame of the Zelinski post-filter's statistics (ZelinskiFilter_f, btk20_src/postfilter/postfilter.cc:57-140): time-aligned
+// snapshot z_c = x_c conj(ta_c), recursive cross-spectral densities phi_ij <- al phi_ij + (1 - al) z_i conj(z_j) over the C(C-1)/2 pairs
+// (summed into s), recursive power spectral densities (summed into den).  `live` is false past the end of the utterance: the state
+// is then left untouched.
+template <int C, bool PK>
+__device__ __forceinline__ void zelinski_csd_step(const float2* x, const float2* ta, float2* csd, float* psd, float al, bool live, float2& s, float& den) {
+  float2 z[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) z[c] = PK ? f2_cmulc(x[c], ta[c]) : cmulc(x[c], ta[c]);
+  s = make_float2(0.f, 0.f);
+  den = 0.f;
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < C - 1; i++)
+#pragma unroll
+    for (int j = i + 1; j < C; j++) {
+      if constexpr (PK) {
+        const float2 zz = f2_cmulc(z[i], z[j]);
+        const float2 ph = (al > 0.f) ? f2_fma_s(csd[idx], al, f2_scale(zz, 1.f - al)) : zz;
+        if (live) csd[idx] = ph;
+        s = f2_add(s, ph);
+      } else {
+      float2 zz = cmulc(z[i], z[j]);
+      float2 ph = (al > 0.f) ? make_float2(fmaf(al, csd[idx].x, (1.f - al) * zz.x), fmaf(al, csd[idx].y, (1.f - al) * zz.y)) : zz;
+      if (live) csd[idx] = ph;
+      s.x += ph.x; s.y += ph.y;
+      }
+      idx++;
+    }
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    float pz = fmaf(z[c].x, z[c].x, z[c].y * z[c].y);
+    float ps = (al > 0.f) ? fmaf(al, psd[c], (1.f - al) * pz) : pz;
+    if (live) psd[c] = ps;
+    den += ps;
   }
 }
 

@@ -208,11 +208,13 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
     } else if constexpr (PF == 1) {
       // ZelinskiFilter_f (postfilter.cc:57-140); alpha = 0 for the first two frames (postfilter.cc:460-463)
       const float al = (t >= 2) ? a.pf_alpha : 0.f;
+      float2 s = make_float2(0.f, 0.f);
+      float den = 0.f;
+      if constexpr (PK) zelinski_csd_step<C, true>(x, ta, csd, psd, al, live, s, den);   // btkb_nlms_math.cuh (its PK = false branch is this code)
+      else {
       float2 z[C];
 #pragma unroll
       for (int c = 0; c < C; c++) z[c] = cmulc(x[c], ta[c]);
-      float2 s = make_float2(0.f, 0.f);
-      float den = 0.f;
       int idx = 0;
 #pragma unroll
       for (int i = 0; i < C - 1; i++)
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
         float ps = (al > 0.f) ? fmaf(al, psd[c], (1.f - al) * pz) : pz;
         if (live) psd[c] = ps;
         den += ps;
+      }
       }
       float num = (a.pf_type & 1) ? fmaxf(s.x, 0.f) : sqrtf(fmaf(s.x, s.x, s.y * s.y));
       float Wf = (num / den) * (2.0f / ((float)C - 1.0f));
@@ -560,7 +563,17 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
     }
     BTKB_LAUNCH(MODE_LMS, 0);
   }
-  if (pf == BTKB_PF_ZELINSKI) BTKB_LAUNCH(MODE_STATIC, 1);
+  if (pf == BTKB_PF_ZELINSKI) {
+    const char* ev = getenv("BTKB_PERBIN_PACKED");   // =1: packed 2 x fp32 CSD recursions (bit-identical; off by default)
+    if (ev && atoi(ev) != 0) {
+      auto kern = k_perbin<C, MODE_STATIC, 1, true>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kern<<<grid, TILE, smem, st>>>(tm, a);
+      return cudaGetLastError();
+    }
+    BTKB_LAUNCH(MODE_STATIC, 1);
+  }
   if (pf == BTKB_PF_MCCOWAN) { if (!a.PFQ) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 2); }
   if (pf == BTKB_PF_LEFKIMMIATIS) { if (!a.PFQ || !a.LAM) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 3); }
   BTKB_LAUNCH(MODE_STATIC, 0);

@@ -49,6 +49,34 @@ static int nlms_mismatches(unsigned seed) {
   return bad;
 }
 
+// The Zelinski post-filter's per-frame statistics (btkb_nlms_math.cuh zelinski_csd_step): 30 frames, alpha = 0 for the first two,
+// the last three past the end of the utterance (live = false); CSDs, PSDs and the two sums must agree bit for bit.
+template <int C>
+static int zelinski_mismatches(unsigned seed) {
+  std::mt19937 rng(seed);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  auto ne = [](float a, float b) { unsigned x, y; std::memcpy(&x, &a, 4); std::memcpy(&y, &b, 4); return x != y; };
+  constexpr int NP = C * (C - 1) / 2;
+  int bad = 0;
+  float2 ta[C], cs[NP], cp[NP];
+  float ps[C], pp[C];
+  for (int c = 0; c < C; c++) { const float ph = 3.f * nd(rng); ta[c] = make_float2(std::cos(ph) / C, std::sin(ph) / C); ps[c] = pp[c] = 0.f; }
+  for (int i = 0; i < NP; i++) cs[i] = cp[i] = make_float2(0.f, 0.f);
+  for (int t = 0; t < 30; t++) {
+    float2 x[C];
+    for (int c = 0; c < C; c++) x[c] = make_float2(3000.f * nd(rng), 3000.f * nd(rng));
+    const float al = (t >= 2) ? 0.7f : 0.f;
+    const bool live = t < 27;
+    float2 s0, s1; float d0, d1;
+    zelinski_csd_step<C, false>(x, ta, cs, ps, al, live, s0, d0);
+    zelinski_csd_step<C, true>(x, ta, cp, pp, al, live, s1, d1);
+    bad += ne(s0.x, s1.x) + ne(s0.y, s1.y) + ne(d0, d1);
+    for (int i = 0; i < NP; i++) bad += ne(cs[i].x, cp[i].x) + ne(cs[i].y, cp[i].y);
+    for (int c = 0; c < C; c++) bad += ne(ps[c], pp[c]);
+  }
+  return bad;
+}
+
 static int regs_differ = 0;
 
 template <int M, int SIGN, bool PK>
@@ -122,13 +150,15 @@ static int run(unsigned seed) {
     bad += ne(f2_sub_ib<-1>(a, b), csub(a, mul_si<-1>(b)));
     bad += ne(f2_scale(a, sc), make_float2(a.x * sc, a.y * sc));
     bad += ne(f2_fma(a, b, make_float2(sc, -sc)), make_float2(fmaf(a.x, b.x, sc), fmaf(a.y, b.y, -sc)));
+    bad += ne(f2_cmulc(a, b), cmulc(a, b));
     { float2 r1 = make_float2(sc, -sc), r2 = r1; cmac(r1, a, b); bad += ne(f2_cmac(r2, a, b), r1); }              // btkb_nlms_math.cuh cmac
     { float2 r1 = make_float2(sc, -sc), r2 = r1; cmac_conj(r1, a, b); bad += ne(f2_cmac_conj(r2, a, b), r1); }    // ... cmac_conj
     // the untangle of k_analysis_r1: A = (zk + conj zm)/2, B = (zk - conj zm)/(2i), exactly as the scalar kernel writes them
     bad += ne(f2_scale(f2_add_conj(a, b), 0.5f), make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y)));
     bad += ne(f2_scale_mi(f2_sub_conj(a, b), 0.5f), make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x)));
   }
-  const int nl = nlms_mismatches<2>(seed) + nlms_mismatches<4>(seed + 1) + nlms_mismatches<8>(seed + 2);
+  const int nl = nlms_mismatches<2>(seed) + nlms_mismatches<4>(seed + 1) + nlms_mismatches<8>(seed + 2) + zelinski_mismatches<2>(seed + 3) +
+                 zelinski_mismatches<4>(seed + 4) + zelinski_mismatches<8>(seed + 5);
   printf("fold %a primitives %d regs_differ %d nlms %d\n", dmax, bad, regs_differ, nl);
   return 0;
 }

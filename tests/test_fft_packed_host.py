@@ -8,7 +8,8 @@ fp64; (2) the packed path — the reformulated radix-4 / radix-8 butterflies (mu
 two-instruction complex product, and the "base + compile-time offset" forms of the three shared-memory layouts — reproduces the
 scalar path BIT FOR BIT; (3) every packed primitive equals the scalar expression it replaces on 20 000 random operands, and the
 packed polyphase MAC equals the scalar one exactly; (4) the NLMS recurrence of the per-bin kernel (csrc/btkb_nlms_math.cuh: Yc = v^H x,
-u.x, the projector step and the leaky update, C = 2, 4, 8) carried over 40 frames gives bit-identical states in both forms.
+u.x, the projector step and the leaky update, C = 2, 4, 8) carried over 40 frames, and the Zelinski post-filter's cross-spectral
+density recursions over 30 frames, give bit-identical states in both forms.
 Test infrastructure only: the product has no CPU path."""
 import os
 import subprocess
@@ -46,4 +47,4 @@ def test_device_fft_source_on_the_cpu_scalar_and_packed(harness, M, sign):
     tail = out[-1].split()
     assert tail[0] == "fold" and float.fromhex(tail[1]) == 0.0 and tail[2] == "primitives" and int(tail[3]) == 0
     assert tail[4] == "regs_differ" and int(tail[5]) == 0      # after the last pass every thread still holds its eight outputs in registers
-    assert tail[6] == "nlms" and int(tail[7]) == 0             # 40 NLMS adaptation steps (C = 2, 4, 8), scalar vs packed: identical states
+    assert tail[6] == "nlms" and int(tail[7]) == 0             # 40 NLMS adaptation steps and 30 Zelinski CSD frames (C = 2, 4, 8), scalar vs packed: identical states
