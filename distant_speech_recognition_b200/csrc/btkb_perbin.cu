@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUt
   }
 }
 
-template <int C>
+template <int C, bool PK = false>   // PK: x_i conj(x_j) and its accumulation as 3 packed instructions instead of 6 (BTKB_PERBIN_PACKED=1)
 __global__ void __launch_bounds__(TILE) k_covariance(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int g0 = blockIdx.x * TILE;
@@ -457,7 +457,11 @@ __global__ void __launch_bounds__(TILE) k_covariance(const __grid_constant__ CUt
       for (int i = 0; i < C; i++) {
         dg[i] = fmaf(x[i].x, x[i].x, fmaf(x[i].y, x[i].y, dg[i]));
 #pragma unroll
-        for (int j = i + 1; j < C; j++) { float2 p = cmulc(x[i], x[j]); off[idx].x += p.x; off[idx].y += p.y; idx++; }
+        for (int j = i + 1; j < C; j++) {
+          if constexpr (PK) off[idx] = f2_add(off[idx], f2_cmulc(x[i], x[j]));
+          else { float2 p = cmulc(x[i], x[j]); off[idx].x += p.x; off[idx].y += p.y; }
+          idx++;
+        }
       }
     }
   }
@@ -593,7 +597,8 @@ cudaError_t launch_perbin(const PerBinArgs& a, cudaStream_t st) {
 template <int C>
 static cudaError_t launch_cov_c(const PerBinArgs& a, cudaStream_t st) {
   const size_t smem = ring_smem<C>();
-  auto kern = k_covariance<C>;
+  const char* ev = getenv("BTKB_PERBIN_PACKED");
+  auto kern = (ev && atoi(ev) != 0) ? k_covariance<C, true> : k_covariance<C, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   CUtensorMap tm;

@@ -607,6 +607,11 @@ def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
             p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)      # static GSC + Zelinski (packed CSD recursions)
             out += [p.fetch_subband(), p.fetch_time(), p.get_postfilter_weights()]
             p.close()
+            p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=U, max_samples=n)
+            p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run_analysis()
+            p.accumulate_covariance(labels=np.tile([0.1, 0.3], (U, 1)), energy_threshold=10.0)      # SMI covariance (packed x_i conj(x_j) accumulation)
+            out.append(p.get_covariance())
+            p.close()
             p = capi.Pipeline(3, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
             p.set_prototypes(h, g); p.submit(np.ascontiguousarray(x[:, :3]), lengths); p.run_analysis()
             out.append(p.fetch_snapshots())
