@@ -162,16 +162,22 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
       const float be = 1.0f - al;
       float2 z[C];
 #pragma unroll
-      for (int c = 0; c < C; c++) z[c] = cmulc(x[c], ta[c]);
+      for (int c = 0; c < C; c++) z[c] = PK ? f2_cmulc(x[c], ta[c]) : cmulc(x[c], ta[c]);
       float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
       int idx = 0;
 #pragma unroll
       for (int i = 0; i < C - 1; i++)
 #pragma unroll
         for (int j = i + 1; j < C; j++) {
+          if constexpr (PK) {
+            const float2 zz = f2_cmulc(z[i], z[j]);
+            a1 = f2_cmac(a1, zz, pfc[idx * TILE]);
+            if (PF == 3) a2 = f2_cmac(a2, zz, pfc[(NP + C + idx) * TILE]);
+          } else {
           const float2 zz = cmulc(z[i], z[j]);
           cmac(a1, zz, pfc[idx * TILE]);
           if (PF == 3) cmac(a2, zz, pfc[(NP + C + idx) * TILE]);
+          }
           idx++;
         }
       const float2 s1 = (al > 0.f) ? make_float2(fmaf(al, S1.x, be * a1.x), fmaf(al, S1.y, be * a1.y)) : a1;
@@ -578,8 +584,20 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
     }
     BTKB_LAUNCH(MODE_STATIC, 1);
   }
-  if (pf == BTKB_PF_MCCOWAN) { if (!a.PFQ) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 2); }
-  if (pf == BTKB_PF_LEFKIMMIATIS) { if (!a.PFQ || !a.LAM) return cudaErrorInvalidValue; BTKB_LAUNCH(MODE_STATIC, 3); }
+  const char* evp = getenv("BTKB_PERBIN_PACKED");
+  const bool pk = evp && atoi(evp) != 0;
+#define BTKB_LAUNCH_PK(PF_)                                                                      \
+  do {                                                                                           \
+    auto kern = k_perbin<C, MODE_STATIC, PF_, true>;                                             \
+    const size_t sm = smem + ((PF_) == 3 ? 2 * (NPAIR + C) : (NPAIR + C)) * TILE * sizeof(float2); \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    if (e != cudaSuccess) return e;                                                              \
+    kern<<<grid, TILE, sm, st>>>(tm, a);                                                         \
+    return cudaGetLastError();                                                                   \
+  } while (0)
+  if (pf == BTKB_PF_MCCOWAN) { if (!a.PFQ) return cudaErrorInvalidValue; if (pk) BTKB_LAUNCH_PK(2); BTKB_LAUNCH(MODE_STATIC, 2); }
+  if (pf == BTKB_PF_LEFKIMMIATIS) { if (!a.PFQ || !a.LAM) return cudaErrorInvalidValue; if (pk) BTKB_LAUNCH_PK(3); BTKB_LAUNCH(MODE_STATIC, 3); }
+#undef BTKB_LAUNCH_PK
   BTKB_LAUNCH(MODE_STATIC, 0);
 #undef BTKB_LAUNCH
 }

@@ -607,6 +607,13 @@ def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
             p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)      # static GSC + Zelinski (packed CSD recursions)
             out += [p.fetch_subband(), p.fetch_time(), p.get_postfilter_weights()]
             p.close()
+            mpos = np.stack([40.0 * (np.arange(8) - 3.5), np.zeros(8), np.zeros(8)], axis=1)
+            for pfk in (capi.PF_MCCOWAN, capi.PF_LEFKIMMIATIS):                                       # packed pair sums of the coherence-based post-filters
+                p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_DS, postfilter=pfk, pf_alpha=0.7, pf_type=2, max_utterances=U, max_samples=n)
+                p.set_prototypes(h, g); p.set_delays(d); p.pf_set_diffuse_noise_model(mpos, 16000.0); p.pf_set_diagonal_loading(0.05)
+                p.submit(x, lengths); p.run(True)
+                out += [p.fetch_subband(), p.get_postfilter_weights()]
+                p.close()
             p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=U, max_samples=n)
             p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run_analysis()
             p.accumulate_covariance(labels=np.tile([0.1, 0.3], (U, 1)), energy_threshold=10.0)      # SMI covariance (packed x_i conj(x_j) accumulation)
