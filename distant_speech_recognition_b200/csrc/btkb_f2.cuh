@@ -6,7 +6,8 @@
 // operand modifiers (checked with cuobjdump on this toolchain, nvcc 12.9):
 //     R.F32            one register broadcast to both halves          (scaling a complex value by a real tap / twiddle part)
 //     R.F32x2.LO_HI    the pair with its halves swapped               (multiplication by +-i)
-//     -R.F32x2...NP    negation of one half only                      (conjugation, the cross terms of a complex product)
+//     [-]R.F32x2...NP  negation of one half only                      (conjugation, the cross terms of a complex product; accepted on
+//                      the first multiplicand and on the addend, NOT on the second multiplicand — see f2_cmac)
 // so a complex add is 1 instruction instead of 2, a complex multiply 2 instead of 4, "a + i b" 1 instead of 2 — with NO extra
 // registers and no data movement: the float2 values are already even/odd register pairs.
 //
@@ -118,8 +119,10 @@ BTKB_F2 float2 f2_scale_mi(float2 d, float s) {
 // acc + a b:        x: fma(a.y, -b.y, fma(a.x, b.x, acc.x))     y: fma(a.y, b.x, fma(a.x, b.y, acc.y))
 BTKB_F2 float2 f2_cmac(float2 acc, float2 a, float2 b) {
 #if defined(__CUDA_ARCH__)
-  const f2raw t = f2_fma_raw(f2_pk(a.x, a.x), f2_pk(b.x, b.y), f2_pk(acc.x, acc.y));
-  return f2_upk(f2_fma_raw(f2_pk(a.y, a.y), f2_pk(-b.y, b.x), t));
+  // (the swapped / half-negated pair goes FIRST: ptxas folds those patterns into modifiers of the first multiplicand only, a
+  // pair in the second slot is rebuilt with a MOV and an FADD per use; the broadcast is accepted in either slot)
+  const f2raw t = f2_fma_raw(f2_pk(b.x, b.y), f2_pk(a.x, a.x), f2_pk(acc.x, acc.y));
+  return f2_upk(f2_fma_raw(f2_pk(-b.y, b.x), f2_pk(a.y, a.y), t));
 #else
   return make_float2(fmaf(a.y, -b.y, fmaf(a.x, b.x, acc.x)), fmaf(a.y, b.x, fmaf(a.x, b.y, acc.y)));
 #endif
@@ -137,8 +140,8 @@ BTKB_F2 float2 f2_cmac_conj(float2 acc, float2 a, float2 b) {
 //                   x: fma(-c.x, v.x, fma(c.y, v.y, x.x))       y: fma(-c.x, v.y, fma(c.y, -v.x, x.y))
 BTKB_F2 float2 f2_sub_cmul(float2 x, float2 c, float2 v) {
 #if defined(__CUDA_ARCH__)
-  const f2raw t = f2_fma_raw(f2_pk(c.y, c.y), f2_pk(v.y, -v.x), f2_pk(x.x, x.y));
-  return f2_upk(f2_fma_raw(f2_pk(-c.x, -c.x), f2_pk(v.x, v.y), t));
+  const f2raw t = f2_fma_raw(f2_pk(v.y, -v.x), f2_pk(c.y, c.y), f2_pk(x.x, x.y));
+  return f2_upk(f2_fma_raw(f2_pk(v.x, v.y), f2_pk(-c.x, -c.x), t));
 #else
   return make_float2(fmaf(-c.x, v.x, fmaf(c.y, v.y, x.x)), fmaf(-c.x, v.y, fmaf(c.y, -v.x, x.y)));
 #endif
