@@ -118,6 +118,10 @@ static int run(unsigned seed) {
   std::normal_distribution<float> nd(0.f, 3000.f);
   std::vector<float2> in0(M), in1(M), tab(M);
   for (int i = 0; i < M; i++) { in0[i] = make_float2(nd(rng), nd(rng)); in1[i] = make_float2(nd(rng), nd(rng)); }
+  if (seed < 3) {   // silent and almost silent frames: all (signed) zeros, or one sample: the zeros of the spectrum must keep their signs too
+    for (int i = 0; i < M; i++) { in0[i] = make_float2(seed == 1 ? -0.f : 0.f, 0.f); in1[i] = make_float2(0.f, (i & 1) ? -0.f : 0.f); }
+    if (seed == 2) { in0[3] = make_float2(1000.f, 0.f); in1[M - 1] = make_float2(0.f, -7.f); }
+  }
   for (int i = 0; i < M; i++) { const double a = 2.0 * M_PI * i / M; tab[i] = make_float2((float)std::cos(a), (float)std::sin(a)); }   // btkb_api.cu:207-214
   std::vector<float2> s0, s1, p0, p1;
   run_pair<M, SIGN, false>(in0, in1, tab, s0, s1);
@@ -138,8 +142,13 @@ static int run(unsigned seed) {
   // every primitive against the scalar expression it replaces
   int bad = 0;
   for (int trial = 0; trial < 20000; trial++) {
-    const float2 a = make_float2(nd(rng), nd(rng)), b = make_float2(nd(rng), nd(rng));
-    const float sc = nd(rng);
+    float2 a = make_float2(nd(rng), nd(rng)), b = make_float2(nd(rng), nd(rng));
+    float sc = nd(rng);
+    if (trial < 4096) {   // signed zeros in every combination (silent / zero-padded frames): the packed forms must keep the SIGN of a zero too
+      const float z[4] = {0.f, -0.f, 1.5f, -2.25f};
+      a = make_float2(z[trial & 3], z[(trial >> 2) & 3]); b = make_float2(z[(trial >> 4) & 3], z[(trial >> 6) & 3]);
+      sc = z[(trial >> 8) & 3] * ((trial >> 10) & 1 ? 1.f : 0.5f) + (((trial >> 11) & 1) ? 0.f : 0.f);
+    }
     auto ne = [&](float2 x, float2 y) { return bits(x.x) != bits(y.x) || bits(x.y) != bits(y.y); };
     bad += ne(f2_add(a, b), cadd(a, b));
     bad += ne(f2_sub(a, b), csub(a, b));

@@ -33,8 +33,9 @@ def harness(tmp_path_factory):
 
 @pytest.mark.parametrize("M", [256, 512, 1024, 2048])
 @pytest.mark.parametrize("sign", [+1, -1])
-def test_device_fft_source_on_the_cpu_scalar_and_packed(harness, M, sign):
-    out = subprocess.run([harness, str(M), str(sign), str(100 + M + sign)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+@pytest.mark.parametrize("seed", [0, 1, 2, 1000])      # 0, 1: silent frames (signed zeros); 2: a single sample; otherwise Gaussian noise
+def test_device_fft_source_on_the_cpu_scalar_and_packed(harness, M, sign, seed):
+    out = subprocess.run([harness, str(M), str(sign), str(seed + (M + sign if seed >= 3 else 0))], capture_output=True, text=True, check=True).stdout.strip().split("\n")
     rows = np.array([[float.fromhex(v) for v in ln.split()] for ln in out[:2 * M]])
     x = [rows[:M, 0] + 1j * rows[:M, 1], rows[:M, 2] + 1j * rows[:M, 3]]
     S = rows[M:]
@@ -42,8 +43,8 @@ def test_device_fft_source_on_the_cpu_scalar_and_packed(harness, M, sign):
         # SIGN = +1: gsl_fft_complex_radix2_backward (unnormalised e^{+2 pi i nk/M}, modulated.cc:396); -1: ..._forward (modulated.cc:559)
         ref = np.fft.ifft(x[i]) * M if sign > 0 else np.fft.fft(x[i])
         got = S[:, 2 * i] + 1j * S[:, 2 * i + 1]
-        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 3e-7
-    assert np.array_equal(S[:, :4], S[:, 4:])                       # packed == scalar, bit for bit (values printed as hex floats)
+        assert np.linalg.norm(got - ref) <= 3e-7 * np.linalg.norm(ref)
+    assert np.array_equal(S[:, :4], S[:, 4:]) and np.array_equal(np.signbit(S[:, :4]), np.signbit(S[:, 4:]))   # packed == scalar, bit for bit (hex floats), zeros with their signs
     tail = out[-1].split()
     assert tail[0] == "fold" and float.fromhex(tail[1]) == 0.0 and tail[2] == "primitives" and int(tail[3]) == 0
     assert tail[4] == "regs_differ" and int(tail[5]) == 0      # after the last pass every thread still holds its eight outputs in registers
