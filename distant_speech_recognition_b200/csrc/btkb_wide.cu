@@ -15,6 +15,7 @@
 #include "btkb_tensor_map.h"
 #include "btkb_fft.cuh"
 #include "../../include/btkb.h"
+#include <cstdlib>
 
 namespace btkb {
 namespace wide {
@@ -57,7 +58,9 @@ __device__ __forceinline__ void macc(float2& acc, float2 a, float2 b) {  // a co
 }
 
 // MODE 0: static weights; MODE 1: NLMS
-template <int L, int MODE>
+// PK = true (BTKB_PERBIN_PACKED=1, off by default): the complex MACs, the projector step and the update as FFMA2 pairs (btkb_f2.cuh);
+// the two norm chains keep their scalar single-accumulator order, so the results stay bit-identical.
+template <int L, int MODE, bool PK = false>
 __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
   constexpr int C = 8 * L;
   constexpr int NTH = TC * L;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ C
     if (MODE == 1 && t + 1 < T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
     float2 y = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; i++) macc(y, x[i], w[i]);
+    for (int i = 0; i < 8; i++) { if constexpr (PK) y = f2_cmac_conj(y, x[i], w[i]); else macc(y, x[i], w[i]); }
     y = red2<L>(y, gm);
     const bool live = t < Tu;
     if (MODE == 1) {
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ C
       if (adapt && live) {   // uniform over the L lanes of a chain
         float2 ux = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 8; i++) mac(ux, uw[i], x[i]);
+        for (int i = 0; i < 8; i++) { if constexpr (PK) ux = f2_cmac(ux, uw[i], x[i]); else mac(ux, uw[i], x[i]); }
         ux = red2<L>(ux, gm);
         const float2 epa = csub(y, ux);
         const float alphaK = gamma / sub;
@@ -161,6 +164,13 @@ __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ C
         float n2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
+          if constexpr (PK) {
+            const float2 q = f2_sub_cmul(x[i], cy, w[i]);
+            const float2 un = f2_add_cmulc(f2_scale(uw[i], keep), ea, q);
+            uw[i] = un;
+            n2 = fmaf(un.x, un.x, fmaf(un.y, un.y, n2));
+            continue;
+          }
           const float qx = fmaf(-cy.x, w[i].x, fmaf(cy.y, w[i].y, x[i].x));
           const float qy = fmaf(-cy.x, w[i].y, fmaf(-cy.y, w[i].x, x[i].y));
           const float unx = fmaf(ea.y, qy, fmaf(ea.x, qx, keep * uw[i].x));
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ C
         if (n2 > a.lms.max_wa_l2norm) {
           const float cK = sqrtf(a.lms.max_wa_l2norm / n2);
 #pragma unroll
-          for (int i = 0; i < 8; i++) { uw[i].x *= cK; uw[i].y *= cK; }
+          for (int i = 0; i < 8; i++) { if constexpr (PK) uw[i] = f2_scale(uw[i], cK); else { uw[i].x *= cK; uw[i].y *= cK; } }
         }
         se = sub;
         n_updates++;
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ C
       if (t >= a.lms.min_frames) {
         float2 ux = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 8; i++) mac(ux, uw[i], x[i]);
+        for (int i = 0; i < 8; i++) { if constexpr (PK) ux = f2_cmac(ux, uw[i], x[i]); else mac(ux, uw[i], x[i]); }
         ux = red2<L>(ux, gm);
         y = csub(y, ux);
       }
@@ -331,7 +341,14 @@ static cudaError_t launch_wide_l(const PerBinArgs& a, cudaStream_t st) {
   cudaError_t e = make_map_wide(&tm, a, C);
   if (e != cudaSuccess) return e;
   const int grid = (a.G + TC - 1) / TC;
-  if (a.kind == BTKB_BF_GSC_LMS) {
+  const char* ev = getenv("BTKB_PERBIN_PACKED");
+  const bool pk = ev && atoi(ev) != 0;
+  if (pk) {
+    auto kern = (a.kind == BTKB_BF_GSC_LMS) ? k_perbin_wide<L, 1, true> : k_perbin_wide<L, 0, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TC * L, smem, st>>>(tm, a);
+  } else if (a.kind == BTKB_BF_GSC_LMS) {
     auto kern = k_perbin_wide<L, 1>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -619,6 +619,12 @@ def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
             p.accumulate_covariance(labels=np.tile([0.1, 0.3], (U, 1)), energy_threshold=10.0)      # SMI covariance (packed x_i conj(x_j) accumulation)
             out.append(p.get_covariance())
             p.close()
+            if M == 512:                                                                                # the lane-split kernel for wide arrays (C = 16)
+                x16c, d16c = synthetic.make_batch(2, 16, 6000, first=90)
+                p = capi.Pipeline(16, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=8), max_utterances=2, max_samples=6000)
+                p.set_prototypes(h, g); p.set_delays(d16c); p.submit(x16c, np.array([6000, 4100], np.int32)); p.run(True)
+                out += [p.fetch_subband(), p.fetch_time()]
+                p.close()
             p = capi.Pipeline(3, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
             p.set_prototypes(h, g); p.submit(np.ascontiguousarray(x[:, :3]), lengths); p.run_analysis()
             out.append(p.fetch_snapshots())

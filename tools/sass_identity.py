@@ -12,7 +12,7 @@ import os, re, subprocess, sys, tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = sys.argv[1] if len(sys.argv) > 1 else "785f6fe"
-UNITS = ("btkb_analysis", "btkb_synthesis", "btkb_perbin")
+UNITS = ("btkb_analysis", "btkb_synthesis", "btkb_perbin", "btkb_wide")
 NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
 
@@ -32,6 +32,7 @@ def new_name(n):
     if "k_perbinI" in n:
         n = re.sub(r"(k_perbinILi\d+ELi\d+ELi\d+)E", r"\1ELb0E", n)
     n = re.sub(r"(k_covarianceILi\d+)E", r"\1ELb0E", n)
+    n = re.sub(r"(k_perbin_wideILi\d+ELi\d+)E", r"\1ELb0E", n)
     if "k_analysis_r1" in n:
         n = n.replace("EEEvNS_12AnalysisArgsE", "ELb0EEEvNS_12AnalysisArgsE")
     if "k_synthesis_fast" in n:
