@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
     float2 v0[8], v1[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { v0[i] = make_float2(0.f, 0.f); v1[i] = make_float2(0.f, 0.f); }
-    if (act0 && !(a.debug & 2)) {
+    if (act0 && (PK || !(a.debug & 2))) {   // (the ablation hooks of BTKB_ANALYSIS_DEBUG exist in the scalar variant only)
       const int base = f * D + MT * M - 1;
 #pragma unroll
       for (int q = 0; q < 8; q++)
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
     fft_first_pass<M, +1, PK>(v0, buf0, tg);
     fft_first_pass<M, +1, PK>(v1, buf1, tg);
     __syncthreads();
-    if (!(a.debug & 4)) {
+    if (PK || !(a.debug & 4)) {
       auto sync = [] { __syncthreads(); };
       FftPassChain<M, +1, 0, decltype(sync), PK>::run(v0, v1, buf0, buf1, tg, tw, sync);
     }
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
         const float2 zm = self ? zk : buf0[M - k];
         const float2 A = PK ? f2_scale(f2_add_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 B = PK ? f2_scale_mi(f2_sub_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-        if (!(a.debug & 1)) {
+        if (PK || !(a.debug & 1)) {
         a.X[((size_t)ta * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
         if (has_b) a.X[((size_t)ta * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
         }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
         const float2 zm = self ? zk : buf1[M - k];
         const float2 A = PK ? f2_scale(f2_add_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 B = PK ? f2_scale_mi(f2_sub_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-        if (!(a.debug & 1)) {
+        if (PK || !(a.debug & 1)) {
         a.X[((size_t)tb * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
         if (has_b) a.X[((size_t)tb * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
         }
