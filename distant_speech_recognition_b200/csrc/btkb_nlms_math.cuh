@@ -116,4 +116,119 @@ __device__ __forceinline__ void zelinski_csd_step(const float2* x, const float2*
   }
 }
 
+// ---- RLS sidelobe canceller (k_perbin_rls, btkb_perbin.cu; SubbandGSCRLSBeamformer.__iter__, lib/pybeamformer.py:817-901) ----
+template <int C>
+struct HermP {   // Hermitian C x C: d[i] real diagonal, o[idx(i,j)], i > j, lower triangle
+  float d[C];
+  float2 o[C * (C - 1) / 2 > 0 ? C * (C - 1) / 2 : 1];
+  __device__ __forceinline__ static constexpr int idx(int i, int j) { return i * (i - 1) / 2 + j; }  // i > j
+  __device__ __forceinline__ float2 get(int i, int j) const {
+    if (i == j) return make_float2(d[i], 0.f);
+    if (i > j) return o[idx(i, j)];
+    const float2 t = o[idx(j, i)];
+    return make_float2(t.x, -t.y);
+  }
+};
+
+// The always-executed part of one RLS adaptation step in the projector form (pybeamformer.py:835-849):
+//   x~ = x - C Yc v,  p = Pt x~,  ip = Re(x~^H p),  Pt <- (Pt - p p^H / (mu + ip)) / mu,
+//   un = u + gamma ep conj(p) / (mu + ip) - reg u Pt^H   (ep = Yc - u.x with the OLD u, the NEW Pt in the regularisation term).
+// The scalar form spells out the multiply-adds nvcc contracts (a - b c -> fma(b, -c, a)), so that the packed form — whose operations
+// are explicit instructions — rounds the same way on the device; the real chain `ip` and the real diagonal of Pt stay scalar in both.
+template <int C, bool PK>
+__device__ __forceinline__ void rls_core_step(const float2* x, const float2* w, const float2* uw, float2 y, HermP<C>& P, float mu, float inv_mu,
+                                                       float gamma, float reg, float2* un) {
+  float2 xt[C], pv[C];
+  if constexpr (PK) {
+    const float2 cy = f2_scale(y, (float)C);
+#pragma unroll
+    for (int c = 0; c < C; c++) xt[c] = f2_sub_cmul(x[c], cy, w[c]);
+#pragma unroll
+    for (int i = 0; i < C; i++) {
+      float2 s = f2_scale(xt[i], P.d[i]);
+#pragma unroll
+      for (int j = 0; j < C; j++) {
+        if (j == i) continue;
+        if (j < i) s = f2_cmac(s, P.o[HermP<C>::idx(i, j)], xt[j]);
+        else s = f2_cmac_conj(s, xt[j], P.o[HermP<C>::idx(j, i)]);   // conj(P_ji) x_j
+      }
+      pv[i] = s;
+    }
+  } else {
+    const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      xt[c] = make_float2(fmaf(-cy.x, w[c].x, fmaf(cy.y, w[c].y, x[c].x)), fmaf(-cy.x, w[c].y, fmaf(-cy.y, w[c].x, x[c].y)));
+#pragma unroll
+    for (int i = 0; i < C; i++) {
+      float2 s = make_float2(P.d[i] * xt[i].x, P.d[i] * xt[i].y);
+#pragma unroll
+      for (int j = 0; j < C; j++) {
+        if (j == i) continue;
+        if (j < i) cmac(s, P.o[HermP<C>::idx(i, j)], xt[j]);
+        else cmac_conj(s, xt[j], P.o[HermP<C>::idx(j, i)]);   // conj(P_ji) x_j
+      }
+      pv[i] = s;
+    }
+  }
+  float ip = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; c++) ip = fmaf(xt[c].x, pv[c].x, fmaf(xt[c].y, pv[c].y, ip));
+  const float inv = 1.0f / (mu + ip);
+  // Pt <- (Pt - p p^H inv) / mu
+#pragma unroll
+  for (int i = 0; i < C; i++) {
+    P.d[i] = fmaf(fmaf(pv[i].x, pv[i].x, pv[i].y * pv[i].y), -inv, P.d[i]) * inv_mu;
+#pragma unroll
+    for (int j = 0; j < i; j++) {
+      float2& e = P.o[HermP<C>::idx(i, j)];
+      if constexpr (PK) {
+        e = f2_scale(f2_fma_s(f2_cmulc(pv[i], pv[j]), -inv, e), inv_mu);
+      } else {
+        const float2 pp = cmulc(pv[i], pv[j]);  // p_i conj(p_j)
+        e.x = fmaf(pp.x, -inv, e.x) * inv_mu; e.y = fmaf(pp.y, -inv, e.y) * inv_mu;
+      }
+    }
+  }
+  const float2 ux = cdot<C, false, PK>(uw, x);
+  const float gi = gamma * inv;
+  if constexpr (PK) {
+    const float2 ge = f2_scale(f2_sub(y, ux), gi);
+#pragma unroll
+    for (int c = 0; c < C; c++) un[c] = f2_cmac_conj(uw[c], ge, pv[c]);   // u + gamma ep conj(p) inv
+  } else {
+    const float2 ep = make_float2(y.x - ux.x, y.y - ux.y);
+    const float2 ge = make_float2(gi * ep.x, gi * ep.y);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      un[c] = uw[c];
+      cmac_conj(un[c], ge, pv[c]);
+    }
+  }
+  if (reg > 0.f) {
+#pragma unroll
+    for (int c = 0; c < C; c++) {  // (u Pt^H)_c = sum_j u_j conj(Pt_cj)
+      if constexpr (PK) {
+        float2 s = f2_scale(uw[c], P.d[c]);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+          if (j == c) continue;
+          if (j < c) s = f2_cmac_conj(s, uw[j], P.o[HermP<C>::idx(c, j)]);
+          else s = f2_cmac(s, uw[j], P.o[HermP<C>::idx(j, c)]);         // conj(P_cj) = P_jc
+        }
+        un[c] = f2_fma_s(s, -reg, un[c]);
+      } else {
+        float2 s = make_float2(uw[c].x * P.d[c], uw[c].y * P.d[c]);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+          if (j == c) continue;
+          if (j < c) cmac_conj(s, uw[j], P.o[HermP<C>::idx(c, j)]);
+          else cmac(s, uw[j], P.o[HermP<C>::idx(j, c)]);         // conj(P_cj) = P_jc
+        }
+        un[c].x = fmaf(-reg, s.x, un[c].x); un[c].y = fmaf(-reg, s.y, un[c].y);
+      }
+    }
+  }
+}
+
 }  // namespace btkb

@@ -271,20 +271,10 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
 //   u  <- u + gamma ep p^H / (mu + ip) - reg u Pt^H      (ep = Yc - u.x with the OLD u, pybeamformer.py:843-847)
 //   |u|^2 > alpha2: quadratic constraint with va = Pt u^H (:851-861);  |u|^2 > max_wa_l2norm: rescale u and reset
 //   Pt = (I - C v v^H) / init_diagonal_load (:862-865).
-template <int C>
-struct HermP {   // Hermitian C x C: d[i] real diagonal, o[idx(i,j)], i > j, lower triangle
-  float d[C];
-  float2 o[C * (C - 1) / 2 > 0 ? C * (C - 1) / 2 : 1];
-  __device__ __forceinline__ static constexpr int idx(int i, int j) { return i * (i - 1) / 2 + j; }  // i > j
-  __device__ __forceinline__ float2 get(int i, int j) const {
-    if (i == j) return make_float2(d[i], 0.f);
-    if (i > j) return o[idx(i, j)];
-    const float2 t = o[idx(j, i)];
-    return make_float2(t.x, -t.y);
-  }
-};
-
-template <int C>
+// PK = true (BTKB_PERBIN_PACKED=1, off by default): the always-executed part of the update (projector step, p = Pt x~, the rank-one
+// update of Pt, the new u with its regularisation term) in packed 2 x fp32 instructions (rls_core_step, btkb_nlms_math.cuh; bit-identical,
+// checked on the CPU); the rarely taken constraint branches stay scalar.
+template <int C, bool PK = false>
 __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUtensorMap tmX, PerBinArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int g0 = blockIdx.x * TILE;
@@ -328,63 +318,12 @@ __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUt
     ring.fetch(t, a.T, x);
     const float energy = e_next;
     if (t + 1 < a.T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
-    float2 y = cdot<C, true>(x, w);   // Yc = v^H x
+    float2 y = cdot<C, true, PK>(x, w);   // Yc = v^H x
     const bool live = t < Tu;
     const bool adapt = energy > (Eavg * inv_sil);
     if (adapt && live) {
-      const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
-      float2 xt[C], pv[C];
-#pragma unroll
-      for (int c = 0; c < C; c++)
-        xt[c] = make_float2(fmaf(-cy.x, w[c].x, fmaf(cy.y, w[c].y, x[c].x)), fmaf(-cy.x, w[c].y, fmaf(-cy.y, w[c].x, x[c].y)));
-#pragma unroll
-      for (int i = 0; i < C; i++) {
-        float2 s = make_float2(P.d[i] * xt[i].x, P.d[i] * xt[i].y);
-#pragma unroll
-        for (int j = 0; j < C; j++) {
-          if (j == i) continue;
-          if (j < i) cmac(s, P.o[HermP<C>::idx(i, j)], xt[j]);
-          else cmac_conj(s, xt[j], P.o[HermP<C>::idx(j, i)]);   // conj(P_ji) x_j
-        }
-        pv[i] = s;
-      }
-      float ip = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; c++) ip = fmaf(xt[c].x, pv[c].x, fmaf(xt[c].y, pv[c].y, ip));
-      const float inv = 1.0f / (mu + ip);
-      // Pt <- (Pt - p p^H inv) / mu
-#pragma unroll
-      for (int i = 0; i < C; i++) {
-        P.d[i] = (P.d[i] - fmaf(pv[i].x, pv[i].x, pv[i].y * pv[i].y) * inv) * inv_mu;
-#pragma unroll
-        for (int j = 0; j < i; j++) {
-          float2& e = P.o[HermP<C>::idx(i, j)];
-          const float2 pp = cmulc(pv[i], pv[j]);  // p_i conj(p_j)
-          e.x = (e.x - pp.x * inv) * inv_mu; e.y = (e.y - pp.y * inv) * inv_mu;
-        }
-      }
-      const float2 ep = csub(y, cdot<C, false>(uw, x));
-      const float2 ge = make_float2(a.rls.gamma * inv * ep.x, a.rls.gamma * inv * ep.y);
       float2 un[C];
-#pragma unroll
-      for (int c = 0; c < C; c++) {  // u + gamma ep conj(p) inv
-        un[c] = uw[c];
-        cmac_conj(un[c], ge, pv[c]);
-      }
-      if (a.rls.regularization_param > 0.f) {
-        const float reg = a.rls.regularization_param;
-#pragma unroll
-        for (int c = 0; c < C; c++) {  // (u Pt^H)_c = sum_j u_j conj(Pt_cj)
-          float2 s = make_float2(uw[c].x * P.d[c], uw[c].y * P.d[c]);
-#pragma unroll
-          for (int j = 0; j < C; j++) {
-            if (j == c) continue;
-            if (j < c) cmac_conj(s, uw[j], P.o[HermP<C>::idx(c, j)]);
-            else cmac(s, uw[j], P.o[HermP<C>::idx(j, c)]);         // conj(P_cj) = P_jc
-          }
-          un[c].x = fmaf(-reg, s.x, un[c].x); un[c].y = fmaf(-reg, s.y, un[c].y);
-        }
-      }
+      rls_core_step<C, PK>(x, w, uw, y, P, mu, inv_mu, a.rls.gamma, a.rls.regularization_param, un);
       if (opt > 0) {
         float n2 = 0.f;
 #pragma unroll
@@ -422,7 +361,7 @@ __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUt
       for (int c = 0; c < C; c++) uw[c] = un[c];
       if (k == 0) n_updates++;
     }
-    if (t >= a.rls.min_frames) y = csub(y, cdot<C, false>(uw, x));
+    if (t >= a.rls.min_frames) y = csub(y, cdot<C, false, PK>(uw, x));
     Eavg = fmaf(Eavg, a.rls.beta, one_m_beta * energy);
     if (valid) a.Y[(size_t)t * a.Gp + g] = live ? y : make_float2(0.f, 0.f);
   }
@@ -555,7 +494,8 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
   } while (0)
   if (a.kind == BTKB_BF_GSC_RLS) {
     if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue;
-    auto kern = k_perbin_rls<C>;
+    const char* evr = getenv("BTKB_PERBIN_PACKED");
+    auto kern = (evr && atoi(evr) != 0) ? k_perbin_rls<C, true> : k_perbin_rls<C, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, TILE, smem, st>>>(tm, a);

@@ -77,6 +77,40 @@ static int zelinski_mismatches(unsigned seed) {
   return bad;
 }
 
+// The RLS sidelobe canceller's adaptation step (btkb_nlms_math.cuh rls_core_step): 40 consecutive steps of one chain from the initial
+// Pt = (I - C v v^H) / load, regularisation on every other step; Pt (diagonal and lower triangle) and the new u must agree bit for bit.
+template <int C>
+static int rls_mismatches(unsigned seed) {
+  std::mt19937 rng(seed);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  auto ne = [](float a, float b) { unsigned x, y; std::memcpy(&x, &a, 4); std::memcpy(&y, &b, 4); return x != y; };
+  constexpr int NP = C * (C - 1) / 2;
+  int bad = 0;
+  float2 w[C], us[C], up[C];
+  for (int c = 0; c < C; c++) { const float ph = 3.f * nd(rng); w[c] = make_float2(std::cos(ph) / C, std::sin(ph) / C); us[c] = up[c] = make_float2(0.f, 0.f); }
+  HermP<C> Ps, Pp;
+  const float inv_load = 1.0f / 1.0e6f;
+  for (int i = 0; i < C; i++) {
+    Ps.d[i] = (1.0f - (float)C * fmaf(w[i].x, w[i].x, w[i].y * w[i].y)) * inv_load;
+    for (int j = 0; j < i; j++)
+      Ps.o[HermP<C>::idx(i, j)] = make_float2(-(float)C * fmaf(w[i].x, w[j].x, w[i].y * w[j].y) * inv_load, -(float)C * fmaf(w[i].y, w[j].x, -w[i].x * w[j].y) * inv_load);
+  }
+  Pp = Ps;
+  const float mu = 0.9999f, inv_mu = 1.0f / mu, gamma = 1.0f;
+  for (int t = 0; t < 40; t++) {
+    float2 x[C], ns[C], np[C];
+    for (int c = 0; c < C; c++) x[c] = make_float2(3000.f * nd(rng), 3000.f * nd(rng));
+    const float2 ys = cdot<C, true, false>(x, w), yp = cdot<C, true, true>(x, w);
+    const float reg = (t & 1) ? 1.0e-2f : 0.f;
+    rls_core_step<C, false>(x, w, us, ys, Ps, mu, inv_mu, gamma, reg, ns);
+    rls_core_step<C, true>(x, w, up, yp, Pp, mu, inv_mu, gamma, reg, np);
+    for (int c = 0; c < C; c++) { bad += ne(ns[c].x, np[c].x) + ne(ns[c].y, np[c].y) + ne(Ps.d[c], Pp.d[c]); us[c] = ns[c]; up[c] = np[c]; }
+    for (int i = 0; i < NP; i++) bad += ne(Ps.o[i].x, Pp.o[i].x) + ne(Ps.o[i].y, Pp.o[i].y);
+    for (int c = 0; c < C; c++) if (!std::isfinite(ns[c].x) || !std::isfinite(ns[c].y)) bad += 1000;   // a chain that blew up proves nothing
+  }
+  return bad;
+}
+
 static int regs_differ = 0;
 
 template <int M, int SIGN, bool PK>
@@ -167,7 +201,8 @@ static int run(unsigned seed) {
     bad += ne(f2_scale_mi(f2_sub_conj(a, b), 0.5f), make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x)));
   }
   const int nl = nlms_mismatches<2>(seed) + nlms_mismatches<4>(seed + 1) + nlms_mismatches<8>(seed + 2) + zelinski_mismatches<2>(seed + 3) +
-                 zelinski_mismatches<4>(seed + 4) + zelinski_mismatches<8>(seed + 5);
+                 zelinski_mismatches<4>(seed + 4) + zelinski_mismatches<8>(seed + 5) + rls_mismatches<2>(seed + 6) + rls_mismatches<4>(seed + 7) +
+                 rls_mismatches<8>(seed + 8);
   printf("fold %a primitives %d regs_differ %d nlms %d\n", dmax, bad, regs_differ, nl);
   return 0;
 }

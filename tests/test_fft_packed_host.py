@@ -48,4 +48,4 @@ def test_device_fft_source_on_the_cpu_scalar_and_packed(harness, M, sign, seed):
     tail = out[-1].split()
     assert tail[0] == "fold" and float.fromhex(tail[1]) == 0.0 and tail[2] == "primitives" and int(tail[3]) == 0
     assert tail[4] == "regs_differ" and int(tail[5]) == 0      # after the last pass every thread still holds its eight outputs in registers
-    assert tail[6] == "nlms" and int(tail[7]) == 0             # 40 NLMS adaptation steps and 30 Zelinski CSD frames (C = 2, 4, 8), scalar vs packed: identical states
+    assert tail[6] == "nlms" and int(tail[7]) == 0             # 40 NLMS adaptation steps, 30 Zelinski CSD frames and 40 RLS steps (u and Pt; C = 2, 4, 8), scalar vs packed: identical states

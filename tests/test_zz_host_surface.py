@@ -585,7 +585,7 @@ def test_batch_front_end_configured_from_the_references_parameter_files():
 @pytest.mark.parametrize("M", [256, 512, 1024])
 def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
     """BTKB_ANALYSIS_PACKED=1 / BTKB_SYNTHESIS_PACKED=1 / BTKB_PERBIN_PACKED=1 select the FADD2 / FMUL2 / FFMA2 variants of k_analysis_r1,
-    k_synthesis_fast and the NLMS recurrence of k_perbin (csrc/btkb_f2.cuh).  They perform the same IEEE operations per component, so snapshots, subband output and time signal must equal
+    k_synthesis_fast, the NLMS recurrence of k_perbin and the RLS step of k_perbin_rls (csrc/btkb_f2.cuh).  They perform the same IEEE operations per component, so snapshots, subband output and time signal must equal
     the default kernels' BIT FOR BIT (the CPU run of the same source says so: tests/test_fft_packed_host.py) — on a ragged batch, and
     for the analysis bank also with an odd channel count (the unpaired last channel)."""
     import os
@@ -624,6 +624,11 @@ def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
                 p = capi.Pipeline(16, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=8), max_utterances=2, max_samples=6000)
                 p.set_prototypes(h, g); p.set_delays(d16c); p.submit(x16c, np.array([6000, 4100], np.int32)); p.run(True)
                 out += [p.fetch_subband(), p.fetch_time()]
+                p.close()
+            for rls in (dict(min_frames=8), dict(min_frames=8, regularization_param=1.0e-2, constraint_option=3, alpha2=1.0e-3)):
+                p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC_RLS, rls=rls, max_utterances=U, max_samples=n)   # packed RLS step (rls_core_step)
+                p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
+                out += [p.fetch_subband(), p.get_active_weights()]
                 p.close()
             p = capi.Pipeline(3, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
             p.set_prototypes(h, g); p.submit(np.ascontiguousarray(x[:, :3]), lengths); p.run_analysis()
