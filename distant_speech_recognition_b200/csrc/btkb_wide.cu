@@ -8,8 +8,8 @@
 // (128 B rows) fetched by one tensor-map TMA instruction with the 128-byte swizzle, which spreads the L lanes of a chain
 // (reading the same column of 8 different rows) over different shared-memory banks.
 //
-// The covariance / MVDR-solve kernels here are the plain CUDA-core versions (one CTA per chain); the tcgen05 batched
-// contraction for the 64-mic covariance is a later-round item.
+// The covariance / MVDR-solve kernels here are the plain CUDA-core versions (one CTA per chain; C = 16, 32); the 64-mic
+// covariance runs on the tensor cores instead (k_covariance_tc, btkb_cov_tc.cu: tcgen05 + TMEM).
 #include <cuda.h>
 #include "btkb_internal.h"
 #include "btkb_tensor_map.h"
