@@ -255,12 +255,24 @@ static void from_device_layout(const std::vector<float2>& src, float* dst, int U
       }
 }
 
+// Weight setters and submissions may arrive in either order and with a different utterance count from one batch to the next (a
+// pipeline sized for 256 utterances must also take the trailing partial batch).  Rules:
+//   * check_weight_batch only validates; begin_weight_batch commits, and is called after the setter's own argument checks, so a
+//     failed call leaves the pipeline untouched;
+//   * a setter whose U differs from the U the resident weights were made for starts a NEW weight set: everything derived for the
+//     old count (manifold, quiescent / active weights, covariance) is void;
+//   * the device layouts of X / Y / weights share the row pitch Gp = roundup(U K, 128), so a resident batch of another size cannot
+//     survive a weight setter for a new U (it is dropped: have_X = have_Y = false), and the beamformer refuses to run while the
+//     weights and the submitted batch disagree (do_beamformer).
 static int check_weight_batch(btkb_pipeline* p, int U, const char* who) {
   if (U < 1 || U > p->Ucap) return fail(BTKB_ERR_INVALID, std::string(who) + ": U out of range");
-  if (p->wU != 0 && p->wU != U && p->U != 0 && p->U != U) return fail(BTKB_ERR_INVALID, std::string(who) + ": U differs from the submitted batch");
+  return BTKB_OK;
+}
+static void begin_weight_batch(btkb_pipeline* p, int U) {
+  if (p->wU != U) { p->have_w = p->have_wl = p->have_ta = p->have_R = false; p->R_is_sum = false; p->NC = 1; }
+  if (p->U != 0 && p->U != U) { p->have_X = p->have_Y = p->have_time = p->have_ua = false; p->U = 0; p->T = 0; p->nb = 0; }
   p->wU = U;
   p->Gp = round_up(U * p->K, 128);
-  return BTKB_OK;
 }
 
 int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
@@ -269,6 +281,7 @@ int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
   if ((p->cfg.beamformer == BTKB_BF_GSC || p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS) && p->C <= 1)  // beamformer.cc:507-510
     return fail(BTKB_ERR_INVALID, "The number of channels must be > 1 but it is " + std::to_string(p->C));
   CK(cudaSetDevice(p->cfg.device));
+  begin_weight_batch(p, U);
   // stage through pinned host memory owned by the pipeline: the call stays asynchronous (no stream sync) and `delays`
   // may be reused by the caller immediately
   if (!p->h_delays) CK(cudaMallocHost((void**)&p->h_delays, (size_t)p->Ucap * p->C * sizeof(double)));
@@ -306,6 +319,7 @@ int btkb_set_weights(btkb_pipeline* p, int U, const float* w) {
   if (!p || !w) return fail(BTKB_ERR_INVALID, "btkb_set_weights: null argument");
   int rc = check_weight_batch(p, U, "btkb_set_weights"); if (rc) return rc;
   CK(cudaSetDevice(p->cfg.device));
+  begin_weight_batch(p, U);
   std::vector<float2> tmp;
   to_device_layout(w, tmp, U, p->K, p->C, p->Gp);
   CK(cudaMemcpyAsync(p->d_W, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
@@ -324,13 +338,14 @@ int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa) {
   if (p->C < 2) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: needs at least two channels");
   if (p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: the blocking-matrix kernels are built for <= 8 channels");
   int rc = check_weight_batch(p, U, "btkb_set_active_weights"); if (rc) return rc;
+  if (U != p->wU) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: the quiescent weights were set for " + std::to_string(p->wU) + " utterances, not " + std::to_string(U));
+  // calc_blocking_matrix_(wq_[f], NC, B_[f]) (beamformer.cc:554-562, 693-700): B is built from the quiescent vector
+  const float2* bsrc = (p->cfg.beamformer == BTKB_BF_MVDR && p->bm_source == 0) ? p->d_TA : p->d_W;
+  if (bsrc == p->d_W && !p->have_w) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");  // calc_blocking_matrix2 returns false without wmvdr (beamformer.cc:2651-2653)
   CK(cudaSetDevice(p->cfg.device));
   std::vector<float2> tmp;
   to_device_layout(wa, tmp, U, p->K, p->C - p->NC, p->Gp);
   CK(cudaMemcpyAsync(p->d_WA, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
-  // calc_blocking_matrix_(wq_[f], NC, B_[f]) (beamformer.cc:554-562, 693-700): B is built from the quiescent vector
-  const float2* bsrc = (p->cfg.beamformer == BTKB_BF_MVDR && p->bm_source == 0) ? p->d_TA : p->d_W;
-  if (bsrc == p->d_W && !p->have_w) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");  // calc_blocking_matrix2 returns false without wmvdr (beamformer.cc:2651-2653)
   CK(launch_blocking_wl(bsrc, p->d_WA, p->d_WL, U, p->C, p->K, p->Gp, p->NC, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   p->have_wl = true;
@@ -350,6 +365,7 @@ int btkb_set_noise_covariance(btkb_pipeline* p, int U, const float* R) {
   if (!p->d_R) return fail(BTKB_ERR_STATE, "btkb_set_noise_covariance: pipeline was not created with BTKB_BF_MVDR");
   int rc = check_weight_batch(p, U, "btkb_set_noise_covariance"); if (rc) return rc;
   CK(cudaSetDevice(p->cfg.device));
+  begin_weight_batch(p, U);
   std::vector<float2> tmp;
   to_device_layout(R, tmp, U, p->K, p->C * p->C, p->Gp);
   CK(cudaMemcpyAsync(p->d_R, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
@@ -363,6 +379,7 @@ int btkb_set_diffuse_noise_model(btkb_pipeline* p, int U, const double* mpos, fl
   if (!p->d_R) return fail(BTKB_ERR_STATE, "btkb_set_diffuse_noise_model: pipeline was not created with BTKB_BF_MVDR");
   int rc = check_weight_batch(p, U, "btkb_set_diffuse_noise_model"); if (rc) return rc;
   CK(cudaSetDevice(p->cfg.device));
+  begin_weight_batch(p, U);
   CK(cudaMemcpyAsync(p->d_mpos, mpos, (size_t)p->C * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
   CK(launch_diffuse_model(p->d_mpos, p->d_R, U, p->C, p->M, p->K, p->Gp, p->cfg.samplerate, sspeed, p->stream));
   CK(cudaStreamSynchronize(p->stream));
@@ -437,7 +454,8 @@ int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu) {
 static int submit_common(btkb_pipeline* p, int U, int n, const int* lengths) {
   if (U < 1 || U > p->Ucap) return fail(BTKB_ERR_INVALID, "btkb_submit: U exceeds max_utterances");
   if (n < 1 || n > p->ncap) return fail(BTKB_ERR_INVALID, "btkb_submit: n exceeds max_samples");
-  if (p->wU != 0 && p->wU != U) return fail(BTKB_ERR_INVALID, "btkb_submit: U differs from the batch the weights were set for");
+  // (weights made for another utterance count stay where they are; do_beamformer refuses to combine them with this batch, and the next
+  // weight setter for this U replaces them — begin_weight_batch)
   p->U = U; p->n = n;
   p->lengths.assign(U, n);
   int Tmax = 0;
@@ -446,6 +464,7 @@ static int submit_common(btkb_pipeline* p, int U, int n, const int* lengths) {
     Tmax = std::max(Tmax, frames_of(p->lengths[u], p->D, p->laN, p->pdA));
   }
   p->T = Tmax; p->nb = std::max(Tmax - p->pdS, 0);
+  if (p->wU != U) { p->have_w = p->have_wl = p->have_ta = p->have_R = false; p->R_is_sum = false; p->NC = 1; p->wU = 0; }   // their row pitch is another Gp
   p->Gp = round_up(U * p->K, 128);
   p->have_X = p->have_Y = p->have_time = p->have_ua = false;
   CK(cudaMemcpyAsync(p->d_len, p->lengths.data(), U * sizeof(int), cudaMemcpyHostToDevice, p->stream));

@@ -113,26 +113,30 @@ __device__ __forceinline__ void dft8(float2* v) {
   dft4<SIGN, PK>(e0, e1, e2, e3);
   dft4<SIGN, PK>(o0, o1, o2, o3);
   const float s = 0.70710678118654752440f;
+  // o1 (1 + SIGN i)/sqrt2 and o3 (-1 + SIGN i)/sqrt2 are never formed: the scale by 1/sqrt2 is folded into the last butterfly as an
+  // explicit multiply-add, v[1] = fma(o1 + SIGN i o1, s, e1), v[5] = fma(o1 + SIGN i o1, -s, e1) (likewise v[3], v[7]).  nvcc's
+  // default -fmad=true contracted the scalar "(sum) * s" + "e +- that" into exactly these FFMAs already (8 per butterfly); writing
+  // them out makes the packed form (FFMA2) round identically and makes the host build of this header (no contraction) agree
+  // with the device.
   if constexpr (PK) {
-    // o1 (1 + SIGN i)/sqrt2 ; SIGN i o2 folded into the last stage ; o3 (-1 + SIGN i)/sqrt2 — the sums the scalar code forms, then * s
-    o1 = f2_scale(f2_add_ib<SIGN>(o1, o1), s);
-    o3 = f2_scale(f2_add_ib<SIGN>(make_float2(-o3.x, -o3.y), o3), s);
+    const float2 u1 = f2_add_ib<SIGN>(o1, o1);
+    const float2 u3 = f2_add_ib<SIGN>(make_float2(-o3.x, -o3.y), o3);
     v[0] = f2_add(e0, o0); v[4] = f2_sub(e0, o0);
-    v[1] = f2_add(e1, o1); v[5] = f2_sub(e1, o1);
+    v[1] = f2_fma_s(u1, s, e1); v[5] = f2_fma_s(u1, -s, e1);
     v[2] = f2_add_ib<SIGN>(e2, o2); v[6] = f2_sub_ib<SIGN>(e2, o2);
-    v[3] = f2_add(e3, o3); v[7] = f2_sub(e3, o3);
+    v[3] = f2_fma_s(u3, s, e3); v[7] = f2_fma_s(u3, -s, e3);
     return;
   }
-  // o1 *= (1 + SIGN i)/sqrt2 ; o2 *= SIGN i ; o3 *= (-1 + SIGN i)/sqrt2
-  float2 t1 = mul_si<SIGN>(o1);
-  o1 = make_float2((o1.x + t1.x) * s, (o1.y + t1.y) * s);
+  // o2 *= SIGN i
+  const float2 t1 = mul_si<SIGN>(o1);
+  const float2 u1 = make_float2(o1.x + t1.x, o1.y + t1.y);
   o2 = mul_si<SIGN>(o2);
-  float2 t3 = mul_si<SIGN>(o3);
-  o3 = make_float2((t3.x - o3.x) * s, (t3.y - o3.y) * s);
+  const float2 t3 = mul_si<SIGN>(o3);
+  const float2 u3 = make_float2(t3.x - o3.x, t3.y - o3.y);
   v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
-  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[1] = make_float2(fmaf(u1.x, s, e1.x), fmaf(u1.y, s, e1.y)); v[5] = make_float2(fmaf(u1.x, -s, e1.x), fmaf(u1.y, -s, e1.y));
   v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
-  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+  v[3] = make_float2(fmaf(u3.x, s, e3.x), fmaf(u3.y, s, e3.y)); v[7] = make_float2(fmaf(u3.x, -s, e3.x), fmaf(u3.y, -s, e3.y));
 }
 
 // Per-thread twiddles for the P radix-8 passes: tw[p][r-1] = exp(SIGN 2 pi i k r / (Ns 8)), k = tid % Ns, Ns = R0 8^p.

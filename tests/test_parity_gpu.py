@@ -348,6 +348,44 @@ def test_batch_ragged_lengths_match_single_runs(capi, protos):
         assert np.all(Y[u, T:] == 0)
 
 
+def test_consecutive_batches_of_different_size_on_one_pipeline(capi, protos):
+    """A pipeline sized for max_utterances must take a trailing partial batch (the weight-batch count was never reset):
+    weight setter and submit in either order, U changing 3 -> 2 -> 3, every batch equal to the same utterances run alone; weights
+    and a batch of different counts are refused; a weight setter for a new count drops the resident batch of the old one."""
+    from distant_speech_recognition_b200 import synthetic
+    M, C, n = 256, 4, 5000
+    x, d = synthetic.make_batch(3, C, n, first=300)
+    lms = dict(min_frames=5)
+    solo = []
+    for u in range(3):
+        q = _pipe(capi, C, M, protos, U=1, n=n, beamformer=capi.BF_GSC_LMS, lms=lms)
+        q.set_delays(d[u:u + 1]); q.submit(x[u:u + 1]); q.run(True)
+        solo.append((q.fetch_subband()[0], q.fetch_time()[0])); q.close()
+    p = _pipe(capi, C, M, protos, U=3, n=n, beamformer=capi.BF_GSC_LMS, lms=lms)
+    p.set_delays(d); p.submit(x); p.run(True)                       # U = 3, setter first
+    Y, y = p.fetch_subband(), p.fetch_time()
+    for u in range(3):
+        assert np.array_equal(Y[u], solo[u][0]) and np.array_equal(y[u], solo[u][1])
+    p.set_delays(d[1:3]); p.submit(x[1:3]); p.run(True)              # U = 2, setter first (what BatchBeamformer.process does)
+    Y, y = p.fetch_subband(), p.fetch_time()
+    assert Y.shape[0] == 2
+    for u in range(2):
+        assert np.array_equal(Y[u], solo[1 + u][0]) and np.array_equal(y[u], solo[1 + u][1])
+    p.submit(x); p.set_delays(d); p.run(True)                       # back to U = 3, submit first
+    Y = p.fetch_subband()
+    for u in range(3):
+        assert np.array_equal(Y[u], solo[u][0])
+    p.submit(x[:2])                                                 # weights are for 3 utterances: refused, not garbage
+    with pytest.raises(capi.BtkbError):
+        p.run(True)
+    p.set_delays(d[:2]); p.run(True)
+    assert np.array_equal(p.fetch_subband()[1], solo[1][0])
+    p.set_delays(d)                                                 # new count while a 2-utterance batch is resident: the batch is dropped
+    with pytest.raises(capi.BtkbError):
+        p.fetch_snapshots()
+    p.close()
+
+
 def test_filterbank_round_trip_and_linearity_full_size(capi, protos):
     """Size-independent properties at configs[1] size (8 mics, M=512, 5 s): D&S of identical channels with zero delays
     returns the analysis->synthesis round trip (interior error ~1.7e-3 with these prototypes), and the

