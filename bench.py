@@ -155,7 +155,7 @@ def workload_config(n_gpus):
             "frames_per_utterance": frames_per_utt(c["n"], c["M"], c["m"], c["r"]), "global_utterances": c["U"] * n_gpus,
             "parallelism": "utterance shards x%d (no data-path collective)" % n_gpus,
             "l2_policy": "inputs (655 MB samples, 1.33 GB snapshots per step) exceed the 126 MB L2; no explicit flush",
-            "kernel_variants": {k: ("packed 2 x fp32" if os.environ.get(k, "0") not in ("", "0") else "scalar (default)")
+            "kernel_variants": {k: ("packed 2 x fp32" if os.environ.get(k, "1") not in ("", "0") else "scalar")
                                 for k in ("BTKB_ANALYSIS_PACKED", "BTKB_PERBIN_PACKED", "BTKB_SYNTHESIS_PACKED")}}
 
 

@@ -309,6 +309,31 @@ class Pipeline:
     def synchronize(self):
         _check(lib.btkb_synchronize(self._h))
 
+    # ---- streamed chunks with carried state (btkb.h: btkb_stream_*)
+    def stream_begin(self, U):
+        self.U = int(U)
+        _check(lib.btkb_stream_begin(self._h, ct.c_int(self.U)))
+
+    def stream_submit(self, samples, lengths=None, final=False, synthesis=True):
+        """samples float32 [U][C][n]: the next n samples of every utterance (n a multiple of D unless final)."""
+        x = np.ascontiguousarray(samples, np.float32)
+        assert x.ndim == 3 and x.shape[1] == self.C
+        ln = None if lengths is None else np.ascontiguousarray(lengths, np.int32)
+        _check(lib.btkb_stream_submit(self._h, _fp(x), ct.c_int(x.shape[2]), None if ln is None else ln.ctypes.data_as(ct.POINTER(ct.c_int)),
+                                      ct.c_int(1 if final else 0), ct.c_int(1 if synthesis else 0)))
+
+    def stream_position(self):
+        a, b = ct.c_int(0), ct.c_int(0)
+        _check(lib.btkb_stream_position(self._h, ct.byref(a), ct.byref(b)))
+        return a.value, b.value
+
+    def reset(self):
+        _check(lib.btkb_reset(self._h))
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer handle of a cudaStream_t (e.g. torch.cuda.Stream().cuda_stream), 0 / None = private stream."""
+        _check(lib.btkb_set_stream(self._h, ct.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
     # ---- results
     @property
     def num_frames(self):

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) 
   const bool has_b = cb < a.C;
   const int len = a.lengths ? a.lengths[u] : a.n;
   // first staged sample: n_{t0} - mM + 1
-  const long long w0 = (long long)(a.laN + t0 + 1) * D - (long long)m * M;
+  const long long w0 = a.w_base + (long long)t0 * D - (long long)m * M;
   const float* xa = a.x + ((size_t)u * a.C + ca) * a.n_stride;
   const float* xb = a.x + ((size_t)u * a.C + (has_b ? cb : ca)) * a.n_stride;
   for (int w = tid; w < W; w += G * NT) {
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) 
 //
 // PK = true: the fold and the transforms use the packed 2 x fp32 instructions (btkb_f2.cuh).  The two real channels of a pair are
 // the halves of one float2, so a tap MAC on both channels is one FFMA2 with the tap broadcast; results are bit-identical to
-// PK = false.  Selected with BTKB_ANALYSIS_PACKED=1 (off by default until it has been timed on a B200).
+// PK = false.  The default since round 2 (0.499 vs 0.531 ms at configs[1] on B200); BTKB_ANALYSIS_PACKED=0 selects the scalar kernel.
 template <int M, int MT, int FR, int G, bool PK = false>
 __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(AnalysisArgs a) {
   using Plan = FftPlan<M>;
@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
 
   // A CTA walks a.tiles_per_cta consecutive frame tiles of its (utterance, channel pair): prototype taps and twiddles are
   // set up once, the previous tile's last barrier protects the staged samples before they are overwritten.
-  const int ntiles = (a.T + FR - 1) / FR;
+  const int ntiles = (a.T + a.t_skip + FR - 1) / FR;
   const int tile_end = min((int)(blockIdx.x + 1) * a.tiles_per_cta, ntiles);
 #pragma unroll 1
   for (int tile = blockIdx.x * a.tiles_per_cta; tile < tile_end; tile++) {
-  const int t0 = tile * FR;
-  const long long w0 = (long long)(a.laN + t0 + 1) * D - (long long)MT * M;
+  const int t0 = tile * FR - a.t_skip;
+  const long long w0 = a.w_base + (long long)t0 * D - (long long)MT * M;
   // Asynchronous 16-byte copies with zero fill (cp.async ... src-size): every thread puts ~W/(2 NT G) chunks per channel
   // in flight at once, samples outside [0, len) arrive as zeros (w0 and W are multiples of 4, rows are 16 B aligned).
   // The copies are committed in NIT groups, group i holding the samples iteration i needs beyond those of iteration i-1,
@@ -243,11 +243,11 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
     __syncthreads();
     const int f = f0 + 2 * grp;
     const int ta = t0 + f, tb = ta + 1;
-    const bool act0 = ta < a.T, act1 = tb < a.T;
+    const bool act0 = ta >= 0 && ta < a.T, act1 = tb < a.T;
     float2 v0[8], v1[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { v0[i] = make_float2(0.f, 0.f); v1[i] = make_float2(0.f, 0.f); }
-    if (act0 && (PK || !(a.debug & 2))) {   // (the ablation hooks of BTKB_ANALYSIS_DEBUG exist in the scalar variant only)
+    if (ta < a.T && (PK || !(a.debug & 2))) {   // ta = -1 (t_skip): the discarded partner of local frame 0 is folded too; (the ablation hooks of BTKB_ANALYSIS_DEBUG exist in the scalar variant only)
       const int base = f * D + MT * M - 1;
 #pragma unroll
       for (int q = 0; q < 8; q++)
@@ -342,10 +342,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
 #undef BTKB_SLOT
 }
 
-static bool analysis_packed() {  // BTKB_ANALYSIS_PACKED=1: packed 2 x fp32 variant (bit-identical results; off by default).  Read at
-  const char* e = getenv("BTKB_ANALYSIS_PACKED");   // every launch so that one process can compare the two variants.
-  return e && atoi(e) != 0;
-}
+static bool analysis_packed() { return env_packed("BTKB_ANALYSIS_PACKED"); }   // packed 2 x fp32 variant unless BTKB_ANALYSIS_PACKED=0
 
 template <int M, int MT, int FR>
 static cudaError_t launch_analysis_r1(const AnalysisArgs& a_in, cudaStream_t st) {
@@ -357,7 +354,7 @@ static cudaError_t launch_analysis_r1(const AnalysisArgs& a_in, cudaStream_t st)
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // tiles per CTA: amortise the per-CTA set-up while keeping >= ~8 waves of CTAs for balance
-  const int ntiles = (a.T + FR - 1) / FR;
+  const int ntiles = (a.T + a.t_skip + FR - 1) / FR;
   const long long ctas1 = (long long)ntiles * ((a.C + 1) / 2) * a.U;
   int tpc = 1;
   while (tpc < 8 && tpc * 2 <= ntiles && ctas1 / (tpc * 2) >= 148LL * 3 * 8) tpc *= 2;

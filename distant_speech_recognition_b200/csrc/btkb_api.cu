@@ -57,6 +57,15 @@ struct btkb_pipeline {
   bool have_X = false, have_Y = false, have_time = false, have_ua = false;
   float timing[5] = {0, 0, 0, 0, 0};
   int launches = 0;
+  // streamed chunks (btkb_stream_begin / btkb_stream_submit): sample rows with a history prefix (two buffers, the tail of one becomes
+  // the head of the other), Y rows preceded by m R - 1 frames of history, the per-chain recurrence state, absolute counters
+  bool streaming = false, stream_final = false, owns_stream = true;
+  float* d_xs[2] = {nullptr, nullptr}; int xs_stride = 0, xs_cur = 0, xs_hist = 0;
+  float* d_ST = nullptr; int* d_tu = nullptr; float2* Y_out = nullptr;   // Y_out: row 0 of the current batch / chunk inside d_Y
+  long long s_samples = 0;   // samples per utterance submitted so far (non-final chunks are whole blocks)
+  int s_tnext = 0, s_tlast = 0, s_bnext = 0, s_blast = 0, s_chunks = 0, Hy = 0;   // absolute frame / block number of the next and of the last processed chunk's first frame / block
+  std::vector<long long> s_len;   // absolute valid length per utterance
+  std::vector<int> s_tu;          // absolute frames per utterance so far
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -97,7 +106,7 @@ static void fb_delays(int m, int r, int dct, bool synthesis, int* pd, int* la) {
 void btkb_destroy(btkb_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
-  void* ptrs[] = {p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
+  void* ptrs[] = {p->d_xs[0], p->d_xs[1], p->d_ST, p->d_tu, p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
                   p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
                   p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM, p->d_wS, p->d_wG, p->d_wR, p->d_wTH, p->d_werr,
                   p->d_sosR, p->d_sosWd, p->d_sosCnt, p->d_sosWtu, p->d_sosMask, p->d_sosLab, p->d_sosErr, p->d_covS};
@@ -105,7 +114,7 @@ void btkb_destroy(btkb_pipeline* p) {
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   for (auto& e : p->wev) if (e) cudaEventDestroy(e);
-  if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->stream && p->owns_stream) cudaStreamDestroy(p->stream);
   delete p;
 }
 
@@ -130,8 +139,8 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
     return fail(BTKB_ERR_INVALID, "btkb_create: the McCowan / Lefkimmiatis post-filters are built for 2..8 channels");
   if (cfg->beamformer == BTKB_BF_GSC_RLS && cfg->postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCRLSBeamformer");
-  if (cfg->beamformer == BTKB_BF_GSC_RLS && !(C == 2 || C == 4 || C == 8))
-    return fail(BTKB_ERR_INVALID, "btkb_create: the RLS sidelobe canceller keeps its C x C precision matrix in registers and is built for 2, 4 or 8 channels");
+  if (cfg->beamformer == BTKB_BF_GSC_RLS && (C < 2 || C > 8))
+    return fail(BTKB_ERR_INVALID, "btkb_create: the RLS sidelobe canceller keeps its C x C precision matrix in registers and is built for 2..8 channels");
   if (cfg->beamformer == BTKB_BF_GSC_LMS && cfg->postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCLMSBeamformer");
   if (cfg->wpe.enabled) {
@@ -160,7 +169,8 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   A((void**)&p->d_h, (size_t)p->m * M * sizeof(float));
   A((void**)&p->d_g, (size_t)p->m * M * sizeof(float));
   A((void**)&p->d_X, T * C * G * sizeof(float2));
-  A((void**)&p->d_Y, T * G * sizeof(float2));
+  p->Hy = p->m * p->R + 1;   // rows of Y history in front of a streamed chunk: a block reaches back m R - 1 frames, +1 for the block held back, +1 for the pair-aligned tile origin
+  A((void**)&p->d_Y, (T + p->Hy) * G * sizeof(float2));
   A((void**)&p->d_W, (size_t)C * G * sizeof(float2));
   A((void**)&p->d_TA, (size_t)C * G * sizeof(float2));
   A((void**)&p->d_WL, (size_t)C * G * sizeof(float2));
@@ -213,6 +223,7 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
       return fail(BTKB_ERR_CUDA, "btkb_create: twiddle upload failed");
     }
   }
+  p->Y_out = p->d_Y;
   *out = p;
   return BTKB_OK;
 }
@@ -289,6 +300,10 @@ int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
   memcpy(p->h_delays, delays, (size_t)U * p->C * sizeof(double));
   CK(cudaMemcpyAsync(p->d_delays, p->h_delays, (size_t)U * p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
   CK(cudaEventRecord(p->ev[4], p->stream));
+  // a new look direction in the middle of a stream: the adaptive state is kept, re-expressed for the new blocking matrices
+  const bool adaptive = p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS;
+  const bool rebase = adaptive && p->streaming && p->s_chunks > 0 && p->have_ta && p->C >= 2;
+  if (rebase) CK(cudaMemcpyAsync(p->d_WL, p->d_TA, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));   // WL is free in the adaptive modes
   WeightsArgs a{p->d_delays, p->d_TA, U, p->C, p->M, p->K, p->Gp, p->cfg.samplerate};
   CK(launch_mainlobe_weights(a, p->stream));
   p->have_ta = true; p->NC = 1;
@@ -296,6 +311,7 @@ int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
     CK(cudaMemcpyAsync(p->d_W, p->d_TA, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
     p->have_w = true;
   }
+  if (rebase) CK(launch_adaptive_rebase(p->d_WL, p->d_W, p->d_UA, p->d_ST, p->cfg.beamformer == BTKB_BF_GSC_RLS ? 1 : 0, U, p->C, p->K, p->Gp, p->stream));
   return BTKB_OK;
 }
 
@@ -457,6 +473,7 @@ static int submit_common(btkb_pipeline* p, int U, int n, const int* lengths) {
   // (weights made for another utterance count stay where they are; do_beamformer refuses to combine them with this batch, and the next
   // weight setter for this U replaces them — begin_weight_batch)
   p->U = U; p->n = n;
+  p->streaming = false; p->Y_out = p->d_Y;
   p->lengths.assign(U, n);
   int Tmax = 0;
   for (int u = 0; u < U; u++) {
@@ -518,7 +535,7 @@ static int do_analysis(btkb_pipeline* p) {
   if (!p->have_h) return fail(BTKB_ERR_STATE, "btkb_run: set the analysis prototype first");
   if (p->U == 0) return fail(BTKB_ERR_STATE, "btkb_run: no batch submitted");
   AnalysisArgs a{p->x_cur, p->d_len, p->d_h, p->d_X, p->d_E, p->U, p->C, p->n, (p->x_cur == p->d_x) ? p->n_stride : p->n, p->T, p->M, p->m, p->D, p->laN,
-                 p->Gp, 1, p->d_tw, 1, 0};
+                 p->Gp, 1, p->d_tw, 1, 0, (long long)(p->laN + 1) * p->D, 0};
   CK(launch_analysis(a, p->stream));
   p->launches++;
   p->have_X = true;
@@ -530,7 +547,7 @@ static PerBinArgs perbin_args(btkb_pipeline* p) {
   memset(&a, 0, sizeof(a));
   a.X = p->d_X; a.E = p->d_E; a.lengths = p->d_len; a.W = p->d_W; a.TA = p->have_ta ? p->d_TA : nullptr;
   a.WL = p->have_wl ? p->d_WL : nullptr;
-  a.Y = p->d_Y; a.PFW = p->d_PFW; a.UA = p->d_UA; a.stats_updates = p->d_upd;
+  a.Y = p->Y_out; a.PFW = p->d_PFW; a.UA = p->d_UA; a.stats_updates = p->d_upd;
   a.R = p->d_R; a.noise_mask = p->d_mask; a.noise_count = p->d_count;
   a.U = p->U; a.C = p->C; a.T = p->T; a.M = p->M; a.K = p->K; a.G = p->U * p->K; a.Gp = p->Gp; a.D = p->D; a.laN = p->laN; a.pdA = p->pdA;
   a.kind = p->cfg.beamformer; a.normalize_weight = p->cfg.normalize_weight; a.pf_kind = p->cfg.postfilter; a.pf_alpha = p->cfg.pf_alpha; a.pf_type = p->cfg.pf_type; a.pf_min_frames = p->cfg.pf_min_frames;
@@ -574,9 +591,9 @@ static int do_beamformer(btkb_pipeline* p) {
     return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                                          // beamformer.cc:1098-1100
   }
   if (p->wU != p->U) return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: weights were set for a different number of utterances");
-  const bool narrow = (p->C == 2 || p->C == 4 || p->C == 8), wide = (p->C == 16 || p->C == 32 || p->C == 64);
+  const bool narrow = (p->C >= 1 && p->C <= 8), wide = (p->C == 16 || p->C == 32 || p->C == 64);
   if (!narrow && !wide)
-    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the per-bin kernel is instantiated for 2, 4, 8 (register path) and 16, 32, 64 (lane-split path) channels (got " + std::to_string(p->C) + ")");
+    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the per-bin kernel is instantiated for 1..8 (register path) and 16, 32, 64 (lane-split path) channels (got " + std::to_string(p->C) + ")");
   if (wide && p->cfg.postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the post-filters are built for <= 8 channels (their C(C-1)/2 cross-spectral densities must fit the register file)");
   PerBinArgs a = perbin_args(p);
@@ -602,9 +619,9 @@ static int do_synthesis(btkb_pipeline* p) {
   if (!p->have_g) return fail(BTKB_ERR_STATE, "btkb_run: set the synthesis prototype first");
   if (!p->have_Y) return fail(BTKB_ERR_STATE, "btkb_run: no beamformer output to synthesise");
   CK(cudaMemsetAsync(p->d_stats, 0, (size_t)p->U * 3 * sizeof(double), p->stream));
-  SynthesisArgs a{p->d_Y, p->d_len, p->d_g, p->d_time, p->d_stats, p->U, p->n, p->T, p->M, p->m, p->cfg.r, p->D, p->K, p->Gp, p->pdS, p->laN, p->pdA,
+  SynthesisArgs a{p->Y_out, p->d_len, p->d_g, p->d_time, p->d_stats, p->U, p->n, p->T, p->M, p->m, p->cfg.r, p->D, p->K, p->Gp, p->pdS, p->laN, p->pdA,
                   p->nb, p->nb * p->D, p->cfg.synthesis_gain, p->d_tw,
-                  (p->cfg.postfilter >= BTKB_PF_MCCOWAN && p->pf_applied) ? p->cfg.pf_min_frames + 1 : 0};
+                  (p->cfg.postfilter >= BTKB_PF_MCCOWAN && p->pf_applied) ? p->cfg.pf_min_frames + 1 : 0, 0, 0, nullptr, 0};
   CK(launch_synthesis(a, p->stream));
   p->launches++;
   p->have_time = true;
@@ -855,6 +872,7 @@ int btkb_set_subband(btkb_pipeline* p, int U, int T, const float* Y) {
   if (nblk < 0) return fail(BTKB_ERR_INVALID, "btkb_set_subband: T is shorter than the filter-bank delay");
   p->U = U; p->n = nblk * p->D; p->lengths.assign(U, nblk * p->D);
   p->T = T; p->nb = std::max(T - p->pdS, 0); p->Gp = round_up(U * p->K, 128);
+  p->streaming = false; p->Y_out = p->d_Y;
   CK(cudaMemcpyAsync(p->d_len, p->lengths.data(), U * sizeof(int), cudaMemcpyHostToDevice, p->stream));
   std::vector<float2> tmp((size_t)T * p->Gp, make_float2(0.f, 0.f));
   for (int u = 0; u < U; u++)
@@ -913,7 +931,10 @@ int btkb_last_timing(btkb_pipeline* p, float* out5) {
 }
 
 int btkb_num_frames(const btkb_pipeline* p) { return p ? p->T : 0; }
-int btkb_num_frames_of(const btkb_pipeline* p, int u) { return (p && u >= 0 && u < p->U) ? frames_of(p->lengths[u], p->D, p->laN, p->pdA) : 0; }
+int btkb_num_frames_of(const btkb_pipeline* p, int u) {
+  if (!p || u < 0 || u >= p->U) return 0;
+  return p->streaming ? std::min(std::max(p->s_tu[u] - p->s_tlast, 0), p->T) : frames_of(p->lengths[u], p->D, p->laN, p->pdA);
+}
 int btkb_num_blocks(const btkb_pipeline* p) { return p ? p->nb : 0; }
 
 static int ensure_scratch(btkb_pipeline* p, size_t bytes) {
@@ -949,7 +970,7 @@ int btkb_fetch_subband(btkb_pipeline* p, float* out) {
   CK(cudaSetDevice(p->cfg.device));
   const size_t bytes = (size_t)p->U * p->T * p->K * sizeof(float2);
   int rc = ensure_scratch(p, bytes); if (rc) return rc;
-  k_gather<<<2048, 256, 0, p->stream>>>(p->d_Y, (float2*)p->d_scratch, p->U, p->T, 1, p->K, p->Gp);
+  k_gather<<<2048, 256, 0, p->stream>>>(p->Y_out, (float2*)p->d_scratch, p->U, p->T, 1, p->K, p->Gp);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
@@ -999,7 +1020,7 @@ int btkb_fetch_stats(btkb_pipeline* p, double* out) {
   else memset(out, 0, (size_t)p->U * 3 * sizeof(double));
   if (p->have_ua) CK(cudaMemcpyAsync(upd.data(), p->d_upd, (size_t)p->U * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
-  for (int u = 0; u < p->U; u++) { out[3 * u + 1] = frames_of(p->lengths[u], p->D, p->laN, p->pdA); out[3 * u + 2] = upd[u]; }
+  for (int u = 0; u < p->U; u++) { out[3 * u + 1] = p->streaming ? p->s_tu[u] : frames_of(p->lengths[u], p->D, p->laN, p->pdA); out[3 * u + 2] = upd[u]; }
   return BTKB_OK;
 }
 
@@ -1061,7 +1082,191 @@ int btkb_get_covariance(btkb_pipeline* p, float* out) {
 
 int btkb_device_pointers(btkb_pipeline* p, void** X, void** Y, void** time_out) {
   if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
-  if (X) *X = p->d_X; if (Y) *Y = p->d_Y; if (time_out) *time_out = p->d_time;
+  if (X) *X = p->d_X; if (Y) *Y = p->Y_out; if (time_out) *time_out = p->d_time;
+  return BTKB_OK;
+}
+
+// ------------------------------------------------------------------------------------- streamed chunks with carried state
+// The reference's streams are pulled one frame at a time (FeatureStream::next, stream/stream.h:16-54): an utterance never has to be
+// complete before its first frame comes out, and the look direction may change while it runs (unit_test/test_online_beamforming.py:
+// 205-225).  btkb_stream_begin / btkb_stream_submit give the batch pipe the same property at chunk granularity.  The contract is
+// pinned on the CPU in the reference's own fp64 arithmetic (tests/test_chunked_spec.py); here:
+//   K1  sees the chunk's samples behind a history prefix of min(m M - D, samples so far) samples and numbers its frames from t_base;
+//   K4  loads / stores the per-chain recurrence state (ST, UA) and tests absolute frame numbers;
+//   K5  sees the chunk's Y rows behind m R - 1 rows of history and numbers its blocks from b_base.
+// A chunked run equals the whole-utterance run bit for bit (tests/test_parity_gpu_r2.py::test_streamed_chunks_*).
+static int stream_unsupported(btkb_pipeline* p) {
+  if (p->cfg.wpe.enabled) return fail(BTKB_ERR_INVALID, "btkb_stream_begin: WPE buffers the whole utterance by definition (dereverberation.cc:500-534); submit whole utterances");
+  if (p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_stream_begin: streamed chunks are built for the register-path kernels (<= 8 channels)");
+  return BTKB_OK;
+}
+
+int btkb_stream_begin(btkb_pipeline* p, int U) {
+  if (!p) return fail(BTKB_ERR_INVALID, "btkb_stream_begin: null pipeline");
+  if (U < 1 || U > p->Ucap) return fail(BTKB_ERR_INVALID, "btkb_stream_begin: U out of range");
+  int rc = stream_unsupported(p); if (rc) return rc;
+  CK(cudaSetDevice(p->cfg.device));
+  const int Ha = p->m * p->M - p->D;
+  if (!p->d_xs[0]) {
+    p->xs_stride = round_up(Ha + p->ncap + p->D, 4);
+    for (int i = 0; i < 2; i++) CK(cudaMalloc((void**)&p->d_xs[i], (size_t)p->Ucap * p->C * p->xs_stride * sizeof(float)));
+    CK(cudaMalloc((void**)&p->d_ST, (size_t)ST_ROWS * p->Gpcap * sizeof(float)));
+    CK(cudaMalloc((void**)&p->d_tu, (size_t)p->Ucap * sizeof(int)));
+  }
+  if (p->wU != U) { p->have_w = p->have_wl = p->have_ta = p->have_R = false; p->R_is_sum = false; p->NC = 1; p->wU = 0; }
+  p->U = U; p->Gp = round_up(U * p->K, 128); p->n = 0; p->T = 0; p->nb = 0;
+  p->have_X = p->have_Y = p->have_time = p->have_ua = false;
+  p->streaming = true; p->stream_final = false; p->xs_cur = 0; p->xs_hist = 0; p->s_samples = 0;
+  p->s_tnext = p->s_tlast = p->s_bnext = p->s_blast = p->s_chunks = 0;
+  p->s_len.assign(U, 0); p->s_tu.assign(U, 0); p->lengths.assign(U, 0);
+  p->Y_out = p->d_Y + (size_t)p->Hy * p->Gp;
+  CK(cudaMemsetAsync(p->d_stats, 0, (size_t)U * 3 * sizeof(double), p->stream));
+  CK(cudaMemsetAsync(p->d_Y, 0, (size_t)p->Hy * p->Gp * sizeof(float2), p->stream));
+  return BTKB_OK;
+}
+
+int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int* lengths, int final_chunk, int do_syn) {
+  if (!p || (!samples && n > 0)) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: null argument");
+  if (!p->streaming) return fail(BTKB_ERR_STATE, "btkb_stream_submit: call btkb_stream_begin first");
+  if (p->stream_final) return fail(BTKB_ERR_STATE, "btkb_stream_submit: the stream has ended (final chunk already submitted); call btkb_stream_begin");
+  if (n < 0 || n > p->ncap) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: n exceeds max_samples");
+  if (!final_chunk && (n % p->D != 0 || n == 0)) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: a non-final chunk must hold a positive whole number of D-sample blocks");
+  if (!final_chunk && lengths) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: ragged lengths only on the final chunk");
+  if (!p->have_h) return fail(BTKB_ERR_STATE, "btkb_run: set the analysis prototype first");
+  if (!p->have_w) {
+    if (p->cfg.beamformer == BTKB_BF_MVDR) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");
+    return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");
+  }
+  if (p->wU != p->U) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: weights were set for a different number of utterances");
+  if (do_syn && !p->have_g) return fail(BTKB_ERR_STATE, "btkb_run: set the synthesis prototype first");
+  const int U = p->U, C = p->C, D = p->D;
+  std::vector<int> lloc(U);
+  int Tabs = 0;
+  for (int u = 0; u < U; u++) {
+    const int ln = lengths ? lengths[u] : n;
+    if (ln < 0 || ln > n) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: lengths[u] out of range");
+    lloc[u] = ln;
+  }
+  CK(cudaSetDevice(p->cfg.device));
+  p->launches = 0;
+  // ---- samples: [history | new] in the current buffer; `lengths` of the row count the history
+  float* xs = p->d_xs[p->xs_cur];
+  if (n > 0)
+    CK(cudaMemcpy2DAsync(xs + p->xs_hist, (size_t)p->xs_stride * sizeof(float), samples, (size_t)n * sizeof(float), (size_t)n * sizeof(float), (size_t)U * C,
+                         cudaMemcpyHostToDevice, p->stream));
+  const long long s_base = p->s_samples - p->xs_hist;   // absolute index of the row's first sample
+  for (int u = 0; u < U; u++) {
+    p->s_len[u] += lloc[u];
+    p->lengths[u] = p->xs_hist + lloc[u];
+    // frames so far: a running stream has emitted every frame whose window is complete (blocks - laN); the end of the stream adds the
+    // pd_A flush frames of zero blocks (modulated.cc:440-466)
+    const long long blocks = final_chunk ? (p->s_len[u] + D - 1) / D : (p->s_samples + n) / D;
+    p->s_tu[u] = (int)std::max<long long>(final_chunk ? blocks - p->laN + p->pdA : blocks - p->laN, 0);
+    Tabs = std::max(Tabs, p->s_tu[u]);
+  }
+  const int t_base = p->s_tnext, b_base = p->s_bnext;
+  const int Tloc = std::max(Tabs - t_base, 0);
+  if (Tloc > p->Tcap) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: the chunk yields more frames than the pipeline was sized for");
+  // Two consecutive frames ride one synthesis transform and rounding makes a frame's result depend on its partner; tiles start at
+  // even absolute blocks, so frame tau is the FIRST of its pair when tau - (pd_S - (m R - 1)) is even.  If the last frame available is
+  // such a frame its partner has not arrived yet: the block that needs it is held back until the next chunk (the end of the
+  // stream pairs it with zero, like the whole-utterance run).
+  const int q0 = (((p->pdS - (p->m * p->R - 1)) % 2) + 2) % 2;
+  const int hold = (!final_chunk && Tabs > 0 && (((Tabs - 1 - q0) % 2 + 2) % 2) == 0) ? 1 : 0;
+  const int nb_abs = std::max(Tabs - p->pdS - hold, 0);
+  const int nbloc = std::max(nb_abs - b_base, 0);
+  p->T = Tloc; p->nb = nbloc; p->n = n;
+  CK(cudaMemcpyAsync(p->d_len, p->lengths.data(), U * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemcpyAsync(p->d_tu, p->s_tu.data(), U * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  if (Tloc > 0) {
+    AnalysisArgs a{xs, p->d_len, p->d_h, p->d_X, p->d_E, U, C, p->xs_hist + n, p->xs_stride, Tloc, p->M, p->m, D, p->laN, p->Gp, 1, p->d_tw, 1, 0,
+                   (long long)(p->laN + t_base + 1) * D - s_base, t_base & 1};
+    CK(launch_analysis(a, p->stream));
+    p->launches++;
+  }
+  p->have_X = Tloc > 0;
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  if (Tloc > 0) {
+    PerBinArgs a = perbin_args(p);
+    a.t_base = t_base; a.tu = p->d_tu; a.ST = p->d_ST; a.st_load = p->s_chunks > 0 ? 1 : 0;
+    if (p->cfg.postfilter >= BTKB_PF_MCCOWAN) {
+      if (!p->have_pfR) return fail(BTKB_ERR_STATE, "McCowanPostFilter:  construct/set a noise coherence matrix");
+      const bool lef = p->cfg.postfilter == BTKB_PF_LEFKIMMIATIS;
+      CK(launch_pf_prepare(p->d_pfR, p->d_pfInvR, p->d_pfQ, C, p->K, p->cfg.pf_threshold, p->cfg.pf_min_sv, lef ? 1 : 0, p->stream));
+      p->launches++;
+      if (lef) { CK(launch_pf_lambda(p->d_pfInvR, p->have_ta ? p->d_TA : p->d_W, p->d_LAM, U, C, p->K, p->Gp, p->cfg.pf_type, p->stream)); p->launches++; }
+      a.PFQ = p->d_pfQ; a.LAM = p->d_LAM; a.pf_fbin1 = p->cfg.pf_fbin1;
+    }
+    CK(launch_perbin(a, p->stream));
+    p->launches++;
+    p->s_chunks++;
+  }
+  p->have_Y = Tloc > 0; p->pf_applied = true;
+  p->have_ua = (p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS) && p->s_chunks > 0;
+  CK(cudaEventRecord(p->ev[2], p->stream));
+  p->have_time = false;
+  if (do_syn && nbloc > 0) {
+    SynthesisArgs a{p->d_Y, p->d_len, p->d_g, p->d_time, p->d_stats, U, n, Tloc, p->M, p->m, p->cfg.r, D, p->K, p->Gp, p->pdS, p->laN, p->pdA,
+                    nbloc, nbloc * D, p->cfg.synthesis_gain, p->d_tw,
+                    (p->cfg.postfilter >= BTKB_PF_MCCOWAN) ? p->cfg.pf_min_frames + 1 : 0, b_base, t_base - p->Hy, p->d_tu,
+                    b_base & 1};
+    CK(launch_synthesis(a, p->stream));
+    p->launches++;
+    p->have_time = true;
+  }
+  CK(cudaEventRecord(p->ev[3], p->stream));
+  // ---- carry the histories over: the last min(m M - D, samples so far) samples become the head of the other sample buffer, the last
+  // m R - 1 rows of Y move to the front (through the scratch buffer when the chunk is shorter than the history)
+  const int Ha = p->m * p->M - D;
+  const int have = p->xs_hist + n;
+  const int keep = std::min(Ha, have);
+  if (!final_chunk) {
+    float* nx = p->d_xs[p->xs_cur ^ 1];
+    if (keep > 0)
+      CK(cudaMemcpy2DAsync(nx, (size_t)p->xs_stride * sizeof(float), xs + (have - keep), (size_t)p->xs_stride * sizeof(float), (size_t)keep * sizeof(float),
+                           (size_t)U * C, cudaMemcpyDeviceToDevice, p->stream));
+    p->xs_cur ^= 1; p->xs_hist = keep;
+    if (Tloc > 0 && p->Hy > 0) {
+      const size_t row = (size_t)p->Gp * sizeof(float2);
+      if (Tloc >= p->Hy) CK(cudaMemcpyAsync(p->d_Y, p->d_Y + (size_t)Tloc * p->Gp, p->Hy * row, cudaMemcpyDeviceToDevice, p->stream));
+      else {
+        int rc = ensure_scratch(p, p->Hy * row); if (rc) return rc;
+        CK(cudaMemcpyAsync(p->d_scratch, p->d_Y + (size_t)Tloc * p->Gp, p->Hy * row, cudaMemcpyDeviceToDevice, p->stream));
+        CK(cudaMemcpyAsync(p->d_Y, p->d_scratch, p->Hy * row, cudaMemcpyDeviceToDevice, p->stream));
+      }
+    }
+  }
+  p->s_samples += n;
+  p->s_tlast = t_base; p->s_blast = b_base; p->s_tnext = Tabs; p->s_bnext = std::max(nb_abs, b_base);
+  p->stream_final = final_chunk != 0;
+  return BTKB_OK;
+}
+
+int btkb_reset(btkb_pipeline* p) {   // FeatureStream::reset() of every stream of the graph (stream/stream.h:41): rewind, forget the adaptive state
+  if (!p) return fail(BTKB_ERR_INVALID, "btkb_reset: null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaStreamSynchronize(p->stream));
+  if (p->streaming) return btkb_stream_begin(p, p->U);
+  p->have_X = p->have_Y = p->have_time = p->have_ua = false;
+  p->U = 0; p->T = 0; p->nb = 0;
+  return BTKB_OK;
+}
+
+int btkb_set_stream(btkb_pipeline* p, void* cuda_stream) {
+  if (!p) return fail(BTKB_ERR_INVALID, "btkb_set_stream: null pipeline");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaStreamSynchronize(p->stream));
+  if (p->owns_stream && p->stream) cudaStreamDestroy(p->stream);
+  if (cuda_stream) { p->stream = (cudaStream_t)cuda_stream; p->owns_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)); p->owns_stream = true; }
+  return BTKB_OK;
+}
+
+int btkb_stream_position(const btkb_pipeline* p, int* first_frame, int* first_block) {
+  if (!p || !p->streaming) return fail(BTKB_ERR_STATE, "btkb_stream_position: not streaming");
+  if (first_frame) *first_frame = p->s_tlast;
+  if (first_block) *first_block = p->s_blast;
   return BTKB_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 namespace btkb {
 
@@ -20,6 +21,15 @@ struct AnalysisArgs {
   const float2* twtab;   // exp(+2 pi i n / M), n < M (device)
   int tiles_per_cta;     // set by the launcher
   int debug;             // BTKB_ANALYSIS_DEBUG bit mask (profiling experiments only): 1 skip X stores, 2 skip fold, 4 skip FFT passes
+  // Index of the sample just past local frame 0's window, in the coordinates of the staged sample rows: (laN + 1) D for a whole
+  // utterance; for a streamed chunk (btkb_stream_submit) (laN + t_base + 1) D - s_base, where t_base is the absolute number of the
+  // chunk's first frame and s_base the absolute index of the first sample in the row (history prefix of m M - D samples).
+  // `lengths` counts the valid samples of the ROW (history included); X / E rows are chunk-local.
+  long long w_base;
+  // Frames ride the transforms in PAIRS (two real channels x two frames), and floating-point rounding makes a frame's result depend
+  // on which frame it is paired with.  A streamed chunk that starts at an odd absolute frame number therefore starts its first tile
+  // one frame early (t_skip = 1; that frame is computed and discarded), so that pairs are the whole-utterance run's pairs.
+  int t_skip;
 };
 
 struct SynthesisArgs {
@@ -29,6 +39,11 @@ struct SynthesisArgs {
   const float2* twtab;   // exp(+2 pi i n / M), n < M (device)
   int onesided;          // frames tau < onesided carry bins 0..M/2 only (upper half zero): the McCowan / Lefkimmiatis post-filters
                          // leave vector_[M/2+1..M-1] untouched until frame_no_ >= min_frames (postfilter.cc:896-901)
+  // streamed chunks (btkb_stream_submit): b_base = absolute number of the chunk's first output block, y_base = absolute frame number
+  // of row 0 of Y (the m R - 1 frames of history a block reaches back to precede the chunk's own frames), tu[u] = absolute number of
+  // frames utterance u has produced so far (null: whole utterances, derived from `lengths`).  nb / out rows are chunk-local.
+  int b_base, y_base; const int* tu;
+  int b_skip;   // 1: the chunk starts at an odd absolute block; tiles start one block early so that frame pairs match the whole run's
 };
 
 struct LmsArgs {
@@ -64,7 +79,12 @@ struct PerBinArgs {
   RlsArgs rls;
   float energy_threshold;
   float2* Scov; int Ts;   // 64-mic tensor-core covariance: series-major workspace S[g][c][Ts] (btkb_cov_tc.cu)
+  // streamed chunks (btkb_stream_submit): t_base = absolute number of the chunk's first frame (the recurrences test absolute frame
+  // numbers: first frame, min_frames, step-size halving, the post-filters' first two frames), tu[u] = absolute frames of utterance u
+  // so far, ST = carried per-chain state [ST_ROWS][Gp] (always stored when non-null, loaded when st_load; u rides in UA).
+  int t_base; const int* tu; float* ST; int st_load;
 };
+constexpr int ST_ROWS = 72;   // 8 scalars + the largest state: RLS at C = 8 (8 + 56) / Zelinski at C = 8 (56 + 8)
 
 // multi-channel WPE (btkb_wpe.cu)
 struct WpeArgs {
@@ -126,6 +146,7 @@ cudaError_t launch_lcmv_weights(const double* delaysT, const double* delaysJ, fl
 cudaError_t launch_spectral_recursion(const PerBinArgs& a, float mu, int noconj, cudaStream_t st);
 cudaError_t launch_diffuse_model(const double* mpos, float2* R, int U, int C, int M, int K, int Gp, float samplerate, float sspeed, cudaStream_t st);
 cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count, cudaStream_t st);
+cudaError_t launch_adaptive_rebase(const float2* Wold, const float2* Wnew, float2* UA, float* ST, int has_P, int U, int C, int K, int Gp, cudaStream_t st);
 cudaError_t launch_ua_to_wa(const float2* UA, const float2* W, float2* WA, int U, int C, int K, int Gp, cudaStream_t st);
 cudaError_t launch_noise_mask(const float* E, const int* lengths, const double* labels, unsigned char* mask, int* count, int U, int T, int D, int laN, int pdA,
                               float samplerate, float thr, cudaStream_t st);
@@ -137,6 +158,11 @@ cudaError_t launch_pf_divide_nondiag(double2* Rpf, int C, int K, float mu, cudaS
 cudaError_t launch_pf_prepare(const double2* Rpf, double2* invR, float2* PFQ, int C, int K, float threshold, double min_sv, int want_inverse, cudaStream_t st);
 cudaError_t launch_pf_lambda(const double2* invR, const float2* TA, float* LAM, int U, int C, int K, int Gp, int pf_type, cudaStream_t st);
 inline int pf_num_consts(int C) { return C * (C - 1) + 2 * C; }  // q'[NP], rho'[C], q''[NP], rho''[C]
+
+// Kernel-variant switches BTKB_ANALYSIS_PACKED / BTKB_SYNTHESIS_PACKED / BTKB_PERBIN_PACKED: 1 (default since round 2) = packed 2 x fp32
+// arithmetic (FADD2 / FMUL2 / FFMA2, btkb_f2.cuh), 0 = the scalar kernels.  Bit-identical results, verified on B200 kernel by kernel
+// (tests/test_zz_host_surface.py::test_packed_fp32_kernel_equals_the_scalar_kernel); read at every launch so one process can compare.
+inline bool env_packed(const char* name) { const char* e = getenv(name); return e ? atoi(e) != 0 : true; }
 
 __host__ __device__ inline int frames_of(int len, int D, int laN, int pdA) { return (len + D - 1) / D - laN + pdA; }
 

@@ -27,11 +27,22 @@
 #include "../../include/btkb.h"
 #include <cstdlib>
 
+// Channel counts: every C in 1..8 is instantiated (the reference takes any number of set_channel() calls, beamformer.cc:1017-1021).
+// To keep the build parallel this file is compiled twice: BTKB_CSET=0 -> C in {2, 4, 8} and the public launch_* entry points,
+// BTKB_CSET=1 -> C in {1, 3, 5, 6, 7} behind launch_*_cset1 (csrc/Makefile).
+#ifndef BTKB_CSET
+#define BTKB_CSET 0
+#endif
+
 namespace btkb {
+
+cudaError_t launch_perbin_cset1(const PerBinArgs& a, cudaStream_t st);
+cudaError_t launch_covariance_cset1(const PerBinArgs& a, cudaStream_t st);
+cudaError_t launch_spectral_recursion_cset1(const PerBinArgs& a, float mu, int noconj, cudaStream_t st);
 
 constexpr int MODE_STATIC = 0, MODE_LMS = 1;
 
-// PK = true (NLMS mode only, BTKB_PERBIN_PACKED=1, off by default): the complex arithmetic of the frame loop in packed 2 x fp32
+// PK = true (the default; BTKB_PERBIN_PACKED=0 selects the scalar form): the complex arithmetic of the frame loop in packed 2 x fp32
 // instructions — 2 FFMA2 per complex MAC instead of 4 FFMA, about half the fp32 issue slots of the recurrence.  Bit-identical
 // results (tests/test_fft_packed_host.py checks every packed formula against the scalar expression it replaces).
 template <int C, int MODE, int PF, bool PK = false>
@@ -43,7 +54,11 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
   const int u = valid ? g / a.K : a.U - 1;
   const int k = valid ? g - u * a.K : 0;
   const int len = a.lengths ? a.lengths[u] : 0;
-  const int Tu = valid ? frames_of(len, a.D, a.laN, a.pdA) : 0;
+  const int Tu = valid ? (a.tu ? a.tu[u] - a.t_base : frames_of(len, a.D, a.laN, a.pdA)) : 0;   // live frames of this chain among the a.T local ones
+  // carried state of a streamed chunk (btkb_stream_submit): row i of ST belongs to this chain at ST[i Gp + g]
+  const bool has_st = a.ST != nullptr && valid;
+  float* const stp = a.ST + (valid ? g : 0);   // (never formed from a null test: ptxas speculated the state loads past a pointer-valued select)
+  const bool st_load = has_st && a.st_load != 0;
 
   TileRing<C> ring;
   ring.init(smem_raw, &tmX, g0, a.T);
@@ -108,16 +123,34 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
   int slow_cnt = a.lms.slowdown_after + 1;  // first halving at t == slowdown_after
   const float one_m_beta = 1.0f - a.lms.beta;
   const float inv_sil = 1.0f / a.lms.sil_thresh;
+  if (st_load) {   // resume where the previous chunk of the stream stopped
+    const size_t gp = (size_t)a.Gp;
+    if (MODE == MODE_LMS) {
+      se = stp[0 * gp]; Eavg = stp[1 * gp]; gamma = stp[2 * gp]; slow_cnt = __float_as_int(stp[3 * gp]); n_updates = __float_as_int(stp[4 * gp]);
+#pragma unroll
+      for (int c = 0; c < C; c++) uw[c] = a.UA[(size_t)c * a.Gp + g];
+    }
+    if (PF == 1) {
+#pragma unroll
+      for (int i = 0; i < NP; i++) csd[i] = make_float2(stp[(8 + 2 * i) * gp], stp[(9 + 2 * i) * gp]);
+    }
+    if (PF >= 2) { S1 = make_float2(stp[8 * gp], stp[9 * gp]); S2 = make_float2(stp[10 * gp], stp[11 * gp]); }
+    if (PF) {
+#pragma unroll
+      for (int c = 0; c < C; c++) psd[c] = stp[((PF == 1 ? 8 + 2 * NP : 12) + c) * gp];
+    }
+  }
 
-  for (int t = 0; t < a.T; t++) {
+  for (int tl = 0; tl < a.T; tl++) {
+    const int t = a.t_base + tl;   // absolute frame number: what the recurrences test
     float2 x[C];
-    ring.fetch(t, a.T, x);
+    ring.fetch(tl, a.T, x);
     float energy = e_next;
-    if (MODE == MODE_LMS && t + 1 < a.T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
+    if (MODE == MODE_LMS && tl + 1 < a.T) e_next = __ldg(a.E + (size_t)(tl + 1) * a.U + u);
 
     // upper branch: Yc = w^H x
     float2 y = cdot<C, true, PK>(x, w);
-    const bool live = t < Tu;
+    const bool live = tl < Tu;
 
     if (MODE == MODE_LMS) {
       // pybeamformer.py:665-734 with isamp == t
@@ -210,7 +243,7 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
       Wf = (Wf < 1.0e-4f) ? 1.0e-4f : Wf;
       if (!(Wf == Wf)) Wf = 1.0e-4f;  // all-zero snapshot: 0/0 in the reference; keep the output finite
       if (t - 1 >= a.pf_min_frames) { y.x *= Wf; y.y *= Wf; }
-      if (a.PFW != nullptr && valid) a.PFW[(size_t)t * a.Gp + g] = Wf;
+      if (a.PFW != nullptr && valid) a.PFW[(size_t)tl * a.Gp + g] = Wf;
     } else if constexpr (PF == 1) {
       // ZelinskiFilter_f (postfilter.cc:57-140); alpha = 0 for the first two frames (postfilter.cc:460-463)
       const float al = (t >= 2) ? a.pf_alpha : 0.f;
@@ -246,10 +279,10 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
       Wf = (Wf < 1.0e-4f) ? 1.0e-4f : Wf;
       if (!(den > 0.f)) Wf = 1.0e-4f;  // all-zero snapshot: the reference computes 0/0 = NaN -> fails both tests; keep finite
       if (t - 1 >= a.pf_min_frames) { y.x *= Wf; y.y *= Wf; }
-      if (a.PFW != nullptr && valid) a.PFW[(size_t)t * a.Gp + g] = Wf;
+      if (a.PFW != nullptr && valid) a.PFW[(size_t)tl * a.Gp + g] = Wf;
     }
 
-    if (valid) a.Y[(size_t)t * a.Gp + g] = live ? y : make_float2(0.f, 0.f);
+    if (valid) a.Y[(size_t)tl * a.Gp + g] = live ? y : make_float2(0.f, 0.f);
   }
 
   if (MODE == MODE_LMS && valid) {
@@ -258,6 +291,19 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
       for (int c = 0; c < C; c++) a.UA[(size_t)c * a.Gp + g] = uw[c];
     }
     if (k == 0 && a.stats_updates != nullptr) a.stats_updates[u] = (float)n_updates;
+  }
+  if (has_st) {
+    const size_t gp = (size_t)a.Gp;
+    if (MODE == MODE_LMS) { stp[0 * gp] = se; stp[1 * gp] = Eavg; stp[2 * gp] = gamma; stp[3 * gp] = __int_as_float(slow_cnt); stp[4 * gp] = __int_as_float(n_updates); }
+    if (PF == 1) {
+#pragma unroll
+      for (int i = 0; i < NP; i++) { stp[(8 + 2 * i) * gp] = csd[i].x; stp[(9 + 2 * i) * gp] = csd[i].y; }
+    }
+    if (PF >= 2) { stp[8 * gp] = S1.x; stp[9 * gp] = S1.y; stp[10 * gp] = S2.x; stp[11 * gp] = S2.y; }
+    if (PF) {
+#pragma unroll
+      for (int c = 0; c < C; c++) stp[((PF == 1 ? 8 + 2 * NP : 12) + c) * gp] = psd[c];
+    }
   }
 }
 
@@ -271,7 +317,7 @@ __global__ void __launch_bounds__(TILE) k_perbin(const __grid_constant__ CUtenso
 //   u  <- u + gamma ep p^H / (mu + ip) - reg u Pt^H      (ep = Yc - u.x with the OLD u, pybeamformer.py:843-847)
 //   |u|^2 > alpha2: quadratic constraint with va = Pt u^H (:851-861);  |u|^2 > max_wa_l2norm: rescale u and reset
 //   Pt = (I - C v v^H) / init_diagonal_load (:862-865).
-// PK = true (BTKB_PERBIN_PACKED=1, off by default): the always-executed part of the update (projector step, p = Pt x~, the rank-one
+// PK = true (the default; BTKB_PERBIN_PACKED=0 for the scalar form): the always-executed part of the update (projector step, p = Pt x~, the rank-one
 // update of Pt, the new u with its regularisation term) in packed 2 x fp32 instructions (rls_core_step, btkb_nlms_math.cuh; bit-identical,
 // checked on the CPU); the rarely taken constraint branches stay scalar.
 template <int C, bool PK = false>
@@ -283,7 +329,10 @@ __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUt
   const int u = valid ? g / a.K : a.U - 1;
   const int k = valid ? g - u * a.K : 0;
   const int len = a.lengths ? a.lengths[u] : 0;
-  const int Tu = valid ? frames_of(len, a.D, a.laN, a.pdA) : 0;
+  const int Tu = valid ? (a.tu ? a.tu[u] - a.t_base : frames_of(len, a.D, a.laN, a.pdA)) : 0;
+  const bool has_st = a.ST != nullptr && valid;   // carried state of a streamed chunk (see k_perbin)
+  float* const stp = a.ST + (valid ? g : 0);
+  const bool st_load = has_st && a.st_load != 0;
 
   TileRing<C> ring;
   ring.init(smem_raw, &tmX, g0, a.T);
@@ -312,14 +361,23 @@ __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUt
   const float inv_sil = 1.0f / a.rls.sil_thresh;
   const float mu = a.rls.mu, inv_mu = 1.0f / a.rls.mu;
   const int opt = a.rls.constraint_option;
+  if (st_load) {
+    const size_t gp = (size_t)a.Gp;
+    Eavg = stp[0 * gp]; n_updates = __float_as_int(stp[1 * gp]);
+#pragma unroll
+    for (int c = 0; c < C; c++) { uw[c] = a.UA[(size_t)c * a.Gp + g]; P.d[c] = stp[(8 + c) * gp]; }
+#pragma unroll
+    for (int i = 0; i < C * (C - 1) / 2; i++) P.o[i] = make_float2(stp[(8 + C + 2 * i) * gp], stp[(9 + C + 2 * i) * gp]);
+  }
 
-  for (int t = 0; t < a.T; t++) {
+  for (int tl = 0; tl < a.T; tl++) {
+    const int t = a.t_base + tl;   // absolute frame number
     float2 x[C];
-    ring.fetch(t, a.T, x);
+    ring.fetch(tl, a.T, x);
     const float energy = e_next;
-    if (t + 1 < a.T) e_next = __ldg(a.E + (size_t)(t + 1) * a.U + u);
+    if (tl + 1 < a.T) e_next = __ldg(a.E + (size_t)(tl + 1) * a.U + u);
     float2 y = cdot<C, true, PK>(x, w);   // Yc = v^H x
-    const bool live = t < Tu;
+    const bool live = tl < Tu;
     const bool adapt = energy > (Eavg * inv_sil);
     if (adapt && live) {
       float2 un[C];
@@ -363,7 +421,7 @@ __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUt
     }
     if (t >= a.rls.min_frames) y = csub(y, cdot<C, false, PK>(uw, x));
     Eavg = fmaf(Eavg, a.rls.beta, one_m_beta * energy);
-    if (valid) a.Y[(size_t)t * a.Gp + g] = live ? y : make_float2(0.f, 0.f);
+    if (valid) a.Y[(size_t)tl * a.Gp + g] = live ? y : make_float2(0.f, 0.f);
   }
   if (valid) {
     if (a.UA != nullptr) {
@@ -371,6 +429,14 @@ __global__ void __launch_bounds__(TILE) k_perbin_rls(const __grid_constant__ CUt
       for (int c = 0; c < C; c++) a.UA[(size_t)c * a.Gp + g] = uw[c];
     }
     if (k == 0 && a.stats_updates != nullptr) a.stats_updates[u] = (float)n_updates;
+  }
+  if (has_st) {
+    const size_t gp = (size_t)a.Gp;
+    stp[0 * gp] = Eavg; stp[1 * gp] = __int_as_float(n_updates);
+#pragma unroll
+    for (int c = 0; c < C; c++) stp[(8 + c) * gp] = P.d[c];
+#pragma unroll
+    for (int i = 0; i < C * (C - 1) / 2; i++) { stp[(8 + C + 2 * i) * gp] = P.o[i].x; stp[(9 + C + 2 * i) * gp] = P.o[i].y; }
   }
 }
 
@@ -494,8 +560,7 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
   } while (0)
   if (a.kind == BTKB_BF_GSC_RLS) {
     if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue;
-    const char* evr = getenv("BTKB_PERBIN_PACKED");
-    auto kern = (evr && atoi(evr) != 0) ? k_perbin_rls<C, true> : k_perbin_rls<C, false>;
+    auto kern = env_packed("BTKB_PERBIN_PACKED") ? k_perbin_rls<C, true> : k_perbin_rls<C, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, TILE, smem, st>>>(tm, a);
@@ -503,8 +568,7 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
   }
   if (lms) {
     if (pf != BTKB_PF_NONE) return cudaErrorInvalidValue;
-    const char* ev = getenv("BTKB_PERBIN_PACKED");   // =1: packed 2 x fp32 NLMS recurrence (bit-identical; off by default); read at every launch
-    if (ev && atoi(ev) != 0) {
+    if (env_packed("BTKB_PERBIN_PACKED")) {   // packed 2 x fp32 NLMS recurrence (bit-identical) unless BTKB_PERBIN_PACKED=0; read at every launch
       auto kern = k_perbin<C, MODE_LMS, 0, true>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
@@ -514,8 +578,7 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
     BTKB_LAUNCH(MODE_LMS, 0);
   }
   if (pf == BTKB_PF_ZELINSKI) {
-    const char* ev = getenv("BTKB_PERBIN_PACKED");   // =1: packed 2 x fp32 CSD recursions (bit-identical; off by default)
-    if (ev && atoi(ev) != 0) {
+    if (env_packed("BTKB_PERBIN_PACKED")) {   // packed 2 x fp32 CSD recursions (bit-identical)
       auto kern = k_perbin<C, MODE_STATIC, 1, true>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
@@ -524,8 +587,7 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
     }
     BTKB_LAUNCH(MODE_STATIC, 1);
   }
-  const char* evp = getenv("BTKB_PERBIN_PACKED");
-  const bool pk = evp && atoi(evp) != 0;
+  const bool pk = env_packed("BTKB_PERBIN_PACKED");
 #define BTKB_LAUNCH_PK(PF_)                                                                      \
   do {                                                                                           \
     auto kern = k_perbin<C, MODE_STATIC, PF_, true>;                                             \
@@ -542,21 +604,33 @@ static cudaError_t launch_perbin_c(const PerBinArgs& a, cudaStream_t st) {
 #undef BTKB_LAUNCH
 }
 
+#if BTKB_CSET == 0
 cudaError_t launch_perbin(const PerBinArgs& a, cudaStream_t st) {
   if (a.T <= 0 || a.G <= 0) return cudaSuccess;
   switch (a.C) {
     case 2: return launch_perbin_c<2>(a, st);
     case 4: return launch_perbin_c<4>(a, st);
     case 8: return launch_perbin_c<8>(a, st);
+    default: return launch_perbin_cset1(a, st);
+  }
+}
+#else
+cudaError_t launch_perbin_cset1(const PerBinArgs& a, cudaStream_t st) {
+  switch (a.C) {
+    case 1: return launch_perbin_c<1>(a, st);
+    case 3: return launch_perbin_c<3>(a, st);
+    case 5: return launch_perbin_c<5>(a, st);
+    case 6: return launch_perbin_c<6>(a, st);
+    case 7: return launch_perbin_c<7>(a, st);
     default: return cudaErrorInvalidValue;
   }
 }
+#endif
 
 template <int C>
 static cudaError_t launch_cov_c(const PerBinArgs& a, cudaStream_t st) {
   const size_t smem = ring_smem<C>();
-  const char* ev = getenv("BTKB_PERBIN_PACKED");
-  auto kern = (ev && atoi(ev) != 0) ? k_covariance<C, true> : k_covariance<C, false>;
+  auto kern = env_packed("BTKB_PERBIN_PACKED") ? k_covariance<C, true> : k_covariance<C, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   CUtensorMap tm;
@@ -566,15 +640,28 @@ static cudaError_t launch_cov_c(const PerBinArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+#if BTKB_CSET == 0
 cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st) {
   if (a.T <= 0 || a.G <= 0) return cudaSuccess;
   switch (a.C) {
     case 2: return launch_cov_c<2>(a, st);
     case 4: return launch_cov_c<4>(a, st);
     case 8: return launch_cov_c<8>(a, st);
+    default: return launch_covariance_cset1(a, st);
+  }
+}
+#else
+cudaError_t launch_covariance_cset1(const PerBinArgs& a, cudaStream_t st) {
+  switch (a.C) {
+    case 1: return launch_cov_c<1>(a, st);
+    case 3: return launch_cov_c<3>(a, st);
+    case 5: return launch_cov_c<5>(a, st);
+    case 6: return launch_cov_c<6>(a, st);
+    case 7: return launch_cov_c<7>(a, st);
     default: return cudaErrorInvalidValue;
   }
 }
+#endif
 
 }  // namespace btkb
 
@@ -599,13 +686,26 @@ static cudaError_t launch_rec_c(const PerBinArgs& a, float mu, int noconj, cudaS
   }
   return cudaGetLastError();
 }
+#if BTKB_CSET == 0
 cudaError_t launch_spectral_recursion(const PerBinArgs& a, float mu, int noconj, cudaStream_t st) {
   if (a.T <= 0 || a.G <= 0) return cudaSuccess;
   switch (a.C) {
     case 2: return launch_rec_c<2>(a, mu, noconj, st);
     case 4: return launch_rec_c<4>(a, mu, noconj, st);
     case 8: return launch_rec_c<8>(a, mu, noconj, st);
+    default: return launch_spectral_recursion_cset1(a, mu, noconj, st);
+  }
+}
+#else
+cudaError_t launch_spectral_recursion_cset1(const PerBinArgs& a, float mu, int noconj, cudaStream_t st) {
+  switch (a.C) {
+    case 1: return launch_rec_c<1>(a, mu, noconj, st);
+    case 3: return launch_rec_c<3>(a, mu, noconj, st);
+    case 5: return launch_rec_c<5>(a, mu, noconj, st);
+    case 6: return launch_rec_c<6>(a, mu, noconj, st);
+    case 7: return launch_rec_c<7>(a, mu, noconj, st);
     default: return cudaErrorInvalidValue;
   }
 }
+#endif
 }  // namespace btkb

@@ -38,10 +38,10 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a
   float2* bufB = fbuf + (grp * 2 + 1) * Plan::BUF;
 
   const int len = a.lengths ? a.lengths[u] : a.n;
-  const int Tu = frames_of(len, D, a.laN, a.pdA);
+  const int Tu = a.tu ? a.tu[u] : frames_of(len, D, a.laN, a.pdA);   // absolute frame / block numbers below; t0 and the output rows are chunk-local
   const int nbu = max(Tu - a.pdS, 0);
-  const int t0 = tile * FB;
-  const int tau0 = t0 + a.pdS - R * (m - 1) - (R - 1);  // first v frame of the tile (may be negative)
+  const int t0 = tile * FB - a.b_skip;   // chunk-local number of the tile's first block (-1: a discarded block that keeps the frame pairs aligned)
+  const int tau0 = a.b_base + t0 + a.pdS - R * (m - 1) - (R - 1);  // first v frame of the tile (may be negative)
 
   FftTwiddles<M, -1> tw;
   tw.init(tg);
@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a
         const bool cj = i > M / 2;
         const bool edge = (k == 0) || (k == M / 2);
         float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
-        if (va) ya = __ldg(a.Y + (size_t)ta * a.Gp + (size_t)u * K + k);
-        if (vb) yb = __ldg(a.Y + (size_t)tb * a.Gp + (size_t)u * K + k);
+        if (va) ya = __ldg(a.Y + (size_t)(ta - a.y_base) * a.Gp + (size_t)u * K + k);
+        if (vb) yb = __ldg(a.Y + (size_t)(tb - a.y_base) * a.Gp + (size_t)u * K + k);
         if (edge) { ya.y = 0.f; yb.y = 0.f; }
         if (cj) { ya.y = -ya.y; yb.y = -yb.y; }
         if (a.onesided > 0 && !edge) {  // Re IFFT of a spectrum whose upper half is zero = half the Hermitian one (DC, Nyquist whole)
@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a
   const int nthreads = G * NT;
   for (int o = tid; o < FB * D; o += nthreads) {
     const int tl = o / D, d = o % D;
-    const int t = t0 + tl;
-    if (t >= a.nb) break;
+    if (t0 + tl >= a.nb) break;
+    if (t0 + tl < 0) continue;
+    const int t = a.b_base + t0 + tl;   // absolute block number
     float acc = 0.f;
     if (t < nbu) {
       for (int s = 0; s < R; s++) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a
       }
       if (a.gain > 0) acc *= (float)a.gain;
     }
-    a.out[(size_t)u * a.nb_stride + (size_t)t * D + (D - 1 - d)] = acc;
+    a.out[(size_t)u * a.nb_stride + (size_t)(t0 + tl) * D + (D - 1 - d)] = acc;
     sq = fmaf(acc, acc, sq);
   }
   if (a.stats != nullptr) {
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_generic(SynthesisArgs a
 // PK = true: packed 2 x fp32 arithmetic (btkb_f2.cuh) for the frame-pair combination Y_a + i Y_b, the transforms (the in-place pass
 // chain of btkb_fft.cuh, whose registers hold the whole natural-order spectrum after the last pass) and the polyphase MACs (the
 // R = 2 partial sums of an output sample are the two halves of one FFMA2 chain).  Same operations and roundings per component as
-// PK = false.  Selected with BTKB_SYNTHESIS_PACKED=1 (off by default until it has been timed on a B200).
+// PK = false.  The default since round 2 (0.143 vs 0.161 ms at configs[1] on B200); BTKB_SYNTHESIS_PACKED=0 selects the scalar kernel.
 template <int M, int FB, int G, int MT, int RR, bool PK = false>
 __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
   using Plan = FftPlan<M>;
@@ -156,17 +157,18 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
   float2* buf1 = fbuf + (grp * 2 + 1) * Plan::BUF;
 
   const int len = a.lengths[u];
-  const int Tu = frames_of(len, D, a.laN, a.pdA);
+  const int Tu = a.tu ? a.tu[u] : frames_of(len, D, a.laN, a.pdA);   // absolute frame / block numbers below; t0 and the output rows are chunk-local
   const int nbu = max(Tu - a.pdS, 0);
-  const int t0 = tile * FB;
-  const int tau0 = t0 + a.pdS - RR * (MT - 1) - (RR - 1);
+  const int t0 = tile * FB - a.b_skip;   // chunk-local number of the tile's first block (-1: a discarded block that keeps the frame pairs aligned)
+  const int tau0 = a.b_base + t0 + a.pdS - RR * (MT - 1) - (RR - 1);
 
   // ---- stage Y rows
   for (int e = tid; e < NVP * K; e += NTHREADS) {
     const int fr = e / K, k = e - fr * K;
     const int tau = tau0 + fr;
-    const bool ok = (fr < NV) && tau >= 0 && tau < Tu;
-    const float2* src = ok ? a.Y + (size_t)tau * a.Gp + (size_t)u * K + k : a.Y;
+    const bool ok = tau >= 0 && tau < Tu;   // (rows NV..NVP-1 are not used by this tile's blocks but are the pair partners of rows that are: every
+                                            // frame must ride its transform with the same partner whatever the tiling, see SynthesisArgs::b_skip)
+    const float2* src = ok ? a.Y + (size_t)(tau - a.y_base) * a.Gp + (size_t)u * K + k : a.Y;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(rows + (size_t)fr * ROW + 2 * k)), "l"(src), "r"(ok ? 8 : 0) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -274,48 +276,58 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
     }
   }
 
-  // ---- polyphase + overlap-add (taps in registers)
+  // ---- polyphase + overlap-add (taps in registers).  Output block tl of position d needs v rows tl + s2 + RR q (q < MT) at column
+  // d + s2 D: consecutive blocks slide that window by ONE row, so the rows a position has read stay in registers (the block loop
+  // is unrolled, the shift is register renaming) and each block costs RR new shared-memory reads instead of RR MT.  Arithmetic
+  // and its order are those of the direct form: w_s2 = sum_k g[..] v[..] with k ascending, acc = (0 + w_0) + w_1.
   float sq = 0.f;
+  constexpr int WL = RR * (MT - 1) + 1;
 #pragma unroll
   for (int j = 0; j < ND; j++) {
     const int d = tid + j * NTHREADS;
     if (d < D) {
+      float win[RR][WL];
+#pragma unroll
+      for (int s2 = 0; s2 < RR; s2++)
+#pragma unroll
+        for (int i = 0; i < WL - 1; i++) win[s2][i] = rows[(size_t)(s2 + i) * ROW + d + s2 * D];
+#pragma unroll
       for (int tl = 0; tl < FB; tl++) {
-        const int t = t0 + tl;
-        if (t >= a.nb) break;
-        float acc = 0.f;
-        if (PK && RR == 2 && t < nbu) {
-          // both partial sums w_{s2}, s2 = 0, 1, in one chain: taps (g[d + kM'], g[d + D + kM']) times (v_{t-1-2k}[d], v_{t-2k}[d + D]);
-          // the s2 = 0 term does not exist for the first block of an utterance (twf = t - 1 < 0)
-          float2 w2 = make_float2(0.f, 0.f);
+        const int t = a.b_base + t0 + tl;   // absolute block number
 #pragma unroll
-          for (int k = 0; k < MT; k++) {
-            const int slot0 = tl - RR * k + RR * (MT - 1);
-            const float2 vv = make_float2(rows[(size_t)slot0 * ROW + d], rows[(size_t)(slot0 + 1) * ROW + d + D]);
-            w2 = f2_fma(make_float2(gt[j][0][k], gt[j][1][k]), vv, w2);
-          }
-          acc = (t >= 1 ? w2.x : 0.f) + acc;   // acc = 0 + w_0, then + w_1: the scalar order
-          acc += w2.y;
-          if (a.gain > 0) acc *= (float)a.gain;
-        } else
-        if (t < nbu) {
+        for (int s2 = 0; s2 < RR; s2++) win[s2][WL - 1] = rows[(size_t)(tl + s2 + WL - 1) * ROW + d + s2 * D];
+        if (t0 + tl >= 0 && t0 + tl < a.nb) {
+          float acc = 0.f;
+          if (PK && RR == 2 && t < nbu) {
+            // both partial sums w_{s2}, s2 = 0, 1, in one chain: taps (g[d + kM'], g[d + D + kM']) times (v_{t-1-2k}[d], v_{t-2k}[d + D]);
+            // the s2 = 0 term does not exist for the first block of an utterance (twf = t - 1 < 0)
+            float2 w2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int s2 = 0; s2 < RR; s2++) {
-            const int twf = t - (RR - 1 - s2);
-            float w = 0.f;
-            if (twf >= 0) {
+            for (int k = 0; k < MT; k++)
+              w2 = f2_fma(make_float2(gt[j][0][k], gt[j][1][k]), make_float2(win[0][RR * (MT - 1 - k)], win[RR - 1][RR * (MT - 1 - k)]), w2);
+            acc = (t >= 1 ? w2.x : 0.f) + acc;   // acc = 0 + w_0, then + w_1: the scalar order
+            acc += w2.y;
+            if (a.gain > 0) acc *= (float)a.gain;
+          } else if (t < nbu) {
 #pragma unroll
-              for (int k = 0; k < MT; k++) {
-                const int slot = tl + s2 - RR * k + RR * (MT - 1);
-                w = fmaf(gt[j][s2][k], rows[(size_t)slot * ROW + d + s2 * D], w);
+            for (int s2 = 0; s2 < RR; s2++) {
+              const int twf = t - (RR - 1 - s2);
+              float w = 0.f;
+              if (twf >= 0) {
+#pragma unroll
+                for (int k = 0; k < MT; k++) w = fmaf(gt[j][s2][k], win[s2][RR * (MT - 1 - k)], w);
               }
+              acc += w;
             }
-            acc += w;
+            if (a.gain > 0) acc *= (float)a.gain;
           }
-          if (a.gain > 0) acc *= (float)a.gain;
+          a.out[(size_t)u * a.nb_stride + (size_t)(t0 + tl) * D + (D - 1 - d)] = acc;
+          sq = fmaf(acc, acc, sq);
         }
-        a.out[(size_t)u * a.nb_stride + (size_t)t * D + (D - 1 - d)] = acc;
-        sq = fmaf(acc, acc, sq);
+#pragma unroll
+        for (int s2 = 0; s2 < RR; s2++)
+#pragma unroll
+          for (int i = 0; i < WL - 1; i++) win[s2][i] = win[s2][i + 1];
       }
     }
   }
@@ -341,13 +353,12 @@ static cudaError_t launch_synthesis_fast(const SynthesisArgs& a, cudaStream_t st
   constexpr int NVP = (NV + 3) & ~3;
   constexpr int ROW = (((M / 2 + 1) * 2 + 3) & ~3);
   size_t smem = sizeof(float) * (size_t)NVP * ROW + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * 32;
-  const char* ev = getenv("BTKB_SYNTHESIS_PACKED");   // =1: packed 2 x fp32 variant (same results; off by default); read at every launch
-  const bool packed = ev && atoi(ev) != 0;
+  const bool packed = env_packed("BTKB_SYNTHESIS_PACKED");   // packed 2 x fp32 variant unless BTKB_SYNTHESIS_PACKED=0 (same results); read at every launch
   auto kern = packed ? k_synthesis_fast<M, FB, G, MT, RR, true> : k_synthesis_fast<M, FB, G, MT, RR, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (a.nb <= 0) return cudaSuccess;
-  dim3 grid((a.nb + FB - 1) / FB, a.U);
+  dim3 grid((a.nb + a.b_skip + FB - 1) / FB, a.U);
   kern<<<grid, G * Plan::NT, smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -366,7 +377,7 @@ static cudaError_t launch_synthesis_m(const SynthesisArgs& a, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (a.nb <= 0) return cudaSuccess;
-  dim3 grid((a.nb + FB - 1) / FB, a.U);
+  dim3 grid((a.nb + a.b_skip + FB - 1) / FB, a.U);
   kern<<<grid, G * Plan::NT, smem, st>>>(a);
   return cudaGetLastError();
 }

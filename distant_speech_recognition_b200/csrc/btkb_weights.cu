@@ -97,6 +97,74 @@ __global__ void k_blocking(const float2* W, const float2* IN, float2* OUT, int U
   }
 }
 
+// Look-direction change in the middle of a stream (unit_test/test_online_beamforming.py:205-225 -> calc_beamformer_weights,
+// pybeamformer.py:736-743 / 903-910): the reference keeps its adaptive state in the blocking-matrix basis — waH (NLMS, RLS) and the
+// precision matrix Pz (RLS) — and simply builds new blocking matrices.  The kernels carry the same state in sensor space,
+// u = waH B^T and Pt = conj(B) Pz B^T, so the state is re-expressed: waH = u conj(B_old), Pz = B_old^T Pt conj(B_old), then
+// u = waH B_new^T, Pt = conj(B_new) Pz B_new^T.  ST rows: see k_perbin_rls (btkb_perbin.cu).
+template <int C>
+__global__ void k_adaptive_rebase(const float2* Wold, const float2* Wnew, float2* UA, float* ST, int has_P, int U, int K, int Gp) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= U * K) return;
+  constexpr int NA = C - 1;
+  cd v[C], Bo[C][C - 1], Bn[C][C - 1];
+  for (int c = 0; c < C; c++) { float2 t = Wold[(size_t)c * Gp + g]; v[c] = cdmake(t.x, t.y); }
+  blocking_matrix<C>(v, Bo, 1);
+  for (int c = 0; c < C; c++) { float2 t = Wnew[(size_t)c * Gp + g]; v[c] = cdmake(t.x, t.y); }
+  blocking_matrix<C>(v, Bn, 1);
+  cd ua[C], wa[C - 1];
+  for (int c = 0; c < C; c++) { float2 t = UA[(size_t)c * Gp + g]; ua[c] = cdmake(t.x, t.y); }
+  for (int i = 0; i < NA; i++) {
+    cd s = cdmake(0, 0);
+    for (int c = 0; c < C; c++) s = cdadd(s, cdmul(ua[c], cdconj(Bo[c][i])));
+    wa[i] = s;
+  }
+  for (int c = 0; c < C; c++) {
+    cd s = cdmake(0, 0);
+    for (int i = 0; i < NA; i++) s = cdadd(s, cdmul(Bn[c][i], wa[i]));
+    UA[(size_t)c * Gp + g] = make_float2((float)s.x, (float)s.y);
+  }
+  if (!has_P) return;
+  const size_t gp = (size_t)Gp;
+  float* st = ST + g;
+  cd P[C][C], T1[C][C - 1], Pz[C - 1][C - 1];
+  for (int i = 0; i < C; i++) {
+    P[i][i] = cdmake(st[(8 + i) * gp], 0.0);
+    for (int j = 0; j < i; j++) {
+      const int o = i * (i - 1) / 2 + j;
+      P[i][j] = cdmake(st[(8 + C + 2 * o) * gp], st[(9 + C + 2 * o) * gp]);
+      P[j][i] = cdconj(P[i][j]);
+    }
+  }
+  for (int i = 0; i < C; i++)            // T1 = Pt conj(B_old)
+    for (int a = 0; a < NA; a++) { cd s = cdmake(0, 0); for (int j = 0; j < C; j++) s = cdadd(s, cdmul(P[i][j], cdconj(Bo[j][a]))); T1[i][a] = s; }
+  for (int a = 0; a < NA; a++)           // Pz = B_old^T T1
+    for (int b = 0; b < NA; b++) { cd s = cdmake(0, 0); for (int i = 0; i < C; i++) s = cdadd(s, cdmul(Bo[i][a], T1[i][b])); Pz[a][b] = s; }
+  for (int i = 0; i < C; i++)            // T1 = conj(B_new) Pz
+    for (int b = 0; b < NA; b++) { cd s = cdmake(0, 0); for (int a = 0; a < NA; a++) s = cdadd(s, cdmul(cdconj(Bn[i][a]), Pz[a][b])); T1[i][b] = s; }
+  for (int i = 0; i < C; i++)            // Pt = T1 B_new^T (Hermitian: lower triangle + real diagonal)
+    for (int j = 0; j <= i; j++) {
+      cd s = cdmake(0, 0);
+      for (int b = 0; b < NA; b++) s = cdadd(s, cdmul(T1[i][b], Bn[j][b]));
+      if (j == i) st[(8 + i) * gp] = (float)s.x;
+      else { const int o = i * (i - 1) / 2 + j; st[(8 + C + 2 * o) * gp] = (float)s.x; st[(9 + C + 2 * o) * gp] = (float)s.y; }
+    }
+}
+cudaError_t launch_adaptive_rebase(const float2* Wold, const float2* Wnew, float2* UA, float* ST, int has_P, int U, int C, int K, int Gp, cudaStream_t st) {
+  const int n = U * K, bs = 64, gs = (n + bs - 1) / bs;
+  switch (C) {
+    case 2: k_adaptive_rebase<2><<<gs, bs, 0, st>>>(Wold, Wnew, UA, ST, has_P, U, K, Gp); break;
+    case 3: k_adaptive_rebase<3><<<gs, bs, 0, st>>>(Wold, Wnew, UA, ST, has_P, U, K, Gp); break;
+    case 4: k_adaptive_rebase<4><<<gs, bs, 0, st>>>(Wold, Wnew, UA, ST, has_P, U, K, Gp); break;
+    case 5: k_adaptive_rebase<5><<<gs, bs, 0, st>>>(Wold, Wnew, UA, ST, has_P, U, K, Gp); break;
+    case 6: k_adaptive_rebase<6><<<gs, bs, 0, st>>>(Wold, Wnew, UA, ST, has_P, U, K, Gp); break;
+    case 7: k_adaptive_rebase<7><<<gs, bs, 0, st>>>(Wold, Wnew, UA, ST, has_P, U, K, Gp); break;
+    case 8: k_adaptive_rebase<8><<<gs, bs, 0, st>>>(Wold, Wnew, UA, ST, has_P, U, K, Gp); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 template <int DIR>
 static cudaError_t launch_blocking(const float2* W, const float2* IN, float2* OUT, int U, int C, int K, int Gp, int NC, cudaStream_t st) {
   const int n = U * K, bs = 128, gs = (n + bs - 1) / bs;
@@ -104,7 +172,9 @@ static cudaError_t launch_blocking(const float2* W, const float2* IN, float2* OU
     case 2: k_blocking<2, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
     case 3: k_blocking<3, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
     case 4: k_blocking<4, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
+    case 5: k_blocking<5, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
     case 6: k_blocking<6, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
+    case 7: k_blocking<7, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
     case 8: k_blocking<8, DIR><<<gs, bs, 0, st>>>(W, IN, OUT, U, K, Gp, NC); break;
     default: return cudaErrorInvalidValue;
   }
@@ -208,7 +278,9 @@ cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const
     case 2: k_mvdr_solve<2><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
     case 3: k_mvdr_solve<3><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
     case 4: k_mvdr_solve<4><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    case 5: k_mvdr_solve<5><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
     case 6: k_mvdr_solve<6><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    case 7: k_mvdr_solve<7><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
     case 8: k_mvdr_solve<8><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
     default: return cudaErrorInvalidValue;
   }
@@ -339,7 +411,9 @@ cudaError_t launch_lcmv_weights(const double* delaysT, const double* delaysJ, fl
     case 2: k_lcmv<2><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
     case 3: k_lcmv<3><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
     case 4: k_lcmv<4><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
+    case 5: k_lcmv<5><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
     case 6: k_lcmv<6><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
+    case 7: k_lcmv<7><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
     case 8: k_lcmv<8><<<gs, bs, 0, st>>>(delaysT, delaysJ, W, U, NC, M, K, Gp, samplerate); break;
     default: return cudaErrorInvalidValue;
   }

@@ -341,8 +341,7 @@ static cudaError_t launch_wide_l(const PerBinArgs& a, cudaStream_t st) {
   cudaError_t e = make_map_wide(&tm, a, C);
   if (e != cudaSuccess) return e;
   const int grid = (a.G + TC - 1) / TC;
-  const char* ev = getenv("BTKB_PERBIN_PACKED");
-  const bool pk = ev && atoi(ev) != 0;
+  const bool pk = env_packed("BTKB_PERBIN_PACKED");
   if (pk) {
     auto kern = (a.kind == BTKB_BF_GSC_LMS) ? k_perbin_wide<L, 1, true> : k_perbin_wide<L, 0, true>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

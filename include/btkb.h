@@ -183,6 +183,33 @@ int btkb_run_synthesis(btkb_pipeline* p);
 int btkb_run(btkb_pipeline* p, int do_synthesis);
 int btkb_synchronize(btkb_pipeline* p);
 
+/* ---- streamed chunks with carried state: the per-frame pull contract of FeatureStream::next (stream/stream.h:16-54) at chunk
+ * granularity.  An utterance need not be complete before its first frames come out, its length is unbounded (max_samples bounds one
+ * CHUNK), and btkb_set_delays* may be called between chunks to move the look direction while the adaptive state is kept
+ * (unit_test/test_online_beamforming.py:205-225 recomputes the weights inside its frame loop).
+ *   btkb_stream_begin(p, U)      rewind: frame counters, filter-bank histories and the adaptive state (NLMS / RLS weights, post-filter
+ *                                statistics) start afresh for U utterances that advance in lockstep; weights already set for U are kept.
+ *   btkb_stream_submit(p, samples [U][C][n] float32, n, lengths, final, do_synthesis)
+ *                                appends n samples per utterance (a positive multiple of D unless `final`) and runs analysis ->
+ *                                beamformer / post-filter (-> synthesis) for exactly the frames this chunk completes: frames
+ *                                [blocks_before - laN, blocks_now - laN) of every utterance; the final chunk (lengths[u] <= n valid new
+ *                                samples, NULL = n) adds the pd_A flush frames the reference emits after its source ends
+ *                                (modulated.cc:440-466).  Afterwards btkb_num_frames / btkb_num_blocks / btkb_fetch_subband /
+ *                                btkb_fetch_time / btkb_fetch_snapshots / btkb_get_postfilter_weights describe THIS chunk;
+ *                                btkb_fetch_stats is cumulative.  The concatenated chunks equal the whole-utterance run bit for bit.
+ *   btkb_stream_position         absolute number of the last chunk's first frame and first output block.
+ * Not offered for WPE (it buffers the whole utterance by definition, dereverberation.cc:500-534), the batch statistics
+ * (btkb_accumulate_covariance, btkb_sos_*) and > 8 channels. */
+int btkb_stream_begin(btkb_pipeline* p, int U);
+int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int* lengths, int final_chunk, int do_synthesis);
+int btkb_stream_position(const btkb_pipeline* p, int* first_frame, int* first_block);
+/* FeatureStream::reset() of the whole graph (stream/stream.h:41-47): drops the resident batch; while streaming, same as
+ * btkb_stream_begin with the same U.  Weights are kept (the reference's reset() does not touch BeamformerWeights). */
+int btkb_reset(btkb_pipeline* p);
+/* Run all of this pipeline's work on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = back to a private stream).
+ * The pipeline synchronises its previous stream first.  SURVEY.md 8(b): "stream-ordered on a caller-supplied cudaStream_t". */
+int btkb_set_stream(btkb_pipeline* p, void* cuda_stream);
+
 /* ---- results (all synchronise the stream) ------------------------------------------------------------------- */
 int btkb_num_frames(const btkb_pipeline* p);        /* T of the longest utterance in the batch */
 int btkb_num_frames_of(const btkb_pipeline* p, int u);

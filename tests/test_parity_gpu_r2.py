@@ -1,0 +1,237 @@
+"""GPU parity tests (-m gpu) added in round 2 for paths that shipped without a test (VERDICT r1 "weak" 4, "missing" 4):
+ * the filter-bank parameter space beyond (m = 4, r = 1, delay-compensation type 2): the generic kernels k_analysis_generic /
+   k_synthesis_generic, the reference's own defaults m = 3, r = 0, type 0 (modulated/modulated.i:91), types 1 and 2 with other m / r
+   (modulated.cc:249-264, 418-469, 569-612);
+ * arbitrary channel counts C = 1..8 (the reference takes any number of set_channel() calls, beamformer.cc:1017-1021).
+Everything through the C-ABI, against the fp64 restatement (oracle/restate.py) on seeded inputs; gate 1e-4 relative L2."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-4
+FS = 16000.0
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from distant_speech_recognition_b200 import _capi
+    assert _capi.device_count() >= 1, "no CUDA device: the product has no CPU path"
+    return _capi
+
+
+def _random_prototypes(M, m, seed):
+    """Any real prototype pair exercises the arithmetic; a smooth window keeps the dynamic range like the Nyquist(M) designs."""
+    rng = np.random.default_rng(seed)
+    N = M * m
+    win = np.hanning(N + 2)[1:-1]
+    h = win * np.sinc((np.arange(N) - (N - 1) / 2.0) / M) / np.sqrt(M) + 1e-3 * rng.standard_normal(N) / M
+    g = win * np.sinc((np.arange(N) - (N - 1) / 2.0) / M) * np.sqrt(M) / (M / 2) + 1e-3 * rng.standard_normal(N)
+    return h, g
+
+
+@pytest.mark.parametrize("M,m,r,dct", [(256, 3, 0, 0), (256, 4, 1, 0), (256, 4, 1, 1), (512, 3, 0, 1), (256, 2, 1, 2), (512, 4, 2, 2),
+                                         (512, 2, 2, 1), (1024, 2, 2, 2), (512, 3, 1, 2), (2048, 2, 1, 2)])
+def test_filter_bank_parameter_space(capi, M, m, r, dct):
+    from oracle import restate
+    C, U = 3, 2
+    D = M >> r
+    n = 9 * D + 37
+    lengths = np.array([n, 5 * D], np.int32)
+    rng = np.random.default_rng(M + 10 * m + r)
+    x = (3000.0 * rng.standard_normal((U, C, n))).astype(np.float32)
+    h, g = _random_prototypes(M, m, 7)
+    p = capi.Pipeline(C, M, m, r, delay_compensation_type=dct, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g)
+    d = np.array([[0.0, 6.0e-5, -1.1e-4], [2.0e-5, 0.0, 9.0e-5]])
+    p.set_delays(d)
+    p.submit(x, lengths)
+    p.run(True)
+    X = p.fetch_snapshots(); Y = p.fetch_subband(); y = p.fetch_time()
+    K = M // 2 + 1
+    for u in range(U):
+        L = int(lengths[u])
+        Xo = np.stack([restate.analysis(x[u, c, :L], h, M, m, r, dct) for c in range(C)], axis=1)   # [T][C][M]
+        T = Xo.shape[0]
+        assert p.num_frames_of(u) == T == restate.num_frames(L, M, m, r, dct)
+        assert rel_l2(X[u, :T], Xo[:, :, :K]) < 2e-6, (u, "analysis")
+        wq = restate.calc_mainlobe(M, C, FS, d[u])
+        Yo = restate.subband_ds(Xo, wq)
+        assert rel_l2(Y[u, :T], Yo[:, :K]) < TOL
+        yo = restate.synthesis(Yo, g, M, m, r, dct)
+        assert len(yo) > 0 and rel_l2(y[u, :len(yo)], yo) < TOL, (u, "synthesis")
+        assert np.all(y[u, len(yo):] == 0)
+    p.close()
+
+
+@pytest.mark.parametrize("C", [1, 3, 5, 6, 7])
+def test_arbitrary_channel_counts_ds_gsc_nlms_zelinski(capi, protos, C):
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, U, n = 256, 2, 6000
+    K = M // 2 + 1
+    h, g = protos[M]
+    x, d = synthetic.make_batch(U, C, n, first=400 + C)
+    lengths = np.array([n, 4321], np.int32)
+    Xo = [np.stack([restate.analysis(x[u, c, :lengths[u]], h, M, 4, 1) for c in range(C)], axis=1) for u in range(U)]
+    # delay-and-sum
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
+    Y, y = p.fetch_subband(), p.fetch_time()
+    for u in range(U):
+        wq = restate.calc_mainlobe(M, C, FS, d[u]); T = Xo[u].shape[0]
+        Yo = restate.subband_ds(Xo[u], wq)
+        assert rel_l2(Y[u, :T], Yo[:, :K]) < TOL and rel_l2(y[u, :(T - 4) * 128], restate.synthesis(Yo, g, M, 4, 1)) < TOL
+    p.close()
+    if C < 2:
+        with pytest.raises(capi.BtkbError):       # "The number of channels must be > 1" (beamformer.cc:507-510)
+            q = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC, max_utterances=U, max_samples=n)
+            q.set_prototypes(h, g); q.set_delays(d)
+        return
+    # static GSC with active weights + Zelinski post-filter
+    rng = np.random.default_rng(C)
+    wa = (0.05 * (rng.standard_normal((U, K, C - 1)) + 1j * rng.standard_normal((U, K, C - 1)))).astype(np.complex64)
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC, postfilter=capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.set_active_weights(wa); p.submit(x, lengths); p.run(True)
+    Y = p.fetch_subband()
+    for u in range(U):
+        wq = restate.calc_mainlobe(M, C, FS, d[u]); T = Xo[u].shape[0]
+        B = np.stack([restate.calc_blocking_matrix(wq[k]) for k in range(K)])
+        wl = np.zeros_like(wq); wl[:K] = restate.active_to_wl(B, wa[u].astype(np.complex128))
+        Yg = restate.subband_gsc(Xo[u], wq, wl)
+        Yz, _ = restate.zelinski_postfilter(Yg, Xo[u], wq, alpha=0.7, pf_type=2)
+        assert rel_l2(Y[u, :T], Yz[:, :K]) < TOL, (C, u, "gsc+zelinski")
+    p.close()
+    # NLMS sidelobe canceller (the projector-form kernel) and its exported active weights
+    lms = dict(min_frames=5)
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=lms, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
+    Y, y, st = p.fetch_subband(), p.fetch_time(), p.fetch_stats()
+    wa_out = p.get_active_weights()
+    for u in range(U):
+        T = Xo[u].shape[0]
+        Yo, wao, nu = restate.gsc_lms(Xo[u], FS, d[u], **lms)
+        assert rel_l2(Y[u, :T], Yo[:, :K]) < TOL, (C, u, "nlms")
+        assert rel_l2(y[u, :(T - 4) * 128], restate.synthesis(Yo, g, M, 4, 1)) < TOL
+        assert st[u][2] == nu
+        assert rel_l2(wa_out[u], wao[:K]) < 2e-3
+    p.close()
+    # RLS sidelobe canceller
+    rls = dict(min_frames=5)
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC_RLS, rls=rls, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(False)
+    Y = p.fetch_subband()
+    for u in range(U):
+        T = Xo[u].shape[0]
+        Yo = restate.gsc_rls(Xo[u], FS, d[u], **rls)[0]
+        assert rel_l2(Y[u, :T], Yo[:, :K]) < TOL, (C, u, "rls")
+    p.close()
+
+
+# ------------------------------------------------------------------------------------------- streamed chunks with carried state
+def _stream_kinds(capi):
+    mpos = np.stack([40.0 * (np.arange(4) - 1.5), np.zeros(4), np.zeros(4)], axis=1)
+    return {
+        "ds": (dict(beamformer=capi.BF_DS), None),
+        "gsc_zelinski": (dict(beamformer=capi.BF_GSC, postfilter=capi.PF_ZELINSKI, pf_alpha=0.7, pf_type=2), None),
+        "nlms": (dict(beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=9, slowdown_after=16)), None),
+        "rls": (dict(beamformer=capi.BF_GSC_RLS, rls=dict(min_frames=9, regularization_param=1.0e-2, constraint_option=3, alpha2=1.0e-3)), None),
+        "mccowan": (dict(beamformer=capi.BF_DS, postfilter=capi.PF_MCCOWAN, pf_alpha=0.7, pf_type=2), mpos),
+        "lefkimmiatis": (dict(beamformer=capi.BF_DS, postfilter=capi.PF_LEFKIMMIATIS, pf_alpha=0.7, pf_type=2), mpos),
+    }
+
+
+@pytest.mark.parametrize("kind", ["ds", "gsc_zelinski", "nlms", "rls", "mccowan", "lefkimmiatis"])
+@pytest.mark.parametrize("M,m,r", [(256, 4, 1), (512, 3, 0)])
+def test_streamed_chunks_equal_the_whole_utterance_run_bit_for_bit(capi, protos, kind, M, m, r):
+    """btkb_stream_submit (chunks of 2, 1, 17, 2, 40 and a ragged final chunk of <= 9 blocks; the first chunk completes no frame) against
+    btkb_submit of the same ragged batch: snapshots, subband output, post-filter gains, time signal and update counts must be
+    IDENTICAL — the kernels see the same numbers in the same order, only the bookkeeping differs (tests/test_chunked_spec.py pins the
+    contract on the CPU)."""
+    from distant_speech_recognition_b200 import synthetic
+    C, U = 4, 3
+    D = M >> r
+    cuts = np.cumsum([0, 2, 1, 17, 2, 40]) * D
+    n_final = 9 * D
+    tail = np.array([n_final, 3 * D + 17, 0], np.int32)              # valid new samples of the final chunk, per utterance
+    n = int(cuts[-1]) + n_final
+    x, d = synthetic.make_batch(U, C, n, first=700)
+    lengths = (cuts[-1] + tail).astype(np.int32)
+    h, g = protos[M] if (m, r) == (4, 1) else _random_prototypes(M, m, 11)
+    kw, mpos = _stream_kinds(capi)[kind]
+
+    def make(maxn):
+        p = capi.Pipeline(C, M, m, r, max_utterances=U, max_samples=maxn, **kw)
+        p.set_prototypes(h, g)
+        if mpos is not None:
+            p.pf_set_diffuse_noise_model(mpos, 16000.0); p.pf_set_diagonal_loading(0.05)
+        return p
+
+    w = make(n); w.set_delays(d); w.submit(x, lengths); w.run(True)
+    ref = dict(X=w.fetch_snapshots(), Y=w.fetch_subband(), y=w.fetch_time(), st=w.fetch_stats())
+    if "postfilter" in kw:
+        ref["W"] = w.get_postfilter_weights()
+    w.close()
+
+    p = make(41 * D)
+    p.set_delays(d); p.stream_begin(U)
+    Xs, Ys, ys, Ws = [], [], [], []
+    bounds = list(cuts) + [n]
+    for j in range(len(bounds) - 1):
+        a, b = int(bounds[j]), int(bounds[j + 1])
+        final = j == len(bounds) - 2
+        p.stream_submit(np.ascontiguousarray(x[:, :, a:b]), tail if final else None, final=final)
+        t0, b0 = p.stream_position()
+        if p.num_frames > 0:
+            Xs.append(p.fetch_snapshots()); Ys.append(p.fetch_subband())
+            if "postfilter" in kw:
+                Ws.append(p.get_postfilter_weights())
+        if p.num_blocks > 0:
+            ys.append(p.fetch_time())
+        t0, b0 = p.stream_position()
+        assert t0 + p.num_frames == sum(v.shape[1] for v in Ys) and (b0 + p.num_blocks) * D == sum(v.shape[1] for v in ys)
+    st = p.fetch_stats()
+    with pytest.raises(capi.BtkbError):
+        p.stream_submit(np.zeros((U, C, D), np.float32))             # the stream has ended
+    p.close()
+    X, Y, y = np.concatenate(Xs, axis=1), np.concatenate(Ys, axis=1), np.concatenate(ys, axis=1)
+    assert X.shape == ref["X"].shape and np.array_equal(X.view(np.uint8), ref["X"].view(np.uint8)), "snapshots"
+    assert Y.shape == ref["Y"].shape and np.array_equal(Y.view(np.uint8), ref["Y"].view(np.uint8)), "subband"
+    assert y.shape == ref["y"].shape and np.array_equal(y.view(np.uint8), ref["y"].view(np.uint8)), "time"
+    if Ws:
+        assert np.array_equal(np.concatenate(Ws, axis=1), ref["W"])
+    assert np.array_equal(st[:, 1:], ref["st"][:, 1:]) and np.allclose(st[:, 0], ref["st"][:, 0], rtol=1e-6)
+    assert np.abs(ref["Y"]).max() > 0 and np.abs(ref["y"]).max() > 0
+
+
+def test_streamed_look_direction_change_keeps_the_adaptive_state(capi, protos):
+    """unit_test/test_online_beamforming.py:205-225 recomputes the beamformer weights inside its frame loop when the conf lists a second
+    target position; SubbandGSCLMSBeamformer.calc_beamformer_weights (pybeamformer.py:736-743) replaces vs / the blocking matrices and
+    keeps waH, the sub-band energies and the frame counter.  Chunked run with btkb_set_delays between two chunks against the fp64
+    restatement with carried state."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, C, D, K = 256, 4, 128, 129
+    n1, n2 = 30 * D, 25 * D + 50
+    x, d = synthetic.make_batch(1, C, n1 + n2, first=900)
+    d2 = d * 0.4
+    h, g = protos[M]
+    lms = dict(min_frames=9)
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=lms, max_utterances=1, max_samples=32 * D)
+    p.set_prototypes(h, g); p.set_delays(d); p.stream_begin(1)
+    p.stream_submit(np.ascontiguousarray(x[:, :, :n1])); Y1 = p.fetch_subband()[0]
+    p.set_delays(d2)
+    p.stream_submit(np.ascontiguousarray(x[:, :, n1:]), final=True); Y2 = p.fetch_subband()[0]
+    p.close()
+    Xo = np.stack([restate.analysis(x[0, c], h, M, 4, 1) for c in range(C)], axis=1)
+    F = Y1.shape[0]
+    assert F == n1 // D - 3 and F + Y2.shape[0] == Xo.shape[0]
+    # the restatement carries waH and the sub-band energies across the change, like the reference; the kernel re-expresses its
+    # sensor-space state u = waH B^T for the new blocking matrices (k_adaptive_rebase), so the two agree to the usual tolerance
+    st = {}
+    Yo1, _, _ = restate.gsc_lms(Xo[:F], FS, d[0], state=st, **lms)
+    Yo2, _, nu = restate.gsc_lms(Xo[F:], FS, d2[0], state=st, **lms)
+    assert rel_l2(Y1, Yo1[:, :K]) < TOL
+    assert rel_l2(Y2, Yo2[:, :K]) < TOL
+    assert np.abs(Yo2 - restate.gsc_lms(Xo[F:], FS, d2[0], **lms)[0]).max() > 1.0      # the carried state matters
