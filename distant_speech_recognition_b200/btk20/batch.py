@@ -93,3 +93,93 @@ class BatchBeamformer:
         else:
             p.run(synthesis)
         return (p.fetch_time() if synthesis else None), p.fetch_subband(), p.fetch_stats()
+
+
+class ShardedBatchBeamformer:
+    """The multi-GPU front end: one process per GPU (torchrun), rank g owns the contiguous utterance range
+    `sharding.shard_range(total, world, rank)`; utterances are independent units (reset_stats per utterance,
+    lib/pybeamformer.py:745-762), so there is NO data-path collective — the only exchange is one all-gather of the per-utterance
+    statistics [sum y^2, frames, updates] at the end of a run (`gather_stats`).
+
+    Within a rank the shard is cut into `sub_batches` pipeline handles, each with its own CUDA stream, and the host loop is
+    software-pipelined over sub-batches AND steps: a sub-batch's results are collected right before its handle is re-submitted, so
+    the H2D engine always has the other sub-batches' uploads queued while this one's kernels run and its D2H drains.  Input is 16-bit
+    PCM in pinned host memory (what SampleFeature reads from wav files, feature/feature.cc:256-305), output the resynthesised float
+    signal into a caller-supplied pinned buffer."""
+
+    def __init__(self, chan_num, h_fb, g_fb, M=512, m=4, r=1, samplerate=16000, beamformer=None, utterances=256, max_samples=80000,
+                 sub_batches=8, device=0, world=None, rank=None):
+        from .. import sharding
+        self.sharding = sharding
+        bf = dict(beamformer or {"type": "gsclms"})
+        kind = bf.pop("type")
+        if kind not in ("gsclms", "gscrls", "delay_and_sum", "ds", "gsc"):
+            raise ValueError("ShardedBatchBeamformer streams one-pass beamformers (delay_and_sum, gsc, gsclms, gscrls); got %r" % kind)
+        self.world, self.rank = self._dist(world, rank)
+        self.U = int(utterances)
+        NP = max(1, min(int(sub_batches), self.U))
+        while self.U % NP:
+            NP -= 1
+        self.NP, self.Us, self.n, self.C = NP, self.U // NP, int(max_samples), chan_num
+        lms = {k: v for k, v in bf.items() if k in _LMS_KEYS} if kind == "gsclms" else None
+        rls = {k: v for k, v in bf.items() if k in _RLS_KEYS} if kind == "gscrls" else None
+        self.pipes = []
+        for _ in range(NP):
+            q = _capi.Pipeline(chan_num, M, m, r, 2, samplerate, _KINDS[kind], max_utterances=self.Us, max_samples=self.n, device=device,
+                               lms=lms or None, rls=rls or None)
+            q.set_prototypes(h_fb, g_fb)
+            self.pipes.append(q)
+        self.D = M >> r
+        self.pending = [None] * NP
+        self.stats = np.zeros((self.U, 3))
+
+    @staticmethod
+    def _dist(world, rank):
+        if world is not None:
+            return int(world), int(rank or 0)
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_world_size(), dist.get_rank()
+        except Exception:  # noqa: BLE001
+            pass
+        return 1, 0
+
+    def shard(self, total):
+        """[start, stop) of this rank in a global batch of `total` utterances."""
+        return self.sharding.shard_range(total, self.world, self.rank)
+
+    def _collect(self, i):
+        out_ptr, itemsize_row = self.pending[i]
+        q = self.pipes[i]
+        q.fetch_time_into(out_ptr + i * self.Us * itemsize_row)
+        self.stats[i * self.Us:(i + 1) * self.Us] = q.fetch_stats()
+        self.pending[i] = None
+
+    def step(self, x16_ptr, delays, out_ptr, out_row_bytes):
+        """One pass over the shard: x16_ptr -> pinned int16 [U][C][n], delays [U][C], out_ptr -> pinned float32 rows of out_row_bytes.
+        Returns immediately after queueing; results of this step are complete after the next step() or drain()."""
+        Us, n, C = self.Us, self.n, self.C
+        for i, q in enumerate(self.pipes):
+            if self.pending[i] is not None:
+                self._collect(i)
+            q.submit_i16_pointer(x16_ptr + i * Us * C * n * 2, Us, n)
+            q.set_delays(delays[i * Us:(i + 1) * Us])
+            q.run(True)
+            self.pending[i] = (out_ptr, out_row_bytes)
+
+    def drain(self):
+        for i in range(self.NP):
+            if self.pending[i] is not None:
+                self._collect(i)
+
+    def launches(self):
+        return sum(int(q.last_timing()["launches"]) for q in self.pipes)
+
+    def gather_stats(self):
+        """The single end-of-run exchange: every rank's per-utterance statistics, in rank order -> [U_total][3]."""
+        return self.sharding.gather_stats(self.stats)
+
+    def close(self):
+        for q in self.pipes:
+            q.close()
