@@ -157,7 +157,7 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   fb_delays(cfg->m, cfg->r, cfg->delay_compensation_type, false, &p->pdA, &p->laN);
   int la_dummy; fb_delays(cfg->m, cfg->r, cfg->delay_compensation_type, true, &p->pdS, &la_dummy);
   p->Ucap = cfg->max_utterances; p->ncap = cfg->max_samples; p->n_stride = round_up(cfg->max_samples, 4);
-  p->Tcap = frames_of(p->ncap, p->D, p->laN, p->pdA);
+  p->Tcap = (p->ncap + p->D - 1) / p->D + p->pdA;   // >= frames_of(ncap): the final chunk of a stream emits its blocks plus all pd_A flush frames
   p->Gpcap = round_up(p->Ucap * p->K, 128);
   const size_t G = (size_t)p->Gpcap, T = (size_t)p->Tcap, U = (size_t)p->Ucap;
   cudaError_t e = cudaSuccess;

@@ -282,6 +282,7 @@ void SingleChannelWPEDereverberationFeature::reset() { impl_->reset(); VectorCom
 // ================================================================================================ beamformers
 SubbandBeamformer::SubbandBeamformer(unsigned fftLen, bool hbs, int kind, const std::string& nm)
     : VectorComplexFeatureStream(fftLen, nm), fftLen_(fftLen), halfBandShift_(hbs), kind_(kind) {
+  if (const char* e = std::getenv("BTK20_CHUNK_BLOCKS")) chunk_blocks_ = std::max(0, std::atoi(e));
   if (hbs) throw jallocation_error("halfBandShift==true is not yet supported\n");  // beamformer.cc:2283-2285 (MVDR); the GPU path is M/2+1 bins only
 }
 SubbandBeamformer::~SubbandBeamformer() { if (pipe_) btkb_destroy(pipe_); }
@@ -293,6 +294,7 @@ void SubbandBeamformer::reset() {
   VectorComplexFeatureStream::reset();
   is_end_ = false;
   realized_ = false;  // adaptive state restarts with the utterance (pybeamformer.py:759-762)
+  live_ = false;
 }
 
 bool SubbandBeamformer::realized_with(const PostFilterConfig& pf, const SynthesisConfig& syn) const {
@@ -363,12 +365,37 @@ void SubbandBeamformer::run_graph(const PostFilterConfig& pf, const SynthesisCon
   }
   if (n == 0) { T_ = 0; nb_ = 0; realized_ = true; pf_used_ = pf; syn_used_ = syn; return; }
   if (syn.enabled && (syn.M != fftLen_)) throw jdimension_error("synthesis bank: inconsistent FFT length (%d vs. %d)", syn.M, fftLen_);
-  ensure_pipeline_(pf, syn, n);
+  live_ = false;
+  const bool chunked = chunk_blocks_ > 0 && !wpe_ && C <= 8 && stream_capable_();
+  {
+    auto* a0 = bank_behind(channels_[0], nullptr);
+    D_ = fftLen_ >> a0->r();
+  }
+  ensure_pipeline_(pf, syn, chunked ? std::min<unsigned>(n, (unsigned)chunk_blocks_ * D_) : n);
   configure_weights_(pipe_);
   if (pf.enabled && pf.kind != BTKB_PF_ZELINSKI) {
     if (!pf.coherence) throw j_error("McCowanPostFilter:  construct/set a noise coherence matrix\n");  // postfilter.cc:828-830
     if (pf.coherence->chanN() != C) throw jdimension_error("noise coherence matrix is %d x %d but the beamformer has %d channels\n", pf.coherence->chanN(), pf.coherence->chanN(), C);
     pf.coherence->push_coherence(pipe_);
+  }
+  if (chunked) {
+    // totals in closed form (modulated.cc:246-264, 418-469): T = ceil(n / D) - laN + pd_A, blocks = T - pd_S
+    auto* a0 = bank_behind(channels_[0], nullptr);
+    const int R = 1 << a0->r(), mm = (int)a0->m(), dct = (int)a0->dct();
+    int pdA, laN = 0, pdS;
+    if (dct == 1) { pdA = mm * R - 1; pdS = mm * R - 1; } else if (dct == 2) { pdA = mm * R - 1; laN = mm * R / 2 - 1; pdS = mm * R / 2; } else { pdA = 2 * mm - 1; pdS = 2 * mm - 1; }
+    T_ = (int)((n + D_ - 1) / D_) - laN + pdA; nb_ = std::max(T_ - pdS, 0);
+    ck(btkb_stream_begin(pipe_, 1));
+    srcs_ = srcs; n_total_ = n; pos_ = 0; T_ready_ = nb_ready_ = chunk_t0_ = 0; weights_dirty_ = false;
+    const unsigned K = fftLen_ / 2 + 1;
+    Y_.assign((size_t)T_ * K, std::complex<float>(0.f, 0.f));
+    time_.assign(syn.enabled ? (size_t)nb_ * D_ : 0, 0.f);
+    pfw_.assign(pf.enabled ? (size_t)T_ * K : 0, 0.f);
+    W_.resize((size_t)K * C);
+    ck(btkb_get_weights(pipe_, reinterpret_cast<float*>(W_.data())));
+    haveX_ = false;
+    realized_ = true; live_ = true; pf_used_ = pf; syn_used_ = syn;
+    return;
   }
   std::vector<float> x((size_t)C * n);
   for (unsigned c = 0; c < C; c++) std::memcpy(&x[(size_t)c * n], srcs[c]->samples().data(), sizeof(float) * n);
@@ -396,10 +423,47 @@ void SubbandBeamformer::run_graph(const PostFilterConfig& pf, const SynthesisCon
   realized_ = true; pf_used_ = pf; syn_used_ = syn;
 }
 
+// Chunked realisation: hand the next chunk_blocks_ blocks of every channel to the GPU and append what comes back.
+void SubbandBeamformer::advance_() {
+  if (!live_ || pos_ >= n_total_) return;
+  if (weights_dirty_) { configure_weights_(pipe_); weights_dirty_ = false; }   // btkb_set_delays* between chunks keeps the adaptive state
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
+  const size_t want = (size_t)chunk_blocks_ * D_;
+  const size_t nc = std::min<size_t>(want, n_total_ - pos_);
+  const bool final_chunk = pos_ + nc >= n_total_;
+  xchunk_.resize((size_t)C * nc);
+  for (unsigned c = 0; c < C; c++) std::memcpy(&xchunk_[(size_t)c * nc], srcs_[c]->samples().data() + pos_, sizeof(float) * nc);
+  ck(btkb_stream_submit(pipe_, xchunk_.data(), (int)nc, nullptr, final_chunk ? 1 : 0, syn_used_.enabled ? 1 : 0));
+  pos_ += nc;
+  const int Tl = btkb_num_frames(pipe_), nbl = btkb_num_blocks(pipe_);
+  chunk_t0_ = T_ready_;
+  if (Tl > 0) {
+    if (T_ready_ + Tl > T_) throw j_error("SubbandBeamformer: chunked realisation produced more frames than the closed form predicts");
+    ck(btkb_fetch_subband(pipe_, reinterpret_cast<float*>(&Y_[(size_t)T_ready_ * K])));
+    if (pf_used_.enabled) ck(btkb_get_postfilter_weights(pipe_, &pfw_[(size_t)T_ready_ * K]));
+    T_ready_ += Tl;
+  }
+  if (syn_used_.enabled && nbl > 0) {
+    if (nb_ready_ + nbl > nb_) throw j_error("SubbandBeamformer: chunked realisation produced more blocks than the closed form predicts");
+    ck(btkb_fetch_time(pipe_, &time_[(size_t)nb_ready_ * D_]));
+    nb_ready_ += nbl;
+  }
+  haveX_ = false;
+}
+void SubbandBeamformer::ensure_frames(int t) {
+  if (!live_) return;
+  while (T_ready_ <= t && pos_ < n_total_) advance_();
+}
+void SubbandBeamformer::ensure_blocks(int b) {
+  if (!live_) return;
+  while (nb_ready_ <= b && pos_ < n_total_) advance_();
+}
+
 const cplx* SubbandBeamformer::next(int frame_no) {
   if (frame_no == frame_no_) return vector_.data();
   if (!realized_) run_graph(PostFilterConfig(), SynthesisConfig());
   if (frame_no_ + 1 >= T_) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  ensure_frames(frame_no_ + 1);
   increment_();
   const unsigned K = fftLen_ / 2 + 1;
   const std::complex<float>* y = &Y_[(size_t)frame_no_ * K];
@@ -412,10 +476,12 @@ SnapShotArrayPtr SubbandBeamformer::snapshot_array() {
   if (!snap_) snap_ = std::make_shared<SnapShotArray>(fftLen_, chanN());
   if (realized_ && pipe_ && frame_no_ >= 0 && frame_no_ < T_) {
     const unsigned K = fftLen_ / 2 + 1, C = chanN();
-    if (!haveX_) { X_.resize((size_t)T_ * C * K); ck(btkb_fetch_snapshots(pipe_, reinterpret_cast<float*>(X_.data()))); haveX_ = true; }
+    const int tl = live_ ? frame_no_ - chunk_t0_ : frame_no_;   // chunked realisation: the device holds the snapshots of the current chunk
+    if (!haveX_) { X_.resize((size_t)btkb_num_frames(pipe_) * C * K); ck(btkb_fetch_snapshots(pipe_, reinterpret_cast<float*>(X_.data()))); haveX_ = true; }
+    if (tl < 0 || (size_t)(tl + 1) * C * K > X_.size()) return snap_;
     std::vector<cplx> full(fftLen_);
     for (unsigned c = 0; c < C; c++) {
-      const std::complex<float>* x = &X_[((size_t)frame_no_ * C + c) * K];
+      const std::complex<float>* x = &X_[((size_t)tl * C + c) * K];
       for (unsigned k = 0; k < K; k++) full[k] = cplx(x[k].real(), x[k].imag());
       for (unsigned k = 1; k < fftLen_ / 2; k++) full[fftLen_ - k] = std::conj(full[k]);
       snap_->set_samples(full.data(), c);
@@ -468,7 +534,7 @@ void SubbandDS::clear_channel() { SubbandBeamformer::clear_channel(); have_delay
 void SubbandDS::calc_array_manifold_vectors(double samplerate, const std::vector<double>& delays) {
   if (delays.size() != chanN())  // beamformer.cc:504-506
     throw jdimension_error("Number of delays does not match number of channels (%d vs. %d).\n", (int)delays.size(), (int)chanN());
-  samplerate_ = samplerate; delays_ = delays; have_delays_ = true; NC_ = 1; delaysJ_.clear(); W_.clear(); invalidate_();   // alloc_bfweight_(1, 1)
+  samplerate_ = samplerate; delays_ = delays; have_delays_ = true; NC_ = 1; delaysJ_.clear(); W_.clear(); invalidate_weights_();   // alloc_bfweight_(1, 1)
 }
 void SubbandDS::calc_array_manifold_vectors_n(double samplerate, const std::vector<double>& delaysT, const std::vector<double>& delaysJ, unsigned NC) {
   const unsigned C = chanN();
@@ -777,6 +843,7 @@ const cplx* ZelinskiPostFilter::next(int frame_no) {  // postfilter.cc:424-491
   const PostFilterConfig pf = config();
   if (!bf_->realized_with(pf, SynthesisConfig())) bf_->run_graph(pf, SynthesisConfig());
   if (frame_no_ + 1 >= bf_->frames()) { is_end_ = true; throw jiterator_error("end of samples!"); }
+  bf_->ensure_frames(frame_no_ + 1);
   increment_();
   const unsigned K = fftLen_ / 2 + 1;
   const std::complex<float>* y = &bf_->Y()[(size_t)frame_no_ * K];
@@ -884,7 +951,7 @@ OverSampledDFTSynthesisBank::OverSampledDFTSynthesisBank(const VectorComplexFeat
   if (prototype.size() != (size_t)M * m) throw jconsistency_error("Prototype sizes do not match (%d vs. %d).", (int)prototype.size(), (int)(M * m));
 }
 OverSampledDFTSynthesisBank::~OverSampledDFTSynthesisBank() { if (pipe_) btkb_destroy(pipe_); }
-void OverSampledDFTSynthesisBank::reset() { samp_->reset(); VectorFloatFeatureStream::reset(); realized_ = false; }
+void OverSampledDFTSynthesisBank::reset() { samp_->reset(); VectorFloatFeatureStream::reset(); realized_ = false; live_bf_ = nullptr; }
 
 void OverSampledDFTSynthesisBank::realize_() {
   SynthesisConfig syn; syn.enabled = true; syn.prototype = prototype_; syn.M = M_; syn.m = m_; syn.r = r_; syn.dct = dct_; syn.gain = gain_;
@@ -893,8 +960,10 @@ void OverSampledDFTSynthesisBank::realize_() {
   else bf = dynamic_cast<SubbandBeamformer*>(samp_.get());
   if (bf) {  // fast path: the whole graph runs on the GPU in one submission
     if (!bf->realized_with(pf, syn)) bf->run_graph(pf, syn);
-    out_ = bf->time_out(); nb_ = bf->blocks();
-  } else {   // arbitrary upstream stream (e.g. a Python object behind PyVectorComplexFeatureStream): drain it, synthesise on the GPU
+    nb_ = bf->blocks(); live_bf_ = bf;
+    if (bf->chunk_blocks() == 0) { out_ = bf->time_out(); live_bf_ = nullptr; }   // chunked realisation: blocks are pulled as next() asks for them
+  } else {
+    live_bf_ = nullptr;   // arbitrary upstream stream (e.g. a Python object behind PyVectorComplexFeatureStream): drain it, synthesise on the GPU
     const unsigned K = M_ / 2 + 1;
     std::vector<std::complex<float>> Y;
     int T = 0;
@@ -930,7 +999,8 @@ const float* OverSampledDFTSynthesisBank::next(int frame_no) {  // modulated.cc:
   if (frame_no_ + 1 >= nb_) { is_end_ = true; throw jiterator_error("end of samples!"); }
   if (frame_no >= 0 && frame_no - 1 != frame_no_) printf("The output might not be continuous %s: %d != %d\n", name().c_str(), frame_no - 1, frame_no_);
   increment_();
-  std::memcpy(vector_.data(), &out_[(size_t)frame_no_ * D_], sizeof(float) * D_);
+  if (live_bf_) { live_bf_->ensure_blocks(frame_no_); std::memcpy(vector_.data(), &live_bf_->time_out()[(size_t)frame_no_ * D_], sizeof(float) * D_); }
+  else std::memcpy(vector_.data(), &out_[(size_t)frame_no_ * D_], sizeof(float) * D_);
   return vector_.data();
 }
 

@@ -266,11 +266,25 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
   int frames() const { return T_; }
   int blocks() const { return nb_; }
   bool realized_with(const PostFilterConfig& pf, const SynthesisConfig& syn) const;
+  // ---- chunked realisation (host-mirror extension; the reference pulls ONE frame per next(), stream/stream.h:16-54).  With
+  // chunk_blocks > 0 the graph is not run on the whole utterance at the first next(): the samples are handed to the GPU
+  // chunk_blocks D-sample blocks at a time through btkb_stream_submit, and a chunk is submitted only when a frame (or output
+  // block) beyond the ones already computed is asked for.  Device memory is bounded by the chunk, and beamformer weights
+  // recomputed between two next() calls (a look-direction change, unit_test/test_online_beamforming.py:205-225) take effect
+  // with the next chunk while the adaptive state is kept.  Default: environment variable BTK20_CHUNK_BLOCKS, else 0 (whole
+  // utterance).  Not used for WPE chains and the batch-statistics beamformers.
+  void set_chunk_blocks(int blocks) { chunk_blocks_ = blocks > 0 ? blocks : 0; invalidate_(); }
+  int chunk_blocks() const { return chunk_blocks_; }
+  void ensure_frames(int t);    // make frame t available (no-op for a whole-utterance realisation)
+  void ensure_blocks(int b);    // make synthesis output block b available
   double samplerate_hint() const { return samplerate_; }
 
  protected:
   virtual void configure_weights_(btkb_pipeline* p) = 0;   // push delays / weights / covariance into a fresh pipeline
-  void invalidate_() { realized_ = false; }
+  virtual bool stream_capable_() const { return true; }   // false: the weights need statistics of the whole utterance on the device
+  void invalidate_() { realized_ = false; live_ = false; }
+  // new weights for the SAME graph: a live chunked stream keeps running and picks them up with its next chunk
+  void invalidate_weights_() { if (live_ && realized_) weights_dirty_ = true; else invalidate_(); }
   void require_weights_(bool ok, const char* msg) const { if (!ok) throw j_error("%s", msg); }
   unsigned fftLen_; bool halfBandShift_; int kind_;
   std::vector<VectorComplexFeatureStreamPtr> channels_;
@@ -289,6 +303,13 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
   SnapShotArrayPtr snap_;
   std::vector<unsigned long> src_versions_;
   void ensure_pipeline_(const PostFilterConfig& pf, const SynthesisConfig& syn, unsigned n_samples);
+  // chunked realisation state
+  int chunk_blocks_ = 0;
+  bool live_ = false, weights_dirty_ = false;
+  std::vector<const SampleFeature*> srcs_; unsigned n_total_ = 0, D_ = 0; size_t pos_ = 0;
+  int T_ready_ = 0, nb_ready_ = 0, chunk_t0_ = 0;
+  std::vector<float> xchunk_;
+  void advance_();
 };
 typedef std::shared_ptr<SubbandBeamformer> SubbandBeamformerPtr;
 
@@ -498,6 +519,7 @@ class OverSampledDFTSynthesisBank : public VectorFloatFeatureStream {
   unsigned M_, m_, r_, D_, dct_; int gain_; int pd_;
   btkb_pipeline* pipe_;            // only for the generic (arbitrary upstream) path
   std::vector<float> out_; int nb_; bool realized_;
+  SubbandBeamformer* live_bf_ = nullptr;   // chunked upstream realisation: output blocks are pulled from it as next() asks for them
 };
 typedef std::shared_ptr<OverSampledDFTSynthesisBank> OverSampledDFTSynthesisBankPtr;
 

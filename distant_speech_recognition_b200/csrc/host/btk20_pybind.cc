@@ -215,7 +215,9 @@ PYBIND11_MODULE(_btk20host, m) {
       .def("clear_channel", &SubbandBeamformer::clear_channel)
       .def("fftLen", &SubbandBeamformer::fftLen).def("chanN", &SubbandBeamformer::chanN)
       .def("snapshot_array", &SubbandBeamformer::snapshot_array)
-      .def("get_weights", &SubbandBeamformer::get_weights, py::arg("fbinX"));
+      .def("get_weights", &SubbandBeamformer::get_weights, py::arg("fbinX"))
+      .def("set_chunk_blocks", &SubbandBeamformer::set_chunk_blocks, py::arg("blocks"))   // host-mirror extension: chunked realisation
+      .def("chunk_blocks", &SubbandBeamformer::chunk_blocks);
 
   py::class_<SubbandDS, SubbandBeamformer, SubbandDSPtr>(m, "SubbandDSPtr")
       .def(py::init([](unsigned fftlen, bool hbs, const std::string& nm) { return std::make_shared<SubbandDS>(fftlen, hbs, nm); }), py::arg("fftlen") = 512,

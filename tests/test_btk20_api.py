@@ -438,3 +438,78 @@ def test_generic_python_stream_into_synthesis_and_analysis_iteration(protos):
     y = np.concatenate([np.array(b) for b in sfb])
     yo = restate.synthesis(0.5 * Xo, gg, M, 4, 1)
     assert y.shape == yo.shape and rel_l2(y, yo) < 1e-5
+
+
+# --------------------------------------------------------------------------- chunked realisation of the stream graph (round 2)
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_blocks", [1, 7, 64])
+def test_frontend_flow_chunked_equals_whole_utterance(protos, chunk_blocks):
+    """set_chunk_blocks(n): the graph behind next() is realised n blocks at a time through btkb_stream_submit instead of on the whole
+    utterance — GSC-NLMS -> synthesis and GSC + Zelinski -> synthesis give the same samples, bit for bit, for every chunk size."""
+    g = load_golden("gsclms_c8_m512"); h, gg = protos[512]; M, D = 512, 256
+
+    def lms(chunk):
+        afbs = _afbs(g["x"], h, M, D)
+        bf = pybeamformer.SubbandGSCLMSBeamformer(afbs, min_frames=int(g["min_frames"]))
+        bf.beamformer().set_chunk_blocks(chunk)
+        bf.calc_beamformer_weights(FS, g["delays"])
+        sfb = OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(bf), prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+        y = np.concatenate([np.array(b) for b in sfb])
+        return y, bf.total_updates(), np.array(bf.active_weights())
+
+    y0, n0, w0 = lms(0)
+    y1, n1, w1 = lms(chunk_blocks)
+    assert rel_l2(y0, g["time"]) < 1e-4
+    assert y1.shape == y0.shape and np.array_equal(y0, y1) and n0 == n1 and np.array_equal(w0, w1)
+
+    gz = load_golden("gsc_zelinski_c8_m512")
+
+    def zel(chunk):
+        afbs = _afbs(gz["x"], h, M, D)
+        bf = pybeamformer.SubbandGSCBeamformer(afbs, Nc=1)
+        bf.beamformer().set_chunk_blocks(chunk)
+        bf._waH[:257] = gz["wa"]
+        bf.calc_beamformer_weights(FS, gz["delays"])
+        pf = ZelinskiPostFilterPtr(PyVectorComplexFeatureStreamPtr(bf), M, 0.7, 2)
+        pf.set_beamformer(bf.beamformer())
+        sfb = OverSampledDFTSynthesisBankPtr(pf, prototype=gg, M=M, m=4, r=1, delay_compensation_type=2)
+        y = np.concatenate([np.array(b) for b in sfb])
+        pf.reset()
+        Y = np.array([np.array(v) for v in pf])
+        return y, Y
+
+    ya, Ya = zel(0)
+    yb, Yb = zel(chunk_blocks)
+    assert rel_l2(ya, gz["time"]) < 1e-4
+    assert np.array_equal(ya, yb) and np.array_equal(Ya, Yb)
+
+
+@pytest.mark.gpu
+def test_frontend_flow_look_direction_change_inside_the_frame_loop(protos):
+    """unit_test/test_online_beamforming.py:205-225: when the conf lists a second target position the script calls
+    beamformer.calc_beamformer_weights() inside `for frame_no, buf in enumerate(sfb)`.  With a chunked realisation the new weights
+    take effect with the next chunk (chunk = 1 block: with the next frame, like the reference) and the NLMS state is kept.  Checked
+    against the fp64 restatement with carried state; the whole-utterance realisation cannot express this (it would restart)."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, D, C, K = 256, 128, 4, 129
+    h, gg = protos[M]
+    x, d = synthetic.make_batch(1, C, 60 * D + 31, first=950)
+    d1, d2 = d[0], 0.3 * d[0]
+    F = 37                                              # the frame after which the look direction changes
+    afbs = _afbs(x[0], h, M, D)
+    bf = pybeamformer.SubbandGSCLMSBeamformer(afbs, min_frames=9)
+    bf.beamformer().set_chunk_blocks(1)
+    bf.calc_beamformer_weights(FS, d1)
+    Y = []
+    for frame_no, v in enumerate(bf):
+        Y.append(np.array(v))
+        if frame_no == F - 1:
+            bf.calc_beamformer_weights(FS, d2)
+    Y = np.array(Y)
+    Xo = np.stack([restate.analysis(x[0, c], h, M, 4, 1) for c in range(C)], axis=1)
+    st = {}
+    Yo1, _, _ = restate.gsc_lms(Xo[:F], FS, d1, state=st, min_frames=9)
+    Yo2, _, _ = restate.gsc_lms(Xo[F:], FS, d2, state=st, min_frames=9)
+    assert Y.shape[0] == Xo.shape[0]
+    assert rel_l2(Y[:F, :K], Yo1[:, :K]) < 1e-4 and rel_l2(Y[F:, :K], Yo2[:, :K]) < 1e-4
