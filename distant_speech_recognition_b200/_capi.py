@@ -205,8 +205,12 @@ class Pipeline:
     def pf_divide_nondiagonal(self, mu):
         _check(lib.btkb_pf_divide_nondiagonal(self._h, ct.c_float(mu)))
 
-    def calc_mvdr_weights(self, mu):
-        _check(lib.btkb_calc_mvdr_weights(self._h, ct.c_float(mu)))
+    def calc_mvdr_weights(self, mu, dthreshold=None):
+        """dthreshold: the reference's singular-value floor (default 1e-8, beamformer.i:414-486): bins below it get the identity."""
+        if dthreshold is None:
+            _check(lib.btkb_calc_mvdr_weights(self._h, ct.c_float(mu)))
+        else:
+            _check(lib.btkb_calc_mvdr_weights_ex(self._h, ct.c_float(mu), ct.c_float(dthreshold)))
 
     # ---- data path
     def submit(self, samples, lengths=None):

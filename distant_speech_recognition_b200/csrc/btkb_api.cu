@@ -456,12 +456,14 @@ int btkb_pf_divide_nondiagonal(btkb_pipeline* p, float mu) {
   return BTKB_OK;
 }
 
-int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu) {
+int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu) { return btkb_calc_mvdr_weights_ex(p, mu, 1.0e-8f); }   // dthreshold default of beamformer.i:414-486
+
+int btkb_calc_mvdr_weights_ex(btkb_pipeline* p, float mu, float dthreshold) {
   if (!p) return fail(BTKB_ERR_INVALID, "btkb_calc_mvdr_weights: null argument");
   if (!p->have_R) return fail(BTKB_ERR_STATE, "Set a spatial spectral matrix before calling calc_mvdr_weights()");  // beamformer.cc:2352-2354
   if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                      // beamformer.cc:2355-2357
   CK(cudaSetDevice(p->cfg.device));
-  if (p->C <= 8) CK(launch_mvdr_solve(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->stream));
+  if (p->C <= 8) CK(launch_mvdr_solve(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, dthreshold, p->stream));
   else CK(launch_mvdr_solve_wide(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->stream));
   p->have_w = true;
   return BTKB_OK;

@@ -145,7 +145,8 @@ cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, in
 cudaError_t launch_lcmv_weights(const double* delaysT, const double* delaysJ, float2* W, int U, int C, int NC, int M, int K, int Gp, float samplerate, cudaStream_t st);
 cudaError_t launch_spectral_recursion(const PerBinArgs& a, float mu, int noconj, cudaStream_t st);
 cudaError_t launch_diffuse_model(const double* mpos, float2* R, int U, int C, int M, int K, int Gp, float samplerate, float sspeed, cudaStream_t st);
-cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count, cudaStream_t st);
+cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count, float dthreshold,
+                              cudaStream_t st);
 cudaError_t launch_adaptive_rebase(const float2* Wold, const float2* Wnew, float2* UA, float* ST, int has_P, int U, int C, int K, int Gp, cudaStream_t st);
 cudaError_t launch_ua_to_wa(const float2* UA, const float2* W, float2* WA, int U, int C, int K, int Gp, cudaStream_t st);
 cudaError_t launch_noise_mask(const float* E, const int* lengths, const double* labels, unsigned char* mask, int* count, int U, int T, int D, int laN, int pdA,

@@ -13,6 +13,7 @@
 //                   double-precision LU solve of R^H t = d — same mathematics, tighter rounding)
 //   k_noise_mask    label / energy gating of accu_stats_from_label  pybeamformer.py:963-975
 #include "btkb_internal.h"
+#include "btkb_jacobi.cuh"
 
 namespace btkb {
 
@@ -219,7 +220,7 @@ cudaError_t launch_diffuse_model(const double* mpos, float2* R, int U, int C, in
 
 // w = (R^H)^-1 d / (C d^H R^-1 d), bin 0: all ones (beamformer.cc:2369-2371).  R row-major [i*C+j][g].
 template <int C>
-__global__ void k_mvdr_solve(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int K, int Gp, float mu, int normalize) {
+__global__ void k_mvdr_solve(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int K, int Gp, float mu, int normalize, float dthreshold) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= U * K) return;
   const int u = g / K, k = g - u * K;
@@ -240,8 +241,12 @@ __global__ void k_mvdr_solve(const float2* R, const float2* Dm, float2* W, const
       A[j][i] = cdconj(rij);
     }
   for (int c = 0; c < C; c++) { float2 t = Dm[(size_t)c * Gp + g]; d[c] = cdmake(t.x, t.y); b[c] = d[c]; }
-  // LU with partial pivoting, in place; solve A t = d
+  // pseudoinverse(R, invR, dThreshold) reports failure when a singular value is below dThreshold and the caller then uses the
+  // identity (beamformer.cc:267-274, 2381-2383): same rule here, on the smallest singular value of the loaded matrix
   bool singular = false;
+  if (dthreshold > 0.f && min_singular_value(&A[0][0], C) < (double)dthreshold) singular = true;
+  // LU with partial pivoting, in place; solve A t = d
+  if (!singular)
   for (int col = 0; col < C; col++) {
     int piv = col; double best = cdabs2(A[col][col]);
     for (int r = col + 1; r < C; r++) { double v = cdabs2(A[r][col]); if (v > best) { best = v; piv = r; } }
@@ -272,16 +277,16 @@ __global__ void k_mvdr_solve(const float2* R, const float2* Dm, float2* W, const
   for (int c = 0; c < C; c++) { cd wv = cddiv(tvec[c], norm); W[(size_t)c * Gp + g] = make_float2((float)wv.x, (float)wv.y); }
 }
 cudaError_t launch_mvdr_solve(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu,
-                              int normalize_by_count, cudaStream_t st) {
+                              int normalize_by_count, float dthreshold, cudaStream_t st) {
   const int n = U * K, bs = 64, gs = (n + bs - 1) / bs;
   switch (C) {
-    case 2: k_mvdr_solve<2><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
-    case 3: k_mvdr_solve<3><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
-    case 4: k_mvdr_solve<4><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
-    case 5: k_mvdr_solve<5><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
-    case 6: k_mvdr_solve<6><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
-    case 7: k_mvdr_solve<7><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
-    case 8: k_mvdr_solve<8><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count); break;
+    case 2: k_mvdr_solve<2><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count, dthreshold); break;
+    case 3: k_mvdr_solve<3><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count, dthreshold); break;
+    case 4: k_mvdr_solve<4><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count, dthreshold); break;
+    case 5: k_mvdr_solve<5><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count, dthreshold); break;
+    case 6: k_mvdr_solve<6><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count, dthreshold); break;
+    case 7: k_mvdr_solve<7><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count, dthreshold); break;
+    case 8: k_mvdr_solve<8><<<gs, bs, 0, st>>>(R, D, W, noise_count, U, K, Gp, mu, normalize_by_count, dthreshold); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

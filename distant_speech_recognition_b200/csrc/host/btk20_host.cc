@@ -723,7 +723,7 @@ void SubbandSOSNative::configure_weights_(btkb_pipeline* p) {
 
 // ---- SubbandMVDR
 SubbandMVDR::SubbandMVDR(unsigned fftLen, bool hbs, const std::string& nm) : SubbandDS(fftLen, hbs, nm, BTKB_BF_MVDR) {}
-void SubbandMVDR::clear_channel() { SubbandDS::clear_channel(); R_.clear(); wmvdr_.clear(); load_f_.clear(); div_f_.clear(); have_R_ = have_w_ = diffuse_ = smi_ = false; }
+void SubbandMVDR::clear_channel() { SubbandDS::clear_channel(); R_.clear(); wmvdr_.clear(); load_f_.clear(); div_f_.clear(); have_R_ = have_w_ = diffuse_ = smi_ = false; inv_ = InvSource(); }
 void SubbandMVDR::set_diagonal_looading(unsigned fbinX, float w) {   // beamformer.cc:2525-2535
   if (!have_R_) throw j_error("Construct first a noise covariance matrix\n");
   const unsigned K = fftLen_ / 2 + 1;
@@ -762,9 +762,15 @@ void SubbandMVDR::set_all_diagonal_loading(double w) {  // beamformer.cc:2511-25
   if (!have_R_) throw j_error("Construct first a noise covariance matrix\n");
   mu_ += (double)(float)w; have_w_ = false; invalidate_();
 }
-bool SubbandMVDR::calc_mvdr_weights(double samplerate, double /*dThreshold*/, bool /*calc_inverse_matrix*/) {  // beamformer.cc:2350-2402
+bool SubbandMVDR::calc_mvdr_weights(double samplerate, double dThreshold, bool calc_inverse_matrix) {  // beamformer.cc:2350-2402
   if (!have_R_) throw jallocation_error("Set a spatial spectral matrix before calling calc_mvdr_weights()\n");
   require_weights_(have_delays_, "call calc_array_manifold_vectorsX() once\n");
+  if (calc_inverse_matrix) {   // pseudoinverse(R_[f], invR_[f], dThreshold) now; later calls with calc_inverse_matrix = false reuse it
+    inv_.R = R_; inv_.diffuse = diffuse_; inv_.mpos = mpos_; inv_.sspeed = sspeed_; inv_.mu = mu_; inv_.load_f = load_f_; inv_.div_f = div_f_; inv_.valid = true;
+    dthreshold_ = (float)dThreshold;
+  } else if (!inv_.valid) {
+    throw j_error("calc_mvdr_weights(calc_inverse_matrix=False) needs an earlier call that computed the inverse matrices\n");   // the reference would read unset invR_
+  }
   samplerate_ = samplerate; have_w_ = true; W_.clear(); invalidate_();
   return true;
 }
@@ -798,6 +804,9 @@ void SubbandMVDR::configure_weights_(btkb_pipeline* p) {
   if (!have_w_) throw j_error("call calc_mvdr_weights() once\n");  // beamformer.cc:2544-2546
   if (NC_ > 1) throw j_error("SubbandMVDR: the GPU MVDR solve takes the delay-and-sum manifold (calc_array_manifold_vectors), not LCMV weights\n");
   ck(btkb_set_delays(p, 1, delays_.data()));
+  // the matrix of the last calc_mvdr_weights(calc_inverse_matrix = true)
+  const std::vector<std::complex<float>>& R_ = inv_.R; const bool diffuse_ = inv_.diffuse; const std::vector<double>& mpos_ = inv_.mpos;
+  const std::vector<double>& load_f_ = inv_.load_f; const std::vector<double>& div_f_ = inv_.div_f; const double sspeed_ = inv_.sspeed, mu_ = inv_.mu;
   if (diffuse_) ck(btkb_set_diffuse_noise_model(p, 1, mpos_.data(), (float)sspeed_));
   else ck(btkb_set_noise_covariance(p, 1, reinterpret_cast<const float*>(R_.data())));
   if (!load_f_.empty() || !div_f_.empty()) {   // per-bin edits (set_diagonal_looading, divide_nondiagonal_elements): O(K C^2) parameter edits
@@ -813,7 +822,7 @@ void SubbandMVDR::configure_weights_(btkb_pipeline* p) {
         }
     ck(btkb_set_noise_covariance(p, 1, reinterpret_cast<const float*>(R.data())));
   }
-  ck(btkb_calc_mvdr_weights(p, (float)mu_));
+  ck(btkb_calc_mvdr_weights_ex(p, (float)mu_, dthreshold_));
 }
 void SubbandMVDRGSC::set_active_weights_f(unsigned fbinX, const std::vector<double>& packed) {
   const unsigned C = chanN(), K = fftLen_ / 2 + 1;

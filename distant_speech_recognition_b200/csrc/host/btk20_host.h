@@ -424,6 +424,10 @@ class SubbandMVDR : public SubbandDS {
   // per-bin edits of R applied when the weights are configured (they commute: loading touches the diagonal only, the division
   // the off-diagonals only): extra diagonal load and the accumulated off-diagonal divisor, [K] each, empty = none
   std::vector<double> load_f_, div_f_;
+  // calc_mvdr_weights(samplerate, dThreshold, calc_inverse_matrix): the matrix the weights are solved with is the one present at the
+  // last call with calc_inverse_matrix = true (the reference keeps invR_ and reuses it, beamformer.cc:2379-2384)
+  struct InvSource { std::vector<std::complex<float>> R; bool diffuse = false; std::vector<double> mpos, load_f, div_f; double sspeed = 343740.0, mu = 0.0; bool valid = false; };
+  InvSource inv_; float dthreshold_ = 1.0e-8f;
 };
 typedef std::shared_ptr<SubbandMVDR> SubbandMVDRPtr;
 

@@ -142,6 +142,10 @@ int btkb_pf_divide_nondiagonal(btkb_pipeline* p, float mu);
  * (calc_mvdr_weights, beamformer.cc:2350-2402).  Uses the covariance from btkb_set_noise_covariance,
  * btkb_set_diffuse_noise_model or btkb_accumulate_covariance. */
 int btkb_calc_mvdr_weights(btkb_pipeline* p, float mu);
+/* the same with the reference's dThreshold (beamformer.i:414-486, default 1e-8): a bin whose loaded matrix has a singular value below
+ * it gets the identity instead of an inverse (pseudoinverse returns false, beamformer.cc:267-274, 2381-2383).  <= 8 channels; the wide
+ * solver keeps its pivot test.  btkb_calc_mvdr_weights(p, mu) == btkb_calc_mvdr_weights_ex(p, mu, 1e-8f). */
+int btkb_calc_mvdr_weights_ex(btkb_pipeline* p, float mu, float dthreshold);
 
 /* ---- data path ------------------------------------------------------------------------------------------------ */
 /* host samples float32 [U][C][n] (int16 scale, like SampleFeature, feature/feature.cc:605-649), lengths[U] <= n (NULL: all n).

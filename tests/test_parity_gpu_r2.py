@@ -235,3 +235,36 @@ def test_streamed_look_direction_change_keeps_the_adaptive_state(capi, protos):
     assert rel_l2(Y1, Yo1[:, :K]) < TOL
     assert rel_l2(Y2, Yo2[:, :K]) < TOL
     assert np.abs(Yo2 - restate.gsc_lms(Xo[F:], FS, d2[0], **lms)[0]).max() > 1.0      # the carried state matters
+
+
+def test_mvdr_weights_singular_value_threshold_rule(capi, protos):
+    """pseudoinverse() reports failure when ANY singular value of R is below dThreshold and calc_mvdr_weights then uses
+    the identity for that bin (beamformer.cc:267-274, 2381-2383).  Bins with s_min = 1e-5 < dthreshold = 1e-3 must come out as the
+    identity solution w = d / (C d^H d) = d C / C = d (|d_c| = 1/C), the others as R^-H d / (C d^H R^-1 d); with the default
+    threshold 1e-8 every bin is solved.  Hermitian and non-Hermitian matrices."""
+    from oracle import restate
+    M, C, K = 256, 4, 129
+    rng = np.random.default_rng(15)
+    d = np.array([[0.0, 6.0e-5, -1.1e-4, 2.0e-4]])
+    R = np.zeros((1, K, C, C), np.complex64)
+    low = set(range(3, K, 7))
+    for k in range(K):
+        Q, _ = np.linalg.qr(rng.standard_normal((C, C)) + 1j * rng.standard_normal((C, C)))
+        s = np.array([2.0, 1.0, 0.5, 1.0e-5 if k in low else 0.1])
+        if k % 2 == 0:
+            R[0, k] = (Q * s) @ Q.conj().T                                  # Hermitian positive definite
+        else:
+            Q2, _ = np.linalg.qr(rng.standard_normal((C, C)) + 1j * rng.standard_normal((C, C)))
+            R[0, k] = (Q * s) @ Q2.conj().T                                 # general: singular values s
+    wq = restate.calc_mainlobe(M, C, FS, d[0])
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=1, max_samples=4000)
+    p.set_prototypes(*protos[M]); p.set_delays(d); p.set_noise_covariance(R)
+    for thr in (1.0e-3, 1.0e-8):
+        p.calc_mvdr_weights(0.0, dthreshold=thr)
+        W = p.get_weights()[0]
+        Wo = restate.calc_mvdr_weights(R[0].astype(np.complex128), wq, thr=thr, single=False)
+        for k in range(1, K):
+            assert rel_l2(W[k], Wo[k]) < (2e-2 if (k in low and thr < 1e-5) else 1e-5), (thr, k)   # s_min = 1e-5 amplifies the complex64 rounding of R
+            if k in low and thr > 1e-5:
+                assert rel_l2(W[k], wq[k]) < 1e-6                           # the identity fallback
+    p.close()
