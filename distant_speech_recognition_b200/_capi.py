@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbtkb.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "btkb.h")
 
-BF_DS, BF_GSC, BF_MVDR, BF_GSC_LMS, BF_GSC_RLS = 0, 1, 2, 3, 4
+BF_DS, BF_GSC, BF_MVDR, BF_GSC_LMS, BF_GSC_RLS, BF_GSC_RLS_CPP = 0, 1, 2, 3, 4, 5
 SOS_BMVDR, SOS_GEV = 0, 1
 PF_NONE, PF_ZELINSKI, PF_MCCOWAN, PF_LEFKIMMIATIS = 0, 1, 2, 3
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
@@ -36,6 +36,10 @@ class RlsParams(ct.Structure):
                 ("constraint_option", ct.c_int), ("min_frames", ct.c_int)]
 
 
+class RlsCppParams(ct.Structure):
+    _fields_ = [("mu", ct.c_float), ("sigma2", ct.c_float), ("init_sigma2", ct.c_float), ("alpha", ct.c_float), ("qctype", ct.c_int), ("update", ct.c_int)]
+
+
 class WpeParams(ct.Structure):
     _fields_ = [("enabled", ct.c_int), ("lower_num", ct.c_int), ("upper_num", ct.c_int), ("iterations_num", ct.c_int),
                 ("load_db", ct.c_double), ("band_width", ct.c_double), ("diagonal_bias", ct.c_double), ("fp32_normal_equations", ct.c_int)]
@@ -46,7 +50,7 @@ class Config(ct.Structure):
                 ("delay_compensation_type", ct.c_int), ("samplerate", ct.c_float), ("beamformer", ct.c_int),
                 ("postfilter", ct.c_int), ("pf_alpha", ct.c_float), ("pf_type", ct.c_int), ("pf_min_frames", ct.c_int),
                 ("lms", LmsParams), ("max_utterances", ct.c_int), ("max_samples", ct.c_int), ("keep_snapshots", ct.c_int), ("synthesis_gain", ct.c_int), ("normalize_weight", ct.c_int),
-                ("pf_threshold", ct.c_float), ("pf_min_sv", ct.c_double), ("pf_fbin1", ct.c_int), ("rls", RlsParams), ("wpe", WpeParams)]
+                ("pf_threshold", ct.c_float), ("pf_min_sv", ct.c_double), ("pf_fbin1", ct.c_int), ("rls", RlsParams), ("wpe", WpeParams), ("rls_cpp", RlsCppParams)]
 
 
 def _load():
@@ -84,7 +88,7 @@ class Pipeline:
 
     def __init__(self, channels, fft_len=512, m=4, r=1, delay_compensation_type=2, samplerate=16000.0, beamformer=BF_DS,
                  postfilter=PF_NONE, pf_alpha=0.6, pf_type=2, pf_min_frames=0, lms=None, max_utterances=1,
-                 max_samples=160000, device=0, normalize_weight=False, pf_threshold=0.99, pf_min_sv=1.0e-8, pf_fbin1=0, rls=None, wpe=None):
+                 max_samples=160000, device=0, normalize_weight=False, pf_threshold=0.99, pf_min_sv=1.0e-8, pf_fbin1=0, rls=None, wpe=None, rls_cpp=None):
         cfg = Config()
         lib.btkb_default_config(ct.byref(cfg))
         cfg.device = device; cfg.channels = channels; cfg.fft_len = fft_len; cfg.m = m; cfg.r = r
@@ -99,6 +103,9 @@ class Pipeline:
             for k, v in rls.items():
                 if k != "slowdown_after":   # a constructor argument the reference's RLS loop never reads
                     setattr(cfg.rls, k, v)
+        if rls_cpp:
+            for k, v in rls_cpp.items():
+                setattr(cfg.rls_cpp, k, v)
         if wpe is not None:
             cfg.wpe.enabled = 1
             for k, v in wpe.items():

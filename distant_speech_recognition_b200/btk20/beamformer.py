@@ -1,3 +1,3 @@
 """btk20.beamformer (beamformer/beamformer.i:46-540): snapshot array and the subband beamformers of the hot path."""
 from .._btk20host import (SnapShotArrayPtr, SubbandBeamformerPtr, SubbandDSPtr, SubbandGSCPtr, SubbandMVDRPtr,  # noqa: F401
-                          SubbandMVDRGSCPtr, SubbandGSCLMSPtr, LmsConfig, SubbandGSCRLSNativePtr, RlsConfig, SubbandSOSNativePtr, calc_all_delays)
+                          SubbandMVDRGSCPtr, SubbandGSCRLSPtr, SubbandGSCLMSPtr, LmsConfig, SubbandGSCRLSNativePtr, RlsConfig, SubbandSOSNativePtr, calc_all_delays)

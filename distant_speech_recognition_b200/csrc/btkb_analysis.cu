@@ -21,6 +21,7 @@
 #include "btkb_internal.h"
 #include "btkb_fft.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace btkb {
 
@@ -350,6 +351,7 @@ static cudaError_t launch_analysis_r1(const AnalysisArgs& a_in, cudaStream_t st)
   using Plan = FftPlan<M>;
   constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
   size_t smem = sizeof(float2) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * 4;
+  if (const char* e = getenv("BTKB_ANALYSIS_SMEM_PAD")) smem += (size_t)std::max(0, atoi(e));   // occupancy experiment: unused extra shared memory per CTA
   auto kern = analysis_packed() ? k_analysis_r1<M, MT, FR, G, true> : k_analysis_r1<M, MT, FR, G, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -93,6 +93,7 @@ void btkb_default_config(btkb_config* c) {
   c->wpe.diagonal_bias = 1.0e-4;
   c->rls.beta = 0.97f; c->rls.gamma = 0.04f; c->rls.mu = 0.97f; c->rls.init_diagonal_load = 1.0e6f; c->rls.regularization_param = 1.0e-2f;
   c->rls.sil_thresh = 1.0e8f; c->rls.alpha2 = 10.f; c->rls.max_wa_l2norm = 100.f; c->rls.constraint_option = 3; c->rls.min_frames = 128;
+  c->rls_cpp.mu = 0.9f; c->rls_cpp.sigma2 = 0.01f; c->rls_cpp.init_sigma2 = 0.01f; c->rls_cpp.alpha = -1.0f; c->rls_cpp.qctype = 0; c->rls_cpp.update = 1;
 }
 
 static void fb_delays(int m, int r, int dct, bool synthesis, int* pd, int* la) {  // modulated.cc:246-264
@@ -133,7 +134,9 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   if (C < 1) return fail(BTKB_ERR_INVALID, "btkb_create: channels must be >= 1");
   if (C > 64) return fail(BTKB_ERR_INVALID, "btkb_create: at most 64 channels");
   if (cfg->max_utterances < 1 || cfg->max_samples < 1) return fail(BTKB_ERR_INVALID, "btkb_create: capacities must be positive");
-  if (cfg->beamformer < BTKB_BF_DS || cfg->beamformer > BTKB_BF_GSC_RLS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown beamformer kind");
+  if (cfg->beamformer < BTKB_BF_DS || cfg->beamformer > BTKB_BF_GSC_RLS_CPP) return fail(BTKB_ERR_INVALID, "btkb_create: unknown beamformer kind");
+  if (cfg->beamformer == BTKB_BF_GSC_RLS_CPP && (C < 2 || C > 8 || cfg->postfilter != BTKB_PF_NONE))
+    return fail(BTKB_ERR_INVALID, "btkb_create: the C++ SubbandGSCRLS kernel is built for 2..8 channels without a fused post-filter");
   if (cfg->postfilter < BTKB_PF_NONE || cfg->postfilter > BTKB_PF_LEFKIMMIATIS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown post-filter kind");
   if (cfg->postfilter >= BTKB_PF_MCCOWAN && (C < 2 || C > 8))
     return fail(BTKB_ERR_INVALID, "btkb_create: the McCowan / Lefkimmiatis post-filters are built for 2..8 channels");
@@ -289,7 +292,7 @@ static void begin_weight_batch(btkb_pipeline* p, int U) {
 int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
   if (!p || !delays) return fail(BTKB_ERR_INVALID, "btkb_set_delays: null argument");
   int rc = check_weight_batch(p, U, "btkb_set_delays"); if (rc) return rc;
-  if ((p->cfg.beamformer == BTKB_BF_GSC || p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS) && p->C <= 1)  // beamformer.cc:507-510
+  if ((p->cfg.beamformer == BTKB_BF_GSC || p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS || p->cfg.beamformer == BTKB_BF_GSC_RLS_CPP) && p->C <= 1)  // beamformer.cc:507-510
     return fail(BTKB_ERR_INVALID, "The number of channels must be > 1 but it is " + std::to_string(p->C));
   CK(cudaSetDevice(p->cfg.device));
   begin_weight_batch(p, U);
@@ -557,6 +560,8 @@ static PerBinArgs perbin_args(btkb_pipeline* p) {
   a.lms = LmsArgs{l.beta, l.gamma, l.init_diagonal_load, l.regularization_param, l.energy_floor, l.sil_thresh, l.max_wa_l2norm, l.min_frames, l.slowdown_after};
   const btkb_rls_params& q = p->cfg.rls;
   a.rls = RlsArgs{q.beta, q.gamma, q.mu, q.init_diagonal_load, q.regularization_param, q.sil_thresh, q.alpha2, q.max_wa_l2norm, q.constraint_option, q.min_frames};
+  const btkb_rls_cpp_params& rc = p->cfg.rls_cpp;
+  a.rlsc = RlsCppArgs{rc.mu, rc.sigma2, rc.init_sigma2, rc.alpha, rc.qctype, rc.update};
   return a;
 }
 
@@ -610,7 +615,13 @@ static int do_beamformer(btkb_pipeline* p) {
     }
     a.PFQ = p->d_pfQ; a.LAM = p->d_LAM; a.pf_fbin1 = p->cfg.pf_fbin1;
   }
-  if (narrow) CK(launch_perbin(a, p->stream)); else CK(launch_perbin_wide(a, p->stream));
+  if (p->cfg.beamformer == BTKB_BF_GSC_RLS_CPP) {
+    if (!narrow) return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the C++ SubbandGSCRLS kernel is built for 2..8 channels");
+    a.WL = p->d_WL;   // final wl = B wa, readable through btkb_get_sidelobe_weights
+    CK(launch_perbin_rls_cpp(a, p->d_delays, p->cfg.samplerate, p->stream));
+    p->have_wl = true;
+  }
+  else if (narrow) CK(launch_perbin(a, p->stream)); else CK(launch_perbin_wide(a, p->stream));
   p->launches++;
   p->have_Y = true; p->pf_applied = true;
   p->have_ua = (p->cfg.beamformer == BTKB_BF_GSC_LMS || p->cfg.beamformer == BTKB_BF_GSC_RLS);
@@ -1100,6 +1111,7 @@ int btkb_device_pointers(btkb_pipeline* p, void** X, void** Y, void** time_out) 
 static int stream_unsupported(btkb_pipeline* p) {
   if (p->cfg.wpe.enabled) return fail(BTKB_ERR_INVALID, "btkb_stream_begin: WPE buffers the whole utterance by definition (dereverberation.cc:500-534); submit whole utterances");
   if (p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_stream_begin: streamed chunks are built for the register-path kernels (<= 8 channels)");
+  if (p->cfg.beamformer == BTKB_BF_GSC_RLS_CPP) return fail(BTKB_ERR_INVALID, "btkb_stream_begin: the fp64 SubbandGSCRLS parity kernel processes whole utterances");
   return BTKB_OK;
 }
 

@@ -56,6 +56,8 @@ struct RlsArgs {
   int constraint_option, min_frames;
 };
 
+struct RlsCppArgs { float mu, sigma2, init_sigma2, alpha; int qctype, update; };   // SubbandGSCRLS (C++), btkb_rls_cpp.cu
+
 struct PerBinArgs {
   const float2* X; const float* E; const int* lengths;
   const float2* W;    // [C][Gp] quiescent / mvdr weights (not conjugated)
@@ -77,6 +79,7 @@ struct PerBinArgs {
   const float2* PFQ; const float* LAM; int pf_fbin1;
   LmsArgs lms;
   RlsArgs rls;
+  RlsCppArgs rlsc;
   float energy_threshold;
   float2* Scov; int Ts;   // 64-mic tensor-core covariance: series-major workspace S[g][c][Ts] (btkb_cov_tc.cu)
   // streamed chunks (btkb_stream_submit): t_base = absolute number of the chunk's first frame (the recurrences test absolute frame
@@ -132,6 +135,7 @@ cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
 cudaError_t launch_synthesis(const SynthesisArgs& a, cudaStream_t st);
 cudaError_t launch_perbin(const PerBinArgs& a, cudaStream_t st);
 cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st);
+cudaError_t launch_perbin_rls_cpp(const PerBinArgs& a, const double* delays, float samplerate, cudaStream_t st);   // fp64, btkb_rls_cpp.cu
 // wide arrays (C = 16, 32, 64): btkb_wide.cu
 cudaError_t launch_perbin_wide(const PerBinArgs& a, cudaStream_t st);
 cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st);

@@ -342,6 +342,7 @@ void SubbandBeamformer::ensure_pipeline_(const PostFilterConfig& pf, const Synth
     c.wpe.enabled = 1; c.wpe.lower_num = (int)w.lower_num; c.wpe.upper_num = (int)w.upper_num; c.wpe.iterations_num = (int)w.iterations_num;
     c.wpe.load_db = w.load_db; c.wpe.band_width = w.band_width; c.wpe.diagonal_bias = w.diagonal_bias;
   }
+  tune_config_(c);
   if (pipe_) { btkb_destroy(pipe_); pipe_ = nullptr; }
   ck(btkb_create(&c, &pipe_));
   ck(btkb_set_prototypes(pipe_, a0->prototype().data(), syn.enabled ? syn.prototype.data() : nullptr, (int)a0->prototype().size()));
@@ -619,6 +620,21 @@ void SubbandGSC::configure_weights_(btkb_pipeline* p) {
   if (have_wq_explicit_) ck(btkb_set_weights(p, 1, reinterpret_cast<const float*>(wq_explicit_.data())));
   else set_delays_(p);
   if (have_wa_) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
+}
+
+// ---- SubbandGSCRLS (the reference's C++ class)
+SubbandGSCRLS::SubbandGSCRLS(unsigned fftLen, bool hbs, float myu, float sigma2, const std::string& nm) : SubbandGSC(fftLen, hbs, nm), mu_(myu), sigma2_(sigma2) {
+  kind_ = BTKB_BF_GSC_RLS_CPP;
+}
+void SubbandGSCRLS::tune_config_(btkb_config& c) {
+  c.rls_cpp.mu = mu_; c.rls_cpp.sigma2 = sigma2_; c.rls_cpp.init_sigma2 = init_sigma2_; c.rls_cpp.alpha = alpha_; c.rls_cpp.qctype = qctype_; c.rls_cpp.update = update_ ? 1 : 0;
+}
+void SubbandGSCRLS::configure_weights_(btkb_pipeline* p) {
+  require_weights_(have_delays_, "call calc_gsc_weights_x() once\n");   // beamformer.cc:1518-1519
+  if (!have_pz_) throw j_error("set the precision matrix with init_precision_matrix() or set_precision_matrix()\n");   // :1520-1521
+  if (NC_ > 1) throw j_error("SubbandGSCRLS: the GPU kernel implements one linear constraint\n");
+  if (chunk_blocks_ > 0) chunk_blocks_ = 0;   // whole utterances only (btkb_stream_begin refuses this kind)
+  ck(btkb_set_delays(p, 1, delays_.data()));
 }
 
 // ---- SubbandGSCLMS

@@ -25,6 +25,7 @@
 #include <vector>
 
 struct btkb_pipeline;
+struct btkb_config;
 
 namespace btk20 {
 
@@ -281,7 +282,8 @@ class SubbandBeamformer : public VectorComplexFeatureStream {
 
  protected:
   virtual void configure_weights_(btkb_pipeline* p) = 0;   // push delays / weights / covariance into a fresh pipeline
-  virtual bool stream_capable_() const { return true; }   // false: the weights need statistics of the whole utterance on the device
+  virtual bool stream_capable_() const { return true; }
+  virtual void tune_config_(btkb_config&) {}   // last word of a subclass on the pipeline configuration (kind-specific parameter blocks)   // false: the weights need statistics of the whole utterance on the device
   void invalidate_() { realized_ = false; live_ = false; }
   // new weights for the SAME graph: a live chunked stream keeps running and picks them up with its next chunk
   void invalidate_weights_() { if (live_ && realized_) weights_dirty_ = true; else invalidate_(); }
@@ -375,6 +377,22 @@ class SubbandGSCRLSNative : public SubbandDS {
   int total_updates();
 };
 typedef std::shared_ptr<SubbandGSCRLSNative> SubbandGSCRLSNativePtr;
+
+// The reference's C++ class SubbandGSCRLS (beamformer.h:236-275, beamformer.cc:1447-1699, beamformer.i:289-339): GSC with an RLS
+// sidelobe canceller in the blocking-matrix basis (Z = B^H x), fp64 on the GPU (BTKB_BF_GSC_RLS_CPP, csrc/btkb_rls_cpp.cu).
+class SubbandGSCRLS : public SubbandGSC {
+ public:
+  SubbandGSCRLS(unsigned fftLen = 512, bool half_band_shift = false, float myu = 0.9f, float sigma2 = 0.01f, const std::string& nm = "SubbandGSCRLS");
+  void init_precision_matrix(float sigma2 = 0.01f) { init_sigma2_ = sigma2; have_pz_ = true; invalidate_(); }                 // beamformer.cc:1479-1492
+  void update_active_weight_vecotrs(bool flag) { update_ = flag; invalidate_(); }                                           // beamformer.h:252 (sic)
+  void set_quadratic_constraint(float alpha, int qctype = 1) { alpha_ = alpha; qctype_ = qctype; invalidate_(); }            // beamformer.h:253-254
+  // set_precision_matrix(fbinX, Pz) (per-bin start matrices, beamformer.cc:1494-1506) is not mirrored: see INTEGRATION.md
+ protected:
+  void configure_weights_(btkb_pipeline* p) override;
+  void tune_config_(btkb_config& c) override;
+  float mu_, sigma2_, init_sigma2_ = 0.01f, alpha_ = -1.0f; int qctype_ = 0; bool update_ = true, have_pz_ = false;
+};
+typedef std::shared_ptr<SubbandGSCRLS> SubbandGSCRLSPtr;
 
 // native body of pybeamformer.SubbandSOSBatchBeamformer / SubbandBlindMVDRBeamformer / SubbandGEVBeamformer
 // (lib/pybeamformer.py:1026-1357): the statistics live on the device in a pipeline of their own and accumulate over calls

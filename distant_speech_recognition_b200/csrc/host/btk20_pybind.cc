@@ -255,6 +255,13 @@ PYBIND11_MODULE(_btk20host, m) {
       .def_readwrite("sil_thresh", &LmsConfig::sil_thresh).def_readwrite("max_wa_l2norm", &LmsConfig::max_wa_l2norm)
       .def_readwrite("min_frames", &LmsConfig::min_frames).def_readwrite("slowdown_after", &LmsConfig::slowdown_after);
 
+  py::class_<SubbandGSCRLS, SubbandGSC, SubbandGSCRLSPtr>(m, "SubbandGSCRLSPtr")   // beamformer.i:289-339
+      .def(py::init([](unsigned fftlen, bool hbs, float myu, float sigma2, const std::string& nm) { return std::make_shared<SubbandGSCRLS>(fftlen, hbs, myu, sigma2, nm); }),
+           py::arg("fftlen"), py::arg("half_band_shift") = false, py::arg("myu") = 0.9f, py::arg("sigma2") = 0.01f, py::arg("nm") = "SubbandGSCRLS")
+      .def("init_precision_matrix", &SubbandGSCRLS::init_precision_matrix, py::arg("sigma2") = 0.01f)
+      .def("update_active_weight_vecotrs", &SubbandGSCRLS::update_active_weight_vecotrs, py::arg("flag"))
+      .def("set_quadratic_constraint", &SubbandGSCRLS::set_quadratic_constraint, py::arg("alpha"), py::arg("qctype") = 1);
+
   py::class_<SubbandGSCLMS, SubbandDS, SubbandGSCLMSPtr>(m, "SubbandGSCLMSPtr")
       .def(py::init([](unsigned fftlen, const LmsConfig& c, const std::string& nm) { return std::make_shared<SubbandGSCLMS>(fftlen, c, nm); }), py::arg("fftlen"),
            py::arg("config"), py::arg("nm") = "SubbandGSCLMS")

@@ -45,6 +45,7 @@ extern "C" {
 #define BTKB_BF_MVDR 2     /* SubbandMVDR / SubbandMVDRGSC: y = (wmvdr - wl)^H x             (beamformer.cc:2537-2587, 2719-2773) */
 #define BTKB_BF_GSC_LMS 3  /* SubbandGSCLMSBeamformer: leaky power-normalised NLMS           (pybeamformer.py:588-762) */
 #define BTKB_BF_GSC_RLS 4  /* SubbandGSCRLSBeamformer: regularised RLS sidelobe canceller    (pybeamformer.py:765-928) */
+#define BTKB_BF_GSC_RLS_CPP 5 /* the C++ class SubbandGSCRLS: RLS in the blocking-matrix basis, fp64 (beamformer.cc:1447-1699) */
 
 /* post-filter kinds */
 #define BTKB_PF_NONE 0
@@ -64,6 +65,15 @@ typedef struct btkb_rls_params { /* defaults = unit_test/confs/gscrls.json / pyb
   int constraint_option;  /* 0 none, 1 quadratic constraint, 2 norm normalisation, 3 both */
   int min_frames;
 } btkb_rls_params;
+
+typedef struct btkb_rls_cpp_params { /* SubbandGSCRLS(fftlen, half_band_shift, myu = 0.9, sigma2 = 0.01) (beamformer.i:306-330) */
+  float mu;           /* forgetting factor myu */
+  float sigma2;       /* diagonal_weights_[f]: the leak of the weight update (constructor argument sigma2) */
+  float init_sigma2;  /* init_precision_matrix(sigma2 = 0.01): Pz = I / sigma2 */
+  float alpha;        /* set_quadratic_constraint(alpha, qctype) */
+  int qctype;         /* 0 none, 1 CONSTANT_NORM, 2 THRESHOLD_LIMITATION (beamformer.h) */
+  int update;         /* update_active_weight_vecotrs(flag), default 1 */
+} btkb_rls_cpp_params;
 
 typedef struct btkb_wpe_params { /* MultiChannelWPEDereverberation ctor (dereverberation.cc:312-334); defaults = unit_test/confs/wpe.json */
   int enabled;         /* 1: btkb_run() dereverberates the snapshots between the analysis bank and the beamformer */
@@ -96,6 +106,7 @@ typedef struct btkb_config {
   int pf_fbin1;                /* Lefkimmiatis: first bin that divides the noise PSD by Lambda = d^H R^-1 d (default 0) */
   btkb_rls_params rls;         /* BTKB_BF_GSC_RLS */
   btkb_wpe_params wpe;         /* multi-channel WPE dereverberation of the snapshots (C = 1, 2, 4 or 8) */
+  btkb_rls_cpp_params rls_cpp; /* BTKB_BF_GSC_RLS_CPP */
 } btkb_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */

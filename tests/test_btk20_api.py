@@ -513,3 +513,25 @@ def test_frontend_flow_look_direction_change_inside_the_frame_loop(protos):
     Yo2, _, _ = restate.gsc_lms(Xo[F:], FS, d2, state=st, min_frames=9)
     assert Y.shape[0] == Xo.shape[0]
     assert rel_l2(Y[:F, :K], Yo1[:, :K]) < 1e-4 and rel_l2(Y[F:, :K], Yo2[:, :K]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_frontend_flow_cpp_subband_gsc_rls(protos):
+    """The reference's C++ class SubbandGSCRLSPtr (beamformer.i:289-339): calc_gsc_weights + init_precision_matrix, iterate; against the
+    compiled reference's output for the class defaults and a quadratic constraint; next() before init_precision_matrix raises."""
+    from distant_speech_recognition_b200.btk20.beamformer import SubbandGSCRLSPtr
+    g = load_golden("gscrls_cpp_c4_m256"); h, gg = protos[256]; M, D = 256, 128
+    for i, (ctor, init, qc) in enumerate(((dict(myu=0.9, sigma2=0.01), 0.01, None), (dict(myu=0.97, sigma2=0.0), 1e6, (0.5, 2)))):
+        afbs = _afbs(g["x"], h, M, D)
+        bf = SubbandGSCRLSPtr(fftlen=M, half_band_shift=False, **ctor)
+        for a in afbs:
+            bf.set_channel(a)
+        bf.calc_gsc_weights(FS, g["delays"])
+        if i == 0:
+            with pytest.raises(Exception, match="precision matrix"):
+                bf.next()
+        bf.init_precision_matrix(init)
+        if qc:
+            bf.set_quadratic_constraint(*qc)
+        Y = np.array([np.array(v) for v in bf])
+        assert Y.shape == (g["Y%d" % i].shape[0], M) and rel_l2(Y[:, :129], g["Y%d" % i]) < 1e-4

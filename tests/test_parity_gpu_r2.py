@@ -7,7 +7,7 @@ Everything through the C-ABI, against the fp64 restatement (oracle/restate.py) o
 import numpy as np
 import pytest
 
-from conftest import rel_l2
+from conftest import load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-4
@@ -268,3 +268,26 @@ def test_mvdr_weights_singular_value_threshold_rule(capi, protos):
             if k in low and thr > 1e-5:
                 assert rel_l2(W[k], wq[k]) < 1e-6                           # the identity fallback
     p.close()
+
+
+def test_cpp_subband_gsc_rls_golden(capi, protos):
+    """SURVEY §8 f3, the C++ class SubbandGSCRLS (beamformer.cc:1447-1699): the fp64 blocking-matrix-form kernel k_perbin_rls_cpp against
+    the output of the compiled reference (golden_gscrls_cpp_c4_m256, tests/golden/make_golden_rls_cpp.py) for the class defaults
+    (mu 0.9, sigma2 0.01, init_precision_matrix(0.01): 14 cancelled digits per update, see btkb_rls_cpp.cu) and for the two
+    quadratic-constraint types; plus the final wl = B wa against the fp64 restatement."""
+    from oracle import restate
+    g = load_golden("gscrls_cpp_c4_m256")
+    CASES = (dict(mu=0.9, sigma2=0.01, init_sigma2=0.01), dict(mu=0.97, sigma2=0.0, init_sigma2=1e6, alpha=0.5, qctype=2),
+             dict(mu=0.95, sigma2=1e-3, init_sigma2=1.0, alpha=0.3, qctype=1))
+    x = g["x"]; M = 256; h, gg = protos[M]
+    X = np.stack([restate.analysis(x[c], h, M, 4, 1) for c in range(4)], axis=1)
+    for i, kw in enumerate(CASES):
+        p = capi.Pipeline(4, M, 4, 1, beamformer=capi.BF_GSC_RLS_CPP, rls_cpp=kw, max_utterances=1, max_samples=x.shape[1])
+        p.set_prototypes(h, gg); p.set_delays(g["delays"][None]); p.submit(x[None]); p.run(True)
+        Y = p.fetch_subband()[0]
+        assert rel_l2(Y, g["Y%d" % i]) < TOL, (i, rel_l2(Y, g["Y%d" % i]))
+        Yo, wlo = restate.gsc_rls_cpp(X, FS, g["delays"], **kw)
+        assert rel_l2(p.fetch_time()[0], restate.synthesis(Yo, gg, M, 4, 1)) < TOL
+        wl = p.get_sidelobe_weights()[0]
+        assert rel_l2(wl[1:], wlo[1:]) < 1e-3, (i, rel_l2(wl[1:], wlo[1:]))
+        p.close()
