@@ -163,7 +163,16 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) 
 // PK = true: the fold and the transforms use the packed 2 x fp32 instructions (btkb_f2.cuh).  The two real channels of a pair are
 // the halves of one float2, so a tap MAC on both channels is one FFMA2 with the tap broadcast; results are bit-identical to
 // PK = false.  The default since round 2 (0.499 vs 0.531 ms at configs[1] on B200); BTKB_ANALYSIS_PACKED=0 selects the scalar kernel.
-template <int M, int MT, int FR, int G, bool PK = false>
+// exact int16 -> fp32 of the two halves of a packed sample word (a | b << 16) without the conversion pipe: 0x4B000000 | (v ^ 0x8000) is the
+// float 2^23 + (v + 32768); subtracting 2^23 + 32768 is exact
+__device__ __forceinline__ float2 unpack_i16x2(uint32_t w) {
+  const uint32_t t = w ^ 0x80008000u;
+  const float lo = __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7610)) - 8421376.0f;
+  const float hi = __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7632)) - 8421376.0f;
+  return make_float2(lo, hi);
+}
+
+template <int M, int MT, int FR, int G, bool PK = false, bool I16 = false>
 __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(AnalysisArgs a) {
   using Plan = FftPlan<M>;
   constexpr int NT = Plan::NT, R0 = Plan::R0, NB = 8 / R0, P = Plan::P;
@@ -176,7 +185,8 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
   // the two channels are staged as separate planes (16-byte cp.async chunks land without a register round trip)
   float* xsa = reinterpret_cast<float*>(smem_raw);                    // [W] channel a
   float* xsb = xsa + W;                                               // [W] channel b
-  float2* fbuf = reinterpret_cast<float2*>(xsb + W);                  // [G][2][BUF]
+  uint32_t* xs16 = reinterpret_cast<uint32_t*>(smem_raw);             // I16: [W] packed (a | b << 16)
+  float2* fbuf = reinterpret_cast<float2*>(smem_raw + (I16 ? sizeof(uint32_t) * W : 2 * sizeof(float) * W));   // [G][2][BUF]
   float* red = reinterpret_cast<float*>(fbuf + G * 2 * Plan::BUF);    // [G][2][NW]
   float2* buf0 = fbuf + (grp * 2 + 0) * Plan::BUF;
   float2* buf1 = fbuf + (grp * 2 + 1) * Plan::BUF;
@@ -184,8 +194,10 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
   const int ca = 2 * pair, cb = 2 * pair + 1;
   const bool has_b = cb < a.C;
   const int len = a.lengths[u];
-  const float* xa = a.x + ((size_t)u * a.C + ca) * a.n_stride;
-  const float* xb = a.x + ((size_t)u * a.C + (has_b ? cb : ca)) * a.n_stride;
+  const float* xa = I16 ? nullptr : a.x + ((size_t)u * a.C + ca) * a.n_stride;
+  const float* xb = I16 ? nullptr : a.x + ((size_t)u * a.C + (has_b ? cb : ca)) * a.n_stride;
+  const int16_t* ya = I16 ? a.x16 + ((size_t)u * a.C + ca) * a.n16_stride : nullptr;
+  const int16_t* yb = I16 ? a.x16 + ((size_t)u * a.C + (has_b ? cb : ca)) * a.n16_stride : nullptr;
   // slot(q): register slot of polyphase index i_q = tg + NT q  (q = b + r NB, slot = b R0 + r)
 #define BTKB_SLOT(q) (((q) % NB) * R0 + (q) / NB)
   float hreg[8 * MT];
@@ -212,6 +224,47 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
   // The copies are committed in NIT groups, group i holding the samples iteration i needs beyond those of iteration i-1,
   // so the first frames start as soon as their window has landed while the rest of the tile is still in flight.
   constexpr int NIT = FR / (2 * G);
+  if constexpr (I16) {
+    // 16-bit PCM: 8 samples of each channel per thread and step (two 16-byte loads), interleaved into packed words with PRMT and stored as
+    // two 16-byte shared-memory writes; samples outside [0, len) are zeros.  All loads of the tile are issued before the first store.
+    static_assert(W % 8 == 0, "tile length must be a multiple of 8 samples");
+    constexpr int NCH = (W / 8 + G * NT - 1) / (G * NT);
+    uint4 ra[NCH], rb[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; j++) {
+      const int w = 8 * (tid + j * G * NT);
+      const long long s = w0 + w;
+      ra[j] = make_uint4(0u, 0u, 0u, 0u); rb[j] = ra[j];
+      if (w < W && s + 8 > 0 && s < (long long)len) {
+        if (s >= 0 && s + 8 <= (long long)len) {
+          ra[j] = __ldg(reinterpret_cast<const uint4*>(ya + s));
+          if (has_b) rb[j] = __ldg(reinterpret_cast<const uint4*>(yb + s));
+        } else {   // ragged edge of the utterance: sample by sample
+          uint16_t ea[8], eb[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const long long si = s + i;
+            const bool ok = si >= 0 && si < (long long)len;
+            ea[i] = ok ? (uint16_t)ya[si] : (uint16_t)0; eb[i] = (ok && has_b) ? (uint16_t)yb[si] : (uint16_t)0;
+          }
+          ra[j] = make_uint4(ea[0] | (uint32_t)ea[1] << 16, ea[2] | (uint32_t)ea[3] << 16, ea[4] | (uint32_t)ea[5] << 16, ea[6] | (uint32_t)ea[7] << 16);
+          rb[j] = make_uint4(eb[0] | (uint32_t)eb[1] << 16, eb[2] | (uint32_t)eb[3] << 16, eb[4] | (uint32_t)eb[5] << 16, eb[6] | (uint32_t)eb[7] << 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; j++) {
+      const int w = 8 * (tid + j * G * NT);
+      if (w < W) {
+        uint4 lo, hi;   // word i = a_i | b_i << 16
+        lo.x = __byte_perm(ra[j].x, rb[j].x, 0x5410); lo.y = __byte_perm(ra[j].x, rb[j].x, 0x7632);
+        lo.z = __byte_perm(ra[j].y, rb[j].y, 0x5410); lo.w = __byte_perm(ra[j].y, rb[j].y, 0x7632);
+        hi.x = __byte_perm(ra[j].z, rb[j].z, 0x5410); hi.y = __byte_perm(ra[j].z, rb[j].z, 0x7632);
+        hi.z = __byte_perm(ra[j].w, rb[j].w, 0x5410); hi.w = __byte_perm(ra[j].w, rb[j].w, 0x7632);
+        *reinterpret_cast<uint4*>(xs16 + w) = lo; *reinterpret_cast<uint4*>(xs16 + w + 4) = hi;
+      }
+    }
+  } else {
 #pragma unroll
   for (int gi = 0; gi < NIT; gi++) {
     const int lo = (gi == 0) ? 0 : (2 * G * gi - 1) * D + MT * M;
@@ -227,11 +280,12 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  }
 #pragma unroll 1
   for (int it = 0; it < NIT; it++) {
     const int f0 = it * 2 * G;
     // groups 0..it must have landed: at most NIT-1-it of the most recent groups may still be pending
-    switch (NIT - 1 - it) {
+    if constexpr (!I16) switch (NIT - 1 - it) {
       case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
       case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
       case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
@@ -254,7 +308,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
       for (int q = 0; q < 8; q++)
 #pragma unroll
         for (int k = 0; k < MT; k++) {
-          const float2 s = make_float2(xsa[base - (tg + NT * q) - k * M], xsb[base - (tg + NT * q) - k * M]);
+          const float2 s = I16 ? unpack_i16x2(xs16[base - (tg + NT * q) - k * M]) : make_float2(xsa[base - (tg + NT * q) - k * M], xsb[base - (tg + NT * q) - k * M]);
           const float h0 = hreg[BTKB_SLOT(q) * MT + k];
           if constexpr (PK) v0[BTKB_SLOT(q)] = f2_fma_s(s, h0, v0[BTKB_SLOT(q)]);
           else {
@@ -274,7 +328,7 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
         }
 #pragma unroll
       for (int q = 0; q < SH; q++) {  // the D new samples of frame t+1 (tap block k = 0)
-        const float2 s = make_float2(xsa[base + D - (tg + NT * q)], xsb[base + D - (tg + NT * q)]);
+        const float2 s = I16 ? unpack_i16x2(xs16[base + D - (tg + NT * q)]) : make_float2(xsa[base + D - (tg + NT * q)], xsb[base + D - (tg + NT * q)]);
         const float h1 = hreg[BTKB_SLOT(q) * MT + 0];
         if constexpr (PK) v1[BTKB_SLOT(q)] = f2_fma_s(s, h1, v1[BTKB_SLOT(q)]);
         else {
@@ -350,9 +404,10 @@ static cudaError_t launch_analysis_r1(const AnalysisArgs& a_in, cudaStream_t st)
   AnalysisArgs a = a_in;
   using Plan = FftPlan<M>;
   constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
-  size_t smem = sizeof(float2) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * 4;
+  const bool i16 = a.x16 != nullptr;
+  size_t smem = (i16 ? sizeof(uint32_t) : sizeof(float2)) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * 4;
   if (const char* e = getenv("BTKB_ANALYSIS_SMEM_PAD")) smem += (size_t)std::max(0, atoi(e));   // occupancy experiment: unused extra shared memory per CTA
-  auto kern = analysis_packed() ? k_analysis_r1<M, MT, FR, G, true> : k_analysis_r1<M, MT, FR, G, false>;
+  auto kern = i16 ? k_analysis_r1<M, MT, FR, G, true, true> : (analysis_packed() ? k_analysis_r1<M, MT, FR, G, true> : k_analysis_r1<M, MT, FR, G, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // tiles per CTA: amortise the per-CTA set-up while keeping >= ~8 waves of CTAs for balance
@@ -383,16 +438,16 @@ static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-static int analysis_tile_frames() {  // tuning knob (frames per CTA tile): BTKB_ANALYSIS_FR=8|16 (default 16)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BTKB_ANALYSIS_FR"); v = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 12) ? 12 : 16; }
-  return v;
+static int analysis_tile_frames(bool i16) {  // tuning knob (frames per CTA tile): BTKB_ANALYSIS_FR=8|12|16; default 16 (3 CTAs/SM), 12 for 16-bit PCM
+  static int v = -1;                       // input at M = 512 (its 24 KB sample tile lets 4 CTAs share an SM: 0.496 vs 0.511 ms)
+  if (v < 0) { const char* e = getenv("BTKB_ANALYSIS_FR"); v = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 12) ? 12 : (e && atoi(e) == 16) ? 16 : 0; }
+  return v ? v : (i16 ? 12 : 16);
 }
 
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st) {
 #define BTKB_CASE(MM)                                                                  \
   case MM:                                                                             \
-    if (a.m == 4 && a.D == MM / 2) return (analysis_tile_frames() == 8) ? launch_analysis_r1<MM, 4, 8>(a, st) : (analysis_tile_frames() == 12 && MM == 512) ? launch_analysis_r1<MM, 4, (MM == 512 ? 12 : 16)>(a, st) : launch_analysis_r1<MM, 4, 16>(a, st); \
+    if (a.m == 4 && a.D == MM / 2) return (analysis_tile_frames(a.x16 != nullptr) == 8) ? launch_analysis_r1<MM, 4, 8>(a, st) : (analysis_tile_frames(a.x16 != nullptr) == 12 && MM == 512) ? launch_analysis_r1<MM, 4, (MM == 512 ? 12 : 16)>(a, st) : launch_analysis_r1<MM, 4, 16>(a, st); \
     return (a.m == 4) ? launch_analysis_m<MM, 4>(a, st) : launch_analysis_m<MM, 0>(a, st);
   switch (a.M) {
     BTKB_CASE(256) BTKB_CASE(512) BTKB_CASE(1024) BTKB_CASE(2048)

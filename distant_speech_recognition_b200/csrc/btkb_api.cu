@@ -37,7 +37,7 @@ struct btkb_pipeline {
   double *d_delays = nullptr, *d_mpos = nullptr, *d_labels = nullptr, *d_stats = nullptr;
   unsigned char* d_mask = nullptr; int* d_count = nullptr;
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
-  int16_t* d_x16 = nullptr; double* h_delays = nullptr; float2* d_tw = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
+  int16_t* d_x16 = nullptr; const int16_t* x16_cur = nullptr; int x16_stride = 0; double* h_delays = nullptr; float2* d_tw = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
   double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
   // multi-channel WPE (lazily sized at create when cfg.wpe.enabled)
   float2 *d_wS = nullptr, *d_wG = nullptr; void* d_wR = nullptr; float* d_wTH = nullptr; int* d_werr = nullptr;
@@ -478,7 +478,7 @@ static int submit_common(btkb_pipeline* p, int U, int n, const int* lengths) {
   // (weights made for another utterance count stay where they are; do_beamformer refuses to combine them with this batch, and the next
   // weight setter for this U replaces them — begin_weight_batch)
   p->U = U; p->n = n;
-  p->streaming = false; p->Y_out = p->d_Y;
+  p->streaming = false; p->Y_out = p->d_Y; p->x16_cur = nullptr;
   p->lengths.assign(U, n);
   int Tmax = 0;
   for (int u = 0; u < U; u++) {
@@ -519,6 +519,10 @@ int btkb_submit_i16(btkb_pipeline* p, const int16_t* samples, int U, int n, cons
   if (!p->d_x16) CK(cudaMalloc((void**)&p->d_x16, (size_t)p->Ucap * p->C * p->n_stride * sizeof(int16_t)));
   const size_t rows = (size_t)U * p->C;
   CK(cudaMemcpyAsync(p->d_x16, samples, rows * n * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
+  // The m = 4, r = 1 analysis kernel reads 16-bit PCM directly (rows must start on 16-byte boundaries); BTKB_ANALYSIS_I16=0 or any other
+  // filter-bank shape converts to float first (k_i16_to_f32), which gives the same snapshots bit for bit (the conversion is exact).
+  static const bool direct = [] { const char* e = getenv("BTKB_ANALYSIS_I16"); return !(e && atoi(e) == 0); }();
+  if (direct && n % 8 == 0 && p->m == 4 && p->cfg.r == 1) { p->x16_cur = p->d_x16; p->x16_stride = n; p->x_cur = p->d_x; return BTKB_OK; }
   k_i16_to_f32<<<148 * 8, 256, 0, p->stream>>>(p->d_x16, p->d_x, rows, n, p->n_stride);
   CK(cudaGetLastError());
   p->x_cur = p->d_x;
@@ -540,7 +544,7 @@ static int do_analysis(btkb_pipeline* p) {
   if (!p->have_h) return fail(BTKB_ERR_STATE, "btkb_run: set the analysis prototype first");
   if (p->U == 0) return fail(BTKB_ERR_STATE, "btkb_run: no batch submitted");
   AnalysisArgs a{p->x_cur, p->d_len, p->d_h, p->d_X, p->d_E, p->U, p->C, p->n, (p->x_cur == p->d_x) ? p->n_stride : p->n, p->T, p->M, p->m, p->D, p->laN,
-                 p->Gp, 1, p->d_tw, 1, 0, (long long)(p->laN + 1) * p->D, 0};
+                 p->Gp, 1, p->d_tw, 1, 0, (long long)(p->laN + 1) * p->D, 0, p->x16_cur, p->x16_stride};
   CK(launch_analysis(a, p->stream));
   p->launches++;
   p->have_X = true;
@@ -1195,7 +1199,7 @@ int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int*
   CK(cudaEventRecord(p->ev[0], p->stream));
   if (Tloc > 0) {
     AnalysisArgs a{xs, p->d_len, p->d_h, p->d_X, p->d_E, U, C, p->xs_hist + n, p->xs_stride, Tloc, p->M, p->m, D, p->laN, p->Gp, 1, p->d_tw, 1, 0,
-                   (long long)(p->laN + t_base + 1) * D - s_base, t_base & 1};
+                   (long long)(p->laN + t_base + 1) * D - s_base, t_base & 1, nullptr, 0};
     CK(launch_analysis(a, p->stream));
     p->launches++;
   }

@@ -30,6 +30,10 @@ struct AnalysisArgs {
   // on which frame it is paired with.  A streamed chunk that starts at an odd absolute frame number therefore starts its first tile
   // one frame early (t_skip = 1; that frame is computed and discarded), so that pairs are the whole-utterance run's pairs.
   int t_skip;
+  // 16-bit PCM input (btkb_submit_i16): rows [U][C][n16_stride] int16, n16_stride a multiple of 8.  When set, the r = 1 fast path reads it
+  // directly (k_analysis_r1<..., I16 = true>): the two channels of a pair are staged as ONE 32-bit word per sample, which halves the
+  // shared-memory wavefronts of the polyphase fold; int16 -> fp32 is exact, so the result equals the float path bit for bit.
+  const int16_t* x16; int n16_stride;
 };
 
 struct SynthesisArgs {

@@ -291,3 +291,31 @@ def test_cpp_subband_gsc_rls_golden(capi, protos):
         wl = p.get_sidelobe_weights()[0]
         assert rel_l2(wl[1:], wlo[1:]) < 1e-3, (i, rel_l2(wl[1:], wlo[1:]))
         p.close()
+
+
+@pytest.mark.parametrize("M,C", [(256, 4), (512, 8), (512, 3), (1024, 2)])
+def test_analysis_reads_16_bit_pcm_directly_and_equals_the_float_path(capi, protos, M, C):
+    """btkb_submit_i16: the m = 4, r = 1 analysis kernel stages the two channels of a pair as one packed 32-bit word per sample
+    (k_analysis_r1<..., I16>) and converts in registers; int16 -> fp32 is exact, so snapshots, subband output and time signal equal
+    those of btkb_submit with the same values as floats BIT FOR BIT — ragged lengths (not multiples of 8), an odd channel count."""
+    from distant_speech_recognition_b200 import synthetic
+    U, n = 3, 9 * 1024
+    x, d = synthetic.make_batch(U, C, n, first=1200 + M, pcm16=True)
+    x16 = x.astype(np.int16)
+    assert np.array_equal(x16.astype(np.float32), x)
+    lengths = np.array([n, n - 1237, 519], np.int32)
+    h, g = protos[M]
+    kw = dict(beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=5)) if C >= 2 else dict(beamformer=capi.BF_DS)
+    out = []
+    for mode in ("float", "i16"):
+        p = capi.Pipeline(C, M, 4, 1, max_utterances=U, max_samples=n, **kw)
+        p.set_prototypes(h, g); p.set_delays(d)
+        if mode == "float":
+            p.submit(x, lengths)
+        else:
+            p.submit_i16(x16, lengths)
+        p.run(True)
+        out.append((p.fetch_snapshots(), p.fetch_subband(), p.fetch_time()))
+        p.close()
+    for a, b in zip(*out):
+        assert a.shape == b.shape and np.abs(a).max() > 0 and np.array_equal(a.view(np.uint8), b.view(np.uint8))

@@ -17,7 +17,12 @@ def main():
     C, M, U, n = int(os.environ.get("PROF_C", 8)), int(os.environ.get("PROF_M", 512)), int(os.environ.get("PROF_U", 256)), 80000
     h, g = proto(M); x, d = tiled_batch(U, C, n, distinct)
     p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_GSC_LMS, max_utterances=U, max_samples=n)
-    p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.synchronize()
+    p.set_prototypes(h, g); p.set_delays(d)
+    if os.environ.get("PROF_I16", "0") != "0":
+        p.submit_i16(x.astype(np.int16))   # 16-bit PCM resident in HBM (PROF_I16=1); default float32, the bench's device-resident arm
+    else:
+        p.submit(x)
+    p.synchronize()
     rows = []
     for i in range(steps + 2):
         p.run(True); p.synchronize()
