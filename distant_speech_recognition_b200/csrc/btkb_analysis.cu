@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(G*(M / 8)) k_analysis_generic(AnalysisArgs a) 
     // ---- untangle the two real channels, write snapshots, channel-0 energy
     float esum = 0.f;
     if (active) {
-      const size_t rowa = ((size_t)t * a.C + ca) * a.Gp + (size_t)u * K;
-      const size_t rowb = ((size_t)t * a.C + cb) * a.Gp + (size_t)u * K;
+      const size_t rowa = ((size_t)t * a.Crow + ca) * a.Gp + (size_t)u * K;
+      const size_t rowb = ((size_t)t * a.Crow + cb) * a.Gp + (size_t)u * K;
 #pragma unroll
       for (int q = 0; q <= 4; q++) {
         int k = tg + q * NT;  // q < 4 covers 0..M/2-1 ; q == 4 only for k == M/2
@@ -361,8 +361,8 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
         const float2 A = PK ? f2_scale(f2_add_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 B = PK ? f2_scale_mi(f2_sub_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
         if (PK || !(a.debug & 1)) {
-        a.X[((size_t)ta * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
-        if (has_b) a.X[((size_t)ta * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
+        a.X[((size_t)ta * a.Crow + ca) * a.Gp + (size_t)u * K + k] = A;
+        if (has_b) a.X[((size_t)ta * a.Crow + cb) * a.Gp + (size_t)u * K + k] = B;
         }
         e0 = fmaf(wgt, fmaf(A.x, A.x, A.y * A.y), e0);
       }
@@ -372,8 +372,8 @@ __global__ void __launch_bounds__(G*(M / 8), (FR <= 12 ? 4 : 3)) k_analysis_r1(A
         const float2 A = PK ? f2_scale(f2_add_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
         const float2 B = PK ? f2_scale_mi(f2_sub_conj(zk, zm), 0.5f) : make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
         if (PK || !(a.debug & 1)) {
-        a.X[((size_t)tb * a.C + ca) * a.Gp + (size_t)u * K + k] = A;
-        if (has_b) a.X[((size_t)tb * a.C + cb) * a.Gp + (size_t)u * K + k] = B;
+        a.X[((size_t)tb * a.Crow + ca) * a.Gp + (size_t)u * K + k] = A;
+        if (has_b) a.X[((size_t)tb * a.Crow + cb) * a.Gp + (size_t)u * K + k] = B;
         }
         e1 = fmaf(wgt, fmaf(A.x, A.x, A.y * A.y), e1);
       }

@@ -24,7 +24,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct btkb_pipeline {
   btkb_config cfg;
-  int C, M, K, D, R, m, laN, pdA, pdS;
+  int C, Cp, M, K, D, R, m, laN, pdA, pdS;   // Cp: channel rows of the device arrays (C, or C padded with zero channels to 16 / 32 / 64 for a wide array)
   int Ucap, ncap, n_stride, Tcap, Gpcap;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -138,6 +138,8 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   if (cfg->beamformer == BTKB_BF_GSC_RLS_CPP && (C < 2 || C > 8 || cfg->postfilter != BTKB_PF_NONE))
     return fail(BTKB_ERR_INVALID, "btkb_create: the C++ SubbandGSCRLS kernel is built for 2..8 channels without a fused post-filter");
   if (cfg->postfilter < BTKB_PF_NONE || cfg->postfilter > BTKB_PF_LEFKIMMIATIS) return fail(BTKB_ERR_INVALID, "btkb_create: unknown post-filter kind");
+  if (cfg->beamformer == BTKB_BF_MVDR && C > 8 && !(C == 16 || C == 32 || C == 64))
+    return fail(BTKB_ERR_INVALID, "btkb_create: MVDR on a wide array is built for 16, 32 or 64 channels (other wide counts run delay-and-sum / GSC / NLMS on zero-padded channel rows)");
   if (cfg->postfilter >= BTKB_PF_MCCOWAN && (C < 2 || C > 8))
     return fail(BTKB_ERR_INVALID, "btkb_create: the McCowan / Lefkimmiatis post-filters are built for 2..8 channels");
   if (cfg->beamformer == BTKB_BF_GSC_RLS && cfg->postfilter != BTKB_PF_NONE)
@@ -147,7 +149,7 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   if (cfg->beamformer == BTKB_BF_GSC_LMS && cfg->postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_create: the reference wires no post-filter behind SubbandGSCLMSBeamformer");
   if (cfg->wpe.enabled) {
-    if (!(C == 1 || C == 2 || C == 4 || C == 8)) return fail(BTKB_ERR_INVALID, "btkb_create: WPE is built for 1, 2, 4 or 8 channels");
+    if (C < 1 || C > 8) return fail(BTKB_ERR_INVALID, "btkb_create: WPE is built for 1..8 channels");
     if (cfg->wpe.lower_num < 0 || cfg->wpe.upper_num < cfg->wpe.lower_num || cfg->wpe.iterations_num < 0)
       return fail(BTKB_ERR_INVALID, "btkb_create: bad WPE lag range / iteration count");
     if (cfg->wpe.band_width > cfg->samplerate / 2.0)  // dereverberation.cc:369-370
@@ -156,7 +158,7 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   CK(cudaSetDevice(cfg->device));
   btkb_pipeline* p = new btkb_pipeline();
   p->cfg = *cfg;
-  p->C = C; p->M = M; p->K = M / 2 + 1; p->m = cfg->m; p->R = 1 << cfg->r; p->D = M >> cfg->r;
+  p->C = C; p->Cp = (C <= 8) ? C : (C <= 16 ? 16 : (C <= 32 ? 32 : 64)); p->M = M; p->K = M / 2 + 1; p->m = cfg->m; p->R = 1 << cfg->r; p->D = M >> cfg->r;
   fb_delays(cfg->m, cfg->r, cfg->delay_compensation_type, false, &p->pdA, &p->laN);
   int la_dummy; fb_delays(cfg->m, cfg->r, cfg->delay_compensation_type, true, &p->pdS, &la_dummy);
   p->Ucap = cfg->max_utterances; p->ncap = cfg->max_samples; p->n_stride = round_up(cfg->max_samples, 4);
@@ -171,14 +173,15 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   A((void**)&p->d_len, U * sizeof(int));
   A((void**)&p->d_h, (size_t)p->m * M * sizeof(float));
   A((void**)&p->d_g, (size_t)p->m * M * sizeof(float));
-  A((void**)&p->d_X, T * C * G * sizeof(float2));
+  const size_t Cp = (size_t)p->Cp;
+  A((void**)&p->d_X, T * Cp * G * sizeof(float2));
   p->Hy = p->m * p->R + 1;   // rows of Y history in front of a streamed chunk: a block reaches back m R - 1 frames, +1 for the block held back, +1 for the pair-aligned tile origin
   A((void**)&p->d_Y, (T + p->Hy) * G * sizeof(float2));
-  A((void**)&p->d_W, (size_t)C * G * sizeof(float2));
-  A((void**)&p->d_TA, (size_t)C * G * sizeof(float2));
-  A((void**)&p->d_WL, (size_t)C * G * sizeof(float2));
-  A((void**)&p->d_WA, (size_t)C * G * sizeof(float2));
-  A((void**)&p->d_UA, (size_t)C * G * sizeof(float2));
+  A((void**)&p->d_W, Cp * G * sizeof(float2));
+  A((void**)&p->d_TA, Cp * G * sizeof(float2));
+  A((void**)&p->d_WL, Cp * G * sizeof(float2));
+  A((void**)&p->d_WA, Cp * G * sizeof(float2));
+  A((void**)&p->d_UA, Cp * G * sizeof(float2));
   if (cfg->beamformer == BTKB_BF_MVDR) A((void**)&p->d_R, (size_t)C * C * G * sizeof(float2));
   A((void**)&p->d_E, T * U * sizeof(float));
   A((void**)&p->d_time, U * (T * p->D) * sizeof(float));
@@ -211,6 +214,10 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
     A((void**)&p->d_wG, (size_t)p->Ucap * p->K * C * p->wpe_L * sizeof(float2));
     A((void**)&p->d_wR, wpe_workspace_bytes(C, p->wpe_L, p->wpe_Lr, p->wpe_chunk, cfg->wpe.fp32_normal_equations));
     A((void**)&p->d_werr, sizeof(int));
+  }
+  if (e == cudaSuccess && p->Cp != C) {   // the padded channel rows stay zero for the life of the pipeline: no kernel writes them
+    e = cudaMemset(p->d_X, 0, T * Cp * G * sizeof(float2));
+    for (float2* q : {p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA}) if (e == cudaSuccess) e = cudaMemset(q, 0, Cp * G * sizeof(float2));
   }
   if (e != cudaSuccess) {
     std::string msg = std::string("btkb_create: allocation failed: ") + cudaGetErrorString(e);
@@ -544,7 +551,7 @@ static int do_analysis(btkb_pipeline* p) {
   if (!p->have_h) return fail(BTKB_ERR_STATE, "btkb_run: set the analysis prototype first");
   if (p->U == 0) return fail(BTKB_ERR_STATE, "btkb_run: no batch submitted");
   AnalysisArgs a{p->x_cur, p->d_len, p->d_h, p->d_X, p->d_E, p->U, p->C, p->n, (p->x_cur == p->d_x) ? p->n_stride : p->n, p->T, p->M, p->m, p->D, p->laN,
-                 p->Gp, 1, p->d_tw, 1, 0, (long long)(p->laN + 1) * p->D, 0, p->x16_cur, p->x16_stride};
+                 p->Gp, 1, p->d_tw, 1, 0, (long long)(p->laN + 1) * p->D, 0, p->x16_cur, p->x16_stride, p->Cp};
   CK(launch_analysis(a, p->stream));
   p->launches++;
   p->have_X = true;
@@ -558,7 +565,7 @@ static PerBinArgs perbin_args(btkb_pipeline* p) {
   a.WL = p->have_wl ? p->d_WL : nullptr;
   a.Y = p->Y_out; a.PFW = p->d_PFW; a.UA = p->d_UA; a.stats_updates = p->d_upd;
   a.R = p->d_R; a.noise_mask = p->d_mask; a.noise_count = p->d_count;
-  a.U = p->U; a.C = p->C; a.T = p->T; a.M = p->M; a.K = p->K; a.G = p->U * p->K; a.Gp = p->Gp; a.D = p->D; a.laN = p->laN; a.pdA = p->pdA;
+  a.U = p->U; a.C = p->Cp; a.Ctrue = p->C; a.T = p->T; a.M = p->M; a.K = p->K; a.G = p->U * p->K; a.Gp = p->Gp; a.D = p->D; a.laN = p->laN; a.pdA = p->pdA;
   a.kind = p->cfg.beamformer; a.normalize_weight = p->cfg.normalize_weight; a.pf_kind = p->cfg.postfilter; a.pf_alpha = p->cfg.pf_alpha; a.pf_type = p->cfg.pf_type; a.pf_min_frames = p->cfg.pf_min_frames;
   const btkb_lms_params& l = p->cfg.lms;
   a.lms = LmsArgs{l.beta, l.gamma, l.init_diagonal_load, l.regularization_param, l.energy_floor, l.sil_thresh, l.max_wa_l2norm, l.min_frames, l.slowdown_after};
@@ -602,9 +609,9 @@ static int do_beamformer(btkb_pipeline* p) {
     return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                                          // beamformer.cc:1098-1100
   }
   if (p->wU != p->U) return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: weights were set for a different number of utterances");
-  const bool narrow = (p->C >= 1 && p->C <= 8), wide = (p->C == 16 || p->C == 32 || p->C == 64);
-  if (!narrow && !wide)
-    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the per-bin kernel is instantiated for 1..8 (register path) and 16, 32, 64 (lane-split path) channels (got " + std::to_string(p->C) + ")");
+  const bool narrow = (p->C >= 1 && p->C <= 8), wide = !narrow;   // wide arrays run the lane-split kernel on 16 / 32 / 64 channel rows (zero-padded)
+  if (wide && p->Cp != p->C && p->cfg.beamformer == BTKB_BF_MVDR)
+    return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: MVDR on a wide array needs 16, 32 or 64 channels (a zero-padded covariance is singular); got " + std::to_string(p->C));
   if (wide && p->cfg.postfilter != BTKB_PF_NONE)
     return fail(BTKB_ERR_INVALID, "btkb_run_beamformer: the post-filters are built for <= 8 channels (their C(C-1)/2 cross-spectral densities must fit the register file)");
   PerBinArgs a = perbin_args(p);
@@ -661,6 +668,7 @@ int btkb_accumulate_covariance(btkb_pipeline* p, const double* labels, float ene
   if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
   if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_accumulate_covariance: run the analysis first");
   if (!p->d_R) return fail(BTKB_ERR_STATE, "btkb_accumulate_covariance: pipeline was not created with BTKB_BF_MVDR");
+  if (p->Cp != p->C) return fail(BTKB_ERR_INVALID, "btkb_accumulate_covariance: wide arrays need 16, 32 or 64 channels");
   CK(cudaSetDevice(p->cfg.device));
   if (labels) {
     CK(cudaMemcpyAsync(p->d_labels, labels, (size_t)p->U * 2 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
@@ -690,7 +698,7 @@ static int ensure_scratch(btkb_pipeline* p, size_t bytes);
 static int sos_check(btkb_pipeline* p, const char* who, bool need_X) {
   if (!p) return fail(BTKB_ERR_INVALID, std::string(who) + ": null pipeline");
   if (p->cfg.beamformer != BTKB_BF_DS) return fail(BTKB_ERR_STATE, std::string(who) + ": the SOS beamformers apply their weights like SubbandDS; create the pipeline with BTKB_BF_DS");
-  if (!(p->C == 2 || p->C == 4 || p->C == 8)) return fail(BTKB_ERR_INVALID, std::string(who) + ": built for 2, 4 or 8 channels");
+  if (p->C < 2 || p->C > 8) return fail(BTKB_ERR_INVALID, std::string(who) + ": built for 2..8 channels");
   if (need_X && !p->have_X) return fail(BTKB_ERR_STATE, std::string(who) + ": run the analysis first");
   if (need_X && p->have_sos && p->sos_U != p->U)
     return fail(BTKB_ERR_INVALID, std::string(who) + ": statistics were accumulated for " + std::to_string(p->sos_U) + " utterances, this batch has " +
@@ -825,6 +833,7 @@ int btkb_sos_get_stats(btkb_pipeline* p, double* Rt, double* Rn, double* counts)
 int btkb_spectral_matrix_update(btkb_pipeline* p, float mu, int legacy_noconj) {
   if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
   if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_spectral_matrix_update: run the analysis first");
+  if (p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_spectral_matrix_update: built for <= 8 channels");
   CK(cudaSetDevice(p->cfg.device));
   if (!p->d_R) CK(cudaMalloc((void**)&p->d_R, (size_t)p->C * p->C * p->Gpcap * sizeof(float2)));
   PerBinArgs a = perbin_args(p);
@@ -963,13 +972,13 @@ static int ensure_scratch(btkb_pipeline* p, size_t bytes) {
 }
 
 // device [T][rows][Gp] complex -> packed [U][T][rows][K]
-__global__ void k_gather(const float2* src, float2* dst, int U, int T, int rows, int K, int Gp) {
+__global__ void k_gather(const float2* src, float2* dst, int U, int T, int rows, int K, int Gp, int row_pitch) {   // row_pitch >= rows: rows per frame in src
   const size_t total = (size_t)U * T * rows * K;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int k = (int)(i % K); size_t r = i / K;
     int c = (int)(r % rows); r /= rows;
     int t = (int)(r % T); int u = (int)(r / T);
-    dst[i] = src[((size_t)t * rows + c) * Gp + (size_t)u * K + k];
+    dst[i] = src[((size_t)t * row_pitch + c) * Gp + (size_t)u * K + k];
   }
 }
 __global__ void k_gather_f(const float* src, float* dst, int U, int T, int K, int Gp) {
@@ -987,7 +996,7 @@ int btkb_fetch_subband(btkb_pipeline* p, float* out) {
   CK(cudaSetDevice(p->cfg.device));
   const size_t bytes = (size_t)p->U * p->T * p->K * sizeof(float2);
   int rc = ensure_scratch(p, bytes); if (rc) return rc;
-  k_gather<<<2048, 256, 0, p->stream>>>(p->Y_out, (float2*)p->d_scratch, p->U, p->T, 1, p->K, p->Gp);
+  k_gather<<<2048, 256, 0, p->stream>>>(p->Y_out, (float2*)p->d_scratch, p->U, p->T, 1, p->K, p->Gp, 1);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
@@ -1000,7 +1009,7 @@ int btkb_fetch_snapshots(btkb_pipeline* p, float* out) {
   CK(cudaSetDevice(p->cfg.device));
   const size_t bytes = (size_t)p->U * p->T * p->C * p->K * sizeof(float2);
   int rc = ensure_scratch(p, bytes); if (rc) return rc;
-  k_gather<<<2048, 256, 0, p->stream>>>(p->d_X, (float2*)p->d_scratch, p->U, p->T, p->C, p->K, p->Gp);
+  k_gather<<<2048, 256, 0, p->stream>>>(p->d_X, (float2*)p->d_scratch, p->U, p->T, p->C, p->K, p->Gp, p->Cp);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, p->d_scratch, bytes, cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
@@ -1199,7 +1208,7 @@ int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int*
   CK(cudaEventRecord(p->ev[0], p->stream));
   if (Tloc > 0) {
     AnalysisArgs a{xs, p->d_len, p->d_h, p->d_X, p->d_E, U, C, p->xs_hist + n, p->xs_stride, Tloc, p->M, p->m, D, p->laN, p->Gp, 1, p->d_tw, 1, 0,
-                   (long long)(p->laN + t_base + 1) * D - s_base, t_base & 1, nullptr, 0};
+                   (long long)(p->laN + t_base + 1) * D - s_base, t_base & 1, nullptr, 0, p->Cp};
     CK(launch_analysis(a, p->stream));
     p->launches++;
   }

@@ -34,6 +34,7 @@ struct AnalysisArgs {
   // directly (k_analysis_r1<..., I16 = true>): the two channels of a pair are staged as ONE 32-bit word per sample, which halves the
   // shared-memory wavefronts of the polyphase fold; int16 -> fp32 is exact, so the result equals the float path bit for bit.
   const int16_t* x16; int n16_stride;
+  int Crow;   // channel rows per frame of X (>= C: wide arrays are padded with all-zero channels to 16 / 32 / 64 rows, btkb_api.cu)
 };
 
 struct SynthesisArgs {
@@ -90,6 +91,7 @@ struct PerBinArgs {
   // numbers: first frame, min_frames, step-size halving, the post-filters' first two frames), tu[u] = absolute frames of utterance u
   // so far, ST = carried per-chain state [ST_ROWS][Gp] (always stored when non-null, loaded when st_load; u rides in UA).
   int t_base; const int* tu; float* ST; int st_load;
+  int Ctrue;  // microphones really present (C counts the zero-padded channel rows of a wide array; the projector step scales by Ctrue)
 };
 constexpr int ST_ROWS = 72;   // 8 scalars + the largest state: RLS at C = 8 (8 + 56) / Zelinski at C = 8 (56 + 8)
 

@@ -220,7 +220,11 @@ cudaError_t launch_sos_accumulate(const SosArgs& a, cudaStream_t st, int* launch
   if (e != cudaSuccess) return e;
   switch (a.C) {
     case 2: e = launch_cov_c<2>(a, st); break;
+    case 3: e = launch_cov_c<3>(a, st); break;
     case 4: e = launch_cov_c<4>(a, st); break;
+    case 5: e = launch_cov_c<5>(a, st); break;
+    case 6: e = launch_cov_c<6>(a, st); break;
+    case 7: e = launch_cov_c<7>(a, st); break;
     case 8: e = launch_cov_c<8>(a, st); break;
     default: return cudaErrorInvalidValue;
   }
@@ -233,7 +237,11 @@ cudaError_t launch_sos_solve(const SosArgs& a, int kind, double gamma, int ref_m
   const int bs = 64, gs = (a.G + bs - 1) / bs;
   switch (a.C) {
     case 2: k_sos_solve<2><<<gs, bs, 0, st>>>(a, kind, gamma, ref_micx, offset); break;
+    case 3: k_sos_solve<3><<<gs, bs, 0, st>>>(a, kind, gamma, ref_micx, offset); break;
     case 4: k_sos_solve<4><<<gs, bs, 0, st>>>(a, kind, gamma, ref_micx, offset); break;
+    case 5: k_sos_solve<5><<<gs, bs, 0, st>>>(a, kind, gamma, ref_micx, offset); break;
+    case 6: k_sos_solve<6><<<gs, bs, 0, st>>>(a, kind, gamma, ref_micx, offset); break;
+    case 7: k_sos_solve<7><<<gs, bs, 0, st>>>(a, kind, gamma, ref_micx, offset); break;
     case 8: k_sos_solve<8><<<gs, bs, 0, st>>>(a, kind, gamma, ref_micx, offset); break;
     default: return cudaErrorInvalidValue;
   }

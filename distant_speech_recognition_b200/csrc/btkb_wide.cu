@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ C
 #pragma unroll
     for (int i = 0; i < 8; i++) nrm = fmaf(w[i].x, w[i].x, fmaf(w[i].y, w[i].y, nrm));
     nrm = red<L>(nrm, gm);
-    const float sc = 1.0f / (sqrtf(nrm) * (float)C);
+    const float sc = 1.0f / (sqrtf(nrm) * (float)a.Ctrue);   // (zero-padded channel rows do not count, see PerBinArgs::Ctrue)
 #pragma unroll
     for (int i = 0; i < 8; i++) { w[i].x *= sc; w[i].y *= sc; }
   }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TC* L) k_perbin_wide(const __grid_constant__ C
         ux = red2<L>(ux, gm);
         const float2 epa = csub(y, ux);
         const float alphaK = gamma / sub;
-        const float2 cy = make_float2((float)C * y.x, (float)C * y.y);
+        const float2 cy = make_float2((float)a.Ctrue * y.x, (float)a.Ctrue * y.y);
         const float2 ea = make_float2(epa.x * alphaK, epa.y * alphaK);
         const float keep = (a.lms.regularization_param > 0.f) ? 1.0f - alphaK * a.lms.regularization_param : 1.0f;
         float n2 = 0.f;

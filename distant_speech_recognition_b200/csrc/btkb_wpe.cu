@@ -405,7 +405,11 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
   switch (C) {
     case 1: corr = k_wpe_corr<1, RT>; break;
     case 2: corr = k_wpe_corr<2, RT>; break;
+    case 3: corr = k_wpe_corr<3, RT>; break;
     case 4: corr = k_wpe_corr<4, RT>; break;
+    case 5: corr = k_wpe_corr<5, RT>; break;
+    case 6: corr = k_wpe_corr<6, RT>; break;
+    case 7: corr = k_wpe_corr<7, RT>; break;
     case 8: corr = k_wpe_corr<8, RT>; break;
     default: return cudaErrorInvalidValue;
   }
@@ -433,7 +437,7 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
 
 cudaError_t launch_wpe(const WpeArgs& a, int chunk, int fp32, cudaStream_t st, int* launches) {
   if (a.T <= 0 || a.G <= 0) return cudaSuccess;
-  if (!(a.C == 1 || a.C == 2 || a.C == 4 || a.C == 8)) return cudaErrorInvalidValue;
+  if (a.C < 1 || a.C > 8) return cudaErrorInvalidValue;
   return fp32 ? launch_wpe_t<float>(a, chunk, st, launches) : launch_wpe_t<double>(a, chunk, st, launches);
 }
 

@@ -59,9 +59,9 @@ def test_kernels_are_sm100a_with_tma(lib):
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4btkb8k_perbinILi8ELi1ELi0ELb0EEEv14CUtensorMap_stNS_10PerBinArgsE", LIB], capture_output=True, text=True).stdout
     assert "UTMALDG" in sass and "SYNCS" in sass
-    assert "FFMA2" not in sass          # the default kernel is the scalar one that was measured on B200 ...
+    assert "FFMA2" not in sass          # the scalar variant (BTKB_PERBIN_PACKED=0) has no packed instructions ...
     for fun in ("_ZN4btkb8k_perbinILi8ELi1ELi0ELb1EEEv14CUtensorMap_stNS_10PerBinArgsE", "_ZN4btkb12k_perbin_rlsILi8ELb1EEEv14CUtensorMap_stNS_10PerBinArgsE",
-                "_ZN4btkb13k_analysis_r1ILi512ELi4ELi16ELi2ELb1EEEvNS_12AnalysisArgsE",
+                "_ZN4btkb13k_analysis_r1ILi512ELi4ELi16ELi2ELb1ELb0EEEvNS_12AnalysisArgsE", "_ZN4btkb13k_analysis_r1ILi512ELi4ELi12ELi2ELb1ELb1EEEvNS_12AnalysisArgsE",
                 "_ZN4btkb16k_synthesis_fastILi512ELi16ELi2ELi4ELi2ELb1EEEvNS_13SynthesisArgsE"):
         sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, LIB], capture_output=True, text=True).stdout
-        assert "FFMA2" in sass and "F32x2.LO_HI" in sass, fun    # ... and the packed variants really are packed (csrc/btkb_f2.cuh)
+        assert "FFMA2" in sass and "F32x2.LO_HI" in sass, fun    # ... and the packed variants (the defaults, incl. the 16-bit PCM analysis kernel) really are packed (csrc/btkb_f2.cuh)

@@ -319,3 +319,71 @@ def test_analysis_reads_16_bit_pcm_directly_and_equals_the_float_path(capi, prot
         p.close()
     for a, b in zip(*out):
         assert a.shape == b.shape and np.abs(a).max() > 0 and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+@pytest.mark.parametrize("C", [3, 6])
+def test_arbitrary_channel_counts_wpe_and_sos(capi, protos, C):
+    """The batch-statistics paths for channel counts other than 2 / 4 / 8: multi-channel WPE (dereverberation.cc:312-733) in front of
+    delay-and-sum, and the blind-MVDR / GEV beamformers from a VAD label (pybeamformer.py:1026-1357), against the fp64 restatement."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, n, K = 256, 8000, 129
+    h, g = protos[M]
+    x, d = synthetic.make_batch(1, C, n, first=1500 + C)
+    X = np.stack([restate.analysis(x[0, c], h, M, 4, 1) for c in range(C)], axis=1)
+    wpe = dict(lower_num=0, upper_num=6, iterations_num=2, load_db=-18.0, band_width=0.0, diagonal_bias=1e-4)
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_DS, max_utterances=1, max_samples=n, wpe=wpe)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.run(True)
+    Xd = restate.wpe(X, **wpe)[0]
+    assert rel_l2(p.fetch_snapshots()[0], Xd[:, :, :K]) < TOL
+    Yo = restate.subband_ds(Xd, restate.calc_mainlobe(M, C, FS, d[0]))
+    assert rel_l2(p.fetch_subband()[0], Yo[:, :K]) < TOL
+    p.close()
+    labels = np.array([[[0.1, 0.3]]])
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_DS, max_utterances=1, max_samples=n)
+    p.set_prototypes(h, g); p.submit(x); p.run_analysis()
+    p.sos_accumulate_from_label(labels, 10.0)
+    Rt, Rn, ct, cn = restate.sos_accumulate(X, FS, M // 2, target_labs=[(0.1, 0.3)], energy_threshold=10.0)
+    for kind in (capi.SOS_BMVDR, capi.SOS_GEV):
+        p.sos_calc_weights(kind, gamma=1e-6, ref_micx=1, offset=0.0)
+        w = p.get_weights()[0]
+        wo = restate.sos_bmvdr_weights(Rt, Rn, ct, cn, gamma=1e-6, ref_micx=1, offset=0.0) if kind == capi.SOS_BMVDR else restate.sos_gev_weights(Rt, Rn, cn, gamma=1e-6)
+        sgn = 1.0 if kind == capi.SOS_BMVDR or np.real(np.vdot(wo[5], w[5])) >= 0 else -1.0      # GEV: one global sign per utterance (LAPACK-defined)
+        assert rel_l2(sgn * w, wo) < TOL, (C, kind)
+        p.run_beamformer(True)
+        assert rel_l2(sgn * p.fetch_subband()[0], restate.sos_apply(X, wo)[:, :K]) < TOL
+    p.close()
+
+
+@pytest.mark.parametrize("C", [9, 12, 20, 48])
+def test_wide_arrays_with_any_channel_count(capi, protos, C):
+    """Wide arrays whose channel count is not 16 / 32 / 64 run the lane-split kernel on zero-padded channel rows (the true count enters
+    the 1/C of the manifold and the projector step): delay-and-sum and GSC-NLMS against the fp64 restatement, ragged batch."""
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    M, U, n, K = 256, 2, 5000, 129
+    h, g = protos[M]
+    x, d = synthetic.make_batch(U, C, n, first=1700 + C)
+    lengths = np.array([n, 3777], np.int32)
+    Xo = [np.stack([restate.analysis(x[u, c, :lengths[u]], h, M, 4, 1) for c in range(C)], axis=1) for u in range(U)]
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
+    X, Y, y = p.fetch_snapshots(), p.fetch_subband(), p.fetch_time()
+    for u in range(U):
+        T = Xo[u].shape[0]
+        assert X.shape[2] == C and rel_l2(X[u, :T], Xo[u][:, :, :K]) < 2e-6
+        Yo = restate.subband_ds(Xo[u], restate.calc_mainlobe(M, C, FS, d[u]))
+        assert rel_l2(Y[u, :T], Yo[:, :K]) < TOL and rel_l2(y[u, :(T - 4) * 128], restate.synthesis(Yo, g, M, 4, 1)) < TOL
+    p.close()
+    lms = dict(min_frames=5)
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=lms, max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
+    Y, st = p.fetch_subband(), p.fetch_stats()
+    for u in range(U):
+        T = Xo[u].shape[0]
+        Yo, _, nu = restate.gsc_lms(Xo[u], FS, d[u], **lms)
+        assert rel_l2(Y[u, :T], Yo[:, :K]) < TOL, (C, u)
+        assert st[u][2] == nu
+    p.close()
+    with pytest.raises(capi.BtkbError):
+        capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=U, max_samples=n)
