@@ -927,6 +927,24 @@ int btkb_run(btkb_pipeline* p, int do_syn) {
   CK(cudaSetDevice(p->cfg.device));
   p->launches = 0;
   CK(cudaEventRecord(p->ev[0], p->stream));
+  // BTKB_FUSED=1: analysis and the per-bin NLMS recurrence in one kernel, the snapshots never reaching HBM (btkb_fused.cu; measured
+  // slower than the two kernels, DESIGN.md 10.1, hence opt-in).  Its time is reported in the "analysis" segment.
+  const bool want_fused = [] { const char* e = getenv("BTKB_FUSED"); return e && atoi(e) != 0; }();   // read at every call so that one process can compare
+  if (want_fused && !p->cfg.wpe.enabled && p->have_h && p->U > 0 && p->have_w && p->wU == p->U) {
+    AnalysisArgs fa{p->x_cur, p->d_len, p->d_h, p->d_X, p->d_E, p->U, p->C, p->n, (p->x_cur == p->d_x) ? p->n_stride : p->n, p->T, p->M, p->m, p->D, p->laN,
+                    p->Gp, 1, p->d_tw, 1, 0, (long long)(p->laN + 1) * p->D, 0, p->x16_cur, p->x16_stride, p->Cp};
+    PerBinArgs fb = perbin_args(p);
+    if (fused_supported(fa, fb)) {
+      CK(launch_fused_analysis_nlms(fa, fb, p->stream));
+      p->launches++;
+      p->have_X = false; p->have_Y = true; p->pf_applied = true; p->have_ua = true;
+      CK(cudaEventRecord(p->ev[1], p->stream));
+      CK(cudaEventRecord(p->ev[2], p->stream));
+      if (do_syn) { int rc2 = do_synthesis(p); if (rc2) return rc2; }
+      CK(cudaEventRecord(p->ev[3], p->stream));
+      return BTKB_OK;
+    }
+  }
   int rc = do_analysis(p); if (rc) return rc;
   if (p->cfg.wpe.enabled) { rc = do_wpe(p, 0, -1); if (rc) return rc; }   // counted in the "analysis" segment of btkb_last_timing; btkb_last_timing_wpe isolates it
   CK(cudaEventRecord(p->ev[1], p->stream));

@@ -138,6 +138,9 @@ struct WeightsArgs {
 };
 
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
+// analysis + per-bin NLMS in one kernel, snapshots kept on the SM (btkb_fused.cu; BTKB_FUSED=1)
+bool fused_supported(const AnalysisArgs& a, const PerBinArgs& b);
+cudaError_t launch_fused_analysis_nlms(const AnalysisArgs& a, const PerBinArgs& b, cudaStream_t st);
 cudaError_t launch_synthesis(const SynthesisArgs& a, cudaStream_t st);
 cudaError_t launch_perbin(const PerBinArgs& a, cudaStream_t st);
 cudaError_t launch_covariance(const PerBinArgs& a, cudaStream_t st);

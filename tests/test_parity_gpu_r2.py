@@ -387,3 +387,33 @@ def test_wide_arrays_with_any_channel_count(capi, protos, C):
     p.close()
     with pytest.raises(capi.BtkbError):
         capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=U, max_samples=n)
+
+
+def test_fused_analysis_nlms_equals_the_two_kernel_path(capi, protos):
+    """BTKB_FUSED=1: k_fused_analysis_nlms (analysis and the per-bin NLMS recurrence in one kernel, snapshots kept in shared memory,
+    csrc/btkb_fused.cu) against the default K1 -> HBM -> K4 path on a ragged batch: same device functions, same frame pairing, so
+    subband output, time signal, exported active weights and update counts must be IDENTICAL; and within tolerance of the oracle."""
+    import os
+    from distant_speech_recognition_b200 import synthetic
+    from oracle import restate
+    C, M, U, n = 8, 512, 5, 11000
+    h, g = protos[M]
+    x, d = synthetic.make_batch(U, C, n, first=2100)
+    lengths = np.array([n, n - 1234, 517, 8191, 1], np.int32)
+    lms = dict(min_frames=7, slowdown_after=20)
+    res = {}
+    try:
+        for tag, env in (("two_kernels", "0"), ("fused", "1")):
+            os.environ["BTKB_FUSED"] = env
+            p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=lms, max_utterances=U, max_samples=n)
+            p.set_prototypes(h, g); p.set_delays(d); p.submit(x, lengths); p.run(True)
+            res[tag] = (p.fetch_subband(), p.fetch_time(), p.get_active_weights(), p.fetch_stats()[:, 1:], p.last_timing()["launches"])
+            p.close()
+    finally:
+        os.environ.pop("BTKB_FUSED", None)
+    assert res["two_kernels"][4] == 3 and res["fused"][4] == 2                  # the fused path really ran
+    for a, b in zip(res["two_kernels"][:4], res["fused"][:4]):
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    X = np.stack([restate.analysis(x[0, c], h, M, 4, 1) for c in range(C)], axis=1)
+    Yo, _, _ = restate.gsc_lms(X, FS, d[0], **lms)
+    assert rel_l2(res["fused"][0][0], Yo[:, :257]) < TOL

@@ -12,7 +12,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 C, M, U, n = 8, 512, 256, 80000
 h, g = proto(M); x, d = tiled_batch(U, C, n, 16)
 out = {}
-for NP in (1, 2, 4, 8):
+for NP in [int(v) for v in os.environ.get("PROBE_NP", "1,2,4,8").split(",")]:
     Us = U // NP
     pipes = []
     for i in range(NP):
