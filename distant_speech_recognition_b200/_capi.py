@@ -186,6 +186,12 @@ class Pipeline:
         _check(lib.btkb_get_wpe_filter(self._h, _fp(out)))
         return out
 
+    def set_wpe_filter(self, G):
+        """G complex64 [U][K][C][C*P] as returned by get_wpe_filter (of this or another pipeline)."""
+        G = np.ascontiguousarray(G, np.complex64)
+        self.U = G.shape[0]
+        _check(lib.btkb_set_wpe_filter(self._h, ct.c_int(G.shape[0]), _fp(G)))
+
     def last_timing_wpe(self):
         ms = ct.c_float(0)
         _check(lib.btkb_last_timing_wpe(self._h, ct.byref(ms)))

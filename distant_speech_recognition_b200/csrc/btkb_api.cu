@@ -867,6 +867,17 @@ int btkb_get_wpe_filter(btkb_pipeline* p, float* out) {
   return BTKB_OK;
 }
 
+int btkb_set_wpe_filter(btkb_pipeline* p, int U, const float* G) {
+  if (!p || !G) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->cfg.wpe.enabled) return fail(BTKB_ERR_STATE, "btkb_set_wpe_filter: the pipeline was created without cfg.wpe.enabled");
+  if (U < 1 || U > p->Ucap) return fail(BTKB_ERR_INVALID, "btkb_set_wpe_filter: U out of range");
+  CK(cudaSetDevice(p->cfg.device));
+  CK(cudaMemcpyAsync(p->d_wG, G, (size_t)U * p->K * p->C * p->wpe_L * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_wpe = true; p->wpe_U = U;
+  return BTKB_OK;
+}
+
 int btkb_last_timing_wpe(btkb_pipeline* p, float* ms) {
   if (!p || !ms) return fail(BTKB_ERR_INVALID, "null argument");
   if (!p->have_wpe) return fail(BTKB_ERR_STATE, "btkb_last_timing_wpe: WPE has not run");

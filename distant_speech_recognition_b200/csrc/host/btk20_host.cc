@@ -65,9 +65,11 @@ unsigned SampleFeature::read(const std::string& fn, int /*format*/, int samplera
   for (int i = 0; i < n; i++) {
     const char* p = &data[((size_t)(cfrom + i) * nch + (chX - 1)) * bytes];
     float v;
-    if (fmt == 3 && bits == 32) { std::memcpy(&v, p, 4); if (norm == 0.0f) v *= 32768.0f; else v *= norm; }
+    // libsndfile semantics of sf_readf_float (feature.cc:265-276, 305): float files are returned as they are; integer files unscaled with
+    // SFC_SET_NORM_FLOAT off (norm == 0), scaled to [-1, 1) with it on; then samples *= norm unless norm is 0 or 1 (feature.cc:339-341)
+    if (fmt == 3 && bits == 32) { std::memcpy(&v, p, 4); if (norm != 0.0f && norm != 1.0f) v *= norm; }
     else if (bits == 16) { int16_t s; std::memcpy(&s, p, 2); v = (norm == 0.0f) ? (float)s : (float)s / 32768.0f * norm; }
-    else if (bits == 32) { int32_t s; std::memcpy(&s, p, 4); v = (norm == 0.0f) ? (float)s / 65536.0f : (float)s / 2147483648.0f * norm; }
+    else if (bits == 32) { int32_t s; std::memcpy(&s, p, 4); v = (norm == 0.0f) ? (float)s : (float)s / 2147483648.0f * norm; }
     else throw jio_error("sndfile error: unsupported sample format (%d bits).", (int)bits);
     samples_[i] = v;
   }
@@ -152,7 +154,7 @@ MultiChannelWPEDereverberation::MultiChannelWPEDereverberation(unsigned subbands
   cfg_.lower_num = lowerN; cfg_.upper_num = upperN; cfg_.iterations_num = iterationsN; cfg_.load_db = loadDb; cfg_.band_width = bandWidth;
   cfg_.diagonal_bias = diagonalBias; cfg_.samplerate = sampleRate;
   if (bandWidth > sampleRate / 2.0) throw jdimension_error("Bandwidth is greater than the Nyquist rate.\n");   // dereverberation.cc:369-370
-  if (!(channelsN == 1 || channelsN == 2 || channelsN == 4 || channelsN == 8)) throw jdimension_error("the GPU WPE is built for 1, 2, 4 or 8 channels (got %d)", channelsN);
+  if (channelsN < 1 || channelsN > 8) throw jdimension_error("the GPU WPE is built for 1..8 channels (got %d)", channelsN);
 }
 MultiChannelWPEDereverberation::~MultiChannelWPEDereverberation() { if (pipe_) btkb_destroy(pipe_); }
 void MultiChannelWPEDereverberation::set_input(const VectorComplexFeatureStreamPtr& samples) {
@@ -220,6 +222,13 @@ void MultiChannelWPEDereverberation::realize_() {
   Xd_.resize((size_t)T_ * channelsN_ * (subbandsN_ / 2 + 1));
   ck(btkb_fetch_snapshots(pipe_, reinterpret_cast<float*>(Xd_.data())));
   realized_ = true;
+}
+std::vector<float> MultiChannelWPEDereverberation::filters() const {
+  if (!estimated_ || !pipe_) throw jinitialization_error("Call MultiChannelWPEDereverberation::estimate_filter()\n");
+  const size_t P = cfg_.upper_num - cfg_.lower_num + 1;
+  std::vector<float> G((size_t)(subbandsN_ / 2 + 1) * channelsN_ * channelsN_ * P * 2);
+  ck(btkb_get_wpe_filter(pipe_, G.data()));
+  return G;
 }
 int MultiChannelWPEDereverberation::frames() {
   if (!estimated_) throw jinitialization_error("Call SingleChannelWPEDereverberationFeature::estimate_filter()\n");   // dereverberation.cc:446-447 (sic)
@@ -402,12 +411,14 @@ void SubbandBeamformer::run_graph(const PostFilterConfig& pf, const SynthesisCon
   for (unsigned c = 0; c < C; c++) std::memcpy(&x[(size_t)c * n], srcs[c]->samples().data(), sizeof(float) * n);
   ck(btkb_submit(pipe_, x.data(), 1, (int)n, nullptr));
   if (wpe_) {
-    // the dereverberation filters are estimated on the utterance being processed, over the frame range given to
-    // MultiChannelWPEDereverberation::estimate_filter (the reference could also carry filters over from other audio)
     if (!wpe_->estimated()) throw jinitialization_error("Call SingleChannelWPEDereverberationFeature::estimate_filter()\n");
     if (wpe_->channelsN() != C) throw jdimension_error("the dereverberator has %d channels, the beamformer %d", (int)wpe_->channelsN(), (int)C);
+    // the filters of the earlier estimate_filter() call are applied to the audio the sources hold NOW, whatever they were estimated on
+    // (MultiChannelWPEDereverberationFeature::next -> calc_every_channel_output, dereverberation.cc:441-497, 713-728)
     ck(btkb_run_analysis(pipe_));
-    ck(btkb_run_wpe(pipe_, wpe_->est_start(), wpe_->est_end()));
+    const std::vector<float> G = wpe_->filters();
+    ck(btkb_set_wpe_filter(pipe_, 1, G.data()));
+    ck(btkb_apply_wpe(pipe_));
     ck(btkb_run_beamformer(pipe_, syn.enabled ? 1 : 0));
   } else {
     ck(btkb_run(pipe_, syn.enabled ? 1 : 0));

@@ -181,6 +181,7 @@ class MultiChannelWPEDereverberation {
   const WpeConfig& config() const { return cfg_; }
   int est_start() const { return est_start_; }
   int est_end() const { return est_end_; }
+  std::vector<float> filters() const;                         // [K][C][C*P] complex64 prediction filters of the last estimate_filter()
  private:
   unsigned gather_(std::vector<float>& x);   // [C][n] samples of the current sources; returns n
   void realize_();

@@ -188,6 +188,10 @@ int btkb_run_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no);
 int btkb_apply_wpe(btkb_pipeline* p);
 /* prediction filters Gn_ [U][K][C][L] complex64, L = C * (upper_num - lower_num + 1), channel-major then lag (zero outside the band) */
 int btkb_get_wpe_filter(btkb_pipeline* p, float* out);
+/* hand prediction filters estimated elsewhere (another pipeline's btkb_get_wpe_filter, same shape [U][K][C][C*P] complex64) to this
+ * pipeline; btkb_apply_wpe then dereverberates with them: MultiChannelWPEDereverberationFeature streams feeding a beamformer apply the
+ * filters of the earlier estimate_filter() call, whatever audio they were estimated on (dereverberation.cc:441-497, 713-728). */
+int btkb_set_wpe_filter(btkb_pipeline* p, int U, const float* G);
 int btkb_run_beamformer(btkb_pipeline* p, int do_synthesis);
 /* inject beamformed subband frames from the host, Y [U][T][K] complex64 (the stream an arbitrary upstream
  * VectorComplexFeatureStream would deliver to OverSampledDFTSynthesisBank::next, modulated.cc:533-549), then

@@ -53,6 +53,13 @@ def test_sample_feature_reads_wav(tmp_path):
     assert n == 1000 and np.array_equal(np.array(s.data()), data.astype(np.float32))   # norm=0: raw int16-scale floats
     with pytest.raises(IOError):
         s.read(os.path.join(tmp_path, "missing.wav"), FS)
+    # 32-bit PCM: libsndfile hands the integers out unscaled when normalisation is off (norm = 0, the scripts' call), feature.cc:265-270
+    path32 = os.path.join(tmp_path, "t32.wav")
+    d32 = (np.arange(-300, 300, dtype=np.int64) * 70001).astype(np.int32)
+    with wave.open(path32, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(4); w.setframerate(FS); w.writeframes(d32.tobytes())
+    s32 = SampleFeaturePtr(block_len=256, shift_len=256, pad_zeros=True)
+    assert s32.read(path32, FS) == 600 and np.array_equal(np.array(s32.data()), d32.astype(np.float32))
 
 
 def test_constructor_checks_and_misc(protos):
@@ -535,3 +542,43 @@ def test_frontend_flow_cpp_subband_gsc_rls(protos):
             bf.set_quadratic_constraint(*qc)
         Y = np.array([np.array(v) for v in bf])
         assert Y.shape == (g["Y%d" % i].shape[0], M) and rel_l2(Y[:, :129], g["Y%d" % i]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_frontend_flow_wpe_filters_of_one_utterance_applied_to_another(protos):
+    """MultiChannelWPEDereverberationFeature streams feeding a beamformer must apply the filters of the EARLIER
+    estimate_filter() call (dereverberation.cc:441-497, 713-728), not re-estimate them on the audio being processed: estimate on
+    utterance A, re-read the sources with utterance B, run analysis -> WPE(apply) -> D&S; against the restatement's
+    wpe_estimate(A) + wpe_apply(B)."""
+    from oracle import restate
+    from distant_speech_recognition_b200 import synthetic
+    from distant_speech_recognition_b200.btk20.dereverberation import MultiChannelWPEDereverberationPtr, MultiChannelWPEDereverberationFeaturePtr
+    M, D, C, n = 256, 128, 3, 6000
+    h, gg = protos[M]
+    xa, d, _, _ = synthetic.make_utterance(71, C, n)
+    xb = synthetic.make_utterance(72, C, n)[0]
+    wpe = dict(lower_num=1, upper_num=5, iterations_num=2, load_db=-25.0, band_width=0.0, diagonal_bias=1e-4)
+    sfs, afbs = [], []
+    for c in range(C):
+        sf = SampleFeaturePtr(block_len=D, shift_len=D, pad_zeros=True); sf.setSamples(xa[c].astype(np.float64), FS)
+        sfs.append(sf); afbs.append(OverSampledDFTAnalysisBankPtr(sf, prototype=h, M=M, m=4, r=1, delay_compensation_type=2))
+    pre = MultiChannelWPEDereverberationPtr(subbands_num=M, channels_num=C, samplerate=FS, **wpe)
+    for a_ in afbs:
+        pre.set_input(a_)
+    pre.estimate_filter()
+    for c in range(C):
+        sfs[c].setSamples(xb[c].astype(np.float64), FS)          # new audio behind the same graph
+    feats = [MultiChannelWPEDereverberationFeaturePtr(pre, channel_no=c) for c in range(C)]
+    ds = SubbandDSPtr(fftlen=M, half_band_shift=False)
+    for f_ in feats:
+        ds.set_channel(f_)
+    ds.calc_array_manifold_vectors(FS, d)
+    Y = np.array([np.array(v) for v in ds])
+    XA = np.stack([restate.analysis(xa[c], h, M, 4, 1) for c in range(C)], axis=1)
+    XB = np.stack([restate.analysis(xb[c], h, M, 4, 1) for c in range(C)], axis=1)
+    G = restate.wpe_estimate(XA, wpe["lower_num"], wpe["upper_num"], wpe["iterations_num"], wpe["load_db"], wpe["band_width"], wpe["diagonal_bias"], FS)
+    XBd = restate.wpe_apply(XB, G, wpe["lower_num"], wpe["upper_num"], wpe["band_width"], FS)
+    Yo = restate.subband_ds(XBd, restate.calc_mainlobe(M, C, FS, d))
+    assert rel_l2(Y[:, :129], Yo[:, :129]) < 1e-4
+    Yre = restate.subband_ds(restate.wpe(XB, samplerate=FS, **wpe)[0], restate.calc_mainlobe(M, C, FS, d))
+    assert rel_l2(Yre[:, :129], Yo[:, :129]) > 1e-3               # re-estimating on B would be visibly different
