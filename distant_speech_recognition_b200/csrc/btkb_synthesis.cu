@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
       }
     fft_first_pass<M, -1, PK>(v0, buf0, tg);
     fft_first_pass<M, -1, PK>(v1, buf1, tg);
-    __syncthreads();   // also: every thread of every group has consumed its Y rows
+    group_sync<NT, G>(grp);   // also: every thread of the group has consumed the Y rows of its quad (only this group reads and rewrites them)
     if constexpr (PK) {
-      auto sync = [] { __syncthreads(); };
+      auto sync = [grp] { group_sync<NT, G>(grp); };
       FftPassChain<M, -1, 0, decltype(sync), PK>::run(v0, v1, buf0, buf1, tg, tw, sync);
       // v[r] = natural-order element tg + r M/8 of the two transforms (all eight still in registers): real parts to row a/c,
       // imaginary parts to row b/d
@@ -243,14 +243,14 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
           wa[i] = v0[r].x; wb[i] = v0[r].y; wc[i] = v1[r].x; wd[i] = v1[r].y;
         }
       }
-      __syncthreads();   // the rows are read by every thread of the CTA in the polyphase stage / the next quad's first pass reuses the buffers
+      group_sync<NT, G>(grp);   // the next quad's first pass reuses the group's buffers (the polyphase stage waits at the CTA barrier below)
     } else {
       int Ns = R0;
 #pragma unroll
       for (int p = 0; p < P; p++) {
 #pragma unroll
         for (int r = 0; r < 8; r++) { v0[r] = buf0[pidx(tg + r * (M / 8))]; v1[r] = buf1[pidx(tg + r * (M / 8))]; }
-        __syncthreads();
+        group_sync<NT, G>(grp);
 #pragma unroll
         for (int r = 1; r < 8; r++) { v0[r] = cmul(v0[r], tw.tw[p][r - 1]); v1[r] = cmul(v1[r], tw.tw[p][r - 1]); }
         dft8<-1>(v0);
@@ -270,11 +270,12 @@ __global__ void __launch_bounds__(G*(M / 8)) k_synthesis_fast(SynthesisArgs a) {
           stockham_store<8>(buf0, v0, tg, Ns);
           stockham_store<8>(buf1, v1, tg, Ns);
         }
-        __syncthreads();
+        group_sync<NT, G>(grp);
         Ns *= 8;
       }
     }
   }
+  __syncthreads();   // every group's v rows are in place: the polyphase stage reads all of them
 
   // ---- polyphase + overlap-add (taps in registers).  Output block tl of position d needs v rows tl + s2 + RR q (q < MT) at column
   // d + s2 D: consecutive blocks slide that window by ONE row, so the rows a position has read stay in registers (the block loop
