@@ -27,6 +27,42 @@ def timed(fn, steps=5, warm=2):
     return (time.perf_counter() - t0) / steps
 
 
+def _rel(a, b):
+    return float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / max(np.linalg.norm(np.asarray(b).ravel()), 1e-300))
+
+
+def parity_and_cpu(p, x, d, M, kind, picks, labels=None):
+    """Parity at benchmark size: the utterances `picks` of the batch the pipeline has just processed against the fp64 restatement
+    (oracle/restate.py), and the reference's own C++ (oracle/_ref) timed on ONE host core for the first of them (cpu_baseline)."""
+    import time as _t
+    from oracle import restate, ref
+    h, g = proto(M)
+    C = x.shape[1]; K = M // 2 + 1; FS = 16000.0
+    Y = p.fetch_subband(); y = p.fetch_time()
+    es, et = 0.0, 0.0
+    for u in picks:
+        X = np.stack([restate.analysis(x[u, c], h, M, 4, 1) for c in range(C)], axis=1)
+        wq = restate.calc_mainlobe(M, C, FS, d[u])
+        if kind == "ds":
+            Yo = restate.subband_ds(X, wq)
+        elif kind == "smimvdr_zelinski":
+            R, _ = restate.smi_covariance(X, FS, M // 2, (tuple(labels[u]),), 10.0)
+            w = restate.calc_mvdr_weights(R + float(np.float32(1e-4)) * np.eye(C), wq, single=False)
+            Yo, _ = restate.zelinski_postfilter(restate.subband_mvdr(X, w), X, wq, 0.7, 2, 0)
+        else:
+            Yo, _, _ = restate.gsc_lms(X, FS, d[u])
+        yo = restate.synthesis(Yo, g, M, 4, 1)
+        T = X.shape[0]
+        es = max(es, _rel(Y[u, :T], Yo[:, :K])); et = max(et, _rel(y[u, :len(yo)], yo))
+    u = picks[0]
+    bf = {"ds": ref.BF_DS, "smimvdr_zelinski": ref.BF_SMI_MVDR, "gsclms": ref.BF_GSC_LMS}[kind]
+    kw = dict(pf=dict(kind="zelinski", alpha=0.7, type=2), smi_label=tuple(labels[u]), mvdr_mu=1e-4) if kind == "smimvdr_zelinski" else {}
+    t0 = _t.perf_counter(); r = ref.beamform(x[u], h, g, d[u], M, 4, 1, bf_kind=bf, do_synthesis=True, want_subband=False, **kw); cpu = _t.perf_counter() - t0
+    return {"parity_check": {"utterances": list(picks), "rel_l2_subband": es, "rel_l2_time": et, "tolerance": 1e-4, "oracle": "oracle/restate.py (fp64)", "pass": bool(max(es, et) < 1e-4)},
+            "cpu_baseline": {"kind": "reference", "cores": 1, "value": float(r["stats"][1]) / cpu, "unit": "frames/s",
+                             "sample": "utterance %d of the batch through the compiled reference (oracle/_ref), %.1f s on one host core" % (u, cpu)}}
+
+
 def main():
     out = {}
     # configs[0]: 2-mic D&S, M=256, one 10 s utterance
@@ -35,7 +71,7 @@ def main():
     p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_DS, max_utterances=U, max_samples=n); p.set_prototypes(h, g); p.set_delays(d); p.submit(x)
     def f0(): p.run(True); p.synchronize()
     s = timed(f0); T = p.num_frames
-    out["configs[0] 2-mic SubbandDS M=256 1x10s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels=p.last_timing())
+    out["configs[0] 2-mic SubbandDS M=256 1x10s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels=p.last_timing(), **parity_and_cpu(p, x, d, M, "ds", [0]))
     p.close()
     # configs[2]: 8-mic SMI-MVDR + Zelinski, M=512, 1000 utterances
     C, M, U, n = 8, 512, 1000, 80000
@@ -46,7 +82,8 @@ def main():
     def f2():
         p.run_analysis(); p.accumulate_covariance(labels, 10.0); p.calc_mvdr_weights(1e-4); p.run_beamformer(True); p.synchronize()
     s = timed(f2, steps=3, warm=1); T = p.num_frames
-    out["configs[2] 8-mic SMI-MVDR+Zelinski M=512 1000x5s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels_last_call=p.last_timing())
+    out["configs[2] 8-mic SMI-MVDR+Zelinski M=512 1000x5s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels_last_call=p.last_timing(),
+                                                                   **parity_and_cpu(p, x, d, M, "smimvdr_zelinski", [3, 522, 999], labels))
     p.close(); del x
     # configs[3]: 64-mic GSC-NLMS, M=512, 256 utterances
     C, M, U, n = 64, 512, 256, 80000
@@ -57,7 +94,7 @@ def main():
     s = timed(f3, steps=3, warm=1); T = p.num_frames; t = p.last_timing()
     bytes_perbin = (C + 1) * (M // 2 + 1) * 8 * U * T
     out["configs[3] 64-mic GSC-NLMS M=512 256x5s"] = dict(frames=U * T, ms=1e3 * s, frames_per_s=U * T / s, kernels=t,
-                                                          perbin_hbm_frac=bytes_perbin / (t["perbin_ms"] * 1e-3) / 1e9 / 6566.7)
+                                                          perbin_hbm_frac=bytes_perbin / (t["perbin_ms"] * 1e-3) / 1e9 / 6530.3, **parity_and_cpu(p, x, d, M, "gsclms", [1, 254]))
     p.close()
     # configs[3] with the covariance pass: 64-mic SMI-MVDR (k_covariance_wide + k_mvdr_solve_wide + static apply), same batch
     p = _capi.Pipeline(C, M, 4, 1, beamformer=_capi.BF_MVDR, max_utterances=U, max_samples=n)
