@@ -374,7 +374,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": "profiles/traffic.json (tools/ncu_traffic.py from the round's ncu --set full capture of this kernel; not measurable inside an unprofiled run)",
                      "peak_source": peak_src, "algorithmic_bytes_per_frame": alg[dom],
-                     "note": {"analysis_ms": "k_analysis is bound by the shared-memory data pipe, not by HBM (ncu, profiles/r02a_ncu_k_analysis_packed_details.txt: L1/TEX data-pipe wavefronts 72 % of peak with the byte count at the decomposition's minimum, issue slots 50 %, DRAM 47 %); the HBM fraction is reported as the contract asks",
+                     "note": {"analysis_ms": "k_analysis is bound by the shared-memory data pipe, not by HBM (ncu, profiles/r02m_ncu_k_analysis_details.txt: L1/TEX data-pipe wavefronts 72 % of peak with the byte count at the decomposition's minimum, issue slots 50 %, DRAM 47 %); the HBM fraction is reported as the contract asks",
                               "perbin_ms": "HBM-bound: ncu DRAM traffic equals the algorithmic bytes (profiles/traffic.json)",
                               "synthesis_ms": "bound by the shared-memory data pipe (ncu: L1/TEX 70 %)"}[dom],
                      "all_kernels_frac": {k: alg[k] * frames_step * args.steps / (ks[k] / 1000.0) / 1e9 / peak for k in ks if ks[k] > 0}},
