@@ -339,6 +339,14 @@ class Pipeline:
         _check(lib.btkb_stream_submit(self._h, _fp(x), ct.c_int(x.shape[2]), None if ln is None else ln.ctypes.data_as(ct.POINTER(ct.c_int)),
                                       ct.c_int(1 if final else 0), ct.c_int(1 if synthesis else 0)))
 
+    def stream_submit_i16(self, samples, lengths=None, final=False, synthesis=True):
+        """The same for 16-bit PCM chunks: samples int16 [U][C][n]."""
+        x = np.ascontiguousarray(samples, np.int16)
+        assert x.ndim == 3 and x.shape[1] == self.C
+        ln = None if lengths is None else np.ascontiguousarray(lengths, np.int32)
+        _check(lib.btkb_stream_submit_i16(self._h, x.ctypes.data_as(ct.POINTER(ct.c_int16)), ct.c_int(x.shape[2]),
+                                          None if ln is None else ln.ctypes.data_as(ct.POINTER(ct.c_int)), ct.c_int(1 if final else 0), ct.c_int(1 if synthesis else 0)))
+
     def stream_position(self):
         a, b = ct.c_int(0), ct.c_int(0)
         _check(lib.btkb_stream_position(self._h, ct.byref(a), ct.byref(b)))

@@ -1181,8 +1181,16 @@ int btkb_stream_begin(btkb_pipeline* p, int U) {
   return BTKB_OK;
 }
 
-int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int* lengths, int final_chunk, int do_syn) {
-  if (!p || (!samples && n > 0)) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: null argument");
+__global__ void k_i16_to_f32_rows(const int16_t* __restrict__ src, float* __restrict__ dst, size_t rows, int n, int dst_stride, int dst_off) {
+  const size_t total = rows * (size_t)n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / n; const int c = (int)(i - r * n);
+    dst[r * dst_stride + dst_off + c] = (float)src[i];
+  }
+}
+
+static int stream_submit_impl(btkb_pipeline* p, const float* samples, const int16_t* samples16, int n, const int* lengths, int final_chunk, int do_syn) {
+  if (!p || (!samples && !samples16 && n > 0)) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: null argument");
   if (!p->streaming) return fail(BTKB_ERR_STATE, "btkb_stream_submit: call btkb_stream_begin first");
   if (p->stream_final) return fail(BTKB_ERR_STATE, "btkb_stream_submit: the stream has ended (final chunk already submitted); call btkb_stream_begin");
   if (n < 0 || n > p->ncap) return fail(BTKB_ERR_INVALID, "btkb_stream_submit: n exceeds max_samples");
@@ -1207,9 +1215,15 @@ int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int*
   p->launches = 0;
   // ---- samples: [history | new] in the current buffer; `lengths` of the row count the history
   float* xs = p->d_xs[p->xs_cur];
-  if (n > 0)
+  if (n > 0 && samples)
     CK(cudaMemcpy2DAsync(xs + p->xs_hist, (size_t)p->xs_stride * sizeof(float), samples, (size_t)n * sizeof(float), (size_t)n * sizeof(float), (size_t)U * C,
                          cudaMemcpyHostToDevice, p->stream));
+  else if (n > 0) {   // 16-bit PCM chunk (live capture): upload as is, widen on the device behind the history prefix
+    if (!p->d_x16) CK(cudaMalloc((void**)&p->d_x16, (size_t)p->Ucap * C * p->n_stride * sizeof(int16_t)));
+    CK(cudaMemcpyAsync(p->d_x16, samples16, (size_t)U * C * n * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
+    k_i16_to_f32_rows<<<148 * 4, 256, 0, p->stream>>>(p->d_x16, xs, (size_t)U * C, n, p->xs_stride, p->xs_hist);
+    CK(cudaGetLastError());
+  }
   const long long s_base = p->s_samples - p->xs_hist;   // absolute index of the row's first sample
   for (int u = 0; u < U; u++) {
     p->s_len[u] += lloc[u];
@@ -1297,6 +1311,13 @@ int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int*
   p->s_tlast = t_base; p->s_blast = b_base; p->s_tnext = Tabs; p->s_bnext = std::max(nb_abs, b_base);
   p->stream_final = final_chunk != 0;
   return BTKB_OK;
+}
+
+int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int* lengths, int final_chunk, int do_syn) {
+  return stream_submit_impl(p, samples, nullptr, n, lengths, final_chunk, do_syn);
+}
+int btkb_stream_submit_i16(btkb_pipeline* p, const int16_t* samples, int n, const int* lengths, int final_chunk, int do_syn) {
+  return stream_submit_impl(p, nullptr, samples, n, lengths, final_chunk, do_syn);
 }
 
 int btkb_reset(btkb_pipeline* p) {   // FeatureStream::reset() of every stream of the graph (stream/stream.h:41): rewind, forget the adaptive state

@@ -221,6 +221,7 @@ int btkb_synchronize(btkb_pipeline* p);
  * (btkb_accumulate_covariance, btkb_sos_*) and > 8 channels. */
 int btkb_stream_begin(btkb_pipeline* p, int U);
 int btkb_stream_submit(btkb_pipeline* p, const float* samples, int n, const int* lengths, int final_chunk, int do_synthesis);
+int btkb_stream_submit_i16(btkb_pipeline* p, const int16_t* samples, int n, const int* lengths, int final_chunk, int do_synthesis);  /* 16-bit PCM chunks (live capture, wav) */
 int btkb_stream_position(const btkb_pipeline* p, int* first_frame, int* first_block);
 /* FeatureStream::reset() of the whole graph (stream/stream.h:41-47): drops the resident batch; while streaming, same as
  * btkb_stream_begin with the same U.  Weights are kept (the reference's reset() does not touch BeamformerWeights). */

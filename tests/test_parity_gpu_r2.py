@@ -417,3 +417,27 @@ def test_fused_analysis_nlms_equals_the_two_kernel_path(capi, protos):
     X = np.stack([restate.analysis(x[0, c], h, M, 4, 1) for c in range(C)], axis=1)
     Yo, _, _ = restate.gsc_lms(X, FS, d[0], **lms)
     assert rel_l2(res["fused"][0][0], Yo[:, :257]) < TOL
+
+
+def test_streamed_16_bit_pcm_chunks_equal_the_float_chunks(capi, protos):
+    """btkb_stream_submit_i16 (live capture hands out 16-bit PCM): identical to btkb_stream_submit with the same values as floats."""
+    from distant_speech_recognition_b200 import synthetic
+    C, M, U, D = 4, 256, 2, 128
+    h, g = protos[M]
+    x, d = synthetic.make_batch(U, C, 30 * D, first=2300, pcm16=True)
+    outs = []
+    for mode in ("float", "i16"):
+        p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=5), max_utterances=U, max_samples=12 * D)
+        p.set_prototypes(h, g); p.set_delays(d); p.stream_begin(U)
+        Ys, ys = [], []
+        for a, b in ((0, 7), (7, 19), (19, 30)):
+            xc = np.ascontiguousarray(x[:, :, a * D:b * D])
+            if mode == "float":
+                p.stream_submit(xc, final=b == 30)
+            else:
+                p.stream_submit_i16(xc.astype(np.int16), final=b == 30)
+            if p.num_frames: Ys.append(p.fetch_subband())
+            if p.num_blocks: ys.append(p.fetch_time())
+        outs.append((np.concatenate(Ys, axis=1), np.concatenate(ys, axis=1)))
+        p.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.abs(outs[0][1]).max() > 0
