@@ -405,7 +405,7 @@ static cudaError_t launch_analysis_r1(const AnalysisArgs& a_in, cudaStream_t st)
   using Plan = FftPlan<M>;
   constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
   const bool i16 = a.x16 != nullptr;
-  size_t smem = (i16 ? sizeof(uint32_t) : sizeof(float2)) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * 4;
+  size_t smem = (i16 ? sizeof(uint32_t) : sizeof(float2)) * ((size_t)(FR - 1) * (M / 2) + (size_t)MT * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 2 * ((Plan::NT + 31) / 32 + 1);   // red[G][2][NW] (round 2: was sized for NW <= 4, M = 2048 has 8 — found by compute-sanitizer)
   if (const char* e = getenv("BTKB_ANALYSIS_SMEM_PAD")) smem += (size_t)std::max(0, atoi(e));   // occupancy experiment: unused extra shared memory per CTA
   auto kern = i16 ? k_analysis_r1<M, MT, FR, G, true, true> : (analysis_packed() ? k_analysis_r1<M, MT, FR, G, true> : k_analysis_r1<M, MT, FR, G, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -429,7 +429,7 @@ static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
   constexpr int FR = 16;
   constexpr int G = (Plan::NT >= 128) ? 1 : (Plan::NT == 64 ? 2 : 4);
   const int m = (MT > 0) ? MT : a.m;
-  size_t smem = sizeof(float2) * ((size_t)(FR - 1) * a.D + (size_t)m * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * 4;
+  size_t smem = sizeof(float2) * ((size_t)(FR - 1) * a.D + (size_t)m * M) + sizeof(float2) * G * 2 * Plan::BUF + sizeof(float) * G * ((Plan::NT + 31) / 32 + 1);   // red[G][NW]
   auto kern = k_analysis_generic<M, MT, FR, G>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
