@@ -35,7 +35,7 @@ struct btkb_pipeline {
   float2 *d_X = nullptr, *d_Y = nullptr, *d_W = nullptr, *d_TA = nullptr, *d_WL = nullptr, *d_WA = nullptr, *d_UA = nullptr, *d_R = nullptr;
   float *d_E = nullptr, *d_time = nullptr, *d_upd = nullptr, *d_PFW = nullptr;
   double *d_delays = nullptr, *d_mpos = nullptr, *d_labels = nullptr, *d_stats = nullptr;
-  unsigned char* d_mask = nullptr; int* d_count = nullptr;
+  unsigned char* d_mask = nullptr; int* d_count = nullptr; unsigned char* d_todo = nullptr;   // d_todo: [Gpcap] per-chain flags of the wide MVDR solve
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   int16_t* d_x16 = nullptr; const int16_t* x16_cur = nullptr; int x16_stride = 0; double* h_delays = nullptr; float2* d_tw = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
   double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
@@ -108,7 +108,7 @@ void btkb_destroy(btkb_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
   void* ptrs[] = {p->d_xs[0], p->d_xs[1], p->d_ST, p->d_tu, p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
-                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
+                  p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_todo, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
                   p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM, p->d_wS, p->d_wG, p->d_wR, p->d_wTH, p->d_werr,
                   p->d_sosR, p->d_sosWd, p->d_sosCnt, p->d_sosWtu, p->d_sosMask, p->d_sosLab, p->d_sosErr, p->d_covS};
   if (p->h_delays) cudaFreeHost(p->h_delays);
@@ -474,7 +474,10 @@ int btkb_calc_mvdr_weights_ex(btkb_pipeline* p, float mu, float dthreshold) {
   if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");                      // beamformer.cc:2355-2357
   CK(cudaSetDevice(p->cfg.device));
   if (p->C <= 8) CK(launch_mvdr_solve(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, dthreshold, p->stream));
-  else CK(launch_mvdr_solve_wide(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->stream));
+  else {
+    if (!p->d_todo) CK(cudaMalloc((void**)&p->d_todo, (size_t)p->Gpcap));
+    CK(launch_mvdr_solve_wide(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->d_todo, p->stream));
+  }
   p->have_w = true;
   return BTKB_OK;
 }

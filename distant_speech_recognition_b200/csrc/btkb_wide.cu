@@ -251,8 +251,9 @@ __device__ __forceinline__ cdw cwdiv(cdw a, cdw b) { double d = b.x * b.x + b.y 
 // pivot search on the q = 0 threads combined through shared memory, distributed row swap, elimination; two barriers per
 // column.  The back substitution runs column-oriented with every row updating itself.
 constexpr int SOLVE_Q = 4;
-__global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize) {
+__global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize, const unsigned char* todo) {
   extern __shared__ __align__(16) unsigned char sm[];
+  if (todo != nullptr && !todo[blockIdx.x]) return;   // solved by the Cholesky kernel (uniform over the CTA)
   cdw* A = reinterpret_cast<cdw*>(sm);          // [C][C+1] augmented, row-major
   __shared__ double wbest[2]; __shared__ int widx[2];
   __shared__ double lam_part[2][2];
@@ -328,6 +329,129 @@ __global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, 
   }
 }
 
+// Hermitian positive-definite case of the same solve — every matrix the path itself builds (sample covariance, diffuse model, loaded
+// versions of them) — as a Cholesky factorisation with ONE WARP PER CHAIN: lower triangle packed in shared memory (C (C + 1) / 2
+// complex doubles, 33 KiB at C = 64 instead of the 66 KiB augmented square), lane l owns rows l and C - 1 - l (balanced: C - 1 - 2 j
+// trailing entries per column for every lane), dependent steps separated by __syncwarp instead of CTA barriers (the LU kernel above
+// spends its time in 4 x 64 of those), half the flops, no pivot search.  A chain whose matrix is not Hermitian (|a_ij - conj(a_ji)|^2
+// > 1e-10 a_ii a_jj) or not positive definite sets todo[g] = 1 and is left to the LU kernel, which then runs only for those chains.
+// R^H t = d with R Hermitian is R t = d;  w = t / (C t^H d)  (beamformer.cc:2386-2398), bin 0: all ones.
+constexpr int CHOL_WARPS = 2;
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
+__global__ void __launch_bounds__(32 * CHOL_WARPS) k_mvdr_solve_wide_chol(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp,
+                                                                          float mu, int normalize, unsigned char* todo) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * CHOL_WARPS + warp;
+  if (g >= U * K) return;
+  const int NT = C * (C + 1) / 2;
+  cdw* Lm = reinterpret_cast<cdw*>(sm) + (size_t)warp * (NT + C);   // packed lower triangle, then the right-hand side / solution [C]
+  cdw* bv = Lm + NT;
+  const int u = g / K, k = g - u * K;
+  if (lane == 0) todo[g] = 0;
+  if (k == 0) { for (int c = lane; c < C; c += 32) W[(size_t)c * Gp + g] = make_float2(1.f, 0.f); return; }
+  double scale = 1.0;
+  if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
+  // rows of this lane: r0 = lane, r1 = C - 1 - lane (C = 16: lanes >= 8 own nothing; C = 32: lanes >= 16 own nothing)
+  const int nrow = (2 * lane < C) ? ((C - 1 - lane != lane) ? 2 : 1) : 0;
+  const int rows[2] = {lane, C - 1 - lane};
+  bool herm = true;
+  for (int q = 0; q < nrow; q++) {
+    const int i = rows[q];
+    for (int j = 0; j <= i; j++) {
+      const float2 a = R[(size_t)(i * C + j) * Gp + g], b = R[(size_t)(j * C + i) * Gp + g];
+      cdw v = cw(0.5 * ((double)a.x + (double)b.x) * scale, 0.5 * ((double)a.y - (double)b.y) * scale);   // Hermitian part
+      if (i == j) { v.x += (double)mu; v.y = 0.0; }
+      Lm[tri(i, j)] = v;
+      const double dr = (double)a.x - (double)b.x, di = (double)a.y + (double)b.y;
+      const double aii = (double)R[(size_t)(i * C + i) * Gp + g].x, ajj = (double)R[(size_t)(j * C + j) * Gp + g].x;
+      if (dr * dr + di * di > 1e-10 * fabs(aii * ajj) + 1e-300) herm = false;
+    }
+    const float2 t = Dm[(size_t)i * Gp + g];
+    bv[i] = cw(t.x, t.y);
+  }
+  bool ok = __all_sync(0xffffffffu, herm);
+  __syncwarp();
+  // ---- Cholesky, right-looking, column by column
+  for (int j = 0; j < C && ok; j++) {
+    const double d = Lm[tri(j, j)].x;           // broadcast read
+    if (!(d > 0.0)) { ok = false; break; }      // uniform over the warp
+    const double sj = sqrt(d), inv = 1.0 / sj;
+    __syncwarp();                                // everybody has read the pivot
+    for (int q = 0; q < nrow; q++) {
+      const int i = rows[q];
+      if (i == j) Lm[tri(j, j)] = cw(sj, 0.0);
+      else if (i > j) { cdw v = Lm[tri(i, j)]; Lm[tri(i, j)] = cw(v.x * inv, v.y * inv); }
+    }
+    __syncwarp();
+    for (int q = 0; q < nrow; q++) {
+      const int i = rows[q];
+      if (i <= j) continue;
+      const cdw lij = Lm[tri(i, j)];
+      cdw* row = Lm + tri(i, 0);
+      // a_ic -= l_ij conj(l_cj), c = j+1 .. i; four entries per step with all loads issued before the first store (the compiler cannot
+      // prove that row[] and the column entries do not alias, and one dependent load -> FMA -> store chain per entry left the warp
+      // waiting on shared-memory latency)
+      int c = j + 1;
+      for (; c + 3 <= i; c += 4) {
+        const cdw l0 = Lm[tri(c, j)], l1 = Lm[tri(c + 1, j)], l2 = Lm[tri(c + 2, j)], l3 = Lm[tri(c + 3, j)];
+        cdw v0 = row[c], v1 = row[c + 1], v2 = row[c + 2], v3 = row[c + 3];
+        v0.x = fma(-lij.x, l0.x, fma(-lij.y, l0.y, v0.x)); v0.y = fma(-lij.y, l0.x, fma(lij.x, l0.y, v0.y));
+        v1.x = fma(-lij.x, l1.x, fma(-lij.y, l1.y, v1.x)); v1.y = fma(-lij.y, l1.x, fma(lij.x, l1.y, v1.y));
+        v2.x = fma(-lij.x, l2.x, fma(-lij.y, l2.y, v2.x)); v2.y = fma(-lij.y, l2.x, fma(lij.x, l2.y, v2.y));
+        v3.x = fma(-lij.x, l3.x, fma(-lij.y, l3.y, v3.x)); v3.y = fma(-lij.y, l3.x, fma(lij.x, l3.y, v3.y));
+        if (c + 3 == i) v3.y = 0.0;
+        row[c] = v0; row[c + 1] = v1; row[c + 2] = v2; row[c + 3] = v3;
+      }
+      for (; c <= i; c++) {
+        const cdw lcj = Lm[tri(c, j)];
+        cdw v = row[c];
+        v.x = fma(-lij.x, lcj.x, fma(-lij.y, lcj.y, v.x));
+        v.y = fma(-lij.y, lcj.x, fma(lij.x, lcj.y, v.y));
+        if (c == i) v.y = 0.0;
+        row[c] = v;
+      }
+    }
+    __syncwarp();
+  }
+  if (!ok) { if (lane == 0) todo[g] = 1; return; }
+  // ---- L y = d (forward), L^H t = y (backward); column-oriented, every lane updates its own rows
+  for (int i = 0; i < C; i++) {
+    const cdw yi = cw(bv[i].x / Lm[tri(i, i)].x, bv[i].y / Lm[tri(i, i)].x);   // every lane computes the same value from broadcast reads
+    __syncwarp();
+    for (int q = 0; q < nrow; q++) {
+      const int r = rows[q];
+      if (r == i) bv[i] = yi;
+      else if (r > i) bv[r] = cwmsub(bv[r], Lm[tri(r, i)], yi);
+    }
+    __syncwarp();
+  }
+  for (int i = C - 1; i >= 0; i--) {
+    const cdw ti = cw(bv[i].x / Lm[tri(i, i)].x, bv[i].y / Lm[tri(i, i)].x);
+    __syncwarp();
+    for (int q = 0; q < nrow; q++) {
+      const int r = rows[q];
+      if (r == i) bv[i] = ti;
+      else if (r < i) { const cdw l = Lm[tri(i, r)]; bv[r] = cwmsub(bv[r], cw(l.x, -l.y), ti); }   // y_r -= conj(l_ir) t_i
+    }
+    __syncwarp();
+  }
+  // ---- Lambda = t^H d, w = t / (C Lambda)
+  double lr = 0.0, li = 0.0;
+  for (int q = 0; q < nrow; q++) {
+    const int r = rows[q];
+    const float2 dd = Dm[(size_t)r * Gp + g]; const cdw tv = bv[r];
+    lr += tv.x * dd.x + tv.y * dd.y; li += tv.x * dd.y - tv.y * dd.x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lr += __shfl_xor_sync(0xffffffffu, lr, o); li += __shfl_xor_sync(0xffffffffu, li, o); }
+  for (int q = 0; q < nrow; q++) {
+    const int r = rows[q];
+    const cdw wv = cwdiv(bv[r], cw(lr * C, li * C));
+    W[(size_t)r * Gp + g] = make_float2((float)wv.x, (float)wv.y);
+  }
+}
+
 static cudaError_t make_map_wide(CUtensorMap* tm, const PerBinArgs& a, int C) {
   return encode_tensor_map_2d_f32(tm, a.X, (cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C, (cuuint64_t)a.Gp * sizeof(float2), (cuuint32_t)(2 * TC), (cuuint32_t)C,
                                   CU_TENSOR_MAP_SWIZZLE_128B);
@@ -382,11 +506,25 @@ cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu,
-                                   int normalize_by_count, cudaStream_t st) {
+                                   int normalize_by_count, unsigned char* todo, cudaStream_t st) {
   const size_t smem = sizeof(wide::cdw) * (size_t)C * (C + 1);
   cudaError_t e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  wide::k_mvdr_solve_wide<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count);
+  // BTKB_SOLVE_CHOL=1 (opt-in, read at every call): Hermitian positive-definite matrices go through the warp-per-chain Cholesky, which flags
+  // the others for the pivoted LU.  Measured at configs[3] size (65 792 matrices of 64 x 64, profiles/r02p_wide_solve.jsonl): 16.9 ms
+  // against 17.7 ms for the LU alone when every matrix is positive definite, 30.6 ms when none is (both kernels run) — one warp per chain
+  // is latency-bound at 6 warps per SM, so the LU stays the default.
+  const bool use_chol = [] { const char* ev = getenv("BTKB_SOLVE_CHOL"); return ev && atoi(ev) != 0; }();
+  if (use_chol && todo != nullptr) {
+    const size_t smc = sizeof(wide::cdw) * (size_t)wide::CHOL_WARPS * ((size_t)C * (C + 1) / 2 + C);
+    e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc);
+    if (e != cudaSuccess) return e;
+    wide::k_mvdr_solve_wide_chol<<<(U * K + wide::CHOL_WARPS - 1) / wide::CHOL_WARPS, 32 * wide::CHOL_WARPS, smc, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    wide::k_mvdr_solve_wide<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+    return cudaGetLastError();
+  }
+  wide::k_mvdr_solve_wide<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, nullptr);
   return cudaGetLastError();
 }
 

@@ -441,3 +441,34 @@ def test_streamed_16_bit_pcm_chunks_equal_the_float_chunks(capi, protos):
         outs.append((np.concatenate(Ys, axis=1), np.concatenate(ys, axis=1)))
         p.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.abs(outs[0][1]).max() > 0
+
+
+@pytest.mark.parametrize("chol", ["0", "1"])
+@pytest.mark.parametrize("C", [16, 64])
+def test_wide_mvdr_solve_cholesky_and_lu_fallback(capi, protos, C, chol, monkeypatch):
+    """The wide MVDR solve (C > 8): Hermitian positive-definite matrices go through the warp-per-chain Cholesky kernel, everything else
+    (here: a general complex matrix, and an indefinite Hermitian one) is flagged and solved by the pivoted LU; both against
+    calc_mvdr_weights in fp64 (beamformer.cc:2350-2402)."""
+    from oracle import restate
+    monkeypatch.setenv("BTKB_SOLVE_CHOL", chol)      # 1: Cholesky kernel + LU for the flagged chains; 0 (default): LU for all
+    M, K = 256, 129
+    rng = np.random.default_rng(C)
+    d = np.cumsum(rng.uniform(0, 3e-5, C))[None]
+    wq = restate.calc_mainlobe(M, C, FS, d[0])
+    R = np.zeros((1, K, C, C), np.complex64)
+    for k in range(K):
+        A = rng.standard_normal((C, C)) + 1j * rng.standard_normal((C, C))
+        if k % 3 == 0:
+            R[0, k] = A @ A.conj().T / C + 0.5 * np.eye(C)                          # Hermitian positive definite -> Cholesky
+        elif k % 3 == 1:
+            R[0, k] = A / np.sqrt(C) + 3.0 * np.eye(C)                              # general complex -> LU
+        else:
+            H = (A + A.conj().T) / np.sqrt(C); R[0, k] = H + 0.1j * 0 + np.diag(np.where(np.arange(C) % 2 == 0, 4.0, -4.0))   # Hermitian indefinite -> LU
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_MVDR, max_utterances=1, max_samples=4000)
+    p.set_prototypes(*protos[M]); p.set_delays(d); p.set_noise_covariance(R)
+    p.calc_mvdr_weights(0.0)
+    W = p.get_weights()[0]
+    Wo = restate.calc_mvdr_weights(R[0].astype(np.complex128), wq, thr=0.0, single=False)
+    for k in range(1, K):
+        assert rel_l2(W[k], Wo[k]) < (2e-5 if k % 3 == 0 else 5e-4), (C, k, k % 3)   # the general / indefinite matrices are worse conditioned
+    p.close()
