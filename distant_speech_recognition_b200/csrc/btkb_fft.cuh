@@ -34,6 +34,7 @@ __device__ __forceinline__ float2 mul_si(float2 a) {
   return SIGN > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 
+#if defined(__CUDACC__)   // (this header is also compiled for the host by tests/host/fft_packed_host.cc)
 // Barrier over the NT threads of ONE transform group (group index grp of G per CTA): the groups of a CTA work on different frames with
 // private exchange buffers, so inside a transform they only have to wait for their own threads — a warp-level barrier when a group is
 // one warp, a named barrier (ids 1..G; 0 stays __syncthreads) when it is several, the CTA barrier when the CTA is one group.
@@ -43,6 +44,7 @@ __device__ __forceinline__ void group_sync(int grp) {
   else if constexpr (NT <= 32) __syncwarp();
   else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(NT) : "memory");
 }
+#endif
 
 template <int M>
 struct FftPlan {
