@@ -1,4 +1,6 @@
-"""Specification check for chunked submission ("chunked submission with carried state"; not built yet).
+"""Specification check for chunked submission (DESIGN.md §4 "Streamed chunks with carried state"; built in round 2 as btkb_stream_begin /
+btkb_stream_submit, which number frames and blocks absolutely instead of dropping the re-computed ones; GPU identity tests:
+tests/test_parity_gpu_r2.py::test_streamed_*).
 
 A live front end hands the pipe an utterance piece by piece.  With the oracle's restatement of the two filter banks
 (oracle/restate.py: OverSampledDFTAnalysisBank::next, modulated/modulated.cc:363-469; OverSampledDFTSynthesisBank::next,

@@ -472,3 +472,34 @@ def test_wide_mvdr_solve_cholesky_and_lu_fallback(capi, protos, C, chol, monkeyp
     for k in range(1, K):
         assert rel_l2(W[k], Wo[k]) < (2e-5 if k % 3 == 0 else 5e-4), (C, k, k % 3)   # the general / indefinite matrices are worse conditioned
     p.close()
+
+
+def test_reset_and_caller_supplied_stream(capi, protos):
+    """btkb_set_stream: the pipeline's work runs on the caller's CUDA stream (SURVEY §8b) — same results as on its private stream;
+    btkb_reset: FeatureStream::reset() of the graph — the resident batch is dropped (weights kept), a live stream starts afresh."""
+    import torch
+    from distant_speech_recognition_b200 import synthetic
+    C, M, U, n, D = 4, 256, 2, 6000, 128
+    h, g = protos[M]
+    x, d = synthetic.make_batch(U, C, n, first=2500)
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_GSC_LMS, lms=dict(min_frames=5), max_utterances=U, max_samples=n)
+    p.set_prototypes(h, g); p.set_delays(d); p.submit(x); p.run(True)
+    Y0, y0 = p.fetch_subband(), p.fetch_time()
+    s = torch.cuda.Stream()
+    p.set_stream(s.cuda_stream)
+    p.submit(x); p.run(True); s.synchronize()
+    assert np.array_equal(p.fetch_subband(), Y0) and np.array_equal(p.fetch_time(), y0)
+    p.set_stream(None)
+    p.submit(x); p.run(True)
+    assert np.array_equal(p.fetch_subband(), Y0)
+    p.reset()
+    with pytest.raises(capi.BtkbError):
+        p.fetch_subband()                                   # nothing resident any more
+    p.submit(x); p.run(True)                                # ... and the weights survived the reset
+    assert np.array_equal(p.fetch_subband(), Y0)
+    p.stream_begin(U)
+    p.stream_submit(np.ascontiguousarray(x[:, :, :20 * D])); a1 = p.fetch_subband()
+    p.reset()                                               # rewinds the live stream: same chunk, same frames, adaptation restarted
+    p.stream_submit(np.ascontiguousarray(x[:, :, :20 * D])); a2 = p.fetch_subband()
+    assert np.array_equal(a1, a2) and np.array_equal(a1[:, :, :], Y0[:, :a1.shape[1], :])
+    p.close()
