@@ -329,6 +329,97 @@ __global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, 
   }
 }
 
+// The same elimination with IMPLICIT pivoting and ONE barrier per column (k_mvdr_solve_wide above: three — pivot search, row swap,
+// elimination).  Rows are never swapped: a row that has served as pivot is marked done and keeps its place, order[col] remembers which
+// row eliminated column col; and the pivot search for column col + 1 rides on the elimination of column col (the q = 0 thread of a row
+// has the row's new entry of column col + 1 in a register the moment it is computed), so the arg-max shuffle needs no barrier of its
+// own and the single barrier publishes both the eliminated entries and the candidates.  Same pivots, same arithmetic per entry as the
+// swapping version (partial pivoting by largest modulus, ties to the smallest row index).
+__global__ void k_mvdr_solve_wide_ip(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize, const unsigned char* todo) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  if (todo != nullptr && !todo[blockIdx.x]) return;
+  cdw* A = reinterpret_cast<cdw*>(sm);          // [C][C+1] augmented, row-major
+  __shared__ double wbest[2][2]; __shared__ int widx[2][2];
+  __shared__ int order[64];
+  __shared__ double lam_part[2][2];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int r = tid % C, q = tid / C;           // blockDim.x == SOLVE_Q * C
+  const int u = g / K, k = g - u * K;
+  const int nwarp0 = (C + 31) / 32;
+  if (k == 0) { if (tid < C) W[(size_t)tid * Gp + g] = make_float2(1.f, 0.f); return; }
+  double scale = 1.0;
+  if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
+  const int LD = C + 1;
+  double cand = -1.0;                           // |A[r][col]|^2 of the column about to be eliminated (q == 0 threads)
+  for (int c = q; c < C; c += SOLVE_Q) {
+    float2 t = R[(size_t)(c * C + r) * Gp + g];
+    cdw v = cw((double)t.x * scale, -(double)t.y * scale);
+    if (c == r) v.x += (double)mu;
+    A[r * LD + c] = v;
+    if (c == 0) cand = v.x * v.x + v.y * v.y;
+  }
+  if (q == 0) { float2 t = Dm[(size_t)r * Gp + g]; A[r * LD + C] = cw(t.x, t.y); }
+  bool done = false, singular = false;
+  int mypos = -1;
+  for (int col = 0; col < C; col++) {
+    if (tid < 32 * nwarp0) {
+      double m2 = (tid < C && !done) ? cand : -1.0; int idx = tid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double om = __shfl_xor_sync(0xffffffffu, m2, o); const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (om > m2 || (om == m2 && oi < idx)) { m2 = om; idx = oi; }
+      }
+      if ((tid & 31) == 0) { wbest[col & 1][tid >> 5] = m2; widx[col & 1][tid >> 5] = idx; }
+    }
+    __syncthreads();   // the one barrier of the column: eliminated entries of column col - 1 and the pivot candidates are visible
+    double best = wbest[col & 1][0]; int piv = widx[col & 1][0];
+    if (nwarp0 > 1 && (wbest[col & 1][1] > best)) { best = wbest[col & 1][1]; piv = widx[col & 1][1]; }
+    if (!(best > 1e-60)) { singular = true; break; }   // uniform over the CTA
+    if (r == piv) { done = true; mypos = col; }
+    if (tid == 0) order[col] = piv;
+    if (!done) {
+      const cdw f = cwdiv(A[r * LD + col], A[piv * LD + col]);   // neither entry is written in this step
+#pragma unroll 4
+      for (int c = col + 1 + q; c <= C; c += SOLVE_Q) {
+        const cdw v = cwmsub(A[r * LD + c], f, A[piv * LD + c]);
+        A[r * LD + c] = v;
+        if (c == col + 1) cand = v.x * v.x + v.y * v.y;           // (q == 0 only) the candidate for the next column
+      }
+    }
+  }
+  __syncthreads();
+  if (!singular) {
+    // back substitution in pivot order: x_col = b[p] / a[p][col] with p = order[col]; every earlier pivot row subtracts a[.][col] x_col
+    for (int col = C - 1; col >= 0; col--) {
+      const int p = order[col];
+      if (q == 0 && r == p) A[p * LD + C] = cwdiv(A[p * LD + C], A[p * LD + col]);
+      __syncthreads();
+      if (q == 0 && mypos < col) A[r * LD + C] = cwmsub(A[r * LD + C], A[r * LD + col], A[p * LD + C]);
+    }
+    __syncthreads();
+  }
+  // unknown c sits in the right-hand side of its pivot row (identity fallback: t = d, beamformer.cc:2381-2383)
+  cdw tv = cw(0.0, 0.0);
+  if (tid < C) {
+    if (singular) { const float2 t = Dm[(size_t)tid * Gp + g]; tv = cw(t.x, t.y); }
+    else tv = A[order[tid] * LD + C];
+  }
+  if (tid < 32 * nwarp0) {
+    double lr = 0.0, li = 0.0;
+    if (tid < C) { const float2 d = Dm[(size_t)tid * Gp + g]; lr = tv.x * d.x + tv.y * d.y; li = tv.x * d.y - tv.y * d.x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lr += __shfl_xor_sync(0xffffffffu, lr, o); li += __shfl_xor_sync(0xffffffffu, li, o); }
+    if ((tid & 31) == 0) { lam_part[tid >> 5][0] = lr; lam_part[tid >> 5][1] = li; }
+  }
+  __syncthreads();
+  double lam_re = lam_part[0][0], lam_im = lam_part[0][1];
+  if (nwarp0 > 1) { lam_re += lam_part[1][0]; lam_im += lam_part[1][1]; }
+  if (tid < C) {
+    const cdw wv = cwdiv(tv, cw(lam_re * C, lam_im * C));
+    W[(size_t)tid * Gp + g] = make_float2((float)wv.x, (float)wv.y);
+  }
+}
+
 // Hermitian positive-definite case of the same solve — every matrix the path itself builds (sample covariance, diffuse model, loaded
 // versions of them) — as a Cholesky factorisation with ONE WARP PER CHAIN: lower triangle packed in shared memory (C (C + 1) / 2
 // complex doubles, 33 KiB at C = 64 instead of the 66 KiB augmented square), lane l owns rows l and C - 1 - l (balanced: C - 1 - 2 j
@@ -508,7 +599,13 @@ cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st) {
 cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu,
                                    int normalize_by_count, unsigned char* todo, cudaStream_t st) {
   const size_t smem = sizeof(wide::cdw) * (size_t)C * (C + 1);
-  cudaError_t e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // BTKB_SOLVE_IP=1 (opt-in): implicit pivoting, one barrier per column instead of three.  Measured 18.07 vs 17.80 ms at configs[3] size
+  // (profiles/r02p_wide_solve.jsonl): the barrier COUNT is not what limits this kernel — ncu (profiles/r02q_ncu_k_mvdr_solve_wide_ip_details.txt):
+  // 137 k warp instructions per matrix for 11 k warp-DFMAs of elimination work, issue slots 43 %, fp64 pipe 23 %, barrier stall still
+  // 4.8 per issue because the 8 warps of a CTA wait for the 2 that search the pivot and for each other's shared-memory latency.
+  const bool ip = [] { const char* ev = getenv("BTKB_SOLVE_IP"); return ev && atoi(ev) != 0; }();
+  auto lu = ip ? wide::k_mvdr_solve_wide_ip : wide::k_mvdr_solve_wide;
+  cudaError_t e = cudaFuncSetAttribute(lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // BTKB_SOLVE_CHOL=1 (opt-in, read at every call): Hermitian positive-definite matrices go through the warp-per-chain Cholesky, which flags
   // the others for the pivoted LU.  Measured at configs[3] size (65 792 matrices of 64 x 64, profiles/r02p_wide_solve.jsonl): 16.9 ms
@@ -521,10 +618,10 @@ cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, 
     if (e != cudaSuccess) return e;
     wide::k_mvdr_solve_wide_chol<<<(U * K + wide::CHOL_WARPS - 1) / wide::CHOL_WARPS, 32 * wide::CHOL_WARPS, smc, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    wide::k_mvdr_solve_wide<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+    lu<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
     return cudaGetLastError();
   }
-  wide::k_mvdr_solve_wide<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, nullptr);
+  lu<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, nullptr);
   return cudaGetLastError();
 }
 
