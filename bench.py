@@ -211,7 +211,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     numa = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs (its version banner at NCCL_DEBUG=WARN/INFO) goes to stderr: stdout carries the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local))
     c = CFG
