@@ -197,6 +197,12 @@ class Pipeline:
         _check(lib.btkb_last_timing_wpe(self._h, ct.byref(ms)))
         return float(ms.value)
 
+    def last_wpe_form(self):
+        """0: the last estimation solved the lag-domain normal equations (L x L), 1: the frame-domain ones (S x S)."""
+        f = ct.c_int(-1)
+        _check(lib.btkb_last_wpe_form(self._h, ct.byref(f)))
+        return int(f.value)
+
     # ---- noise coherence of the McCowan / Lefkimmiatis post-filters (postfilter.cc:541-680)
     def pf_set_diffuse_noise_model(self, mpos, samplerate=16000.0, sspeed=343740.0):
         mp = np.ascontiguousarray(mpos, np.float64)

@@ -41,7 +41,7 @@ struct btkb_pipeline {
   double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
   // multi-channel WPE (lazily sized at create when cfg.wpe.enabled)
   float2 *d_wS = nullptr, *d_wG = nullptr; void* d_wR = nullptr; float* d_wTH = nullptr; int* d_werr = nullptr;
-  int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_Ts = 0, wpe_nbins = 0, wpe_U = 0; bool have_wpe = false;
+  int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_Ts = 0, wpe_nbins = 0, wpe_U = 0, wpe_form = -1, wpe_last_form = -1; size_t wpe_slot = 0; bool have_wpe = false;
   cudaEvent_t wev[2] = {nullptr, nullptr};
   // SOS batch beamformers (lazily allocated by the first btkb_sos_accumulate_*)
   double2 *d_sosR = nullptr, *d_sosWd = nullptr; double* d_sosCnt = nullptr; float *d_sosWtu = nullptr, *d_sosMask = nullptr; double* d_sosLab = nullptr;
@@ -201,8 +201,15 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
   A((void**)&p->d_count, U * sizeof(int));
   A((void**)&p->d_tw, (size_t)M * sizeof(float2));
   if (cfg->wpe.enabled) {
-    p->wpe_P = cfg->wpe.upper_num - cfg->wpe.lower_num + 1; p->wpe_L = C * p->wpe_P; p->wpe_Lr = round_up(p->wpe_L + 1, 2);  // column L exists: the augmented row carries its own diagonal entry
+    p->wpe_P = cfg->wpe.upper_num - cfg->wpe.lower_num + 1; p->wpe_L = C * p->wpe_P;
     p->wpe_Ts = round_up(p->Tcap, 2);
+    // Which normal equations (btkb_wpe.cu): -1 = per batch, the smaller of the lag-domain (L x L) and the frame-domain (S x S) system.
+    // BTKB_WPE_FORM=lag|frame pins one for the life of the pipeline; pinning "frame" sizes the matrix slots for S up to Tcap.
+    const char* fe = getenv("BTKB_WPE_FORM");
+    p->wpe_form = (fe && !strcmp(fe, "lag")) ? 0 : (fe && !strcmp(fe, "frame")) ? 1 : -1;
+    const int nslot = (p->wpe_form == 1) ? std::max(p->wpe_L, std::max(p->Tcap - cfg->wpe.lower_num, 0)) : p->wpe_L;
+    p->wpe_Lr = round_up(nslot + 1, 2);  // column L exists: the augmented row carries its own diagonal entry
+    p->wpe_slot = (size_t)(nslot + 1) * p->wpe_Lr;
     const int lo = (cfg->wpe.band_width == 0.0) ? M / 2 : (int)((cfg->wpe.band_width / (cfg->samplerate / 2.0)) * (M / 2));  // set_band_width_ (:365-373)
     p->wpe_nbins = std::min(lo, p->K - 1) + 1;
     const char* ce = getenv("BTKB_WPE_CHUNK");
@@ -212,7 +219,7 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
     A((void**)&p->d_wS, (size_t)p->Ucap * p->K * C * p->wpe_Ts * sizeof(float2));
     A((void**)&p->d_wTH, (size_t)p->Ucap * p->K * C * p->wpe_Ts * sizeof(float));
     A((void**)&p->d_wG, (size_t)p->Ucap * p->K * C * p->wpe_L * sizeof(float2));
-    A((void**)&p->d_wR, wpe_workspace_bytes(C, p->wpe_L, p->wpe_Lr, p->wpe_chunk, cfg->wpe.fp32_normal_equations));
+    A((void**)&p->d_wR, wpe_workspace_bytes(C, p->wpe_slot, p->wpe_chunk, cfg->wpe.fp32_normal_equations));
     A((void**)&p->d_werr, sizeof(int));
   }
   if (e == cudaSuccess && p->Cp != C) {   // the padded channel rows stay zero for the life of the pipeline: no kernel writes them
@@ -591,6 +598,9 @@ static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no, bool a
   a.est_frames = (end_frame_no < 0) ? -1 : std::max(0, end_frame_no - std::max(start_frame_no, 0));   // fill_buffer_ (:500-534) never skips input frames
   a.load_factor = (float)pow(10.0, w.load_db / 10.0); a.diagonal_bias = (float)w.diagonal_bias;
   a.apply_only = apply_only ? 1 : 0;
+  a.slot = p->wpe_slot;
+  a.Sd = std::max(((a.est_frames >= 0) ? std::min(a.T, a.est_frames) : a.T) - a.lowerN, 0);
+  a.form = (p->wpe_form >= 0) ? p->wpe_form : (a.Sd < a.L ? 1 : 0);   // the frame-domain system has S <= Sd rows, the lag-domain one L
   CK(cudaMemsetAsync(p->d_werr, 0, sizeof(int), p->stream));
   CK(cudaEventRecord(p->wev[0], p->stream));
   CK(launch_wpe(a, p->wpe_chunk, p->cfg.wpe.fp32_normal_equations, p->stream, &p->launches));
@@ -601,7 +611,7 @@ static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no, bool a
   if (err)  // dereverberation.cc:676-678
     return fail(BTKB_ERR_INVALID, "MultiChannelWPEDereverberation: GSL Cholesky decomposition failed.\nSome channels may be too similar. Try to increase 'diagonal_bias' or use 'SingleChannelWPEDereverberationFeature' for each channel");
   p->have_wpe = true;
-  if (!apply_only) p->wpe_U = p->U;
+  if (!apply_only) { p->wpe_U = p->U; p->wpe_last_form = a.form; }
   return BTKB_OK;
 }
 
@@ -887,6 +897,13 @@ int btkb_last_timing_wpe(btkb_pipeline* p, float* ms) {
   CK(cudaSetDevice(p->cfg.device));
   CK(cudaEventSynchronize(p->wev[1]));
   CK(cudaEventElapsedTime(ms, p->wev[0], p->wev[1]));
+  return BTKB_OK;
+}
+
+int btkb_last_wpe_form(btkb_pipeline* p, int* form) {
+  if (!p || !form) return fail(BTKB_ERR_INVALID, "null argument");
+  if (!p->have_wpe || p->wpe_last_form < 0) return fail(BTKB_ERR_STATE, "btkb_last_wpe_form: no filter has been estimated by this pipeline");
+  *form = p->wpe_last_form;
   return BTKB_OK;
 }
 

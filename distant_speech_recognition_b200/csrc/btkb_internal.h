@@ -102,14 +102,19 @@ struct WpeArgs {
   float2* S;             // [G][C][Ts] series-major copy of X
   float* TH;             // [G][C][Ts] theta
   float2* Gf;            // [G][C][L] prediction filters (chains outside the estimated band stay zero)
-  void* Rw;              // workspace [chunk][C][L+1][Lr] complex128 (or complex64): lower triangle of R_c, row L = conj(r_c)
+  void* Rw;              // workspace of matrix slots, complex128 (or complex64), `slot` elements each.  Lag-domain form: [chunk][C] slots,
+                         // [L+1][Lr]: lower triangle of R_c, row L = conj(r_c).  Frame-domain form: [chunk][C+1] slots, [Sd+1][Lr]: the
+                         // C loaded systems of a problem and, in slot C, the Gram matrix K they share
+  size_t slot;           // elements per slot (>= (L+1) Lr; >= (Sd+1) Lr when the frame-domain form may be used)
+  int form;              // 0: lag-domain normal equations (L x L), 1: frame-domain (S x S, S = estimation frames - lower)
+  int Sd;                // frame-domain form: largest S in the batch
   int* err_flag;         // set to 1 when a Cholesky pivot is not positive
   int U, C, T, Ts, K, G, Gp, D, laN, pdA;
   int lowerN, P, L, Lr, iterations, nbins, est_frames;
   float load_factor, diagonal_bias;
   int apply_only;        // keep the filters Gf of an earlier estimation and run the output stage only
 };
-size_t wpe_workspace_bytes(int C, int L, int Lr, int chunk, int fp32);
+size_t wpe_workspace_bytes(int C, size_t slot, int chunk, int fp32);
 cudaError_t launch_wpe(const WpeArgs& a, int chunk, int fp32, cudaStream_t st, int* launches);
 
 // SOS batch beamformers (btkb_sos.cu)

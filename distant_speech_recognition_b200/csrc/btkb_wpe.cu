@@ -19,6 +19,17 @@
 // panel-wise backward substitution.  Arithmetic: fp64 like the reference (RT = double; the loaded normal equations need it for
 // the 1e-4 parity budget) or fp32 (cfg.wpe.fp32_normal_equations) on the CUDA cores; DESIGN.md K7 says why the Gram is not on the
 // tensor cores.
+//
+// Two forms of the same normal equations.  With A = [lags(s)] (L x S, S = estimation frames - lower), Theta_c = diag(theta_c) and
+// ybar_c(s) = conj(x_c(s)), calc_Rr_ + load_R_ build  (A Theta_c^-1 A^H + delta_c I) g_c = A Theta_c^-1 ybar_c  with the uniform
+// loading  delta_c = bias + load_factor (max_i (A Theta_c^-1 A^H)_ii + bias).  By the push-through identity
+//     g_c = A (K + delta_c Theta_c)^-1 ybar_c,      K = A^H A   (S x S, the same for every channel and every iteration),
+// so when an utterance is shorter than the filter (S < L: 5 s at D = 512 are 157 frames against L = 8 x 33 = 264) the batch is
+// served in this FRAME-DOMAIN form: k_wpe_gram_dual forms K once per problem, k_wpe_chol<DUAL> adds delta_c Theta_c on the fly,
+// factors the S x S system and maps the solution back through A.  Symmetric diagonal scaling (Theta^1/2) turns K + delta Theta
+// into delta I + Theta^-1/2 K Theta^-1/2, which has the spectrum of the lag-domain matrix, and Cholesky's backward error does not
+// depend on such scaling: same conditioning, (S / L)^3 of the factorisation work, and the Gram is not repeated per channel or
+// iteration.  a.form picks the form per batch (btkb_api.cu: do_wpe).
 #include "btkb_internal.h"
 #include <math.h>
 #include <algorithm>
@@ -80,9 +91,9 @@ __device__ __forceinline__ void load_series_t(const WpeArgs& a, int g, int nfr, 
 
 // MODE 0: theta over the estimation frames; MODE 1: the output stage over every frame of the utterance (writes X in place)
 template <int MODE>
-__global__ void __launch_bounds__(128) k_wpe_resid(WpeArgs a) {
+__global__ void __launch_bounds__(128) k_wpe_resid(WpeArgs a, int q0) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int g = (MODE == 0) ? problem_chain(a, blockIdx.x) : blockIdx.x;
+  const int g = (MODE == 0) ? problem_chain(a, q0 + blockIdx.x) : blockIdx.x;
   if (g >= a.G) return;
   const int u = g / a.K, k = g - u * a.K;
   const int Tu = frames_of(a.lengths[u], a.D, a.laN, a.pdA);
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_corr(WpeArgs a, int q0
   }
   __syncthreads();
   const int L = a.L, P = a.P, Lr = a.Lr;
-  CX* Rq = reinterpret_cast<CX*>(a.Rw) + (size_t)blockIdx.y * C * (size_t)(L + 1) * Lr;
+  CX* Rq = reinterpret_cast<CX*>(a.Rw) + (size_t)blockIdx.y * C * a.slot;
   const int nS = max(nfr - a.lowerN, 0);   // s' = s - lower, s = lower .. nfr-1
   const int L2 = (L + 1) / 2;
   const int ntiles = L2 * (L2 + 1) / 2;
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_corr(WpeArgs a, int q0
     }
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      CX* Rc = Rq + (size_t)c * (L + 1) * Lr;
+      CX* Rc = Rq + (size_t)c * a.slot;
       Rc[(size_t)i0 * Lr + j0] = acc[0][c];
       if (j0 + 1 < L && j0 + 1 <= i0) Rc[(size_t)i0 * Lr + j0 + 1] = acc[1][c];
       if (i0 + 1 < L) {
@@ -201,45 +212,141 @@ __global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_corr(WpeArgs a, int q0
       }
     }
 #pragma unroll
-    for (int c = 0; c < C; c++) Rq[((size_t)c * (L + 1) + L) * Lr + j] = acc[c];
+    for (int c = 0; c < C; c++) Rq[(size_t)c * a.slot + (size_t)L * Lr + j] = acc[c];
   }
 }
 
-// one CTA per (problem, channel): diagonal bias + loading, panel Cholesky of the augmented matrix, backward substitution
+// Frame-domain form: K[s][s'] = sum_i conj(lags_i(s)) lags_i(s') (lower triangle, s' <= s) of the problems [q0, q0 + gridDim.y)
+// into slot C of each problem; blockIdx.x = split.  A thread owns a 2 x 2 tile; along the lag index the two rows (columns) of a
+// tile read the same series one frame apart, so each step loads 2 new values for 4 complex MACs.
 template <typename RT>
+__global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_gram_dual(WpeArgs a, int q0) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typedef cx<RT> CX;
+  const int g = problem_chain(a, q0 + blockIdx.y);
+  const int u = g / a.K;
+  const int nfr = est_frames_of(a, u);
+  const int xstride = a.P + a.T, P = a.P, C = a.C, Lr = a.Lr;
+  CX* xs = reinterpret_cast<CX*>(smem);
+  load_series_t<RT>(a, g, nfr, xs, xstride);
+  __syncthreads();
+  const int nS = max(nfr - a.lowerN, 0);
+  CX* Kq = reinterpret_cast<CX*>(a.Rw) + ((size_t)blockIdx.y * (C + 1) + C) * a.slot;
+  const int S2 = (nS + 1) / 2;
+  const int ntiles = S2 * (S2 + 1) / 2;
+  for (int tq = blockIdx.x * blockDim.x + threadIdx.x; tq < ntiles; tq += gridDim.x * blockDim.x) {
+    int bi = (int)((sqrtf(8.0f * (float)tq + 1.0f) - 1.0f) * 0.5f);
+    while ((bi + 1) * (bi + 2) / 2 <= tq) bi++;
+    while (bi * (bi + 1) / 2 > tq) bi--;
+    const int bj = tq - bi * (bi + 1) / 2;
+    const int s0 = 2 * bi, t0 = 2 * bj;
+    const int ds = (s0 + 1 < nS) ? 1 : 0, dt = (t0 + 1 < nS) ? 1 : 0;
+    CX k00 = mk<RT>(0, 0), k01 = k00, k10 = k00, k11 = k00;   // k[s][t] += x(t - l) conj(x(s - l))
+    auto mac = [](CX& acc, const CX& b, const CX& av) {        // acc += b conj(av)
+      acc.x = fma(b.x, av.x, acc.x); acc.x = fma(b.y, av.y, acc.x); acc.y = fma(b.y, av.x, acc.y); acc.y = fma(-b.x, av.y, acc.y);
+    };
+    for (int cp = 0; cp < C; cp++) {
+      const CX* ps = xs + (size_t)cp * xstride + P + s0;
+      const CX* pt = xs + (size_t)cp * xstride + P + t0;
+      CX as1 = ps[ds], bt1 = pt[dt];
+      for (int l = 0; l < P; l++) {
+        const CX as0 = ps[-l], bt0 = pt[-l];
+        mac(k00, bt0, as0); mac(k01, bt1, as0); mac(k10, bt0, as1); mac(k11, bt1, as1);
+        as1 = as0; bt1 = bt0;   // x(s0 + 1 - (l + 1)) = x(s0 - l)
+      }
+    }
+    Kq[(size_t)s0 * Lr + t0] = k00;
+    if (dt && t0 + 1 <= s0) Kq[(size_t)s0 * Lr + t0 + 1] = k01;
+    if (ds) {
+      Kq[(size_t)(s0 + 1) * Lr + t0] = k10;
+      if (dt) Kq[(size_t)(s0 + 1) * Lr + t0 + 1] = k11;
+    }
+  }
+}
+
+// one CTA per (problem, channel): diagonal bias + loading, panel Cholesky of the augmented matrix, backward substitution.
+// DUAL: the frame-domain system (K + delta_c Theta_c) z = ybar_c of size S = the utterance's estimation frames - lower, read from the
+// problem's shared K while the first panel is processed, then g_c = A z.
+template <typename RT, bool DUAL>
 __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0, int C) {
   extern __shared__ __align__(16) unsigned char smem[];
   typedef cx<RT> CX;
   const int qq = blockIdx.x / C, c = blockIdx.x - qq * C;
   const int g = problem_chain(a, q0 + qq);
-  const int L = a.L, Lr = a.Lr, n = L + 1;
-  CX* A = reinterpret_cast<CX*>(a.Rw) + ((size_t)qq * C + c) * (size_t)n * Lr;
+  const int Lcap = DUAL ? a.Sd : a.L;     // sizes the shared-memory layout (the same for every CTA of the launch)
+  const int nfr = DUAL ? est_frames_of(a, g / a.K) : 0;
+  const int L = DUAL ? max(nfr - a.lowerN, 0) : a.L;
+  const int Lr = a.Lr, n = L + 1;
+  CX* A = reinterpret_cast<CX*>(a.Rw) + ((size_t)qq * (DUAL ? C + 1 : C) + c) * a.slot;
+  const CX* Kq = reinterpret_cast<const CX*>(a.Rw) + ((size_t)qq * (C + 1) + C) * a.slot;   // DUAL only
   CX* Pn = reinterpret_cast<CX*>(smem);                   // [n][WPE_LD] current panel (rows relative to j0); row stride 17
                                                            // elements: lanes on consecutive rows hit different banks
   CX* yv = Pn + (size_t)WPE_NB * WPE_LD;                   // [L] back-substitution vector: lives inside the panel buffer (the
                                                            // back substitution only needs its first WPE_NB rows as the diagonal block)
-  RT* red = reinterpret_cast<RT*>(Pn + max((size_t)n * WPE_LD, (size_t)WPE_NB * WPE_LD + L));   // [32] (small L: yv ends past the panel)
+  RT* red = reinterpret_cast<RT*>(Pn + max((size_t)(Lcap + 1) * WPE_LD, (size_t)WPE_NB * WPE_LD + Lcap));   // [32] (small L: yv ends past the panel)
+  RT* th = red + 32;                                       // DUAL: [Lcap] theta_c(s + lower), then the C series as float2 [C][P + T]
+  const int xstride = a.P + a.T;
+  float2* xs = reinterpret_cast<float2*>(th + ((Lcap + 1) & ~1));
   const int tid = threadIdx.x;
   const RT bias = (RT)a.diagonal_bias, loadf = (RT)a.load_factor;
+  RT delta = 0;
 
-  // ---- diagonal: + diagonal_bias (calc_Rr_, :577-580), then |d| + max|d| load_factor (load_R_, :648-663)
-  RT mx = 0;
-  for (int i = tid; i < L; i += blockDim.x) {
-    CX d = A[(size_t)i * Lr + i];
-    d.x += bias;
-    mx = fmax(mx, sqrt(fma(d.x, d.x, d.y * d.y)));
+  if (DUAL) {
+    // ---- delta_c = bias + load_factor (max_i R_ii + bias), R_ii = sum_s |lags_i(s)|^2 / theta_c(s)   (calc_Rr_ :577-580, load_R_ :648-663)
+    load_series(a, g, nfr, xs, xstride);
+    RT* wi = reinterpret_cast<RT*>(Pn);                    // 1 / theta, scratch until the first panel is loaded
+    for (int s2 = tid; s2 < L; s2 += blockDim.x) {
+      const RT t = (RT)a.TH[((size_t)g * C + c) * a.Ts + s2 + a.lowerN];
+      th[s2] = t; wi[s2] = (RT)1 / t;
+    }
+    __syncthreads();
+    RT mx = 0;
+    for (int i = tid; i < a.L; i += blockDim.x) {
+      const float2* pi = xs + (size_t)(i / a.P) * xstride + a.P - (i % a.P);
+      RT acc = 0;
+      for (int s2 = 0; s2 < L; s2++) { const float2 v = pi[s2]; acc = fma(fma((RT)v.x, (RT)v.x, (RT)v.y * (RT)v.y), wi[s2], acc); }
+      mx = fmax(mx, acc + bias);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, red[w]);
+    delta = bias + mx * loadf;
+    __syncthreads();                                       // wi is dead: the panel buffer may be overwritten
+  } else {
+    // ---- diagonal: + diagonal_bias (calc_Rr_, :577-580), then |d| + max|d| load_factor (load_R_, :648-663)
+    RT mx = 0;
+    for (int i = tid; i < L; i += blockDim.x) {
+      CX d = A[(size_t)i * Lr + i];
+      d.x += bias;
+      mx = fmax(mx, sqrt(fma(d.x, d.x, d.y * d.y)));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, red[w]);
+    for (int i = tid; i < L; i += blockDim.x) {
+      CX d = A[(size_t)i * Lr + i];
+      d.x += bias;
+      A[(size_t)i * Lr + i] = mk<RT>(sqrt(fma(d.x, d.x, d.y * d.y)) + mx * loadf, 0);
+    }
+    __syncthreads();
   }
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) red[tid >> 5] = mx;
-  __syncthreads();
-  mx = 0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, red[w]);
-  for (int i = tid; i < L; i += blockDim.x) {
-    CX d = A[(size_t)i * Lr + i];
-    d.x += bias;
-    A[(size_t)i * Lr + i] = mk<RT>(sqrt(fma(d.x, d.x, d.y * d.y)) + mx * loadf, 0);
-  }
-  __syncthreads();
+  // entry (row, col), col <= row, of the system before any update: DUAL reads K, the loading and the right-hand side; row L is the
+  // augmented row conj(rhs) = x_c(s + lower)
+  auto src0 = [&](int row, int col) -> CX {
+    if (!DUAL) return A[(size_t)row * Lr + col];
+    if (row == L) {
+      if (col == L) return mk<RT>(0, 0);
+      const float2 v = xs[(size_t)c * xstride + a.P + col + a.lowerN];
+      return mk<RT>((RT)v.x, (RT)v.y);
+    }
+    CX v = Kq[(size_t)row * Lr + col];
+    if (row == col) { v.x = fma(delta, th[row], v.x); v.y = 0; }
+    return v;
+  };
 
   bool bad = false;
   for (int j0 = 0; j0 < L; j0 += WPE_NB) {
@@ -248,7 +355,7 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     // ---- load the panel
     for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
       const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      Pn[r * WPE_LD + jj] = (jj < nb && jj <= r) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
+      Pn[r * WPE_LD + jj] = (jj < nb && jj <= r) ? ((DUAL && j0 == 0) ? src0(r, jj) : A[(size_t)(j0 + r) * Lr + j0 + jj]) : mk<RT>(0, 0);
     }
     __syncthreads();
     // ---- factor the nb x nb diagonal block with ONE warp (lane = row, __syncwarp between the dependent steps) ...
@@ -330,7 +437,11 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
         }
         auto upd = [&](int q, int pcol, const CX& sv) {
           const int row = ri + q * nt4, col = rk + pcol * nt4;
-          if (row < nt && col < nt) { CX* dst = A + (size_t)(j1 + row) * Lr + j1 + col; CX v = *dst; v.x += sv.x; v.y += sv.y; *dst = v; }
+          if (row < nt && col < nt) {
+            CX* dst = A + (size_t)(j1 + row) * Lr + j1 + col;
+            CX v = (DUAL && j0 == 0) ? src0(j1 + row, j1 + col) : *dst;
+            v.x += sv.x; v.y += sv.y; *dst = v;
+          }
         };
         if (diag) {
 #pragma unroll
@@ -370,13 +481,25 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     }
     __syncthreads();
   }
-  for (int j = tid; j < L; j += blockDim.x) a.Gf[((size_t)g * C + c) * L + j] = make_float2((float)yv[j].x, (float)yv[j].y);
+  if (DUAL) {   // g_c = A z: g_i = sum_s lags_i(s) z_s
+    for (int i = tid; i < a.L; i += blockDim.x) {
+      const float2* pi = xs + (size_t)(i / a.P) * xstride + a.P - (i % a.P);
+      CX acc = mk<RT>(0, 0);
+      for (int s2 = 0; s2 < L; s2++) {
+        const float2 v = pi[s2]; const CX z = yv[s2];
+        acc.x = fma((RT)v.x, z.x, acc.x); acc.x = fma(-(RT)v.y, z.y, acc.x); acc.y = fma((RT)v.x, z.y, acc.y); acc.y = fma((RT)v.y, z.x, acc.y);
+      }
+      a.Gf[((size_t)g * C + c) * a.L + i] = make_float2((float)acc.x, (float)acc.y);
+    }
+  } else {
+    for (int j = tid; j < L; j += blockDim.x) a.Gf[((size_t)g * C + c) * L + j] = make_float2((float)yv[j].x, (float)yv[j].y);
+  }
 }
 
 }  // namespace
 
-size_t wpe_workspace_bytes(int C, int L, int Lr, int chunk, int fp32) {
-  return (size_t)chunk * C * (size_t)(L + 1) * Lr * (fp32 ? sizeof(float2) : sizeof(double2));
+size_t wpe_workspace_bytes(int C, size_t slot, int chunk, int fp32) {
+  return (size_t)chunk * (C + 1) * slot * (fp32 ? sizeof(float2) : sizeof(double2));   // C systems + the shared K of the frame-domain form
 }
 
 template <typename RT>
@@ -393,16 +516,22 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
     e = cudaMemsetAsync(a.Gf, 0, (size_t)a.G * C * a.L * sizeof(float2), st);
     if (e != cudaSuccess) return e;
   }
+  const bool dual = a.form == 1;
   const int xstride = a.P + a.T;
+  const int Lcap = dual ? a.Sd : a.L;
+  if ((size_t)(Lcap + 1) * a.Lr > a.slot || Lcap + 1 > a.Lr) return cudaErrorInvalidValue;
   const size_t sm_resid = ((size_t)C * xstride + (size_t)C * a.L) * sizeof(float2);
-  const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (size_t)C * a.T * sizeof(RT);
-  const size_t sm_chol = std::max((size_t)(a.L + 1) * WPE_LD, (size_t)WPE_NB * WPE_LD + a.L) * sizeof(cx<RT>) + 32 * sizeof(RT);
+  const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (dual ? 0 : (size_t)C * a.T * sizeof(RT));
+  const size_t sm_chol = std::max((size_t)(Lcap + 1) * WPE_LD, (size_t)WPE_NB * WPE_LD + Lcap) * sizeof(cx<RT>) + 32 * sizeof(RT) +
+                         (dual ? (size_t)((Lcap + 1) & ~1) * sizeof(RT) + (size_t)C * xstride * sizeof(float2) : 0);
   if (sm_resid > 200 * 1024 || sm_corr > 200 * 1024 || sm_chol > 200 * 1024) return cudaErrorInvalidValue;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_wpe_chol<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol)) != cudaSuccess) return e;
+  void (*chol)(WpeArgs, int, int) = dual ? k_wpe_chol<RT, true> : k_wpe_chol<RT, false>;
+  if ((e = cudaFuncSetAttribute(chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol)) != cudaSuccess) return e;
   void (*corr)(WpeArgs, int) = nullptr;
-  switch (C) {
+  if (dual) corr = k_wpe_gram_dual<RT>;
+  else switch (C) {
     case 1: corr = k_wpe_corr<1, RT>; break;
     case 2: corr = k_wpe_corr<2, RT>; break;
     case 3: corr = k_wpe_corr<3, RT>; break;
@@ -415,21 +544,39 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
   }
   if ((e = cudaFuncSetAttribute(corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_corr)) != cudaSuccess) return e;
   const int nprob = a.U * a.nbins;
-  const int split = 8;
-  for (int it = 0; it < (a.apply_only ? 0 : a.iterations); it++) {
-    k_wpe_resid<0><<<nprob, 128, sm_resid, st>>>(a);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    (*launches)++;
-    for (int q0 = 0; q0 < nprob; q0 += chunk) {
+  const int iters = a.apply_only ? 0 : a.iterations;
+  if (dual) {
+    // chunk-major: K of a problem is formed once and serves every channel and every iteration (problems are independent, so
+    // running the iterations of one chunk back to back is the same computation as estimate_Gn_'s iteration-major loop)
+    for (int q0 = 0; q0 < nprob && iters > 0; q0 += chunk) {
       const int nq = (nprob - q0 < chunk) ? nprob - q0 : chunk;
-      corr<<<dim3(split, nq), WPE_CORR_THREADS, sm_corr, st>>>(a, q0);
+      corr<<<dim3(4, nq), WPE_CORR_THREADS, sm_corr, st>>>(a, q0);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
-      k_wpe_chol<RT><<<nq * C, WPE_CHOL_THREADS, sm_chol, st>>>(a, q0, C);
+      (*launches)++;
+      for (int it = 0; it < iters; it++) {
+        k_wpe_resid<0><<<nq, 128, sm_resid, st>>>(a, q0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        chol<<<nq * C, WPE_CHOL_THREADS, sm_chol, st>>>(a, q0, C);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        (*launches) += 2;
+      }
+    }
+  } else {
+    for (int it = 0; it < iters; it++) {
+      k_wpe_resid<0><<<nprob, 128, sm_resid, st>>>(a, 0);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
-      (*launches) += 2;
+      (*launches)++;
+      for (int q0 = 0; q0 < nprob; q0 += chunk) {
+        const int nq = (nprob - q0 < chunk) ? nprob - q0 : chunk;
+        corr<<<dim3(8, nq), WPE_CORR_THREADS, sm_corr, st>>>(a, q0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        chol<<<nq * C, WPE_CHOL_THREADS, sm_chol, st>>>(a, q0, C);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        (*launches) += 2;
+      }
     }
   }
-  k_wpe_resid<1><<<a.G, 128, sm_resid, st>>>(a);
+  k_wpe_resid<1><<<a.G, 128, sm_resid, st>>>(a, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   (*launches)++;
   return cudaSuccess;

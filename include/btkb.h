@@ -283,6 +283,10 @@ int btkb_last_timing(btkb_pipeline* p, float* out5);
 /* device pointers for zero-copy consumers (torch tensors via from_dlpack / data_ptr): X, Y, time */
 /* device time (ms) of the last WPE pass (estimation + output stage) */
 int btkb_last_timing_wpe(btkb_pipeline* p, float* ms);
+/* which normal equations the last estimation solved: 0 = lag-domain (L x L, L = C x lags, what estimate_Gn_ builds,
+ * dereverberation.cc:553-690), 1 = frame-domain (S x S, S = estimation frames - lower; the same filters through the push-through
+ * identity, chosen per batch when S < L).  The environment variable BTKB_WPE_FORM=lag|frame, read at create, pins one. */
+int btkb_last_wpe_form(btkb_pipeline* p, int* form);
 int btkb_device_pointers(btkb_pipeline* p, void** X, void** Y, void** time_out);
 
 #ifdef __cplusplus

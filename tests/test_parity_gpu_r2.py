@@ -504,3 +504,73 @@ def test_reset_and_caller_supplied_stream(capi, protos):
     p.stream_submit(np.ascontiguousarray(x[:, :, :20 * D])); a2 = p.fetch_subband()
     assert np.array_equal(a1, a2) and np.array_equal(a1[:, :, :], Y0[:, :a1.shape[1], :])
     p.close()
+
+
+# ---- WPE: the frame-domain form of the normal equations (btkb_wpe.cu: k_wpe_gram_dual, k_wpe_chol<DUAL>)
+
+def _wpe_snapshots(capi, protos, C, M, x, kw, form, monkeypatch, lengths=None, U=1):
+    kw = dict(kw)
+    start, end = kw.pop("start_frame_no", 0), kw.pop("end_frame_no", -1)
+    if form is None:
+        monkeypatch.delenv("BTKB_WPE_FORM", raising=False)
+    else:
+        monkeypatch.setenv("BTKB_WPE_FORM", form)
+    h, g = protos[M]
+    p = capi.Pipeline(C, M, 4, 1, beamformer=capi.BF_DS, max_utterances=U, max_samples=x.shape[-1], wpe=kw)
+    p.set_prototypes(h, g)
+    p.submit(x if x.ndim == 3 else x[None], lengths)
+    p.run_analysis(); p.run_wpe(start, end)
+    out = p.fetch_snapshots(), p.get_wpe_filter(), p.last_wpe_form()
+    p.close()
+    return out
+
+
+@pytest.mark.gpu
+def test_wpe_frame_domain_form_reproduces_the_reference_goldens(capi, protos, monkeypatch):
+    """estimate_Gn_ (dereverberation.cc:553-690) solves (A Th^-1 A^H + delta I) g = A Th^-1 ybar, an L x L system; the frame-domain
+    form g = A (A^H A + delta Th)^-1 ybar is the same filter through an S x S system.  Pinned to either form the product reproduces
+    the compiled reference's dereverberated snapshots (goldens of tests/golden/make_golden_wpe.py, S > L here) and the two forms
+    agree with each other far inside the parity budget — including estimate_filter(start, end) windows, lower > 0 and a band limit."""
+    from test_oracle import WPE_A, WPE_B, WPE_C, WPE_8
+    g = load_golden("wpe_c4_m256")
+    for tag, kw in (("a", WPE_A), ("b", WPE_B), ("c", WPE_C)):
+        Xl, Gl, fl = _wpe_snapshots(capi, protos, 4, 256, g["x"], kw, "lag", monkeypatch)
+        Xf, Gf, ff = _wpe_snapshots(capi, protos, 4, 256, g["x"], kw, "frame", monkeypatch)
+        assert (fl, ff) == (0, 1)
+        assert rel_l2(Xl[0], g["X" + tag]) < TOL and rel_l2(Xf[0], g["X" + tag]) < TOL, tag
+        assert rel_l2(Xf[0], Xl[0]) < 2e-6 and rel_l2(Gf, Gl) < 1e-4, (tag, rel_l2(Xf[0], Xl[0]), rel_l2(Gf, Gl))
+    g = load_golden("wpe_c8_m512")
+    Xf, Gf, ff = _wpe_snapshots(capi, protos, 8, 512, g["x"], WPE_8, "frame", monkeypatch)
+    assert ff == 1 and rel_l2(Xf[0], g["Xa"]) < TOL
+
+
+@pytest.mark.gpu
+def test_wpe_picks_the_smaller_system_per_batch(capi, protos, monkeypatch):
+    """Utterances shorter than the filter (S = frames - lower < L = C x lags — configs[4]'s 5 s utterances against 8 x 33 taps) are
+    served in the frame-domain form, longer ones in the lag-domain form; ragged batch, every utterance against the fp64
+    restatement of the reference (dereverberation.cc:441-700), filters included, and against the lag-domain form pinned."""
+    from oracle import restate
+    from distant_speech_recognition_b200 import synthetic
+    M, C, U, n = 256, 4, 3, 3300
+    K = M // 2 + 1
+    h, _ = protos[M]
+    X, _ = synthetic.make_batch(U, C, n, first=40)
+    lengths = np.array([n, n - 700, 40], np.int32)           # the last one: a handful of frames
+    wpe = dict(lower_num=1, upper_num=9, iterations_num=2, load_db=-18.0, band_width=0.0, diagonal_bias=1e-4)   # L = 36, S <= 28
+    Xa, Ga, fa = _wpe_snapshots(capi, protos, C, M, X, wpe, None, monkeypatch, lengths, U)
+    Xl, Gl, fl = _wpe_snapshots(capi, protos, C, M, X, wpe, "lag", monkeypatch, lengths, U)
+    assert (fa, fl) == (1, 0)
+    for u in range(U):
+        xu = X[u][:, : lengths[u]]
+        Xs = np.stack([restate.analysis(xu[c], h, M, 4, 1) for c in range(C)], axis=1)
+        Xw, G, used = restate.wpe(Xs, samplerate=FS, **wpe)
+        T = Xs.shape[0]
+        assert rel_l2(Xa[u][:T], Xw[:, :, :K]) < TOL and rel_l2(Xl[u][:T], Xw[:, :, :K]) < TOL, u
+        if np.abs(G).max() > 0:
+            assert rel_l2(Ga[u], np.transpose(G, (1, 0, 2))) < 1e-3, u
+        assert rel_l2(Xa[u][:T], Xl[u][:T]) < 2e-6, u
+    # a long batch goes back to the lag-domain form on the same pipeline settings
+    n2 = 9000
+    X2, _ = synthetic.make_batch(1, C, n2, first=40)
+    _, _, f2 = _wpe_snapshots(capi, protos, C, M, X2, wpe, None, monkeypatch)
+    assert f2 == 0
