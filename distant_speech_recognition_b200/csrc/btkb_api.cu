@@ -41,7 +41,7 @@ struct btkb_pipeline {
   double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
   // multi-channel WPE (lazily sized at create when cfg.wpe.enabled)
   float2 *d_wS = nullptr, *d_wG = nullptr; void* d_wR = nullptr; float* d_wTH = nullptr; int* d_werr = nullptr;
-  int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_Ts = 0, wpe_nbins = 0, wpe_U = 0, wpe_form = -1, wpe_last_form = -1; size_t wpe_slot = 0; bool have_wpe = false;
+  int wpe_P = 0, wpe_L = 0, wpe_Lr = 0, wpe_chunk = 0, wpe_chunk_frame = 0, wpe_chol_threads = 0, wpe_Ts = 0, wpe_nbins = 0, wpe_U = 0, wpe_form = -1, wpe_last_form = -1; size_t wpe_slot = 0; bool have_wpe = false;
   cudaEvent_t wev[2] = {nullptr, nullptr};
   // SOS batch beamformers (lazily allocated by the first btkb_sos_accumulate_*)
   double2 *d_sosR = nullptr, *d_sosWd = nullptr; double* d_sosCnt = nullptr; float *d_sosWtu = nullptr, *d_sosMask = nullptr; double* d_sosLab = nullptr;
@@ -215,11 +215,16 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
     const char* ce = getenv("BTKB_WPE_CHUNK");
     p->wpe_chunk = ce ? std::max(1, atoi(ce)) : 55;   // 55 x 8 = 440 Cholesky CTAs fit one wave at 3 CTAs/SM x 148 SMs (56 spills 4 CTAs into a second wave: 663 -> 862 ms measured)
     p->wpe_chunk = std::min(p->wpe_chunk, p->Ucap * p->wpe_nbins);
+    // frame-domain form: 128-thread CTAs, 4 per SM -> 592 systems in flight
+    const char* cf = getenv("BTKB_WPE_CHUNK_FRAME");
+    p->wpe_chunk_frame = std::min(cf ? std::max(1, atoi(cf)) : std::max(1, 592 / C), p->Ucap * p->wpe_nbins);
+    const char* ct = getenv("BTKB_WPE_CHOL_THREADS");
+    p->wpe_chol_threads = ct ? std::min(256, std::max(32, atoi(ct) / 32 * 32)) : 0;
     for (auto& ev : p->wev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     A((void**)&p->d_wS, (size_t)p->Ucap * p->K * C * p->wpe_Ts * sizeof(float2));
     A((void**)&p->d_wTH, (size_t)p->Ucap * p->K * C * p->wpe_Ts * sizeof(float));
     A((void**)&p->d_wG, (size_t)p->Ucap * p->K * C * p->wpe_L * sizeof(float2));
-    A((void**)&p->d_wR, wpe_workspace_bytes(C, p->wpe_slot, p->wpe_chunk, cfg->wpe.fp32_normal_equations));
+    A((void**)&p->d_wR, wpe_workspace_bytes(C, p->wpe_slot, std::max(p->wpe_chunk, p->wpe_chunk_frame), cfg->wpe.fp32_normal_equations));
     A((void**)&p->d_werr, sizeof(int));
   }
   if (e == cudaSuccess && p->Cp != C) {   // the padded channel rows stay zero for the life of the pipeline: no kernel writes them
@@ -598,7 +603,7 @@ static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no, bool a
   a.est_frames = (end_frame_no < 0) ? -1 : std::max(0, end_frame_no - std::max(start_frame_no, 0));   // fill_buffer_ (:500-534) never skips input frames
   a.load_factor = (float)pow(10.0, w.load_db / 10.0); a.diagonal_bias = (float)w.diagonal_bias;
   a.apply_only = apply_only ? 1 : 0;
-  a.slot = p->wpe_slot;
+  a.slot = p->wpe_slot; a.chunk_frame = p->wpe_chunk_frame; a.chol_threads = p->wpe_chol_threads;
   a.Sd = std::max(((a.est_frames >= 0) ? std::min(a.T, a.est_frames) : a.T) - a.lowerN, 0);
   a.form = (p->wpe_form >= 0) ? p->wpe_form : (a.Sd < a.L ? 1 : 0);   // the frame-domain system has S <= Sd rows, the lag-domain one L
   CK(cudaMemsetAsync(p->d_werr, 0, sizeof(int), p->stream));

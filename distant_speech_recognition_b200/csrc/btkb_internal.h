@@ -108,6 +108,8 @@ struct WpeArgs {
   size_t slot;           // elements per slot (>= (L+1) Lr; >= (Sd+1) Lr when the frame-domain form may be used)
   int form;              // 0: lag-domain normal equations (L x L), 1: frame-domain (S x S, S = estimation frames - lower)
   int Sd;                // frame-domain form: largest S in the batch
+  int chunk_frame;       // host side: problems per launch in the frame-domain form (`chunk` of launch_wpe serves the lag-domain form)
+  int chol_threads;      // host side: CTA size of k_wpe_chol (0: 256 lag-domain, 128 frame-domain)
   int* err_flag;         // set to 1 when a Cholesky pivot is not positive
   int U, C, T, Ts, K, G, Gp, D, laN, pdA;
   int lowerN, P, L, Lr, iterations, nbins, est_frames;

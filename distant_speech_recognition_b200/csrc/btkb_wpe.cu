@@ -264,6 +264,17 @@ __global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_gram_dual(WpeArgs a, i
   }
 }
 
+// elements of the panel buffer: the panel, or the first WPE_NB rows + the back-substitution vector, or (frame-domain form) the
+// nseries float2 series values that alias it outside the factorisation
+template <typename RT>
+__host__ __device__ inline size_t chol_region0(int Lcap, int nseries) {
+  size_t e = (size_t)(Lcap + 1) * WPE_LD;
+  const size_t e2 = (size_t)WPE_NB * WPE_LD + Lcap, e3 = ((size_t)nseries * sizeof(float2) + sizeof(cx<RT>) - 1) / sizeof(cx<RT>);
+  if (e2 > e) e = e2;
+  if (e3 > e) e = e3;
+  return e;
+}
+
 // one CTA per (problem, channel): diagonal bias + loading, panel Cholesky of the augmented matrix, backward substitution.
 // DUAL: the frame-domain system (K + delta_c Theta_c) z = ybar_c of size S = the utterance's estimation frames - lower, read from the
 // problem's shared K while the first panel is processed, then g_c = A z.
@@ -283,18 +294,28 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
                                                            // elements: lanes on consecutive rows hit different banks
   CX* yv = Pn + (size_t)WPE_NB * WPE_LD;                   // [L] back-substitution vector: lives inside the panel buffer (the
                                                            // back substitution only needs its first WPE_NB rows as the diagonal block)
-  RT* red = reinterpret_cast<RT*>(Pn + max((size_t)(Lcap + 1) * WPE_LD, (size_t)WPE_NB * WPE_LD + Lcap));   // [32] (small L: yv ends past the panel)
-  RT* th = red + 32;                                       // DUAL: [Lcap] theta_c(s + lower), then the C series as float2 [C][P + T]
   const int xstride = a.P + a.T;
-  float2* xs = reinterpret_cast<float2*>(th + ((Lcap + 1) & ~1));
+  RT* red = reinterpret_cast<RT*>(Pn + chol_region0<RT>(Lcap, DUAL ? C * xstride : 0));   // [32]
+  RT* dinv = red + 16;                                     // [WPE_NB] 1 / L_jj of the current diagonal block
+  unsigned char* tri = reinterpret_cast<unsigned char*>(red + 32);   // [136][2] (row, column) of the e-th entry of a lower triangle
+  RT* th = reinterpret_cast<RT*>(tri + 272);               // DUAL: [Lcap] theta_c(s + lower)
+  CX* zs = reinterpret_cast<CX*>(th + ((Lcap + 1) & ~1));  // DUAL: [Lcap] the solution z (and 1 / theta as scratch in the prologue)
+  float2* xs = reinterpret_cast<float2*>(Pn);              // DUAL: the C series [C][P + T]; ALIASES the panel buffer — alive only before
+                                                           // the first panel is loaded (delta) and after the back substitution (g = A z)
   const int tid = threadIdx.x;
   const RT bias = (RT)a.diagonal_bias, loadf = (RT)a.load_factor;
   RT delta = 0;
+  for (int e = tid; e < 136; e += blockDim.x) {
+    int rr = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while ((rr + 1) * (rr + 2) / 2 <= e) rr++;
+    while (rr * (rr + 1) / 2 > e) rr--;
+    tri[2 * e] = (unsigned char)rr; tri[2 * e + 1] = (unsigned char)(e - rr * (rr + 1) / 2);
+  }
 
   if (DUAL) {
     // ---- delta_c = bias + load_factor (max_i R_ii + bias), R_ii = sum_s |lags_i(s)|^2 / theta_c(s)   (calc_Rr_ :577-580, load_R_ :648-663)
     load_series(a, g, nfr, xs, xstride);
-    RT* wi = reinterpret_cast<RT*>(Pn);                    // 1 / theta, scratch until the first panel is loaded
+    RT* wi = reinterpret_cast<RT*>(zs);                    // 1 / theta
     for (int s2 = tid; s2 < L; s2 += blockDim.x) {
       const RT t = (RT)a.TH[((size_t)g * C + c) * a.Ts + s2 + a.lowerN];
       th[s2] = t; wi[s2] = (RT)1 / t;
@@ -313,7 +334,7 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     mx = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, red[w]);
     delta = bias + mx * loadf;
-    __syncthreads();                                       // wi is dead: the panel buffer may be overwritten
+    __syncthreads();                                       // the series are dead: the panel buffer may be overwritten
   } else {
     // ---- diagonal: + diagonal_bias (calc_Rr_, :577-580), then |d| + max|d| load_factor (load_R_, :648-663)
     RT mx = 0;
@@ -340,7 +361,7 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     if (!DUAL) return A[(size_t)row * Lr + col];
     if (row == L) {
       if (col == L) return mk<RT>(0, 0);
-      const float2 v = xs[(size_t)c * xstride + a.P + col + a.lowerN];
+      const float2 v = a.S[((size_t)g * C + c) * a.Ts + col + a.lowerN];
       return mk<RT>((RT)v.x, (RT)v.y);
     }
     CX v = Kq[(size_t)row * Lr + col];
@@ -358,41 +379,48 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
       Pn[r * WPE_LD + jj] = (jj < nb && jj <= r) ? ((DUAL && j0 == 0) ? src0(r, jj) : A[(size_t)(j0 + r) * Lr + j0 + jj]) : mk<RT>(0, 0);
     }
     __syncthreads();
-    // ---- factor the nb x nb diagonal block with ONE warp (lane = row, __syncwarp between the dependent steps) ...
+    // ---- factor the nb x nb diagonal block with ONE warp (no CTA barrier inside): per column a scaling by 1 / sqrt(pivot), then the
+    // rank-one update of the remaining triangle with its (row, column) pairs dealt out to the 32 lanes
     if (tid < 32) {
-      const int r = tid;
       for (int jj = 0; jj < nb; jj++) {
         const RT dj = Pn[jj * WPE_LD + jj].x;
         if (!(dj > (RT)0)) bad = true;
-        const RT inv = (RT)1 / sqrt(fmax(dj, (RT)1e-30));
+        const RT inv = rsqrt(fmax(dj, (RT)1e-30));
         __syncwarp();   // every lane has read the pivot before its owner overwrites it
-        if (r < nb) {
-          if (r == jj) Pn[r * WPE_LD + jj] = mk<RT>(dj * inv, 0);
-          else if (r > jj) { CX v = Pn[r * WPE_LD + jj]; Pn[r * WPE_LD + jj] = mk<RT>(v.x * inv, v.y * inv); }
+        if (tid >= jj && tid < nb) {
+          if (tid == jj) { Pn[tid * WPE_LD + jj] = mk<RT>(dj * inv, 0); dinv[jj] = inv; }
+          else { const CX v = Pn[tid * WPE_LD + jj]; Pn[tid * WPE_LD + jj] = mk<RT>(v.x * inv, v.y * inv); }
         }
         __syncwarp();
-        if (r < nb && r > jj) {
-          const CX lij = Pn[r * WPE_LD + jj];
-          for (int kk = jj + 1; kk <= r; kk++) {
-            CX v = Pn[r * WPE_LD + kk];
-            cmsubc(v, lij, Pn[kk * WPE_LD + jj]);
-            if (kk == r) v.y = 0;
-            Pn[r * WPE_LD + kk] = v;
-          }
+        const int m = nb - 1 - jj;
+        for (int e = tid; e < m * (m + 1) / 2; e += 32) {
+          const int r = jj + 1 + tri[2 * e], kk = jj + 1 + tri[2 * e + 1];
+          CX v = Pn[r * WPE_LD + kk];
+          cmsubc(v, Pn[r * WPE_LD + jj], Pn[kk * WPE_LD + jj]);
+          if (kk == r) v.y = 0;
+          Pn[r * WPE_LD + kk] = v;
         }
         __syncwarp();
       }
     }
     __syncthreads();
-    // ---- ... then the rows below it are independent: L21 = A21 L11^-H, one thread per row, no barrier (the earlier
-    // column-by-column sweep over the whole panel cost three CTA barriers per column, ~800 per matrix)
+    // ---- ... then the rows below it are independent: L21 = A21 L11^-H, one thread per row held in registers, right-looking (once
+    // x_jj is final the remaining entries of the row take their updates independently of one another), no barrier
     for (int r = nb + tid; r < nrows; r += blockDim.x) {
       CX* pr = Pn + (size_t)r * WPE_LD;
-      for (int jj = 0; jj < nb; jj++) {
-        CX v = pr[jj];
-        for (int q = 0; q < jj; q++) cmsubc(v, pr[q], Pn[jj * WPE_LD + q]);
-        const RT inv = (RT)1 / Pn[jj * WPE_LD + jj].x;
-        pr[jj] = mk<RT>(v.x * inv, v.y * inv);
+      CX v[WPE_NB];
+#pragma unroll
+      for (int jj = 0; jj < WPE_NB; jj++) v[jj] = pr[jj];
+#pragma unroll
+      for (int jj = 0; jj < WPE_NB; jj++) {
+        if (jj < nb) {
+          const RT inv = dinv[jj];
+          v[jj] = mk<RT>(v[jj].x * inv, v[jj].y * inv);
+#pragma unroll
+          for (int q = jj + 1; q < WPE_NB; q++)
+            if (q < nb) cmsubc(v[q], v[jj], Pn[q * WPE_LD + jj]);
+          pr[jj] = v[jj];
+        }
       }
     }
     __syncthreads();
@@ -465,12 +493,16 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
       Db[r * WPE_LD + jj] = (jj <= r && jj < nb) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {   // column sweep: once g_jj is final, the lanes q < jj take y_q -= g_jj conj(L[jj][q])
+      const RT invd = (tid < nb) ? (RT)1 / Db[tid * WPE_LD + tid].x : (RT)0;
       for (int jj = nb - 1; jj >= 0; jj--) {
-        CX s = yv[j0 + jj];
-        for (int kk = jj + 1; kk < nb; kk++) cmsubc(s, yv[j0 + kk], Db[kk * WPE_LD + jj]);  // s -= g_kk conj(L[kk][jj])
-        const RT inv = (RT)1 / Db[jj * WPE_LD + jj].x;
-        yv[j0 + jj] = mk<RT>(s.x * inv, s.y * inv);
+        const CX yj = yv[j0 + jj];
+        const RT inv = __shfl_sync(0xffffffffu, invd, jj);
+        const CX gj = mk<RT>(yj.x * inv, yj.y * inv);
+        __syncwarp();
+        if (tid == jj) yv[j0 + jj] = gj;
+        else if (tid < jj) { CX sv = yv[j0 + tid]; cmsubc(sv, gj, Db[jj * WPE_LD + tid]); yv[j0 + tid] = sv; }
+        __syncwarp();
       }
     }
     __syncthreads();
@@ -482,11 +514,15 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     __syncthreads();
   }
   if (DUAL) {   // g_c = A z: g_i = sum_s lags_i(s) z_s
+    for (int j = tid; j < L; j += blockDim.x) zs[j] = yv[j];
+    __syncthreads();
+    load_series(a, g, nfr, xs, xstride);
+    __syncthreads();
     for (int i = tid; i < a.L; i += blockDim.x) {
       const float2* pi = xs + (size_t)(i / a.P) * xstride + a.P - (i % a.P);
       CX acc = mk<RT>(0, 0);
       for (int s2 = 0; s2 < L; s2++) {
-        const float2 v = pi[s2]; const CX z = yv[s2];
+        const float2 v = pi[s2]; const CX z = zs[s2];
         acc.x = fma((RT)v.x, z.x, acc.x); acc.x = fma(-(RT)v.y, z.y, acc.x); acc.y = fma((RT)v.x, z.y, acc.y); acc.y = fma((RT)v.y, z.x, acc.y);
       }
       a.Gf[((size_t)g * C + c) * a.L + i] = make_float2((float)acc.x, (float)acc.y);
@@ -522,8 +558,10 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
   if ((size_t)(Lcap + 1) * a.Lr > a.slot || Lcap + 1 > a.Lr) return cudaErrorInvalidValue;
   const size_t sm_resid = ((size_t)C * xstride + (size_t)C * a.L) * sizeof(float2);
   const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (dual ? 0 : (size_t)C * a.T * sizeof(RT));
-  const size_t sm_chol = std::max((size_t)(Lcap + 1) * WPE_LD, (size_t)WPE_NB * WPE_LD + Lcap) * sizeof(cx<RT>) + 32 * sizeof(RT) +
-                         (dual ? (size_t)((Lcap + 1) & ~1) * sizeof(RT) + (size_t)C * xstride * sizeof(float2) : 0);
+  const size_t sm_chol = chol_region0<RT>(Lcap, dual ? C * xstride : 0) * sizeof(cx<RT>) + 32 * sizeof(RT) + 272 +
+                         (dual ? (size_t)((Lcap + 1) & ~1) * sizeof(RT) + (size_t)Lcap * sizeof(cx<RT>) : 0);
+  const int chol_threads = a.chol_threads > 0 ? a.chol_threads : (dual ? 128 : WPE_CHOL_THREADS);
+  if (dual) chunk = a.chunk_frame > 0 ? a.chunk_frame : chunk;
   if (sm_resid > 200 * 1024 || sm_corr > 200 * 1024 || sm_chol > 200 * 1024) return cudaErrorInvalidValue;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
@@ -556,7 +594,7 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
       for (int it = 0; it < iters; it++) {
         k_wpe_resid<0><<<nq, 128, sm_resid, st>>>(a, q0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        chol<<<nq * C, WPE_CHOL_THREADS, sm_chol, st>>>(a, q0, C);
+        chol<<<nq * C, chol_threads, sm_chol, st>>>(a, q0, C);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         (*launches) += 2;
       }
@@ -570,7 +608,7 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
         const int nq = (nprob - q0 < chunk) ? nprob - q0 : chunk;
         corr<<<dim3(8, nq), WPE_CORR_THREADS, sm_corr, st>>>(a, q0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        chol<<<nq * C, WPE_CHOL_THREADS, sm_chol, st>>>(a, q0, C);
+        chol<<<nq * C, chol_threads, sm_chol, st>>>(a, q0, C);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         (*launches) += 2;
       }
