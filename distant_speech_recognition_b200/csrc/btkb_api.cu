@@ -215,9 +215,11 @@ int btkb_create(const btkb_config* cfg, btkb_pipeline** out) {
     const char* ce = getenv("BTKB_WPE_CHUNK");
     p->wpe_chunk = ce ? std::max(1, atoi(ce)) : 55;   // 55 x 8 = 440 Cholesky CTAs fit one wave at 3 CTAs/SM x 148 SMs (56 spills 4 CTAs into a second wave: 663 -> 862 ms measured)
     p->wpe_chunk = std::min(p->wpe_chunk, p->Ucap * p->wpe_nbins);
-    // frame-domain form: 128-thread CTAs, 4 per SM -> 592 systems in flight
+    // frame-domain form: 128-thread CTAs, 4 per SM -> 592 systems in flight; eight such waves per launch (77.9 ms per 8 utterances of configs[4] against 79.9 with four and 83.8 with two)
     const char* cf = getenv("BTKB_WPE_CHUNK_FRAME");
-    p->wpe_chunk_frame = std::min(cf ? std::max(1, atoi(cf)) : std::max(1, 592 / C), p->Ucap * p->wpe_nbins);
+    const size_t esz = cfg->wpe.fp32_normal_equations ? sizeof(float2) : sizeof(double2);
+    const int fit = (int)std::max<size_t>(1, ((size_t)6 << 30) / ((size_t)(C + 1) * p->wpe_slot * esz));   // workspace <= 6 GiB
+    p->wpe_chunk_frame = std::min(std::min(cf ? std::max(1, atoi(cf)) : std::max(1, 4736 / C), fit), p->Ucap * p->wpe_nbins);
     const char* ct = getenv("BTKB_WPE_CHOL_THREADS");
     p->wpe_chol_threads = ct ? std::min(256, std::max(32, atoi(ct) / 32 * 32)) : 0;
     for (auto& ev : p->wev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
@@ -604,6 +606,7 @@ static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no, bool a
   a.load_factor = (float)pow(10.0, w.load_db / 10.0); a.diagonal_bias = (float)w.diagonal_bias;
   a.apply_only = apply_only ? 1 : 0;
   a.slot = p->wpe_slot; a.chunk_frame = p->wpe_chunk_frame; a.chol_threads = p->wpe_chol_threads;
+  { const char* pf = getenv("BTKB_WPE_PREFETCH"); a.prefetch = pf ? atoi(pf) : 1; }
   a.Sd = std::max(((a.est_frames >= 0) ? std::min(a.T, a.est_frames) : a.T) - a.lowerN, 0);
   a.form = (p->wpe_form >= 0) ? p->wpe_form : (a.Sd < a.L ? 1 : 0);   // the frame-domain system has S <= Sd rows, the lag-domain one L
   CK(cudaMemsetAsync(p->d_werr, 0, sizeof(int), p->stream));

@@ -216,51 +216,56 @@ __global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_corr(WpeArgs a, int q0
   }
 }
 
-// Frame-domain form: K[s][s'] = sum_i conj(lags_i(s)) lags_i(s') (lower triangle, s' <= s) of the problems [q0, q0 + gridDim.y)
-// into slot C of each problem; blockIdx.x = split.  A thread owns a 2 x 2 tile; along the lag index the two rows (columns) of a
-// tile read the same series one frame apart, so each step loads 2 new values for 4 complex MACs.
+// Frame-domain form: K[s][s'] = sum_i conj(lags_i(s)) lags_i(s') (lower triangle, s' <= s) of the problems [q0, q0 + gridDim.x) into
+// slot C of each problem.  With lags_(c, l)(s) = x_c(s - l) the entry on diagonal d = s - s' is a window sum of ONE sequence,
+//     K[s' + d][s'] = sum_{l < P} p_d(s' - l),      p_d(t) = sum_c conj(x_c(t + d)) x_c(t)   (0 for t < 0),
+// so a diagonal costs C complex MACs per entry for p_d and P additions for the window instead of C P MACs — and the window is summed
+// directly (no running add / subtract: after a loud passage that would leave rounding residue where K is exactly small).  One CTA per
+// problem, WPE_GRAM_DG diagonals at a time through a shared-memory line buffer with P - 1 leading zeros.
+constexpr int WPE_GRAM_DG = 8;
 template <typename RT>
 __global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_gram_dual(WpeArgs a, int q0) {
   extern __shared__ __align__(16) unsigned char smem[];
   typedef cx<RT> CX;
-  const int g = problem_chain(a, q0 + blockIdx.y);
+  const int g = problem_chain(a, q0 + blockIdx.x);
   const int u = g / a.K;
   const int nfr = est_frames_of(a, u);
   const int xstride = a.P + a.T, P = a.P, C = a.C, Lr = a.Lr;
+  const int pstride = a.Sd + P;                       // line buffer: [P - 1 zeros | p_d(0 .. nS - d - 1)]
   CX* xs = reinterpret_cast<CX*>(smem);
+  CX* pb = xs + (size_t)C * xstride;                  // [WPE_GRAM_DG][pstride]
   load_series_t<RT>(a, g, nfr, xs, xstride);
+  for (int i = threadIdx.x; i < WPE_GRAM_DG * pstride; i += blockDim.x) pb[i] = mk<RT>(0, 0);
   __syncthreads();
   const int nS = max(nfr - a.lowerN, 0);
-  CX* Kq = reinterpret_cast<CX*>(a.Rw) + ((size_t)blockIdx.y * (C + 1) + C) * a.slot;
-  const int S2 = (nS + 1) / 2;
-  const int ntiles = S2 * (S2 + 1) / 2;
-  for (int tq = blockIdx.x * blockDim.x + threadIdx.x; tq < ntiles; tq += gridDim.x * blockDim.x) {
-    int bi = (int)((sqrtf(8.0f * (float)tq + 1.0f) - 1.0f) * 0.5f);
-    while ((bi + 1) * (bi + 2) / 2 <= tq) bi++;
-    while (bi * (bi + 1) / 2 > tq) bi--;
-    const int bj = tq - bi * (bi + 1) / 2;
-    const int s0 = 2 * bi, t0 = 2 * bj;
-    const int ds = (s0 + 1 < nS) ? 1 : 0, dt = (t0 + 1 < nS) ? 1 : 0;
-    CX k00 = mk<RT>(0, 0), k01 = k00, k10 = k00, k11 = k00;   // k[s][t] += x(t - l) conj(x(s - l))
-    auto mac = [](CX& acc, const CX& b, const CX& av) {        // acc += b conj(av)
-      acc.x = fma(b.x, av.x, acc.x); acc.x = fma(b.y, av.y, acc.x); acc.y = fma(b.y, av.x, acc.y); acc.y = fma(-b.x, av.y, acc.y);
-    };
-    for (int cp = 0; cp < C; cp++) {
-      const CX* ps = xs + (size_t)cp * xstride + P + s0;
-      const CX* pt = xs + (size_t)cp * xstride + P + t0;
-      CX as1 = ps[ds], bt1 = pt[dt];
-      for (int l = 0; l < P; l++) {
-        const CX as0 = ps[-l], bt0 = pt[-l];
-        mac(k00, bt0, as0); mac(k01, bt1, as0); mac(k10, bt0, as1); mac(k11, bt1, as1);
-        as1 = as0; bt1 = bt0;   // x(s0 + 1 - (l + 1)) = x(s0 - l)
+  CX* Kq = reinterpret_cast<CX*>(a.Rw) + ((size_t)blockIdx.x * (C + 1) + C) * a.slot;
+  for (int d0 = 0; d0 < nS; d0 += WPE_GRAM_DG) {
+    for (int i = threadIdx.x; i < WPE_GRAM_DG * nS; i += blockDim.x) {
+      const int dd = i / nS, t = i - dd * nS, d = d0 + dd;
+      CX acc = mk<RT>(0, 0);
+      if (t + d < nS) {
+        for (int c = 0; c < C; c++) {
+          const CX av = xs[(size_t)c * xstride + P + t + d], b = xs[(size_t)c * xstride + P + t];   // acc += b conj(av)
+          acc.x = fma(b.x, av.x, acc.x); acc.x = fma(b.y, av.y, acc.x); acc.y = fma(b.y, av.x, acc.y); acc.y = fma(-b.x, av.y, acc.y);
+        }
+      }
+      pb[(size_t)dd * pstride + P - 1 + t] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < WPE_GRAM_DG * nS; i += blockDim.x) {
+      const int dd = i / nS, t = i - dd * nS, d = d0 + dd;
+      if (t + d < nS) {
+        const CX* pp = pb + (size_t)dd * pstride + P - 1 + t;
+        CX e0 = mk<RT>(0, 0), e1 = e0;
+        int l = 0;
+        for (; l + 1 < P; l += 2) { const CX v0 = pp[-l], v1 = pp[-l - 1]; e0.x += v0.x; e0.y += v0.y; e1.x += v1.x; e1.y += v1.y; }
+        if (l < P) { const CX v0 = pp[-l]; e0.x += v0.x; e0.y += v0.y; }
+        CX k = mk<RT>(e0.x + e1.x, e0.y + e1.y);
+        if (d == 0) k.y = 0;
+        Kq[(size_t)(t + d) * Lr + t] = k;
       }
     }
-    Kq[(size_t)s0 * Lr + t0] = k00;
-    if (dt && t0 + 1 <= s0) Kq[(size_t)s0 * Lr + t0 + 1] = k01;
-    if (ds) {
-      Kq[(size_t)(s0 + 1) * Lr + t0] = k10;
-      if (dt) Kq[(size_t)(s0 + 1) * Lr + t0 + 1] = k11;
-    }
+    __syncthreads();
   }
 }
 
@@ -447,6 +452,19 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
           pa[q] = Pn + (size_t)(nb + min(ri + q * nt4, nt - 1)) * WPE_LD;
           pb[q] = Pn + (size_t)(nb + min(rk + q * nt4, nt - 1)) * WPE_LD;
         }
+        if (a.prefetch) {
+          // the entries this tile will read-modify-write come from L2 (or, first panel of the frame-domain form, from K): ask for them
+          // now so that they sit in L1 when the 16-column product below is done — no registers are held while they travel
+          const CX* base = (DUAL && j0 == 0) ? Kq : A;
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int pc = 0; pc <= q; pc++) {
+              const int row = ri + q * nt4, col = rk + pc * nt4;
+              if (row < nt && col < nt && (pc < q || diag))
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)(j1 + row) * Lr + j1 + col));
+            }
+        }
         CX sd[4], so[6];
 #pragma unroll
         for (int e = 0; e < 4; e++) sd[e] = mk<RT>(0, 0);
@@ -557,7 +575,7 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
   const int Lcap = dual ? a.Sd : a.L;
   if ((size_t)(Lcap + 1) * a.Lr > a.slot || Lcap + 1 > a.Lr) return cudaErrorInvalidValue;
   const size_t sm_resid = ((size_t)C * xstride + (size_t)C * a.L) * sizeof(float2);
-  const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (dual ? 0 : (size_t)C * a.T * sizeof(RT));
+  const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (dual ? (size_t)WPE_GRAM_DG * (a.Sd + a.P) * sizeof(cx<RT>) : (size_t)C * a.T * sizeof(RT));
   const size_t sm_chol = chol_region0<RT>(Lcap, dual ? C * xstride : 0) * sizeof(cx<RT>) + 32 * sizeof(RT) + 272 +
                          (dual ? (size_t)((Lcap + 1) & ~1) * sizeof(RT) + (size_t)Lcap * sizeof(cx<RT>) : 0);
   const int chol_threads = a.chol_threads > 0 ? a.chol_threads : (dual ? 128 : WPE_CHOL_THREADS);
@@ -588,7 +606,7 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
     // running the iterations of one chunk back to back is the same computation as estimate_Gn_'s iteration-major loop)
     for (int q0 = 0; q0 < nprob && iters > 0; q0 += chunk) {
       const int nq = (nprob - q0 < chunk) ? nprob - q0 : chunk;
-      corr<<<dim3(4, nq), WPE_CORR_THREADS, sm_corr, st>>>(a, q0);
+      corr<<<nq, WPE_CORR_THREADS, sm_corr, st>>>(a, q0);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       (*launches)++;
       for (int it = 0; it < iters; it++) {

@@ -24,7 +24,7 @@ for form in os.environ.get("WPE_FORMS", "lag,frame").split(","):
                     ms_per_utterance=p.last_timing_wpe() / U, s_per_1024_utt=s * 1024 / U)
         if tag == "fp64" and not ref:
             ref = dict(G=G, X=X, form=form)
-        else:
+        elif ref:
             line["vs_%s_fp64" % ref["form"]] = dict(filters_rel_l2=rel(G, ref["G"]), snapshots_rel_l2=rel(X, ref["X"]))
         print(json.dumps({"wpe chain %s, %s-domain, %d utterances" % (tag, form, U): line}), flush=True)
         p.close()
