@@ -197,6 +197,16 @@ class Pipeline:
         _check(lib.btkb_last_timing_wpe(self._h, ct.byref(ms)))
         return float(ms.value)
 
+    def upgrade_blocking_matrix(self):
+        """SubbandMVDRGSC::upgrade_blocking_matrix (beamformer.cc:2674-2691)."""
+        _check(lib.btkb_upgrade_blocking_matrix(self._h))
+
+    def blocking_matrix_output(self, out_chan):
+        """b_i^H x for every frame: complex64 [U][T][K] (SubbandMVDRGSC::blocking_matrix_output, beamformer.cc:2693-2716)."""
+        out = np.empty((self.U, self.num_frames(), self.K), np.complex64)
+        _check(lib.btkb_blocking_matrix_output(self._h, ct.c_int(out_chan), _fp(out)))
+        return out
+
     def last_wpe_form(self):
         """0: the last estimation solved the lag-domain normal equations (L x L), 1: the frame-domain ones (S x S)."""
         f = ct.c_int(-1)

@@ -50,6 +50,8 @@ struct btkb_pipeline {
   bool have_pfR = false, pf_applied = false;  // pf_applied: d_Y came out of this pipeline's post-filter (not btkb_set_subband)
   // batch state
   int U = 0, n = 0, T = 0, nb = 0, Gp = 0, wU = 0, NC = 1;
+  float2 *d_BS = nullptr, *d_BI = nullptr, *d_Z = nullptr;   // upgrade_blocking_matrix / blocking_matrix_output (allocated on first use)
+  bool bm_upgraded = false;
   int bm_source = 0;  // BTKB_BF_MVDR: 0 = blocking matrix from the delay-and-sum manifold (calc_blocking_matrix1), 1 = from wmvdr (calc_blocking_matrix2)
   double* d_delaysJ = nullptr;
   std::vector<int> lengths;
@@ -107,7 +109,7 @@ static void fb_delays(int m, int r, int dct, bool synthesis, int* pd, int* la) {
 void btkb_destroy(btkb_pipeline* p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
-  void* ptrs[] = {p->d_xs[0], p->d_xs[1], p->d_ST, p->d_tu, p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
+  void* ptrs[] = {p->d_BS, p->d_BI, p->d_Z, p->d_xs[0], p->d_xs[1], p->d_ST, p->d_tu, p->d_x, p->d_len, p->d_h, p->d_g, p->d_X, p->d_Y, p->d_W, p->d_TA, p->d_WL, p->d_WA, p->d_UA, p->d_R, p->d_E, p->d_time, p->d_upd,
                   p->d_PFW, p->d_delays, p->d_mpos, p->d_labels, p->d_stats, p->d_mask, p->d_todo, p->d_count, p->d_scratch, p->d_x16, p->d_delaysJ, p->d_tw,
                   p->d_pfR, p->d_pfInvR, p->d_pfQ, p->d_LAM, p->d_wS, p->d_wG, p->d_wR, p->d_wTH, p->d_werr,
                   p->d_sosR, p->d_sosWd, p->d_sosCnt, p->d_sosWtu, p->d_sosMask, p->d_sosLab, p->d_sosErr, p->d_covS};
@@ -330,7 +332,7 @@ int btkb_set_delays(btkb_pipeline* p, int U, const double* delays) {
   if (rebase) CK(cudaMemcpyAsync(p->d_WL, p->d_TA, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));   // WL is free in the adaptive modes
   WeightsArgs a{p->d_delays, p->d_TA, U, p->C, p->M, p->K, p->Gp, p->cfg.samplerate};
   CK(launch_mainlobe_weights(a, p->stream));
-  p->have_ta = true; p->NC = 1;
+  p->have_ta = true; p->NC = 1; p->bm_upgraded = false;   // new BeamformerWeights (alloc_bfweight_): an upgraded blocking matrix is gone
   if (p->cfg.beamformer != BTKB_BF_MVDR) {
     CK(cudaMemcpyAsync(p->d_W, p->d_TA, (size_t)p->C * p->Gp * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
     p->have_w = true;
@@ -372,6 +374,14 @@ int btkb_set_weights(btkb_pipeline* p, int U, const float* w) {
   return BTKB_OK;
 }
 
+static PerBinArgs perbin_args(btkb_pipeline* p);
+// the vector the blocking matrix is orthogonal to: wq (the delay-and-sum manifold or, after calc_blocking_matrix2, wmvdr) or,
+// after upgrade_blocking_matrix, the stored wq - wl
+static const float2* blocking_source(const btkb_pipeline* p) {
+  if (p->bm_upgraded) return p->d_BS;
+  return (p->cfg.beamformer == BTKB_BF_MVDR && p->bm_source == 0) ? p->d_TA : p->d_W;
+}
+
 int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa) {
   if (!p || !wa) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: null argument");
   if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_gsc_weights_x() once");  // beamformer.cc:1369-1371
@@ -380,7 +390,7 @@ int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa) {
   int rc = check_weight_batch(p, U, "btkb_set_active_weights"); if (rc) return rc;
   if (U != p->wU) return fail(BTKB_ERR_INVALID, "btkb_set_active_weights: the quiescent weights were set for " + std::to_string(p->wU) + " utterances, not " + std::to_string(U));
   // calc_blocking_matrix_(wq_[f], NC, B_[f]) (beamformer.cc:554-562, 693-700): B is built from the quiescent vector
-  const float2* bsrc = (p->cfg.beamformer == BTKB_BF_MVDR && p->bm_source == 0) ? p->d_TA : p->d_W;
+  const float2* bsrc = blocking_source(p);
   if (bsrc == p->d_W && !p->have_w) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");  // calc_blocking_matrix2 returns false without wmvdr (beamformer.cc:2651-2653)
   CK(cudaSetDevice(p->cfg.device));
   std::vector<float2> tmp;
@@ -396,7 +406,55 @@ int btkb_set_blocking_source(btkb_pipeline* p, int from_mvdr_weights) {
   if (!p) return fail(BTKB_ERR_INVALID, "btkb_set_blocking_source: null pipeline");
   if (p->cfg.beamformer != BTKB_BF_MVDR) return fail(BTKB_ERR_INVALID, "btkb_set_blocking_source: only a BTKB_BF_MVDR pipeline has two candidate quiescent vectors");
   p->bm_source = from_mvdr_weights ? 1 : 0;
+  p->bm_upgraded = false;
   p->have_wl = false;  // alloc_bfweight_(1, 1): the active weights set so far are gone (beamformer.cc:2640, 2655)
+  return BTKB_OK;
+}
+
+int btkb_upgrade_blocking_matrix(btkb_pipeline* p) {
+  if (!p) return fail(BTKB_ERR_INVALID, "btkb_upgrade_blocking_matrix: null pipeline");
+  if (p->cfg.beamformer != BTKB_BF_MVDR) return fail(BTKB_ERR_INVALID, "btkb_upgrade_blocking_matrix: SubbandMVDRGSC only (BTKB_BF_MVDR)");
+  if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");
+  if (p->C < 2 || p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_upgrade_blocking_matrix: the blocking-matrix kernels are built for 2..8 channels");
+  const float2* wq = (p->bm_source == 0) ? p->d_TA : p->d_W;   // wq_f: what calc_blocking_matrix1 / 2 stored (beamformer.cc:2638-2672)
+  if (wq == p->d_W && !p->have_w) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");
+  CK(cudaSetDevice(p->cfg.device));
+  if (!p->d_BS) CK(cudaMalloc((void**)&p->d_BS, (size_t)p->Cp * p->Gp * sizeof(float2)));
+  CK(launch_upgrade_source(wq, p->have_wl ? p->d_WL : nullptr, p->d_BS, p->C, p->wU, p->K, p->Gp, -1, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  p->bm_upgraded = true;   // wl keeps its value until the next set_active_weights, as in the reference
+  return BTKB_OK;
+}
+
+int btkb_blocking_matrix_output(btkb_pipeline* p, int outChanX, float* out) {
+  if (!p || !out) return fail(BTKB_ERR_INVALID, "btkb_blocking_matrix_output: null argument");
+  if (p->cfg.beamformer != BTKB_BF_MVDR) return fail(BTKB_ERR_INVALID, "btkb_blocking_matrix_output: SubbandMVDRGSC only (BTKB_BF_MVDR)");
+  if (!p->have_X) return fail(BTKB_ERR_STATE, "btkb_blocking_matrix_output: run the analysis first");
+  if (!p->have_ta) return fail(BTKB_ERR_STATE, "call calc_array_manifold_vectorsX() once");
+  if (p->C < 2 || p->C > 8) return fail(BTKB_ERR_INVALID, "btkb_blocking_matrix_output: the blocking-matrix kernels are built for 2..8 channels");
+  if (outChanX < 0 || outChanX >= p->C - p->NC) return fail(BTKB_ERR_INVALID, "btkb_blocking_matrix_output: outChanX must be in [0, C - NC)");
+  if (p->wU != p->U) return fail(BTKB_ERR_INVALID, "btkb_blocking_matrix_output: weights were set for a different number of utterances");
+  const float2* bsrc = blocking_source(p);
+  if (bsrc == p->d_W && !p->have_w) return fail(BTKB_ERR_STATE, "call calc_mvdr_weights() once");
+  CK(cudaSetDevice(p->cfg.device));
+  const size_t G = (size_t)p->Gp;
+  if (!p->d_BI) CK(cudaMalloc((void**)&p->d_BI, (size_t)2 * p->Cp * G * sizeof(float2)));   // [C] b_i, then [C] the unit active weights
+  if (!p->d_Z) CK(cudaMalloc((void**)&p->d_Z, (size_t)p->Tcap * G * sizeof(float2)));
+  float2* unit = p->d_BI + (size_t)p->Cp * G;
+  CK(launch_upgrade_source(nullptr, nullptr, unit, p->C - p->NC, p->U, p->K, p->Gp, outChanX, p->stream));
+  CK(launch_blocking_wl(bsrc, unit, p->d_BI, p->U, p->C, p->K, p->Gp, p->NC, p->stream));   // column outChanX of B
+  PerBinArgs a = perbin_args(p);   // b_i^H x for every frame = the delay-and-sum kernel with b_i as its weights
+  a.kind = BTKB_BF_DS; a.W = p->d_BI; a.WL = nullptr; a.TA = nullptr; a.Y = p->d_Z; a.PFW = nullptr; a.pf_kind = BTKB_PF_NONE; a.normalize_weight = 0;
+  a.ST = nullptr; a.st_load = 0;
+  CK(launch_perbin(a, p->stream));
+  p->launches += 3;
+  std::vector<float2> tmp((size_t)p->T * G);
+  CK(cudaMemcpyAsync(tmp.data(), p->d_Z, tmp.size() * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  float2* o = reinterpret_cast<float2*>(out);
+  for (int u = 0; u < p->U; u++)
+    for (int t = 0; t < p->T; t++)
+      memcpy(o + ((size_t)u * p->T + t) * p->K, tmp.data() + (size_t)t * G + (size_t)u * p->K, (size_t)p->K * sizeof(float2));
   return BTKB_OK;
 }
 

@@ -164,6 +164,7 @@ cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st);
 
 // setup kernels (btkb_weights.cu)
 cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, int NC, cudaStream_t st);
+cudaError_t launch_upgrade_source(const float2* WQ, const float2* WL, float2* OUT, int rows, int U, int K, int Gp, int unit, cudaStream_t st);
 cudaError_t launch_lcmv_weights(const double* delaysT, const double* delaysJ, float2* W, int U, int C, int NC, int M, int K, int Gp, float samplerate, cudaStream_t st);
 cudaError_t launch_spectral_recursion(const PerBinArgs& a, float mu, int noconj, cudaStream_t st);
 cudaError_t launch_diffuse_model(const double* mpos, float2* R, int U, int C, int M, int K, int Gp, float samplerate, float sspeed, cudaStream_t st);

@@ -148,6 +148,28 @@ static cudaError_t launch_blocking(const float2* W, const float2* IN, float2* OU
   }
   return cudaGetLastError();
 }
+// SubbandMVDRGSC::upgrade_blocking_matrix (beamformer.cc:2674-2691): the vector the blocking matrix is orthogonal to becomes
+// wq - wl for the bins 1 .. (bin 0 keeps wq: the reference's loop starts at fbinX = 1); `unit` >= 0 instead writes the unit
+// active-weight vector e_unit (rows of OUT = C - NC) used to read one column of B
+__global__ void k_upgrade_source(const float2* WQ, const float2* WL, float2* OUT, int rows, int U, int K, int Gp, int unit) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= U * K) return;
+  const int k = g % K;
+  for (int c = 0; c < rows; c++) {
+    float2 v;
+    if (unit >= 0) v = make_float2(c == unit ? 1.f : 0.f, 0.f);
+    else {
+      v = WQ[(size_t)c * Gp + g];
+      if (k > 0 && WL) { const float2 l = WL[(size_t)c * Gp + g]; v.x -= l.x; v.y -= l.y; }
+    }
+    OUT[(size_t)c * Gp + g] = v;
+  }
+}
+cudaError_t launch_upgrade_source(const float2* WQ, const float2* WL, float2* OUT, int rows, int U, int K, int Gp, int unit, cudaStream_t st) {
+  const int n = U * K, bs = 128;
+  k_upgrade_source<<<(n + bs - 1) / bs, bs, 0, st>>>(WQ, WL, OUT, rows, U, K, Gp, unit);
+  return cudaGetLastError();
+}
 cudaError_t launch_blocking_wl(const float2* W, const float2* WA, float2* WL, int U, int C, int K, int Gp, int NC, cudaStream_t st) {
   return launch_blocking<0>(W, WA, WL, U, C, K, Gp, NC, st);
 }

@@ -858,12 +858,56 @@ void SubbandMVDRGSC::set_active_weights_f(unsigned fbinX, const std::vector<doub
   if (wa_.size() != (size_t)K * (C - 1)) wa_.assign((size_t)K * (C - 1), std::complex<float>(0, 0));
   bool nz = false;
   for (unsigned i = 0; i < C - 1; i++) { wa_[(size_t)fbinX * (C - 1) + i] = std::complex<float>((float)packed[2 * i], (float)packed[2 * i + 1]); nz |= packed[2 * i] != 0 || packed[2 * i + 1] != 0; }
-  have_wa_ = have_wa_ || nz; invalidate_();
+  have_wa_ = have_wa_ || nz; wa_since_upgrade_ = true; invalidate_();
 }
 void SubbandMVDRGSC::configure_weights_(btkb_pipeline* p) {
   SubbandMVDR::configure_weights_(p);
   if (bm_from_mvdr_) ck(btkb_set_blocking_source(p, 1));
-  if (have_wa_) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
+  const unsigned C = chanN(), K = fftLen_ / 2 + 1;
+  for (const auto& w : upgrades_) {   // replay: the active weights in force at each upgrade, then the upgrade
+    if (w.size() == (size_t)K * (C - 1)) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(w.data())));
+    ck(btkb_upgrade_blocking_matrix(p));
+  }
+  if (have_wa_ && (upgrades_.empty() || wa_since_upgrade_)) ck(btkb_set_active_weights(p, 1, reinterpret_cast<const float*>(wa_.data())));
+}
+void SubbandMVDRGSC::upgrade_blocking_matrix() {
+  if (halfBandShift_) throw j_error("halfBandShift is not implemented\n");
+  upgrades_.push_back(have_wa_ ? wa_ : std::vector<std::complex<float>>());
+  wa_since_upgrade_ = false; invalidate_();
+}
+const cplx* SubbandMVDRGSC::blocking_matrix_output(int outChanX) {
+  if (chunk_blocks_ > 0) throw j_error("blocking_matrix_output: not offered for a chunked realisation (set_chunk_blocks(0))\n");
+  if (!realized_) run_graph(PostFilterConfig(), SynthesisConfig());
+  const unsigned K = fftLen_ / 2 + 1;
+  if (Z_chan_ != outChanX || Z_of_ != (const void*)Y_.data() || Z_T_ != T_) {
+    Z_.resize((size_t)btkb_num_frames(pipe_) * K);
+    ck(btkb_blocking_matrix_output(pipe_, outChanX, reinterpret_cast<float*>(Z_.data())));
+    Z_chan_ = outChanX; Z_of_ = (const void*)Y_.data(); Z_T_ = T_;
+  }
+  bmout_.assign(fftLen_, cplx(0, 0));
+  const int t = frame_no_ < 0 ? 0 : frame_no_;
+  if (t >= T_) throw jiterator_error("end of samples!");
+  for (unsigned k = 0; k < K; k++) { const std::complex<float> z = Z_[(size_t)t * K + k]; bmout_[k] = cplx(z.real(), z.imag()); }
+  if (frame_no_ >= 0) for (unsigned k = 1; k < fftLen_ / 2; k++) bmout_[fftLen_ - k] = vector_[fftLen_ - k];   // what next() left in the shared vector
+  return bmout_.data();
+}
+const cplx* SubbandOrthogonalizer::next(int frame_no) {   // beamformer.cc:2786-2806
+  if (frame_no == frame_no_) return vector_.data();
+  const cplx* v = (outChanX_ <= 0) ? beamformer_->next(frame_no) : beamformer_->blocking_matrix_output(outChanX_ - 1);
+  std::copy(v, v + size(), vector_.begin());
+  increment_();
+  return vector_.data();
+}
+void SpectralMatrixArray::update() {   // beamformer.cc:122-143
+  SnapShotArray::update();
+  const unsigned C = nChan();
+  const cplx alpha = cplx(1.0, 0) - mu_;
+  for (unsigned f = 0; f < fftLen(); f++) {
+    cplx* R = &matrices_[(size_t)f * C * C];
+    const cplx* x = snapshot(f);
+    for (unsigned i = 0; i < C; i++)
+      for (unsigned j = 0; j < C; j++) R[i * C + j] = R[i * C + j] * mu_ + alpha * (x[i] * x[j]);
+  }
 }
 
 // ================================================================================================ post-filter
@@ -987,25 +1031,36 @@ OverSampledDFTSynthesisBank::OverSampledDFTSynthesisBank(const VectorComplexFeat
   if (prototype.size() != (size_t)M * m) throw jconsistency_error("Prototype sizes do not match (%d vs. %d).", (int)prototype.size(), (int)(M * m));
 }
 OverSampledDFTSynthesisBank::~OverSampledDFTSynthesisBank() { if (pipe_) btkb_destroy(pipe_); }
-void OverSampledDFTSynthesisBank::reset() { samp_->reset(); VectorFloatFeatureStream::reset(); realized_ = false; live_bf_ = nullptr; }
+void OverSampledDFTSynthesisBank::reset() { samp_->reset(); VectorFloatFeatureStream::reset(); realized_ = false; live_bf_ = nullptr; pushed_.clear(); npushed_ = 0; }
+void OverSampledDFTSynthesisBank::input_source_vector(const std::vector<cplx>& block) {   // modulated.h:330 -> update_buf_ (modulated.cc:551-567)
+  if (block.size() != M_) throw jdimension_error("Input block length (%d) != fftLen (%d)\n", (int)block.size(), (int)M_);
+  if (realized_) throw j_error("input_source_vector: frames can be pushed until the first next() (the mirror synthesises the utterance in one pass)\n");
+  // pushed frames enter the buffer without a polyphase sum (update_buf_ only).  With R = 1 an output depends on the buffer alone and the
+  // concatenated sequence reproduces the reference exactly; with R > 1 the first R - 1 outputs would also need the polyphase sums the
+  // reference did NOT form for the pushed frames, which a one-pass synthesis of the concatenation cannot leave out.
+  if (r_ != 0) throw j_error("input_source_vector: offered for critically sampled banks (r = 0) only\n");
+  const unsigned K = M_ / 2 + 1;
+  for (unsigned k = 0; k < K; k++) pushed_.push_back(std::complex<float>((float)block[k].real(), (float)block[k].imag()));
+  npushed_++;
+}
 
 void OverSampledDFTSynthesisBank::realize_() {
   SynthesisConfig syn; syn.enabled = true; syn.prototype = prototype_; syn.M = M_; syn.m = m_; syn.r = r_; syn.dct = dct_; syn.gain = gain_;
   SubbandBeamformer* bf = nullptr; PostFilterConfig pf;
   if (auto* z = dynamic_cast<ZelinskiPostFilter*>(samp_.get())) { bf = z->beamformer().get(); pf = z->config(); }
   else bf = dynamic_cast<SubbandBeamformer*>(samp_.get());
-  if (bf) {  // fast path: the whole graph runs on the GPU in one submission
+  if (bf && npushed_ == 0) {  // fast path: the whole graph runs on the GPU in one submission
     if (!bf->realized_with(pf, syn)) bf->run_graph(pf, syn);
     nb_ = bf->blocks(); live_bf_ = bf;
     if (bf->chunk_blocks() == 0) { out_ = bf->time_out(); live_bf_ = nullptr; }   // chunked realisation: blocks are pulled as next() asks for them
   } else {
     live_bf_ = nullptr;   // arbitrary upstream stream (e.g. a Python object behind PyVectorComplexFeatureStream): drain it, synthesise on the GPU
     const unsigned K = M_ / 2 + 1;
-    std::vector<std::complex<float>> Y;
-    int T = 0;
-    for (;;) {
+    std::vector<std::complex<float>> Y = pushed_;   // frames handed in through input_source_vector sit in the buffer ahead of the source's
+    int T = npushed_;
+    for (int ts = 0;; ts++) {
       const cplx* f;
-      try { f = samp_->next(T); } catch (jiterator_error&) { break; }
+      try { f = samp_->next(ts); } catch (jiterator_error&) { break; }
       Y.resize((size_t)(T + 1) * K);
       for (unsigned k = 0; k < K; k++) Y[(size_t)T * K + k] = std::complex<float>((float)f[k].real(), (float)f[k].imag());
       T++;

@@ -141,8 +141,10 @@ class SnapShotArray {
   SnapShotArray(unsigned fftlen, unsigned nchan) : fftLen_(fftlen), nChan_(nchan), samples_((size_t)fftlen * nchan), snapshots_((size_t)fftlen * nchan) {}
   const cplx* snapshot(unsigned fbinX) const { return &snapshots_[(size_t)fbinX * nChan_]; }
   void set_samples(const cplx* samp, unsigned chanX) { for (unsigned k = 0; k < fftLen_; k++) samples_[(size_t)chanX * fftLen_ + k] = samp[k]; }
-  void update() { for (unsigned k = 0; k < fftLen_; k++) for (unsigned c = 0; c < nChan_; c++) snapshots_[(size_t)k * nChan_ + c] = samples_[(size_t)c * fftLen_ + k]; }
-  void zero() { std::fill(samples_.begin(), samples_.end(), cplx(0, 0)); std::fill(snapshots_.begin(), snapshots_.end(), cplx(0, 0)); }
+  virtual ~SnapShotArray() {}
+  virtual void update() { for (unsigned k = 0; k < fftLen_; k++) for (unsigned c = 0; c < nChan_; c++) snapshots_[(size_t)k * nChan_ + c] = samples_[(size_t)c * fftLen_ + k]; }
+  virtual void zero() { std::fill(samples_.begin(), samples_.end(), cplx(0, 0)); std::fill(snapshots_.begin(), snapshots_.end(), cplx(0, 0)); }
+  const cplx* samples(unsigned chanX) const { return &samples_[(size_t)chanX * fftLen_]; }
   unsigned fftLen() const { return fftLen_; }
   unsigned nChan() const { return nChan_; }
  private:
@@ -150,6 +152,24 @@ class SnapShotArray {
   std::vector<cplx> samples_, snapshots_;
 };
 typedef std::shared_ptr<SnapShotArray> SnapShotArrayPtr;
+
+// SpectralMatrixArray (beamformer/spectralinfoarray.h:43-63, beamformer.cc:95-143): the per-frame container of the recursively
+// averaged spectral matrices, R <- mu R + (1 - mu) x x^T per bin (no conjugate, as the reference).  An interface container like
+// SnapShotArray: one frame of C^2 values per bin is kept and updated here; the whole-utterance recursion on the GPU is
+// btkb_spectral_matrix_update.  FBSpectralMatrixArray is not mirrored: its update() indexes the channel-major sample vectors by
+// the bin number (beamformer.cc:163: samples_[ifft], an array of nChan vectors), i.e. it reads out of bounds for bins >= nChan.
+class SpectralMatrixArray : public SnapShotArray {
+ public:
+  SpectralMatrixArray(unsigned fftlen, unsigned nchan, float forget_factor = 0.95f)
+      : SnapShotArray(fftlen, nchan), mu_(forget_factor), matrices_((size_t)fftlen * nchan * nchan) {}
+  const cplx* matrix_f(unsigned idx) const { if (idx >= fftLen()) throw jindex_error("index %d >= fftLen %d\n", (int)idx, (int)fftLen()); return &matrices_[(size_t)idx * nChan() * nChan()]; }
+  void update() override;
+  void zero() override { SnapShotArray::zero(); std::fill(matrices_.begin(), matrices_.end(), cplx(0, 0)); }
+ protected:
+  cplx mu_;
+  std::vector<cplx> matrices_;
+};
+typedef std::shared_ptr<SpectralMatrixArray> SpectralMatrixArrayPtr;
 
 // ----------------------------------------------------------------------------------------------------------------
 // WPE dereverberation (dereverberation/dereverberation.h).  The reference estimates the filters from a buffered pass over the
@@ -458,18 +478,43 @@ class SubbandMVDRGSC : public SubbandMVDR {
   // B orthogonal to the delay-and-sum weights (beamformer.cc:2638-2643); like the reference's alloc_bfweight_ both variants drop
   // the active weights set before
   bool calc_blocking_matrix1(double samplerate, const std::vector<double>& delaysT) {
-    calc_array_manifold_vectors(samplerate, delaysT); bm_from_mvdr_ = false; wa_.clear(); have_wa_ = false; return true;
+    calc_array_manifold_vectors(samplerate, delaysT); bm_from_mvdr_ = false; wa_.clear(); have_wa_ = false; upgrades_.clear(); return true;
   }
   // B orthogonal to the MVDR weights (beamformer.cc:2649-2672); false when calc_mvdr_weights() has not been called
   bool calc_blocking_matrix2() {
     if (!have_w_) return false;
-    bm_from_mvdr_ = true; wa_.clear(); have_wa_ = false; invalidate_(); return true;
+    bm_from_mvdr_ = true; wa_.clear(); have_wa_ = false; upgrades_.clear(); invalidate_(); return true;
   }
+  // beamformer.cc:2674-2691: the blocking matrix of the bins >= 1 becomes the one orthogonal to wq - wl (wl = B wa of the active
+  // weights set so far); active weights set afterwards go through the new matrix.  The mirror keeps the active weights of each
+  // upgrade and replays set / upgrade in order when the pipeline is configured (whole vectors: an upgrade between the per-bin
+  // set_active_weights_f calls of ONE weight vector is not tracked bin by bin).
+  void upgrade_blocking_matrix();
+  // beamformer.cc:2693-2716: b_outChanX^H x of the CURRENT frame for the bins 0..M/2; the upper half of the returned vector is what
+  // the reference's shared output vector holds there after next(): the conjugate-symmetric half of the beamformer output
+  const cplx* blocking_matrix_output(int outChanX = 0);
  protected:
   void configure_weights_(btkb_pipeline* p) override;
   std::vector<std::complex<float>> wa_; bool have_wa_ = false, bm_from_mvdr_ = false;
+  std::vector<std::vector<std::complex<float>>> upgrades_;   // active weights in force at each upgrade_blocking_matrix()
+  bool wa_since_upgrade_ = false;
+  std::vector<std::complex<float>> Z_; int Z_chan_ = -1; const void* Z_of_ = nullptr; int Z_T_ = 0;
+  std::vector<cplx> bmout_;
 };
 typedef std::shared_ptr<SubbandMVDRGSC> SubbandMVDRGSCPtr;
+
+// SubbandOrthogonalizer (beamformer.h / beamformer.cc:2776-2806): streams the beamformer output (outChanX <= 0) or the output of
+// blocking-matrix branch outChanX - 1 of a SubbandMVDRGSC
+class SubbandOrthogonalizer : public VectorComplexFeatureStream {
+ public:
+  SubbandOrthogonalizer(const SubbandMVDRGSCPtr& beamformer, int outChanX = 0, const std::string& nm = "SubbandOrthogonalizer")
+      : VectorComplexFeatureStream(beamformer->fftLen(), nm), beamformer_(beamformer), outChanX_(outChanX) {}
+  const cplx* next(int frame_no = -5) override;
+  void reset() override { beamformer_->reset(); VectorComplexFeatureStream::reset(); }
+ private:
+  SubbandMVDRGSCPtr beamformer_; int outChanX_;
+};
+typedef std::shared_ptr<SubbandOrthogonalizer> SubbandOrthogonalizerPtr;
 
 // ----------------------------------------------------------------------------------------------------------------
 class ZelinskiPostFilter : public VectorComplexFeatureStream {
@@ -535,8 +580,12 @@ class OverSampledDFTSynthesisBank : public VectorFloatFeatureStream {
   const float* next(int frame_no = -5) override;
   void reset() override;
   double polyphase(unsigned m, unsigned n) const { return prototype_.at(m + M_ * n); }
+  // modulated.h:330: hand the bank one subband frame directly (update_buf_); the frames pushed before the first next() enter the
+  // buffer ahead of the source's frames, so the outputs are those of the concatenated sequence from block (number pushed) on; r = 0 only
+  void input_source_vector(const std::vector<cplx>& block);
  private:
   void realize_();
+  std::vector<std::complex<float>> pushed_; int npushed_ = 0;
   VectorComplexFeatureStreamPtr samp_;
   std::vector<double> prototype_;
   unsigned M_, m_, r_, D_, dct_; int gain_; int pd_;

@@ -164,7 +164,9 @@ PYBIND11_MODULE(_btk20host, m) {
                        unsigned dct, int gain, const std::string& nm) { return std::make_shared<OverSampledDFTSynthesisBank>(samp, vec_d(prototype), M, mm, r, dct, gain, nm); }),
            py::arg("samp"), py::arg("prototype"), py::arg("M"), py::arg("m"), py::arg("r") = 0, py::arg("delay_compensation_type") = 0, py::arg("gain_factor") = 1,
            py::arg("nm") = "OverSampledDFTSynthesisBank")
-      .def("polyphase", &OverSampledDFTSynthesisBank::polyphase, py::arg("m"), py::arg("n"));
+      .def("polyphase", &OverSampledDFTSynthesisBank::polyphase, py::arg("m"), py::arg("n"))
+      .def("input_source_vector", [](OverSampledDFTSynthesisBank& s, py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> block) {
+             s.input_source_vector(std::vector<cplx>(block.data(), block.data() + block.size())); }, py::arg("block"));
 
   // dereverberation/dereverberation.i:46-185
   py::class_<SingleChannelWPEDereverberationFeature, VectorComplexFeatureStream, SingleChannelWPEDereverberationFeaturePtr>(m, "SingleChannelWPEDereverberationFeaturePtr")
@@ -209,6 +211,15 @@ PYBIND11_MODULE(_btk20host, m) {
         if ((unsigned)a.size() != s.fftLen()) throw jdimension_error("set_samples: expected %d bins", s.fftLen());
         s.set_samples(a.data(), ch); }, py::arg("samp"), py::arg("chanX"))
       .def("update", &SnapShotArray::update).def("zero", &SnapShotArray::zero).def("fftLen", &SnapShotArray::fftLen).def("nChan", &SnapShotArray::nChan);
+
+  // beamformer/beamformer.i:83-114
+  py::class_<SpectralMatrixArray, SnapShotArray, SpectralMatrixArrayPtr>(m, "SpectralMatrixArrayPtr")
+      .def(py::init<unsigned, unsigned, float>(), py::arg("fftLn"), py::arg("nChn"), py::arg("forgetFact") = 0.95f)
+      .def("matrix_f", [](SpectralMatrixArray& s, unsigned idx) {
+             const cplx* p = s.matrix_f(idx);
+             return py::array_t<cplx>({(size_t)s.nChan(), (size_t)s.nChan()}, {sizeof(cplx) * s.nChan(), sizeof(cplx)}, p, py::cast(&s, py::return_value_policy::reference)); },
+           py::arg("idx"))
+      .def("update", &SpectralMatrixArray::update).def("zero", &SpectralMatrixArray::zero);
 
   py::class_<SubbandBeamformer, VectorComplexFeatureStream, SubbandBeamformerPtr>(m, "SubbandBeamformerPtr")
       .def("set_channel", &SubbandBeamformer::set_channel, py::arg("chan"))
@@ -335,7 +346,15 @@ PYBIND11_MODULE(_btk20host, m) {
       .def("zero_active_weights", &SubbandMVDRGSC::zero_active_weights)
       .def("calc_blocking_matrix1", [](SubbandMVDRGSC& s, double fs, py::array_t<double, py::array::c_style | py::array::forcecast> d) { return s.calc_blocking_matrix1(fs, vec_d(d)); },
            py::arg("samplerate"), py::arg("delaysT"))
-      .def("calc_blocking_matrix2", &SubbandMVDRGSC::calc_blocking_matrix2);
+      .def("calc_blocking_matrix2", &SubbandMVDRGSC::calc_blocking_matrix2)
+      .def("upgrade_blocking_matrix", &SubbandMVDRGSC::upgrade_blocking_matrix)
+      .def("blocking_matrix_output", [](SubbandMVDRGSC& s, int outChanX) { const cplx* p = s.blocking_matrix_output(outChanX); return view<cplx>(s, p, s.size()); },
+           py::arg("outChanX") = 0);
+
+  // beamformer/beamformer.i:543-568
+  py::class_<SubbandOrthogonalizer, VectorComplexFeatureStream, SubbandOrthogonalizerPtr>(m, "SubbandOrthogonalizerPtr")
+      .def(py::init([](SubbandMVDRGSCPtr beamformer, int outChanX, const std::string& nm) { return std::make_shared<SubbandOrthogonalizer>(beamformer, outChanX, nm); }),
+           py::arg("beamformer"), py::arg("outChanX") = 0, py::arg("nm") = "SubbandOrthogonalizer");
 
   py::class_<ZelinskiPostFilter, VectorComplexFeatureStream, ZelinskiPostFilterPtr>(m, "ZelinskiPostFilterPtr")
       .def(py::init<const VectorComplexFeatureStreamPtr&, unsigned, double, int, int, const std::string&>(), py::arg("output"), py::arg("M"), py::arg("alpha") = 0.6,

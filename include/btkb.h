@@ -135,6 +135,13 @@ int btkb_set_active_weights(btkb_pipeline* p, int U, const float* wa);
  * 1: the MVDR weights of the last btkb_calc_mvdr_weights — calc_blocking_matrix2 (beamformer.cc:2649-2672).
  * Like the reference's alloc_bfweight_, the call discards active weights set before it. */
 int btkb_set_blocking_source(btkb_pipeline* p, int from_mvdr_weights);
+/* SubbandMVDRGSC::upgrade_blocking_matrix (beamformer.cc:2674-2691): from now on the blocking matrix of the bins >= 1 is the one
+ * orthogonal to wq - wl (wq = the vector calc_blocking_matrix1 / 2 chose, wl = B wa of the last btkb_set_active_weights); bin 0
+ * keeps its matrix, wl keeps its value until active weights are set again.  btkb_set_blocking_source undoes it. */
+int btkb_upgrade_blocking_matrix(btkb_pipeline* p);
+/* SubbandMVDRGSC::blocking_matrix_output(outChanX) (beamformer.cc:2693-2716) for every frame of the batch:
+ * out [U][T][K] complex64 = b_outChanX^H x, b_i = column i of the current blocking matrix (what SubbandOrthogonalizer streams) */
+int btkb_blocking_matrix_output(btkb_pipeline* p, int outChanX, float* out);
 /* noise covariance R [U][K][C][C] complex64, row-major (set_noise_spatial_spectral_matrix, beamformer.cc:2410-2433) */
 int btkb_set_noise_covariance(btkb_pipeline* p, int U, const float* R);
 /* diffuse-noise coherence from microphone positions [C][3] (mm) (set_diffuse_noise_model, beamformer.cc:2442-2509) */

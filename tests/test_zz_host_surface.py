@@ -666,3 +666,106 @@ def test_packed_fp32_kernel_equals_the_scalar_kernel(capi, protos, case, M):
     for k, (a, b) in got.items():
         assert np.abs(a.view(np.float32) if a.dtype != np.float64 and a.dtype != np.complex128 else a.view(np.float64)).max() > 0, (case, k, "all-zero output")
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), "%s M=%d: packed != scalar, (max ulp, rel L2) per output: %r" % (case, M, report)
+
+
+@pytest.mark.gpu
+def test_mvdrgsc_upgrade_blocking_matrix_and_orthogonalizer(protos):
+    """SubbandMVDRGSC::upgrade_blocking_matrix / blocking_matrix_output and SubbandOrthogonalizer (beamformer.cc:2674-2716, 2776-2806):
+    after an upgrade the blocking matrix of the bins >= 1 is orthogonal to wq - wl (bin 0 keeps its matrix), active weights set
+    afterwards go through it, and branch i of the blocking matrix streams b_i^H x."""
+    from oracle import restate
+    from distant_speech_recognition_b200.btk20.beamformer import SubbandOrthogonalizerPtr
+    g = load_golden("mvdrsd_zelinski1_c4_m256"); h, _ = protos[256]; M, D, C, K = 256, 128, 4, 129
+    afbs = _afbs(g["x"], h, M, D)
+    X = np.stack([restate.analysis(g["x"][c], h, M, 4, 1) for c in range(C)], axis=1)
+    rng = np.random.default_rng(11)
+    wa1 = 0.05 * (rng.standard_normal((K, C - 1)) + 1j * rng.standard_normal((K, C - 1)))
+    wa2 = 0.05 * (rng.standard_normal((K, C - 1)) + 1j * rng.standard_normal((K, C - 1)))
+    wq = restate.calc_mainlobe(M, C, FS, g["delays"])
+    R = restate.diffuse_noise_model(M, g["mpos"], FS)[:K].astype(complex)
+    R[:, np.eye(C, dtype=bool)] += float(np.float32(g["mu"]))
+    wm = np.zeros((M, C), complex); wm[:K] = restate.calc_mvdr_weights(R, wq[:K], single=False)
+
+    def make():
+        bf = SubbandMVDRGSCPtr(fftlen=M)
+        for a in afbs:
+            bf.set_channel(a)
+        bf.calc_array_manifold_vectors(FS, g["delays"])
+        bf.set_diffuse_noise_model(g["mpos"], FS, 343740.0)
+        bf.set_all_diagonal_loading(float(g["mu"]))
+        bf.calc_mvdr_weights(FS, 1e-8, True)
+        assert bf.calc_blocking_matrix2()
+        return bf
+
+    def put(bf, wa):
+        for k in range(K):
+            bf.set_active_weights_f(k, np.stack([wa[k].real, wa[k].imag], axis=1).ravel())
+
+    B0 = np.stack([restate.calc_blocking_matrix(wm[k]) for k in range(K)])
+    wl1 = restate.active_to_wl(B0, wa1)
+    B1 = np.stack([B0[0]] + [restate.calc_blocking_matrix(wm[k] - wl1[k]) for k in range(1, K)])   # fbinX = 1 .. (beamformer.cc:2681)
+    # (a) set, upgrade: the output still uses the old wl; the branches come from the NEW matrix
+    bf = make(); put(bf, wa1); bf.upgrade_blocking_matrix()
+    wl = np.zeros((M, C), complex); wl[:K] = wl1
+    want_y = restate.subband_mvdr(X, wm, wl)
+    # the orthogonalizer with outChanX = 0 pulls the beamformer; the branch streams read the SAME frame (they never advance it,
+    # beamformer.cc:2793-2798), so they are driven frame by frame next to it
+    so0 = SubbandOrthogonalizerPtr(bf, outChanX=0)
+    branches = {i: SubbandOrthogonalizerPtr(bf, outChanX=i + 1) for i in (0, C - 2)}
+    Y, Z = [], {i: [] for i in branches}
+    for t, y in enumerate(so0):
+        Y.append(np.array(y))
+        for i, so in branches.items():
+            Z[i].append(np.array(so.next(t)))
+    Y = np.array(Y)
+    assert Y.shape == (X.shape[0], M) and rel_l2(Y[:, :K], want_y[:, :K]) < TOL
+    for i in branches:
+        Zi = np.array(Z[i])
+        want = np.einsum("kc,tck->tk", np.conj(B1[:, :, i]), X[:, :, :K])
+        assert Zi.shape == (X.shape[0], M) and rel_l2(Zi[:, :K], want) < TOL, i
+        assert rel_l2(Zi[:, K:], want_y[:, K:]) < TOL          # the reference's shared output vector keeps the beamformer's upper half
+    # (b) set, upgrade, set again: wl = B1 wa2
+    bf = make(); put(bf, wa1); bf.upgrade_blocking_matrix(); put(bf, wa2)
+    wl = np.zeros((M, C), complex); wl[:K] = restate.active_to_wl(B1, wa2)
+    Y = np.array([np.array(v) for v in bf])
+    assert rel_l2(Y[:, :K], restate.subband_mvdr(X, wm, wl)[:, :K]) < TOL
+    wl_old = np.zeros((M, C), complex); wl_old[:K] = restate.active_to_wl(B0, wa2)
+    assert rel_l2(Y[:, 1:K], restate.subband_mvdr(X, wm, wl_old)[:, 1:K]) > 1e-3      # and that differs from the matrix before the upgrade
+    # (c) without active weights the first branch is b_0^H x of calc_blocking_matrix2's matrix, bin 0 included
+    bf = make()
+    Z = []
+    for t, y in enumerate(bf):
+        Z.append(np.array(bf.blocking_matrix_output(0)))
+    assert rel_l2(np.array(Z)[:, :K], np.einsum("kc,tck->tk", np.conj(B0[:, :, 0]), X[:, :, :K])) < TOL
+
+
+@pytest.mark.gpu
+def test_synthesis_bank_input_source_vector(protos):
+    """OverSampledDFTSynthesisBank::input_source_vector (modulated/modulated.h:330): frames pushed before the first next() enter the
+    buffer ahead of the source's; the outputs are those of the concatenated sequence from block (number pushed) on (r = 0)."""
+    from oracle import restate
+    from distant_speech_recognition_b200.btk20.modulated import OverSampledDFTSynthesisBankPtr
+    from distant_speech_recognition_b200.btk20.stream import PyVectorComplexFeatureStreamPtr
+    M, m, r = 256, 2, 0
+    rng = np.random.default_rng(5)
+    gproto = rng.standard_normal(M * m) / M
+    T, P = 12, 3
+    Y = rng.standard_normal((T + P, M // 2 + 1)) + 1j * rng.standard_normal((T + P, M // 2 + 1))
+    Y[:, 0] = Y[:, 0].real; Y[:, -1] = Y[:, -1].real
+    full = restate._hermitian_fill(Y, M)
+
+    class Src:
+        def size(self):
+            return M
+        def __iter__(self):
+            return iter(full[P:])
+        def reset(self):
+            pass
+    syn = OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(Src()), prototype=gproto, M=M, m=m, r=r, delay_compensation_type=2)
+    for t in range(P):
+        syn.input_source_vector(full[t])
+    got = np.concatenate([np.array(v) for v in syn])
+    want = restate.synthesis(full, gproto, M, m, r, 2).reshape(-1, M)[P:].ravel()
+    assert got.shape == want.shape and rel_l2(got, want) < TOL
+    with pytest.raises(Exception):
+        OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(Src()), prototype=gproto, M=M, m=m, r=1, delay_compensation_type=2).input_source_vector(full[0])
