@@ -665,6 +665,7 @@ static int do_wpe(btkb_pipeline* p, int start_frame_no, int end_frame_no, bool a
   a.apply_only = apply_only ? 1 : 0;
   a.slot = p->wpe_slot; a.chunk_frame = p->wpe_chunk_frame; a.chol_threads = p->wpe_chol_threads;
   { const char* pf = getenv("BTKB_WPE_PREFETCH"); a.prefetch = pf ? atoi(pf) : 1; }
+  { const char* mm = getenv("BTKB_WPE_MMA"); a.mma = mm ? atoi(mm) : 1; }
   a.Sd = std::max(((a.est_frames >= 0) ? std::min(a.T, a.est_frames) : a.T) - a.lowerN, 0);
   a.form = (p->wpe_form >= 0) ? p->wpe_form : (a.Sd < a.L ? 1 : 0);   // the frame-domain system has S <= Sd rows, the lag-domain one L
   CK(cudaMemsetAsync(p->d_werr, 0, sizeof(int), p->stream));

@@ -111,6 +111,7 @@ struct WpeArgs {
   int chunk_frame;       // host side: problems per launch in the frame-domain form (`chunk` of launch_wpe serves the lag-domain form)
   int chol_threads;      // host side: CTA size of k_wpe_chol (0: 256 lag-domain, 128 frame-domain)
   int prefetch;          // k_wpe_chol: L1 prefetch of the trailing entries ahead of their update
+  int mma;               // k_wpe_chol (fp64): trailing update on the fp64 tensor cores (mma.sync m8n8k4)
   int* err_flag;         // set to 1 when a Cholesky pivot is not positive
   int U, C, T, Ts, K, G, Gp, D, laN, pdA;
   int lowerN, P, L, Lr, iterations, nbins, est_frames;

@@ -33,14 +33,15 @@
 #include "btkb_internal.h"
 #include <math.h>
 #include <algorithm>
+#include <type_traits>
 
 namespace btkb {
 namespace {
 
 constexpr int WPE_NB = 16;        // Cholesky panel width
-constexpr int WPE_LD = WPE_NB + 1; // row stride of the panel in shared memory (elements)
 constexpr int WPE_CORR_THREADS = 256;
 constexpr int WPE_CHOL_THREADS = 256;
+constexpr int WPE_CHOL_THREADS_FRAME = 128;   // frame-domain form: smaller systems, four CTAs per SM
 
 template <typename RT> struct cx { RT x, y; };
 template <typename RT> __device__ __forceinline__ cx<RT> mk(RT x, RT y) { cx<RT> r; r.x = x; r.y = y; return r; }
@@ -269,22 +270,39 @@ __global__ void __launch_bounds__(WPE_CORR_THREADS) k_wpe_gram_dual(WpeArgs a, i
   }
 }
 
-// elements of the panel buffer: the panel, or the first WPE_NB rows + the back-substitution vector, or (frame-domain form) the
-// nseries float2 series values that alias it outside the factorisation
+// ---- k_wpe_chol: shared-memory layout
+// The panel [rows][WPE_NB] lives in shared memory as two planes (real, imaginary) of RT with a row stride of WPE_PS = 20 elements
+// and the column index XOR-swizzled with the low four bits of the row: idx(r, j) = r * 20 + (j ^ (r & 15)).  That one layout is
+// conflict-free for both access shapes of the kernel: "every lane its own row, all lanes the same column" (scaling, TRSM, panel
+// load / store: 16 rows x one column hit 16 different 8-byte bank pairs, because the swizzle spreads a column over the 16
+// positions of a row group and the stride rotates the groups), and the fp64 tensor-core fragments of the trailing update (lane
+// l reads row l / 4, column k0 + l % 4: four rows x four columns per half-warp = 16 different bank pairs, because 20 elements
+// = 8 banks mod 32 separate the rows and the swizzle only permutes the four columns inside their aligned group).
+// RT = float keeps the interleaved layout (one 8-byte access per complex value, row stride 17 values): it has no tensor-core path.
+constexpr int WPE_PS = 20;
+constexpr int WPE_LD = WPE_NB + 1;
+__device__ __forceinline__ int pidx(int r, int j) { return r * WPE_PS + (j ^ (r & 15)); }
+// RT elements of the panel buffer: two planes of Lcap + 1 rows; (frame-domain form) at least the nseries float2 series values
+// that alias it outside the factorisation
 template <typename RT>
 __host__ __device__ inline size_t chol_region0(int Lcap, int nseries) {
-  size_t e = (size_t)(Lcap + 1) * WPE_LD;
-  const size_t e2 = (size_t)WPE_NB * WPE_LD + Lcap, e3 = ((size_t)nseries * sizeof(float2) + sizeof(cx<RT>) - 1) / sizeof(cx<RT>);
-  if (e2 > e) e = e2;
+  size_t e = (size_t)2 * (Lcap + 1) * (sizeof(RT) == 8 ? WPE_PS : WPE_LD);
+  const size_t e3 = ((size_t)nseries * sizeof(float2) + sizeof(RT) - 1) / sizeof(RT);
   if (e3 > e) e = e3;
-  return e;
+  return (e + 1) & ~(size_t)1;
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // one CTA per (problem, channel): diagonal bias + loading, panel Cholesky of the augmented matrix, backward substitution.
 // DUAL: the frame-domain system (K + delta_c Theta_c) z = ybar_c of size S = the utterance's estimation frames - lower, read from the
 // problem's shared K while the first panel is processed, then g_c = A z.
-template <typename RT, bool DUAL>
-__global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0, int C) {
+// MMA (RT = double): the trailing update A22 -= L21 L21^H runs on the fp64 tensor cores (mma.sync m8n8k4: measured 37.1 TFLOP/s on
+// this GPU, the rate of the DFMA pipe, with an eighth of the issue slots and a third of the shared-memory traffic of the scalar
+// tile): a warp owns a 16 x 16 block of the lower triangle, 2 x 2 fragments, real and imaginary parts as four real products.
+template <typename RT, bool DUAL, bool MMA>
+__global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREADS, DUAL ? 4 : 2) k_wpe_chol(WpeArgs a, int q0, int C) {
   extern __shared__ __align__(16) unsigned char smem[];
   typedef cx<RT> CX;
   const int qq = blockIdx.x / C, c = blockIdx.x - qq * C;
@@ -295,18 +313,20 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
   const int Lr = a.Lr, n = L + 1;
   CX* A = reinterpret_cast<CX*>(a.Rw) + ((size_t)qq * (DUAL ? C + 1 : C) + c) * a.slot;
   const CX* Kq = reinterpret_cast<const CX*>(a.Rw) + ((size_t)qq * (C + 1) + C) * a.slot;   // DUAL only
-  CX* Pn = reinterpret_cast<CX*>(smem);                   // [n][WPE_LD] current panel (rows relative to j0); row stride 17
-                                                           // elements: lanes on consecutive rows hit different banks
-  CX* yv = Pn + (size_t)WPE_NB * WPE_LD;                   // [L] back-substitution vector: lives inside the panel buffer (the
-                                                           // back substitution only needs its first WPE_NB rows as the diagonal block)
   const int xstride = a.P + a.T;
-  RT* red = reinterpret_cast<RT*>(Pn + chol_region0<RT>(Lcap, DUAL ? C * xstride : 0));   // [32]
-  RT* dinv = red + 16;                                     // [WPE_NB] 1 / L_jj of the current diagonal block
+  RT* Pre = reinterpret_cast<RT*>(smem);                   // current panel, rows relative to j0: real plane ...
+  RT* Pim = Pre + (size_t)(Lcap + 1) * WPE_PS;             // ... and imaginary plane
+  RT* red = Pre + chol_region0<RT>(Lcap, DUAL ? C * xstride : 0);   // [16] block reduction, [16] 1 / L_jj of the current diagonal block
+  RT* dinv = red + 16;
   unsigned char* tri = reinterpret_cast<unsigned char*>(red + 32);   // [136][2] (row, column) of the e-th entry of a lower triangle
-  RT* th = reinterpret_cast<RT*>(tri + 272);               // DUAL: [Lcap] theta_c(s + lower)
-  CX* zs = reinterpret_cast<CX*>(th + ((Lcap + 1) & ~1));  // DUAL: [Lcap] the solution z (and 1 / theta as scratch in the prologue)
-  float2* xs = reinterpret_cast<float2*>(Pn);              // DUAL: the C series [C][P + T]; ALIASES the panel buffer — alive only before
+  CX* yv = reinterpret_cast<CX*>(tri + 272);               // [Lcap] back-substitution vector (DUAL prologue: 1 / theta as scratch)
+  RT* th = reinterpret_cast<RT*>(yv + Lcap);               // DUAL: [Lcap] theta_c(s + lower)
+  float2* xs = reinterpret_cast<float2*>(smem);            // DUAL: the C series [C][P + T]; ALIASES the panel buffer — alive only before
                                                            // the first panel is loaded (delta) and after the back substitution (g = A z)
+  constexpr bool PLANAR = sizeof(RT) == 8;
+  CX* Pn = reinterpret_cast<CX*>(smem);                    // RT = float: interleaved panel
+  auto ldp = [&](int r, int j) -> CX { if (PLANAR) { const int i = pidx(r, j); return mk<RT>(Pre[i], Pim[i]); } return Pn[r * WPE_LD + j]; };
+  auto stp = [&](int r, int j, const CX& v) { if (PLANAR) { const int i = pidx(r, j); Pre[i] = v.x; Pim[i] = v.y; } else Pn[r * WPE_LD + j] = v; };
   const int tid = threadIdx.x;
   const RT bias = (RT)a.diagonal_bias, loadf = (RT)a.load_factor;
   RT delta = 0;
@@ -320,7 +340,7 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
   if (DUAL) {
     // ---- delta_c = bias + load_factor (max_i R_ii + bias), R_ii = sum_s |lags_i(s)|^2 / theta_c(s)   (calc_Rr_ :577-580, load_R_ :648-663)
     load_series(a, g, nfr, xs, xstride);
-    RT* wi = reinterpret_cast<RT*>(zs);                    // 1 / theta
+    RT* wi = reinterpret_cast<RT*>(yv);                    // 1 / theta
     for (int s2 = tid; s2 < L; s2 += blockDim.x) {
       const RT t = (RT)a.TH[((size_t)g * C + c) * a.Ts + s2 + a.lowerN];
       th[s2] = t; wi[s2] = (RT)1 / t;
@@ -378,32 +398,42 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
   for (int j0 = 0; j0 < L; j0 += WPE_NB) {
     const int nb = min(WPE_NB, L - j0);
     const int nrows = n - j0;   // rows j0 .. L (the augmented row included)
-    // ---- load the panel
-    for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
-      const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      Pn[r * WPE_LD + jj] = (jj < nb && jj <= r) ? ((DUAL && j0 == 0) ? src0(r, jj) : A[(size_t)(j0 + r) * Lr + j0 + jj]) : mk<RT>(0, 0);
+    // ---- load the panel (columns >= nb and the part above the diagonal as zeros)
+    // (four loads in flight per thread before the first store: the values come from L2)
+    for (int i0 = tid; i0 < nrows * WPE_NB; i0 += 4 * blockDim.x) {
+      CX v4[4];
+#pragma unroll
+      for (int u4 = 0; u4 < 4; u4++) {
+        const int i = i0 + u4 * blockDim.x, r = i / WPE_NB, jj = i - r * WPE_NB;
+        v4[u4] = (i < nrows * WPE_NB && jj < nb && jj <= r) ? ((DUAL && j0 == 0) ? src0(r, jj) : A[(size_t)(j0 + r) * Lr + j0 + jj]) : mk<RT>(0, 0);
+      }
+#pragma unroll
+      for (int u4 = 0; u4 < 4; u4++) {
+        const int i = i0 + u4 * blockDim.x, r = i / WPE_NB, jj = i - r * WPE_NB;
+        if (i < nrows * WPE_NB) stp(r, jj, v4[u4]);
+      }
     }
     __syncthreads();
     // ---- factor the nb x nb diagonal block with ONE warp (no CTA barrier inside): per column a scaling by 1 / sqrt(pivot), then the
     // rank-one update of the remaining triangle with its (row, column) pairs dealt out to the 32 lanes
     if (tid < 32) {
       for (int jj = 0; jj < nb; jj++) {
-        const RT dj = Pn[jj * WPE_LD + jj].x;
+        const RT dj = ldp(jj, jj).x;
         if (!(dj > (RT)0)) bad = true;
         const RT inv = rsqrt(fmax(dj, (RT)1e-30));
         __syncwarp();   // every lane has read the pivot before its owner overwrites it
         if (tid >= jj && tid < nb) {
-          if (tid == jj) { Pn[tid * WPE_LD + jj] = mk<RT>(dj * inv, 0); dinv[jj] = inv; }
-          else { const CX v = Pn[tid * WPE_LD + jj]; Pn[tid * WPE_LD + jj] = mk<RT>(v.x * inv, v.y * inv); }
+          if (tid == jj) { stp(tid, jj, mk<RT>(dj * inv, 0)); dinv[jj] = inv; }
+          else { const CX v = ldp(tid, jj); stp(tid, jj, mk<RT>(v.x * inv, v.y * inv)); }
         }
         __syncwarp();
         const int m = nb - 1 - jj;
         for (int e = tid; e < m * (m + 1) / 2; e += 32) {
           const int r = jj + 1 + tri[2 * e], kk = jj + 1 + tri[2 * e + 1];
-          CX v = Pn[r * WPE_LD + kk];
-          cmsubc(v, Pn[r * WPE_LD + jj], Pn[kk * WPE_LD + jj]);
+          CX v = ldp(r, kk);
+          cmsubc(v, ldp(r, jj), ldp(kk, jj));
           if (kk == r) v.y = 0;
-          Pn[r * WPE_LD + kk] = v;
+          stp(r, kk, v);
         }
         __syncwarp();
       }
@@ -412,10 +442,9 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     // ---- ... then the rows below it are independent: L21 = A21 L11^-H, one thread per row held in registers, right-looking (once
     // x_jj is final the remaining entries of the row take their updates independently of one another), no barrier
     for (int r = nb + tid; r < nrows; r += blockDim.x) {
-      CX* pr = Pn + (size_t)r * WPE_LD;
       CX v[WPE_NB];
 #pragma unroll
-      for (int jj = 0; jj < WPE_NB; jj++) v[jj] = pr[jj];
+      for (int jj = 0; jj < WPE_NB; jj++) v[jj] = ldp(r, jj);
 #pragma unroll
       for (int jj = 0; jj < WPE_NB; jj++) {
         if (jj < nb) {
@@ -423,8 +452,8 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
           v[jj] = mk<RT>(v[jj].x * inv, v[jj].y * inv);
 #pragma unroll
           for (int q = jj + 1; q < WPE_NB; q++)
-            if (q < nb) cmsubc(v[q], v[jj], Pn[q * WPE_LD + jj]);
-          pr[jj] = v[jj];
+            if (q < nb) cmsubc(v[q], v[jj], ldp(q, jj));
+          stp(r, jj, v[jj]);
         }
       }
     }
@@ -432,26 +461,95 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     // ---- write the factored panel back (needed by the backward substitution)
     for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
       const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      if (jj < nb && jj <= r) A[(size_t)(j0 + r) * Lr + j0 + jj] = Pn[r * WPE_LD + jj];
+      if (jj < nb && jj <= r) A[(size_t)(j0 + r) * Lr + j0 + jj] = ldp(r, jj);
     }
     // ---- trailing update: A[i][k] -= sum_jj Pn[i][jj] conj(Pn[k][jj]) for j1 <= k <= i <= L
     const int j1 = j0 + nb;
     const int nt = n - j1;             // trailing rows (incl. the augmented one)
-    if (nt > 0) {
+    if (MMA && nt > 0) {
+      // A warp owns 16 x 16 blocks (bi >= bk) of the trailing triangle.  S = L21(bi) L21(bk)^H as four real products per fragment:
+      // Sr = Ar Br^T + Ai Bi^T, Si = Ai Br^T - Ar Bi^T; the fragment of B^T is read from the panel exactly like the one of A (lane l:
+      // row l / 4, column k0 + l % 4).  A lane ends up with rows bi 16 + ti 8 + l / 4 and the column pairs bk 16 + tk 8 + 2 (l % 4) + {0, 1}:
+      // 32 contiguous bytes per read-modify-write of A.  Rows past the end are clamped for the loads and dropped at the store; columns
+      // >= nb of the panel are zero.
+      const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5, lr = lane >> 2, lc = lane & 3;
+      const int nb16 = (nt + 15) >> 4;
+      for (int bp = warp; bp < nb16 * (nb16 + 1) / 2; bp += nw) {
+        int bi = (int)((sqrtf(8.0f * (float)bp + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= bp) bi++;
+        while (bi * (bi + 1) / 2 > bp) bi--;
+        const int bk = bp - bi * (bi + 1) / 2;
+        const CX* base = (DUAL && j0 == 0) ? Kq : A;
+        if (a.prefetch) {
+#pragma unroll
+          for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+            for (int tk = 0; tk < 2; tk++) {
+              const int row = bi * 16 + ti * 8 + lr, col = bk * 16 + tk * 8 + 2 * lc;
+              if (row < nt && col < nt && col <= row) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)(j1 + row) * Lr + j1 + col));
+            }
+        }
+        int ba[2], ca[2], bb[2], cb[2];   // pidx(r, k0 + lc) = r * WPE_PS + ((lc ^ (r & 15)) ^ k0) for k0 = 0, 4, 8, 12
+#pragma unroll
+        for (int t2 = 0; t2 < 2; t2++) {
+          const int ra = nb + min(bi * 16 + t2 * 8 + lr, nt - 1), rb = nb + min(bk * 16 + t2 * 8 + lr, nt - 1);
+          ba[t2] = ra * WPE_PS; ca[t2] = lc ^ (ra & 15); bb[t2] = rb * WPE_PS; cb[t2] = lc ^ (rb & 15);
+        }
+        double sr[2][2][2], si[2][2][2];
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+          for (int tk = 0; tk < 2; tk++) { sr[ti][tk][0] = sr[ti][tk][1] = 0.0; si[ti][tk][0] = si[ti][tk][1] = 0.0; }
+#pragma unroll
+        for (int k0 = 0; k0 < WPE_NB; k0 += 4) {
+          double ar[2], ai[2], br[2], bim[2], nbi[2];
+#pragma unroll
+          for (int t2 = 0; t2 < 2; t2++) {
+            const int oa = ba[t2] + (ca[t2] ^ k0), ob = bb[t2] + (cb[t2] ^ k0);
+            ar[t2] = (double)Pre[oa]; ai[t2] = (double)Pim[oa]; br[t2] = (double)Pre[ob]; bim[t2] = (double)Pim[ob]; nbi[t2] = -bim[t2];
+          }
+#pragma unroll
+          for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+            for (int tk = 0; tk < 2; tk++) {
+              dmma884(sr[ti][tk][0], sr[ti][tk][1], ar[ti], br[tk]);
+              dmma884(sr[ti][tk][0], sr[ti][tk][1], ai[ti], bim[tk]);
+              dmma884(si[ti][tk][0], si[ti][tk][1], ai[ti], br[tk]);
+              dmma884(si[ti][tk][0], si[ti][tk][1], ar[ti], nbi[tk]);
+            }
+        }
+        // read-modify-write of the block: all eight old values are requested before the first store (the compiler cannot move a load
+        // of A across a store to A, and each would otherwise be its own round trip to L2)
+        CX old[2][2][2];
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+          for (int tk = 0; tk < 2; tk++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int row = bi * 16 + ti * 8 + lr, col = bk * 16 + tk * 8 + 2 * lc + e;
+              if (row < nt && col < nt && col <= row) old[ti][tk][e] = (DUAL && j0 == 0) ? src0(j1 + row, j1 + col) : A[(size_t)(j1 + row) * Lr + j1 + col];
+            }
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+          for (int tk = 0; tk < 2; tk++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int row = bi * 16 + ti * 8 + lr, col = bk * 16 + tk * 8 + 2 * lc + e;
+              if (row < nt && col < nt && col <= row)
+                A[(size_t)(j1 + row) * Lr + j1 + col] = mk<RT>(old[ti][tk][e].x - (RT)sr[ti][tk][e], old[ti][tk][e].y - (RT)si[ti][tk][e]);
+            }
+      }
+    } else if (nt > 0) {
       // A thread owns the entries (ri + q nt4, rk + p nt4), q, p = 0..3, of the trailing block (nt4 = ceil(nt / 4)): the
-      // four-way interleave puts the lanes of a warp on CONSECUTIVE panel rows (conflict-free 16-byte loads with the padded
-      // stride, the row operand is a broadcast) and makes the global read-modify-write of A coalesced along a row.  Of the
-      // 16 entries the 6 with q > p always lie in the lower triangle, the 4 with q == p do iff rk <= ri, the rest never.
+      // four-way interleave puts the lanes of a warp on CONSECUTIVE panel rows and makes the global read-modify-write of A
+      // coalesced along a row.  Of the 16 entries the 6 with q > p always lie in the lower triangle, the 4 with q == p do iff
+      // rk <= ri, the rest never.
       const int nt4 = (nt + 3) / 4;
       for (int tq = tid; tq < nt4 * nt4; tq += blockDim.x) {
         const int ri = tq / nt4, rk = tq - ri * nt4;
         const bool diag = rk <= ri;
-        const CX* pa[4]; const CX* pb[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          pa[q] = Pn + (size_t)(nb + min(ri + q * nt4, nt - 1)) * WPE_LD;
-          pb[q] = Pn + (size_t)(nb + min(rk + q * nt4, nt - 1)) * WPE_LD;
-        }
         if (a.prefetch) {
           // the entries this tile will read-modify-write come from L2 (or, first panel of the frame-domain form, from K): ask for them
           // now so that they sit in L1 when the 16-column product below is done — no registers are held while they travel
@@ -465,6 +563,9 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)(j1 + row) * Lr + j1 + col));
             }
         }
+        int pa[4], pb[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { pa[q] = nb + min(ri + q * nt4, nt - 1); pb[q] = nb + min(rk + q * nt4, nt - 1); }
         CX sd[4], so[6];
 #pragma unroll
         for (int e = 0; e < 4; e++) sd[e] = mk<RT>(0, 0);
@@ -473,7 +574,7 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
         for (int jj = 0; jj < nb; jj++) {
           CX av[4], bv[4];
 #pragma unroll
-          for (int q = 0; q < 4; q++) { av[q] = pa[q][jj]; bv[q] = pb[q][jj]; }
+          for (int q = 0; q < 4; q++) { av[q] = ldp(pa[q], jj); bv[q] = ldp(pb[q], jj); }
           if (diag) {
 #pragma unroll
             for (int q = 0; q < 4; q++) cmsubc(sd[q], av[q], bv[q]);
@@ -481,45 +582,53 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
           cmsubc(so[0], av[1], bv[0]); cmsubc(so[1], av[2], bv[0]); cmsubc(so[2], av[2], bv[1]);
           cmsubc(so[3], av[3], bv[0]); cmsubc(so[4], av[3], bv[1]); cmsubc(so[5], av[3], bv[2]);
         }
-        auto upd = [&](int q, int pcol, const CX& sv) {
+        // all old values are requested before the first store (see the tensor-core branch)
+        auto fetch = [&](int q, int pcol, CX& sv) {   // sv <- old + sv
           const int row = ri + q * nt4, col = rk + pcol * nt4;
           if (row < nt && col < nt) {
-            CX* dst = A + (size_t)(j1 + row) * Lr + j1 + col;
-            CX v = (DUAL && j0 == 0) ? src0(j1 + row, j1 + col) : *dst;
-            v.x += sv.x; v.y += sv.y; *dst = v;
+            const CX v = (DUAL && j0 == 0) ? src0(j1 + row, j1 + col) : A[(size_t)(j1 + row) * Lr + j1 + col];
+            sv.x += v.x; sv.y += v.y;
           }
+        };
+        auto put = [&](int q, int pcol, const CX& sv) {
+          const int row = ri + q * nt4, col = rk + pcol * nt4;
+          if (row < nt && col < nt) A[(size_t)(j1 + row) * Lr + j1 + col] = sv;
         };
         if (diag) {
 #pragma unroll
-          for (int q = 0; q < 4; q++) upd(q, q, sd[q]);
+          for (int q = 0; q < 4; q++) fetch(q, q, sd[q]);
         }
-        upd(1, 0, so[0]); upd(2, 0, so[1]); upd(2, 1, so[2]); upd(3, 0, so[3]); upd(3, 1, so[4]); upd(3, 2, so[5]);
+        fetch(1, 0, so[0]); fetch(2, 0, so[1]); fetch(2, 1, so[2]); fetch(3, 0, so[3]); fetch(3, 1, so[4]); fetch(3, 2, so[5]);
+        if (diag) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) put(q, q, sd[q]);
+        }
+        put(1, 0, so[0]); put(2, 0, so[1]); put(2, 1, so[2]); put(3, 0, so[3]); put(3, 1, so[4]); put(3, 2, so[5]);
       }
     }
     __syncthreads();
   }
   if (bad && tid == 0) atomicExch(a.err_flag, 1);
 
-  // ---- backward substitution L^H gvec = y, y_j = conj(A[L][j])
+  // ---- backward substitution L^H gvec = y, y_j = conj(A[L][j]); the diagonal block of a panel sits in rows 0 .. 15 of the panel buffer
   for (int j = tid; j < L; j += blockDim.x) { const CX v = A[(size_t)L * Lr + j]; yv[j] = mk<RT>(v.x, -v.y); }
   __syncthreads();
-  CX* Db = Pn;  // [WPE_NB][WPE_NB] diagonal block
   for (int j0 = ((L - 1) / WPE_NB) * WPE_NB; j0 >= 0; j0 -= WPE_NB) {
     const int nb = min(WPE_NB, L - j0);
     for (int i = tid; i < nb * WPE_NB; i += blockDim.x) {
       const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      Db[r * WPE_LD + jj] = (jj <= r && jj < nb) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0);
+      stp(r, jj, (jj <= r && jj < nb) ? A[(size_t)(j0 + r) * Lr + j0 + jj] : mk<RT>(0, 0));
     }
     __syncthreads();
     if (tid < 32) {   // column sweep: once g_jj is final, the lanes q < jj take y_q -= g_jj conj(L[jj][q])
-      const RT invd = (tid < nb) ? (RT)1 / Db[tid * WPE_LD + tid].x : (RT)0;
+      const RT invd = (tid < nb) ? (RT)1 / ldp(tid, tid).x : (RT)0;
       for (int jj = nb - 1; jj >= 0; jj--) {
         const CX yj = yv[j0 + jj];
         const RT inv = __shfl_sync(0xffffffffu, invd, jj);
         const CX gj = mk<RT>(yj.x * inv, yj.y * inv);
         __syncwarp();
         if (tid == jj) yv[j0 + jj] = gj;
-        else if (tid < jj) { CX sv = yv[j0 + tid]; cmsubc(sv, gj, Db[jj * WPE_LD + tid]); yv[j0 + tid] = sv; }
+        else if (tid < jj) { CX sv = yv[j0 + tid]; cmsubc(sv, gj, ldp(jj, tid)); yv[j0 + tid] = sv; }
         __syncwarp();
       }
     }
@@ -532,15 +641,13 @@ __global__ void __launch_bounds__(WPE_CHOL_THREADS) k_wpe_chol(WpeArgs a, int q0
     __syncthreads();
   }
   if (DUAL) {   // g_c = A z: g_i = sum_s lags_i(s) z_s
-    for (int j = tid; j < L; j += blockDim.x) zs[j] = yv[j];
-    __syncthreads();
     load_series(a, g, nfr, xs, xstride);
     __syncthreads();
     for (int i = tid; i < a.L; i += blockDim.x) {
       const float2* pi = xs + (size_t)(i / a.P) * xstride + a.P - (i % a.P);
       CX acc = mk<RT>(0, 0);
       for (int s2 = 0; s2 < L; s2++) {
-        const float2 v = pi[s2]; const CX z = zs[s2];
+        const float2 v = pi[s2]; const CX z = yv[s2];
         acc.x = fma((RT)v.x, z.x, acc.x); acc.x = fma(-(RT)v.y, z.y, acc.x); acc.y = fma((RT)v.x, z.y, acc.y); acc.y = fma((RT)v.y, z.x, acc.y);
       }
       a.Gf[((size_t)g * C + c) * a.L + i] = make_float2((float)acc.x, (float)acc.y);
@@ -576,14 +683,16 @@ static cudaError_t launch_wpe_t(const WpeArgs& a, int chunk, cudaStream_t st, in
   if ((size_t)(Lcap + 1) * a.Lr > a.slot || Lcap + 1 > a.Lr) return cudaErrorInvalidValue;
   const size_t sm_resid = ((size_t)C * xstride + (size_t)C * a.L) * sizeof(float2);
   const size_t sm_corr = (size_t)C * xstride * sizeof(cx<RT>) + (dual ? (size_t)WPE_GRAM_DG * (a.Sd + a.P) * sizeof(cx<RT>) : (size_t)C * a.T * sizeof(RT));
-  const size_t sm_chol = chol_region0<RT>(Lcap, dual ? C * xstride : 0) * sizeof(cx<RT>) + 32 * sizeof(RT) + 272 +
-                         (dual ? (size_t)((Lcap + 1) & ~1) * sizeof(RT) + (size_t)Lcap * sizeof(cx<RT>) : 0);
-  const int chol_threads = a.chol_threads > 0 ? a.chol_threads : (dual ? 128 : WPE_CHOL_THREADS);
+  const size_t sm_chol = chol_region0<RT>(Lcap, dual ? C * xstride : 0) * sizeof(RT) + 32 * sizeof(RT) + 272 + (size_t)Lcap * sizeof(cx<RT>) +
+                         (dual ? (size_t)Lcap * sizeof(RT) : 0);
+  const bool mma = std::is_same<RT, double>::value && a.mma;
+  const int chol_threads = dual ? std::min(a.chol_threads > 0 ? a.chol_threads : WPE_CHOL_THREADS_FRAME, WPE_CHOL_THREADS_FRAME)
+                                : (a.chol_threads > 0 ? a.chol_threads : WPE_CHOL_THREADS);
   if (dual) chunk = a.chunk_frame > 0 ? a.chunk_frame : chunk;
   if (sm_resid > 200 * 1024 || sm_corr > 200 * 1024 || sm_chol > 200 * 1024) return cudaErrorInvalidValue;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_wpe_resid<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_resid)) != cudaSuccess) return e;
-  void (*chol)(WpeArgs, int, int) = dual ? k_wpe_chol<RT, true> : k_wpe_chol<RT, false>;
+  void (*chol)(WpeArgs, int, int) = dual ? (mma ? k_wpe_chol<RT, true, true> : k_wpe_chol<RT, true, false>) : (mma ? k_wpe_chol<RT, false, true> : k_wpe_chol<RT, false, false>);
   if ((e = cudaFuncSetAttribute(chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol)) != cudaSuccess) return e;
   void (*corr)(WpeArgs, int) = nullptr;
   if (dual) corr = k_wpe_gram_dual<RT>;
