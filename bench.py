@@ -211,8 +211,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     numa = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs (its version banner at NCCL_DEBUG=WARN/INFO) goes to stderr: stdout carries the single JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries the single JSON line: NCCL prints its version banner to stdout when the first communicator is created
+        # (whatever NCCL_DEBUG says in this image), so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local))
     c = CFG
     U, C, n, M, m, r = c["U"], c["C"], c["n"], c["M"], c["m"], c["r"]

@@ -35,8 +35,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush(); saved_fd = os.dup(1); os.dup2(2, 1)   # NCCL's version banner goes to stderr, stdout carries the JSON line
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
     C, M, n = 8, 1024, 80000
     Ub, Ug = args.sub_batch, args.utterances_per_gpu
     assert Ug % Ub == 0
@@ -57,7 +61,7 @@ def main():
 
     sub_batch()                                        # warm-up (also pages the library in)
     T = p.num_frames
-    wpe_ms = p.last_timing_wpe(); tim = p.last_timing()
+    wpe_ms = p.last_timing_wpe(); tim = p.last_timing(); form = ("lag-domain (L x L)", "frame-domain (S x S)")[p.last_wpe_form()]
     parity = None
     if args.parity and rank == 0:
         from oracle import restate
@@ -83,7 +87,7 @@ def main():
         line = {"workload": "configs[4]: 8-mic SubbandGSC (NLMS) + multi-channel WPE (33 lags, 2 iterations, %s normal equations), 1024 subbands, %d utterances of 5 s on %d GPU(s) (%d per GPU, sub-batches of %d)"
                             % ("fp32" if args.fp32_normal_equations else "fp64", world * Ug, world, Ug, Ub),
                 "n_gpus": world, "utterances": world * Ug, "frames": frames, "seconds": dt, "frames_per_s": frames / dt, "xrt": world * Ug * (n / 16000.0) / dt,
-                "ms_per_utterance_per_gpu": 1e3 * dt / Ug, "wpe_ms_per_sub_batch": wpe_ms, "kernel_ms_per_sub_batch": tim, "parity_check": parity,
+                "ms_per_utterance_per_gpu": 1e3 * dt / Ug, "wpe_ms_per_sub_batch": wpe_ms, "wpe_normal_equations": form, "kernel_ms_per_sub_batch": tim, "parity_check": parity,
                 "input": "16-bit PCM resident on the host, uploaded per sub-batch (pageable); time signal left on the device"}
         if args.cpu_sample > 0:
             from oracle import ref, restate
