@@ -395,6 +395,8 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
   };
 
   bool bad = false;
+  bool ahead = false;   // look-ahead (tensor-core path): rows 0 .. 15 of the panel buffer already hold this panel's FACTORED diagonal block
+  int* ctr = reinterpret_cast<int*>(red + 15);   // next unclaimed block of the trailing update
   for (int j0 = 0; j0 < L; j0 += WPE_NB) {
     const int nb = min(WPE_NB, L - j0);
     const int nrows = n - j0;   // rows j0 .. L (the augmented row included)
@@ -405,29 +407,29 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
 #pragma unroll
       for (int u4 = 0; u4 < 4; u4++) {
         const int i = i0 + u4 * blockDim.x, r = i / WPE_NB, jj = i - r * WPE_NB;
-        v4[u4] = (i < nrows * WPE_NB && jj < nb && jj <= r) ? ((DUAL && j0 == 0) ? src0(r, jj) : A[(size_t)(j0 + r) * Lr + j0 + jj]) : mk<RT>(0, 0);
+        v4[u4] = (i < nrows * WPE_NB && jj < nb && jj <= r && !(ahead && r < WPE_NB)) ? ((DUAL && j0 == 0) ? src0(r, jj) : A[(size_t)(j0 + r) * Lr + j0 + jj]) : mk<RT>(0, 0);
       }
 #pragma unroll
       for (int u4 = 0; u4 < 4; u4++) {
         const int i = i0 + u4 * blockDim.x, r = i / WPE_NB, jj = i - r * WPE_NB;
-        if (i < nrows * WPE_NB) stp(r, jj, v4[u4]);
+        if (i < nrows * WPE_NB && !(ahead && r < WPE_NB)) stp(r, jj, v4[u4]);
       }
     }
     __syncthreads();
     // ---- factor the nb x nb diagonal block with ONE warp (no CTA barrier inside): per column a scaling by 1 / sqrt(pivot), then the
     // rank-one update of the remaining triangle with its (row, column) pairs dealt out to the 32 lanes
-    if (tid < 32) {
-      for (int jj = 0; jj < nb; jj++) {
+    auto factor_diag = [&](int nbd) {   // warp 0, all 32 lanes
+      for (int jj = 0; jj < nbd; jj++) {
         const RT dj = ldp(jj, jj).x;
         if (!(dj > (RT)0)) bad = true;
         const RT inv = rsqrt(fmax(dj, (RT)1e-30));
         __syncwarp();   // every lane has read the pivot before its owner overwrites it
-        if (tid >= jj && tid < nb) {
+        if (tid >= jj && tid < nbd) {
           if (tid == jj) { stp(tid, jj, mk<RT>(dj * inv, 0)); dinv[jj] = inv; }
           else { const CX v = ldp(tid, jj); stp(tid, jj, mk<RT>(v.x * inv, v.y * inv)); }
         }
         __syncwarp();
-        const int m = nb - 1 - jj;
+        const int m = nbd - 1 - jj;
         for (int e = tid; e < m * (m + 1) / 2; e += 32) {
           const int r = jj + 1 + tri[2 * e], kk = jj + 1 + tri[2 * e + 1];
           CX v = ldp(r, kk);
@@ -437,8 +439,17 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
         }
         __syncwarp();
       }
+    };
+    if (!ahead) {
+      if (tid < 32) factor_diag(nb);
+      __syncthreads();
     }
-    __syncthreads();
+    // the factored diagonal block goes back to A here (the backward substitution reads it): its rows of the panel buffer are free
+    // from the next barrier on
+    for (int i = tid; i < nb * WPE_NB; i += blockDim.x) {
+      const int r = i / WPE_NB, jj = i - r * WPE_NB;
+      if (jj < nb && jj <= r) A[(size_t)(j0 + r) * Lr + j0 + jj] = ldp(r, jj);
+    }
     // ---- ... then the rows below it are independent: L21 = A21 L11^-H, one thread per row held in registers, right-looking (once
     // x_jj is final the remaining entries of the row take their updates independently of one another), no barrier
     for (int r = nb + tid; r < nrows; r += blockDim.x) {
@@ -457,15 +468,20 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
         }
       }
     }
-    __syncthreads();
-    // ---- write the factored panel back (needed by the backward substitution)
-    for (int i = tid; i < nrows * WPE_NB; i += blockDim.x) {
-      const int r = i / WPE_NB, jj = i - r * WPE_NB;
-      if (jj < nb && jj <= r) A[(size_t)(j0 + r) * Lr + j0 + jj] = ldp(r, jj);
-    }
     // ---- trailing update: A[i][k] -= sum_jj Pn[i][jj] conj(Pn[k][jj]) for j1 <= k <= i <= L
     const int j1 = j0 + nb;
     const int nt = n - j1;             // trailing rows (incl. the augmented one)
+    // look-ahead: when the next panel is a full one, warp 0 takes block (0, 0) of the trailing triangle — the next diagonal block —
+    // first, keeps its updated values in rows 0 .. 15 of the panel buffer instead of storing them, and factors them there while the
+    // other warps work through the remaining blocks (claimed from a shared counter, so that warp 0 simply joins in late)
+    const bool look = MMA && (L - j1 >= WPE_NB);
+    if (tid == 0) *ctr = look ? 1 : 0;
+    __syncthreads();
+    // ---- write the factored rows below the diagonal block back (needed by the backward substitution)
+    for (int i = nb * WPE_NB + tid; i < nrows * WPE_NB; i += blockDim.x) {
+      const int r = i / WPE_NB, jj = i - r * WPE_NB;
+      if (jj < nb) A[(size_t)(j0 + r) * Lr + j0 + jj] = ldp(r, jj);
+    }
     if (MMA && nt > 0) {
       // A warp owns 16 x 16 blocks (bi >= bk) of the trailing triangle.  S = L21(bi) L21(bk)^H as four real products per fragment:
       // Sr = Ar Br^T + Ai Bi^T, Si = Ai Br^T - Ar Bi^T; the fragment of B^T is read from the panel exactly like the one of A (lane l:
@@ -474,7 +490,16 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
       // >= nb of the panel are zero.
       const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5, lr = lane >> 2, lc = lane & 3;
       const int nb16 = (nt + 15) >> 4;
-      for (int bp = warp; bp < nb16 * (nb16 + 1) / 2; bp += nw) {
+      bool mine = look && warp == 0;   // block (0, 0) is still to be done by this warp
+      for (;;) {
+        int bp = 0;
+        if (!mine) {
+          if (lane == 0) bp = atomicAdd(ctr, 1);
+          bp = __shfl_sync(0xffffffffu, bp, 0);
+          if (bp >= nb16 * (nb16 + 1) / 2) break;
+        }
+        const bool keep = mine;          // this block stays on chip
+        mine = false;
         int bi = (int)((sqrtf(8.0f * (float)bp + 1.0f) - 1.0f) * 0.5f);
         while ((bi + 1) * (bi + 2) / 2 <= bp) bi++;
         while (bi * (bi + 1) / 2 > bp) bi--;
@@ -537,10 +562,14 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
 #pragma unroll
             for (int e = 0; e < 2; e++) {
               const int row = bi * 16 + ti * 8 + lr, col = bk * 16 + tk * 8 + 2 * lc + e;
-              if (row < nt && col < nt && col <= row)
-                A[(size_t)(j1 + row) * Lr + j1 + col] = mk<RT>(old[ti][tk][e].x - (RT)sr[ti][tk][e], old[ti][tk][e].y - (RT)si[ti][tk][e]);
+              if (row < nt && col < nt && col <= row) {
+                const CX v = mk<RT>(old[ti][tk][e].x - (RT)sr[ti][tk][e], old[ti][tk][e].y - (RT)si[ti][tk][e]);
+                if (keep) stp(row, col, v); else A[(size_t)(j1 + row) * Lr + j1 + col] = v;
+              }
             }
+        if (keep) { __syncwarp(); factor_diag(WPE_NB); }
       }
+      (void)nw;
     } else if (nt > 0) {
       // A thread owns the entries (ri + q nt4, rk + p nt4), q, p = 0..3, of the trailing block (nt4 = ceil(nt / 4)): the
       // four-way interleave puts the lanes of a warp on CONSECUTIVE panel rows and makes the global read-modify-write of A
@@ -606,6 +635,7 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
         put(1, 0, so[0]); put(2, 0, so[1]); put(2, 1, so[2]); put(3, 0, so[3]); put(3, 1, so[4]); put(3, 2, so[5]);
       }
     }
+    ahead = look;
     __syncthreads();
   }
   if (bad && tid == 0) atomicExch(a.err_flag, 1);
