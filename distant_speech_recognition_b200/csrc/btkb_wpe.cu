@@ -16,9 +16,10 @@
 // (4 + 2C FMA per entry-frame instead of 4C).  The right-hand side rides along as row L of the matrix (the Cholesky factor
 // of [[R, r], [r^H, .]] carries L^-1 r in its last row), so the forward substitution costs nothing extra; k_wpe_chol is a
 // right-looking panel Cholesky (panel in shared memory, trailing update on the L2-resident workspace) followed by a
-// panel-wise backward substitution.  Arithmetic: fp64 like the reference (RT = double; the loaded normal equations need it for
-// the 1e-4 parity budget) or fp32 (cfg.wpe.fp32_normal_equations) on the CUDA cores; DESIGN.md K7 says why the Gram is not on the
-// tensor cores.
+// panel-wise backward substitution; in fp64 its trailing update runs on the fp64 tensor cores (mma.sync m8n8k4, SASS DMMA) and the
+// next diagonal block is factored ahead by one warp while the others finish the update (see k_wpe_chol).  Arithmetic: fp64 like the
+// reference (RT = double; the loaded normal equations need it for the 1e-4 parity budget) or fp32 (cfg.wpe.fp32_normal_equations) on
+// the CUDA cores; DESIGN.md K7 says why the Gram is not a tensor-core GEMM.
 //
 // Two forms of the same normal equations.  With A = [lags(s)] (L x S, S = estimation frames - lower), Theta_c = diag(theta_c) and
 // ybar_c(s) = conj(x_c(s)), calc_Rr_ + load_R_ build  (A Theta_c^-1 A^H + delta_c I) g_c = A Theta_c^-1 ybar_c  with the uniform
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
       // row l / 4, column k0 + l % 4).  A lane ends up with rows bi 16 + ti 8 + l / 4 and the column pairs bk 16 + tk 8 + 2 (l % 4) + {0, 1}:
       // 32 contiguous bytes per read-modify-write of A.  Rows past the end are clamped for the loads and dropped at the store; columns
       // >= nb of the panel are zero.
-      const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5, lr = lane >> 2, lc = lane & 3;
+      const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
       const int nb16 = (nt + 15) >> 4;
       bool mine = look && warp == 0;   // block (0, 0) is still to be done by this warp
       for (;;) {
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(DUAL ? WPE_CHOL_THREADS_FRAME : WPE_CHOL_THREA
             }
         if (keep) { __syncwarp(); factor_diag(WPE_NB); }
       }
-      (void)nw;
+
     } else if (nt > 0) {
       // A thread owns the entries (ri + q nt4, rk + p nt4), q, p = 0..3, of the trailing block (nt4 = ceil(nt / 4)): the
       // four-way interleave puts the lanes of a warp on CONSECUTIVE panel rows and makes the global read-modify-write of A
