@@ -543,6 +543,246 @@ __global__ void __launch_bounds__(32 * CHOL_WARPS) k_mvdr_solve_wide_chol(const 
   }
 }
 
+// The same Hermitian positive-definite solve as a BLOCKED Cholesky on the fp64 tensor cores, one CTA of four warps per chain, the whole
+// lower block triangle in shared memory (C = 16 NB: NB (NB + 1) / 2 blocks of 16 x 16, two planes (re, im), row stride 20 doubles,
+// column XOR-swizzled with the row inside the block: the layout of btkb_wpe.cu's panel, conflict-free both for row-per-lane sweeps and
+// for mma fragments; 51 KB at C = 64, four CTAs per SM).  Per 16-column panel: the diagonal block by one warp (column sweep, pairs of the
+// rank-one update dealt out to the lanes), L21 = A21 L11^-H one thread per row in registers, A22 -= L21 L21^H as mma.sync m8n8k4 f64 on
+// 16 x 16 blocks — nothing leaves the SM between loading R and storing w.  Then L y = d and L^H t = y panel by panel (the 16 x 16 solves
+// by shuffles in one warp, the rest one thread per row), w = t / (C t^H d).  Chains that are not Hermitian positive definite are flagged
+// for the pivoted LU exactly like k_mvdr_solve_wide_chol does.
+constexpr int BLK_THREADS = 128;
+constexpr int BLK_PS = 20;
+__device__ __forceinline__ int blk_idx(int r, int j) {   // block column of j <= block row of r
+  const int bi = r >> 4, bk = j >> 4;
+  return (bi * (bi + 1) / 2 + bk) * (16 * BLK_PS) + (r & 15) * BLK_PS + ((j & 15) ^ (r & 15));
+}
+__device__ __forceinline__ void dmma884w(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp,
+                                                                        float mu, int normalize, unsigned char* todo) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  __shared__ int s_ok;
+  __shared__ double s_lam[2][BLK_THREADS / 32];
+  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NB = C >> 4, plane = NB * (NB + 1) / 2 * 16 * BLK_PS;
+  double* Mre = reinterpret_cast<double*>(sm);
+  double* Mim = Mre + plane;
+  cdw* bv = reinterpret_cast<cdw*>(Mim + plane);   // [C] right-hand side / solution
+  double* dg = reinterpret_cast<double*>(bv + C);  // [C] the raw diagonal (Hermitian test)
+  double* dinv = dg + C;                           // [16] 1 / L_jj of the current diagonal block
+  auto ld = [&](int r, int j) -> cdw { const int i = blk_idx(r, j); return cw(Mre[i], Mim[i]); };
+  auto st = [&](int r, int j, cdw v) { const int i = blk_idx(r, j); Mre[i] = v.x; Mim[i] = v.y; };
+  const int u = g / K, k = g - u * K;
+  if (tid == 0) { todo[g] = 0; s_ok = 1; }
+  if (k == 0) { for (int c = tid; c < C; c += BLK_THREADS) W[(size_t)c * Gp + g] = make_float2(1.f, 0.f); return; }
+  double scale = 1.0;
+  if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
+  for (int c = tid; c < C; c += BLK_THREADS) {
+    dg[c] = (double)R[(size_t)(c * C + c) * Gp + g].x;
+    const float2 t = Dm[(size_t)c * Gp + g];
+    bv[c] = cw(t.x, t.y);
+  }
+  __syncthreads();
+  // ---- load the Hermitian part of the lower triangle (+ mu on the diagonal); four pairs of loads in flight per thread
+  bool herm = true;
+  for (int e0 = tid; e0 < C * C; e0 += 4 * BLK_THREADS) {
+    float2 a4[4], b4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = e0 + q * BLK_THREADS, i = e / C, j = e - i * C;
+      if (e < C * C && j <= i) { a4[q] = R[(size_t)(i * C + j) * Gp + g]; b4[q] = R[(size_t)(j * C + i) * Gp + g]; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = e0 + q * BLK_THREADS, i = e / C, j = e - i * C;
+      if (e < C * C && j <= i) {
+        cdw v = cw(0.5 * ((double)a4[q].x + (double)b4[q].x) * scale, 0.5 * ((double)a4[q].y - (double)b4[q].y) * scale);
+        if (i == j) { v.x += (double)mu; v.y = 0.0; }
+        st(i, j, v);
+        const double dr = (double)a4[q].x - (double)b4[q].x, di = (double)a4[q].y + (double)b4[q].y;
+        if (dr * dr + di * di > 1e-10 * fabs(dg[i] * dg[j]) + 1e-300) herm = false;
+      }
+    }
+  }
+  if (!herm) s_ok = 0;
+  __syncthreads();
+  if (!s_ok) { if (tid == 0) todo[g] = 1; return; }
+
+  // ---- blocked right-looking Cholesky
+  for (int p = 0; p < NB; p++) {
+    const int j0 = 16 * p;
+    if (warp == 0) {
+      for (int jj = 0; jj < 16; jj++) {
+        const double dj = Mre[blk_idx(j0 + jj, j0 + jj)];
+        if (!(dj > 0.0)) s_ok = 0;
+        const double inv = rsqrt(fmax(dj, 1e-300));
+        __syncwarp();   // every lane has read the pivot before its owner overwrites it
+        if (lane >= jj && lane < 16) {
+          if (lane == jj) { st(j0 + lane, j0 + jj, cw(dj * inv, 0.0)); dinv[jj] = inv; }
+          else { const cdw v = ld(j0 + lane, j0 + jj); st(j0 + lane, j0 + jj, cw(v.x * inv, v.y * inv)); }
+        }
+        __syncwarp();
+        const int m = 15 - jj;
+        for (int e = lane; e < m * (m + 1) / 2; e += 32) {
+          int rr = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+          while ((rr + 1) * (rr + 2) / 2 <= e) rr++;
+          while (rr * (rr + 1) / 2 > e) rr--;
+          const int r = j0 + jj + 1 + rr, kk = j0 + jj + 1 + (e - rr * (rr + 1) / 2);
+          const cdw lr_ = ld(r, j0 + jj), lk = ld(kk, j0 + jj);
+          cdw v = ld(r, kk);
+          v.x = fma(-lr_.x, lk.x, fma(-lr_.y, lk.y, v.x)); v.y = fma(-lr_.y, lk.x, fma(lr_.x, lk.y, v.y));   // v -= l_r conj(l_k)
+          if (kk == r) v.y = 0.0;
+          st(r, kk, v);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (!s_ok) { if (tid == 0) todo[g] = 1; return; }
+    // L21 = A21 L11^-H: one thread per row below the block, the row's 16 entries in registers, right-looking
+    {
+      const int r = j0 + 16 + tid;
+      if (r < C) {
+        cdw v[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; jj++) v[jj] = ld(r, j0 + jj);
+#pragma unroll
+        for (int jj = 0; jj < 16; jj++) {
+          const double inv = dinv[jj];
+          v[jj] = cw(v[jj].x * inv, v[jj].y * inv);
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            if (q > jj) {
+              const cdw l = ld(j0 + q, j0 + jj);
+              v[q].x = fma(-v[jj].x, l.x, fma(-v[jj].y, l.y, v[q].x)); v[q].y = fma(-v[jj].y, l.x, fma(v[jj].x, l.y, v[q].y));   // v_q -= x_jj conj(L[q][jj])
+            }
+          }
+          st(r, j0 + jj, v[jj]);
+        }
+      }
+    }
+    __syncthreads();
+    // A22 -= L21 L21^H on 16 x 16 blocks (bi >= bk > p), one block per warp and turn
+    {
+      const int nt = NB - 1 - p, lr = lane >> 2, lc = lane & 3;
+      for (int bp = warp; bp < nt * (nt + 1) / 2; bp += BLK_THREADS / 32) {
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= bp) bi++;
+        const int bk = bp - bi * (bi + 1) / 2;
+        const int ri = (p + 1 + bi) * 16, rk = (p + 1 + bk) * 16;
+        double sr[2][2][2], si[2][2][2];
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+          for (int tk = 0; tk < 2; tk++) { sr[ti][tk][0] = sr[ti][tk][1] = 0.0; si[ti][tk][0] = si[ti][tk][1] = 0.0; }
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0 += 4) {
+          double ar[2], ai[2], br[2], bim[2], nbi[2];
+#pragma unroll
+          for (int t2 = 0; t2 < 2; t2++) {
+            const int ia = blk_idx(ri + t2 * 8 + lr, j0 + k0 + lc), ib = blk_idx(rk + t2 * 8 + lr, j0 + k0 + lc);
+            ar[t2] = Mre[ia]; ai[t2] = Mim[ia]; br[t2] = Mre[ib]; bim[t2] = Mim[ib]; nbi[t2] = -bim[t2];
+          }
+#pragma unroll
+          for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+            for (int tk = 0; tk < 2; tk++) {
+              dmma884w(sr[ti][tk][0], sr[ti][tk][1], ar[ti], br[tk]);
+              dmma884w(sr[ti][tk][0], sr[ti][tk][1], ai[ti], bim[tk]);
+              dmma884w(si[ti][tk][0], si[ti][tk][1], ai[ti], br[tk]);
+              dmma884w(si[ti][tk][0], si[ti][tk][1], ar[ti], nbi[tk]);
+            }
+        }
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+          for (int tk = 0; tk < 2; tk++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int row = ri + ti * 8 + lr, col = rk + tk * 8 + 2 * lc + e;
+              if (col <= row) {
+                const int i = blk_idx(row, col);
+                Mre[i] -= sr[ti][tk][e]; Mim[i] = (col == row) ? 0.0 : Mim[i] - si[ti][tk][e];
+              }
+            }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- L y = d, panel by panel: the 16 x 16 triangular solve in one warp (lane q holds y_q; the finished entries travel by shuffle), then
+  // every row below takes its update
+  for (int p = 0; p < NB; p++) {
+    const int j0 = 16 * p;
+    if (warp == 0) {
+      const int q = lane & 15;
+      cdw y = bv[j0 + q];
+      const double invq = 1.0 / Mre[blk_idx(j0 + q, j0 + q)];
+      for (int jj = 0; jj < 16; jj++) {
+        const cdw gj = cw(__shfl_sync(0xffffffffu, y.x * invq, jj), __shfl_sync(0xffffffffu, y.y * invq, jj));
+        if (q == jj) y = gj;
+        else if (q > jj) y = cwmsub(y, ld(j0 + q, j0 + jj), gj);
+      }
+      if (lane < 16) bv[j0 + q] = y;
+    }
+    __syncthreads();
+    {
+      const int r = j0 + 16 + tid;
+      if (r < C) {
+        cdw s = bv[r];
+#pragma unroll
+        for (int jj = 0; jj < 16; jj++) s = cwmsub(s, ld(r, j0 + jj), bv[j0 + jj]);
+        bv[r] = s;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- L^H t = y, last panel first
+  for (int p = NB - 1; p >= 0; p--) {
+    const int j0 = 16 * p;
+    if (warp == 0) {
+      const int q = lane & 15;
+      cdw y = bv[j0 + q];
+      const double invq = 1.0 / Mre[blk_idx(j0 + q, j0 + q)];
+      for (int jj = 15; jj >= 0; jj--) {
+        const cdw tj = cw(__shfl_sync(0xffffffffu, y.x * invq, jj), __shfl_sync(0xffffffffu, y.y * invq, jj));
+        if (q == jj) y = tj;
+        else if (q < jj) { const cdw l = ld(j0 + jj, j0 + q); y = cwmsub(y, cw(l.x, -l.y), tj); }   // y_q -= conj(L[jj][q]) t_jj
+      }
+      if (lane < 16) bv[j0 + q] = y;
+    }
+    __syncthreads();
+    {
+      const int r = tid;
+      if (r < j0) {
+        cdw s = bv[r];
+#pragma unroll
+        for (int jj = 0; jj < 16; jj++) { const cdw l = ld(j0 + jj, r); s = cwmsub(s, cw(l.x, -l.y), bv[j0 + jj]); }
+        bv[r] = s;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- Lambda = t^H d, w = t / (C Lambda)
+  double lr = 0.0, li = 0.0;
+  for (int r = tid; r < C; r += BLK_THREADS) {
+    const float2 dd = Dm[(size_t)r * Gp + g]; const cdw tv = bv[r];
+    lr += tv.x * dd.x + tv.y * dd.y; li += tv.x * dd.y - tv.y * dd.x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lr += __shfl_xor_sync(0xffffffffu, lr, o); li += __shfl_xor_sync(0xffffffffu, li, o); }
+  if (lane == 0) { s_lam[0][warp] = lr; s_lam[1][warp] = li; }
+  __syncthreads();
+  lr = 0.0; li = 0.0;
+  for (int w = 0; w < BLK_THREADS / 32; w++) { lr += s_lam[0][w]; li += s_lam[1][w]; }
+  for (int r = tid; r < C; r += BLK_THREADS) {
+    const cdw wv = cwdiv(bv[r], cw(lr * C, li * C));
+    W[(size_t)r * Gp + g] = make_float2((float)wv.x, (float)wv.y);
+  }
+}
+
 static cudaError_t make_map_wide(CUtensorMap* tm, const PerBinArgs& a, int C) {
   return encode_tensor_map_2d_f32(tm, a.X, (cuuint64_t)2 * a.Gp, (cuuint64_t)a.T * C, (cuuint64_t)a.Gp * sizeof(float2), (cuuint32_t)(2 * TC), (cuuint32_t)C,
                                   CU_TENSOR_MAP_SWIZZLE_128B);
@@ -611,7 +851,23 @@ cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, 
   // the others for the pivoted LU.  Measured at configs[3] size (65 792 matrices of 64 x 64, profiles/r02p_wide_solve.jsonl): 16.9 ms
   // against 17.7 ms for the LU alone when every matrix is positive definite, 30.6 ms when none is (both kernels run) — one warp per chain
   // is latency-bound at 6 warps per SM, so the LU stays the default.
-  const bool use_chol = [] { const char* ev = getenv("BTKB_SOLVE_CHOL"); return ev && atoi(ev) != 0; }();
+  // BTKB_SOLVE_CHOL=2 (opt-in): the blocked tensor-core Cholesky, one CTA per chain with the matrix resident in shared memory.  Measured at
+  // configs[3] size (profiles/r02ah_wide_solve_blocked.txt): 12.6 ms against 16.9 ms (warp-per-chain Cholesky) and 17.7 ms (LU) when every matrix
+  // is positive definite, 28.5 ms when none is (62 noise frames for 64 channels with a 1e-4 loading: every chain falls back to the LU) —
+  // which is why the LU, whose time does not depend on the matrices, stays the default.
+  const int chol_mode = [] { const char* ev = getenv("BTKB_SOLVE_CHOL"); return ev ? atoi(ev) : 0; }();
+  const bool use_chol = chol_mode != 0;
+  if (chol_mode == 2 && todo != nullptr && C % 16 == 0 && C <= 64) {
+    // blocked Cholesky on the fp64 tensor cores, one CTA per chain, matrix resident in shared memory
+    const int NBk = C / 16;
+    const size_t smb = (size_t)2 * (NBk * (NBk + 1) / 2) * 16 * wide::BLK_PS * sizeof(double) + (size_t)C * sizeof(wide::cdw) + (size_t)(C + 16) * sizeof(double);
+    e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    if (e != cudaSuccess) return e;
+    wide::k_mvdr_solve_wide_blk<<<U * K, wide::BLK_THREADS, smb, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    lu<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+    return cudaGetLastError();
+  }
   if (use_chol && todo != nullptr) {
     const size_t smc = sizeof(wide::cdw) * (size_t)wide::CHOL_WARPS * ((size_t)C * (C + 1) / 2 + C);
     e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc);
