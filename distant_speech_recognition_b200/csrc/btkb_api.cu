@@ -35,7 +35,7 @@ struct btkb_pipeline {
   float2 *d_X = nullptr, *d_Y = nullptr, *d_W = nullptr, *d_TA = nullptr, *d_WL = nullptr, *d_WA = nullptr, *d_UA = nullptr, *d_R = nullptr;
   float *d_E = nullptr, *d_time = nullptr, *d_upd = nullptr, *d_PFW = nullptr;
   double *d_delays = nullptr, *d_mpos = nullptr, *d_labels = nullptr, *d_stats = nullptr;
-  unsigned char* d_mask = nullptr; int* d_count = nullptr; unsigned char* d_todo = nullptr;   // d_todo: [Gpcap] per-chain flags of the wide MVDR solve
+  unsigned char* d_mask = nullptr; int* d_count = nullptr; int* d_todo = nullptr;   // d_todo: [1 + Gpcap] chains the Cholesky pass of the wide MVDR solve leaves to the LU (d_todo[0] = count)
   void* d_scratch = nullptr; size_t scratch_bytes = 0;
   int16_t* d_x16 = nullptr; const int16_t* x16_cur = nullptr; int x16_stride = 0; double* h_delays = nullptr; float2* d_tw = nullptr;  // lazily allocated int16 staging; pinned host staging for delays
   double2 *d_pfR = nullptr, *d_pfInvR = nullptr; float2* d_pfQ = nullptr; float* d_LAM = nullptr;  // McCowan / Lefkimmiatis coherence + constants
@@ -547,8 +547,21 @@ int btkb_calc_mvdr_weights_ex(btkb_pipeline* p, float mu, float dthreshold) {
   CK(cudaSetDevice(p->cfg.device));
   if (p->C <= 8) CK(launch_mvdr_solve(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, dthreshold, p->stream));
   else {
-    if (!p->d_todo) CK(cudaMalloc((void**)&p->d_todo, (size_t)p->Gpcap));
-    CK(launch_mvdr_solve_wide(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, p->d_todo, p->stream));
+    if (!p->d_todo) CK(cudaMalloc((void**)&p->d_todo, ((size_t)p->Gpcap + 1) * sizeof(int)));
+    // Which solver (btkb_wide.cu: launch_mvdr_solve_wide).  The blocked tensor-core Cholesky is 2.3 x faster than the pivoted LU on Hermitian
+    // positive-definite matrices and leaves the others to the LU, so a batch it cannot factor pays for both.  A covariance accumulated on the
+    // device from fewer frames than channels is rank deficient (only the loading keeps it definite, and not in fp32 storage): such a batch
+    // goes straight to the LU.  BTKB_SOLVE_CHOL=0/1/2 and BTKB_SOLVE_IP=1 pin a solver.
+    int mode = 2;
+    if (p->R_is_sum) {
+      std::vector<int> cnt((size_t)p->wU);
+      CK(cudaMemcpyAsync(cnt.data(), p->d_count, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+      CK(cudaStreamSynchronize(p->stream));
+      for (int c : cnt) if (c < 2 * p->C) mode = 0;
+    }
+    if (const char* ev = getenv("BTKB_SOLVE_CHOL")) mode = std::min(2, std::max(0, atoi(ev)));
+    if (const char* ev = getenv("BTKB_SOLVE_IP")) { if (atoi(ev) != 0) mode = 3; }
+    CK(launch_mvdr_solve_wide(p->d_R, p->d_TA, p->d_W, p->d_count, p->wU, p->C, p->K, p->Gp, mu, p->R_is_sum ? 1 : 0, mode, p->d_todo, p->stream));
   }
   p->have_w = true;
   return BTKB_OK;

@@ -160,7 +160,8 @@ cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st);
 cudaError_t launch_covariance_tc(const PerBinArgs& a, cudaStream_t st);
 size_t covariance_tc_workspace_bytes(int G, int C, int T);   // C = 64: tcgen05 / TMEM (btkb_cov_tc.cu)
 cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize_by_count,
-                                   unsigned char* todo /* [U K] scratch flags, may be null */, cudaStream_t st);
+                                   int mode /* 0 LU, 1 warp Cholesky + LU, 2 blocked tensor-core Cholesky + LU, 3 implicit-pivoting LU */,
+                                   int* list /* [1 + U K] chains left to the LU by the Cholesky modes */, cudaStream_t st);
 cudaError_t launch_mainlobe_weights(const WeightsArgs& a, cudaStream_t st);
 
 // setup kernels (btkb_weights.cu)

@@ -12,6 +12,7 @@
 // covariance runs on the tensor cores instead (k_covariance_tc, btkb_cov_tc.cu: tcgen05 + TMEM).
 #include <cuda.h>
 #include "btkb_internal.h"
+#include <algorithm>
 #include "btkb_tensor_map.h"
 #include "btkb_fft.cuh"
 #include "../../include/btkb.h"
@@ -251,17 +252,22 @@ __device__ __forceinline__ cdw cwdiv(cdw a, cdw b) { double d = b.x * b.x + b.y 
 // pivot search on the q = 0 threads combined through shared memory, distributed row swap, elimination; two barriers per
 // column.  The back substitution runs column-oriented with every row updating itself.
 constexpr int SOLVE_Q = 4;
-__global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize, const unsigned char* todo) {
+// `list` non-null: the CTAs walk the chains list[1 .. list[0]] that a Cholesky kernel flagged (a small fixed grid: an empty list costs
+// nothing, where one CTA per chain — each claiming the 66 KB matrix buffer just to find its flag clear — cost 4.7 ms at configs[3] size).
+__global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu, int normalize, const int* list) {
   extern __shared__ __align__(16) unsigned char sm[];
-  if (todo != nullptr && !todo[blockIdx.x]) return;   // solved by the Cholesky kernel (uniform over the CTA)
   cdw* A = reinterpret_cast<cdw*>(sm);          // [C][C+1] augmented, row-major
   __shared__ double wbest[2]; __shared__ int widx[2];
   __shared__ double lam_part[2][2];
-  const int g = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int r = tid % C, q = tid / C;           // blockDim.x == SOLVE_Q * C
-  const int u = g / K, k = g - u * K;
   const int nwarp0 = (C + 31) / 32;             // warps holding the q = 0 threads
-  if (k == 0) { if (tid < C) W[(size_t)tid * Gp + g] = make_float2(1.f, 0.f); return; }
+  const int nwork = list ? list[0] : U * K;
+ for (int it = blockIdx.x; it < nwork; it += gridDim.x) {   // (every exit below is uniform over the CTA)
+  __syncthreads();                              // the previous chain's buffers are free
+  const int g = list ? list[1 + it] : it;
+  const int u = g / K, k = g - u * K;
+  if (k == 0) { if (tid < C) W[(size_t)tid * Gp + g] = make_float2(1.f, 0.f); continue; }
   double scale = 1.0;
   if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
   const int LD = C + 1;
@@ -327,6 +333,7 @@ __global__ void k_mvdr_solve_wide(const float2* R, const float2* Dm, float2* W, 
     const cdw wv = cwdiv(A[tid * LD + C], cw(lam_re * C, lam_im * C));
     W[(size_t)tid * Gp + g] = make_float2((float)wv.x, (float)wv.y);
   }
+ }
 }
 
 // The same elimination with IMPLICIT pivoting and ONE barrier per column (k_mvdr_solve_wide above: three — pivot search, row swap,
@@ -425,12 +432,12 @@ __global__ void k_mvdr_solve_wide_ip(const float2* R, const float2* Dm, float2* 
 // complex doubles, 33 KiB at C = 64 instead of the 66 KiB augmented square), lane l owns rows l and C - 1 - l (balanced: C - 1 - 2 j
 // trailing entries per column for every lane), dependent steps separated by __syncwarp instead of CTA barriers (the LU kernel above
 // spends its time in 4 x 64 of those), half the flops, no pivot search.  A chain whose matrix is not Hermitian (|a_ij - conj(a_ji)|^2
-// > 1e-10 a_ii a_jj) or not positive definite sets todo[g] = 1 and is left to the LU kernel, which then runs only for those chains.
+// > 1e-10 a_ii a_jj) or not positive definite is appended to `list` and left to the LU kernel, which then runs only for those chains.
 // R^H t = d with R Hermitian is R t = d;  w = t / (C t^H d)  (beamformer.cc:2386-2398), bin 0: all ones.
 constexpr int CHOL_WARPS = 2;
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
 __global__ void __launch_bounds__(32 * CHOL_WARPS) k_mvdr_solve_wide_chol(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp,
-                                                                          float mu, int normalize, unsigned char* todo) {
+                                                                          float mu, int normalize, int* list) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * CHOL_WARPS + warp;
@@ -439,7 +446,6 @@ __global__ void __launch_bounds__(32 * CHOL_WARPS) k_mvdr_solve_wide_chol(const 
   cdw* Lm = reinterpret_cast<cdw*>(sm) + (size_t)warp * (NT + C);   // packed lower triangle, then the right-hand side / solution [C]
   cdw* bv = Lm + NT;
   const int u = g / K, k = g - u * K;
-  if (lane == 0) todo[g] = 0;
   if (k == 0) { for (int c = lane; c < C; c += 32) W[(size_t)c * Gp + g] = make_float2(1.f, 0.f); return; }
   double scale = 1.0;
   if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
@@ -505,7 +511,7 @@ __global__ void __launch_bounds__(32 * CHOL_WARPS) k_mvdr_solve_wide_chol(const 
     }
     __syncwarp();
   }
-  if (!ok) { if (lane == 0) todo[g] = 1; return; }
+  if (!ok) { if (lane == 0) list[1 + atomicAdd(list, 1)] = g; return; }   // left to the pivoted LU
   // ---- L y = d (forward), L^H t = y (backward); column-oriented, every lane updates its own rows
   for (int i = 0; i < C; i++) {
     const cdw yi = cw(bv[i].x / Lm[tri(i, i)].x, bv[i].y / Lm[tri(i, i)].x);   // every lane computes the same value from broadcast reads
@@ -561,9 +567,9 @@ __device__ __forceinline__ void dmma884w(double& c0, double& c1, double a, doubl
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const float2* R, const float2* Dm, float2* W, const int* noise_count, int U, int C, int K, int Gp,
-                                                                        float mu, int normalize, unsigned char* todo) {
+                                                                        float mu, int normalize, int* list) {
   extern __shared__ __align__(16) unsigned char sm[];
-  __shared__ int s_ok;
+  __shared__ int s_ok, s_herm;   // pivots positive so far / matrix Hermitian (two flags: each is written in one phase and read after the barrier that ends it)
   __shared__ double s_lam[2][BLK_THREADS / 32];
   const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NB = C >> 4, plane = NB * (NB + 1) / 2 * 16 * BLK_PS;
@@ -575,7 +581,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
   auto ld = [&](int r, int j) -> cdw { const int i = blk_idx(r, j); return cw(Mre[i], Mim[i]); };
   auto st = [&](int r, int j, cdw v) { const int i = blk_idx(r, j); Mre[i] = v.x; Mim[i] = v.y; };
   const int u = g / K, k = g - u * K;
-  if (tid == 0) { todo[g] = 0; s_ok = 1; }
+  if (tid == 0) { s_ok = 1; s_herm = 1; }
   if (k == 0) { for (int c = tid; c < C; c += BLK_THREADS) W[(size_t)c * Gp + g] = make_float2(1.f, 0.f); return; }
   double scale = 1.0;
   if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
@@ -606,9 +612,9 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
       }
     }
   }
-  if (!herm) s_ok = 0;
+  if (!herm) s_herm = 0;
   __syncthreads();
-  if (!s_ok) { if (tid == 0) todo[g] = 1; return; }
+  if (!s_herm) { if (tid == 0) list[1 + atomicAdd(list, 1)] = g; return; }   // left to the pivoted LU
 
   // ---- blocked right-looking Cholesky
   for (int p = 0; p < NB; p++) {
@@ -640,7 +646,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
       }
     }
     __syncthreads();
-    if (!s_ok) { if (tid == 0) todo[g] = 1; return; }
+    if (!s_ok) { if (tid == 0) list[1 + atomicAdd(list, 1)] = g; return; }   // left to the pivoted LU
     // L21 = A21 L11^-H: one thread per row below the block, the row's 16 entries in registers, right-looking
     {
       const int r = j0 + 16 + tid;
@@ -718,7 +724,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
     const int j0 = 16 * p;
     if (warp == 0) {
       const int q = lane & 15;
-      cdw y = bv[j0 + q];
+      cdw y = (lane < 16) ? bv[j0 + q] : cw(0.0, 0.0);   // lanes 16 .. 31 only keep the shuffles full-warp
       const double invq = 1.0 / Mre[blk_idx(j0 + q, j0 + q)];
       for (int jj = 0; jj < 16; jj++) {
         const cdw gj = cw(__shfl_sync(0xffffffffu, y.x * invq, jj), __shfl_sync(0xffffffffu, y.y * invq, jj));
@@ -744,7 +750,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
     const int j0 = 16 * p;
     if (warp == 0) {
       const int q = lane & 15;
-      cdw y = bv[j0 + q];
+      cdw y = (lane < 16) ? bv[j0 + q] : cw(0.0, 0.0);
       const double invq = 1.0 / Mre[blk_idx(j0 + q, j0 + q)];
       for (int jj = 15; jj >= 0; jj--) {
         const cdw tj = cw(__shfl_sync(0xffffffffu, y.x * invq, jj), __shfl_sync(0xffffffffu, y.y * invq, jj));
@@ -837,47 +843,40 @@ cudaError_t launch_covariance_wide(const PerBinArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_mvdr_solve_wide(const float2* R, const float2* D, float2* W, const int* noise_count, int U, int C, int K, int Gp, float mu,
-                                   int normalize_by_count, unsigned char* todo, cudaStream_t st) {
+                                   int normalize_by_count, int mode, int* list, cudaStream_t st) {
+  // mode 0: pivoted LU for every chain (time independent of the matrices: 17.7 ms at configs[3] size).
+  // mode 1 / 2: Hermitian positive-definite chains by a Cholesky kernel — 1: one warp per chain (16.9 ms), 2: blocked, on the fp64 tensor cores,
+  //   matrix resident in shared memory (7.8 ms) — which appends every other chain to `list` (list[0] = count) for the LU, run by a small fixed
+  //   grid over that list.  A batch of numerically indefinite matrices (62 noise frames for 64 channels with a 1e-4 loading) costs both passes;
+  //   btkb_api.cu picks the mode per call from what it knows about the matrices (frames accumulated per utterance), BTKB_SOLVE_CHOL overrides.
+  // mode 3: the LU with implicit pivoting (one barrier per column; 18.1 ms, profiles/r02q_*: the barrier COUNT is not what limits the LU —
+  //   137 k warp instructions per matrix for 11 k warp-DFMAs of elimination work, issue slots 43 %, fp64 pipe 23 %).
   const size_t smem = sizeof(wide::cdw) * (size_t)C * (C + 1);
-  // BTKB_SOLVE_IP=1 (opt-in): implicit pivoting, one barrier per column instead of three.  Measured 18.07 vs 17.80 ms at configs[3] size
-  // (profiles/r02p_wide_solve.jsonl): the barrier COUNT is not what limits this kernel — ncu (profiles/r02q_ncu_k_mvdr_solve_wide_ip_details.txt):
-  // 137 k warp instructions per matrix for 11 k warp-DFMAs of elimination work, issue slots 43 %, fp64 pipe 23 %, barrier stall still
-  // 4.8 per issue because the 8 warps of a CTA wait for the 2 that search the pivot and for each other's shared-memory latency.
-  const bool ip = [] { const char* ev = getenv("BTKB_SOLVE_IP"); return ev && atoi(ev) != 0; }();
-  auto lu = ip ? wide::k_mvdr_solve_wide_ip : wide::k_mvdr_solve_wide;
-  cudaError_t e = cudaFuncSetAttribute(lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  // BTKB_SOLVE_CHOL=1 (opt-in, read at every call): Hermitian positive-definite matrices go through the warp-per-chain Cholesky, which flags
-  // the others for the pivoted LU.  Measured at configs[3] size (65 792 matrices of 64 x 64, profiles/r02p_wide_solve.jsonl): 16.9 ms
-  // against 17.7 ms for the LU alone when every matrix is positive definite, 30.6 ms when none is (both kernels run) — one warp per chain
-  // is latency-bound at 6 warps per SM, so the LU stays the default.
-  // BTKB_SOLVE_CHOL=2 (opt-in): the blocked tensor-core Cholesky, one CTA per chain with the matrix resident in shared memory.  Measured at
-  // configs[3] size (profiles/r02ah_wide_solve_blocked.txt): 12.6 ms against 16.9 ms (warp-per-chain Cholesky) and 17.7 ms (LU) when every matrix
-  // is positive definite, 28.5 ms when none is (62 noise frames for 64 channels with a 1e-4 loading: every chain falls back to the LU) —
-  // which is why the LU, whose time does not depend on the matrices, stays the default.
-  const int chol_mode = [] { const char* ev = getenv("BTKB_SOLVE_CHOL"); return ev ? atoi(ev) : 0; }();
-  const bool use_chol = chol_mode != 0;
-  if (chol_mode == 2 && todo != nullptr && C % 16 == 0 && C <= 64) {
-    // blocked Cholesky on the fp64 tensor cores, one CTA per chain, matrix resident in shared memory
-    const int NBk = C / 16;
-    const size_t smb = (size_t)2 * (NBk * (NBk + 1) / 2) * 16 * wide::BLK_PS * sizeof(double) + (size_t)C * sizeof(wide::cdw) + (size_t)(C + 16) * sizeof(double);
-    e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-    if (e != cudaSuccess) return e;
-    wide::k_mvdr_solve_wide_blk<<<U * K, wide::BLK_THREADS, smb, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    lu<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+  if (mode == 3) {
+    if ((e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_ip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    wide::k_mvdr_solve_wide_ip<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, nullptr);
     return cudaGetLastError();
   }
-  if (use_chol && todo != nullptr) {
-    const size_t smc = sizeof(wide::cdw) * (size_t)wide::CHOL_WARPS * ((size_t)C * (C + 1) / 2 + C);
-    e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc);
-    if (e != cudaSuccess) return e;
-    wide::k_mvdr_solve_wide_chol<<<(U * K + wide::CHOL_WARPS - 1) / wide::CHOL_WARPS, 32 * wide::CHOL_WARPS, smc, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+  if ((mode == 1 || mode == 2) && list != nullptr) {
+    if ((e = cudaMemsetAsync(list, 0, sizeof(int), st)) != cudaSuccess) return e;
+    if (mode == 2 && C % 16 == 0 && C <= 64) {
+      const int NBk = C / 16;
+      const size_t smb = (size_t)2 * (NBk * (NBk + 1) / 2) * 16 * wide::BLK_PS * sizeof(double) + (size_t)C * sizeof(wide::cdw) + (size_t)(C + 16) * sizeof(double);
+      if ((e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb)) != cudaSuccess) return e;
+      wide::k_mvdr_solve_wide_blk<<<U * K, wide::BLK_THREADS, smb, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, list);
+    } else {
+      const size_t smc = sizeof(wide::cdw) * (size_t)wide::CHOL_WARPS * ((size_t)C * (C + 1) / 2 + C);
+      if ((e = cudaFuncSetAttribute(wide::k_mvdr_solve_wide_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc)) != cudaSuccess) return e;
+      wide::k_mvdr_solve_wide_chol<<<(U * K + wide::CHOL_WARPS - 1) / wide::CHOL_WARPS, 32 * wide::CHOL_WARPS, smc, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, list);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    lu<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, todo);
+    const int grid = std::min(U * K, 148 * 3);   // three 66 KB CTAs per SM: the whole list in flight at the LU's own occupancy
+    wide::k_mvdr_solve_wide<<<grid, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, list);
     return cudaGetLastError();
   }
-  lu<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, nullptr);
+  wide::k_mvdr_solve_wide<<<U * K, wide::SOLVE_Q * C, smem, st>>>(R, D, W, noise_count, U, C, K, Gp, mu, normalize_by_count, nullptr);
   return cudaGetLastError();
 }
 

@@ -443,15 +443,18 @@ def test_streamed_16_bit_pcm_chunks_equal_the_float_chunks(capi, protos):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.abs(outs[0][1]).max() > 0
 
 
-@pytest.mark.parametrize("chol,ip", [("0", "0"), ("1", "0"), ("0", "1"), ("2", "0")])
+@pytest.mark.parametrize("chol,ip", [("", ""), ("0", "0"), ("1", "0"), ("0", "1"), ("2", "0")])
 @pytest.mark.parametrize("C", [16, 64])
 def test_wide_mvdr_solve_cholesky_and_lu_fallback(capi, protos, C, chol, ip, monkeypatch):
     """The wide MVDR solve (C > 8): Hermitian positive-definite matrices go through the warp-per-chain Cholesky kernel, everything else
     (here: a general complex matrix, and an indefinite Hermitian one) is flagged and solved by the pivoted LU; both against
     calc_mvdr_weights in fp64 (beamformer.cc:2350-2402)."""
     from oracle import restate
-    monkeypatch.setenv("BTKB_SOLVE_CHOL", chol)      # 1 / 2: warp-per-chain / blocked tensor-core Cholesky + LU for the flagged chains; 0: LU for all
-    monkeypatch.setenv("BTKB_SOLVE_IP", ip)          # 1: the LU with implicit pivoting (one barrier per column); 0 (default): row swaps
+    if chol == "":                                    # default: the solver is picked per call (user-supplied matrices: blocked Cholesky + LU for the rest)
+        monkeypatch.delenv("BTKB_SOLVE_CHOL", raising=False); monkeypatch.delenv("BTKB_SOLVE_IP", raising=False)
+    else:
+        monkeypatch.setenv("BTKB_SOLVE_CHOL", chol)  # 1 / 2: warp-per-chain / blocked tensor-core Cholesky + LU for the flagged chains; 0: LU for all
+        monkeypatch.setenv("BTKB_SOLVE_IP", ip)      # 1: the LU with implicit pivoting (one barrier per column); 0: row swaps
     M, K = 256, 129
     rng = np.random.default_rng(C)
     d = np.cumsum(rng.uniform(0, 3e-5, C))[None]

@@ -20,7 +20,8 @@ for name, labels in (("all frames (label never fires)", np.tile(np.array([[100.0
     print(json.dumps({"cov64 " + name: dict(tc=os.environ.get("BTKB_COV_TC", "1"), ms=1e3 * s, hbm_frac_read_X_plus_write_R=(xbytes + rbytes) / s / 1e9 / 6530.3,
                                             tflops_complex_gram=8.0 * C * C * K * U * T / s / 1e12)}))
 s = timed(lambda: (p.calc_mvdr_weights(1e-4), p.synchronize()), steps=3, warm=1)
-print(json.dumps({"mvdr solve 64 x 64, 65 792 matrices, covariance of 62 noise frames + 1e-4 (numerically not positive definite: pivoted LU for all)": dict(ms=1e3 * s)}))
+solver = os.environ.get("BTKB_SOLVE_CHOL", "auto")
+print(json.dumps({"mvdr solve 64 x 64, 65 792 matrices, covariance of 62 noise frames + 1e-4 (rank deficient, numerically not positive definite)": dict(ms=1e3 * s, BTKB_SOLVE_CHOL=solver)}))
 p.accumulate_covariance(np.tile(np.array([[100.0, 200.0]]), (U, 1)), 10.0)
 s = timed(lambda: (p.calc_mvdr_weights(1e-4), p.synchronize()), steps=3, warm=1)
-print(json.dumps({"mvdr solve 64 x 64, 65 792 matrices, covariance of all 317 frames + 1e-4 (positive definite: warp-per-chain Cholesky)": dict(ms=1e3 * s, chol=os.environ.get("BTKB_SOLVE_CHOL", "1"))}))
+print(json.dumps({"mvdr solve 64 x 64, 65 792 matrices, covariance of all 317 frames + 1e-4 (positive definite)": dict(ms=1e3 * s, BTKB_SOLVE_CHOL=solver)}))
