@@ -230,12 +230,10 @@ __global__ void k_mvdr_solve(const float2* R, const float2* Dm, float2* W, const
       A[j][i] = cdconj(rij);
     }
   for (int c = 0; c < C; c++) { float2 t = Dm[(size_t)c * Gp + g]; d[c] = cdmake(t.x, t.y); b[c] = d[c]; }
-  // pseudoinverse(R, invR, dThreshold) reports failure when a singular value is below dThreshold and the caller then uses the
-  // identity (beamformer.cc:267-274, 2381-2383): same rule here, on the smallest singular value of the loaded matrix
+  // LU with partial pivoting, in place (multipliers below the diagonal, rows physically swapped, perm[r] = original row now at r)
+  int perm[C];
+  for (int i = 0; i < C; i++) perm[i] = i;
   bool singular = false;
-  if (dthreshold > 0.f && min_singular_value(&A[0][0], C) < (double)dthreshold) singular = true;
-  // LU with partial pivoting, in place; solve A t = d
-  if (!singular)
   for (int col = 0; col < C; col++) {
     int piv = col; double best = cdabs2(A[col][col]);
     for (int r = col + 1; r < C; r++) { double v = cdabs2(A[r][col]); if (v > best) { best = v; piv = r; } }
@@ -243,11 +241,48 @@ __global__ void k_mvdr_solve(const float2* R, const float2* Dm, float2* W, const
     if (piv != col) {
       for (int j = 0; j < C; j++) { cd t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
       cd t = b[col]; b[col] = b[piv]; b[piv] = t;
+      const int pi = perm[col]; perm[col] = perm[piv]; perm[piv] = pi;
     }
     for (int r = col + 1; r < C; r++) {
       cd f = cddiv(A[r][col], A[col][col]);
       for (int j = col + 1; j < C; j++) A[r][j] = cdsub(A[r][j], cdmul(f, A[col][j]));
       b[r] = cdsub(b[r], cdmul(f, b[col]));
+      A[r][col] = f;
+    }
+  }
+  // pseudoinverse(R, invR, dThreshold) reports failure when a singular value is below dThreshold and the caller then uses the
+  // identity (beamformer.cc:267-274, 2381-2383): same rule here, on the smallest singular value of the loaded matrix.  The exact value
+  // (Jacobi, btkb_jacobi.cuh) is needed only when the threshold lies inside the bracket the LU factors give for free,
+  //     1 / ||A^-1||_F  <=  sigma_min  <=  sqrt(C) / ||A^-1||_F
+  // (C extra pairs of triangular solves; the Jacobi of every chain made configs[2] ten times slower than round 1: 55 ms against 5.7).
+  if (!singular && dthreshold > 0.f) {
+    double inv_f2 = 0.0;
+    for (int i = 0; i < C; i++) {
+      cd y[C];
+      for (int r = 0; r < C; r++) y[r] = cdmake(perm[r] == i ? 1.0 : 0.0, 0.0);
+      for (int col = 0; col < C; col++)
+        for (int r = col + 1; r < C; r++) y[r] = cdsub(y[r], cdmul(A[r][col], y[col]));
+      for (int r = C - 1; r >= 0; r--) {
+        cd sacc = y[r];
+        for (int j = r + 1; j < C; j++) sacc = cdsub(sacc, cdmul(A[r][j], y[j]));
+        y[r] = cddiv(sacc, A[r][r]);
+        inv_f2 += cdabs2(y[r]);
+      }
+    }
+    const double thr = (double)dthreshold;
+    const double lo = (inv_f2 > 0.0) ? 1.0 / sqrt(inv_f2) : 0.0;      // NaN / inf from a numerically singular U land in the exact test too
+    const double hi = sqrt((double)C) * lo;
+    if (hi < thr) singular = true;
+    else if (!(lo >= thr)) {
+      cd Ao[C][C];
+      for (int i = 0; i < C; i++)
+        for (int j = 0; j < C; j++) {
+          float2 t = R[(size_t)(i * C + j) * Gp + g];
+          cd rij = cdmake((double)t.x * scale, (double)t.y * scale);
+          if (i == j) rij.x += (double)mu;
+          Ao[j][i] = cdconj(rij);
+        }
+      singular = min_singular_value(&Ao[0][0], C) < thr;
     }
   }
   cd tvec[C];
