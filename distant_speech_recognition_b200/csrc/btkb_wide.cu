@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ int s_ok, s_herm;   // pivots positive so far / matrix Hermitian (two flags: each is written in one phase and read after the barrier that ends it)
   __shared__ double s_lam[2][BLK_THREADS / 32];
+  __shared__ unsigned char s_tri[120][2];   // (row, column) of the e-th entry of a 15 x 15 lower triangle: the pairs of the rank-one updates
   const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NB = C >> 4, plane = NB * (NB + 1) / 2 * 16 * BLK_PS;
   double* Mre = reinterpret_cast<double*>(sm);
@@ -583,12 +584,17 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
   const int u = g / K, k = g - u * K;
   if (tid == 0) { s_ok = 1; s_herm = 1; }
   if (k == 0) { for (int c = tid; c < C; c += BLK_THREADS) W[(size_t)c * Gp + g] = make_float2(1.f, 0.f); return; }
+  if (tid < 120) {
+    int rr = 0;
+    while ((rr + 1) * (rr + 2) / 2 <= tid) rr++;
+    s_tri[tid][0] = (unsigned char)rr; s_tri[tid][1] = (unsigned char)(tid - rr * (rr + 1) / 2);
+  }
   double scale = 1.0;
   if (normalize && noise_count != nullptr && noise_count[u] > 0) scale = 1.0 / (double)noise_count[u];
   for (int c = tid; c < C; c += BLK_THREADS) {
     dg[c] = (double)R[(size_t)(c * C + c) * Gp + g].x;
     const float2 t = Dm[(size_t)c * Gp + g];
-    bv[c] = cw(t.x, t.y);
+    bv[c] = cw(t.x, -t.y);   // the right-hand side rides along as the row vector a = d^H (x L^H = a  <=>  x = (L^-1 d)^H): forward solve for free
   }
   __syncthreads();
   // ---- load the Hermitian part of the lower triangle (+ mu on the diagonal); four pairs of loads in flight per thread
@@ -616,44 +622,46 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
   __syncthreads();
   if (!s_herm) { if (tid == 0) list[1 + atomicAdd(list, 1)] = g; return; }   // left to the pivoted LU
 
-  // ---- blocked right-looking Cholesky
+  // ---- blocked right-looking Cholesky.  Per panel: [diagonal block, one warp] -> TRSM of the rows below (and of the right-hand-side row)
+  // -> trailing update.  From the second panel on the diagonal block is factored AHEAD: warp 0 takes it out of the trailing update of the
+  // previous panel first and factors it while warps 1 .. 3 update the other blocks and the right-hand-side row.
+  auto factor_diag = [&](int j0) {   // warp 0, all 32 lanes
+    for (int jj = 0; jj < 16; jj++) {
+      const double dj = Mre[blk_idx(j0 + jj, j0 + jj)];
+      if (!(dj > 0.0)) s_ok = 0;
+      const double inv = rsqrt(fmax(dj, 1e-300));
+      __syncwarp();   // every lane has read the pivot before its owner overwrites it
+      if (lane >= jj && lane < 16) {
+        if (lane == jj) { st(j0 + lane, j0 + jj, cw(dj * inv, 0.0)); dinv[jj] = inv; }
+        else { const cdw v = ld(j0 + lane, j0 + jj); st(j0 + lane, j0 + jj, cw(v.x * inv, v.y * inv)); }
+      }
+      __syncwarp();
+      const int m = 15 - jj;
+      for (int e = lane; e < m * (m + 1) / 2; e += 32) {
+        const int r = j0 + jj + 1 + s_tri[e][0], kk = j0 + jj + 1 + s_tri[e][1];
+        const cdw lr_ = ld(r, j0 + jj), lk = ld(kk, j0 + jj);
+        cdw v = ld(r, kk);
+        v.x = fma(-lr_.x, lk.x, fma(-lr_.y, lk.y, v.x)); v.y = fma(-lr_.y, lk.x, fma(lr_.x, lk.y, v.y));   // v -= l_r conj(l_k)
+        if (kk == r) v.y = 0.0;
+        st(r, kk, v);
+      }
+      __syncwarp();
+    }
+  };
+  if (warp == 0) factor_diag(0);
+  __syncthreads();
   for (int p = 0; p < NB; p++) {
     const int j0 = 16 * p;
-    if (warp == 0) {
-      for (int jj = 0; jj < 16; jj++) {
-        const double dj = Mre[blk_idx(j0 + jj, j0 + jj)];
-        if (!(dj > 0.0)) s_ok = 0;
-        const double inv = rsqrt(fmax(dj, 1e-300));
-        __syncwarp();   // every lane has read the pivot before its owner overwrites it
-        if (lane >= jj && lane < 16) {
-          if (lane == jj) { st(j0 + lane, j0 + jj, cw(dj * inv, 0.0)); dinv[jj] = inv; }
-          else { const cdw v = ld(j0 + lane, j0 + jj); st(j0 + lane, j0 + jj, cw(v.x * inv, v.y * inv)); }
-        }
-        __syncwarp();
-        const int m = 15 - jj;
-        for (int e = lane; e < m * (m + 1) / 2; e += 32) {
-          int rr = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-          while ((rr + 1) * (rr + 2) / 2 <= e) rr++;
-          while (rr * (rr + 1) / 2 > e) rr--;
-          const int r = j0 + jj + 1 + rr, kk = j0 + jj + 1 + (e - rr * (rr + 1) / 2);
-          const cdw lr_ = ld(r, j0 + jj), lk = ld(kk, j0 + jj);
-          cdw v = ld(r, kk);
-          v.x = fma(-lr_.x, lk.x, fma(-lr_.y, lk.y, v.x)); v.y = fma(-lr_.y, lk.x, fma(lr_.x, lk.y, v.y));   // v -= l_r conj(l_k)
-          if (kk == r) v.y = 0.0;
-          st(r, kk, v);
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    if (!s_ok) { if (tid == 0) list[1 + atomicAdd(list, 1)] = g; return; }   // left to the pivoted LU
-    // L21 = A21 L11^-H: one thread per row below the block, the row's 16 entries in registers, right-looking
+    if (!s_ok) { if (tid == 0) list[1 + atomicAdd(list, 1)] = g; return; }   // left to the pivoted LU (uniform: s_ok was last written before a barrier)
+    // L21 = A21 L11^-H: one thread per row below the block, the row's 16 entries in registers, right-looking; the thread after the
+    // last row does the same for the right-hand-side row (x_p = a_p L11^-H)
     {
       const int r = j0 + 16 + tid;
-      if (r < C) {
+      if (r <= C) {
+        const bool rhs = r == C;
         cdw v[16];
 #pragma unroll
-        for (int jj = 0; jj < 16; jj++) v[jj] = ld(r, j0 + jj);
+        for (int jj = 0; jj < 16; jj++) v[jj] = rhs ? bv[j0 + jj] : ld(r, j0 + jj);
 #pragma unroll
         for (int jj = 0; jj < 16; jj++) {
           const double inv = dinv[jj];
@@ -665,15 +673,17 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
               v[q].x = fma(-v[jj].x, l.x, fma(-v[jj].y, l.y, v[q].x)); v[q].y = fma(-v[jj].y, l.x, fma(v[jj].x, l.y, v[q].y));   // v_q -= x_jj conj(L[q][jj])
             }
           }
-          st(r, j0 + jj, v[jj]);
+          if (rhs) bv[j0 + jj] = v[jj]; else st(r, j0 + jj, v[jj]);
         }
       }
     }
     __syncthreads();
-    // A22 -= L21 L21^H on 16 x 16 blocks (bi >= bk > p), one block per warp and turn
+    // A22 -= L21 L21^H on 16 x 16 blocks (bi >= bk > p).  Block 0 = the next diagonal block: warp 0 updates it and factors it right away;
+    // the other blocks go round warps 1 .. 3, which also take the right-hand-side row: a_c -= sum_jj x_p[jj] conj(L[c][j0 + jj]), c >= j0 + 16
     {
       const int nt = NB - 1 - p, lr = lane >> 2, lc = lane & 3;
-      for (int bp = warp; bp < nt * (nt + 1) / 2; bp += BLK_THREADS / 32) {
+      const int npair = nt * (nt + 1) / 2;
+      for (int bp = (warp == 0) ? 0 : warp; bp < npair; bp += (warp == 0) ? npair : BLK_THREADS / 32 - 1) {
         int bi = 0;
         while ((bi + 1) * (bi + 2) / 2 <= bp) bi++;
         const int bk = bp - bi * (bi + 1) / 2;
@@ -714,37 +724,22 @@ __global__ void __launch_bounds__(BLK_THREADS, 4) k_mvdr_solve_wide_blk(const fl
               }
             }
       }
-    }
-    __syncthreads();
-  }
-
-  // ---- L y = d, panel by panel: the 16 x 16 triangular solve in one warp (lane q holds y_q; the finished entries travel by shuffle), then
-  // every row below takes its update
-  for (int p = 0; p < NB; p++) {
-    const int j0 = 16 * p;
-    if (warp == 0) {
-      const int q = lane & 15;
-      cdw y = (lane < 16) ? bv[j0 + q] : cw(0.0, 0.0);   // lanes 16 .. 31 only keep the shuffles full-warp
-      const double invq = 1.0 / Mre[blk_idx(j0 + q, j0 + q)];
-      for (int jj = 0; jj < 16; jj++) {
-        const cdw gj = cw(__shfl_sync(0xffffffffu, y.x * invq, jj), __shfl_sync(0xffffffffu, y.y * invq, jj));
-        if (q == jj) y = gj;
-        else if (q > jj) y = cwmsub(y, ld(j0 + q, j0 + jj), gj);
-      }
-      if (lane < 16) bv[j0 + q] = y;
-    }
-    __syncthreads();
-    {
-      const int r = j0 + 16 + tid;
-      if (r < C) {
-        cdw s = bv[r];
+      if (warp == 0) { if (nt > 0) { __syncwarp(); factor_diag(j0 + 16); } }
+      else {
+        for (int c = j0 + 16 + (tid - 32); c < C; c += BLK_THREADS - 32) {
+          cdw acc = bv[c];
 #pragma unroll
-        for (int jj = 0; jj < 16; jj++) s = cwmsub(s, ld(r, j0 + jj), bv[j0 + jj]);
-        bv[r] = s;
+          for (int jj = 0; jj < 16; jj++) { const cdw l = ld(c, j0 + jj); acc = cwmsub(acc, bv[j0 + jj], cw(l.x, -l.y)); }   // a_c -= x_jj conj(L[c][j0 + jj])
+          bv[c] = acc;
+        }
       }
     }
     __syncthreads();
   }
+  // y = L^-1 d = conj(x)
+  for (int c = tid; c < C; c += BLK_THREADS) bv[c].y = -bv[c].y;
+  __syncthreads();
+
   // ---- L^H t = y, last panel first
   for (int p = NB - 1; p >= 0; p--) {
     const int j0 = 16 * p;
