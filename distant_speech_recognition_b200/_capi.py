@@ -197,6 +197,13 @@ class Pipeline:
         _check(lib.btkb_last_timing_wpe(self._h, ct.byref(ms)))
         return float(ms.value)
 
+    def set_snapshots(self, X):
+        """X complex64 [U][T][C][K]: snapshots computed elsewhere take the place of the analysis output."""
+        X = np.ascontiguousarray(X, np.complex64)
+        assert X.ndim == 4 and X.shape[2] == self.C and X.shape[3] == self.K
+        self.U = X.shape[0]
+        _check(lib.btkb_set_snapshots(self._h, ct.c_int(X.shape[0]), ct.c_int(X.shape[1]), _fp(X)))
+
     def upgrade_blocking_matrix(self):
         """SubbandMVDRGSC::upgrade_blocking_matrix (beamformer.cc:2674-2691)."""
         _check(lib.btkb_upgrade_blocking_matrix(self._h))

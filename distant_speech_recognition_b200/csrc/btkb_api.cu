@@ -1021,6 +1021,30 @@ int btkb_set_subband(btkb_pipeline* p, int U, int T, const float* Y) {
   return BTKB_OK;
 }
 
+int btkb_set_snapshots(btkb_pipeline* p, int U, int T, const float* X) {
+  if (!p || !X) return fail(BTKB_ERR_INVALID, "btkb_set_snapshots: null argument");
+  if (U < 1 || U > p->Ucap || T < 0 || T > p->Tcap) return fail(BTKB_ERR_INVALID, "btkb_set_snapshots: U or T exceeds the pipeline capacity");
+  if (p->cfg.wpe.enabled) return fail(BTKB_ERR_INVALID, "btkb_set_snapshots: not offered for a pipeline with cfg.wpe.enabled");
+  CK(cudaSetDevice(p->cfg.device));
+  const int nblk = T - p->pdA + p->laN;   // a length that yields exactly T frames: T = ceil(len/D) - laN + pdA
+  if (nblk < 0) return fail(BTKB_ERR_INVALID, "btkb_set_snapshots: T is shorter than the filter-bank delay");
+  if (p->wU != 0 && p->wU != U) { p->have_w = p->have_wl = p->have_ta = p->have_R = false; p->R_is_sum = false; p->NC = 1; p->wU = 0; }
+  p->U = U; p->n = nblk * p->D; p->lengths.assign(U, nblk * p->D);
+  p->T = T; p->nb = std::max(T - p->pdS, 0); p->Gp = round_up(U * p->K, 128);
+  p->streaming = false; p->Y_out = p->d_Y;
+  CK(cudaMemcpyAsync(p->d_len, p->lengths.data(), U * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+  std::vector<float2> tmp((size_t)T * p->Cp * p->Gp, make_float2(0.f, 0.f));
+  for (int u = 0; u < U; u++)
+    for (int t = 0; t < T; t++)
+      for (int c = 0; c < p->C; c++)
+        memcpy(&tmp[((size_t)t * p->Cp + c) * p->Gp + (size_t)u * p->K], X + 2 * ((((size_t)u * T + t) * p->C + c) * p->K), sizeof(float2) * p->K);
+  CK(cudaMemcpyAsync(p->d_X, tmp.data(), tmp.size() * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemsetAsync(p->d_E, 0, (size_t)std::max(T, 1) * U * sizeof(float), p->stream));   // channel-0 frame energy: not known for foreign snapshots
+  CK(cudaStreamSynchronize(p->stream));
+  p->have_X = true; p->have_Y = false; p->have_time = false; p->have_ua = false; p->pf_applied = false;
+  return BTKB_OK;
+}
+
 int btkb_run_synthesis(btkb_pipeline* p) {
   if (!p) return fail(BTKB_ERR_INVALID, "null pipeline");
   CK(cudaSetDevice(p->cfg.device));

@@ -916,9 +916,65 @@ ZelinskiPostFilter::ZelinskiPostFilter(const VectorComplexFeatureStreamPtr& outp
   if (output->size() != fftLen) throw jdimension_error("Input block length (%d) != fftLen (%d)\n", output->size(), fftLen);  // postfilter.cc:366-368
   bf_ = std::dynamic_pointer_cast<SubbandDS>(output);
 }
-void ZelinskiPostFilter::reset() { samp_->reset(); if (bf_) bf_->reset(); VectorComplexFeatureStream::reset(); is_end_ = false; }
+void ZelinskiPostFilter::reset() { samp_->reset(); if (bf_) bf_->reset(); VectorComplexFeatureStream::reset(); is_end_ = false; foreign_ready_ = false; }
+ZelinskiPostFilter::~ZelinskiPostFilter() { if (fpipe_) btkb_destroy(fpipe_); }
+void ZelinskiPostFilter::set_array_manifold_vector(unsigned fbinX, const std::vector<cplx>& v, bool half_band_shift, unsigned NC) {   // postfilter.cc:393-417
+  if (fbinX >= fftLen_) throw jdimension_error("fbinX %d must be less than %d\n", (int)fbinX, (int)fftLen_);
+  if (half_band_shift) throw j_error("halfBandShift is not implemented\n");
+  if (NC != 1) throw j_error("set_array_manifold_vector: one constraint only\n");
+  const unsigned K = fftLen_ / 2 + 1;
+  if (manifold_C_ != v.size()) { manifold_C_ = (unsigned)v.size(); manifold_.assign((size_t)K * manifold_C_, std::complex<float>(0, 0)); }
+  if (fbinX < K) for (unsigned c = 0; c < manifold_C_; c++) manifold_[(size_t)fbinX * manifold_C_ + c] = std::complex<float>((float)v[c].real(), (float)v[c].imag());
+  foreign_ready_ = false;
+}
+void ZelinskiPostFilter::realize_foreign_() {
+  const unsigned K = fftLen_ / 2 + 1, C = manifold_C_;
+  if (C != snap_foreign_->nChan() || fftLen_ != snap_foreign_->fftLen()) throw jdimension_error("snapshot array (%d channels) and manifold vectors (%d) do not match\n", (int)snap_foreign_->nChan(), (int)C);
+  if (config().kind != BTKB_PF_ZELINSKI) throw j_error("set_snapshot_array: offered for the Zelinski filter (McCowan / Lefkimmiatis take set_beamformer)\n");
+  // drain the foreign output; whoever produces it updates the shared snapshot array as a side effect of its own next()
+  std::vector<std::complex<float>> X;
+  fout_.clear(); fT_ = 0;
+  for (int t = 0;; t++) {
+    const cplx* f;
+    try { f = samp_->next(t); } catch (jiterator_error&) { break; }
+    fout_.insert(fout_.end(), f, f + fftLen_);
+    X.resize((size_t)(t + 1) * C * K);
+    for (unsigned c = 0; c < C; c++)
+      for (unsigned k = 0; k < K; k++) { const cplx v = snap_foreign_->snapshot(k)[c]; X[((size_t)t * C + c) * K + k] = std::complex<float>((float)v.real(), (float)v.imag()); }
+    fT_ = t + 1;
+  }
+  fgain_.assign((size_t)fT_ * K, 1.f);
+  if (fT_ > 0) {
+    if (fpipe_) { btkb_destroy(fpipe_); fpipe_ = nullptr; }
+    btkb_config c; btkb_default_config(&c);
+    c.channels = (int)C; c.fft_len = (int)fftLen_; c.m = 4; c.r = 1; c.delay_compensation_type = 2; c.max_utterances = 1;
+    c.max_samples = (fT_ + 8) * (int)(fftLen_ >> 1);
+    c.beamformer = BTKB_BF_DS; c.postfilter = BTKB_PF_ZELINSKI; c.pf_alpha = (float)alpha_; c.pf_type = type_; c.pf_min_frames = min_frames_;
+    ck(btkb_create(&c, &fpipe_));
+    ck(btkb_set_weights(fpipe_, 1, reinterpret_cast<const float*>(manifold_.data())));
+    ck(btkb_set_snapshots(fpipe_, 1, fT_, reinterpret_cast<const float*>(X.data())));
+    ck(btkb_run_beamformer(fpipe_, 0));
+    ck(btkb_get_postfilter_weights(fpipe_, fgain_.data()));
+  }
+  foreign_ready_ = true;
+}
 const cplx* ZelinskiPostFilter::next(int frame_no) {  // postfilter.cc:424-491
   if (frame_no == frame_no_) return vector_.data();
+  if (!bf_ && snap_foreign_ && manifold_C_ > 0) {
+    if (!foreign_ready_) realize_foreign_();
+    if (frame_no_ + 1 >= fT_) { is_end_ = true; throw jiterator_error("end of samples!"); }
+    increment_();
+    const unsigned K = fftLen_ / 2 + 1;
+    const cplx* y = &fout_[(size_t)frame_no_ * fftLen_];
+    for (unsigned k = 0; k < fftLen_; k++) vector_[k] = y[k];
+    // the reference tests frame_no_ < min_frames_ BEFORE it increments (postfilter.cc:470-475): frames 0 .. min_frames only update the
+    // statistics (NO_USE_POST_FILTER returns before the filtering loop, :196-198) and the output passes as it came
+    if (frame_no_ > min_frames_) {
+      for (unsigned k = 0; k < K; k++) vector_[k] = y[k] * (double)fgain_[(size_t)frame_no_ * K + k];   // ZelinskiFilter: vector_ <- wp1 * output (postfilter.cc:57-219)
+      for (unsigned k = 1; k < fftLen_ / 2; k++) vector_[fftLen_ - k] = std::conj(vector_[k]);
+    }
+    return vector_.data();
+  }
   if (!bf_) throw j_error("set beamformer's weights \n");  // postfilter.cc:443-445
   const PostFilterConfig pf = config();
   if (!bf_->realized_with(pf, SynthesisConfig())) bf_->run_graph(pf, SynthesisConfig());

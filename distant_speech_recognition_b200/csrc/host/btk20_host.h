@@ -524,6 +524,13 @@ class ZelinskiPostFilter : public VectorComplexFeatureStream {
   const cplx* next(int frame_no = -5) override;
   void reset() override;
   void set_beamformer(const SubbandDSPtr& bf) { bf_ = bf; }
+  // postfilter.cc:384-417: the wiring WITHOUT a beamformer object — the snapshots of a foreign stream and one time-alignment vector per bin
+  // (wq for the TYPE_ZELINSKI2 variants, the array manifold otherwise: both are "the vector the filter aligns the channels with").
+  // The mirror drains the output stream at the first next(), copying the shared snapshot array after every frame, runs the filter
+  // statistics on the GPU (btkb_set_snapshots + the Zelinski epilogue of the per-bin kernel) and multiplies the foreign output by the gains.
+  void set_snapshot_array(const SnapShotArrayPtr& snap) { snap_foreign_ = snap; foreign_ready_ = false; }
+  void set_array_manifold_vector(unsigned fbinX, const std::vector<cplx>& v, bool half_band_shift = false, unsigned NC = 1);
+  ~ZelinskiPostFilter();
   std::vector<cplx> postfilter_weights();
   const SubbandDSPtr& beamformer() const { return bf_; }
   virtual PostFilterConfig config() const { PostFilterConfig c; c.enabled = true; c.alpha = alpha_; c.type = type_; c.min_frames = min_frames_; return c; }
@@ -532,6 +539,10 @@ class ZelinskiPostFilter : public VectorComplexFeatureStream {
   virtual int onesided_frames_() const { return 0; }  // frames whose upper half-spectrum the reference leaves untouched
   unsigned fftLen_; VectorComplexFeatureStreamPtr samp_; double alpha_; int type_, min_frames_;
   SubbandDSPtr bf_;
+  // foreign-stream wiring
+  SnapShotArrayPtr snap_foreign_; std::vector<std::complex<float>> manifold_; unsigned manifold_C_ = 0; bool foreign_ready_ = false;
+  btkb_pipeline* fpipe_ = nullptr; std::vector<cplx> fout_; std::vector<float> fgain_; int fT_ = 0;
+  void realize_foreign_();
 };
 typedef std::shared_ptr<ZelinskiPostFilter> ZelinskiPostFilterPtr;
 

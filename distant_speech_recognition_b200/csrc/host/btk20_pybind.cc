@@ -360,6 +360,10 @@ PYBIND11_MODULE(_btk20host, m) {
       .def(py::init<const VectorComplexFeatureStreamPtr&, unsigned, double, int, int, const std::string&>(), py::arg("output"), py::arg("M"), py::arg("alpha") = 0.6,
            py::arg("type") = 2, py::arg("min_frames") = 0, py::arg("nm") = "ZelinskPostFilter")
       .def("set_beamformer", &ZelinskiPostFilter::set_beamformer, py::arg("beamformer"))
+      .def("set_snapshot_array", &ZelinskiPostFilter::set_snapshot_array, py::arg("snapShotArray"))
+      .def("set_array_manifold_vector", [](ZelinskiPostFilter& s, unsigned fbinX, py::array_t<std::complex<double>, py::array::c_style | py::array::forcecast> v, bool hbs, unsigned NC) {
+             s.set_array_manifold_vector(fbinX, std::vector<cplx>(v.data(), v.data() + v.size()), hbs, NC); },
+           py::arg("fbinX"), py::arg("arrayManifoldVector"), py::arg("halfBandShift") = false, py::arg("NC") = 1)
       .def("postfilter_weights", &ZelinskiPostFilter::postfilter_weights);
 
   py::class_<McCowanPostFilter, ZelinskiPostFilter, McCowanPostFilterPtr>(m, "McCowanPostFilterPtr")

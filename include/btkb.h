@@ -205,6 +205,10 @@ int btkb_run_beamformer(btkb_pipeline* p, int do_synthesis);
  * btkb_run_synthesis resynthesises them.  lengths are taken from T: every utterance is treated as T frames long. */
 int btkb_set_subband(btkb_pipeline* p, int U, int T, const float* Y);
 int btkb_run_synthesis(btkb_pipeline* p);
+/* snapshots computed elsewhere, X [U][T][C][K] complex64, take the place of the analysis output (the per-bin kernels, the covariance pass
+ * and the post-filters then run on them; the frame energies the NLMS / SOS gates read are zero).  What a ZelinskiPostFilter wired with
+ * set_snapshot_array / set_array_manifold_vector instead of set_beamformer needs (postfilter/postfilter.cc:384-417, 424-491). */
+int btkb_set_snapshots(btkb_pipeline* p, int U, int T, const float* X);
 /* whole pipe: analysis -> beamformer (+post-filter) -> synthesis */
 int btkb_run(btkb_pipeline* p, int do_synthesis);
 int btkb_synchronize(btkb_pipeline* p);

@@ -769,3 +769,49 @@ def test_synthesis_bank_input_source_vector(protos):
     assert got.shape == want.shape and rel_l2(got, want) < TOL
     with pytest.raises(Exception):
         OverSampledDFTSynthesisBankPtr(PyVectorComplexFeatureStreamPtr(Src()), prototype=gproto, M=M, m=m, r=1, delay_compensation_type=2).input_source_vector(full[0])
+
+
+@pytest.mark.gpu
+def test_zelinski_postfilter_on_a_foreign_stream(protos):
+    """ZelinskiPostFilter wired WITHOUT a beamformer object: set_snapshot_array + set_array_manifold_vector per bin
+    (postfilter/postfilter.cc:384-417), the output stream being any beamformer that shares the snapshot array.  Here: a Python stream
+    that applies its own (non delay-and-sum) weights and updates the shared SnapShotArrayPtr frame by frame.  Expected: the filter gains
+    from the snapshots and the manifold, times THAT stream's output (ZelinskiFilter, postfilter.cc:57-219); also C-ABI level:
+    btkb_set_snapshots."""
+    from oracle import restate
+    from distant_speech_recognition_b200.btk20.beamformer import SnapShotArrayPtr
+    from distant_speech_recognition_b200.btk20.postfilter import ZelinskiPostFilterPtr
+    from distant_speech_recognition_b200.btk20.stream import PyVectorComplexFeatureStreamPtr
+    g = load_golden("mvdrsd_zelinski1_c4_m256"); h, _ = protos[256]; M, C, K = 256, 4, 129
+    X = np.stack([restate.analysis(g["x"][c], h, M, 4, 1) for c in range(C)], axis=1)[:40]          # [T][C][M]
+    T = X.shape[0]
+    rng = np.random.default_rng(21)
+    wf = np.zeros((M, C), complex)
+    wf[:K] = (rng.standard_normal((K, C)) + 1j * rng.standard_normal((K, C))) / C
+    Yf = restate.subband_ds(X, wf)                                                                   # the foreign beamformer's output
+    wq = restate.calc_mainlobe(M, C, FS, g["delays"])
+    snap = SnapShotArrayPtr(M, C)
+
+    class Foreign:
+        def size(self):
+            return M
+        def __iter__(self):
+            for t in range(T):
+                for c in range(C):
+                    snap.set_samples(X[t, c], c)
+                snap.update()
+                yield Yf[t]
+        def reset(self):
+            pass
+    for alpha, pf_type, min_frames in ((0.6, 2, 0), (0.7, 1, 3)):
+        pf = ZelinskiPostFilterPtr(PyVectorComplexFeatureStreamPtr(Foreign()), M, alpha, pf_type, min_frames)
+        pf.set_snapshot_array(snap)
+        for k in range(M):
+            pf.set_array_manifold_vector(k, wq[k], False, 1)
+        out = np.array([np.array(v) for v in pf])
+        want, gains = restate.zelinski_postfilter(Yf, X, wq, alpha, pf_type, min_frames)
+        assert out.shape == want.shape and rel_l2(out[:, :K], want[:, :K]) < TOL, (alpha, pf_type)
+        assert rel_l2(out[min_frames + 1:, K:], want[min_frames + 1:, K:]) < TOL
+        assert rel_l2(want[:, :K], Yf[:, :K]) > 1e-2                                                 # the filter does something
+    with pytest.raises(Exception):                                                                   # neither wiring: "set beamformer's weights"
+        next(iter(ZelinskiPostFilterPtr(PyVectorComplexFeatureStreamPtr(Foreign()), M, 0.6, 2, 0)))
